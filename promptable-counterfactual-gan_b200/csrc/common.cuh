@@ -1,0 +1,77 @@
+// Shared host/device helpers for libpcg.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace pcg {
+
+// ---- error plumbing: internal code throws, the extern "C" layer converts to codes --------------
+void set_last_error(const std::string& msg);
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PCG_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      throw ::pcg::Error(2, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +       \
+                                __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+    }                                                                                         \
+  } while (0)
+
+#define PCG_REQUIRE(cond, msg)                                                                \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      throw ::pcg::Error(1, std::string("invalid argument: ") + (msg) + " [" #cond "] (" +    \
+                                __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+    }                                                                                         \
+  } while (0)
+
+#define PCG_LAUNCH_CHECK() PCG_CHECK_CUDA(cudaGetLastError())
+
+// Number of SMs of the current device (cached).
+int sm_count();
+
+// Counts kernels launched by this library (bench.py's "gpu_launches").
+extern unsigned long long g_launch_count;
+#define PCG_COUNT_LAUNCH() (++::pcg::g_launch_count)
+
+// ---- storage-type conversion ---------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// Activation codes shared by every kernel.
+enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
+
+}  // namespace pcg

@@ -1,0 +1,643 @@
+// Tensor-core convolution kernels for sm_100a.
+//
+//  * conv_tc_fprop_kernel<BN>: persistent, warp-specialised implicit GEMM
+//        Y[M = N*Ho*Wo][Cout] = im2col(X)[M][taps*Cin] * W[Cout][taps*Cin]^T
+//    - A operand: NHWC bf16 activations fetched by TMA in *im2col mode* (128 pixels x 64 channels
+//      per filter tap, zero fill at the image border, 128B swizzle) -> no im2col buffer in HBM.
+//    - B operand: packed bf16 weights fetched by tiled TMA (BN rows x 64 k, 128B swizzle).
+//    - tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) issued by one thread, fp32
+//      accumulators double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1.
+//    - epilogue warps: tcgen05.ld -> +bias -> activation -> +residual -> bf16 store, plus the
+//      per-channel sum / sum-of-squares partials train-mode BatchNorm needs (reference:
+//      conditional_counteRGAN/mnist/models/generator.py:11-15,17-22).
+//  * conv_tc_wgrad64_kernel: dW = X^T * dY with K = pixels; both operands MN-major straight from
+//    the NHWC tensors (TMA im2col for the shifted X taps), two taps per M=128 MMA, five fp32
+//    accumulators resident in TMEM for the whole kernel, per-CTA partials reduced deterministically.
+//
+// Reference semantics being replaced: torch.nn.Conv2d forward / ConvolutionBackward0 as called by
+// conditional_counteRGAN/mnist/models/generator.py:11,14,49.
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+namespace pcg {
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------
+// Tensor-map creation (driver entry points resolved at run time; libcuda is not linked)
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+static void load_driver_entry_points() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+  });
+  if (!g_encode_tiled || !g_encode_im2col)
+    throw Error(3, "cuTensorMapEncodeTiled/Im2col driver entry points unavailable");
+}
+
+// [rows][cols] bf16 row-major matrix, box = box_rows x 64 columns, 128B swizzle.
+static CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  load_driver_entry_points();
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(bf16)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return m;
+}
+
+// NHWC bf16 activation, im2col mode: 128 pixels x 64 channels per box.
+static CUtensorMap make_tmap_im2col(const bf16* base, int N, int H, int W, int C, int ksize,
+                                    int stride, int pad) {
+  load_driver_entry_points();
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  // base-pixel bounding box: lower = -pad, upper = pad - (k-1)  (dilation 1), W then H.
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims,
+                               strides, lower, upper, /*channelsPerPixel=*/64,
+                               /*pixelsPerColumn=*/128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeIm2col failed: " + std::to_string(int(r)));
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// fprop / dgrad implicit GEMM
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_M = 128;
+constexpr int A_STAGE_BYTES = TILE_M * 128;       // 128 pixels x 64 bf16
+constexpr int PIPE_BYTES = 196608;                // operand ring budget
+constexpr int FPROP_THREADS = 192;                // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+
+struct FpropParams {
+  int M, Ho, Wo, stride, pad, ksize, cin_blocks, Cout;
+  int num_m_tiles, num_n_tiles;
+  const float* bias;
+  int act;
+  float slope;
+  const bf16* add_src;
+  bf16* out;
+  float* stats;
+};
+
+template <int BN>
+struct FpropCfg {
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int STATS_BYTES = 4 * 2 * BN * 4;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STATS_BYTES + 256;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Sum over the 32 lanes of a warp of 32 per-lane values; lane l ends up with column l's total.
+__device__ __forceinline__ float butterfly_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < cnt / 2; ++j) {
+      float send = upper ? v[j] : v[j + cnt / 2];
+      float keep = upper ? v[j + cnt / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(FPROP_THREADS, 1)
+conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const FpropParams p) {
+  using Cfg = FpropCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* ring = smem;
+  float* stats_smem = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STATS_BYTES);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int taps = p.ksize * p.ksize;
+  const int num_kb = taps * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int hw = p.Ho * p.Wo;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        const int p0 = m_tile * TILE_M;
+        const int n_img = p0 / hw, rem = p0 % hw;
+        const int cw = (rem % p.Wo) * p.stride - p.pad;
+        const int ch = (rem / p.Wo) * p.stride - p.pad;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.ksize, s = tap % p.ksize;
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
+            tma_load_im2col_4d(&tmA, &full[stage], sa, cb * 64, cw, ch, n_img, (uint16_t)s, (uint16_t)r);
+            tma_load_2d(&tmB, &full[stage], sa + A_STAGE_BYTES, (tap * p.cin_blocks + cb) * 64,
+                        n_tile * BN);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {     // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
+            const uint64_t da = umma_smem_desc(a_base + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(b_base + k * 32, 16, 1024);
+            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);       // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);           // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float acc_s[BN / 32], acc_q[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) acc_s[i] = acc_q[i] = 0.f;
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const long long pix = (long long)m_tile * TILE_M + row;
+      const bool valid = pix < p.M;
+#pragma unroll
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + chunk * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_tile * BN + chunk * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.act == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        } else if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.add_src != nullptr && valid) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.add_src + pix * p.Cout + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u = __ldg(src + j4);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h[e]);
+              v[j4 * 8 + e * 2] += f.x;
+              v[j4 * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u;
+            u.x = pack_bf16x2(v[j4 * 8 + 0], v[j4 * 8 + 1]);
+            u.y = pack_bf16x2(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+            u.z = pack_bf16x2(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+            u.w = pack_bf16x2(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+            dst[j4] = u;
+          }
+        }
+        if (p.stats != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = valid ? v[j] : 0.f;
+            sq[j] = v[j] * v[j];
+          }
+          acc_s[chunk] += butterfly_colsum32(v, lane);
+          acc_q[chunk] += butterfly_colsum32(sq, lane);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+
+    if (p.stats != nullptr) {
+      // stats_smem[q][2*BN]: (sum[BN], sumsq[BN]) per epilogue warp, then a fixed-order 4-way add.
+#pragma unroll
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        stats_smem[q * 2 * BN + chunk * 32 + lane] = acc_s[chunk];
+        stats_smem[q * 2 * BN + BN + chunk * 32 + lane] = acc_q[chunk];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;
+      for (int i = e; i < 2 * BN; i += 128) {
+        float t = stats_smem[i] + stats_smem[2 * BN + i] + stats_smem[4 * BN + i] + stats_smem[6 * BN + i];
+        p.stats[(size_t)blockIdx.x * 2 * BN + i] = t;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+int conv_tc_grid(long long M, int Cout) {
+  int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
+  long long tiles = ((M + TILE_M - 1) / TILE_M) * (Cout / bn);
+  int sms = sm_count();
+  return (int)(tiles < sms ? tiles : sms);
+}
+
+template <int BN>
+static void launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int grid,
+                         cudaStream_t stream) {
+  using Cfg = FpropCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fprop_kernel<BN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  conv_tc_fprop_kernel<BN><<<grid, FPROP_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk, int Cout, int ksize,
+                   int stride, int pad, const ConvEpilogue& epi, bf16* out, cudaStream_t stream) {
+  PCG_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tensor-core conv needs Cin, Cout multiples of 64");
+  PCG_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)out & 15) == 0,
+              "16-byte alignment");
+  const int Ho = (H + 2 * pad - ksize) / stride + 1;
+  const int Wo = (W + 2 * pad - ksize) / stride + 1;
+  const long long M = (long long)N * Ho * Wo;
+  const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
+  PCG_REQUIRE(epi.stats == nullptr || Cout == bn, "BN statistics need a single N tile");
+  FpropParams p;
+  p.M = (int)M; p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.pad = pad; p.ksize = ksize;
+  p.cin_blocks = Cin / 64; p.Cout = Cout;
+  p.num_m_tiles = (int)((M + TILE_M - 1) / TILE_M);
+  p.num_n_tiles = Cout / bn;
+  p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
+  p.out = out; p.stats = epi.stats;
+  CUtensorMap tmA = make_tmap_im2col(in, N, H, W, Cin, ksize, stride, pad);
+  CUtensorMap tmB = make_tmap_2d(wpk, Cout, (uint64_t)ksize * ksize * Cin, bn);
+  const int grid = conv_tc_grid(M, Cout);
+  if (bn == 256) launch_fprop<256>(tmA, tmB, p, grid, stream);
+  else if (bn == 128) launch_fprop<128>(tmA, tmB, p, grid, stream);
+  else launch_fprop<64>(tmA, tmB, p, grid, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad (Cin = Cout = 64, 3x3, stride 1, pad 1)
+// ------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;
+constexpr int WG_X_STAGE = 2 * A_STAGE_BYTES;      // two taps per stage
+constexpr int WG_STAGES = 4;
+constexpr int WG_DY_BYTES = A_STAGE_BYTES;
+constexpr int WG_TMEM_COLS = 512;                  // 5 accumulators x 64 columns, power of two
+constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_X_STAGE + 2 * WG_DY_BYTES + 256;
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       int M, int H, int W, int num_pblocks, float* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sx = smem;                                    // [WG_STAGES][2][128 px][64 ci]
+  uint8_t* sdy = smem + WG_STAGES * WG_X_STAGE;          // [2][128 px][64 co]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdy + 2 * WG_DY_BYTES);
+  uint64_t* full = bars;                 // [WG_STAGES]
+  uint64_t* empty = bars + WG_STAGES;    // [WG_STAGES]
+  uint64_t* dyfull = bars + 2 * WG_STAGES;   // [2]
+  uint64_t* dyempty = dyfull + 2;            // [2]
+  uint64_t* done = dyempty + 2;              // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&dyfull[s], 1); mbar_init(&dyempty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, WG_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, db = 0;
+      uint32_t phase = 0, dphase = 0;
+      const int hw = H * W;
+      for (int pb = blockIdx.x; pb < num_pblocks; pb += gridDim.x) {
+        const int p0 = pb * TILE_M;
+        const int n_img = p0 / hw, rem = p0 % hw;
+        const int cw = rem % W - 1, ch = rem / W - 1;
+        mbar_wait(&dyempty[db], dphase ^ 1);
+        mbar_expect_tx(&dyfull[db], WG_DY_BYTES);
+        tma_load_2d(&tmDY, &dyfull[db], sdy + db * WG_DY_BYTES, 0, p0);
+        for (int j = 0; j < 5; ++j) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], j < 4 ? WG_X_STAGE : A_STAGE_BYTES);
+          uint8_t* dst = sx + stage * WG_X_STAGE;
+          const int t0 = 2 * j;
+          tma_load_im2col_4d(&tmX, &full[stage], dst, 0, cw, ch, n_img, (uint16_t)(t0 % 3),
+                             (uint16_t)(t0 / 3));
+          if (j < 4) {
+            const int t1 = t0 + 1;
+            tma_load_im2col_4d(&tmX, &full[stage], dst + A_STAGE_BYTES, 0, cw, ch, n_img,
+                               (uint16_t)(t1 % 3), (uint16_t)(t1 / 3));
+          }
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        db ^= 1;
+        if (db == 0) dphase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // A = [X@tap(2j) | X@tap(2j+1)] : MN-major, M = 128 (two 64-channel blocks LBO apart)
+      // B = dY tile                     : MN-major, N = 64
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      int stage = 0, db = 0;
+      uint32_t phase = 0, dphase = 0;
+      bool first = true;
+      for (int pb = blockIdx.x; pb < num_pblocks; pb += gridDim.x) {
+        mbar_wait(&dyfull[db], dphase);
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(sdy + db * WG_DY_BYTES);
+        for (int j = 0; j < 5; ++j) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sx + stage * WG_X_STAGE);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {      // 8 x (K = 16 pixels = 2 swizzle atoms of 8 rows)
+            const uint64_t da = umma_smem_desc(a_base + k * 2048, A_STAGE_BYTES, 1024);
+            const uint64_t dbd = umma_smem_desc(b_base + k * 2048, A_STAGE_BYTES, 1024);
+            umma_f16(tmem_base + j * 64, da, dbd, idesc, (!first || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&dyempty[db]);
+        first = false;
+        db ^= 1;
+        if (db == 0) dphase ^= 1;
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;            // accumulator row = (tap parity, ci)
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* my = part + (size_t)blockIdx.x * 9 * 64 * 64;
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+      const int tap = 2 * j + (row >> 6);
+      const int ci = row & 63;
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + j * 64 + chunk * 32, r);
+        tmem_ld_wait();
+        if (tap < 9) {
+          float4* dst = reinterpret_cast<float4*>(my + ((size_t)tap * 64 + ci) * 64 + chunk * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            dst[j4] = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
+                                  __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, WG_TMEM_COLS);
+  }
+}
+
+int conv_tc_wgrad_grid(long long M) {
+  long long nb = (M + TILE_M - 1) / TILE_M;
+  int sms = sm_count();
+  return (int)(nb < sms ? nb : sms);
+}
+
+void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* part,
+                     cudaStream_t stream) {
+  const long long M = (long long)N * H * W;
+  CUtensorMap tmX = make_tmap_im2col(x, N, H, W, 64, 3, 1, 1);
+  CUtensorMap tmDY = make_tmap_2d(dy, (uint64_t)M, 64, 128);
+  static bool configured = false;
+  if (!configured) {
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad64_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+    configured = true;
+  }
+  const int nb = (int)((M + TILE_M - 1) / TILE_M);
+  const int grid = conv_tc_wgrad_grid(M);
+  conv_tc_wgrad64_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(tmX, tmDY, (int)M, H, W, nb, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// part[cta][tap][ci][co] -> dw[co][ci][tap]; fixed summation order (deterministic).
+__global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (tap, ci, co), co fastest
+  if (idx >= 9 * 64 * 64) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= nparts; c += 4) {
+    s0 += part[(size_t)(c + 0) * 36864 + idx];
+    s1 += part[(size_t)(c + 1) * 36864 + idx];
+    s2 += part[(size_t)(c + 2) * 36864 + idx];
+    s3 += part[(size_t)(c + 3) * 36864 + idx];
+  }
+  for (; c < nparts; ++c) s0 += part[(size_t)c * 36864 + idx];
+  const int co = idx & 63, ci = (idx >> 6) & 63, tap = idx >> 12;
+  dw[(co * 64 + ci) * 9 + tap] = (s0 + s1) + (s2 + s3);
+}
+
+void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream) {
+  wgrad_reduce_tc_kernel<<<cdiv(36864, 256), 256, 0, stream>>>(part, nparts, dw);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------
+__global__ void pack_conv_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int ksize,
+                                            bf16* __restrict__ fprop, bf16* __restrict__ dgrad) {
+  const int taps = ksize * ksize;
+  const int total = Cout * Cin * taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % taps, ci = (i / taps) % Cin, co = i / (taps * Cin);
+    const bf16 v = __float2bfloat16_rn(w[i]);
+    if (fprop) fprop[((size_t)co * taps + tap) * Cin + ci] = v;
+    if (dgrad) dgrad[((size_t)ci * taps + (taps - 1 - tap)) * Cout + co] = v;
+  }
+}
+
+void pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, bf16* fprop, bf16* dgrad,
+                          cudaStream_t stream) {
+  const int total = Cout * Cin * ksize * ksize;
+  pack_conv_weights_tc_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, Cout, Cin, ksize, fprop, dgrad);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// debug: one im2col box
+// ------------------------------------------------------------------------------------------
+__global__ void debug_im2col_kernel(const __grid_constant__ CUtensorMap tmA, int cblock, int cw, int ch,
+                                    int n_img, int s, int r, bf16* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + A_STAGE_BYTES);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, A_STAGE_BYTES);
+    tma_load_im2col_4d(&tmA, bar, smem, cblock * 64, cw, ch, n_img, (uint16_t)s, (uint16_t)r);
+  }
+  mbar_wait(bar, 0);
+  // de-swizzle: row = pixel (128 B), 16-byte chunk c stored at chunk (c ^ (row & 7))
+  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {
+    const int row = i >> 3, c = i & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(smem + row * 128 + ((c ^ (row & 7)) << 4));
+    reinterpret_cast<uint4*>(out)[row * 8 + c] = v;
+  }
+}
+
+void debug_im2col_tile(const bf16* in, int N, int H, int W, int Cin, int ksize, int stride, int pad,
+                       int first_pixel, int tap_r, int tap_s, int cblock, bf16* out128x64,
+                       cudaStream_t stream) {
+  const int Ho = (H + 2 * pad - ksize) / stride + 1;
+  const int Wo = (W + 2 * pad - ksize) / stride + 1;
+  CUtensorMap tmA = make_tmap_im2col(in, N, H, W, Cin, ksize, stride, pad);
+  const int hw = Ho * Wo;
+  const int n_img = first_pixel / hw, rem = first_pixel % hw;
+  const int cw = (rem % Wo) * stride - pad, ch = (rem / Wo) * stride - pad;
+  debug_im2col_kernel<<<1, 128, A_STAGE_BYTES + 1024 + 64, stream>>>(tmA, cblock, cw, ch, n_img, tap_s,
+                                                                      tap_r, out128x64);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+}  // namespace pcg

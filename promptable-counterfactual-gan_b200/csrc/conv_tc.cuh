@@ -1,0 +1,48 @@
+// Tensor-core (tcgen05 / TMEM / TMA-im2col) convolution kernels for sm_100a — host interface.
+#pragma once
+#include "common.cuh"
+
+namespace pcg {
+
+// Epilogue description shared by the fprop/dgrad implicit-GEMM kernel.
+struct ConvEpilogue {
+  const float* bias = nullptr;   // [Cout] fp32, added before activation
+  int act = ACT_NONE;            // ACT_NONE / ACT_LRELU / ACT_RELU applied to (acc + bias)
+  float slope = 0.2f;
+  const bf16* add_src = nullptr; // [M][Cout] bf16 added after activation (residual / skip gradient)
+  float* stats = nullptr;        // [grid][2*Cout] fp32 per-CTA partial (sum, sum of squares) of the
+                                 // pre-rounding output values, for train-mode BatchNorm
+};
+
+// Number of CTAs conv_tc_fprop launches for a problem (rows of the `stats` partial buffer).
+int conv_tc_grid(long long M, int Cout);
+
+// out[M][Cout] (NHWC bf16) = epilogue( im2col(in)[M][taps*Cin] * wpk[Cout][taps*Cin]^T )
+//   in  : NHWC bf16 [N][H][W][Cin], Cin % 64 == 0
+//   wpk : bf16 [Cout][ksize*ksize][Cin] (tap-major, channel fastest), Cout % 64 == 0
+// The data-gradient of a stride-1 convolution is the same call on dY with the rotated/transposed
+// packing produced by pack_conv_weights_tc().
+void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk, int Cout, int ksize,
+                   int stride, int pad, const ConvEpilogue& epi, bf16* out, cudaStream_t stream);
+
+// dW partials of a 3x3 / stride-1 / pad-1 convolution with Cin = Cout = 64:
+//   part[cta][tap][ci][co] (fp32) = sum over the CTA's pixels of x[p + tap][ci] * dy[p][co]
+// `part` must hold conv_tc_wgrad_grid(M) * 9*64*64 floats; reduce with wgrad_reduce_tc().
+int conv_tc_wgrad_grid(long long M);
+void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* part,
+                     cudaStream_t stream);
+// dw[co][ci][3][3] (fp32, torch OIHW) = sum_cta part[cta][tap][ci][co];  db[co] = sum_p dy[p][co]
+// is produced by the caller's BN/bias kernels, not here.
+void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream);
+
+// fp32 OIHW [Cout][Cin][k][k] -> bf16 [Cout][k*k][Cin] (fprop) and, if dgrad != nullptr,
+// bf16 [Cin][k*k][Cout] with the taps rotated by 180 degrees (dgrad of a stride-1 conv).
+void pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, bf16* fprop, bf16* dgrad,
+                          cudaStream_t stream);
+
+// Debug: what one im2col TMA box of 128 pixels x 64 channels delivers (de-swizzled), for tests.
+void debug_im2col_tile(const bf16* in, int N, int H, int W, int Cin, int ksize, int stride, int pad,
+                       int first_pixel, int tap_r, int tap_s, int cblock, bf16* out128x64,
+                       cudaStream_t stream);
+
+}  // namespace pcg
