@@ -38,6 +38,9 @@ int pcg_version(void);
 /* Kernels launched by this library since load (bench.py "gpu_launches"). */
 unsigned long long pcg_launch_count(void);
 
+/* Device-to-device copy on `stream` (test helper for reading plan-owned tensors). */
+int pcg_memcpy_d2d(void* dst, const void* src, size_t nbytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Per-kernel entry points (used by the parity tests; the step plan calls the same code).
  * ------------------------------------------------------------------------------------------ */
@@ -72,6 +75,91 @@ int pcg_pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, void*
 int pcg_debug_im2col_tile(const void* in, int N, int H, int W, int Cin, int ksize, int stride, int pad,
                           int first_pixel, int tap_r, int tap_s, int cblock, void* out128x64,
                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MNIST conv CounteRGAN step plan
+ *   replaces the loop body of conditional_counteRGAN/mnist/trainer.py:89-132 (train_countergan)
+ *   and the forwards of models/generator.py:71-86, models/discriminator.py:33-38,
+ *   models/classifier.py:25-28.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pcg_mnist_plan pcg_mnist_plan;
+
+typedef struct pcg_mnist_config {
+  int batch;              /* samples per step on this GPU                                        */
+  int base_ch;            /* ResidualGenerator(base_ch=...)   generator.py:32  (64)              */
+  int n_resblocks;        /* ResidualGenerator(n_resblocks=...)                (6)               */
+  int precision;          /* PCG_F32: CUDA-core fp32 everywhere; PCG_BF16: bf16 activations,
+                             tcgen05 tensor-core convolutions with fp32 accumulation             */
+  float g_lr, d_lr;       /* config.py:10-11                                                     */
+  float beta1, beta2, adam_eps;   /* torch.optim.Adam defaults .9 / .999 / 1e-8 (trainer.py:77)  */
+  float lambda_adv, lambda_cls, lambda_reg, lambda_mask;   /* config.py:12-15                    */
+  float residual_scaling; /* generator.py:33 (0.1)                                               */
+  float grad_scale;       /* gradients are multiplied by this before Adam (1/world_size)         */
+  int pollute_d_grads;    /* !=0: the G step also accumulates its weight gradients into d_grads,
+                             as the reference's g_loss.backward() does (diagnostic only)         */
+} pcg_mnist_config;
+
+/* Caller-owned device memory the plan borrows.  All fp32 unless stated.  Arena layouts are given
+ * by pcg_mnist_layout().  Gradients are WRITTEN (not accumulated) by every step. */
+typedef struct pcg_mnist_buffers {
+  float* g_params; float* g_grads; float* g_adam_m; float* g_adam_v; int* g_step;
+  float* g_bn_running;        /* [2*n_resblocks][2][base_ch]: (running_mean, running_var) per BN,
+                                 order bn1, bn2 of block 0, bn1, bn2 of block 1, ...             */
+  long long* g_bn_nbt;        /* [2*n_resblocks] num_batches_tracked (int64)                      */
+  float* d_params; float* d_grads; float* d_adam_m; float* d_adam_v; int* d_step;
+  const float* c_params;      /* frozen classifier                                               */
+} pcg_mnist_buffers;
+
+typedef struct pcg_mnist_inputs {   /* device pointers                                            */
+  const float* x;             /* [B][1][28][28] in [-1,1]                                         */
+  const long long* y;         /* [B] int64 labels              trainer.py:90                      */
+  const long long* target;    /* [B] int64 target classes      trainer.py:94 (injected draw)      */
+  const float* mask;          /* [B][1][28][28] {0,1}          trainer.py:95 (injected draw)      */
+} pcg_mnist_inputs;
+
+/* indices into the scalar block written by the step (device float[PCG_MNIST_NSCALARS]) */
+enum {
+  PCG_S_D_LOSS = 0, PCG_S_G_LOSS = 1, PCG_S_G_ADV = 2, PCG_S_G_CLS = 3, PCG_S_REG_L1 = 4,
+  PCG_S_MASK_PEN = 5, PCG_S_D_REAL_P = 6, PCG_S_D_FAKE_P = 7, PCG_S_D_LOSS_REAL = 8,
+  PCG_S_D_LOSS_FAKE = 9, PCG_MNIST_NSCALARS = 16
+};
+
+/* net: 0 = generator, 1 = discriminator, 2 = classifier.  Returns the number of parameter
+ * tensors; if idx >= 0 also the arena offset / element count (floats) of tensor idx, tensors in
+ * module.parameters() order.  *total = arena size in floats. */
+int pcg_mnist_layout(int net, int base_ch, int n_resblocks, int idx, long long* offset,
+                     long long* numel, long long* total);
+
+int pcg_mnist_plan_create(const pcg_mnist_config* cfg, const pcg_mnist_buffers* buf,
+                          pcg_mnist_plan** out);
+int pcg_mnist_plan_destroy(pcg_mnist_plan* plan);
+/* Re-derive the packed (kernel-layout) weights from the fp32 arenas; call after the caller
+ * modified parameters behind the plan's back (load_state_dict, optimizer of its own...). */
+int pcg_mnist_refresh_weights(pcg_mnist_plan* plan, void* stream);
+
+/* One full iteration = the four phases below in order.  scalars: device float[PCG_MNIST_NSCALARS]. */
+int pcg_mnist_step(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream);
+/* phase 1: G forward, x_cf, D forward/backward on (x,y) and (x_cf.detach(), target) -> d_grads */
+int pcg_mnist_step_d_grads(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream);
+/* phase 2: Adam on D (gradient all-reduce, if any, happens between phase 1 and 2) */
+int pcg_mnist_step_d_update(pcg_mnist_plan* plan, void* stream);
+/* phase 3: D forward with the updated D, classifier forward/backward, losses, G backward -> g_grads */
+int pcg_mnist_step_g_grads(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream);
+/* phase 4: Adam on G */
+int pcg_mnist_step_g_update(pcg_mnist_plan* plan, void* stream);
+
+/* Module forwards (nn.Module.forward mirrors).  training != 0: BatchNorm uses batch statistics and
+ * updates the running buffers (generator.py train mode); == 0: running statistics. */
+int pcg_mnist_g_forward(pcg_mnist_plan* plan, const float* x, const long long* target,
+                        const float* mask, int training, float* raw, float* masked, void* stream);
+int pcg_mnist_d_forward(pcg_mnist_plan* plan, const float* x, const long long* cond, float* logits,
+                        void* stream);
+int pcg_mnist_c_forward(pcg_mnist_plan* plan, const float* x, float* logits, void* stream);
+
+/* Test hook: device pointer / element count / dtype (PCG_F32 or PCG_BF16) of an internal NHWC
+ * tensor by name ("h0", "y1.3", "z1.0", "y2.5", "h.6", "hm", "x_cf", "raw", "dxd", "dxc", ...). */
+int pcg_mnist_debug_tensor(pcg_mnist_plan* plan, const char* name, void** ptr, long long* numel,
+                           int* dtype);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,12 @@ const char* pcg_last_error(void) { return t_last_error.c_str(); }
 int pcg_version(void) { return PCG_VERSION; }
 unsigned long long pcg_launch_count(void) { return g_launch_count; }
 
+int pcg_memcpy_d2d(void* dst, const void* src, size_t nbytes, void* stream) {
+  PCG_API_BEGIN
+  PCG_CHECK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  PCG_API_END
+}
+
 int pcg_conv_tc_grid(long long M, int Cout) {
   try { return conv_tc_grid(M, Cout); } catch (const std::exception& e) { set_last_error(e.what()); return -1; }
 }

@@ -1,0 +1,473 @@
+// CUDA-core convolution kernels (fp32 math, NHWC storage in fp32 or bf16).
+//
+// Replaces, for the layers the tcgen05 kernels do not take: nn.Conv2d / nn.Linear forward and
+// ConvolutionBackward0 / AddmmBackward0 of
+//   conditional_counteRGAN/mnist/models/generator.py:39,50        (conv_in 3->64, conv_out 64->1)
+//   conditional_counteRGAN/mnist/models/discriminator.py:14-24     (4 stride-2 convs, no bias)
+//   conditional_counteRGAN/mnist/models/classifier.py:8-21         (3 convs + 2 linears, eval)
+//
+// Three kernel families:
+//   gemm_conv_kernel<MODE>   64x64x16 smem-tiled implicit GEMM; MODE = fprop gather or dgrad gather
+//   skinny_conv_kernel<MODE> <= 4 output channels (conv_out fprop, data-gradients wrt 1-3 channel
+//                            images): one warp per pixel, HBM/L2-bound
+//   wgrad kernels            split-K over pixels with per-slice partials reduced in fixed order
+#include "conv_generic.cuh"
+
+namespace pcg {
+
+enum { MODE_FPROP = 0, MODE_DGRAD = 1 };
+
+// Row (output pixel) -> base coordinates; shared by fprop/dgrad gathers.
+struct RowCoord {
+  int n, h, w;   // pixel of the OUTPUT tensor of this GEMM (fprop: (n,ho,wo); dgrad: (n,hi,wi))
+};
+
+template <int MODE>
+struct Gather {
+  // Source tensor spatial dims / channels and GEMM-K decomposition.
+  int srcH, srcW, srcC;     // tensor being gathered from
+  int ksize, stride, pad;
+  // Returns element offset into the source tensor (pixel base, channel 0) or -1 if the tap is void.
+  __device__ __forceinline__ long long pixel_offset(const RowCoord& rc, int tap) const {
+    const int r = tap / ksize, s = tap - r * ksize;
+    int sh, sw;
+    if (MODE == MODE_FPROP) {
+      sh = rc.h * stride - pad + r;
+      sw = rc.w * stride - pad + s;
+    } else {
+      const int th = rc.h + pad - r, tw = rc.w + pad - s;
+      if (th < 0 || tw < 0) return -1;
+      if (stride > 1 && ((th % stride) != 0 || (tw % stride) != 0)) return -1;
+      sh = th / stride;
+      sw = tw / stride;
+    }
+    if (sh < 0 || sh >= srcH || sw < 0 || sw >= srcW) return -1;
+    return (((long long)rc.n * srcH + sh) * srcW + sw) * srcC;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 f = *reinterpret_cast<const float4*>(p);
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+template <>
+__device__ __forceinline__ void load4<bf16>(const bf16* p, float (&v)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+constexpr int GT = 64;     // tile M = tile N
+constexpr int GK = 16;     // tile K
+constexpr int GPAD = 4;
+
+template <typename TOut>
+struct EpiDev {
+  const float* bias; int act; float slope;
+  const TOut* add_src; const TOut* act_ref; int ref_act; float ref_slope;
+};
+
+template <typename TOut>
+__device__ __forceinline__ float apply_epilogue(float v, const EpiDev<TOut>& e, long long row, int col, int ld) {
+  if (e.bias) v += __ldg(e.bias + col);
+  if (e.act == ACT_LRELU) v = v > 0.f ? v : v * e.slope;
+  else if (e.act == ACT_RELU) v = fmaxf(v, 0.f);
+  if (e.add_src) v += to_f(e.add_src[row * ld + col]);
+  if (e.act_ref) {
+    const float a = to_f(e.act_ref[row * ld + col]);
+    if (e.ref_act == ACT_LRELU) v *= (a > 0.f ? 1.f : e.ref_slope);
+    else if (e.ref_act == ACT_RELU) v *= (a > 0.f ? 1.f : 0.f);
+  }
+  return v;
+}
+
+// C[M][Nc] = A_gather[M][K] * B[Nc][K]^T ; K = taps * srcC with (tap, channel) ordering.
+template <int MODE, typename TIn, typename TOut, bool VEC>
+__global__ void __launch_bounds__(256)
+gemm_conv_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt, TOut* __restrict__ dst,
+                 long long M, int Nc, int K, int outH, int outW, Gather<MODE> ga, EpiDev<TOut> epi) {
+  __shared__ float As[2][GK][GT + GPAD];
+  __shared__ float Bs[2][GK][GT + GPAD];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * GT;
+  const int n0 = blockIdx.y * GT;
+
+  // loader mapping: 64 rows x 16 k, thread -> (row = tid/4, 4 consecutive k at (tid%4)*4)
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  RowCoord rc;
+  const long long am = m0 + lrow;
+  const bool arow_ok = am < M;
+  {
+    long long t = arow_ok ? am : 0;
+    rc.w = (int)(t % outW); t /= outW;
+    rc.h = (int)(t % outH); rc.n = (int)(t / outH);
+  }
+  const int bn = n0 + lrow;
+  const bool brow_ok = bn < Nc;
+
+  float ra[4], rb[4];
+  auto load_tile = [&](int k0) {
+    const int k = k0 + lk;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ra[i] = rb[i] = 0.f;
+    if (VEC) {
+      // srcC % 4 == 0 and K % 4 == 0: the 4 k's share a tap and are contiguous channels
+      if (k < K) {
+        if (arow_ok) {
+          const int tap = k / ga.srcC, c = k - tap * ga.srcC;
+          const long long off = ga.pixel_offset(rc, tap);
+          if (off >= 0) load4<TIn>(src + off + c, ra);
+        }
+        if (brow_ok) load4<float>(wgt + (size_t)bn * K + k, rb);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = k + i;
+        if (kk < K) {
+          if (arow_ok) {
+            const int tap = kk / ga.srcC, c = kk - tap * ga.srcC;
+            const long long off = ga.pixel_offset(rc, tap);
+            if (off >= 0) ra[i] = to_f(src[off + c]);
+          }
+          if (brow_ok) rb[i] = wgt[(size_t)bn * K + kk];
+        }
+      }
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[buf][lk + i][lrow] = ra[i];
+      Bs[buf][lk + i][lrow] = rb[i];
+    }
+  };
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + GK - 1) / GK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tile((kt + 1) * GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col < Nc) dst[row * Nc + col] = from_f<TOut>(apply_epilogue(acc[i][j], epi, row, col, Nc));
+    }
+  }
+}
+
+// <= 4 output channels: one warp per output pixel, lanes over the source channels.
+template <int MODE, typename TIn, typename TOut, int NC>
+__global__ void __launch_bounds__(256)
+skinny_conv_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt, TOut* __restrict__ dst,
+                   long long M, int K, int outH, int outW, Gather<MODE> ga, EpiDev<TOut> epi) {
+  extern __shared__ float wsm[];   // [NC][K]
+  for (int i = threadIdx.x; i < NC * K; i += blockDim.x) wsm[i] = wgt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int taps = ga.ksize * ga.ksize;
+  for (long long m = warp_global; m < M; m += nwarps) {
+    RowCoord rc;
+    long long t = m;
+    rc.w = (int)(t % outW); t /= outW;
+    rc.h = (int)(t % outH); rc.n = (int)(t / outH);
+    float acc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+    for (int tap = 0; tap < taps; ++tap) {
+      const long long off = ga.pixel_offset(rc, tap);
+      if (off < 0) continue;
+      for (int c = lane; c < ga.srcC; c += 32) {
+        const float a = to_f(src[off + c]);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[j] = fmaf(a, wsm[j * K + tap * ga.srcC + c], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) dst[m * NC + j] = from_f<TOut>(apply_epilogue(acc[j], epi, m, j, NC));
+    }
+  }
+}
+
+template <typename TOut>
+static EpiDev<TOut> to_dev(const GenEpilogue<TOut>& e) {
+  EpiDev<TOut> d;
+  d.bias = e.bias; d.act = e.act; d.slope = e.slope; d.add_src = e.add_src;
+  d.act_ref = e.act_ref; d.ref_act = e.ref_act; d.ref_slope = e.ref_slope;
+  return d;
+}
+
+template <int MODE, typename TIn, typename TOut>
+static void launch_conv(const TIn* src, const float* wgt, TOut* dst, long long M, int Nc, int K, int outH,
+                        int outW, const Gather<MODE>& ga, const GenEpilogue<TOut>& epi, cudaStream_t stream) {
+  const EpiDev<TOut> e = to_dev(epi);
+  if (Nc <= 4) {
+    const int blocks = (int)((M * 32 + 255) / 256 < (long long)sm_count() * 16 ? (M * 32 + 255) / 256
+                                                                               : (long long)sm_count() * 16);
+    const size_t sm = (size_t)Nc * K * sizeof(float);
+    PCG_REQUIRE(sm <= 48 * 1024, "skinny conv weights must fit 48 KB of shared memory");
+    switch (Nc) {
+      case 1: skinny_conv_kernel<MODE, TIn, TOut, 1><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
+      case 2: skinny_conv_kernel<MODE, TIn, TOut, 2><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
+      case 3: skinny_conv_kernel<MODE, TIn, TOut, 3><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
+      default: skinny_conv_kernel<MODE, TIn, TOut, 4><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
+    }
+  } else {
+    dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((Nc + GT - 1) / GT));
+    const bool vec = (ga.srcC % 4 == 0) && (K % 4 == 0) && (((uintptr_t)src & 15) == 0) &&
+                     (((uintptr_t)wgt & 15) == 0);
+    if (vec) gemm_conv_kernel<MODE, TIn, TOut, true><<<grid, 256, 0, stream>>>(src, wgt, dst, M, Nc, K, outH, outW, ga, e);
+    else gemm_conv_kernel<MODE, TIn, TOut, false><<<grid, 256, 0, stream>>>(src, wgt, dst, M, Nc, K, outH, outW, ga, e);
+  }
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename TIn, typename TOut>
+void conv_fprop_generic(const TIn* in, const ConvGeom& g, const float* wf, const GenEpilogue<TOut>& epi,
+                        TOut* out, cudaStream_t stream) {
+  Gather<MODE_FPROP> ga;
+  ga.srcH = g.H; ga.srcW = g.W; ga.srcC = g.Cin; ga.ksize = g.ksize; ga.stride = g.stride; ga.pad = g.pad;
+  launch_conv<MODE_FPROP>(in, wf, out, g.Mout(), g.Cout, g.K(), g.Ho(), g.Wo(), ga, epi, stream);
+}
+
+template <typename TIn, typename TOut>
+void conv_dgrad_generic(const TIn* dout, const ConvGeom& g, const float* wd, const GenEpilogue<TOut>& epi,
+                        TOut* din, cudaStream_t stream) {
+  Gather<MODE_DGRAD> ga;
+  ga.srcH = g.Ho(); ga.srcW = g.Wo(); ga.srcC = g.Cout; ga.ksize = g.ksize; ga.stride = g.stride; ga.pad = g.pad;
+  launch_conv<MODE_DGRAD>(dout, wd, din, g.Min(), g.Cin, g.ksize * g.ksize * g.Cout, g.H, g.W, ga, epi, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: part[z][co][k] = sum over pixel slice z of dy[p][co] * x[p@tap][ci],  k = (tap, ci)
+// ------------------------------------------------------------------------------------------
+template <typename TIn, typename TDy, bool VEC>
+__global__ void __launch_bounds__(256)
+wgrad_gemm_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, float* __restrict__ part, long long P,
+                  int Cout, int K, int outH, int outW, long long slice, Gather<MODE_FPROP> ga) {
+  __shared__ float As[2][GK][GT + GPAD];   // [pixel][co]
+  __shared__ float Bs[2][GK][GT + GPAD];   // [pixel][k]
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.x * GT, k0 = blockIdx.y * GT;
+  const long long p_begin = (long long)blockIdx.z * slice;
+  const long long p_end = p_begin + slice < P ? p_begin + slice : P;
+
+  const int lp = tid >> 4, lc = (tid & 15) * 4;   // 16 pixels x 64 columns, 4 consecutive columns each
+  float ra[4], rb[4];
+  auto load_tile = [&](long long pbase) {
+    const long long p = pbase + lp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ra[i] = rb[i] = 0.f;
+    if (p < p_end) {
+      if (VEC) {
+        if (co0 + lc < Cout) load4<TDy>(dy + p * Cout + co0 + lc, ra);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (co0 + lc + i < Cout) ra[i] = to_f(dy[p * Cout + co0 + lc + i]);
+      }
+      RowCoord rc;
+      long long t = p;
+      rc.w = (int)(t % outW); t /= outW;
+      rc.h = (int)(t % outH); rc.n = (int)(t / outH);
+      const int k = k0 + lc;
+      if (VEC) {
+        if (k < K) {
+          const int tap = k / ga.srcC, c = k - tap * ga.srcC;
+          const long long off = ga.pixel_offset(rc, tap);
+          if (off >= 0) load4<TIn>(x + off + c, rb);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kk = k + i;
+          if (kk < K) {
+            const int tap = kk / ga.srcC, c = kk - tap * ga.srcC;
+            const long long off = ga.pixel_offset(rc, tap);
+            if (off >= 0) rb[i] = to_f(x[off + c]);
+          }
+        }
+      }
+    }
+  };
+  auto store_tile = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lp][lc]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    *reinterpret_cast<float4*>(&Bs[buf][lp][lc]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+  };
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const long long npix = p_end > p_begin ? p_end - p_begin : 0;
+  const int nt = (int)((npix + GK - 1) / GK);
+  if (nt > 0) {
+    load_tile(p_begin);
+    store_tile(0);
+    __syncthreads();
+  }
+  for (int t = 0; t < nt; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nt) load_tile(p_begin + (long long)(t + 1) * GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (t + 1 < nt) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  float* my = part + (size_t)blockIdx.z * Cout * K;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) my[(size_t)co * K + k] = acc[i][j];
+    }
+  }
+}
+
+// part[z][co][(tap,ci)] -> dw[co][ci][tap] (torch OIHW), fixed order over z.
+__global__ void wgrad_reduce_generic_kernel(const float* __restrict__ part, int nz, int Cout, int Cin, int taps,
+                                            float* __restrict__ dw) {
+  const int K = taps * Cin;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * K) return;
+  float s = 0.f;
+  for (int z = 0; z < nz; ++z) s += part[(size_t)z * Cout * K + idx];
+  const int co = idx / K, k = idx - co * K;
+  const int tap = k / Cin, ci = k - tap * Cin;
+  dw[((size_t)co * Cin + ci) * taps + tap] = s;
+}
+
+static int wgrad_slices(const ConvGeom& g) {
+  const long long P = g.Mout();
+  const int tiles = cdiv(g.Cout, GT) * cdiv(g.K(), GT);
+  long long want = (4LL * 148 + tiles - 1) / tiles;
+  long long maxz = (P + 255) / 256;       // at least 256 pixels per slice
+  if (want > maxz) want = maxz;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  return (int)want;
+}
+
+size_t conv_wgrad_generic_scratch(const ConvGeom& g) {
+  return (size_t)wgrad_slices(g) * g.Cout * g.K();
+}
+
+template <typename TIn, typename TDy>
+void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float* scratch, float* dw,
+                        cudaStream_t stream) {
+  Gather<MODE_FPROP> ga;
+  ga.srcH = g.H; ga.srcW = g.W; ga.srcC = g.Cin; ga.ksize = g.ksize; ga.stride = g.stride; ga.pad = g.pad;
+  const long long P = g.Mout();
+  const int nz = wgrad_slices(g);
+  const long long slice = ((P + nz - 1) / nz + GK - 1) / GK * GK;
+  dim3 grid(cdiv(g.Cout, GT), cdiv(g.K(), GT), nz);
+  const bool vec = (g.Cin % 4 == 0) && (g.Cout % 4 == 0) && (((uintptr_t)in & 15) == 0) &&
+                   (((uintptr_t)dout & 15) == 0);
+  if (vec) wgrad_gemm_kernel<TIn, TDy, true><<<grid, 256, 0, stream>>>(in, dout, scratch, P, g.Cout, g.K(), g.Ho(), g.Wo(), slice, ga);
+  else wgrad_gemm_kernel<TIn, TDy, false><<<grid, 256, 0, stream>>>(in, dout, scratch, P, g.Cout, g.K(), g.Ho(), g.Wo(), slice, ga);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+  wgrad_reduce_generic_kernel<<<cdiv((long long)g.Cout * g.K(), 256), 256, 0, stream>>>(scratch, nz, g.Cout, g.Cin,
+                                                                                        g.ksize * g.ksize, dw);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void pack_generic_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int perm_hw,
+                                    float* __restrict__ wf, float* __restrict__ wd) {
+  const int total = Cout * Cin * taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % taps;
+    int ci = (i / taps) % Cin;
+    const int co = i / (taps * Cin);
+    if (perm_hw > 0) {           // torch flatten index c*HW + hw  ->  NHWC flatten index hw*C + c
+      const int C = Cin / perm_hw;
+      const int c = ci / perm_hw, hw = ci - c * perm_hw;
+      ci = hw * C + c;
+    }
+    const float v = w[i];
+    if (wf) wf[((size_t)co * taps + tap) * Cin + ci] = v;
+    if (wd) wd[((size_t)ci * taps + tap) * Cout + co] = v;
+  }
+}
+
+void pack_conv_weights_generic(const float* w, int Cout, int Cin, int ksize, int perm_hw, float* wf, float* wd,
+                               cudaStream_t stream) {
+  const int total = Cout * Cin * ksize * ksize;
+  int blocks = cdiv(total, 256);
+  if (blocks > 1184) blocks = 1184;
+  pack_generic_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, ksize * ksize, perm_hw, wf, wd);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// explicit instantiations
+#define INST(TI, TO)                                                                                      \
+  template void conv_fprop_generic<TI, TO>(const TI*, const ConvGeom&, const float*, const GenEpilogue<TO>&, \
+                                           TO*, cudaStream_t);                                            \
+  template void conv_dgrad_generic<TI, TO>(const TI*, const ConvGeom&, const float*, const GenEpilogue<TO>&, \
+                                           TO*, cudaStream_t);                                            \
+  template void conv_wgrad_generic<TI, TO>(const TI*, const TO*, const ConvGeom&, float*, float*, cudaStream_t);
+INST(float, float)
+INST(bf16, bf16)
+INST(float, bf16)
+INST(bf16, float)
+#undef INST
+
+}  // namespace pcg

@@ -100,6 +100,9 @@ struct FpropParams {
   int act;
   float slope;
   const bf16* add_src;
+  const bf16* act_ref;
+  int ref_act;
+  float ref_slope;
   bf16* out;
   float* stats;
 };
@@ -286,6 +289,21 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
         }
+        if (p.act_ref != nullptr && valid) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.act_ref + pix * p.Cout + col0);
+          const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u = __ldg(src + j4);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h[e]);
+              v[j4 * 8 + e * 2] *= (f.x > 0.f ? 1.f : neg);
+              v[j4 * 8 + e * 2 + 1] *= (f.y > 0.f ? 1.f : neg);
+            }
+          }
+        }
         if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + col0);
 #pragma unroll
@@ -377,6 +395,7 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
   p.num_m_tiles = (int)((M + TILE_M - 1) / TILE_M);
   p.num_n_tiles = Cout / bn;
   p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
+  p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
   p.out = out; p.stats = epi.stats;
   CUtensorMap tmA = make_tmap_im2col(in, N, H, W, Cin, ksize, stride, pad);
   CUtensorMap tmB = make_tmap_2d(wpk, Cout, (uint64_t)ksize * ksize * Cin, bn);

@@ -10,6 +10,9 @@ struct ConvEpilogue {
   int act = ACT_NONE;            // ACT_NONE / ACT_LRELU / ACT_RELU applied to (acc + bias)
   float slope = 0.2f;
   const bf16* add_src = nullptr; // [M][Cout] bf16 added after activation (residual / skip gradient)
+  const bf16* act_ref = nullptr; // [M][Cout] bf16: result is multiplied by d act/d pre evaluated at
+  int ref_act = ACT_NONE;        // act_ref (the activation OUTPUT; LReLU/ReLU derivative from its sign)
+  float ref_slope = 0.2f;
   float* stats = nullptr;        // [grid][2*Cout] fp32 per-CTA partial (sum, sum of squares) of the
                                  // pre-rounding output values, for train-mode BatchNorm
 };

@@ -1,0 +1,740 @@
+// HBM-bound kernels of the GAN step (see elementwise.cuh for the reference call sites).
+#include "elementwise.cuh"
+
+namespace pcg {
+
+// ---------------------------------------------------------------------------------------------
+// vector helpers: 4 consecutive channels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 f = *reinterpret_cast<const float4*>(p);
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+__device__ __forceinline__ void ld4(const bf16* p, float (&v)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+__device__ __forceinline__ float act_grad(float out, int act, float slope) {
+  if (act == ACT_LRELU) return out > 0.f ? 1.f : slope;
+  if (act == ACT_RELU) return out > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column reductions over a row slice of an [M][C] matrix.
+// Block = 256 threads; C/4 threads span a row (4 channels each); 256/(C/4) rows per pass.
+// Each block writes part[blockIdx.x][NV*C].
+// ---------------------------------------------------------------------------------------------
+struct RowSlice {
+  long long begin, end;
+};
+__device__ __forceinline__ RowSlice row_slice(long long M) {
+  const long long rps = (M + gridDim.x - 1) / gridDim.x;
+  RowSlice r;
+  r.begin = (long long)blockIdx.x * rps;
+  r.end = r.begin + rps < M ? r.begin + rps : M;
+  return r;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_col_reduce(float (&acc)[NV][4], int C, float* part_row) {
+  // threads with the same (threadIdx.x % (C/4)) own the same 4 channels
+  __shared__ float red[256 * 4];
+  const int lpr = C >> 2;
+  const int cg = threadIdx.x % lpr;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.x * 4 + j] = acc[v][j];
+    __syncthreads();
+    if (threadIdx.x < lpr) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int r = threadIdx.x; r < 256; r += lpr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += red[r * 4 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part_row[v * C + cg * 4 + j] = s[j];
+    }
+  }
+}
+
+static void check_colshape(int C) {
+  PCG_REQUIRE(C % 4 == 0 && C <= 1024 && (256 % (C / 4)) == 0, "channel count must be 4*2^k <= 1024");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, long long M, int C,
+                                                      float* __restrict__ part) {
+  const int lpr = C >> 2, rpp = 256 / lpr;
+  const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
+  const RowSlice sl = row_slice(M);
+  float acc[2][4] = {};
+  for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
+    float v[4];
+    ld4(y + r * C + cg * 4, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[0][j] += v[j];
+      acc[1][j] = fmaf(v[j], v[j], acc[1][j]);
+    }
+  }
+  block_col_reduce<2>(acc, C, part + (size_t)blockIdx.x * 2 * C);
+}
+
+template <typename T>
+void bn_stats_partial(const T* y, long long M, int C, float* part, cudaStream_t s) {
+  check_colshape(C);
+  bn_stats_kernel<T><<<STAT_PARTS, 256, 0, s>>>(y, M, C, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, long long* nbt,
+                                   float* mean_o, float* rstd_o, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt != nullptr) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < nparts; ++i) {
+    s += (double)part[(size_t)i * 2 * C + c];
+    q += (double)part[(size_t)i * 2 * C + C + c];
+  }
+  const double mean = s / (double)M;
+  double var = q / (double)M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float a = gamma[c] * rstd;
+  mean_o[c] = (float)mean;
+  rstd_o[c] = rstd;
+  scale[c] = a;
+  shift[c] = beta[c] - (float)mean * a;
+  if (running_mean != nullptr) {
+    const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+void bn_finalize(const float* part, int nparts, long long M, int C, const float* gamma, const float* beta,
+                 float eps, float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
+                 float* rstd, float* scale, float* shift, cudaStream_t s) {
+  bn_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
+                                               running_var, nbt, mean, rstd, scale, shift);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, long long n4, int C,
+                                                          int act, float slope, T* __restrict__ z) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % C);
+    float v[4];
+    ld4(y + i * 4, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = act_fwd(fmaf(v[j], __ldg(scale + c + j), __ldg(shift + c + j)), act, slope);
+    st4(z + i * 4, v);
+  }
+}
+
+static int ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+template <typename T>
+void bn_apply_act(const T* y, const float* scale, const float* shift, long long M, int C, int act, float slope, T* z,
+                  cudaStream_t s) {
+  PCG_REQUIRE(C % 4 == 0, "C % 4");
+  const long long n4 = M * C / 4;
+  bn_apply_act_kernel<T><<<ew_blocks(n4), 256, 0, s>>>(y, scale, shift, n4, C, act, slope, z);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_residual_kernel(const T* __restrict__ y, const T* __restrict__ h, const float* __restrict__ scale,
+                         const float* __restrict__ shift, float res_scale, long long n4, int C, T* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % C);
+    float v[4], hv[4];
+    ld4(y + i * 4, v);
+    ld4(h + i * 4, hv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      v[j] = hv[j] + res_scale * fmaf(v[j], __ldg(scale + c + j), __ldg(shift + c + j));
+    st4(out + i * 4, v);
+  }
+}
+
+template <typename T>
+void bn_apply_residual(const T* y, const T* h, const float* scale, const float* shift, float res_scale, long long M,
+                       int C, T* out, cudaStream_t s) {
+  PCG_REQUIRE(C % 4 == 0, "C % 4");
+  const long long n4 = M * C / 4;
+  bn_apply_residual_kernel<T><<<ew_blocks(n4), 256, 0, s>>>(y, h, scale, shift, res_scale, n4, C, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// g = gscale * dsrc * act'(scale*y + shift)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_partial_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                      float gscale, int act, float slope, long long M, int C, float* __restrict__ part) {
+  const int lpr = C >> 2, rpp = 256 / lpr;
+  const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
+  const RowSlice sl = row_slice(M);
+  float mu[4], rs[4], a[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mu[j] = mean[cg * 4 + j]; rs[j] = rstd[cg * 4 + j]; a[j] = scale[cg * 4 + j]; b[j] = shift[cg * 4 + j];
+  }
+  float acc[2][4] = {};
+  for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
+    float d[4], v[4];
+    ld4(dsrc + r * C + cg * 4, d);
+    ld4(y + r * C + cg * 4, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = gscale * d[j] * act_grad(fmaf(v[j], a[j], b[j]), act, slope);
+      acc[0][j] += g;
+      acc[1][j] = fmaf(g, (v[j] - mu[j]) * rs[j], acc[1][j]);
+    }
+  }
+  block_col_reduce<2>(acc, C, part + (size_t)blockIdx.x * 2 * C);
+}
+
+template <typename T>
+void bn_bwd_partial(const T* dsrc, const T* y, const float* mean, const float* rstd, const float* scale,
+                    const float* shift, float gscale, int act, float slope, long long M, int C, float* part,
+                    cudaStream_t s) {
+  check_colshape(C);
+  bn_bwd_partial_kernel<T><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, gscale, act, slope, M, C, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, float* dgamma,
+                                       float* dbeta, float* c12) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < nparts; ++i) {
+    s1 += (double)part[(size_t)i * 2 * C + c];
+    s2 += (double)part[(size_t)i * 2 * C + C + c];
+  }
+  dbeta[c] = (float)s1;
+  dgamma[c] = (float)s2;
+  c12[c] = (float)(s1 / (double)M);
+  c12[C + c] = (float)(s2 / (double)M);
+}
+
+void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* dgamma, float* dbeta, float* c12,
+                     cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, M, C, dgamma, dbeta, c12);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ c12, float gscale, int act, float slope, long long M, int C,
+                    T* __restrict__ dy, float* __restrict__ part_db) {
+  const int lpr = C >> 2, rpp = 256 / lpr;
+  const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
+  const RowSlice sl = row_slice(M);
+  float mu[4], rs[4], a[4], b[4], c1[4], c2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cg * 4 + j;
+    mu[j] = mean[c]; rs[j] = rstd[c]; a[j] = scale[c]; b[j] = shift[c]; c1[j] = c12[c]; c2[j] = c12[C + c];
+  }
+  float acc[1][4] = {};
+  for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
+    float d[4], v[4], o[4];
+    ld4(dsrc + r * C + cg * 4, d);
+    ld4(y + r * C + cg * 4, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = gscale * d[j] * act_grad(fmaf(v[j], a[j], b[j]), act, slope);
+      const float xhat = (v[j] - mu[j]) * rs[j];
+      o[j] = a[j] * (g - c1[j] - xhat * c2[j]);     // a = gamma * rstd
+      acc[0][j] += o[j];
+    }
+    st4(dy + r * C + cg * 4, o);
+  }
+  block_col_reduce<1>(acc, C, part_db + (size_t)blockIdx.x * C);
+}
+
+template <typename T>
+void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rstd, const float* scale,
+                  const float* shift, const float* gamma, const float* c12, float gscale, int act, float slope,
+                  long long M, int C, T* dy, float* part_db, cudaStream_t s) {
+  (void)gamma;
+  check_colshape(C);
+  bn_bwd_apply_kernel<T><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, c12, gscale, act, slope, M, C, dy,
+                                                   part_db);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ part, int nparts, int stride, int C, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int i = 0; i < nparts; ++i) s += (double)part[(size_t)i * stride + c];
+  out[c] = (float)s;
+}
+void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s) {
+  colsum_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, stride, C, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, long long M, int C,
+                                                    float* __restrict__ part) {
+  const RowSlice sl = row_slice(M);
+  if ((C & 3) == 0 && (256 % (C >> 2)) == 0 && C <= 1024) {
+    const int lpr = C >> 2, rpp = 256 / lpr;
+    const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
+    float acc[1][4] = {};
+    for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
+      float v[4];
+      ld4(a + r * C + cg * 4, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[0][j] += v[j];
+    }
+    block_col_reduce<1>(acc, C, part + (size_t)blockIdx.x * C);
+  } else {
+    // tiny / odd channel counts (e.g. C = 1): one column at a time, block tree reduction
+    __shared__ float red[256];
+    for (int c = 0; c < C; ++c) {
+      float s = 0.f;
+      for (long long r = sl.begin + threadIdx.x; r < sl.end; r += 256) s += to_f(a[r * C + c]);
+      red[threadIdx.x] = s;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) part[(size_t)blockIdx.x * C + c] = red[0];
+      __syncthreads();
+    }
+  }
+}
+template <typename T>
+void colsum_partial(const T* a, long long M, int C, float* part, cudaStream_t s) {
+  colsum_kernel<T><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// input assembly / embedding gradient
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void g_input_kernel(const float* __restrict__ x, const float* __restrict__ embed,
+                               const long long* __restrict__ label, const float* __restrict__ mask, long long total,
+                               int HW, T* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), p = (int)(i - (long long)n * HW);
+    out[i * 3 + 0] = from_f<T>(x[i]);
+    out[i * 3 + 1] = from_f<T>(embed[(size_t)label[n] * HW + p]);
+    out[i * 3 + 2] = from_f<T>(mask[i]);
+  }
+}
+template <typename T>
+void g_input(const float* x, const float* embed, const long long* label, const float* mask, int B, int HW, T* out,
+             cudaStream_t s) {
+  const long long total = (long long)B * HW;
+  g_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(x, embed, label, mask, total, HW, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void d_input_kernel(const float* __restrict__ x, const float* __restrict__ embed,
+                               const long long* __restrict__ label, long long total, int HW, T* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), p = (int)(i - (long long)n * HW);
+    out[i * 2 + 0] = from_f<T>(x[i]);
+    out[i * 2 + 1] = from_f<T>(embed[(size_t)label[n] * HW + p]);
+  }
+}
+template <typename T>
+void d_input(const float* x, const float* embed, const long long* label, int B, int HW, T* out, cudaStream_t s) {
+  const long long total = (long long)B * HW;
+  d_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(x, embed, label, total, HW, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void embed_grad_kernel(const T* __restrict__ src, int nch, int ch, const long long* __restrict__ label,
+                                  int B, int HW, float* __restrict__ dE) {
+  const int cls = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float s = 0.f;
+  for (int n = 0; n < B; ++n) {
+    if (label[n] == cls) s += to_f(src[((size_t)n * HW + p) * nch + ch]);
+  }
+  dE[(size_t)cls * HW + p] = s;
+}
+template <typename T>
+void embed_grad(const T* src, int nch, int ch, const long long* label, int B, int HW, int num_classes, float* dE,
+                cudaStream_t s) {
+  dim3 grid(cdiv(HW, 128), num_classes);
+  embed_grad_kernel<T><<<grid, 128, 0, s>>>(src, nch, ch, label, B, HW, dE);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual head
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+residual_head_fwd_kernel(const float* __restrict__ c, const float* __restrict__ x, const float* __restrict__ mask,
+                         float rs, long long n, float* __restrict__ raw, float* __restrict__ masked,
+                         float* __restrict__ x_cf, float* __restrict__ part) {
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long b = (long long)blockIdx.x * per, e = b + per < n ? b + per : n;
+  float s0 = 0.f, s1 = 0.f;
+  for (long long i = b + threadIdx.x; i < e; i += 256) {
+    const float r = c[i] * rs, m = mask[i];
+    const float mr = r * m;
+    raw[i] = r;
+    masked[i] = mr;
+    x_cf[i] = fminf(fmaxf(x[i] + mr, -1.f), 1.f);
+    s0 += fabsf(mr);
+    s1 += fabsf(r * (1.f - m));
+  }
+  __shared__ float red[2][8];
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, d = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; d += red[1][w]; }
+    part[blockIdx.x * 2 + 0] = a;
+    part[blockIdx.x * 2 + 1] = d;
+  }
+}
+void residual_head_fwd(const float* c, const float* x, const float* mask, float rs, long long n, float* raw,
+                       float* masked, float* x_cf, float* part, cudaStream_t s) {
+  residual_head_fwd_kernel<<<STAT_PARTS, 256, 0, s>>>(c, x, mask, rs, n, raw, masked, x_cf, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+template <typename T>
+__global__ void residual_head_bwd_kernel(const float* __restrict__ dxd, int dxd_ch, const float* __restrict__ dxc,
+                                         const float* __restrict__ raw, const float* __restrict__ x,
+                                         const float* __restrict__ mask, float rs, float lreg, float lmask,
+                                         long long n, T* __restrict__ g_c) {
+  const float inv_n = 1.f / (float)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float r = raw[i], m = mask[i];
+    const float mr = r * m;
+    const float pre = x[i] + mr;
+    const float pass = (pre >= -1.f && pre <= 1.f) ? 1.f : 0.f;
+    const float dxcf = dxd[i * dxd_ch] + dxc[i];
+    const float d_masked = pass * dxcf + lreg * sgn(mr) * inv_n;
+    const float d_raw = d_masked * m + lmask * sgn(r * (1.f - m)) * (1.f - m) * inv_n;
+    g_c[i] = from_f<T>(rs * d_raw);
+  }
+}
+template <typename T>
+void residual_head_bwd(const float* dxd, int dxd_ch, const float* dxc, const float* raw, const float* x,
+                       const float* mask, float rs, float lreg, float lmask, long long n, T* g_c, cudaStream_t s) {
+  residual_head_bwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>(dxd, dxd_ch, dxc, raw, x, mask, rs, lreg, lmask, n, g_c);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// discriminator head, BCE, CE
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void d_head_fwd_kernel(const T* __restrict__ z, int B, int HW, int C, const float* __restrict__ w,
+                                  const float* __restrict__ b, float* __restrict__ logits) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= B) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float m = 0.f;
+    for (int p = 0; p < HW; ++p) m += to_f(z[((size_t)n * HW + p) * C + c]);
+    s = fmaf(m / (float)HW, w[c], s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) logits[n] = s + b[0];
+}
+template <typename T>
+void d_head_fwd(const T* z, int B, int HW, int C, const float* w, const float* b, float* logits, cudaStream_t s) {
+  d_head_fwd_kernel<T><<<cdiv(B, 8), 256, 0, s>>>(z, B, HW, C, w, b, logits);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__device__ __forceinline__ float block_sum_1024(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;   // valid in warp 0
+}
+
+// one block per segment
+__global__ void bce_logits_kernel(const float* __restrict__ logits, int seg, float t0, float t1, float w0, float w1,
+                                  float* out_loss, float* out_p, float* __restrict__ dlogit) {
+  __shared__ float red[32];
+  const int sidx = blockIdx.x;
+  const float t = sidx == 0 ? t0 : t1, wgt = sidx == 0 ? w0 : w1;
+  float sl = 0.f, sp = 0.f;
+  for (int i = threadIdx.x; i < seg; i += blockDim.x) {
+    const float z = logits[sidx * seg + i];
+    const float sig = 1.f / (1.f + expf(-z));
+    sl += fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
+    sp += sig;
+    dlogit[sidx * seg + i] = wgt * (sig - t) / (float)seg;
+  }
+  sl = block_sum_1024(sl, red);
+  sp = block_sum_1024(sp, red);
+  if (threadIdx.x == 0) {
+    out_loss[sidx] = sl / (float)seg;
+    out_p[sidx] = sp / (float)seg;
+  }
+}
+void bce_logits(const float* logits, int seg, int nseg, float t0, float t1, float w0, float w1, float* out_loss,
+                float* out_p, float* dlogit, cudaStream_t s) {
+  PCG_REQUIRE(nseg == 1 || nseg == 2, "1 or 2 segments");
+  bce_logits_kernel<<<nseg, 256, 0, s>>>(logits, seg, t0, t1, w0, w1, out_loss, out_p, dlogit);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// grid.x = B (one block per sample) for g; dw/db by a second tiny kernel.
+template <typename T>
+__global__ void d_head_bwd_kernel(const T* __restrict__ z, const float* __restrict__ dlogit, int HW, int C,
+                                  const float* __restrict__ w, float slope, T* __restrict__ g) {
+  const int n = blockIdx.x;
+  const float dl = dlogit[n] / (float)HW;
+  for (int i = threadIdx.x; i < HW * C; i += blockDim.x) {
+    const int c = i % C;
+    const float zz = to_f(z[(size_t)n * HW * C + i]);
+    g[(size_t)n * HW * C + i] = from_f<T>(dl * w[c] * (zz > 0.f ? 1.f : slope));
+  }
+}
+template <typename T>
+__global__ void d_head_wgrad_kernel(const T* __restrict__ z, const float* __restrict__ dlogit, int B, int HW, int C,
+                                    float* __restrict__ dw, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float s = 0.f;
+    for (int n = 0; n < B; ++n) {
+      float m = 0.f;
+      for (int p = 0; p < HW; ++p) m += to_f(z[((size_t)n * HW + p) * C + c]);
+      s = fmaf(dlogit[n], m / (float)HW, s);
+    }
+    dw[c] = s;
+  }
+  if (c == 0) {
+    float s = 0.f;
+    for (int n = 0; n < B; ++n) s += dlogit[n];
+    db[0] = s;
+  }
+}
+template <typename T>
+void d_head_bwd(const T* z, const float* dlogit, int B, int HW, int C, const float* w, float slope, T* g, float* dw,
+                float* db, cudaStream_t s) {
+  d_head_bwd_kernel<T><<<B, 256, 0, s>>>(z, dlogit, HW, C, w, slope, g);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+  if (dw != nullptr) {
+    d_head_wgrad_kernel<T><<<cdiv(C, 64), 64, 0, s>>>(z, dlogit, B, HW, C, dw, db);
+    PCG_COUNT_LAUNCH();
+    PCG_LAUNCH_CHECK();
+  }
+}
+
+__global__ void ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int B, int NC,
+                               float wgt, float* loss, float* __restrict__ dlogits) {
+  __shared__ float red[32];
+  float sl = 0.f;
+  for (int n = threadIdx.x; n < B; n += blockDim.x) {
+    const float* l = logits + (size_t)n * NC;
+    float mx = l[0];
+    for (int j = 1; j < NC; ++j) mx = fmaxf(mx, l[j]);
+    float se = 0.f;
+    for (int j = 0; j < NC; ++j) se += expf(l[j] - mx);
+    const float lse = mx + logf(se);
+    const int t = (int)target[n];
+    sl += lse - l[t];
+    for (int j = 0; j < NC; ++j) {
+      const float p = expf(l[j] - lse);
+      dlogits[(size_t)n * NC + j] = wgt * (p - (j == t ? 1.f : 0.f)) / (float)B;
+    }
+  }
+  sl = block_sum_1024(sl, red);
+  if (threadIdx.x == 0) loss[0] = sl / (float)B;
+}
+void ce_loss(const float* logits, const long long* target, int B, int NC, float wgt, float* loss, float* dlogits,
+             cudaStream_t s) {
+  ce_loss_kernel<<<1, 256, 0, s>>>(logits, target, B, NC, wgt, loss, dlogits);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__global__ void l1_finalize_kernel(const float* __restrict__ part, int nparts, float inv_n, float* out2) {
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int i = 0; i < nparts; ++i) s += (double)part[i * 2 + threadIdx.x];
+    out2[threadIdx.x] = (float)(s * (double)inv_n);
+  }
+}
+void l1_finalize(const float* part, int nparts, float inv_n, float* out2, cudaStream_t s) {
+  l1_finalize_kernel<<<1, 32, 0, s>>>(part, nparts, inv_n, out2);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__global__ void g_loss_combine_kernel(const float* g_adv, const float* g_cls, const float* reg, const float* mpen,
+                                      float la, float lc, float lr, float lm, float* out) {
+  out[0] = la * g_adv[0] + lc * g_cls[0] + lr * reg[0] + lm * mpen[0];
+}
+void g_loss_combine(const float* g_adv, const float* g_cls, const float* reg, const float* mpen, float la, float lc,
+                    float lr, float lm, float* out, cudaStream_t s) {
+  g_loss_combine_kernel<<<1, 1, 0, s>>>(g_adv, g_cls, reg, mpen, la, lc, lr, lm, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 long long n, const int* __restrict__ step, float lr, float beta1, float beta2, float eps,
+                 float grad_scale) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step + 1);
+    const double bc1 = 1.0 - pow((double)beta1, t);
+    const double bc2 = 1.0 - pow((double)beta2, t);
+    s_step_size = (float)((double)lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.f - beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * beta2 + (1.f - beta2) * gi * gi;           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);              // param.addcdiv_(exp_avg, denom, -step_size)
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+__global__ void adam_step_inc_kernel(int* step) { *step += 1; }
+
+void adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
+               float beta2, float eps, float grad_scale, cudaStream_t s) {
+  adam_flat_kernel<<<ew_blocks(n), 256, 0, s>>>(p, g, m, v, n, step, lr, beta1, beta2, eps, grad_scale);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+  adam_step_inc_kernel<<<1, 1, 0, s>>>(step);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void fill_zero_kernel(T* p, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = from_f<T>(0.f);
+}
+template <typename T>
+void fill_zero(T* p, long long n, cudaStream_t s) {
+  fill_zero_kernel<T><<<ew_blocks(n), 256, 0, s>>>(p, n);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, long long n, T* __restrict__ dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f<T>(src[i]);
+}
+template <typename T>
+void convert_from_f32(const float* src, long long n, T* dst, cudaStream_t s) {
+  convert_kernel<T><<<ew_blocks(n), 256, 0, s>>>(src, n, dst);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+#define INST(T)                                                                                                    \
+  template void bn_stats_partial<T>(const T*, long long, int, float*, cudaStream_t);                               \
+  template void bn_apply_act<T>(const T*, const float*, const float*, long long, int, int, float, T*, cudaStream_t); \
+  template void bn_apply_residual<T>(const T*, const T*, const float*, const float*, float, long long, int, T*,    \
+                                     cudaStream_t);                                                                \
+  template void bn_bwd_partial<T>(const T*, const T*, const float*, const float*, const float*, const float*,      \
+                                  float, int, float, long long, int, float*, cudaStream_t);                        \
+  template void bn_bwd_apply<T>(const T*, const T*, const float*, const float*, const float*, const float*,        \
+                                const float*, const float*, float, int, float, long long, int, T*, float*,          \
+                                cudaStream_t);                                                                     \
+  template void colsum_partial<T>(const T*, long long, int, float*, cudaStream_t);                                 \
+  template void g_input<T>(const float*, const float*, const long long*, const float*, int, int, T*, cudaStream_t); \
+  template void d_input<T>(const float*, const float*, const long long*, int, int, T*, cudaStream_t);              \
+  template void embed_grad<T>(const T*, int, int, const long long*, int, int, int, float*, cudaStream_t);          \
+  template void residual_head_bwd<T>(const float*, int, const float*, const float*, const float*, const float*,    \
+                                     float, float, float, long long, T*, cudaStream_t);                            \
+  template void d_head_fwd<T>(const T*, int, int, int, const float*, const float*, float*, cudaStream_t);          \
+  template void d_head_bwd<T>(const T*, const float*, int, int, int, const float*, float, T*, float*, float*,      \
+                              cudaStream_t);                                                                       \
+  template void fill_zero<T>(T*, long long, cudaStream_t);                                                         \
+  template void convert_from_f32<T>(const float*, long long, T*, cudaStream_t);
+INST(float)
+INST(bf16)
+#undef INST
+
+}  // namespace pcg

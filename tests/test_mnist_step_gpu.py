@@ -1,0 +1,165 @@
+"""GPU parity of the native MNIST CounteRGAN step against the CPU oracle (same seeded inputs).
+
+Tolerances (max-norm relative error, |a-b|_inf / |b|_inf):
+  fp32 mode  (CUDA-core kernels)          activations 2e-5, gradients 2e-4, parameters after Adam see below
+  bf16 mode  (tcgen05, bf16 storage)      activations 2e-2, gradients 6e-2
+Adam turns a gradient g into a step of size ~lr*sign(g) for the first iterations, so an element whose
+gradient is within rounding error of zero may legitimately move by +lr on one side and -lr on the other.
+Post-update parameters are therefore compared through the update itself with a robust norm:
+mean_i |dp_native_i - dp_oracle_i| <= upd_tol * lr   (fp32: 0.02, bf16: 0.1).
+"""
+import ctypes
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from oracle import mnist_countergan as O
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def nhwc_to_nchw(flat, B, C, H=28, W=28):
+    return flat.view(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+
+
+class Harness:
+    def __init__(self, B, base_ch, nres, precision, seed=0, pollute=False, hp=None):
+        import pcg_b200  # noqa: F401
+        from pcg_b200.mnist import plan as P
+        self.P = P
+        self.B, self.ch, self.nres = B, base_ch, nres
+        dev = "cuda"
+        self.PG = O.synth_params(O.g_param_shapes(base_ch, nres), seed + 1, "G")
+        self.PD = O.synth_params(O.d_param_shapes(), seed + 2, "D")
+        self.PC = O.synth_params(O.c_param_shapes(), seed + 3, "C")
+        self.BG = O.g_buffers(base_ch, nres)
+        self.S = O.make_state(self.PG, self.BG, self.PD, self.PC)
+        self.hp = hp or O.Hyper()
+        self.ga = P.Arena(0, base_ch, nres, dev).load_dict([v.to(dev) for v in self.PG.values()])
+        self.da = P.Arena(1, base_ch, nres, dev).load_dict([v.to(dev) for v in self.PD.values()])
+        self.ca = P.Arena(2, base_ch, nres, dev).load_dict([v.to(dev) for v in self.PC.values()])
+        self.bn_running = torch.zeros(2 * nres, 2, base_ch, device=dev)
+        self.bn_running[:, 1] = 1.0
+        self.bn_nbt = torch.zeros(2 * nres, dtype=torch.int64, device=dev)
+        cfg = P.StepConfig(precision=precision, pollute_d_grads=pollute, g_lr=self.hp.g_lr, d_lr=self.hp.d_lr,
+                           lambda_adv=self.hp.lambda_adv, lambda_cls=self.hp.lambda_cls,
+                           lambda_reg=self.hp.lambda_reg, lambda_mask=self.hp.lambda_mask)
+        self.plan = P.MnistStepPlan(B, self.ga, self.da, self.ca, self.bn_running, self.bn_nbt, cfg, base_ch, nres)
+
+    def arena_dict(self, arena, shapes, grad=False):
+        return OrderedDict((k, arena.view(i, shp, grad=grad).detach().cpu().clone())
+                           for i, (k, shp) in enumerate(shapes.items()))
+
+    def g_shapes(self):
+        return O.g_param_shapes(self.ch, self.nres)
+
+
+def _check(report, name, got, exp, tol):
+    e = relerr(got, exp)
+    report.append((name, e, tol))
+    return e <= tol
+
+
+def _run_step_compare(B, ch, nres, precision, act_tol, grad_tol, upd_tol, n_steps=1, mnist_like=False, seed=0):
+    H = Harness(B, ch, nres, precision, seed)
+    report, ok = [], True
+    for step in range(n_steps):
+        x, y, t, mask = O.synth_batch(B, 500 + seed + step, mnist_like=mnist_like or (step % 2 == 1))
+        p_before_g = {k: v.detach().clone() for k, v in H.S["G"].items()}
+        p_before_d = {k: v.detach().clone() for k, v in H.S["D"].items()}
+        taps = {}
+        sc, gr = O.countergan_step(H.S, x, y, t, mask, H.hp, n_resblocks=nres, taps=taps)
+        xd, yd, td, md = x.cuda(), y.cuda(), t.cuda(), mask.cuda().contiguous()
+        # run the phases separately so gradients can be read before Adam consumes them
+        H.plan.step_d_grads(xd, yd, td, md)
+        torch.cuda.synchronize()
+        gD = H.arena_dict(H.da, O.d_param_shapes(), grad=True)
+        if step == 0:
+            ok &= _check(report, "h0", nhwc_to_nchw(H.plan.debug_tensor("h.0"), B, ch), taps["h0"], act_tol)
+            for i in range(nres):
+                ok &= _check(report, f"y1.{i}", nhwc_to_nchw(H.plan.debug_tensor(f"y1.{i}"), B, ch), taps[f"y1.{i}"], act_tol)
+                ok &= _check(report, f"z1.{i}", nhwc_to_nchw(H.plan.debug_tensor(f"z1.{i}"), B, ch), taps[f"z1.{i}"], act_tol)
+                ok &= _check(report, f"y2.{i}", nhwc_to_nchw(H.plan.debug_tensor(f"y2.{i}"), B, ch), taps[f"y2.{i}"], act_tol)
+                ok &= _check(report, f"h.{i+1}", nhwc_to_nchw(H.plan.debug_tensor(f"h.{i+1}"), B, ch), taps[f"h.{i+1}"], act_tol)
+            ok &= _check(report, "hm", nhwc_to_nchw(H.plan.debug_tensor("hm"), B, ch), taps["hm"], act_tol)
+            ok &= _check(report, "raw", H.plan.debug_tensor("raw").view(B, 1, 28, 28), gr["raw"], act_tol)
+            ok &= _check(report, "x_cf", H.plan.debug_tensor("x_cf").view(B, 1, 28, 28), gr["x_cf"], act_tol)
+            ok &= _check(report, "d_logits", H.plan.debug_tensor("d_logits").view(2 * B, 1),
+                         torch.cat([gr["d_real"], gr["d_fake"]]), act_tol * 5)
+        for k in gD:
+            ok &= _check(report, f"s{step} dD/{k}", gD[k], gr["D"][k], grad_tol)
+        H.plan.step_d_update()
+        H.plan.step_g_grads(xd, yd, td, md)
+        torch.cuda.synchronize()
+        gG = H.arena_dict(H.ga, H.g_shapes(), grad=True)
+        for k in gG:
+            if O.is_bn_shadowed_bias(k):
+                # analytically zero; both sides hold rounding noise
+                scale = max(gr["G"][k.replace("bias", "weight")].abs().max().item(), 1e-12)
+                e = gG[k].abs().max().item() / scale
+                report.append((f"s{step} dG/{k} (zero-grad noise / |dW|)", e, 1e-2))
+                ok &= e <= 1e-2
+                continue
+            ok &= _check(report, f"s{step} dG/{k}", gG[k], gr["G"][k], grad_tol)
+        H.plan.step_g_update()
+        torch.cuda.synchronize()
+        # scalars
+        got = H.plan.scalars_dict()
+        for k, v in sc.items():
+            e = abs(got[k] - v) / (abs(v) + 1e-12)
+            report.append((f"s{step} scalar/{k}", e, act_tol * 20))
+            ok &= e <= act_tol * 20
+        # parameter updates, measured in units of lr
+        for (arena, shapes, S_key, before, lr) in ((H.da, O.d_param_shapes(), "D", p_before_d, H.hp.d_lr),
+                                                  (H.ga, H.g_shapes(), "G", p_before_g, H.hp.g_lr)):
+            now = H.arena_dict(arena, shapes)
+            for k in now:
+                if O.is_bn_shadowed_bias(k):
+                    continue
+                d_nat = now[k] - before[k]
+                d_or = H.S[S_key][k].detach() - before[k]
+                e = ((d_nat - d_or).abs().mean() / lr).item()
+                report.append((f"s{step} upd/{S_key}/{k} (mean |diff| in units of lr)", e, upd_tol))
+                ok &= e <= upd_tol
+    # BN running stats
+    for i in range(nres):
+        for j in (1, 2):
+            rm = H.bn_running[2 * i + (j - 1), 0].cpu()
+            rv = H.bn_running[2 * i + (j - 1), 1].cpu()
+            ok &= _check(report, f"bn{j}.{i}.running_mean", rm, H.S["GB"][f"resblocks.{i}.bn{j}.running_mean"], act_tol * 5)
+            ok &= _check(report, f"bn{j}.{i}.running_var", rv, H.S["GB"][f"resblocks.{i}.bn{j}.running_var"], act_tol * 5)
+    assert int(H.bn_nbt[0].item()) == n_steps
+    bad = [r for r in report if not r[1] <= r[2]]
+    worst = sorted(report, key=lambda r: -(r[1] / r[2]))[:8]
+    msg = "\n".join(f"{n}: err {e:.3e} tol {t:.1e}" for n, e, t in (bad[:40] or worst))
+    print(f"[{precision} B={B} ch={ch} nres={nres}] {len(report)} checks, {len(bad)} failed; worst:\n" +
+          "\n".join(f"   {n}: {e:.3e} (tol {t:.1e})" for n, e, t in worst))
+    assert ok, msg
+
+
+def test_step_fp32_small():
+    _run_step_compare(B=8, ch=16, nres=2, precision="fp32", act_tol=2e-5, grad_tol=2e-4, upd_tol=0.02, n_steps=3)
+
+
+def test_step_fp32_full_arch():
+    _run_step_compare(B=8, ch=64, nres=6, precision="fp32", act_tol=2e-5, grad_tol=2e-4, upd_tol=0.02, n_steps=2)
+
+
+def test_step_fp32_ragged_batch():
+    _run_step_compare(B=3, ch=64, nres=2, precision="fp32", act_tol=2e-5, grad_tol=2e-4, upd_tol=0.02, n_steps=1,
+                      mnist_like=True)
+
+
+def test_step_bf16_full_arch():
+    _run_step_compare(B=16, ch=64, nres=6, precision="bf16", act_tol=3e-2, grad_tol=8e-2, upd_tol=0.1, n_steps=2)
+
+
+def test_step_bf16_ragged_batch():
+    _run_step_compare(B=5, ch=64, nres=2, precision="bf16", act_tol=3e-2, grad_tol=8e-2, upd_tol=0.1, n_steps=1,
+                      mnist_like=True)
