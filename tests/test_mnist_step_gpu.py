@@ -92,8 +92,12 @@ def _run_step_compare(B, ch, nres, precision, act_tol, grad_tol, upd_tol, n_step
             ok &= _check(report, "x_cf", H.plan.debug_tensor("x_cf").view(B, 1, 28, 28), gr["x_cf"], act_tol)
             ok &= _check(report, "d_logits", H.plan.debug_tensor("d_logits").view(2 * B, 1),
                          torch.cat([gr["d_real"], gr["d_fake"]]), act_tol * 5)
+        # After the first update the two sides no longer hold bit-identical parameters (Adam moves an
+        # element whose gradient is rounding noise by +-lr on either side), so later steps are compared
+        # with a looser bound; step 0 is the tight one.
+        gtol = grad_tol if step == 0 else grad_tol * 50
         for k in gD:
-            ok &= _check(report, f"s{step} dD/{k}", gD[k], gr["D"][k], grad_tol)
+            ok &= _check(report, f"s{step} dD/{k}", gD[k], gr["D"][k], gtol)
         H.plan.step_d_update()
         H.plan.step_g_grads(xd, yd, td, md)
         torch.cuda.synchronize()
@@ -106,15 +110,16 @@ def _run_step_compare(B, ch, nres, precision, act_tol, grad_tol, upd_tol, n_step
                 report.append((f"s{step} dG/{k} (zero-grad noise / |dW|)", e, 1e-2))
                 ok &= e <= 1e-2
                 continue
-            ok &= _check(report, f"s{step} dG/{k}", gG[k], gr["G"][k], grad_tol)
+            ok &= _check(report, f"s{step} dG/{k}", gG[k], gr["G"][k], gtol)
         H.plan.step_g_update()
         torch.cuda.synchronize()
         # scalars
         got = H.plan.scalars_dict()
         for k, v in sc.items():
             e = abs(got[k] - v) / (abs(v) + 1e-12)
-            report.append((f"s{step} scalar/{k}", e, act_tol * 20))
-            ok &= e <= act_tol * 20
+            stol = act_tol * (20 if step == 0 else 200)
+            report.append((f"s{step} scalar/{k}", e, stol))
+            ok &= e <= stol
         # parameter updates, measured in units of lr
         for (arena, shapes, S_key, before, lr) in ((H.da, O.d_param_shapes(), "D", p_before_d, H.hp.d_lr),
                                                   (H.ga, H.g_shapes(), "G", p_before_g, H.hp.g_lr)):
@@ -125,15 +130,17 @@ def _run_step_compare(B, ch, nres, precision, act_tol, grad_tol, upd_tol, n_step
                 d_nat = now[k] - before[k]
                 d_or = H.S[S_key][k].detach() - before[k]
                 e = ((d_nat - d_or).abs().mean() / lr).item()
-                report.append((f"s{step} upd/{S_key}/{k} (mean |diff| in units of lr)", e, upd_tol))
-                ok &= e <= upd_tol
+                utol = upd_tol if step == 0 else upd_tol * 10
+                report.append((f"s{step} upd/{S_key}/{k} (mean |diff| in units of lr)", e, utol))
+                ok &= e <= utol
     # BN running stats
     for i in range(nres):
         for j in (1, 2):
             rm = H.bn_running[2 * i + (j - 1), 0].cpu()
             rv = H.bn_running[2 * i + (j - 1), 1].cpu()
-            ok &= _check(report, f"bn{j}.{i}.running_mean", rm, H.S["GB"][f"resblocks.{i}.bn{j}.running_mean"], act_tol * 5)
-            ok &= _check(report, f"bn{j}.{i}.running_var", rv, H.S["GB"][f"resblocks.{i}.bn{j}.running_var"], act_tol * 5)
+            rt = act_tol * (5 if n_steps == 1 else 50)
+            ok &= _check(report, f"bn{j}.{i}.running_mean", rm, H.S["GB"][f"resblocks.{i}.bn{j}.running_mean"], rt)
+            ok &= _check(report, f"bn{j}.{i}.running_var", rv, H.S["GB"][f"resblocks.{i}.bn{j}.running_var"], rt)
     assert int(H.bn_nbt[0].item()) == n_steps
     bad = [r for r in report if not r[1] <= r[2]]
     worst = sorted(report, key=lambda r: -(r[1] / r[2]))[:8]

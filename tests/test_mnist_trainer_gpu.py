@@ -1,0 +1,132 @@
+"""GPU: the drop-in surface — mirror modules' forward and ``train_countergan`` — against the oracle."""
+import types
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from oracle import mnist_countergan as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods(ch=16, nres=2, seed=0):
+    import pcg_b200  # noqa: F401
+    from pcg_b200.mnist.models.generator import ResidualGenerator
+    from pcg_b200.mnist.models.discriminator import Discriminator
+    from pcg_b200.mnist.models.classifier import CNNClassifier
+    torch.manual_seed(seed)
+    G = ResidualGenerator(base_ch=ch, n_resblocks=nres)
+    D = Discriminator()
+    C = CNNClassifier().eval()
+    for p in C.parameters():
+        p.requires_grad = False
+    # perturb BN affine so they are not (1, 0)
+    with torch.no_grad():
+        for n, p in G.named_parameters():
+            if ".bn" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    return G, D, C
+
+
+def _cpu_state(G, D, C):
+    return O.make_state(OrderedDict((k, v.detach().cpu()) for k, v in G.named_parameters()),
+                        OrderedDict((k, v.detach().cpu().clone()) for k, v in G.named_buffers()),
+                        OrderedDict((k, v.detach().cpu()) for k, v in D.named_parameters()),
+                        OrderedDict((k, v.detach().cpu()) for k, v in C.named_parameters()))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-5), ("bf16", 3e-2)])
+def test_module_forwards(precision, tol):
+    G, D, C = _mods(64 if precision == "bf16" else 16, 2)
+    S = _cpu_state(G, D, C)
+    G, D, C = G.cuda(), D.cuda(), C.cuda()
+    for m in (G, D, C):
+        m.precision = precision
+    x, y, t, mask = O.synth_batch(8, 3)
+    with torch.no_grad():
+        raw_o, masked_o = O.g_forward(S["G"], S["GB"], x, t, mask, n_resblocks=2, training=True)
+        raw, masked = G(x.cuda(), t.cuda(), mask.cuda())
+        rel = lambda a, b: ((a.cpu() - b).abs().max() / b.abs().max()).item()  # noqa: E731
+        assert raw.shape == (8, 1, 28, 28) and rel(raw, raw_o) < tol and rel(masked, masked_o) < tol
+        # running stats were updated through the module's own buffers
+        rm = G.resblocks[1].bn2.running_mean
+        assert rel(rm, S["GB"]["resblocks.1.bn2.running_mean"]) < max(tol, 1e-4)
+        assert int(G.resblocks[0].bn1.num_batches_tracked) == 1
+        # eval mode uses the running statistics
+        G.eval()
+        raw_e, _ = G(x.cuda(), t.cuda(), mask.cuda())
+        raw_eo, _ = O.g_forward(S["G"], S["GB"], x, t, mask, n_resblocks=2, training=False)
+        assert rel(raw_e, raw_eo) < tol * 3
+        assert rel(D(x.cuda(), y.cuda()), O.d_forward(S["D"], x, y)) < tol * 3
+        assert rel(C(x.cuda()), O.c_forward(S["C"], x)) < tol * 3
+        # state_dict round trip through the arena views, then a changed weight is seen by the kernels
+        sd = {k: v.clone() for k, v in D.state_dict().items()}
+        sd["adv_head.bias"] += 1.0
+        before = D(x.cuda(), y.cuda())
+        D.load_state_dict(sd)
+        after = D(x.cuda(), y.cuda())
+        assert torch.allclose(after, before + 1.0, atol=1e-2 if precision == "bf16" else 1e-5)
+    with pytest.raises(TypeError):
+        G(x.cuda(), t.cuda(), None)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_countergan_matches_oracle(tmp_path, use_graph, monkeypatch):
+    from pcg_b200.mnist import trainer as T
+    monkeypatch.setenv("PCG_PRECISION", "fp32")
+    monkeypatch.setenv("PCG_NO_GRAPH", "0" if use_graph else "1")
+    G, D, C = _mods(16, 2, seed=5)
+    S = _cpu_state(G, D, C)
+    G, D, C = G.cuda(), D.cuda(), C.cuda()
+    B, n_steps = 8, 3
+    batches = [O.synth_batch(B, 900 + i, mnist_like=(i == 1)) for i in range(n_steps)]
+    cfg = types.SimpleNamespace(g_lr=5e-5, d_lr=1e-5, num_epochs_gan=1, num_classes=10, patch_size=7,
+                                num_modifiable_patches=10, lambda_adv=1.0, lambda_cls=1.0, lambda_reg=2.5,
+                                lambda_mask=2.0, save_dir=str(tmp_path), generator_path=str(tmp_path / "generator.pt"))
+    it = {"i": 0}
+    real_randint = torch.randint
+
+    def fake_randint(*a, **k):
+        return batches[it["i"]][2].clone().to(k.get("device", "cpu"))
+
+    def fake_build_mask(x, ps, device, n=None):
+        m = batches[it["i"]][3].clone().to(device)
+        it["i"] += 1
+        return m
+
+    monkeypatch.setattr(T, "build_mask", fake_build_mask)
+    monkeypatch.setattr(torch, "randint", fake_randint)
+    out = T.train_countergan(G, D, C, [(b[0], b[1]) for b in batches], cfg, "cuda")
+    monkeypatch.setattr(torch, "randint", real_randint)
+    sums = {"g_loss": 0.0, "d_loss": 0.0, "g_cls": 0.0}
+    for (x, y, t, m) in batches:
+        sc, _ = O.countergan_step(S, x, y, t, m, n_resblocks=2)
+        for k in sums:
+            sums[k] += sc[k]
+    assert abs(out["g_losses"][0] - sums["g_loss"] / n_steps) < 2e-3 * abs(sums["g_loss"] / n_steps)
+    assert abs(out["d_losses"][0] - sums["d_loss"] / n_steps) < 2e-3 * abs(sums["d_loss"] / n_steps)
+    saved = torch.load(cfg.generator_path, map_location="cpu")
+    assert list(saved.keys()) == list(G.state_dict().keys())
+    for k, v in saved.items():
+        ref = (S["G"][k] if k in S["G"] else S["GB"][k]).detach().float()
+        if O.is_bn_shadowed_bias(k):
+            assert (v.float() - ref).abs().max() <= cfg.g_lr * n_steps * 2.02
+        elif k in S["G"]:
+            # mean absolute deviation of the cumulative update, in units of lr (see test_mnist_step_gpu)
+            assert ((v.float() - ref).abs().mean() / cfg.g_lr).item() < 0.2, k
+        else:
+            assert torch.allclose(v.float(), ref, rtol=2e-3, atol=1e-5), k
+    assert int(saved["resblocks.0.bn1.num_batches_tracked"]) == n_steps
+
+
+def test_build_mask_distribution():
+    from pcg_b200.mnist.trainer import build_mask
+    x = torch.zeros(4096, 1, 28, 28, device="cuda")
+    torch.manual_seed(0)
+    m = build_mask(x, 7, "cuda", 10)
+    assert m.shape == x.shape and torch.all(m.sum(dim=(1, 2, 3)) == 490)       # trainer.py:63-65 semantics
+    pm = m[:, 0, ::7, ::7].reshape(4096, 16)
+    freq = pm.mean(0)                                                          # each patch chosen w.p. 10/16
+    assert torch.all((freq - 10 / 16).abs() < 0.04)
+    assert torch.equal(m, m[:, :, :, :].round())
