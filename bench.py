@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one full G+D training iteration of the MNIST conv CounteRGAN
+(conditional_counteRGAN/mnist/trainer.py:89-132) at batch 512 per GPU, synthetic 1x28x28 inputs.
+
+    python bench.py --gpus N --steps K --warmup W            # native arm (libpcg, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the
+                                                             # reference's step on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM, `e2e` = the same
+through the user-facing trainer call with pinned host batches copied in and the loss scalars read
+back every step.  See DESIGN.md §Measurement for how every field is produced.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "conditional_counteRGAN/mnist conv CounteRGAN, frozen CNN classifier, synthetic 1x28x28, batch 512/GPU"
+METRIC = "GAN train samples/sec (G+D step) on MNIST CounteRGAN"
+BATCH = 512
+CPU_SAMPLE_BATCH = 128          # reference default batch_size (config.py:4); bounds the CPU arm's step time
+
+# algorithmic work of the dominant kernel: 64->64 3x3 conv over B*784 pixels
+CONV_FLOPS = 2.0 * BATCH * 784 * 64 * 576
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_step_rate(steps, warmup, batch=CPU_SAMPLE_BATCH, threads=None):
+    """Times the oracle port of the reference step (oracle/mnist_countergan.py) on the host cores."""
+    import torch
+    from oracle import mnist_countergan as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    PG = O.synth_params(O.g_param_shapes(), 1, "G")
+    PD = O.synth_params(O.d_param_shapes(), 2, "D")
+    PC = O.synth_params(O.c_param_shapes(), 3, "C")
+    S = O.make_state(PG, O.g_buffers(), PD, PC)
+    batches = [O.synth_batch(batch, 10 + i) for i in range(2)]
+    for i in range(warmup):
+        O.countergan_step(S, *batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.countergan_step(S, *batches[i % 2])
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    # bound the whole run to a few minutes regardless of K: ~2 s per B=128 step on 8 cores
+    steps = min(steps, 40)
+    warmup = min(warmup, 3)
+    rate, ms, threads = cpu_step_rate(steps, warmup)
+    sample = (f"oracle port of trainer.py:89-132 (torch CPU fp32), {steps} steps of B={CPU_SAMPLE_BATCH} "
+              f"after {warmup} warm-up, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cpu_batch_per_step": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import _lib
+    from pcg_b200.mnist import trainer as T
+    from pcg_b200.mnist.models.classifier import CNNClassifier
+    from pcg_b200.mnist.models.discriminator import Discriminator
+    from pcg_b200.mnist.models.generator import ResidualGenerator
+    from oracle import mnist_countergan as O      # synthetic batch generator only (inputs, not compute)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: libpcg has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.load()
+
+    torch.manual_seed(0)                          # identical replicas on every rank
+    G = ResidualGenerator().to(dev)
+    D = Discriminator().to(dev)
+    C = CNNClassifier().to(dev).eval()
+    for p in C.parameters():
+        p.requires_grad = False
+    import types
+    cfg = types.SimpleNamespace(g_lr=5e-5, d_lr=1e-5, num_classes=10, patch_size=7, num_modifiable_patches=10,
+                                lambda_adv=1.0, lambda_cls=1.0, lambda_reg=2.5, lambda_mask=2.0)
+    tr = T.CounterGanTrainer(G, D, C, cfg, dev, precision=args.precision, use_graph=not args.no_graph)
+    T._warm_plan(tr, BATCH)
+
+    # ring of device-resident synthetic batches (per-rank seeds), cycled so no step reuses the previous inputs
+    ring = []
+    for i in range(4):
+        x, y, t, m = O.synth_batch(BATCH, 1000 * (rank + 1) + i, mnist_like=(i % 2 == 1))
+        ring.append(tuple(v.to(dev).contiguous() for v in (x, y, t, m)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # launches per step (counted on an eager, un-captured step)
+    tr_eager_graph = tr.use_graph
+    tr.use_graph = False
+    n0 = _lib.launch_count()
+    tr.step(*ring[0])
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+    tr.use_graph = tr_eager_graph
+
+    for i in range(max(args.warmup, 3)):
+        tr.step(*ring[i % 4])
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        p = tr.step(*ring[i % 4])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = BATCH * world * args.steps / (ms * 1e-3)
+    scal = p.scalars_dict()
+
+    # ---- e2e: pinned host batches -> H2D -> device-side target/mask draw -> step -> D2H scalars, every step
+    hx = [r[0].cpu().pin_memory() for r in ring]
+    hy = [r[1].cpu().pin_memory() for r in ring]
+    e2e_steps = max(args.steps, 5)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        x = hx[i % 4].to(dev, non_blocking=True)
+        y = hy[i % 4].to(dev, non_blocking=True)
+        tgt = torch.randint(0, 10, (BATCH,), device=dev)
+        mask = T.build_mask(x, 7, dev, 10)
+        p = tr.step(x, y, tgt, mask)
+        host_scal = p.scalars.cpu()               # D2H read of the losses (sync), as the reference's .item() calls
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = BATCH * world * e2e_steps / (t.item() * 1e-3)
+    h2d = hx[0].numel() * 4 + hy[0].numel() * 8
+    d2h = host_scal.numel() * 4
+
+    # ---- per-launcher device time inside the step (eager, CUDA events on the launching stream)
+    prof, roof = None, None
+    if rank == 0:
+        import ctypes
+        tr.use_graph = False
+        _lib.check(L.pcg_profile_begin())
+        nprof = 3
+        for i in range(nprof):
+            tr.step(*ring[i % 4])
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(L.pcg_profile_end(buf, ctypes.c_size_t(len(buf))))
+        prof = json.loads(buf.value.decode())
+        tot = sum(v["ms"] for v in prof.values())
+        for v in prof.values():
+            v["ms_per_step"] = v["ms"] / nprof
+            v["share"] = v["ms"] / tot if tot else 0.0
+            v["launches_per_step"] = v["launches"] / nprof
+        pk, which = peaks()
+        if "conv_tc_fprop" in prof:
+            # 64->64 fprop/dgrad launches dominate this launcher; D/C launches are counted with their own FLOPs below
+            k = prof["conv_tc_fprop"]
+            flops_per_step = flops_tc_fprop_per_step()
+            achieved = flops_per_step / (k["ms_per_step"] * 1e-3) / 1e12
+            peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            roof = {"bound": "tensor", "kernel": "conv_tc_fprop_kernel (tcgen05 implicit GEMM, fprop+dgrad)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside the step)",
+                    "avg_launch_us": k["ms"] / k["launches"] * 1e3}
+        tr.use_graph = tr_eager_graph
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            rate, _, threads = cpu_step_rate(3, 1)
+            cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                   "sample": f"oracle port of trainer.py:89-132, 3 steps of B={CPU_SAMPLE_BATCH} after 1 warm-up"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "cuda_graph": tr.use_graph, "l2": "working set (~3 GB of saved activations per step) >> 126 MB L2; "
+                       "4 rotating input batches"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "launches_per_step": int(launches_per_step),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in (prof or {}).items()},
+            "losses": {k: round(v, 5) for k, v in scal.items()},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def flops_tc_fprop_per_step():
+    """Algorithmic FLOPs executed by conv_tc_fprop launches in one step at B=512 (bf16 plan):
+    G: 13 fprop + 13 dgrad of the 64->64 conv; D (3 tensor-core layers): fwd on 2B + fwd on B; C: conv.4 + fc.1."""
+    g = 26 * CONV_FLOPS
+    d_layers = (49 * 128 * 576, 16 * 256 * 1152, 4 * 256 * 2304)
+    d = sum(2.0 * m for m in d_layers) * (3 * BATCH)
+    c = 2.0 * BATCH * (49 * 128 * 576 + 6272 * 256)
+    return g + d + c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PCG_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

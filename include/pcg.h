@@ -38,6 +38,12 @@ int pcg_version(void);
 /* Kernels launched by this library since load (bench.py "gpu_launches"). */
 unsigned long long pcg_launch_count(void);
 
+/* Per-launcher device timing: begin() enables CUDA-event brackets around every kernel launcher
+ * (not usable during graph capture); end() synchronises, disables, and writes a JSON object
+ * {"launcher": {"ms": total, "launches": n}, ...} into out (host buffer of cap bytes). */
+int pcg_profile_begin(void);
+int pcg_profile_end(char* out, size_t cap);
+
 /* Device-to-device copy on `stream` (test helper for reading plan-owned tensors). */
 int pcg_memcpy_d2d(void* dst, const void* src, size_t nbytes, void* stream);
 
@@ -95,6 +101,8 @@ typedef struct pcg_mnist_config {
   float lambda_adv, lambda_cls, lambda_reg, lambda_mask;   /* config.py:12-15                    */
   float residual_scaling; /* generator.py:33 (0.1)                                               */
   float grad_scale;       /* gradients are multiplied by this before Adam (1/world_size)         */
+  int use_tensor_cores;   /* PCG_BF16 only: 0 keeps bf16 storage but runs every convolution on the CUDA-core
+                             kernels (A/B check of the tcgen05 path); 1 = tcgen05 where eligible        */
   int pollute_d_grads;    /* !=0: the G step also accumulates its weight gradients into d_grads,
                              as the reference's g_loss.backward() does (diagnostic only)         */
 } pcg_mnist_config;

@@ -4,10 +4,30 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 
+#include <string.h>
+
+#include <map>
+#include <vector>
+
 namespace pcg {
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 unsigned long long g_launch_count = 0;
+
+bool g_profile_on = false;
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
+  if (!g_profile_on) return;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, stream);
+}
+ProfileScope::~ProfileScope() {
+  if (e0 == nullptr) return;
+  cudaEventRecord(e1, stream);
+  g_prof.push_back({name, e0, e1});
+}
 
 int sm_count() {
   static int n = 0;
@@ -40,6 +60,46 @@ extern "C" {
 const char* pcg_last_error(void) { return t_last_error.c_str(); }
 int pcg_version(void) { return PCG_VERSION; }
 unsigned long long pcg_launch_count(void) { return g_launch_count; }
+
+int pcg_profile_begin(void) {
+  PCG_API_BEGIN
+  PCG_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_profile_on = true;
+  PCG_API_END
+}
+
+int pcg_profile_end(char* out, size_t cap) {
+  PCG_API_BEGIN
+  g_profile_on = false;
+  PCG_CHECK_CUDA(cudaDeviceSynchronize());
+  std::map<std::string, std::pair<double, int>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      auto& a = agg[r.name];
+      a.first += ms;
+      a.second += 1;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"ms\": %.6f, \"launches\": %d}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  PCG_REQUIRE(out != nullptr && js.size() + 1 <= cap, "profile buffer too small");
+  memcpy(out, js.c_str(), js.size() + 1);
+  PCG_API_END
+}
 
 int pcg_memcpy_d2d(void* dst, const void* src, size_t nbytes, void* stream) {
   PCG_API_BEGIN

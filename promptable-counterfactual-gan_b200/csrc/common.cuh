@@ -44,6 +44,20 @@ int sm_count();
 extern unsigned long long g_launch_count;
 #define PCG_COUNT_LAUNCH() (++::pcg::g_launch_count)
 
+// ---- optional per-launcher device timing (bench.py roofline / kernel-share breakdown) ----------
+// When enabled (pcg_profile_begin), every launcher brackets its kernels with CUDA events on the
+// launching stream; pcg_profile_end() synchronises and reports total ms + launch count per name.
+// Must be off during CUDA-graph capture.
+extern bool g_profile_on;
+struct ProfileScope {
+  const char* name;
+  cudaStream_t stream;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfileScope(const char* n, cudaStream_t s);
+  ~ProfileScope();
+};
+#define PCG_PROFILE(name, stream) ::pcg::ProfileScope _pcg_prof_scope(name, stream)
+
 // ---- storage-type conversion ---------------------------------------------------------------
 typedef __nv_bfloat16 bf16;
 

@@ -238,6 +238,7 @@ static EpiDev<TOut> to_dev(const GenEpilogue<TOut>& e) {
 template <int MODE, typename TIn, typename TOut>
 static void launch_conv(const TIn* src, const float* wgt, TOut* dst, long long M, int Nc, int K, int outH,
                         int outW, const Gather<MODE>& ga, const GenEpilogue<TOut>& epi, cudaStream_t stream) {
+  PCG_PROFILE("conv_generic", stream);
   const EpiDev<TOut> e = to_dev(epi);
   if (Nc <= 4) {
     const int blocks = (int)((M * 32 + 255) / 256 < (long long)sm_count() * 16 ? (M * 32 + 255) / 256
@@ -410,6 +411,7 @@ size_t conv_wgrad_generic_scratch(const ConvGeom& g) {
 template <typename TIn, typename TDy>
 void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float* scratch, float* dw,
                         cudaStream_t stream) {
+  PCG_PROFILE("wgrad_generic", stream);
   Gather<MODE_FPROP> ga;
   ga.srcH = g.H; ga.srcW = g.W; ga.srcC = g.Cin; ga.ksize = g.ksize; ga.stride = g.stride; ga.pad = g.pad;
   const long long P = g.Mout();
@@ -449,6 +451,7 @@ __global__ void pack_generic_kernel(const float* __restrict__ w, int Cout, int C
 
 void pack_conv_weights_generic(const float* w, int Cout, int Cin, int ksize, int perm_hw, float* wf, float* wd,
                                cudaStream_t stream) {
+  PCG_PROFILE("pack_weights", stream);
   const int total = Cout * Cin * ksize * ksize;
   int blocks = cdiv(total, 256);
   if (blocks > 1184) blocks = 1184;

@@ -367,6 +367,7 @@ int conv_tc_grid(long long M, int Cout) {
 template <int BN>
 static void launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int grid,
                          cudaStream_t stream) {
+  PCG_PROFILE("conv_tc_fprop", stream);
   using Cfg = FpropCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -555,6 +556,7 @@ int conv_tc_wgrad_grid(long long M) {
 
 void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* part,
                      cudaStream_t stream) {
+  PCG_PROFILE("conv_tc_wgrad64", stream);
   const long long M = (long long)N * H * W;
   CUtensorMap tmX = make_tmap_im2col(x, N, H, W, 64, 3, 1, 1);
   CUtensorMap tmDY = make_tmap_2d(dy, (uint64_t)M, 64, 128);
@@ -589,6 +591,7 @@ __global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, int npart
 }
 
 void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream) {
+  PCG_PROFILE("wgrad_reduce_tc", stream);
   wgrad_reduce_tc_kernel<<<cdiv(36864, 256), 256, 0, stream>>>(part, nparts, dw);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -611,6 +614,7 @@ __global__ void pack_conv_weights_tc_kernel(const float* __restrict__ w, int Cou
 
 void pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, bf16* fprop, bf16* dgrad,
                           cudaStream_t stream) {
+  PCG_PROFILE("pack_weights", stream);
   const int total = Cout * Cin * ksize * ksize;
   pack_conv_weights_tc_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, Cout, Cin, ksize, fprop, dgrad);
   PCG_COUNT_LAUNCH();

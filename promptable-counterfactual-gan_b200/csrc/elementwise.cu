@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, 
 
 template <typename T>
 void bn_stats_partial(const T* y, long long M, int C, float* part, cudaStream_t s) {
+  PCG_PROFILE("bn_stats", s);
   check_colshape(C);
   bn_stats_kernel<T><<<STAT_PARTS, 256, 0, s>>>(y, M, C, part);
   PCG_COUNT_LAUNCH();
@@ -140,6 +141,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, l
 void bn_finalize(const float* part, int nparts, long long M, int C, const float* gamma, const float* beta,
                  float eps, float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
                  float* rstd, float* scale, float* shift, cudaStream_t s) {
+  PCG_PROFILE("bn_finalize", s);
   bn_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
                                                running_var, nbt, mean, rstd, scale, shift);
   PCG_COUNT_LAUNCH();
@@ -169,6 +171,7 @@ static int ew_blocks(long long n) {
 template <typename T>
 void bn_apply_act(const T* y, const float* scale, const float* shift, long long M, int C, int act, float slope, T* z,
                   cudaStream_t s) {
+  PCG_PROFILE("bn_apply", s);
   PCG_REQUIRE(C % 4 == 0, "C % 4");
   const long long n4 = M * C / 4;
   bn_apply_act_kernel<T><<<ew_blocks(n4), 256, 0, s>>>(y, scale, shift, n4, C, act, slope, z);
@@ -195,6 +198,7 @@ bn_apply_residual_kernel(const T* __restrict__ y, const T* __restrict__ h, const
 template <typename T>
 void bn_apply_residual(const T* y, const T* h, const float* scale, const float* shift, float res_scale, long long M,
                        int C, T* out, cudaStream_t s) {
+  PCG_PROFILE("bn_apply", s);
   PCG_REQUIRE(C % 4 == 0, "C % 4");
   const long long n4 = M * C / 4;
   bn_apply_residual_kernel<T><<<ew_blocks(n4), 256, 0, s>>>(y, h, scale, shift, res_scale, n4, C, out);
@@ -235,6 +239,7 @@ template <typename T>
 void bn_bwd_partial(const T* dsrc, const T* y, const float* mean, const float* rstd, const float* scale,
                     const float* shift, float gscale, int act, float slope, long long M, int C, float* part,
                     cudaStream_t s) {
+  PCG_PROFILE("bn_bwd_reduce", s);
   check_colshape(C);
   bn_bwd_partial_kernel<T><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, gscale, act, slope, M, C, part);
   PCG_COUNT_LAUNCH();
@@ -258,6 +263,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
 
 void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* dgamma, float* dbeta, float* c12,
                      cudaStream_t s) {
+  PCG_PROFILE("bn_finalize", s);
   bn_bwd_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, M, C, dgamma, dbeta, c12);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -299,6 +305,7 @@ template <typename T>
 void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rstd, const float* scale,
                   const float* shift, const float* gamma, const float* c12, float gscale, int act, float slope,
                   long long M, int C, T* dy, float* part_db, cudaStream_t s) {
+  PCG_PROFILE("bn_bwd_apply", s);
   (void)gamma;
   check_colshape(C);
   bn_bwd_apply_kernel<T><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, c12, gscale, act, slope, M, C, dy,
@@ -315,6 +322,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ part, int npart
   out[c] = (float)s;
 }
 void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   colsum_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, stride, C, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, lo
 }
 template <typename T>
 void colsum_partial(const T* a, long long M, int C, float* part, cudaStream_t s) {
+  PCG_PROFILE("colsum", s);
   colsum_kernel<T><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -376,6 +385,7 @@ __global__ void g_input_kernel(const float* __restrict__ x, const float* __restr
 template <typename T>
 void g_input(const float* x, const float* embed, const long long* label, const float* mask, int B, int HW, T* out,
              cudaStream_t s) {
+  PCG_PROFILE("small", s);
   const long long total = (long long)B * HW;
   g_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(x, embed, label, mask, total, HW, out);
   PCG_COUNT_LAUNCH();
@@ -393,6 +403,7 @@ __global__ void d_input_kernel(const float* __restrict__ x, const float* __restr
 }
 template <typename T>
 void d_input(const float* x, const float* embed, const long long* label, int B, int HW, T* out, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   const long long total = (long long)B * HW;
   d_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(x, embed, label, total, HW, out);
   PCG_COUNT_LAUNCH();
@@ -414,6 +425,7 @@ __global__ void embed_grad_kernel(const T* __restrict__ src, int nch, int ch, co
 template <typename T>
 void embed_grad(const T* src, int nch, int ch, const long long* label, int B, int HW, int num_classes, float* dE,
                 cudaStream_t s) {
+  PCG_PROFILE("embed_grad", s);
   dim3 grid(cdiv(HW, 128), num_classes);
   embed_grad_kernel<T><<<grid, 128, 0, s>>>(src, nch, ch, label, B, HW, dE);
   PCG_COUNT_LAUNCH();
@@ -453,6 +465,7 @@ residual_head_fwd_kernel(const float* __restrict__ c, const float* __restrict__ 
 }
 void residual_head_fwd(const float* c, const float* x, const float* mask, float rs, long long n, float* raw,
                        float* masked, float* x_cf, float* part, cudaStream_t s) {
+  PCG_PROFILE("residual_head", s);
   residual_head_fwd_kernel<<<STAT_PARTS, 256, 0, s>>>(c, x, mask, rs, n, raw, masked, x_cf, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -480,6 +493,7 @@ __global__ void residual_head_bwd_kernel(const float* __restrict__ dxd, int dxd_
 template <typename T>
 void residual_head_bwd(const float* dxd, int dxd_ch, const float* dxc, const float* raw, const float* x,
                        const float* mask, float rs, float lreg, float lmask, long long n, T* g_c, cudaStream_t s) {
+  PCG_PROFILE("residual_head", s);
   residual_head_bwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>(dxd, dxd_ch, dxc, raw, x, mask, rs, lreg, lmask, n, g_c);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -505,6 +519,7 @@ __global__ void d_head_fwd_kernel(const T* __restrict__ z, int B, int HW, int C,
 }
 template <typename T>
 void d_head_fwd(const T* z, int B, int HW, int C, const float* w, const float* b, float* logits, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   d_head_fwd_kernel<T><<<cdiv(B, 8), 256, 0, s>>>(z, B, HW, C, w, b, logits);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -546,6 +561,7 @@ __global__ void bce_logits_kernel(const float* __restrict__ logits, int seg, flo
 }
 void bce_logits(const float* logits, int seg, int nseg, float t0, float t1, float w0, float w1, float* out_loss,
                 float* out_p, float* dlogit, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   PCG_REQUIRE(nseg == 1 || nseg == 2, "1 or 2 segments");
   bce_logits_kernel<<<nseg, 256, 0, s>>>(logits, seg, t0, t1, w0, w1, out_loss, out_p, dlogit);
   PCG_COUNT_LAUNCH();
@@ -586,6 +602,7 @@ __global__ void d_head_wgrad_kernel(const T* __restrict__ z, const float* __rest
 template <typename T>
 void d_head_bwd(const T* z, const float* dlogit, int B, int HW, int C, const float* w, float slope, T* g, float* dw,
                 float* db, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   d_head_bwd_kernel<T><<<B, 256, 0, s>>>(z, dlogit, HW, C, w, slope, g);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -619,6 +636,7 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, const long long
 }
 void ce_loss(const float* logits, const long long* target, int B, int NC, float wgt, float* loss, float* dlogits,
              cudaStream_t s) {
+  PCG_PROFILE("small", s);
   ce_loss_kernel<<<1, 256, 0, s>>>(logits, target, B, NC, wgt, loss, dlogits);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -632,6 +650,7 @@ __global__ void l1_finalize_kernel(const float* __restrict__ part, int nparts, f
   }
 }
 void l1_finalize(const float* part, int nparts, float inv_n, float* out2, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   l1_finalize_kernel<<<1, 32, 0, s>>>(part, nparts, inv_n, out2);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -643,6 +662,7 @@ __global__ void g_loss_combine_kernel(const float* g_adv, const float* g_cls, co
 }
 void g_loss_combine(const float* g_adv, const float* g_cls, const float* reg, const float* mpen, float la, float lc,
                     float lr, float lm, float* out, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   g_loss_combine_kernel<<<1, 1, 0, s>>>(g_adv, g_cls, reg, mpen, la, lc, lr, lm, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -680,6 +700,7 @@ __global__ void adam_step_inc_kernel(int* step) { *step += 1; }
 
 void adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
                float beta2, float eps, float grad_scale, cudaStream_t s) {
+  PCG_PROFILE("adam", s);
   adam_flat_kernel<<<ew_blocks(n), 256, 0, s>>>(p, g, m, v, n, step, lr, beta1, beta2, eps, grad_scale);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -695,6 +716,7 @@ __global__ void fill_zero_kernel(T* p, long long n) {
 }
 template <typename T>
 void fill_zero(T* p, long long n, cudaStream_t s) {
+  PCG_PROFILE("small", s);
   fill_zero_kernel<T><<<ew_blocks(n), 256, 0, s>>>(p, n);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -706,6 +728,7 @@ __global__ void convert_kernel(const float* __restrict__ src, long long n, T* __
 }
 template <typename T>
 void convert_from_f32(const float* src, long long n, T* dst, cudaStream_t s) {
+  PCG_PROFILE("pack_weights", s);
   convert_kernel<T><<<ew_blocks(n), 256, 0, s>>>(src, n, dst);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();

@@ -176,7 +176,7 @@ struct MnistPlan : PlanBase {
       const size_t sc = conv_wgrad_generic_scratch(L.g);
       if (sc > wg_scratch_elems) wg_scratch_elems = sc;
     }
-    if (kBf16 && Cin % 64 == 0 && Cout % 64 == 0) {
+    if (kBf16 && cfg.use_tensor_cores && Cin % 64 == 0 && Cout % 64 == 0) {
       L.tcf = alloc<bf16>(n);
       L.tc_fprop = true;
       if (stride == 1 && k == 3 && pad == 1 && need_wd && perm_hw == 0) {

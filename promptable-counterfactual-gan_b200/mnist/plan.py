@@ -24,7 +24,8 @@ class _Config(ctypes.Structure):
                 ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("adam_eps", ctypes.c_float),
                 ("lambda_adv", ctypes.c_float), ("lambda_cls", ctypes.c_float), ("lambda_reg", ctypes.c_float),
                 ("lambda_mask", ctypes.c_float), ("residual_scaling", ctypes.c_float),
-                ("grad_scale", ctypes.c_float), ("pollute_d_grads", ctypes.c_int)]
+                ("grad_scale", ctypes.c_float), ("use_tensor_cores", ctypes.c_int),
+                ("pollute_d_grads", ctypes.c_int)]
 
 
 class _Buffers(ctypes.Structure):
@@ -52,6 +53,7 @@ class StepConfig:
     residual_scaling: float = 0.1
     grad_scale: float = 1.0
     pollute_d_grads: bool = False
+    use_tensor_cores: bool = True    # bf16 only; False = same storage, CUDA-core convolutions (A/B check)
     precision: str = "bf16"      # "bf16" (tcgen05 tensor cores) or "fp32" (CUDA cores, exact mode)
 
 
@@ -128,7 +130,7 @@ class MnistStepPlan:
         self._cfg = _Config(batch, base_ch, n_resblocks, PCG_BF16 if c.precision == "bf16" else PCG_F32,
                             c.g_lr, c.d_lr, c.beta1, c.beta2, c.adam_eps, c.lambda_adv, c.lambda_cls,
                             c.lambda_reg, c.lambda_mask, c.residual_scaling, c.grad_scale,
-                            1 if c.pollute_d_grads else 0)
+                            1 if c.use_tensor_cores else 0, 1 if c.pollute_d_grads else 0)
         P = lambda t: t.data_ptr()  # noqa: E731
         self._buf = _Buffers(P(g_arena.data), P(g_arena.grad), P(self.adam["g_m"]), P(self.adam["g_v"]),
                              P(self.adam["g_step"]), P(bn_running), P(bn_nbt), P(d_arena.data), P(d_arena.grad),
