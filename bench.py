@@ -226,7 +226,7 @@ def run_native(args):
     d2h = host_scal.numel() * 4
 
     # ---- per-launcher device time inside the step (eager, CUDA events on the launching stream)
-    prof, roof = None, None
+    prof, roof, detail = None, None, None
     if rank == 0:
         import ctypes
         tr.use_graph = False
@@ -243,6 +243,13 @@ def run_native(args):
             v["share"] = v["ms"] / tot if tot else 0.0
             v["launches_per_step"] = v["launches"] / nprof
         pk, which = peaks()
+        detail = prof
+        prof = {}
+        for name, v in detail.items():      # "launcher:layer.op" -> aggregate per launcher
+            a = prof.setdefault(name.split(":")[0], {"ms": 0.0, "launches": 0, "ms_per_step": 0.0, "share": 0.0,
+                                                      "launches_per_step": 0.0})
+            for kk in a:
+                a[kk] += v[kk]
         if "conv_tc_fprop" in prof:
             # 64->64 fprop/dgrad launches dominate this launcher; D/C launches are counted with their own FLOPs below
             k = prof["conv_tc_fprop"]
@@ -273,6 +280,8 @@ def run_native(args):
             "launches_per_step": int(launches_per_step),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in (prof or {}).items()},
+            "kernel_detail_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(
+                (detail or {}).items(), key=lambda kv: -kv[1]["ms_per_step"])[:40]} if prof else {},
             "losses": {k: round(v, 5) for k, v in scal.items()},
         }
         print(json.dumps(line), flush=True)

@@ -15,7 +15,8 @@ void set_last_error(const std::string& msg) { t_last_error = msg; }
 unsigned long long g_launch_count = 0;
 
 bool g_profile_on = false;
-struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+const char* g_prof_tag = nullptr;
+struct ProfRec { std::string name; cudaEvent_t e0, e1; };
 static std::vector<ProfRec> g_prof;
 ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
   if (!g_profile_on) return;
@@ -26,7 +27,7 @@ ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s) {
 ProfileScope::~ProfileScope() {
   if (e0 == nullptr) return;
   cudaEventRecord(e1, stream);
-  g_prof.push_back({name, e0, e1});
+  g_prof.push_back({g_prof_tag ? std::string(name) + ":" + g_prof_tag : std::string(name), e0, e1});
 }
 
 int sm_count() {

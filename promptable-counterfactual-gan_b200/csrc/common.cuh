@@ -49,6 +49,12 @@ extern unsigned long long g_launch_count;
 // launching stream; pcg_profile_end() synchronises and reports total ms + launch count per name.
 // Must be off during CUDA-graph capture.
 extern bool g_profile_on;
+extern const char* g_prof_tag;     // optional finer label set by the plan ("d.conv2.dgrad", ...)
+struct ProfTag {
+  const char* prev;
+  explicit ProfTag(const char* t) : prev(g_prof_tag) { g_prof_tag = t; }
+  ~ProfTag() { g_prof_tag = prev; }
+};
 struct ProfileScope {
   const char* name;
   cudaStream_t stream;

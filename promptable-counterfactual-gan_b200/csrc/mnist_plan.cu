@@ -71,6 +71,7 @@ struct ConvLayer {
   bf16* tcd = nullptr;        // bf16 [Cin][taps][Cout], taps rotated
   bool tc_fprop = false, tc_dgrad = false, tc_wgrad = false;
   int perm_hw = 0;
+  std::string name, tag_f, tag_d, tag_w;
 
   void pack(cudaStream_t s) const {
     pack_conv_weights_generic(w, g.Cout, g.Cin, g.ksize, perm_hw, wf, wd, s);
@@ -165,8 +166,9 @@ struct MnistPlan : PlanBase {
     return reinterpret_cast<U*>(p);
   }
 
-  void setup_conv(ConvLayer<T>& L, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, const float* w,
-                  const float* b, float* dw, float* db, bool need_wd, int perm_hw = 0) {
+  void setup_conv(ConvLayer<T>& L, const std::string& name, int N, int H, int W, int Cin, int Cout, int k, int stride,
+                  int pad, const float* w, const float* b, float* dw, float* db, bool need_wd, int perm_hw = 0) {
+    L.name = name; L.tag_f = name + ".fprop"; L.tag_d = name + ".dgrad"; L.tag_w = name + ".wgrad";
     L.g = ConvGeom{N, H, W, Cin, Cout, k, stride, pad};
     L.w = w; L.b = b; L.dw = dw; L.db = db; L.perm_hw = perm_hw;
     const size_t n = (size_t)Cout * Cin * k * k;
@@ -203,12 +205,12 @@ struct MnistPlan : PlanBase {
 
     // ---- generator
     g_embed = GP(0); g_dembed = GG(0);
-    setup_conv(g_in, B, 28, 28, 3, ch, 3, 1, 1, GP(1), GP(2), GG(1), GG(2), true);
+    setup_conv(g_in, "g.conv_in", B, 28, 28, 3, ch, 3, 1, 1, GP(1), GP(2), GG(1), GG(2), true);
     g_c1.resize(nres); g_c2.resize(nres); bn1.resize(nres); bn2.resize(nres);
     for (int i = 0; i < nres; ++i) {
       const int t = 3 + i * 8;
-      setup_conv(g_c1[i], B, 28, 28, ch, ch, 3, 1, 1, GP(t), GP(t + 1), GG(t), GG(t + 1), true);
-      setup_conv(g_c2[i], B, 28, 28, ch, ch, 3, 1, 1, GP(t + 4), GP(t + 5), GG(t + 4), GG(t + 5), true);
+      setup_conv(g_c1[i], "g.res", B, 28, 28, ch, ch, 3, 1, 1, GP(t), GP(t + 1), GG(t), GG(t + 1), true);
+      setup_conv(g_c2[i], "g.res", B, 28, 28, ch, ch, 3, 1, 1, GP(t + 4), GP(t + 5), GG(t + 4), GG(t + 5), true);
       BN* bns[2] = {&bn1[i], &bn2[i]};
       for (int j = 0; j < 2; ++j) {
         BN& q = *bns[j];
@@ -222,23 +224,23 @@ struct MnistPlan : PlanBase {
     }
     {
       const int t = 3 + nres * 8;
-      setup_conv(g_mid, B, 28, 28, ch, ch, 3, 1, 1, GP(t), GP(t + 1), GG(t), GG(t + 1), true);
-      setup_conv(g_out, B, 28, 28, ch, 1, 3, 1, 1, GP(t + 2), GP(t + 3), GG(t + 2), GG(t + 3), true);
+      setup_conv(g_mid, "g.res", B, 28, 28, ch, ch, 3, 1, 1, GP(t), GP(t + 1), GG(t), GG(t + 1), true);
+      setup_conv(g_out, "g.conv_out", B, 28, 28, ch, 1, 3, 1, 1, GP(t + 2), GP(t + 3), GG(t + 2), GG(t + 3), true);
     }
     // ---- discriminator (batched real+fake in the D step -> 2B)
     d_embed = DP(0); d_dembed = DG(0);
     {
       const int cin[4] = {2, 64, 128, 256}, cout[4] = {64, 128, 256, 256}, hw[4] = {28, 14, 7, 4};
       for (int l = 0; l < 4; ++l)
-        setup_conv(d_conv[l], 2 * B, hw[l], hw[l], cin[l], cout[l], 3, 2, 1, DP(1 + l), nullptr, DG(1 + l), nullptr, true);
+        setup_conv(d_conv[l], "d.conv" + std::to_string(l), 2 * B, hw[l], hw[l], cin[l], cout[l], 3, 2, 1, DP(1 + l), nullptr, DG(1 + l), nullptr, true);
     }
     d_head_w = DP(5); d_head_b = DP(6); d_dhead_w = DG(5); d_dhead_b = DG(6);
     // ---- classifier (frozen; data gradients only)
-    setup_conv(c_conv[0], B, 28, 28, 1, 32, 3, 1, 1, CP(0), CP(1), nullptr, nullptr, true);
-    setup_conv(c_conv[1], B, 28, 28, 32, 64, 3, 2, 1, CP(2), CP(3), nullptr, nullptr, true);
-    setup_conv(c_conv[2], B, 14, 14, 64, 128, 3, 2, 1, CP(4), CP(5), nullptr, nullptr, true);
-    setup_conv(c_fc1, B, 1, 1, 6272, 256, 1, 1, 0, CP(6), CP(7), nullptr, nullptr, true, /*perm_hw=*/49);
-    setup_conv(c_fc2, B, 1, 1, 256, 10, 1, 1, 0, CP(8), CP(9), nullptr, nullptr, true);
+    setup_conv(c_conv[0], "c.conv0", B, 28, 28, 1, 32, 3, 1, 1, CP(0), CP(1), nullptr, nullptr, true);
+    setup_conv(c_conv[1], "c.conv1", B, 28, 28, 32, 64, 3, 2, 1, CP(2), CP(3), nullptr, nullptr, true);
+    setup_conv(c_conv[2], "c.conv2", B, 14, 14, 64, 128, 3, 2, 1, CP(4), CP(5), nullptr, nullptr, true);
+    setup_conv(c_fc1, "c.fc1", B, 1, 1, 6272, 256, 1, 1, 0, CP(6), CP(7), nullptr, nullptr, true, /*perm_hw=*/49);
+    setup_conv(c_fc2, "c.fc2", B, 1, 1, 256, 10, 1, 1, 0, CP(8), CP(9), nullptr, nullptr, true);
 
     // ---- workspaces
     const size_t act = (size_t)MG * ch;
@@ -294,6 +296,7 @@ struct MnistPlan : PlanBase {
   template <typename TIn, typename TOut>
   void fprop(const ConvLayer<T>& L, const TIn* in, GenEpilogue<TOut> e, TOut* out, cudaStream_t s, float* stats = nullptr,
              int* nparts = nullptr, int n_override = 0) {
+    ProfTag _tag(L.tag_f.c_str());
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, bf16>::value) {
@@ -311,6 +314,7 @@ struct MnistPlan : PlanBase {
   }
   template <typename TIn, typename TOut>
   void dgrad(const ConvLayer<T>& L, const TIn* dout, GenEpilogue<TOut> e, TOut* din, cudaStream_t s, int n_override = 0) {
+    ProfTag _tag(L.tag_d.c_str());
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, bf16>::value) {
@@ -323,6 +327,7 @@ struct MnistPlan : PlanBase {
   }
   template <typename TIn, typename TDy>
   void wgrad(const ConvLayer<T>& L, const TIn* in, const TDy* dout, cudaStream_t s, int n_override = 0) {
+    ProfTag _tag(L.tag_w.c_str());
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TDy, bf16>::value) {
