@@ -227,6 +227,105 @@ skinny_conv_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt, T
   }
 }
 
+
+// ---- vectorised skinny kernel: LPP lanes span one pixel's source channels (8 channels = 16/32 B per lane),
+// 32/LPP pixels per warp instruction, fully coalesced; shuffle-reduce over the LPP lanes.
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __bfloat1622float2(h[e]);
+    v[2 * e] = f.x; v[2 * e + 1] = f.y;
+  }
+}
+
+template <int MODE, typename TIn, typename TOut, int NC, int LPP>
+__global__ void __launch_bounds__(256)
+skinny_conv_v2_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt, TOut* __restrict__ dst,
+                      long long M, int K, int outH, int outW, Gather<MODE> ga, EpiDev<TOut> epi) {
+  extern __shared__ float wsm[];   // [NC][K]
+  for (int i = threadIdx.x; i < NC * K; i += blockDim.x) wsm[i] = wgt[i];
+  __syncthreads();
+  constexpr int PPW = 32 / LPP;                 // pixels per warp pass
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPP, cl = lane % LPP;   // pixel slot in the warp, channel-group of this lane
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int taps = ga.ksize * ga.ksize;
+  for (long long m0 = warp_global * PPW; m0 < M; m0 += nwarps * PPW) {
+    const long long m = m0 + sub;
+    float acc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+    if (m < M) {
+      RowCoord rc;
+      long long t = m;
+      rc.w = (int)(t % outW); t /= outW;
+      rc.h = (int)(t % outH); rc.n = (int)(t / outH);
+      for (int tap = 0; tap < taps; ++tap) {
+        const long long off = ga.pixel_offset(rc, tap);
+        if (off < 0) continue;
+        float a[8];
+        load8<TIn>(src + off + cl * 8, a);
+        const float* wrow = wsm + tap * ga.srcC + cl * 8;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wrow + j * K);
+          const float4 w1 = *reinterpret_cast<const float4*>(wrow + j * K + 4);
+          acc[j] = fmaf(a[0], w0.x, acc[j]); acc[j] = fmaf(a[1], w0.y, acc[j]);
+          acc[j] = fmaf(a[2], w0.z, acc[j]); acc[j] = fmaf(a[3], w0.w, acc[j]);
+          acc[j] = fmaf(a[4], w1.x, acc[j]); acc[j] = fmaf(a[5], w1.y, acc[j]);
+          acc[j] = fmaf(a[6], w1.z, acc[j]); acc[j] = fmaf(a[7], w1.w, acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (cl == 0 && m < M) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) dst[m * NC + j] = from_f<TOut>(apply_epilogue(acc[j], epi, m, j, NC));
+    }
+  }
+}
+
+template <int MODE, typename TIn, typename TOut, int NC>
+static bool launch_skinny_v2(const TIn* src, const float* wgt, TOut* dst, long long M, int K, int outH, int outW,
+                             const Gather<MODE>& ga, const EpiDev<TOut>& e, cudaStream_t stream) {
+  const int lpp = ga.srcC / 8;
+  if (ga.srcC % 8 != 0 || lpp > 32 || (lpp & (lpp - 1)) != 0 || (((uintptr_t)src) & 31) != 0 || (K % 4) != 0)
+    return false;
+  const size_t sm = (size_t)NC * K * sizeof(float);
+  if (sm > 48 * 1024) return false;
+  const long long warps_needed = (M * lpp + 31) / 32;
+  long long blocks = (warps_needed + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define PCG_SK(L) skinny_conv_v2_kernel<MODE, TIn, TOut, NC, L><<<(int)blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e)
+  switch (lpp) {
+    case 1: PCG_SK(1); break;
+    case 2: PCG_SK(2); break;
+    case 4: PCG_SK(4); break;
+    case 8: PCG_SK(8); break;
+    case 16: PCG_SK(16); break;
+    default: PCG_SK(32); break;
+  }
+#undef PCG_SK
+  return true;
+}
+
 template <typename TOut>
 static EpiDev<TOut> to_dev(const GenEpilogue<TOut>& e) {
   EpiDev<TOut> d;
@@ -240,7 +339,17 @@ static void launch_conv(const TIn* src, const float* wgt, TOut* dst, long long M
                         int outW, const Gather<MODE>& ga, const GenEpilogue<TOut>& epi, cudaStream_t stream) {
   PCG_PROFILE("conv_generic", stream);
   const EpiDev<TOut> e = to_dev(epi);
+  bool done = false;
   if (Nc <= 4) {
+    switch (Nc) {
+      case 1: done = launch_skinny_v2<MODE, TIn, TOut, 1>(src, wgt, dst, M, K, outH, outW, ga, e, stream); break;
+      case 2: done = launch_skinny_v2<MODE, TIn, TOut, 2>(src, wgt, dst, M, K, outH, outW, ga, e, stream); break;
+      case 3: done = launch_skinny_v2<MODE, TIn, TOut, 3>(src, wgt, dst, M, K, outH, outW, ga, e, stream); break;
+      default: done = launch_skinny_v2<MODE, TIn, TOut, 4>(src, wgt, dst, M, K, outH, outW, ga, e, stream); break;
+    }
+  }
+  if (done) {
+  } else if (Nc <= 4) {
     const int blocks = (int)((M * 32 + 255) / 256 < (long long)sm_count() * 16 ? (M * 32 + 255) / 256
                                                                                : (long long)sm_count() * 16);
     const size_t sm = (size_t)Nc * K * sizeof(float);
@@ -272,10 +381,18 @@ void conv_fprop_generic(const TIn* in, const ConvGeom& g, const float* wf, const
 
 template <typename TIn, typename TOut>
 void conv_dgrad_generic(const TIn* dout, const ConvGeom& g, const float* wd, const GenEpilogue<TOut>& epi,
-                        TOut* din, cudaStream_t stream) {
+                        TOut* din, cudaStream_t stream, int ch_select) {
   Gather<MODE_DGRAD> ga;
   ga.srcH = g.Ho(); ga.srcW = g.Wo(); ga.srcC = g.Cout; ga.ksize = g.ksize; ga.stride = g.stride; ga.pad = g.pad;
-  launch_conv<MODE_DGRAD>(dout, wd, din, g.Min(), g.Cin, g.ksize * g.ksize * g.Cout, g.H, g.W, ga, epi, stream);
+  const int K = g.ksize * g.ksize * g.Cout;
+  if (ch_select >= 0) {
+    // only input channel `ch_select` is wanted: a 1-column problem on that row of wd, compact [Min][1] output
+    PCG_REQUIRE(ch_select < g.Cin && epi.add_src == nullptr && epi.act_ref == nullptr && epi.bias == nullptr,
+                "channel-select dgrad takes no epilogue tensors");
+    launch_conv<MODE_DGRAD>(dout, wd + (size_t)ch_select * K, din, g.Min(), 1, K, g.H, g.W, ga, epi, stream);
+    return;
+  }
+  launch_conv<MODE_DGRAD>(dout, wd, din, g.Min(), g.Cin, K, g.H, g.W, ga, epi, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -380,6 +497,72 @@ wgrad_gemm_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, float* 
   }
 }
 
+
+// ---- skinny wgrad (Cout <= 4, Cin % 8 == 0): lanes over input channels, accumulators in registers,
+// one partial row per block: part[block][co][k].
+template <typename TIn, typename TDy, int NC, int LPP>
+__global__ void __launch_bounds__(256)
+wgrad_skinny_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, float* __restrict__ part, long long P,
+                    int K, int outH, int outW, Gather<MODE_FPROP> ga) {
+  constexpr int PPW = 32 / LPP;
+  constexpr int MAXTAPS = 9;
+  extern __shared__ float red[];    // [8 warps][NC][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPP, cl = lane % LPP;
+  const int taps = ga.ksize * ga.ksize;
+  float acc[NC][MAXTAPS][8];
+#pragma unroll
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int t = 0; t < MAXTAPS; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][t][e] = 0.f;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p0 = warp_global * PPW; p0 < P; p0 += nwarps * PPW) {
+    const long long p = p0 + sub;
+    if (p >= P) continue;
+    float g[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) g[j] = to_f(dy[p * NC + j]);
+    RowCoord rc;
+    long long t = p;
+    rc.w = (int)(t % outW); t /= outW;
+    rc.h = (int)(t % outH); rc.n = (int)(t / outH);
+#pragma unroll
+    for (int tap = 0; tap < MAXTAPS; ++tap) {
+      if (tap >= taps) break;
+      const long long off = ga.pixel_offset(rc, tap);
+      if (off < 0) continue;
+      float a[8];
+      load8<TIn>(x + off + cl * 8, a);
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][tap][e] = fmaf(g[j], a[e], acc[j][tap][e]);
+    }
+  }
+  // reduce over the PPW pixel slots of the warp, then over the 8 warps of the block (fixed order)
+#pragma unroll
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int tap = 0; tap < MAXTAPS; ++tap)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = acc[j][tap][e];
+#pragma unroll
+        for (int o = LPP; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (sub == 0 && tap < taps) red[((size_t)warp * NC + j) * K + tap * ga.srcC + cl * 8 + e] = v;
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NC * K; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[(size_t)w * NC * K + i];
+    part[(size_t)blockIdx.x * NC * K + i] = s;
+  }
+}
+
 // part[z][co][(tap,ci)] -> dw[co][ci][tap] (torch OIHW), fixed order over z.
 __global__ void wgrad_reduce_generic_kernel(const float* __restrict__ part, int nz, int Cout, int Cin, int taps,
                                             float* __restrict__ dw) {
@@ -393,7 +576,15 @@ __global__ void wgrad_reduce_generic_kernel(const float* __restrict__ part, int 
   dw[((size_t)co * Cin + ci) * taps + tap] = s;
 }
 
+static bool wgrad_is_skinny(const ConvGeom& g) {
+  const int lpp = g.Cin / 8;
+  return g.Cout == 1 && g.Cin % 8 == 0 && lpp <= 32 && (lpp & (lpp - 1)) == 0 && g.ksize <= 3 &&
+         (size_t)8 * g.Cout * g.K() * sizeof(float) <= 48 * 1024;
+}
+constexpr int WG_SKINNY_BLOCKS = 592;
+
 static int wgrad_slices(const ConvGeom& g) {
+  if (wgrad_is_skinny(g)) return WG_SKINNY_BLOCKS;
   const long long P = g.Mout();
   const int tiles = cdiv(g.Cout, GT) * cdiv(g.K(), GT);
   long long want = (4LL * 148 + tiles - 1) / tiles;
@@ -416,6 +607,26 @@ void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float
   ga.srcH = g.H; ga.srcW = g.W; ga.srcC = g.Cin; ga.ksize = g.ksize; ga.stride = g.stride; ga.pad = g.pad;
   const long long P = g.Mout();
   const int nz = wgrad_slices(g);
+  if (wgrad_is_skinny(g) && (((uintptr_t)in) & 31) == 0) {
+    const size_t sm = (size_t)8 * g.Cout * g.K() * sizeof(float);
+#define PCG_WS(L) wgrad_skinny_kernel<TIn, TDy, 1, L><<<WG_SKINNY_BLOCKS, 256, sm, stream>>>(in, dout, scratch, P, g.K(), g.Ho(), g.Wo(), ga)
+    switch (g.Cin / 8) {
+      case 1: PCG_WS(1); break;
+      case 2: PCG_WS(2); break;
+      case 4: PCG_WS(4); break;
+      case 8: PCG_WS(8); break;
+      case 16: PCG_WS(16); break;
+      default: PCG_WS(32); break;
+    }
+#undef PCG_WS
+    PCG_COUNT_LAUNCH();
+    PCG_LAUNCH_CHECK();
+    wgrad_reduce_generic_kernel<<<cdiv((long long)g.Cout * g.K(), 256), 256, 0, stream>>>(scratch, nz, g.Cout, g.Cin,
+                                                                                          g.ksize * g.ksize, dw);
+    PCG_COUNT_LAUNCH();
+    PCG_LAUNCH_CHECK();
+    return;
+  }
   const long long slice = ((P + nz - 1) / nz + GK - 1) / GK * GK;
   dim3 grid(cdiv(g.Cout, GT), cdiv(g.K(), GT), nz);
   const bool vec = (g.Cin % 4 == 0) && (g.Cout % 4 == 0) && (((uintptr_t)in & 15) == 0) &&
@@ -465,7 +676,7 @@ void pack_conv_weights_generic(const float* w, int Cout, int Cin, int ksize, int
   template void conv_fprop_generic<TI, TO>(const TI*, const ConvGeom&, const float*, const GenEpilogue<TO>&, \
                                            TO*, cudaStream_t);                                            \
   template void conv_dgrad_generic<TI, TO>(const TI*, const ConvGeom&, const float*, const GenEpilogue<TO>&, \
-                                           TO*, cudaStream_t);                                            \
+                                           TO*, cudaStream_t, int);                                          \
   template void conv_wgrad_generic<TI, TO>(const TI*, const TO*, const ConvGeom&, float*, float*, cudaStream_t);
 INST(float, float)
 INST(bf16, bf16)

@@ -36,7 +36,8 @@ void conv_fprop_generic(const TIn* in, const ConvGeom& g, const float* wf, const
 // din[Min][Cin] = epi( gather(dout) * wd^T ),  wd fp32 [Cin][taps][Cout] (taps NOT rotated)
 template <typename TIn, typename TOut>
 void conv_dgrad_generic(const TIn* dout, const ConvGeom& g, const float* wd, const GenEpilogue<TOut>& epi,
-                        TOut* din, cudaStream_t stream);
+                        TOut* din, cudaStream_t stream, int ch_select = -1);
+// ch_select >= 0 (Cin <= 4 only): compute just that input channel, compact [Min][1] output.
 
 // dw (torch OIHW fp32 [Cout][Cin][k][k]) = sum_pixels dout[p][co] * in[p@tap][ci]
 // `scratch` must hold conv_wgrad_generic_scratch(g) floats.  If db != nullptr also db[co] = sum dout.

@@ -66,15 +66,16 @@ static CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, 
 }
 
 // NHWC bf16 activation, im2col mode: 128 pixels x 64 channels per box.
-static CUtensorMap make_tmap_im2col(const bf16* base, int N, int H, int W, int C, int ksize,
-                                    int stride, int pad) {
+// The base pixel walks the box [lower, dim + upper) in steps of `stride`; the element fetched for a
+// filter tap is base + tap offset, zero-filled outside the tensor.
+static CUtensorMap make_tmap_im2col_box(const bf16* base, int N, int H, int W, int C, int lower_w, int lower_h,
+                                        int upper_w, int upper_h, int stride) {
   load_driver_entry_points();
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  // base-pixel bounding box: lower = -pad, upper = pad - (k-1)  (dilation 1), W then H.
-  int lower[2] = {-pad, -pad};
-  int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encode_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims,
                                strides, lower, upper, /*channelsPerPixel=*/64,
@@ -83,6 +84,10 @@ static CUtensorMap make_tmap_im2col(const bf16* base, int N, int H, int W, int C
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeIm2col failed: " + std::to_string(int(r)));
   return m;
+}
+// Convolution window: lower = -pad, upper = pad - (k-1)  (dilation 1).
+static CUtensorMap make_tmap_im2col(const bf16* base, int N, int H, int W, int C, int ksize, int stride, int pad) {
+  return make_tmap_im2col_box(base, N, H, W, C, -pad, -pad, pad - (ksize - 1), pad - (ksize - 1), stride);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -94,7 +99,11 @@ constexpr int PIPE_BYTES = 196608;                // operand ring budget
 constexpr int FPROP_THREADS = 192;                // warp0 TMA, warp1 MMA, warps 2-5 epilogue
 
 struct FpropParams {
-  int M, Ho, Wo, stride, pad, ksize, cin_blocks, Cout;
+  int M, Ho, Wo;                 // GEMM rows = N*Ho*Wo base pixels
+  int tstride, lower_h, lower_w; // base coordinate of output (ho, wo) = ho*tstride + lower_h, ...
+  int taps_h, taps_w, cin_blocks, Cout;
+  // output row m = (n, ho, wo) is stored at pixel (n*OH + ho*os + oh0)*OW + wo*os + ow0 of the output tensor
+  int OH, OW, os, oh0, ow0;
   int num_m_tiles, num_n_tiles;
   const float* bias;
   int act;
@@ -157,7 +166,7 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int taps = p.ksize * p.ksize;
+  const int taps = p.taps_h * p.taps_w;
   const int num_kb = taps * p.cin_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -192,10 +201,10 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
         const int p0 = m_tile * TILE_M;
         const int n_img = p0 / hw, rem = p0 % hw;
-        const int cw = (rem % p.Wo) * p.stride - p.pad;
-        const int ch = (rem / p.Wo) * p.stride - p.pad;
+        const int cw = (rem % p.Wo) * p.tstride + p.lower_w;
+        const int ch = (rem / p.Wo) * p.tstride + p.lower_h;
         for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.ksize, s = tap % p.ksize;
+          const int r = tap / p.taps_w, s = tap % p.taps_w;
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
@@ -253,8 +262,14 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const long long pix = (long long)m_tile * TILE_M + row;
-      const bool valid = pix < p.M;
+      const long long mrow = (long long)m_tile * TILE_M + row;
+      const bool valid = mrow < p.M;
+      long long pix = mrow;
+      if (p.os != 1 || p.OH != p.Ho || p.OW != p.Wo) {
+        const int hw = p.Ho * p.Wo;
+        const int n_img = (int)(mrow / hw), rem = (int)(mrow % hw);
+        pix = ((long long)n_img * p.OH + (rem / p.Wo) * p.os + p.oh0) * p.OW + (rem % p.Wo) * p.os + p.ow0;
+      }
 #pragma unroll
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t r[32];
@@ -357,8 +372,10 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+static int pick_bn(int Cout) { return (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : (Cout % 64 == 0) ? 64 : 32; }
+
 int conv_tc_grid(long long M, int Cout) {
-  int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
+  int bn = pick_bn(Cout);
   long long tiles = ((M + TILE_M - 1) / TILE_M) * (Cout / bn);
   int sms = sm_count();
   return (int)(tiles < sms ? tiles : sms);
@@ -388,10 +405,12 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
   const int Ho = (H + 2 * pad - ksize) / stride + 1;
   const int Wo = (W + 2 * pad - ksize) / stride + 1;
   const long long M = (long long)N * Ho * Wo;
-  const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
+  const int bn = pick_bn(Cout);
   PCG_REQUIRE(epi.stats == nullptr || Cout == bn, "BN statistics need a single N tile");
   FpropParams p;
-  p.M = (int)M; p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.pad = pad; p.ksize = ksize;
+  p.M = (int)M; p.Ho = Ho; p.Wo = Wo; p.tstride = stride; p.lower_h = -pad; p.lower_w = -pad;
+  p.taps_h = ksize; p.taps_w = ksize;
+  p.OH = Ho; p.OW = Wo; p.os = 1; p.oh0 = 0; p.ow0 = 0;
   p.cin_blocks = Cin / 64; p.Cout = Cout;
   p.num_m_tiles = (int)((M + TILE_M - 1) / TILE_M);
   p.num_n_tiles = Cout / bn;
@@ -404,6 +423,70 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
   if (bn == 256) launch_fprop<256>(tmA, tmB, p, grid, stream);
   else if (bn == 128) launch_fprop<128>(tmA, tmB, p, grid, stream);
   else launch_fprop<64>(tmA, tmB, p, grid, stream);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// data gradient of a 3x3 / stride-2 / pad-1 convolution: four parity classes (hi%2, wi%2), each a
+// stride-1 implicit GEMM over dY with 1, 2, 2 or 4 taps whose rows scatter to every other pixel of dX
+// ------------------------------------------------------------------------------------------
+__global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ c00,
+                                     bf16* __restrict__ c01, bf16* __restrict__ c10, bf16* __restrict__ c11) {
+  // class (ph,pw): taps_h = ph ? 2 : 1; window offset oh -> filter row r = ph ? (oh == 0 ? 2 : 0) : 1
+  const int total = Cout * Cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int s = i % 3, r = (i / 3) % 3, ci = (i / 9) % Cin, co = i / (9 * Cin);
+    const int ph = (r == 1) ? 0 : 1, pw = (s == 1) ? 0 : 1;
+    const int oh = (r == 0) ? 1 : 0, ow = (s == 0) ? 1 : 0;
+    const int taps_w = pw ? 2 : 1, taps = (ph ? 2 : 1) * taps_w;
+    bf16* dst = ph ? (pw ? c11 : c10) : (pw ? c01 : c00);
+    dst[((size_t)ci * taps + oh * taps_w + ow) * Cout + co] = __float2bfloat16_rn(w[i]);
+  }
+}
+
+size_t conv_tc_dgrad_s2_pack_elems(int Cout, int Cin) { return (size_t)Cout * Cin * 9; }
+
+void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStream_t stream) {
+  PCG_PROFILE("pack_weights", stream);
+  const size_t u = (size_t)Cout * Cin;
+  pack_dgrad_s2_kernel<<<cdiv((long long)u * 9, 256) > 1184 ? 1184 : cdiv((long long)u * 9, 256), 256, 0, stream>>>(
+      w, Cout, Cin, packed, packed + u, packed + 3 * u, packed + 5 * u);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, const bf16* packed,
+                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream) {
+  PCG_REQUIRE(Cout % 64 == 0 && Cin % 32 == 0, "strided tensor-core dgrad needs Cout % 64 == 0, Cin % 32 == 0");
+  PCG_REQUIRE(epi.stats == nullptr && epi.bias == nullptr, "no bias / statistics in the dgrad epilogue");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t u = (size_t)Cout * Cin;
+  const size_t cls_off[4] = {0, u, 3 * u, 5 * u};
+  const int bn = pick_bn(Cin);
+  for (int cls = 0; cls < 4; ++cls) {
+    const int ph = cls >> 1, pw = cls & 1;
+    const int Ah = (H + 1 - ph) / 2, Aw = (W + 1 - pw) / 2;
+    if (Ah <= 0 || Aw <= 0) continue;
+    const int th = ph ? 2 : 1, tw = pw ? 2 : 1;
+    FpropParams p;
+    p.M = N * Ah * Aw; p.Ho = Ah; p.Wo = Aw; p.tstride = 1; p.lower_h = 0; p.lower_w = 0;
+    p.taps_h = th; p.taps_w = tw;
+    p.OH = H; p.OW = W; p.os = 2; p.oh0 = ph; p.ow0 = pw;
+    p.cin_blocks = Cout / 64; p.Cout = Cin;
+    p.num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
+    p.num_n_tiles = Cin / bn;
+    p.bias = nullptr; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
+    p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
+    p.out = dx; p.stats = nullptr;
+    CUtensorMap tmA = make_tmap_im2col_box(dy, N, Ho, Wo, Cout, 0, 0, Aw - Wo, Ah - Ho, 1);
+    CUtensorMap tmB = make_tmap_2d(packed + cls_off[cls], Cin, (uint64_t)th * tw * Cout, bn);
+    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    if (bn == 256) launch_fprop<256>(tmA, tmB, p, grid, stream);
+    else if (bn == 128) launch_fprop<128>(tmA, tmB, p, grid, stream);
+    else if (bn == 64) launch_fprop<64>(tmA, tmB, p, grid, stream);
+    else launch_fprop<32>(tmA, tmB, p, grid, stream);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -28,6 +28,16 @@ int conv_tc_grid(long long M, int Cout);
 void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk, int Cout, int ksize,
                    int stride, int pad, const ConvEpilogue& epi, bf16* out, cudaStream_t stream);
 
+// Data gradient of a 3x3 / stride-2 / pad-1 convolution on the tensor cores.
+//   dy bf16 NHWC [N][Ho][Wo][Cout] -> dx bf16 NHWC [N][H][W][Cin]; `packed` = 9*Cout*Cin bf16 written by
+//   pack_dgrad_s2_tc (four parity-class matrices [Cin][taps_class][Cout], 1 + 2 + 2 + 4 taps).
+// Four launches of the fprop kernel, one per (hi%2, wi%2) class: each is a stride-1 implicit GEMM over dY whose
+// output rows scatter to every other pixel of dx.  Epilogue: act / add_src / act_ref as in fprop (no bias/stats).
+size_t conv_tc_dgrad_s2_pack_elems(int Cout, int Cin);
+void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStream_t stream);
+void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, const bf16* packed,
+                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream);
+
 // dW partials of a 3x3 / stride-1 / pad-1 convolution with Cin = Cout = 64:
 //   part[cta][tap][ci][co] (fp32) = sum over the CTA's pixels of x[p + tap][ci] * dy[p][co]
 // `part` must hold conv_tc_wgrad_grid(M) * 9*64*64 floats; reduce with wgrad_reduce_tc().

@@ -110,18 +110,24 @@ void bn_stats_partial(const T* y, long long M, int C, float* part, cudaStream_t 
   PCG_LAUNCH_CHECK();
 }
 
+// Fixed-order parallel sum of column c over `nparts` partial rows by one warp (lane l takes rows
+// l, l+32, ... then a shuffle tree): deterministic and ~30x shorter dependency chain than a serial loop.
+__device__ __forceinline__ double warp_colsum(const float* __restrict__ part, int nparts, size_t stride, int c) {
+  double s = 0.0;
+  for (int i = threadIdx.x & 31; i < nparts; i += 32) s += (double)part[(size_t)i * stride + c];
+  return warp_sum(s);
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, long long* nbt,
                                    float* mean_o, float* rstd_o, float* scale, float* shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt != nullptr) *nbt += 1;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int i = 0; i < nparts; ++i) {
-    s += (double)part[(size_t)i * 2 * C + c];
-    q += (double)part[(size_t)i * 2 * C + C + c];
-  }
+  const double s = warp_colsum(part, nparts, 2 * (size_t)C, c);
+  const double q = warp_colsum(part, nparts, 2 * (size_t)C, C + c);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / (double)M;
   double var = q / (double)M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -142,7 +148,7 @@ void bn_finalize(const float* part, int nparts, long long M, int C, const float*
                  float eps, float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
                  float* rstd, float* scale, float* shift, cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  bn_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
+  bn_finalize_kernel<<<cdiv(C, 8), 256, 0, s>>>(part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
                                                running_var, nbt, mean, rstd, scale, shift);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -248,13 +254,11 @@ void bn_bwd_partial(const T* dsrc, const T* y, const float* mean, const float* r
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, float* dgamma,
                                        float* dbeta, float* c12) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < nparts; ++i) {
-    s1 += (double)part[(size_t)i * 2 * C + c];
-    s2 += (double)part[(size_t)i * 2 * C + C + c];
-  }
+  const double s1 = warp_colsum(part, nparts, 2 * (size_t)C, c);
+  const double s2 = warp_colsum(part, nparts, 2 * (size_t)C, C + c);
+  if ((threadIdx.x & 31) != 0) return;
   dbeta[c] = (float)s1;
   dgamma[c] = (float)s2;
   c12[c] = (float)(s1 / (double)M);
@@ -264,7 +268,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
 void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* dgamma, float* dbeta, float* c12,
                      cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  bn_bwd_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, M, C, dgamma, dbeta, c12);
+  bn_bwd_finalize_kernel<<<cdiv(C, 8), 256, 0, s>>>(part, nparts, M, C, dgamma, dbeta, c12);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -315,15 +319,14 @@ void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rst
 }
 
 __global__ void colsum_finalize_kernel(const float* __restrict__ part, int nparts, int stride, int C, float* out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s = 0.0;
-  for (int i = 0; i < nparts; ++i) s += (double)part[(size_t)i * stride + c];
-  out[c] = (float)s;
+  const double s = warp_colsum(part, nparts, (size_t)stride, c);
+  if ((threadIdx.x & 31) == 0) out[c] = (float)s;
 }
 void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  colsum_finalize_kernel<<<cdiv(C, 64), 64, 0, s>>>(part, nparts, stride, C, out);
+  colsum_finalize_kernel<<<cdiv(C, 8), 256, 0, s>>>(part, nparts, stride, C, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -583,20 +586,26 @@ __global__ void d_head_bwd_kernel(const T* __restrict__ z, const float* __restri
 template <typename T>
 __global__ void d_head_wgrad_kernel(const T* __restrict__ z, const float* __restrict__ dlogit, int B, int HW, int C,
                                     float* __restrict__ dw, float* __restrict__ db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // block = 64 channels x 4 sample-lanes; fixed-order reduction over the 4 sample-lanes in shared memory
+  __shared__ float red[4][64];
+  const int cl = threadIdx.x & 63, ns = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  float s = 0.f;
   if (c < C) {
-    float s = 0.f;
-    for (int n = 0; n < B; ++n) {
+    for (int n = ns; n < B; n += 4) {
       float m = 0.f;
       for (int p = 0; p < HW; ++p) m += to_f(z[((size_t)n * HW + p) * C + c]);
       s = fmaf(dlogit[n], m / (float)HW, s);
     }
-    dw[c] = s;
   }
-  if (c == 0) {
-    float s = 0.f;
-    for (int n = 0; n < B; ++n) s += dlogit[n];
-    db[0] = s;
+  red[ns][cl] = s;
+  __syncthreads();
+  if (ns == 0 && c < C) dw[c] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    float t = 0.f;
+    for (int n = threadIdx.x; n < B; n += 32) t += dlogit[n];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) db[0] = t;
   }
 }
 template <typename T>
@@ -607,7 +616,7 @@ void d_head_bwd(const T* z, const float* dlogit, int B, int HW, int C, const flo
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
   if (dw != nullptr) {
-    d_head_wgrad_kernel<T><<<cdiv(C, 64), 64, 0, s>>>(z, dlogit, B, HW, C, dw, db);
+    d_head_wgrad_kernel<T><<<cdiv(C, 64), 256, 0, s>>>(z, dlogit, B, HW, C, dw, db);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
   }
@@ -643,15 +652,15 @@ void ce_loss(const float* logits, const long long* target, int B, int NC, float 
 }
 
 __global__ void l1_finalize_kernel(const float* __restrict__ part, int nparts, float inv_n, float* out2) {
-  if (threadIdx.x < 2) {
-    double s = 0.0;
-    for (int i = 0; i < nparts; ++i) s += (double)part[i * 2 + threadIdx.x];
-    out2[threadIdx.x] = (float)(s * (double)inv_n);
+  const int c = threadIdx.x >> 5;
+  if (c < 2) {
+    const double s = warp_colsum(part, nparts, 2, c);
+    if ((threadIdx.x & 31) == 0) out2[c] = (float)(s * (double)inv_n);
   }
 }
 void l1_finalize(const float* part, int nparts, float inv_n, float* out2, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  l1_finalize_kernel<<<1, 32, 0, s>>>(part, nparts, inv_n, out2);
+  l1_finalize_kernel<<<1, 64, 0, s>>>(part, nparts, inv_n, out2);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

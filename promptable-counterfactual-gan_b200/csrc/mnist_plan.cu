@@ -69,7 +69,8 @@ struct ConvLayer {
   float* wd = nullptr;        // fp32 [Cin][taps][Cout]
   bf16* tcf = nullptr;        // bf16 [Cout][taps][Cin]
   bf16* tcd = nullptr;        // bf16 [Cin][taps][Cout], taps rotated
-  bool tc_fprop = false, tc_dgrad = false, tc_wgrad = false;
+  bf16* tcs2 = nullptr;       // bf16 parity-class matrices of the stride-2 data gradient
+  bool tc_fprop = false, tc_dgrad = false, tc_wgrad = false, tc_dgrad_s2 = false;
   int perm_hw = 0;
   std::string name, tag_f, tag_d, tag_w;
 
@@ -82,6 +83,7 @@ struct ConvLayer {
       PCG_REQUIRE(perm_hw == 0, "permuted tc dgrad packing unsupported");
       pack_conv_weights_tc(w, g.Cout, g.Cin, g.ksize, nullptr, tcd, s);
     }
+    if (tcs2) pack_dgrad_s2_tc(w, g.Cout, g.Cin, tcs2, s);
   }
 };
 
@@ -186,6 +188,11 @@ struct MnistPlan : PlanBase {
         L.tc_dgrad = true;
       }
       if (Cin == 64 && Cout == 64 && k == 3 && stride == 1 && pad == 1 && dw) L.tc_wgrad = true;
+    }
+    if (kBf16 && cfg.use_tensor_cores && stride == 2 && k == 3 && pad == 1 && Cout % 64 == 0 && Cin % 32 == 0 &&
+        need_wd && perm_hw == 0) {
+      L.tcs2 = alloc<bf16>(conv_tc_dgrad_s2_pack_elems(Cout, Cin));
+      L.tc_dgrad_s2 = true;
     }
   }
 
@@ -313,13 +320,22 @@ struct MnistPlan : PlanBase {
     }
   }
   template <typename TIn, typename TOut>
-  void dgrad(const ConvLayer<T>& L, const TIn* dout, GenEpilogue<TOut> e, TOut* din, cudaStream_t s, int n_override = 0) {
+  void dgrad(const ConvLayer<T>& L, const TIn* dout, GenEpilogue<TOut> e, TOut* din, cudaStream_t s, int n_override = 0,
+             int ch_select = -1) {
     ProfTag _tag(L.tag_d.c_str());
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
+    if (ch_select >= 0) {
+      conv_dgrad_generic<TIn, TOut>(dout, g, L.wd, e, din, s, ch_select);
+      return;
+    }
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, bf16>::value) {
       if (L.tc_dgrad) {
         conv_tc_fprop(dout, g.N, g.H, g.W, g.Cout, L.tcd, g.Cin, g.ksize, 1, g.pad, to_tc(e, nullptr), din, s);
+        return;
+      }
+      if (L.tc_dgrad_s2) {
+        conv_tc_dgrad_s2(dout, g.N, g.H, g.W, g.Cin, g.Cout, L.tcs2, to_tc(e, nullptr), din, s);
         return;
       }
     }
@@ -406,8 +422,9 @@ struct MnistPlan : PlanBase {
     }
     d_head_fwd<T>(dz[3], n, 4, 256, d_head_w, d_head_b, dlogits_d, s);
   }
-  // backward from ddlogit; weight grads written when `wg`; data gradient wrt the 2-channel input in dxd
-  void d_bwd(int n, bool wg, cudaStream_t s) {
+  // backward from ddlogit; weight grads written when `wg`; dxd[n][784] = gradient wrt input channel `in_ch`
+  // (0 = image, needed by the G step; 1 = label-embedding map, needed by the D step)
+  void d_bwd(int n, bool wg, int in_ch, cudaStream_t s) {
     d_head_bwd<T>(dz[3], ddlogit, n, 4, 256, d_head_w, 0.2f, dg[3], wg ? d_dhead_w : nullptr, wg ? d_dhead_b : nullptr, s);
     for (int l = 3; l >= 1; --l) {
       if (wg) wgrad<T, T>(d_conv[l], dz[l - 1], dg[l], s, n);
@@ -416,7 +433,7 @@ struct MnistPlan : PlanBase {
     }
     if (wg) wgrad<T, T>(d_conv[0], a0, dg[0], s, n);
     GenEpilogue<float> e0;
-    dgrad<T, float>(d_conv[0], dg[0], e0, dxd, s, n);
+    dgrad<T, float>(d_conv[0], dg[0], e0, dxd, s, n, in_ch);
   }
 
   // ---------------------------------------------------------------- phases
@@ -431,8 +448,8 @@ struct MnistPlan : PlanBase {
     bce_logits(dlogits_d, B, 2, 1.f, 0.f, 1.f, 1.f, scal + PCG_S_D_LOSS_REAL, scal + PCG_S_D_REAL_P, ddlogit, s);
     g_loss_combine(scal + PCG_S_D_LOSS_REAL, scal + PCG_S_D_LOSS_FAKE, scal + PCG_S_D_LOSS_REAL,
                    scal + PCG_S_D_LOSS_REAL, 1.f, 1.f, 0.f, 0.f, scal + PCG_S_D_LOSS, s);
-    d_bwd(2 * B, true, s);
-    embed_grad<float>(dxd, 2, 1, labels2, 2 * B, 784, 10, d_dembed, s);
+    d_bwd(2 * B, true, 1, s);
+    embed_grad<float>(dxd, 1, 0, labels2, 2 * B, 784, 10, d_dembed, s);
   }
 
   void step_d_update(cudaStream_t s) override {
@@ -458,7 +475,7 @@ struct MnistPlan : PlanBase {
     d_input<T>(x_cf, d_embed, in.target, B, 784, a0, s);
     d_fwd(B, s);
     bce_logits(dlogits_d, B, 1, 1.f, 1.f, cfg.lambda_adv, cfg.lambda_adv, scal + PCG_S_G_ADV, scal_tmp, ddlogit, s);
-    d_bwd(B, cfg.pollute_d_grads != 0, s);
+    d_bwd(B, cfg.pollute_d_grads != 0, 0, s);
     // --- classifier path (trainer.py:118)
     c_fwd(x_cf, s);
     ce_loss(clogits, in.target, B, 10, cfg.lambda_cls, scal + PCG_S_G_CLS, cdlogits, s);
@@ -474,7 +491,7 @@ struct MnistPlan : PlanBase {
     g_loss_combine(scal + PCG_S_G_ADV, scal + PCG_S_G_CLS, scal + PCG_S_REG_L1, scal + PCG_S_MASK_PEN, cfg.lambda_adv,
                    cfg.lambda_cls, cfg.lambda_reg, cfg.lambda_mask, scal + PCG_S_G_LOSS, s);
     // --- through clamp / mask / scaling (trainer.py:97,99,119; generator.py:80-82)
-    residual_head_bwd<T>(dxd, 2, dxc, raw, in.x, in.mask, cfg.residual_scaling, cfg.lambda_reg, cfg.lambda_mask, MG,
+    residual_head_bwd<T>(dxd, 1, dxc, raw, in.x, in.mask, cfg.residual_scaling, cfg.lambda_reg, cfg.lambda_mask, MG,
                          g_c, s);
     // --- generator backward
     wgrad<T, T>(g_out, hm, g_c, s);
@@ -530,9 +547,9 @@ struct MnistPlan : PlanBase {
     bias_grad(dh, MG, ch, g_in.db, s);
     {
       GenEpilogue<float> e;
-      dgrad<T, float>(g_in, dh, e, dinp, s);
+      dgrad<T, float>(g_in, dh, e, dinp, s, 0, /*ch_select=*/1);    // only the label-embedding channel
     }
-    embed_grad<float>(dinp, 3, 1, in.target, B, 784, 10, g_dembed, s);
+    embed_grad<float>(dinp, 1, 0, in.target, B, 784, 10, g_dembed, s);
   }
 
   void step_g_update(cudaStream_t s) override {
