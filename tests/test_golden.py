@@ -48,7 +48,9 @@ def _check_train_summaries(z, get, n_steps, lr_g, atol_lr):
             assert np.abs(got[2:] - ref[2:]).max() <= 2.02 * lr * n_steps, key
             continue
         if "running" in k:
-            assert np.allclose(got, ref, rtol=3e-4, atol=1e-6), key
+            # BN running statistics after n_steps (momentum 0.1): absolute 2e-5 on O(0.01-1) values
+            assert np.allclose(got[2:], ref[2:], rtol=1e-3, atol=2e-5), key
+            assert abs(got[1] - ref[1]) <= 1e-3 * abs(ref[1]) + 1e-4, key
             continue
         # samples: most agree to rounding; a few noise-gradient elements may differ by O(lr)
         d = np.abs(got[2:] - ref[2:])
