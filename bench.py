@@ -250,13 +250,13 @@ def run_native(args):
                                                       "launches_per_step": 0.0})
             for kk in a:
                 a[kk] += v[kk]
-        if "conv_tc_fprop" in prof:
-            # 64->64 fprop/dgrad launches dominate this launcher; D/C launches are counted with their own FLOPs below
-            k = prof["conv_tc_fprop"]
-            flops_per_step = flops_tc_fprop_per_step()
+        if "conv_tc64_fprop" in prof:
+            # the 26 fprop + dgrad launches of the 64->64 convolution (halo-tile tcgen05 kernel)
+            k = prof["conv_tc64_fprop"]
+            flops_per_step = 26 * CONV_FLOPS
             achieved = flops_per_step / (k["ms_per_step"] * 1e-3) / 1e12
             peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-            roof = {"bound": "tensor", "kernel": "conv_tc_fprop_kernel (tcgen05 implicit GEMM, fprop+dgrad)",
+            roof = {"bound": "tensor", "kernel": "conv_tc64_fprop_kernel (tcgen05 halo-tile conv 64->64, 13 fprop + 13 dgrad per step)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside the step)",
                     "avg_launch_us": k["ms"] / k["launches"] * 1e3}

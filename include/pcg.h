@@ -74,6 +74,17 @@ int pcg_conv_tc_fprop(const void* in, int N, int H, int W, int Cin, const void* 
 int pcg_conv_tc_wgrad_grid(long long M);
 int pcg_conv_tc_wgrad64(const void* x, const void* dy, int N, int H, int W, float* part, float* dw,
                         void* stream);
+/* Halo-tile variants for the 64->64 / 3x3 / stride-1 / pad-1 case (conv_tc64.cu): one TMA box per tile,
+ * weights resident in shared memory, the nine taps are shifted views of the tile.  Same operand layouts as
+ * pcg_conv_tc_fprop / pcg_conv_tc_wgrad64; stats rows = pcg_conv_tc64_grid(N, H, W). */
+int pcg_conv_tc64_grid(int N, int H, int W);
+int pcg_conv_tc64_fprop(const void* in, int N, int H, int W, const void* wpk, const float* bias, int act,
+                        float slope, const void* add_src, const void* act_ref, int ref_act, void* out,
+                        float* stats, void* stream);
+int pcg_conv_tc64_wgrad(const void* x, const void* dy, int N, int H, int W, float* part, float* dw,
+                        void* stream);
+int pcg_conv_tc64_set_variant(int v);
+
 /* fp32 OIHW -> bf16 [Cout][taps][Cin] (fprop) and rotated [Cin][taps][Cout] (dgrad; may be NULL). */
 int pcg_pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, void* fprop, void* dgrad,
                              void* stream);

@@ -134,6 +134,26 @@ int pcg_conv_tc_wgrad64(const void* x, const void* dy, int N, int H, int W, floa
   PCG_API_END
 }
 
+int pcg_conv_tc64_grid(int N, int H, int W) {
+  try { return conv_tc64_grid(N, H, W); } catch (const std::exception& e) { set_last_error(e.what()); return -1; }
+}
+int pcg_conv_tc64_set_variant(int v) { conv_tc64_set_variant(v); return 0; }
+int pcg_conv_tc64_fprop(const void* in, int N, int H, int W, const void* wpk, const float* bias, int act, float slope,
+                        const void* add_src, const void* act_ref, int ref_act, void* out, float* stats, void* stream) {
+  PCG_API_BEGIN
+  ConvEpilogue e;
+  e.bias = bias; e.act = act; e.slope = slope; e.add_src = (const bf16*)add_src; e.stats = stats;
+  e.act_ref = (const bf16*)act_ref; e.ref_act = ref_act; e.ref_slope = slope;
+  conv_tc64_fprop((const bf16*)in, N, H, W, (const bf16*)wpk, e, (bf16*)out, (cudaStream_t)stream);
+  PCG_API_END
+}
+int pcg_conv_tc64_wgrad(const void* x, const void* dy, int N, int H, int W, float* part, float* dw, void* stream) {
+  PCG_API_BEGIN
+  conv_tc64_wgrad((const bf16*)x, (const bf16*)dy, N, H, W, part, (cudaStream_t)stream);
+  wgrad_reduce_tc(part, conv_tc64_grid(N, H, W), dw, (cudaStream_t)stream);
+  PCG_API_END
+}
+
 int pcg_pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, void* fprop, void* dgrad,
                              void* stream) {
   PCG_API_BEGIN

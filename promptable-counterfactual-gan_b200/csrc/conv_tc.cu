@@ -50,7 +50,7 @@ static void load_driver_entry_points() {
 }
 
 // [rows][cols] bf16 row-major matrix, box = box_rows x 64 columns, 128B swizzle.
-static CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   load_driver_entry_points();
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
@@ -68,7 +68,7 @@ static CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, 
 // NHWC bf16 activation, im2col mode: 128 pixels x 64 channels per box.
 // The base pixel walks the box [lower, dim + upper) in steps of `stride`; the element fetched for a
 // filter tap is base + tap offset, zero-filled outside the tensor.
-static CUtensorMap make_tmap_im2col_box(const bf16* base, int N, int H, int W, int C, int lower_w, int lower_h,
+CUtensorMap make_tmap_im2col_box(const bf16* base, int N, int H, int W, int C, int lower_w, int lower_h,
                                         int upper_w, int upper_h, int stride) {
   load_driver_entry_points();
   CUtensorMap m;
@@ -83,6 +83,20 @@ static CUtensorMap make_tmap_im2col_box(const bf16* base, int N, int H, int W, i
                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeIm2col failed: " + std::to_string(int(r)));
+  return m;
+}
+// NHWC bf16 activation, tiled mode: box = 64 channels x box_w x box_h x 1 image, 128B swizzle, zero OOB fill.
+CUtensorMap make_tmap_nhwc_box(const bf16* base, int N, int H, int W, int C, int box_w, int box_h) {
+  load_driver_entry_points();
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string(int(r)));
   return m;
 }
 // Convolution window: lower = -pad, upper = pad - (k-1)  (dilation 1).
@@ -233,12 +247,15 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(ring + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const uint64_t da = umma_smem_desc(a_base, 16, 1024);
+          const uint64_t db = umma_smem_desc(a_base + A_STAGE_BYTES, 16, 1024);
+          // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: advance the start-address field by 2
+          if (kb == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {     // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
-            const uint64_t da = umma_smem_desc(a_base + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(b_base + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
           }
           umma_commit(&empty[stage]);       // frees the smem slot once these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -580,12 +597,15 @@ conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         for (int j = 0; j < 5; ++j) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sx + stage * WG_X_STAGE);
+          const uint64_t da = umma_smem_desc(smem_u32(sx + stage * WG_X_STAGE), A_STAGE_BYTES, 1024);
+          const uint64_t dbd = umma_smem_desc(b_base, A_STAGE_BYTES, 1024);
+          // 8 x (K = 16 pixels = 2 swizzle atoms of 8 rows = 2048 B): start-address field += 128
+          if (first) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {      // 8 x (K = 16 pixels = 2 swizzle atoms of 8 rows)
-            const uint64_t da = umma_smem_desc(a_base + k * 2048, A_STAGE_BYTES, 1024);
-            const uint64_t dbd = umma_smem_desc(b_base + k * 2048, A_STAGE_BYTES, 1024);
-            umma_f16(tmem_base + j * 64, da, dbd, idesc, (!first || k != 0) ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + j * 64, da + 128 * k, dbd + 128 * k, idesc, k != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + j * 64, da + 128 * k, dbd + 128 * k, idesc, 1u);
           }
           umma_commit(&empty[stage]);
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }

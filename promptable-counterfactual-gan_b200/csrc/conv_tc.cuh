@@ -1,5 +1,7 @@
 // Tensor-core (tcgen05 / TMEM / TMA-im2col) convolution kernels for sm_100a — host interface.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace pcg {
@@ -52,6 +54,24 @@ void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stre
 // bf16 [Cin][k*k][Cout] with the taps rotated by 180 degrees (dgrad of a stride-1 conv).
 void pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, bf16* fprop, bf16* dgrad,
                           cudaStream_t stream);
+
+// ---- tensor-map builders shared by the tensor-core kernels (driver entry points resolved at run time)
+CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+CUtensorMap make_tmap_im2col_box(const bf16* base, int N, int H, int W, int C, int lower_w, int lower_h,
+                                 int upper_w, int upper_h, int stride);
+CUtensorMap make_tmap_nhwc_box(const bf16* base, int N, int H, int W, int C, int box_w, int box_h);
+
+// ---- 64 -> 64, 3x3, stride 1, pad 1 convolutions with a shared-memory halo tile (conv_tc64.cu) ----------
+// One TMA box per tile brings (R+2) x (W+2) zero-padded pixels; the nine filter taps are shifted views of that
+// tile (UMMA descriptors offset by (r*(W+2)+s) rows), the 72 KB of weights stay resident in shared memory.
+// L2->SM traffic per output tile drops from 216 KB (im2col per tap + weights) to ~23 KB.
+int conv_tc64_grid(int N, int H, int W);             // CTAs launched = rows of the BN-statistics partial buffer
+bool conv_tc64_supported(int H, int W);
+void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const ConvEpilogue& epi, bf16* out,
+                     cudaStream_t stream);
+// part[conv_tc64_grid][9][64 ci][64 co] fp32; reduce with wgrad_reduce_tc().
+void conv_tc64_wgrad(const bf16* x, const bf16* dy, int N, int H, int W, float* part, cudaStream_t stream);
+void conv_tc64_set_variant(int v);                   // bring-up: descriptor base-offset policy
 
 // Debug: what one im2col TMA box of 128 pixels x 64 channels delivers (de-swizzled), for tests.
 void debug_im2col_tile(const bf16* in, int N, int H, int W, int Cin, int ksize, int stride, int pad,

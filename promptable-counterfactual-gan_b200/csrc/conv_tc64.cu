@@ -1,0 +1,479 @@
+// 64 -> 64 channel, 3x3, stride-1, pad-1 convolution kernels with a shared-memory halo tile.
+//
+// The im2col kernels of conv_tc.cu fetch every filter tap from L2 separately (9 x 16 KB per 128 output
+// pixels) and re-fetch the weights for every tile: ~216 KB of L2->SM traffic per tile, which makes them
+// L2-bandwidth bound (8 TB/s) at 6x the MMA time.  Here one 4-D TMA box per tile brings the (R+2) x (W+2)
+// zero-padded input pixels of R output rows (23 KB for 28x28 images), and the nine taps are *shifted views*
+// of that tile: output position i = hh*(W+2) + ww reads tile row i + r*(W+2) + s for tap (r, s), so the A
+// operand of tap (r, s) is the same shared-memory matrix started (r*(W+2)+s) rows later.  The packed weights
+// (72 KB) are loaded once per CTA.  Two of every W+2 accumulator rows are padding columns and are discarded
+// (R*W of 128 MMA rows are useful: 112/128 for 28x28).
+//
+// Replaces: nn.Conv2d(64, 64, 3, padding=1) forward and ConvolutionBackward0 (dgrad with rotated weights,
+// wgrad) of conditional_counteRGAN/mnist/models/generator.py:11,14,49.
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+namespace pcg {
+using namespace tc;
+
+static int g_variant = 0;
+void conv_tc64_set_variant(int v) { g_variant = v; }
+
+constexpr int C64 = 64;
+constexpr int W_BYTES = 9 * 64 * 128;            // resident weights: 9 taps x [64 rows][64 k] bf16
+constexpr int IN_STAGE_BYTES = 24576;            // >= (127 + 2*(W+2) + 2 + 1) * 128 for W <= 28
+constexpr int F_STAGES = 4;
+constexpr int F_THREADS = 320;                   // warp0 TMA, warp1 MMA, warps 2-9 epilogue
+constexpr int F_SMEM_BYTES = 1024 + W_BYTES + F_STAGES * IN_STAGE_BYTES + 8 * 2 * 64 * 4 + 256;
+
+struct F64Params {
+  int N, H, W, WP, R, tiles_per_img, total_tiles;
+  const float* bias;
+  int act;
+  float slope;
+  const bf16* add_src;
+  const bf16* act_ref;
+  int ref_act;
+  float ref_slope;
+  bf16* out;
+  float* stats;
+  int variant;
+};
+
+bool conv_tc64_supported(int H, int W) {
+  const int WP = W + 2;
+  if (WP > 128) return false;
+  const int R = 128 / WP;
+  return R >= 1 && (127 + 2 * WP + 3) * 128 <= IN_STAGE_BYTES && (R + 2) <= 256 && WP <= 256;
+}
+
+int conv_tc64_grid(int N, int H, int W) {
+  const int R = 128 / (W + 2);
+  const long long tiles = (long long)N * ((H + R - 1) / R);
+  const int sms = sm_count();
+  return (int)(tiles < sms ? tiles : sms);
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < cnt / 2; ++j) {
+      const float send = upper ? v[j] : v[j + cnt / 2];
+      const float keep = upper ? v[j + cnt / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ uint64_t a_desc(uint32_t addr, uint32_t lbo, int variant) {
+  // variant 0: swizzle phase taken from the absolute shared-memory address (base_offset = 0)
+  // variant 1: base_offset = (address >> 7) & 7, for starts that are not 1024-byte aligned
+  return umma_smem_desc(addr, lbo, 1024, variant == 1 ? ((addr >> 7) & 7u) : 0u);
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                       const F64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sw = smem;                                   // weights
+  uint8_t* sin = smem + W_BYTES;                        // input halo tiles
+  float* stats_smem = reinterpret_cast<float*>(sin + F_STAGES * IN_STAGE_BYTES);   // [8 warps][2][32]... see below
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + 8 * 2 * 64 * 4);
+  uint64_t* full = bars;                 // [F_STAGES]
+  uint64_t* empty = bars + F_STAGES;     // [F_STAGES]
+  uint64_t* wfull = bars + 2 * F_STAGES; // [1]
+  uint64_t* tfull = wfull + 1;           // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < F_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  }
+  // rows of a halo tile beyond the TMA box are read by the (discarded) padding rows of the MMA: keep them finite
+  for (int i = threadIdx.x; i < F_STAGES * IN_STAGE_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sin)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int box_bytes = (p.R + 2) * p.WP * 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, W_BYTES);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(&tmW, wfull, sw + tap * 8192, tap * 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.R;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], box_bytes);
+        tma_load_4d(&tmX, &full[stage], sin + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n);
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    {
+      // the whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
+      // one elected lane issues the MMAs and commits
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(wfull, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint64_t b0 = umma_smem_desc(smem_u32(sw), 16, 1024);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        // descriptors: constant upper bits, only the start-address field moves (3 instructions per MMA)
+        const uint64_t a0 = a_desc(smem_u32(sin + stage * IN_STAGE_BYTES), 16, p.variant);
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t at = a0 + (uint64_t)(((tap / 3) * p.WP + (tap % 3)) * 8);     // (r*WP+s)*128 B >> 4
+            const uint64_t bt = b0 + (uint64_t)(tap * 512);                               // tap*8192 B >> 4
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, at + 2 * k, bt + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---- epilogue: 8 warps; warp e -> TMEM lane quarter (warp & 3), column half (e >> 2)
+    const int e = warp - 2;
+    const int q = warp & 3, half = e >> 2;
+    const int row = q * 32 + lane;                  // accumulator row = padded position hh*WP + ww
+    const int hh = row / p.WP, ww = row - hh * p.WP;
+    const bool row_ok = hh < p.R && ww < p.W;
+    const int col0 = half * 32;
+    // bias lives in shared memory (read as 8 broadcast float4 per tile) to keep registers for the statistics
+    float* bias_s = stats_smem + 8 * 2 * 32;        // [64], behind the [8][2][32] statistics block
+    if (e == 0) {
+      bias_s[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
+      bias_s[lane + 32] = p.bias ? __ldg(p.bias + lane + 32) : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // BatchNorm statistics: per-thread running sums of the raw accumulators over all tiles of this CTA (64 FP ops
+    // per tile); the bias is folded in analytically and the cross-row reduction runs once, after the last tile.
+    float acc_s[32], acc_q[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc_s[j] = acc_q[j] = 0.f;
+    int nvalid = 0;
+    const bool want_stats = p.stats != nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.R;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * 64 + col0, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);                    // accumulator is in registers: release TMEM early
+      const bool valid = row_ok && (h0 + hh) < p.H;
+      const long long pix = ((long long)n * p.H + h0 + hh) * p.W + ww;
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + j4 * 4);
+          v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
+          v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+          v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
+          v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+        }
+        if (p.act == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        } else if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.add_src != nullptr) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.add_src + pix * C64 + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 u = __ldg(src + j4);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(h2[t]);
+              v[j4 * 8 + t * 2] += f.x;
+              v[j4 * 8 + t * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (p.act_ref != nullptr) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.act_ref + pix * C64 + col0);
+          const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 u = __ldg(src + j4);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(h2[t]);
+              v[j4 * 8 + t * 2] *= (f.x > 0.f ? 1.f : neg);
+              v[j4 * 8 + t * 2 + 1] *= (f.y > 0.f ? 1.f : neg);
+            }
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * C64 + col0);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 u;
+          u.x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1]);
+          u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+          u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+          u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+          dst[j4] = u;
+        }
+        if (want_stats) {           // statistics are only requested with act == NONE and no add/act_ref
+          ++nvalid;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(r[j]);
+            acc_s[j] += a;
+            acc_q[j] = fmaf(a, a, acc_q[j]);
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (want_stats) {
+      // sum(a+b) = sum a + n b ; sum (a+b)^2 = sum a^2 + 2 b sum a + n b^2
+      const float nv = (float)nvalid;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float b = bias_s[col0 + j], sa = acc_s[j];
+        acc_q[j] = acc_q[j] + 2.f * b * sa + nv * b * b;
+        acc_s[j] = sa + nv * b;
+      }
+      const float ts = colsum32(acc_s, lane);      // lane l now holds column col0 + l over this warp's 32 rows
+      const float tq = colsum32(acc_q, lane);
+      // stats_smem[e][2][32]: per epilogue warp (sum, sumsq) of its 32 columns; fixed-order add over the 4 quarters
+      stats_smem[(e * 2 + 0) * 32 + lane] = ts;
+      stats_smem[(e * 2 + 1) * 32 + lane] = tq;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int t = threadIdx.x - 64;              // 0..255
+      if (t < 128) {
+        const int which = t >> 6, col = t & 63;    // which: 0 sum, 1 sumsq
+        const int hf = col >> 5, l = col & 31;
+        float s = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) s += stats_smem[(((hf * 4 + qq) * 2) + which) * 32 + l];
+        p.stats[(size_t)blockIdx.x * 128 + which * 64 + col] = s;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const ConvEpilogue& epi, bf16* out,
+                     cudaStream_t stream) {
+  PCG_PROFILE("conv_tc64_fprop", stream);
+  PCG_REQUIRE(conv_tc64_supported(H, W), "image too wide for the halo-tile kernel");
+  F64Params p;
+  p.N = N; p.H = H; p.W = W; p.WP = W + 2; p.R = 128 / p.WP;
+  p.tiles_per_img = (H + p.R - 1) / p.R;
+  p.total_tiles = N * p.tiles_per_img;
+  p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
+  p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
+  p.out = out; p.stats = epi.stats; p.variant = g_variant;
+  PCG_REQUIRE(epi.stats == nullptr || (epi.act == ACT_NONE && epi.add_src == nullptr && p.act_ref == nullptr),
+              "BatchNorm statistics are taken of (accumulator + bias) only");
+  CUtensorMap tmX = make_tmap_nhwc_box(in, N, H, W, 64, p.WP, p.R + 2);
+  CUtensorMap tmW = make_tmap_2d(wpk, 64, 576, 64);
+  static bool configured = false;
+  if (!configured) {
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    configured = true;
+  }
+  conv_tc64_fprop_kernel<<<conv_tc64_grid(N, H, W), F_THREADS, F_SMEM_BYTES, stream>>>(tmX, tmW, p);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dW[tap][ci][co] = sum_p x[p@tap][ci] * dy[p][co]; K = the 128 padded positions of a tile
+// ------------------------------------------------------------------------------------------
+constexpr int G_STAGES = 4;
+constexpr int DY_STAGE_BYTES = 16384;            // 128 rows x 128 B (rows >= R*(W+2) stay zero)
+constexpr int G_THREADS = 192;
+constexpr int G_SMEM_BYTES = 1024 + G_STAGES * (IN_STAGE_BYTES + DY_STAGE_BYTES) + 256;
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, int N, int H,
+                       int W, int WP, int R, int tiles_per_img, int total_tiles, int variant,
+                       float* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sx = smem;
+  uint8_t* sdy = smem + G_STAGES * IN_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdy + G_STAGES * DY_STAGE_BYTES);
+  uint64_t* full = bars;               // [G_STAGES]
+  uint64_t* empty = bars + G_STAGES;   // [G_STAGES]
+  uint64_t* done = bars + 2 * G_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < G_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  // zero everything once: x rows past the box are read by padding positions whose dy rows are zero (must be
+  // finite), dy rows [R*WP, 128) must be exactly zero
+  for (int i = threadIdx.x; i < G_STAGES * (IN_STAGE_BYTES + DY_STAGE_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int xbytes = (R + 2) * WP * 128, dybytes = R * WP * 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, h0 = (tile % tiles_per_img) * R;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], xbytes + dybytes);
+        tma_load_4d(&tmX, &full[stage], sx + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n);
+        tma_load_4d(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES, 0, 0, h0, n);
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);     // A, B both MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t x_base = smem_u32(sx + stage * IN_STAGE_BYTES);
+        const uint64_t b0 = umma_smem_desc(smem_u32(sdy + stage * DY_STAGE_BYTES), 16, 1024);
+        if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int t0 = 2 * j, t1 = (j < 4) ? t0 + 1 : t0;
+          const uint32_t o0 = (uint32_t)((t0 / 3) * WP + (t0 % 3)) * 128u;
+          const uint32_t o1 = (uint32_t)((t1 / 3) * WP + (t1 % 3)) * 128u;
+          const uint32_t lbo = (j < 4) ? (o1 - o0) : 128u;            // distance between the two 64-channel M blocks
+          const uint64_t aj = a_desc(x_base + o0, lbo, variant);
+          if (first) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + j * 64, aj + 128 * k, b0 + 128 * k, idesc, k != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + j * 64, aj + 128 * k, b0 + 128 * k, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        first = false;
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(done);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* my = part + (size_t)blockIdx.x * 9 * 64 * 64;
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+      const int tap = 2 * j + (row >> 6), ci = row & 63;
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + j * 64 + chunk * 32, r);
+        tmem_ld_wait();
+        if (tap < 9) {
+          float4* dst = reinterpret_cast<float4*>(my + ((size_t)tap * 64 + ci) * 64 + chunk * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            dst[j4] = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
+                                  __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+void conv_tc64_wgrad(const bf16* x, const bf16* dy, int N, int H, int W, float* part, cudaStream_t stream) {
+  PCG_PROFILE("conv_tc64_wgrad", stream);
+  PCG_REQUIRE(conv_tc64_supported(H, W), "image too wide for the halo-tile kernel");
+  const int WP = W + 2, R = 128 / WP;
+  const int tiles_per_img = (H + R - 1) / R;
+  CUtensorMap tmX = make_tmap_nhwc_box(x, N, H, W, 64, WP, R + 2);
+  CUtensorMap tmDY = make_tmap_nhwc_box(dy, N, H, W, 64, WP, R);
+  static bool configured = false;
+  if (!configured) {
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    configured = true;
+  }
+  conv_tc64_wgrad_kernel<<<conv_tc64_grid(N, H, W), G_THREADS, G_SMEM_BYTES, stream>>>(
+      tmX, tmDY, N, H, W, WP, R, tiles_per_img, N * tiles_per_img, g_variant, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+}  // namespace pcg

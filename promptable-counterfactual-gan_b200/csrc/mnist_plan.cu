@@ -71,6 +71,7 @@ struct ConvLayer {
   bf16* tcd = nullptr;        // bf16 [Cin][taps][Cout], taps rotated
   bf16* tcs2 = nullptr;       // bf16 parity-class matrices of the stride-2 data gradient
   bool tc_fprop = false, tc_dgrad = false, tc_wgrad = false, tc_dgrad_s2 = false;
+  bool tc64 = false;          // 64->64 3x3 s1 p1: halo-tile kernels (conv_tc64.cu)
   int perm_hw = 0;
   std::string name, tag_f, tag_d, tag_w;
 
@@ -188,6 +189,7 @@ struct MnistPlan : PlanBase {
         L.tc_dgrad = true;
       }
       if (Cin == 64 && Cout == 64 && k == 3 && stride == 1 && pad == 1 && dw) L.tc_wgrad = true;
+      L.tc64 = Cin == 64 && Cout == 64 && k == 3 && stride == 1 && pad == 1 && conv_tc64_supported(H, W);
     }
     if (kBf16 && cfg.use_tensor_cores && stride == 2 && k == 3 && pad == 1 && Cout % 64 == 0 && Cin % 32 == 0 &&
         need_wd && perm_hw == 0) {
@@ -307,6 +309,11 @@ struct MnistPlan : PlanBase {
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, bf16>::value) {
+      if (L.tc_fprop && L.tc64) {
+        conv_tc64_fprop(in, g.N, g.H, g.W, L.tcf, to_tc(e, stats), out, s);
+        if (nparts) *nparts = conv_tc64_grid(g.N, g.H, g.W);
+        return;
+      }
       if (L.tc_fprop) {
         conv_tc_fprop(in, g.N, g.H, g.W, g.Cin, L.tcf, g.Cout, g.ksize, g.stride, g.pad, to_tc(e, stats), out, s);
         if (nparts) *nparts = conv_tc_grid(g.Mout(), g.Cout);
@@ -330,6 +337,10 @@ struct MnistPlan : PlanBase {
       return;
     }
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, bf16>::value) {
+      if (L.tc_dgrad && L.tc64) {
+        conv_tc64_fprop(dout, g.N, g.H, g.W, L.tcd, to_tc(e, nullptr), din, s);
+        return;
+      }
       if (L.tc_dgrad) {
         conv_tc_fprop(dout, g.N, g.H, g.W, g.Cout, L.tcd, g.Cin, g.ksize, 1, g.pad, to_tc(e, nullptr), din, s);
         return;
@@ -347,6 +358,11 @@ struct MnistPlan : PlanBase {
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TDy, bf16>::value) {
+      if (L.tc_wgrad && L.tc64) {
+        conv_tc64_wgrad(in, dout, g.N, g.H, g.W, tc_part, s);
+        wgrad_reduce_tc(tc_part, conv_tc64_grid(g.N, g.H, g.W), L.dw, s);
+        return;
+      }
       if (L.tc_wgrad) {
         conv_tc_wgrad64(in, dout, g.N, g.H, g.W, tc_part, s);
         wgrad_reduce_tc(tc_part, conv_tc_wgrad_grid(g.Mout()), L.dw, s);

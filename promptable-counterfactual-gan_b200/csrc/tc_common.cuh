@@ -67,6 +67,14 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4-D tiled load (NHWC box): coordinates (c, w, h, n) of the box corner; out-of-range elements are zero-filled.
+__device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, void* dst, int c, int w, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
 // 4-D im2col load on an NHWC tensor: coordinates (c, w, h, n) of the first pixel in the
 // padded "base pixel" space, filter-tap offsets (off_w, off_h).
 __device__ __forceinline__ void tma_load_im2col_4d(const void* desc, uint64_t* bar, void* dst, int c,
@@ -140,14 +148,20 @@ __device__ __forceinline__ void tmem_ld_wait() {
 //   MN-major : rows of 128 B (64 bf16 along M/N) indexed by k; 8-k groups SBO bytes apart;
 //              successive 64-element M/N blocks LBO bytes apart.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;                  // [49,52) matrix base offset
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);                 // [0,14)  start address
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;        // [16,30) leading byte offset
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;        // [32,46) stride byte offset
   d |= 1ull << 46;                                                    // [46,48) version = 1
   d |= 2ull << 61;                                                    // [61,64) SWIZZLE_128B
   return d;
+}
+// The single MMA-issuing thread must spend only a few instructions per tcgen05.mma (an M128xN64xK16 MMA lasts
+// 32 cycles), so descriptors are built once and advanced by adding to the 14-bit start-address field.
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) {
+  return desc + (uint64_t)(bytes >> 4);
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and f32 D.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {

@@ -186,6 +186,88 @@ def exp_perf():
     print("PERF DONE")
 
 
+def exp_v2():
+    for variant in (0, 1):
+        L.pcg_conv_tc64_set_variant(variant)
+        torch.manual_seed(4)
+        print("=== variant", variant)
+        for (N, HW) in [(8, 28), (3, 28), (5, 14)]:
+            x = torch.randn(N, 64, HW, HW, device=dev)
+            w = torch.randn(64, 64, 3, 3, device=dev) * (2.0 / 576) ** 0.5
+            b = torch.randn(64, device=dev) * 0.1
+            xn = nhwc_bf16(x)
+            wf, wd = pack(w)
+            grid = L.pcg_conv_tc64_grid(N, HW, HW)
+            out = torch.full((N, HW, HW, 64), 7.0, dtype=torch.bfloat16, device=dev)
+            stats = torch.zeros(grid, 128, device=dev)
+            _lib.check(L.pcg_conv_tc64_fprop(P(xn), N, HW, HW, P(wf), P(b), 0, ctypes.c_float(0.2), None, None, 0, P(out),
+                                             P(stats), _lib.stream_ptr()))
+            sync()
+            ref = F.conv2d(xn.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=1)
+            got = out.float().permute(0, 3, 1, 2)
+            s = stats.sum(0)
+            print(f"v2 fprop N={N} {HW}x{HW}: max abs err {(got - ref).abs().max().item():.4e} (ref max {ref.abs().max().item():.2f})"
+                  f"  stats rel err {((s[:64] - ref.sum(dim=(0, 2, 3))).abs().max() / ref.sum(dim=(0, 2, 3)).abs().max()).item():.2e}"
+                  f" {((s[64:] - (ref * ref).sum(dim=(0, 2, 3))).abs().max() / (ref * ref).sum(dim=(0, 2, 3)).abs().max()).item():.2e}")
+            dy = torch.randn(N, 64, HW, HW, device=dev) * 0.1
+            dyn = nhwc_bf16(dy)
+            part = torch.zeros(grid, 9 * 64 * 64, device=dev)
+            dw = torch.zeros(64, 64, 3, 3, device=dev)
+            _lib.check(L.pcg_conv_tc64_wgrad(P(xn), P(dyn), N, HW, HW, P(part), P(dw), _lib.stream_ptr()))
+            sync()
+            wz = torch.zeros(64, 64, 3, 3, device=dev, requires_grad=True)
+            yy = F.conv2d(xn.float().permute(0, 3, 1, 2), wz, None, padding=1)
+            (gw,) = torch.autograd.grad(yy, wz, dyn.float().permute(0, 3, 1, 2))
+            print(f"v2 wgrad N={N}: max abs err {(dw - gw).abs().max().item():.4e} (ref max {gw.abs().max().item():.2f})")
+    print("V2 DONE")
+
+
+def exp_v2perf():
+    L.pcg_conv_tc64_set_variant(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    torch.manual_seed(3)
+    N, HW = 512, 28
+    bufs = [torch.randn(N, HW, HW, 64, device=dev).to(torch.bfloat16) for _ in range(4)]
+    outs = [torch.empty_like(bufs[0]) for _ in range(4)]
+    w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
+    b = torch.zeros(64, device=dev)
+    wf, wd = pack(w)
+    grid = L.pcg_conv_tc64_grid(N, HW, HW)
+    stats = torch.zeros(grid, 128, device=dev)
+    part = torch.zeros(grid, 9 * 64 * 64, device=dev)
+    dw = torch.zeros(64, 64, 3, 3, device=dev)
+    st = _lib.stream_ptr()
+    M = N * HW * HW
+    it = {"i": 0}
+
+    def run_f():
+        i = it["i"] = (it["i"] + 1) % 4
+        _lib.check(L.pcg_conv_tc64_fprop(P(bufs[i]), N, HW, HW, P(wf), P(b), 0, ctypes.c_float(0.2), None, None, 0,
+                                         P(outs[i]), P(stats), st))
+
+    def run_d():
+        i = it["i"] = (it["i"] + 1) % 4
+        _lib.check(L.pcg_conv_tc64_fprop(P(bufs[i]), N, HW, HW, P(wd), None, 0, ctypes.c_float(0.2), P(outs[(i + 1) % 4]),
+                                         None, 0, P(outs[i]), None, st))
+
+    def run_w():
+        i = it["i"] = (it["i"] + 1) % 4
+        _lib.check(L.pcg_conv_tc64_wgrad(P(bufs[i]), P(outs[i]), N, HW, HW, P(part), P(dw), st))
+
+    for name, fn in (("v2 fprop+stats", run_f), ("v2 dgrad+add", run_d), ("v2 wgrad+reduce", run_w)):
+        for _ in range(3):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"{name}: {ms * 1e3:.1f} us  {2.0 * M * 64 * 576 / ms / 1e9:.1f} TFLOP/s")
+    print("V2PERF DONE")
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    {"im2col": exp_im2col, "fprop": exp_fprop, "wgrad": exp_wgrad, "perf": exp_perf}[sys.argv[1]]()
+    {"im2col": exp_im2col, "fprop": exp_fprop, "wgrad": exp_wgrad, "perf": exp_perf, "v2": exp_v2, "v2perf": exp_v2perf}[sys.argv[1]]()
