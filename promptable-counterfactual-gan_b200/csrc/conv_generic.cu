@@ -271,7 +271,13 @@ skinny_conv_v2_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt
       long long t = m;
       rc.w = (int)(t % outW); t /= outW;
       rc.h = (int)(t % outH); rc.n = (int)(t / outH);
-      for (int tap = 0; tap < taps; ++tap) {
+      // data gradient: only taps with (h + pad - r) % stride == 0 contribute -> visit exactly those
+      const int r0 = (MODE == MODE_DGRAD) ? (rc.h + ga.pad) % ga.stride : 0;
+      const int s0 = (MODE == MODE_DGRAD) ? (rc.w + ga.pad) % ga.stride : 0;
+      const int step = (MODE == MODE_DGRAD) ? ga.stride : 1;
+      for (int r = r0; r < ga.ksize; r += step)
+      for (int sx = s0; sx < ga.ksize; sx += step) {
+        const int tap = r * ga.ksize + sx;
         const long long off = ga.pixel_offset(rc, tap);
         if (off < 0) continue;
         float a[8];
@@ -574,6 +580,13 @@ __global__ void wgrad_reduce_generic_kernel(const float* __restrict__ part, int 
   const int co = idx / K, k = idx - co * K;
   const int tap = k / Cin, ci = k - tap * Cin;
   dw[((size_t)co * Cin + ci) * taps + tap] = s;
+}
+
+void wgrad_reduce_generic(const float* part, int nz, int Cout, int Cin, int taps, float* dw, cudaStream_t stream) {
+  PCG_PROFILE("wgrad_reduce", stream);
+  wgrad_reduce_generic_kernel<<<cdiv((long long)Cout * Cin * taps, 256), 256, 0, stream>>>(part, nz, Cout, Cin, taps, dw);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
 }
 
 static bool wgrad_is_skinny(const ConvGeom& g) {

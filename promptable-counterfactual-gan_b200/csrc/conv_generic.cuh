@@ -46,6 +46,9 @@ template <typename TIn, typename TDy>
 void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float* scratch, float* dw,
                         cudaStream_t stream);
 
+// dw[co][ci][tap] (torch OIHW) = sum_z part[z][co][(tap, ci)], fixed order.
+void wgrad_reduce_generic(const float* part, int nz, int Cout, int Cin, int taps, float* dw, cudaStream_t stream);
+
 // torch OIHW fp32 -> wf [Cout][taps][Cin] and wd [Cin][taps][Cout] (either may be nullptr).
 // `perm_hw` > 0: the Cin axis of a Linear that consumes a flattened NCHW [C][perm_hw] map is
 // re-ordered to NHWC flatten order (classifier fc.1, classifier.py:17-18).

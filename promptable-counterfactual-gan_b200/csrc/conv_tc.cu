@@ -651,6 +651,197 @@ conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// general wgrad on the tensor cores (3x3, pad 1, stride 1 or 2, Cin % 64 == 0, Cout % 64 == 0)
+//   part[z][co][(tap, ci)] = sum over the z-th pixel slice of dY[p][co] * X[p@tap][ci]
+// CTA = (pair of (tap, 64-channel block) units, K slice).  A = two im2col tiles of X (MN-major, M = 128),
+// B = the dY tile (MN-major, N = Cout tile up to 256), K = 128 pixels per pipeline stage; one fp32
+// accumulator (128 lanes x Ntile columns) in TMEM per CTA; partials reduced by wgrad_reduce_generic.
+// ------------------------------------------------------------------------------------------
+constexpr int WGG_THREADS = 192;
+constexpr int WGG_STAGES = 2;
+
+template <int NT>   // Cout tile: 64, 128 or 256
+struct WggCfg {
+  static constexpr int DY_BYTES = (NT / 64) * A_STAGE_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + DY_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + WGG_STAGES * STAGE_BYTES + 256;
+};
+
+struct WggParams {
+  int P, Ho, Wo, stride, cin_blocks, Cout, K;       // K = 9 * Cin
+  int units, pairs, n_tiles, ksplit, kb_per_split, num_kb;
+  float* part;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(WGG_THREADS, 1)
+conv_tc_wgrad_general_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                             const WggParams p) {
+  using Cfg = WggCfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WGG_STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + WGG_STAGES;
+  uint64_t* done = bars + 2 * WGG_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work item
+  int w = blockIdx.x;
+  const int z = w % p.ksplit; w /= p.ksplit;
+  const int nt = w % p.n_tiles; w /= p.n_tiles;
+  const int pair = w;
+  const int u0 = 2 * pair, u1 = (u0 + 1 < p.units) ? u0 + 1 : u0;
+  const int kb0 = z * p.kb_per_split;
+  const int kb1 = (kb0 + p.kb_per_split < p.num_kb) ? kb0 + p.kb_per_split : p.num_kb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < WGG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, NT < 32 ? 32 : NT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int hw = p.Ho * p.Wo;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int p0 = kb * TILE_M;
+        const int n_img = p0 / hw, rem = p0 % hw;
+        const int cw = (rem % p.Wo) * p.stride - 1, ch = (rem / p.Wo) * p.stride - 1;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES;
+        for (int h = 0; h < 2; ++h) {
+          const int u = h ? u1 : u0;
+          const int tap = u / p.cin_blocks, cb = u % p.cin_blocks;
+          tma_load_im2col_4d(&tmX, &full[stage], dst + h * A_STAGE_BYTES, cb * 64, cw, ch, n_img, (uint16_t)(tap % 3),
+                             (uint16_t)(tap / 3));
+        }
+        for (int nb = 0; nb < NT / 64; ++nb)
+          tma_load_2d(&tmDY, &full[stage], dst + (2 + nb) * A_STAGE_BYTES, nt * NT + nb * 64, p0);
+        if (++stage == WGG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+      const uint64_t da = umma_smem_desc(base, A_STAGE_BYTES, 1024);                        // M blocks 16 KB apart
+      const uint64_t db = umma_smem_desc(base + 2 * A_STAGE_BYTES, A_STAGE_BYTES, 1024);    // N blocks 16 KB apart
+      if (elect_one()) {
+        if (kb == kb0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_f16(tmem_base, da + 128 * k, db + 128 * k, idesc, k != 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_f16(tmem_base, da + 128 * k, db + 128 * k, idesc, 1u);
+        }
+        umma_commit(&empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == WGG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int u = (row >> 6) ? u1 : u0;
+    const bool row_ok = (row < 64) || (u1 != u0);
+    const int kcol = u * 64 + (row & 63);           // (tap, ci) column of the partial matrix
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* my = p.part + (size_t)z * p.Cout * p.K;
+    const bool any = kb1 > kb0;
+#pragma unroll 1
+    for (int chunk = 0; chunk < NT / 32; ++chunk) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + chunk * 32, r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = nt * NT + chunk * 32 + j;
+          my[(size_t)co * p.K + kcol] = any ? __uint_as_float(r[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, NT < 32 ? 32 : NT);
+  }
+}
+
+static void wgg_plan(int N, int H, int W, int Cin, int Cout, int stride, WggParams& p, int& nt_size) {
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  p.P = N * Ho * Wo; p.Ho = Ho; p.Wo = Wo; p.stride = stride;
+  p.cin_blocks = Cin / 64; p.Cout = Cout; p.K = 9 * Cin;
+  p.units = 9 * p.cin_blocks; p.pairs = (p.units + 1) / 2;
+  nt_size = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
+  p.n_tiles = Cout / nt_size;
+  p.num_kb = (p.P + TILE_M - 1) / TILE_M;
+  int want = (2 * sm_count()) / (p.pairs * p.n_tiles);
+  if (want < 1) want = 1;
+  if (want > p.num_kb) want = p.num_kb;
+  p.kb_per_split = (p.num_kb + want - 1) / want;
+  p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+}
+
+int conv_tc_wgrad_general_splits(int N, int H, int W, int Cin, int Cout, int stride) {
+  WggParams p; int nt;
+  wgg_plan(N, H, W, Cin, Cout, stride, p, nt);
+  return p.ksplit;
+}
+
+void conv_tc_wgrad_general(const bf16* x, const bf16* dy, int N, int H, int W, int Cin, int Cout, int stride,
+                           float* part, cudaStream_t stream) {
+  PCG_PROFILE("conv_tc_wgrad_general", stream);
+  PCG_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && (stride == 1 || stride == 2), "unsupported wgrad shape");
+  WggParams p; int nt;
+  wgg_plan(N, H, W, Cin, Cout, stride, p, nt);
+  p.part = part;
+  CUtensorMap tmX = make_tmap_im2col(x, N, H, W, Cin, 3, stride, 1);
+  CUtensorMap tmDY = make_tmap_2d(dy, (uint64_t)p.P, (uint64_t)Cout, 128);
+  const int grid = p.pairs * p.n_tiles * p.ksplit;
+#define PCG_WGG(NTV)                                                                                               \
+  {                                                                                                                \
+    static bool configured = false;                                                                                \
+    if (!configured) {                                                                                             \
+      PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_general_kernel<NTV>,                                       \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, WggCfg<NTV>::SMEM_BYTES)); \
+      configured = true;                                                                                           \
+    }                                                                                                              \
+    conv_tc_wgrad_general_kernel<NTV><<<grid, WGG_THREADS, WggCfg<NTV>::SMEM_BYTES, stream>>>(tmX, tmDY, p);       \
+  }
+  if (nt == 256) PCG_WGG(256) else if (nt == 128) PCG_WGG(128) else PCG_WGG(64)
+#undef PCG_WGG
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 int conv_tc_wgrad_grid(long long M) {
   long long nb = (M + TILE_M - 1) / TILE_M;
   int sms = sm_count();

@@ -50,6 +50,12 @@ void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* 
 // is produced by the caller's BN/bias kernels, not here.
 void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream);
 
+// General tensor-core wgrad (3x3, pad 1, stride 1|2, Cin % 64 == 0, Cout % 64 == 0):
+//   part[z][co][(tap, ci)] fp32, z < conv_tc_wgrad_general_splits(...); reduce with wgrad_reduce_generic().
+int conv_tc_wgrad_general_splits(int N, int H, int W, int Cin, int Cout, int stride);
+void conv_tc_wgrad_general(const bf16* x, const bf16* dy, int N, int H, int W, int Cin, int Cout, int stride,
+                           float* part, cudaStream_t stream);
+
 // fp32 OIHW [Cout][Cin][k][k] -> bf16 [Cout][k*k][Cin] (fprop) and, if dgrad != nullptr,
 // bf16 [Cin][k*k][Cout] with the taps rotated by 180 degrees (dgrad of a stride-1 conv).
 void pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, bf16* fprop, bf16* dgrad,

@@ -72,6 +72,7 @@ struct ConvLayer {
   bf16* tcs2 = nullptr;       // bf16 parity-class matrices of the stride-2 data gradient
   bool tc_fprop = false, tc_dgrad = false, tc_wgrad = false, tc_dgrad_s2 = false;
   bool tc64 = false;          // 64->64 3x3 s1 p1: halo-tile kernels (conv_tc64.cu)
+  bool tc_wgrad_gen = false;  // general tensor-core wgrad (conv_tc.cu)
   int perm_hw = 0;
   std::string name, tag_f, tag_d, tag_w;
 
@@ -190,6 +191,11 @@ struct MnistPlan : PlanBase {
       }
       if (Cin == 64 && Cout == 64 && k == 3 && stride == 1 && pad == 1 && dw) L.tc_wgrad = true;
       L.tc64 = Cin == 64 && Cout == 64 && k == 3 && stride == 1 && pad == 1 && conv_tc64_supported(H, W);
+      if (dw && k == 3 && pad == 1 && !L.tc_wgrad) {
+        L.tc_wgrad_gen = true;
+        const size_t sc = (size_t)conv_tc_wgrad_general_splits(N, H, W, Cin, Cout, stride) * Cout * Cin * 9;
+        if (sc > wg_scratch_elems) wg_scratch_elems = sc;
+      }
     }
     if (kBf16 && cfg.use_tensor_cores && stride == 2 && k == 3 && pad == 1 && Cout % 64 == 0 && Cin % 32 == 0 &&
         need_wd && perm_hw == 0) {
@@ -361,6 +367,12 @@ struct MnistPlan : PlanBase {
       if (L.tc_wgrad && L.tc64) {
         conv_tc64_wgrad(in, dout, g.N, g.H, g.W, tc_part, s);
         wgrad_reduce_tc(tc_part, conv_tc64_grid(g.N, g.H, g.W), L.dw, s);
+        return;
+      }
+      if (L.tc_wgrad_gen) {
+        conv_tc_wgrad_general(in, dout, g.N, g.H, g.W, g.Cin, g.Cout, g.stride, wg_scratch, s);
+        wgrad_reduce_generic(wg_scratch, conv_tc_wgrad_general_splits(g.N, g.H, g.W, g.Cin, g.Cout, g.stride), g.Cout,
+                             g.Cin, 9, L.dw, s);
         return;
       }
       if (L.tc_wgrad) {
