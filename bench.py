@@ -233,15 +233,17 @@ def run_native(args):
 
     # ---- per-launcher device time inside the step (eager, CUDA events on the launching stream)
     prof, roof, detail = None, None, None
+    # every rank runs the same eager steps (the step contains collectives when world > 1); rank 0 reports
+    import ctypes
+    tr.use_graph = False
+    _lib.check(L.pcg_profile_begin())
+    nprof = 3
+    for i in range(nprof):
+        tr.step(*ring[i % 4])
+    buf = ctypes.create_string_buffer(1 << 16)
+    _lib.check(L.pcg_profile_end(buf, ctypes.c_size_t(len(buf))))
+    tr.use_graph = tr_eager_graph
     if rank == 0:
-        import ctypes
-        tr.use_graph = False
-        _lib.check(L.pcg_profile_begin())
-        nprof = 3
-        for i in range(nprof):
-            tr.step(*ring[i % 4])
-        buf = ctypes.create_string_buffer(1 << 16)
-        _lib.check(L.pcg_profile_end(buf, ctypes.c_size_t(len(buf))))
         prof = json.loads(buf.value.decode())
         tot = sum(v["ms"] for v in prof.values())
         for v in prof.values():
@@ -262,11 +264,11 @@ def run_native(args):
             flops_per_step = 26 * CONV_FLOPS
             achieved = flops_per_step / (k["ms_per_step"] * 1e-3) / 1e12
             peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-            roof = {"bound": "tensor", "kernel": "conv_tc64_fprop_kernel (tcgen05 halo-tile conv 64->64, 13 fprop + 13 dgrad per step)",
+            roof = {"bound": "tensor",
+                    "kernel": "conv_tc64_fprop_kernel (tcgen05 halo-tile conv 64->64, 13 fprop + 13 dgrad per step)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside the step)",
                     "avg_launch_us": k["ms"] / k["launches"] * 1e3}
-        tr.use_graph = tr_eager_graph
 
     if rank == 0:
         cpu = None

@@ -71,10 +71,14 @@ class CounterGanTrainer:
         self.graphs = {}
         self.static = {}
 
+    def _step_cfg_grad_scale(self):
+        """Gradients are summed by the all-reduce; the 1/world_size average is folded into Adam."""
+        return 1.0 / self.world
+
     def _step_cfg(self):
         c = self.cfg
         return P.StepConfig(g_lr=c.g_lr, d_lr=c.d_lr, lambda_adv=c.lambda_adv, lambda_cls=c.lambda_cls,
-                            lambda_reg=c.lambda_reg, lambda_mask=c.lambda_mask, grad_scale=1.0 / self.world,
+                            lambda_reg=c.lambda_reg, lambda_mask=c.lambda_mask, grad_scale=self._step_cfg_grad_scale(),
                             precision=self.precision)
 
     def plan(self, bs):
@@ -146,7 +150,8 @@ class CounterGanTrainer:
     def _capture_fn(fn):
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g):
+        # thread_local: other threads (e.g. the NCCL watchdog polling events) must not invalidate the capture
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             fn()
         return g
 
