@@ -180,6 +180,67 @@ int pcg_mnist_c_forward(pcg_mnist_plan* plan, const float* x, float* logits, voi
 int pcg_mnist_debug_tensor(pcg_mnist_plan* plan, const char* name, void** ptr, long long* numel,
                            int* dtype);
 
+/* ------------------------------------------------------------------------------------------
+ * Primitive operators (fp32, NHWC / row-major) composed by the Python step plans of the other
+ * hot-path configurations: conditional_gan/moons/make_moons_cgan.py:83-135,
+ * simple_gan/moons/make_moons_gan.py:49-93, conditional_counteRGAN/{moons,house_sales_kc_usa}/trainer.py,
+ * dconv_gan/mnist/mnist_dcgan.py:143-175.  nn.Linear is the 1x1 case of the convolution entry points
+ * (weights [out][in] == [Cout][1][Cin]); nn.ConvTranspose2d forward is pcg_conv_dgrad of the mirrored
+ * convolution, its input gradient pcg_conv_fprop.
+ * ------------------------------------------------------------------------------------------ */
+int pcg_conv_fprop(const float* in, int N, int H, int W, int Cin, const float* wf /*[Cout][k*k][Cin]*/, int Cout,
+                   int k, int stride, int pad, const float* bias, int act, float slope, const float* add_src,
+                   float* out, void* stream);
+int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float* wd /*[Cin][k*k][Cout]*/, int Cout,
+                   int k, int stride, int pad, const float* add_src, const float* act_ref, int ref_act,
+                   float ref_slope, float* din, void* stream);
+long long pcg_conv_wgrad_scratch(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad);
+int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int Cin, int Cout, int k, int stride,
+                   int pad, float* scratch, float* dw /*torch OIHW*/, void* stream);
+int pcg_pack_conv_weights(const float* w /*torch OIHW*/, int Cout, int Cin, int k, int perm_hw, float* wf, float* wd,
+                          void* stream);
+long long pcg_stat_scratch_floats(int C);
+int pcg_colsum(const float* a, long long M, int C, float* scratch, float* out, void* stream);
+/* nn.BatchNorm{1,2}d in train mode over M rows x C channels (+ fused activation), and its backward
+ * (dz = gradient wrt the activation output; dbias_prev = column sums of dy, the bias gradient of the layer in front) */
+int pcg_bn_train_fwd(const float* y, long long M, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
+                     float* rstd, float* scale, float* shift, int act, float slope, float* z, float* scratch,
+                     void* stream);
+int pcg_bn_train_bwd(const float* dz, const float* y, long long M, int C, const float* gamma, const float* mean,
+                     const float* rstd, const float* scale, const float* shift, float gscale, int act, float slope,
+                     float* dy, float* dgamma, float* dbeta, float* dbias_prev, float* c12, float* scratch,
+                     float* scratch2, void* stream);
+int pcg_bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,
+                const float* rv, float eps, float* y, float* scale_out, void* stream);
+int pcg_scale_cols(const float* dy, long long rows, int C, const float* scale, float* dx, void* stream);
+/* elementwise: op codes 1 relu, 2 lrelu(a), 3 sigmoid, 4 tanh, 5 scale(a), 6 copy; binary 0 add (alpha*a+beta*b), 1 mul */
+int pcg_unary(const float* x, long long n, int op, float a, float* y, void* stream);
+int pcg_unary_bwd(const float* dy, const float* y, long long n, int op, float a, float* dx, void* stream);
+int pcg_binary(const float* a, const float* b, long long n, int op, float alpha, float beta, float* out, void* stream);
+int pcg_copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows,
+                  int ncols, float alpha, int accumulate, void* stream);
+int pcg_onehot(const long long* lab, long long rows, int nc, float* dst, int dst_ld, int c0, void* stream);
+int pcg_reduce_scalar(const float* x, long long n, int absval, float scale, float* out, float gscale, float* dx,
+                      void* stream);
+int pcg_rownorm_mean(const float* x, long long rows, int cols, int p, float* out, float gscale, float* dx,
+                     void* stream);
+/* kind 0: -mean log(sigmoid) terms on logits; 1: BCELoss (log clamped at -100); 2: Wasserstein mean */
+int pcg_gan_loss(const float* z, int n, int kind, float t, float wgt, float* out_loss, float* out_aux, float* dz,
+                 void* stream);
+int pcg_combine_scalars(int n, const float* host_coeffs, const float* const* host_ptrs, float* out, void* stream);
+int pcg_spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
+                          float* sigma, void* stream);
+int pcg_spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
+                          const float* sigma, float* dW, void* stream);
+int pcg_gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y,
+                           void* stream);
+int pcg_softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, void* stream);
+int pcg_ce_loss(const float* logits, const long long* target, int B, int NC, float wgt, float* loss, float* dlogits,
+                void* stream);
+int pcg_adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
+                  float beta2, float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

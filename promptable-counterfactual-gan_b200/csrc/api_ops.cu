@@ -1,0 +1,189 @@
+// extern "C" wrappers of the primitive operators used by the Python-composed step plans
+// (pcg_b200/ops.py).  fp32, row-major / NHWC; see include/pcg.h for the contracts.
+#include "../../include/pcg.h"
+
+#include "common.cuh"
+#include "conv_generic.cuh"
+#include "elementwise.cuh"
+#include "ops.cuh"
+
+using namespace pcg;
+
+#define PCG_API_BEGIN try {
+#define PCG_API_END                                   \
+  return 0;                                           \
+  }                                                   \
+  catch (const pcg::Error& e) {                       \
+    pcg::set_last_error(e.what());                    \
+    return e.code;                                    \
+  }                                                   \
+  catch (const std::exception& e) {                   \
+    pcg::set_last_error(e.what());                    \
+    return 99;                                        \
+  }
+#define ST ((cudaStream_t)stream)
+
+static ConvGeom geom(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
+  return ConvGeom{N, H, W, Cin, Cout, k, stride, pad};
+}
+
+extern "C" {
+
+int pcg_conv_fprop(const float* in, int N, int H, int W, int Cin, const float* wf, int Cout, int k, int stride, int pad,
+                   const float* bias, int act, float slope, const float* add_src, float* out, void* stream) {
+  PCG_API_BEGIN
+  GenEpilogue<float> e;
+  e.bias = bias; e.act = act; e.slope = slope; e.add_src = add_src;
+  conv_fprop_generic<float, float>(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, e, out, ST);
+  PCG_API_END
+}
+int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float* wd, int Cout, int k, int stride, int pad,
+                   const float* add_src, const float* act_ref, int ref_act, float ref_slope, float* din, void* stream) {
+  PCG_API_BEGIN
+  GenEpilogue<float> e;
+  e.add_src = add_src; e.act_ref = act_ref; e.ref_act = ref_act; e.ref_slope = ref_slope;
+  conv_dgrad_generic<float, float>(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, e, din, ST);
+  PCG_API_END
+}
+long long pcg_conv_wgrad_scratch(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
+  return (long long)conv_wgrad_generic_scratch(geom(N, H, W, Cin, Cout, k, stride, pad));
+}
+int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                   float* scratch, float* dw, void* stream) {
+  PCG_API_BEGIN
+  conv_wgrad_generic<float, float>(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), scratch, dw, ST);
+  PCG_API_END
+}
+int pcg_pack_conv_weights(const float* w, int Cout, int Cin, int k, int perm_hw, float* wf, float* wd, void* stream) {
+  PCG_API_BEGIN
+  pack_conv_weights_generic(w, Cout, Cin, k, perm_hw, wf, wd, ST);
+  PCG_API_END
+}
+int pcg_colsum(const float* a, long long M, int C, float* scratch, float* out, void* stream) {
+  PCG_API_BEGIN
+  colsum_partial<float>(a, M, C, scratch, ST);
+  colsum_finalize(scratch, STAT_PARTS, C, C, out, ST);
+  PCG_API_END
+}
+long long pcg_stat_scratch_floats(int C) { return (long long)STAT_PARTS * 2 * C; }
+
+int pcg_bn_train_fwd(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, long long* nbt, float* mean, float* rstd, float* scale,
+                     float* shift, int act, float slope, float* z, float* scratch, void* stream) {
+  PCG_API_BEGIN
+  bn_stats_partial<float>(y, M, C, scratch, ST);
+  bn_finalize(scratch, STAT_PARTS, M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, rstd, scale,
+              shift, ST);
+  bn_apply_act<float>(y, scale, shift, M, C, act, slope, z, ST);
+  PCG_API_END
+}
+int pcg_bn_train_bwd(const float* dz, const float* y, long long M, int C, const float* gamma, const float* mean,
+                     const float* rstd, const float* scale, const float* shift, float gscale, int act, float slope,
+                     float* dy, float* dgamma, float* dbeta, float* dbias_prev, float* c12, float* scratch,
+                     float* scratch2, void* stream) {
+  PCG_API_BEGIN
+  bn_bwd_partial<float>(dz, y, mean, rstd, scale, shift, gscale, act, slope, M, C, scratch, ST);
+  bn_bwd_finalize(scratch, STAT_PARTS, M, C, dgamma, dbeta, c12, ST);
+  bn_bwd_apply<float>(dz, y, mean, rstd, scale, shift, gamma, c12, gscale, act, slope, M, C, dy, scratch2, ST);
+  if (dbias_prev) colsum_finalize(scratch2, STAT_PARTS, C, C, dbias_prev, ST);
+  PCG_API_END
+}
+int pcg_bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,
+                const float* rv, float eps, float* y, float* scale_out, void* stream) {
+  PCG_API_BEGIN
+  bn_eval(x, rows, C, gamma, beta, rm, rv, eps, y, scale_out, ST);
+  PCG_API_END
+}
+int pcg_scale_cols(const float* dy, long long rows, int C, const float* scale, float* dx, void* stream) {
+  PCG_API_BEGIN
+  scale_cols(dy, rows, C, scale, dx, ST);
+  PCG_API_END
+}
+int pcg_unary(const float* x, long long n, int op, float a, float* y, void* stream) {
+  PCG_API_BEGIN
+  unary(x, n, op, a, y, ST);
+  PCG_API_END
+}
+int pcg_unary_bwd(const float* dy, const float* y, long long n, int op, float a, float* dx, void* stream) {
+  PCG_API_BEGIN
+  unary_bwd(dy, y, n, op, a, dx, ST);
+  PCG_API_END
+}
+int pcg_binary(const float* a, const float* b, long long n, int op, float alpha, float beta, float* out, void* stream) {
+  PCG_API_BEGIN
+  binary(a, b, n, op, alpha, beta, out, ST);
+  PCG_API_END
+}
+int pcg_copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows, int ncols,
+                  float alpha, int accumulate, void* stream) {
+  PCG_API_BEGIN
+  copy_cols(src, src_ld, c0_src, dst, dst_ld, c0_dst, rows, ncols, alpha, accumulate, ST);
+  PCG_API_END
+}
+int pcg_onehot(const long long* lab, long long rows, int nc, float* dst, int dst_ld, int c0, void* stream) {
+  PCG_API_BEGIN
+  onehot(lab, rows, nc, dst, dst_ld, c0, ST);
+  PCG_API_END
+}
+int pcg_reduce_scalar(const float* x, long long n, int absval, float scale, float* out, float gscale, float* dx,
+                      void* stream) {
+  PCG_API_BEGIN
+  reduce_scalar(x, n, absval, scale, out, gscale, dx, ST);
+  PCG_API_END
+}
+int pcg_rownorm_mean(const float* x, long long rows, int cols, int p, float* out, float gscale, float* dx, void* stream) {
+  PCG_API_BEGIN
+  rownorm_mean(x, rows, cols, p, out, gscale, dx, ST);
+  PCG_API_END
+}
+int pcg_gan_loss(const float* z, int n, int kind, float t, float wgt, float* out_loss, float* out_aux, float* dz,
+                 void* stream) {
+  PCG_API_BEGIN
+  gan_loss(z, n, kind, t, wgt, out_loss, out_aux, dz, ST);
+  PCG_API_END
+}
+int pcg_combine_scalars(int n, const float* coeffs, const float* const* ptrs, float* out, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(n >= 1 && n <= 6, "1..6 terms");
+  ScalarTerms t;
+  t.n = n;
+  for (int i = 0; i < n; ++i) { t.c[i] = coeffs[i]; t.p[i] = ptrs[i]; }
+  combine_scalars(t, out, ST);
+  PCG_API_END
+}
+int pcg_spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
+                          float* sigma, void* stream) {
+  PCG_API_BEGIN
+  spectral_norm_fwd(W, N, K, u, v, eps, do_iter, Wn, sigma, ST);
+  PCG_API_END
+}
+int pcg_spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
+                          const float* sigma, float* dW, void* stream) {
+  PCG_API_BEGIN
+  spectral_norm_bwd(dWn, Wn, N, K, u, v, sigma, dW, ST);
+  PCG_API_END
+}
+int pcg_gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y, void* stream) {
+  PCG_API_BEGIN
+  gumbel_softmax_fwd(logits, g, rows, n, tau, y, ST);
+  PCG_API_END
+}
+int pcg_softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, void* stream) {
+  PCG_API_BEGIN
+  softmax_bwd(dy, y, rows, n, tau, dl, ST);
+  PCG_API_END
+}
+int pcg_ce_loss(const float* logits, const long long* target, int B, int NC, float wgt, float* loss, float* dlogits,
+                void* stream) {
+  PCG_API_BEGIN
+  ce_loss(logits, target, B, NC, wgt, loss, dlogits, ST);
+  PCG_API_END
+}
+int pcg_adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
+                  float beta2, float eps, float grad_scale, void* stream) {
+  PCG_API_BEGIN
+  adam_flat(p, g, m, v, n, step, lr, beta1, beta2, eps, grad_scale, ST);
+  PCG_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// Small fp32 primitives used by the MLP / tabular / DCGAN step plans (conditional_gan/moons,
+// simple_gan/moons, conditional_counteRGAN/{moons,house_sales_kc_usa}, dconv_gan/mnist).
+// Row-major [rows][cols] matrices.  Every kernel here is latency/HBM-bound and tiny at the reference's
+// problem sizes; the step plans capture them in a CUDA graph.
+#include "ops.cuh"
+
+namespace pcg {
+
+static int blocks_for(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+#define GRID_STRIDE(i, n) \
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+// ------------------------------------------------------------------ elementwise
+__global__ void unary_kernel(const float* __restrict__ x, long long n, int op, float a, float* __restrict__ y) {
+  GRID_STRIDE(i, n) {
+    const float v = x[i];
+    float r;
+    switch (op) {
+      case OP_RELU: r = fmaxf(v, 0.f); break;
+      case OP_LRELU: r = v > 0.f ? v : v * a; break;
+      case OP_SIGMOID: r = 1.f / (1.f + expf(-v)); break;
+      case OP_TANH: r = tanhf(v); break;
+      case OP_SCALE: r = v * a; break;
+      case OP_COPY: r = v; break;
+      default: r = v;
+    }
+    y[i] = r;
+  }
+}
+void unary(const float* x, long long n, int op, float a, float* y, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  unary_kernel<<<blocks_for(n), 256, 0, s>>>(x, n, op, a, y);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// dx = dy * f'(.) evaluated from the activation OUTPUT y
+__global__ void unary_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n, int op,
+                                 float a, float* __restrict__ dx) {
+  GRID_STRIDE(i, n) {
+    const float o = y[i], g = dy[i];
+    float r;
+    switch (op) {
+      case OP_RELU: r = o > 0.f ? g : 0.f; break;
+      case OP_LRELU: r = o > 0.f ? g : g * a; break;
+      case OP_SIGMOID: r = g * o * (1.f - o); break;
+      case OP_TANH: r = g * (1.f - o * o); break;
+      case OP_SCALE: r = g * a; break;
+      default: r = g;
+    }
+    dx[i] = r;
+  }
+}
+void unary_bwd(const float* dy, const float* y, long long n, int op, float a, float* dx, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  unary_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(dy, y, n, op, a, dx);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// out = alpha * a (op) b   with op in {add, mul}; b may broadcast over rows when b_cols > 0 (b is [cols])
+__global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int op,
+                              float alpha, float beta, float* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    const float x = a[i], y = b[i];
+    out[i] = op == OP_MUL ? alpha * x * y : alpha * x + beta * y;
+  }
+}
+void binary(const float* a, const float* b, long long n, int op, float alpha, float beta, float* out, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  binary_kernel<<<blocks_for(n), 256, 0, s>>>(a, b, n, op, alpha, beta, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// out[r][c0_out + j] = src[r][c0_src + j], j < ncols  (column block copy between matrices of different widths);
+// accumulate != 0 adds instead of overwriting (gradient of a tensor used twice).
+__global__ void copy_cols_kernel(const float* __restrict__ src, int src_ld, int c0_src, float* __restrict__ dst,
+                                 int dst_ld, int c0_dst, long long rows, int ncols, float alpha, int accumulate) {
+  const long long n = rows * ncols;
+  GRID_STRIDE(i, n) {
+    const long long r = i / ncols;
+    const int j = (int)(i - r * ncols);
+    const float v = alpha * src[r * src_ld + c0_src + j];
+    float* d = dst + r * dst_ld + c0_dst + j;
+    *d = accumulate ? *d + v : v;
+  }
+}
+void copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows, int ncols,
+               float alpha, int accumulate, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  copy_cols_kernel<<<blocks_for(rows * ncols), 256, 0, s>>>(src, src_ld, c0_src, dst, dst_ld, c0_dst, rows, ncols, alpha,
+                                                           accumulate);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+__global__ void onehot_kernel(const long long* __restrict__ lab, long long rows, int nc, float* __restrict__ dst,
+                              int dst_ld, int c0) {
+  const long long n = rows * nc;
+  GRID_STRIDE(i, n) {
+    const long long r = i / nc;
+    const int j = (int)(i - r * nc);
+    dst[r * dst_ld + c0 + j] = lab[r] == j ? 1.f : 0.f;
+  }
+}
+void onehot(const long long* lab, long long rows, int nc, float* dst, int dst_ld, int c0, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  onehot_kernel<<<blocks_for(rows * nc), 256, 0, s>>>(lab, rows, nc, dst, dst_ld, c0);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ reductions to a scalar (single block, fixed order)
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+// out = scale * sum_i f(x_i), f in {id, abs}; optional dx_i = gscale * f'(x_i)   (sign(0) = 0 as torch.abs backward)
+__global__ void reduce_scalar_kernel(const float* __restrict__ x, long long n, int absval, float scale, float* out,
+                                     float gscale, float* __restrict__ dx) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    s += absval ? fabsf(v) : v;
+    if (dx) dx[i] = absval ? gscale * ((v > 0.f) - (v < 0.f)) : gscale;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+void reduce_scalar(const float* x, long long n, int absval, float scale, float* out, float gscale, float* dx,
+                   cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  reduce_scalar_kernel<<<1, 1024, 0, s>>>(x, n, absval, scale, out, gscale, dx);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// out = mean_r ||x_r||_p (p = 1 or 2); dx_r = gscale/rows * d||x_r||_p / dx   (zero sub-gradient at x_r = 0 for p=2)
+__global__ void rownorm_mean_kernel(const float* __restrict__ x, long long rows, int cols, int p, float* out,
+                                    float gscale, float* __restrict__ dx) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < cols; ++c) {
+      const float v = x[r * cols + c];
+      a += p == 1 ? fabsf(v) : v * v;
+    }
+    const float nrm = p == 1 ? a : sqrtf(a);
+    s += nrm;
+    if (dx) {
+      for (int c = 0; c < cols; ++c) {
+        const float v = x[r * cols + c];
+        float g;
+        if (p == 1) g = (float)((v > 0.f) - (v < 0.f));
+        else g = nrm > 0.f ? v / nrm : 0.f;
+        dx[r * cols + c] = gscale * g / (float)rows;
+      }
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s / (float)rows;
+}
+void rownorm_mean(const float* x, long long rows, int cols, int p, float* out, float gscale, float* dx, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  rownorm_mean_kernel<<<1, 1024, 0, s>>>(x, rows, cols, p, out, gscale, dx);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ GAN losses on discriminator outputs
+// kind 0 (log / saturating GAN, make_moons_gan.py:70,81): z are pre-sigmoid logits, p = sigmoid(z)
+//        term t=1: loss = -mean log p       dz = wgt * -(1 - p) / n
+//        term t=0: loss = -mean log(1 - p)  dz = wgt *  p / n
+// kind 1 (BCELoss on probabilities, mnist_dcgan.py:125): same formulas with torch's log clamp at -100
+// kind 2 (Wasserstein, moons/trainer.py:77,83): loss = sign * mean z ; dz = wgt * sign / n   (t=1 -> sign=-1)
+__global__ void gan_loss_kernel(const float* __restrict__ z, int n, int kind, float t, float wgt, float* out_loss,
+                                float* out_aux, float* __restrict__ dz) {
+  __shared__ float red[32];
+  float sl = 0.f, sp = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = z[i];
+    if (kind == 2) {
+      const float sign = t > 0.5f ? -1.f : 1.f;
+      sl += sign * v;
+      sp += 1.f / (1.f + expf(-v));
+      dz[i] = wgt * sign / (float)n;
+    } else {
+      const float p = 1.f / (1.f + expf(-v));
+      float lp = logf(p), l1p = logf(1.f - p);
+      if (kind == 1) { lp = fmaxf(lp, -100.f); l1p = fmaxf(l1p, -100.f); }
+      sl += t > 0.5f ? -lp : -l1p;
+      sp += p;
+      dz[i] = wgt * (t > 0.5f ? -(1.f - p) : p) / (float)n;
+    }
+  }
+  sl = block_sum(sl, red);
+  sp = block_sum(sp, red);
+  if (threadIdx.x == 0) {
+    out_loss[0] = sl / (float)n;
+    if (out_aux) out_aux[0] = sp / (float)n;
+  }
+}
+void gan_loss(const float* z, int n, int kind, float t, float wgt, float* out_loss, float* out_aux, float* dz,
+              cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  gan_loss_kernel<<<1, 256, 0, s>>>(z, n, kind, t, wgt, out_loss, out_aux, dz);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// out[0] = sum_i c_i * in_i[0]  (up to 6 scalar terms)
+__global__ void combine_kernel(ScalarTerms t, float* out) {
+  float s = 0.f;
+  for (int i = 0; i < t.n; ++i) s += t.c[i] * t.p[i][0];
+  out[0] = s;
+}
+void combine_scalars(const ScalarTerms& t, float* out, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  combine_kernel<<<1, 1, 0, s>>>(t, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ spectral norm (torch/nn/utils/spectral_norm.py:62-113)
+// One power iteration in place on (u, v) (train mode), sigma = u^T W v, Wn = W / sigma.  Single block: the
+// matrices are at most 128 x 64.
+__global__ void spectral_norm_fwd_kernel(const float* __restrict__ W, int N, int K, float* u, float* v, float eps,
+                                         int do_iter, float* __restrict__ Wn, float* sigma_out) {
+  extern __shared__ float sm[];     // u[N], v[K], red[32]
+  float* su = sm;
+  float* sv = sm + N;
+  float* red = sv + K;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) su[i] = u[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) sv[i] = v[i];
+  __syncthreads();
+  if (do_iter) {
+    // v = normalize(W^T u)
+    float part = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float a = 0.f;
+      for (int n = 0; n < N; ++n) a = fmaf(W[n * K + k], su[n], a);
+      sv[k] = a;
+      part += a * a;
+    }
+    float nrm = sqrtf(block_sum(part, red));
+    __shared__ float bc;
+    if (threadIdx.x == 0) bc = fmaxf(nrm, eps);
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) sv[k] /= bc;
+    __syncthreads();
+    // u = normalize(W v)
+    part = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float a = 0.f;
+      for (int k = 0; k < K; ++k) a = fmaf(W[n * K + k], sv[k], a);
+      su[n] = a;
+      part += a * a;
+    }
+    nrm = sqrtf(block_sum(part, red));
+    if (threadIdx.x == 0) bc = fmaxf(nrm, eps);
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) su[n] /= bc;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) u[i] = su[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) v[i] = sv[i];
+  }
+  // sigma = u^T W v
+  float part = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < K; ++k) a = fmaf(W[n * K + k], sv[k], a);
+    part = fmaf(su[n], a, part);
+  }
+  const float sg = block_sum(part, red);
+  __shared__ float s_sigma;
+  if (threadIdx.x == 0) { s_sigma = sg; sigma_out[0] = sg; }
+  __syncthreads();
+  const float inv = 1.f / s_sigma;
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) Wn[i] = W[i] * inv;
+}
+void spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
+                       float* sigma, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  const size_t sm = (size_t)(N + K + 40) * sizeof(float);
+  spectral_norm_fwd_kernel<<<1, 256, sm, s>>>(W, N, K, u, v, eps, do_iter, Wn, sigma);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+// dW = (dWn - (sum dWn .* Wn) * u v^T) / sigma      (u, v treated as constants, as torch does)
+__global__ void spectral_norm_bwd_kernel(const float* __restrict__ dWn, const float* __restrict__ Wn, int N, int K,
+                                         const float* __restrict__ u, const float* __restrict__ v,
+                                         const float* __restrict__ sigma, float* __restrict__ dW) {
+  __shared__ float red[32];
+  __shared__ float s_dot;
+  float part = 0.f;
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) part = fmaf(dWn[i], Wn[i], part);
+  const float dot = block_sum(part, red);
+  if (threadIdx.x == 0) s_dot = dot;
+  __syncthreads();
+  const float inv = 1.f / sigma[0];
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    dW[i] = (dWn[i] - s_dot * u[n] * v[k]) * inv;
+  }
+}
+void spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
+                       const float* sigma, float* dW, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  spectral_norm_bwd_kernel<<<1, 256, 0, s>>>(dWn, Wn, N, K, u, v, sigma, dW);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ Gumbel-softmax (soft), noise injected
+// y = softmax((logits + g) / tau) ; backward dlogits = y .* (dy - sum_j dy_j y_j) / tau
+__global__ void gumbel_softmax_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ g, long long rows,
+                                          int n, float tau, float* __restrict__ y) {
+  GRID_STRIDE(r, rows) {
+    const float* l = logits + r * n;
+    const float* gg = g + r * n;
+    float mx = -INFINITY;
+    for (int j = 0; j < n; ++j) mx = fmaxf(mx, (l[j] + gg[j]) / tau);
+    float se = 0.f;
+    for (int j = 0; j < n; ++j) se += expf((l[j] + gg[j]) / tau - mx);
+    for (int j = 0; j < n; ++j) y[r * n + j] = expf((l[j] + gg[j]) / tau - mx) / se;
+  }
+}
+void gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  gumbel_softmax_fwd_kernel<<<blocks_for(rows), 256, 0, s>>>(logits, g, rows, n, tau, y);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+__global__ void softmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long rows, int n,
+                                   float tau, float* __restrict__ dl) {
+  GRID_STRIDE(r, rows) {
+    float dot = 0.f;
+    for (int j = 0; j < n; ++j) dot = fmaf(dy[r * n + j], y[r * n + j], dot);
+    for (int j = 0; j < n; ++j) dl[r * n + j] = y[r * n + j] * (dy[r * n + j] - dot) / tau;
+  }
+}
+void softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  softmax_bwd_kernel<<<blocks_for(rows), 256, 0, s>>>(dy, y, rows, n, tau, dl);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ BatchNorm in eval mode (running stats) as affine
+__global__ void bn_eval_kernel(const float* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ rm,
+                               const float* __restrict__ rv, float eps, float* __restrict__ y, float* __restrict__ scale_out) {
+  const long long n = rows * C;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+    y[i] = (x[i] - rm[c]) * sc + beta[c];
+    if (scale_out && i < C) scale_out[c] = sc;
+  }
+}
+void bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,
+             const float* rv, float eps, float* y, float* scale_out, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  bn_eval_kernel<<<blocks_for(rows * C), 256, 0, s>>>(x, rows, C, gamma, beta, rm, rv, eps, y, scale_out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+// dx = dy * scale[c]
+__global__ void scale_cols_kernel(const float* __restrict__ dy, long long rows, int C, const float* __restrict__ scale,
+                                  float* __restrict__ dx) {
+  const long long n = rows * C;
+  GRID_STRIDE(i, n) dx[i] = dy[i] * scale[i % C];
+}
+void scale_cols(const float* dy, long long rows, int C, const float* scale, float* dx, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  scale_cols_kernel<<<blocks_for(rows * C), 256, 0, s>>>(dy, rows, C, scale, dx);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+}  // namespace pcg

@@ -1,0 +1,37 @@
+// Small fp32 primitives for the MLP / tabular / DCGAN step plans — host interface (see ops.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pcg {
+
+enum UnaryOp { OP_RELU = 1, OP_LRELU = 2, OP_SIGMOID = 3, OP_TANH = 4, OP_SCALE = 5, OP_COPY = 6 };
+enum BinaryOp { OP_ADD = 0, OP_MUL = 1 };
+
+void unary(const float* x, long long n, int op, float a, float* y, cudaStream_t s);
+void unary_bwd(const float* dy, const float* y, long long n, int op, float a, float* dx, cudaStream_t s);
+void binary(const float* a, const float* b, long long n, int op, float alpha, float beta, float* out, cudaStream_t s);
+void copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows, int ncols,
+               float alpha, int accumulate, cudaStream_t s);
+void onehot(const long long* lab, long long rows, int nc, float* dst, int dst_ld, int c0, cudaStream_t s);
+void reduce_scalar(const float* x, long long n, int absval, float scale, float* out, float gscale, float* dx,
+                   cudaStream_t s);
+void rownorm_mean(const float* x, long long rows, int cols, int p, float* out, float gscale, float* dx, cudaStream_t s);
+void gan_loss(const float* z, int n, int kind, float t, float wgt, float* out_loss, float* out_aux, float* dz,
+              cudaStream_t s);
+struct ScalarTerms {
+  int n;
+  float c[6];
+  const float* p[6];
+};
+void combine_scalars(const ScalarTerms& t, float* out, cudaStream_t s);
+void spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
+                       float* sigma, cudaStream_t s);
+void spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
+                       const float* sigma, float* dW, cudaStream_t s);
+void gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y, cudaStream_t s);
+void softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, cudaStream_t s);
+void bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,
+             const float* rv, float eps, float* y, float* scale_out, cudaStream_t s);
+void scale_cols(const float* dy, long long rows, int C, const float* scale, float* dx, cudaStream_t s);
+
+}  // namespace pcg

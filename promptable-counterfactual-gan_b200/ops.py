@@ -1,0 +1,273 @@
+"""Thin ctypes wrappers of libpcg's primitive operators (include/pcg.h, "Primitive operators").
+
+Every function enqueues one or a few kernels on the current CUDA stream and returns nothing; outputs are
+caller-allocated torch tensors (fp32, contiguous).  No torch arithmetic happens here — the step plans built on
+these wrappers are captured in a CUDA graph, so the Python overhead is paid once.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+RELU, LRELU, SIGMOID, TANH, SCALE, COPY = 1, 2, 3, 4, 5, 6
+ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
+ADD, MUL = 0, 1
+GAN_LOG, GAN_BCE, GAN_WASSERSTEIN = 0, 1, 2
+
+_f = ctypes.c_float
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+P = _lib.ptr
+
+
+def _L():
+    return _lib.load()
+
+
+def _s():
+    return _lib.stream_ptr()
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.is_contiguous(), "libpcg operators need contiguous CUDA tensors"
+
+
+def stat_scratch(C, device):
+    L = _L()
+    L.pcg_stat_scratch_floats.restype = ctypes.c_longlong
+    return torch.zeros(int(L.pcg_stat_scratch_floats(C)), device=device)
+
+
+# ---------------------------------------------------------------- convolution / linear
+def pack_weights(w, k, wf=None, wd=None, perm_hw=0):
+    """torch OIHW (or [out,in] with k=1) -> wf [Cout][k*k][Cin], wd [Cin][k*k][Cout]."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    _chk(w, wf, wd)
+    _lib.check(_L().pcg_pack_conv_weights(P(w), Cout, Cin, k, perm_hw, P(wf), P(wd), _s()))
+
+
+def conv_fprop(x, N, H, W, Cin, wf, Cout, k, stride, pad, out, bias=None, act=ACT_NONE, slope=0.2, add_src=None):
+    _chk(x, wf, out, bias, add_src)
+    _lib.check(_L().pcg_conv_fprop(P(x), N, H, W, Cin, P(wf), Cout, k, stride, pad, P(bias), act, _f(slope), P(add_src),
+                                   P(out), _s()))
+
+
+def conv_dgrad(dout, N, H, W, Cin, wd, Cout, k, stride, pad, din, add_src=None, act_ref=None, ref_act=ACT_NONE,
+               ref_slope=0.2):
+    """din[N,H,W,Cin] = gradient of conv(geometry N,H,W,Cin -> Cout) wrt its input, given dout."""
+    _chk(dout, wd, din, add_src, act_ref)
+    _lib.check(_L().pcg_conv_dgrad(P(dout), N, H, W, Cin, P(wd), Cout, k, stride, pad, P(add_src), P(act_ref), ref_act,
+                                   _f(ref_slope), P(din), _s()))
+
+
+def conv_wgrad_scratch(N, H, W, Cin, Cout, k, stride, pad, device):
+    L = _L()
+    L.pcg_conv_wgrad_scratch.restype = ctypes.c_longlong
+    return torch.zeros(int(L.pcg_conv_wgrad_scratch(N, H, W, Cin, Cout, k, stride, pad)), device=device)
+
+
+def conv_wgrad(x, dout, N, H, W, Cin, Cout, k, stride, pad, scratch, dw):
+    _chk(x, dout, scratch, dw)
+    _lib.check(_L().pcg_conv_wgrad(P(x), P(dout), N, H, W, Cin, Cout, k, stride, pad, P(scratch), P(dw), _s()))
+
+
+def linear_fwd(x, w, out, bias=None, act=ACT_NONE, slope=0.2):
+    """out[B,N] = act(x[B,K] @ w[N,K]^T + bias)."""
+    B, K = x.shape
+    conv_fprop(x, B, 1, 1, K, w, w.shape[0], 1, 1, 0, out, bias, act, slope)
+
+
+def linear_dgrad(dy, wT, dx, K, act_ref=None, ref_act=ACT_NONE, ref_slope=0.2, add_src=None):
+    """dx[B,K] = dy[B,N] @ w[N,K], with wT = w^T [K,N] (pack_weights(..., wd=wT)); optional activation derivative."""
+    B, N = dy.shape
+    conv_dgrad(dy, B, 1, 1, K, wT, N, 1, 1, 0, dx, add_src, act_ref, ref_act, ref_slope)
+
+
+def linear_wgrad(x, dy, scratch, dw, db=None, stat=None):
+    B, K = x.shape
+    N = dy.shape[1]
+    conv_wgrad(x, dy, B, 1, 1, K, N, 1, 1, 0, scratch, dw)
+    if db is not None:
+        colsum(dy, stat, db)
+
+
+def colsum(a, scratch, out):
+    M, C = a.shape[0] if a.dim() == 2 else a.numel() // a.shape[-1], a.shape[-1]
+    _chk(a, scratch, out)
+    _lib.check(_L().pcg_colsum(P(a), _ll(M), C, P(scratch), P(out), _s()))
+
+
+# ---------------------------------------------------------------- batch norm
+class BNState:
+    """Saved statistics of one train-mode BatchNorm forward (C channels)."""
+
+    def __init__(self, C, device):
+        z = lambda: torch.zeros(C, device=device)  # noqa: E731
+        self.mean, self.rstd, self.scale, self.shift = z(), z(), z(), z()
+        self.c12 = torch.zeros(2 * C, device=device)
+        self.scratch = stat_scratch(C, device)
+        self.scratch2 = stat_scratch(C, device)
+
+
+def bn_train_fwd(y, M, C, gamma, beta, running_mean, running_var, nbt, st, z, act=ACT_NONE, slope=0.2, eps=1e-5,
+                 momentum=0.1):
+    _chk(y, gamma, beta, z)
+    _lib.check(_L().pcg_bn_train_fwd(P(y), _ll(M), C, P(gamma), P(beta), _f(eps), _f(momentum), P(running_mean),
+                                     P(running_var), P(nbt), P(st.mean), P(st.rstd), P(st.scale), P(st.shift), act,
+                                     _f(slope), P(z), P(st.scratch), _s()))
+
+
+def bn_train_bwd(dz, y, M, C, gamma, st, dy, dgamma, dbeta, dbias_prev=None, gscale=1.0, act=ACT_NONE, slope=0.2):
+    _chk(dz, y, dy, dgamma, dbeta, dbias_prev)
+    _lib.check(_L().pcg_bn_train_bwd(P(dz), P(y), _ll(M), C, P(gamma), P(st.mean), P(st.rstd), P(st.scale), P(st.shift),
+                                     _f(gscale), act, _f(slope), P(dy), P(dgamma), P(dbeta), P(dbias_prev), P(st.c12),
+                                     P(st.scratch), P(st.scratch2), _s()))
+
+
+def bn_eval(x, gamma, beta, rm, rv, y, scale_out=None, eps=1e-5):
+    rows, C = x.numel() // x.shape[-1], x.shape[-1]
+    _lib.check(_L().pcg_bn_eval(P(x), _ll(rows), C, P(gamma), P(beta), P(rm), P(rv), _f(eps), P(y), P(scale_out), _s()))
+
+
+def scale_cols(dy, scale, dx):
+    rows, C = dy.numel() // dy.shape[-1], dy.shape[-1]
+    _lib.check(_L().pcg_scale_cols(P(dy), _ll(rows), C, P(scale), P(dx), _s()))
+
+
+# ---------------------------------------------------------------- elementwise / reductions / losses
+def unary(x, op, y, a=0.0):
+    _chk(x, y)
+    _lib.check(_L().pcg_unary(P(x), _ll(x.numel()), op, _f(a), P(y), _s()))
+
+
+def unary_bwd(dy, y, op, dx, a=0.0):
+    _chk(dy, y, dx)
+    _lib.check(_L().pcg_unary_bwd(P(dy), P(y), _ll(y.numel()), op, _f(a), P(dx), _s()))
+
+
+def binary(a, b, op, out, alpha=1.0, beta=1.0):
+    _chk(a, b, out)
+    _lib.check(_L().pcg_binary(P(a), P(b), _ll(a.numel()), op, _f(alpha), _f(beta), P(out), _s()))
+
+
+def copy_cols(src, c0_src, dst, c0_dst, ncols, alpha=1.0, accumulate=False):
+    _chk(src, dst)
+    rows = src.shape[0]
+    _lib.check(_L().pcg_copy_cols(P(src), src.shape[1], c0_src, P(dst), dst.shape[1], c0_dst, _ll(rows), ncols, _f(alpha),
+                                  1 if accumulate else 0, _s()))
+
+
+def onehot(labels, nc, dst, c0=0):
+    _chk(labels, dst)
+    _lib.check(_L().pcg_onehot(P(labels), _ll(labels.numel()), nc, P(dst), dst.shape[1], c0, _s()))
+
+
+def reduce_scalar(x, out, scale=1.0, absval=False, dx=None, gscale=0.0):
+    _chk(x, out, dx)
+    _lib.check(_L().pcg_reduce_scalar(P(x), _ll(x.numel()), 1 if absval else 0, _f(scale), P(out), _f(gscale), P(dx), _s()))
+
+
+def rownorm_mean(x, p, out, dx=None, gscale=0.0):
+    _chk(x, out, dx)
+    _lib.check(_L().pcg_rownorm_mean(P(x), _ll(x.shape[0]), x.shape[1], p, P(out), _f(gscale), P(dx), _s()))
+
+
+def gan_loss(z, kind, t, out_loss, dz, wgt=1.0, out_aux=None):
+    _chk(z, out_loss, dz, out_aux)
+    _lib.check(_L().pcg_gan_loss(P(z), z.numel(), kind, _f(t), _f(wgt), P(out_loss), P(out_aux), P(dz), _s()))
+
+
+def combine(terms, out):
+    """out[0] = sum coeff * scalar_tensor[0] over up to 6 (coeff, tensor) pairs."""
+    n = len(terms)
+    coeffs = (ctypes.c_float * n)(*[float(c) for c, _ in terms])
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for _, t in terms])
+    _lib.check(_L().pcg_combine_scalars(n, coeffs, ptrs, P(out), _s()))
+
+
+def spectral_norm_fwd(W, u, v, Wn, sigma, do_iter=True, eps=1e-12):
+    N, K = W.shape
+    _chk(W, u, v, Wn, sigma)
+    _lib.check(_L().pcg_spectral_norm_fwd(P(W), N, K, P(u), P(v), _f(eps), 1 if do_iter else 0, P(Wn), P(sigma), _s()))
+
+
+def spectral_norm_bwd(dWn, Wn, u, v, sigma, dW):
+    N, K = Wn.shape
+    _lib.check(_L().pcg_spectral_norm_bwd(P(dWn), P(Wn), N, K, P(u), P(v), P(sigma), P(dW), _s()))
+
+
+def gumbel_softmax_fwd(logits, g, tau, y):
+    rows, n = logits.shape
+    _lib.check(_L().pcg_gumbel_softmax_fwd(P(logits), P(g), _ll(rows), n, _f(tau), P(y), _s()))
+
+
+def softmax_bwd(dy, y, tau, dl):
+    rows, n = y.shape
+    _lib.check(_L().pcg_softmax_bwd(P(dy), P(y), _ll(rows), n, _f(tau), P(dl), _s()))
+
+
+def ce_loss(logits, target, loss, dlogits, wgt=1.0):
+    B, NC = logits.shape
+    _lib.check(_L().pcg_ce_loss(P(logits), P(target), B, NC, _f(wgt), P(loss), P(dlogits), _s()))
+
+
+def adam(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    _chk(p, g, m, v, step)
+    _lib.check(_L().pcg_adam_flat(P(p), P(g), P(m), P(v), _ll(p.numel()), P(step), _f(lr), _f(beta1), _f(beta2), _f(eps),
+                                  _f(grad_scale), _s()))
+
+
+class FlatParams:
+    """Parameters of a small network as views into one flat fp32 buffer (+ grads, Adam state), so that the
+    optimizer is one kernel and ``nn.Parameter`` tensors can alias the slices (state_dict keeps working)."""
+
+    def __init__(self, named_shapes, device):
+        self.names = [n for n, _ in named_shapes]
+        self.shapes = {n: tuple(s) for n, s in named_shapes}
+        offs, off = {}, 0
+        for n, s in named_shapes:
+            offs[n] = off
+            numel = 1
+            for d in s:
+                numel *= d
+            off += (numel + 3) // 4 * 4
+        self.offsets, self.size = offs, off
+        self.data = torch.zeros(off, device=device)
+        self.grad = torch.zeros(off, device=device)
+        self.m = torch.zeros(off, device=device)
+        self.v = torch.zeros(off, device=device)
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def _view(self, buf, n):
+        s = self.shapes[n]
+        numel = 1
+        for d in s:
+            numel *= d
+        return buf[self.offsets[n]:self.offsets[n] + numel].view(s)
+
+    def p(self, n):
+        return self._view(self.data, n)
+
+    def g(self, n):
+        return self._view(self.grad, n)
+
+    def load(self, tensors):
+        for n, t in tensors.items():
+            self.p(n).copy_(t.to(self.data.device, torch.float32))
+        return self
+
+    def adopt(self, module):
+        """Re-points the module's parameters at the flat buffer (values copied in first)."""
+        for n, prm in module.named_parameters():
+            v = self.p(n)
+            v.copy_(prm.detach().to(v.device, torch.float32))
+            prm.data = v
+            if prm.requires_grad:
+                prm.grad = self.g(n)
+        return self
+
+    def adam_step(self, lr, grad_scale=1.0):
+        adam(self.data, self.grad, self.m, self.v, self.step, lr, grad_scale=grad_scale)

@@ -40,3 +40,26 @@ def experiment(rel_dir):
         os.chdir(cwd)
         sys.path.remove(d)
         _purge()
+
+
+def lift(rel_path, names=(), loop_var=None, extra=None):
+    """AST-lifts definitions out of a reference *script* (scripts cannot be imported: they train at import
+    time).  Returns (namespace, loop_code): the namespace holds the class / function definitions named in
+    ``names`` executed unmodified; ``loop_code`` is the compiled top-level ``for <loop_var> in ...`` statement
+    (the script's training loop), or None.  Nothing is copied into the repository."""
+    import ast
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    src = open(os.path.join(REF_ROOT, rel_path)).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np, "device": torch.device("cpu")}
+    ns.update(extra or {})
+    loop = None
+    for node in tree.body:
+        if isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in names:
+            exec(compile(ast.Module([node], []), rel_path, "exec"), ns)
+        if loop_var and isinstance(node, ast.For) and getattr(node.target, "id", None) == loop_var and loop is None:
+            loop = compile(ast.Module([node], []), rel_path, "exec")
+    return ns, loop
