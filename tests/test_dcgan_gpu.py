@@ -1,0 +1,81 @@
+"""GPU parity of the native DCGAN plan against the oracle (fp32)."""
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from oracle import dcgan as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_dcgan_step_matches_oracle(graph):
+    import pcg_b200  # noqa: F401
+    from pcg_b200.dcgan import DcganPlan
+    B = 8
+    PG, PD = O.synth_params(O.g_shapes(), 5), O.synth_params(O.d_shapes(), 6)
+    S = O.make_state(PG, O.buffers(O.g_shapes()), PD, O.buffers(O.d_shapes()))
+    plan = DcganPlan(B, "cuda", use_graph=graph)
+    plan.G.load(PG)
+    plan.D.load(PD)
+    plan.refresh()
+    for step in range(2):
+        real, noise = O.synth_batch(B, 70 + step)
+        pG0 = {k: v.detach().clone() for k, v in S["G"].items()}
+        pD0 = {k: v.detach().clone() for k, v in S["D"].items()}
+        sc, gr = O.dcgan_step(S, real, noise)
+        got = plan.step(real.cuda(), noise.cuda()).tolist()
+        tol = 5e-5 if step == 0 else 5e-3
+        for i, k in ((0, "errD"), (1, "errG"), (4, "D_x"), (5, "D_G_z1"), (6, "D_G_z2")):
+            assert abs(got[i] - sc[k]) <= tol * abs(sc[k]) + 1e-6, (step, k, got[i], sc[k])
+        if step == 0:
+            assert rel(plan.ga[4].view(B, 1, 64, 64), gr["fake"]) < 2e-5
+            for k in gr["G"]:
+                assert rel(plan.G.g(k), gr["G"][k]) < 5e-4, k
+            for net, P0, key, flat in ((S["D"], pD0, "D", plan.D), (S["G"], pG0, "G", plan.G)):
+                for k in P0:
+                    d_nat = flat.p(k).cpu() - P0[k]
+                    d_or = net[k].detach() - P0[k]
+                    assert ((d_nat - d_or).abs().mean() / 2e-4).item() < 0.03, (key, k)
+    # BN buffers: G updated once per step, D three times per step
+    assert int(plan.g_bn[0]["nbt"]) == 2 and int(plan.d_bn[1]["nbt"]) == 6
+    assert rel(plan.g_bn[2]["rm"], S["GB"]["main.7.running_mean"]) < 2e-3
+    assert rel(plan.d_bn[3]["rv"], S["DB"]["main.9.running_var"]) < 2e-3
+
+
+def test_mirror_modules_forward_and_train_loop():
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import dcgan as DC
+    torch.manual_seed(1)
+    netG, netD = DC.Generator().cuda(), DC.Discriminator().cuda()
+    netG.apply(DC.weights_init)
+    netD.apply(DC.weights_init)
+    assert [k for k in netG.state_dict() if k.endswith("weight") and netG.state_dict()[k].dim() == 4] == \
+        [k for k in O.g_shapes() if len(O.g_shapes()[k]) == 4]
+    PG = OrderedDict((k, v.detach().cpu()) for k, v in netG.named_parameters())
+    BG = OrderedDict((k, v.detach().cpu().clone()) for k, v in netG.named_buffers())
+    PD = OrderedDict((k, v.detach().cpu()) for k, v in netD.named_parameters())
+    BD = OrderedDict((k, v.detach().cpu().clone()) for k, v in netD.named_buffers())
+    real, noise = O.synth_batch(4, 3)
+    with torch.no_grad():
+        fake = netG(noise.cuda())
+        assert fake.shape == (4, 1, 64, 64) and rel(fake, O.g_forward(PG, BG, noise)) < 3e-5
+        assert rel(netD(real.cuda()), O.d_forward(PD, BD, real)) < 3e-5
+        netG.eval()
+        assert rel(netG(noise.cuda()), O.g_forward(PG, BG, noise, training=False)) < 3e-5
+        netG.train()
+    cfg = dict(DC.config, epochs=1)
+    loader = [(O.synth_batch(4, 100 + i)[0],) for i in range(3)]
+    gl, dl = DC.train_dcgan(netG, netD, loader, cfg)
+    assert len(gl) == 1 and gl[0] == gl[0] and dl[0] == dl[0]
+    assert int(netG.main[1].num_batches_tracked) >= 3
