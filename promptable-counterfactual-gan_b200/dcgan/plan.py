@@ -272,6 +272,10 @@ class DcganPlan:
 
     # ------------------------------------------------------------------ one iteration
     def _body(self):
+        self._d_phase()
+        self._g_phase()
+
+    def _d_phase(self):
         B, D, G = self.B, self.D, self.G
         b1, b2 = self.betas
         g1 = lambda n: D.g(n)  # noqa: E731
@@ -289,6 +293,11 @@ class DcganPlan:
         K.combine([(1.0, self.scal[2:3]), (1.0, self.scal[3:4])], self.scal[0:1])
         K.adam(D.data, D.grad, D.m, D.v, D.step, self.lr, b1, b2)     # optimizerD.step() :164
         self._pack_d()
+
+    def _g_phase(self):
+        B, D, G = self.B, self.D, self.G
+        b1, b2 = self.betas
+        g2 = lambda n: D._view(self.D_grad2, n)  # noqa: E731
         # (2) G through the updated D (:169-175)
         self._d_fwd(self.ga[4], 1)
         K.gan_loss(self.dy[1][4].view(-1), K.GAN_BCE, 1.0, self.scal[1:2], self.dz, out_aux=self.scal[6:7])
