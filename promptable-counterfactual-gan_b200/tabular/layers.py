@@ -1,0 +1,191 @@
+"""Building blocks of the tabular step plans: dense layers (optionally spectrally normalised), train-mode
+BatchNorm1d, the spectral-norm MLP critic shared by both tabular CounteRGANs, graph capture.  Every method only
+enqueues libpcg kernels (pcg_b200.ops); gradients are written into FlatParams arenas."""
+import torch
+
+from .. import ops as K
+
+
+class Ctx:
+    """Shared scratch of one plan."""
+
+    def __init__(self, B, dev, max_dim=256):
+        self.B, self.dev = B, dev
+        self.stat = K.stat_scratch(max(max_dim, 4), dev)
+        self.wsc = torch.zeros(int(K.conv_wgrad_scratch(B, 1, 1, max_dim, max_dim, 1, 1, 0, dev).numel()) + 1024, device=dev)
+
+    def z(self, *s):
+        return torch.zeros(*s, device=self.dev)
+
+
+class Dense:
+    def __init__(self, ctx, flat, name, k_in, n_out):
+        self.ctx, self.flat, self.name, self.k, self.n = ctx, flat, name, k_in, n_out
+        self.wT = ctx.z(k_in, n_out)
+
+    def W(self):
+        return self.flat.p(self.name + ".weight")
+
+    def b(self):
+        return self.flat.p(self.name + ".bias")
+
+    def refresh(self):
+        K.pack_weights(self.W(), 1, wd=self.wT)
+
+    def fwd(self, x, out, act=K.ACT_NONE, slope=0.2):
+        K.linear_fwd(x, self.W(), out, self.b(), act, slope)
+
+    def dgrad(self, dy, dx, **kw):
+        K.linear_dgrad(dy, self.wT, dx, self.k, **kw)
+
+    def wgrad(self, x, dy):
+        K.linear_wgrad(x, dy, self.ctx.wsc, self.flat.g(self.name + ".weight"), self.flat.g(self.name + ".bias"),
+                       self.ctx.stat)
+
+
+class BN1d:
+    """Train-mode BatchNorm1d over the batch rows; running buffers are caller tensors (module buffers)."""
+
+    def __init__(self, ctx, flat, name, C):
+        self.ctx, self.flat, self.name, self.C = ctx, flat, name, C
+        self.rm, self.rv = ctx.z(C), torch.ones(C, device=ctx.dev)
+        self.nbt = torch.zeros((), dtype=torch.int64, device=ctx.dev)
+        self.st = K.BNState(C, ctx.dev)
+
+    def fwd(self, y, z, act=K.ACT_NONE, training=True):
+        g, b = self.flat.p(self.name + ".weight"), self.flat.p(self.name + ".bias")
+        if training:
+            K.bn_train_fwd(y, y.shape[0], self.C, g, b, self.rm, self.rv, self.nbt, self.st, z, act=act)
+        else:
+            K.bn_eval(y, g, b, self.rm, self.rv, z)
+            if act == K.ACT_RELU:
+                K.unary(z, K.RELU, z)
+
+    def bwd(self, dz, y, dy, act=K.ACT_NONE):
+        K.bn_train_bwd(dz, y, y.shape[0], self.C, self.flat.p(self.name + ".weight"), self.st, dy,
+                       self.flat.g(self.name + ".weight"), self.flat.g(self.name + ".bias"), act=act)
+
+
+class SNDense:
+    """spectral_norm(nn.Linear) (torch/nn/utils/spectral_norm.py): one power iteration per forward call in train mode,
+    in place on the module's u / v; each of the plan's forward passes keeps its own snapshot (u, v, sigma, W/sigma)
+    because torch's graph holds clones taken at call time."""
+
+    def __init__(self, ctx, flat, name, k_in, n_out, passes=2):
+        self.ctx, self.flat, self.name, self.k, self.n = ctx, flat, name, k_in, n_out
+        z = ctx.z
+        self.u, self.v = z(n_out), z(k_in)
+        self.Wn = [z(n_out, k_in) for _ in range(passes)]
+        self.WnT = [z(k_in, n_out) for _ in range(passes)]
+        self.sigma = [z(1) for _ in range(passes)]
+        self.us = [z(n_out) for _ in range(passes)]
+        self.vs = [z(k_in) for _ in range(passes)]
+        self.dWn = z(n_out, k_in)
+
+    def W(self):
+        return self.flat.p(self.name + ".weight_orig")
+
+    def b(self):
+        return self.flat.p(self.name + ".bias")
+
+    def normalise(self, p, iterate=True):
+        K.spectral_norm_fwd(self.W(), self.u, self.v, self.Wn[p], self.sigma[p], do_iter=iterate)
+        K.unary(self.u, K.COPY, self.us[p])
+        K.unary(self.v, K.COPY, self.vs[p])
+        K.pack_weights(self.Wn[p], 1, wd=self.WnT[p])
+
+    def fwd(self, x, out, p, act=K.ACT_NONE, slope=0.2):
+        K.linear_fwd(x, self.Wn[p], out, self.b(), act, slope)
+
+    def dgrad(self, dy, dx, p, **kw):
+        K.linear_dgrad(dy, self.WnT[p], dx, self.k, **kw)
+
+    def wgrad(self, x, dy, p, garena):
+        """garena(name) -> gradient slot.  dW_orig = (dWn - <dWn, Wn> u v^T) / sigma."""
+        K.linear_wgrad(x, dy, self.ctx.wsc, self.dWn, garena(self.name + ".bias"), self.ctx.stat)
+        K.spectral_norm_bwd(self.dWn, self.Wn[p], self.us[p], self.vs[p], self.sigma[p], garena(self.name + ".weight_orig"))
+
+
+class Critic:
+    """cat[x, onehot] -> 4 spectral-norm Linear layers with LeakyReLU(0.2) between
+    (moons/models/discriminator.py:6-22, house_sales_kc_usa/models/discriminator.py:5-20)."""
+
+    def __init__(self, ctx, dims, device):
+        self.ctx, self.dims = ctx, dims
+        B = ctx.B
+        names = []
+        for i, (a, b) in enumerate(dims):
+            names += [(f"net.{2 * i}.bias", (b,)), (f"net.{2 * i}.weight_orig", (b, a))]
+        self.flat = K.FlatParams(names, device)
+        self.grad2 = torch.zeros_like(self.flat.grad)
+        self.layers = [SNDense(ctx, self.flat, f"net.{2 * i}", a, b) for i, (a, b) in enumerate(dims)]
+        self.din = [ctx.z(B, dims[0][0]) for _ in range(2)]
+        self.h = [[ctx.z(B, b) for (_, b) in dims] for _ in range(2)]
+        self.dh = [ctx.z(B, b) for (_, b) in dims]
+        self.ddin = ctx.z(B, dims[0][0])
+
+    def adopt(self, module):
+        self.flat.adopt(module)
+        for i, L in enumerate(self.layers):
+            lin = module.net[2 * i]
+            L.u.copy_(lin.weight_u)
+            L.v.copy_(lin.weight_v)
+            lin._buffers["weight_u"], lin._buffers["weight_v"] = L.u, L.v
+
+    def fwd(self, x, onehot, p, iterate=True):
+        """Forward pass p (0 or 1): power iteration + normalisation of every layer, then the MLP; returns [B,1]."""
+        xd = x.shape[1]
+        K.copy_cols(x, 0, self.din[p], 0, xd)
+        K.copy_cols(onehot, 0, self.din[p], xd, onehot.shape[1])
+        h = self.din[p]
+        for i, L in enumerate(self.layers):
+            L.normalise(p, iterate)
+            L.fwd(h, self.h[p][i], p, K.ACT_LRELU if i < 3 else K.ACT_NONE, 0.2)
+            h = self.h[p][i]
+        return h
+
+    def bwd(self, dz, p, garena=None, want_dx=False):
+        """dz: gradient wrt the critic output [B,1].  Weight gradients go to garena (None = data gradient only)."""
+        d = dz
+        for i in range(3, -1, -1):
+            L = self.layers[i]
+            xin = self.din[p] if i == 0 else self.h[p][i - 1]
+            if garena is not None:
+                L.wgrad(xin, d, p, garena)
+            if i == 0:
+                if want_dx:
+                    L.dgrad(d, self.ddin, p)
+                break
+            L.dgrad(d, self.dh[i - 1], p, act_ref=self.h[p][i - 1], ref_act=K.ACT_LRELU, ref_slope=0.2)
+            d = self.dh[i - 1]
+        return self.ddin
+
+    def g1(self, n):
+        return self.flat.g(n)
+
+    def g2(self, n):
+        return self.flat._view(self.grad2, n)
+
+
+class GraphStep:
+    """Runs ``body`` eagerly once on a state snapshot (module loads, attribute setting), then replays a CUDA graph."""
+
+    def __init__(self, body, state_tensors, refresh, use_graph=True):
+        self.body, self.state, self.refresh, self.use_graph, self.graph = body, state_tensors, refresh, use_graph, None
+
+    def __call__(self):
+        if not self.use_graph:
+            self.body()
+            return
+        if self.graph is None:
+            snap = [t.clone() for t in self.state()]
+            self.body()
+            torch.cuda.synchronize()
+            for dst, src in zip(self.state(), snap):
+                dst.copy_(src)
+            self.refresh()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.body()
+        self.graph.replay()

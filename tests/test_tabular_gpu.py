@@ -1,0 +1,82 @@
+"""GPU parity of the native tabular CounteRGAN plans (moons, KC house sales) against the oracle."""
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from oracle import tabular_countergan as T
+
+pytestmark = pytest.mark.gpu
+
+
+def l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+def _load_critic(plan_D, PD, BD):
+    plan_D.flat.load(PD)
+    for i, L in enumerate(plan_D.layers):
+        L.u.copy_(BD[f"net.{2 * i}.weight_u"])
+        L.v.copy_(BD[f"net.{2 * i}.weight_v"])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_moons_step_matches_oracle(graph):
+    import pcg_b200  # noqa: F401
+    from pcg_b200.tabular.moons import MoonsPlan
+    gs, ds, cs = T.moons_shapes()
+    PG, PD, PC = T.synth_params(gs, 1), T.synth_params(ds, 2), T.synth_params(cs, 3)
+    BD = T.sn_buffers(T.moons_d_dims(), 4)
+    S = T.make_state(PG, T.bn_buffers(gs), PD, BD, PC)
+    B = 64
+    plan = MoonsPlan(B, "cuda", use_graph=graph)
+    plan.G.load(PG)
+    plan.C.load(PC)
+    _load_critic(plan.D, PD, BD)
+    plan.refresh()
+    names = ["d_loss", "g_loss", "g_adv", "g_cls", "l1", "l2", "mask_pen"]
+    for step in range(3):
+        b = T.moons_batch(B, 50 + step)
+        sc, gr = T.moons_step(S, *b)
+        got = plan.step(*[t.cuda() for t in b]).tolist()
+        tol = 3e-5 if step == 0 else 3e-3
+        for i, k in enumerate(names):
+            assert abs(got[i] - sc[k]) <= tol * max(abs(sc[k]), 1e-3), (step, k, got[i], sc[k])
+        if step == 0:
+            for k in gr["G"]:
+                if k in ("net.0.bias", "net.3.bias", "net.6.bias"):
+                    continue        # BN-shadowed biases: analytically zero gradient
+                assert l2(plan.G.g(k), gr["G"][k]) < 2e-3, (k, l2(plan.G.g(k), gr["G"][k]))
+    # spectral-norm vectors advanced three times per step on both sides
+    assert l2(plan.D.layers[0].u, S["DB"]["net.0.weight_u"]) < 1e-3
+    assert l2(plan.gbn[1].rm, S["GB"]["net.4.running_mean"]) < 5e-2
+    for k in S["D"]:
+        assert ((plan.D.flat.p(k).cpu() - S["D"][k].detach()).abs().mean() / 1e-3).item() < 0.1, k
+
+
+def test_moons_mirror_and_trainer(tmp_path):
+    import numpy as np
+    import pcg_b200  # noqa: F401
+    from pcg_b200.tabular import moons as MO
+    torch.manual_seed(0)
+    G = MO.ResidualGenerator(2, 32, 3).cuda()
+    C = MO.NNClassifier(2).cuda()
+    assert list(G.state_dict().keys())[:7] == ["net.0.weight", "net.0.bias", "net.1.weight", "net.1.bias",
+                                               "net.1.running_mean", "net.1.running_var", "net.1.num_batches_tracked"]
+    x, y, t, mask = T.moons_batch(32, 7)
+    PG = OrderedDict((k, v.detach().cpu()) for k, v in G.named_parameters())
+    BG = OrderedDict((k, v.detach().cpu().clone()) for k, v in G.named_buffers())
+    oh = torch.nn.functional.one_hot(t, 3).float()
+    raw, masked = G(x.cuda(), oh.cuda(), mask.cuda())
+    raw_o, masked_o = T.moons_g_forward(PG, BG, x, oh, mask)
+    assert l2(raw, raw_o) < 1e-5 and l2(masked, masked_o) < 1e-5
+    cfg = {"cuda": "cuda", "seed": 1, "epochs": 2, "batch_size": 32, "lr_G": 1e-3, "lr_D": 1e-3, "lambda_cls": 2.0,
+           "lambda_reg_l1": 5.0, "lambda_reg_l2": 5.0, "lambda_mask": 3.0, "input_dim": 2, "hidden_dim": 32,
+           "out_dir": str(tmp_path), "generator_path": str(tmp_path / "g.pt")}
+    X = np.random.RandomState(0).randn(128, 2).astype(np.float32)
+    yv = np.random.RandomState(1).randint(0, 3, 128)
+    d, g = MO.train_countergan(G, cfg, X, yv, C)
+    assert len(d) == 2 and np.isfinite(d).all() and np.isfinite(g).all()
+    sd = torch.load(cfg["generator_path"])
+    assert list(sd.keys()) == list(G.state_dict().keys())
