@@ -80,3 +80,72 @@ def test_moons_mirror_and_trainer(tmp_path):
     assert len(d) == 2 and np.isfinite(d).all() and np.isfinite(g).all()
     sd = torch.load(cfg["generator_path"])
     assert list(sd.keys()) == list(G.state_dict().keys())
+
+
+def _kc_plan(B, graph):
+    import pcg_b200  # noqa: F401
+    from pcg_b200.tabular.kc import KcPlan
+    cat = OrderedDict((f, {"n": n, "raw_values": T.KC_RAW[f]}) for f, n in T.KC_CAT.items())
+    return KcPlan(B, "cuda", cat, T.KC_CONT, use_graph=graph)
+
+
+@pytest.mark.parametrize("graph,B", [(False, 64), (True, 256)])
+def test_kc_step_matches_oracle(graph, B):
+    gs, ds, cs = T.kc_shapes()
+    PG, PD, PC = T.synth_params(gs, 1), T.synth_params(ds, 2), T.synth_params(cs, 3)
+    BD, BC = T.sn_buffers(T.kc_d_dims(), 4), T.bn_buffers(cs, 5, randomize=True)
+    S = T.make_state(PG, T.bn_buffers(gs), PD, BD, PC, BC)
+    plan = _kc_plan(B, graph)
+    plan.G.load(PG)
+    plan.C.load(PC)
+    for j, nm in enumerate(plan.c_bn_names):
+        plan.c_rm[j].copy_(BC[nm + ".running_mean"])
+        plan.c_rv[j].copy_(BC[nm + ".running_var"])
+    _load_critic(plan.D, PD, BD)
+    plan.refresh()
+    nv = T.kc_norm_vals()
+    names = ["d_loss", "g_loss", "g_adv", "g_cls", "reg", "mask_pen"]
+    for step in range(2):
+        b = T.kc_batch(B, 80 + step)
+        sc, gr = T.kc_step(S, *b, nv)
+        x, y, t, mask, noise = b
+        got = plan.step(x.cuda(), y.cuda(), t.cuda(), mask.cuda(), [e.cuda() for e in noise]).tolist()
+        tol = 5e-5 if step == 0 else 5e-3
+        for i, k in enumerate(names):
+            assert abs(got[i] - sc[k]) <= tol * max(abs(sc[k]), 1e-3), (step, k, got[i], sc[k])
+        if step == 0:
+            assert l2(plan.xcf, gr["x_cf"]) < 1e-5
+            for k in gr["G"]:
+                if k.endswith("fc1.bias") or k.endswith("fc2.bias") or gr["G"][k] is None:
+                    continue        # BN-shadowed biases: analytically zero gradient
+                assert l2(plan.G.g(k), gr["G"][k]) < 3e-3, (k, l2(plan.G.g(k), gr["G"][k]))
+            d = plan.diagnostics()
+            for k in ("pred_gain", "sparsity", "l2", "flip"):
+                assert abs(d[k] - sc[k]) <= 2e-3 * max(abs(sc[k]), 1e-2), (k, d[k], sc[k])
+    for k in S["D"]:
+        assert ((plan.D.flat.p(k).cpu() - S["D"][k].detach()).abs().mean() / 1e-3).item() < 0.1, k
+
+
+def test_kc_mirror_and_trainer(tmp_path):
+    import numpy as np
+    import pcg_b200  # noqa: F401
+    from pcg_b200.tabular import kc as KC
+    cat = OrderedDict((f, {"n": n, "raw_values": T.KC_RAW[f]}) for f, n in T.KC_CAT.items())
+    torch.manual_seed(0)
+    G = KC.ResidualGenerator(17, 32, 4, T.KC_CONT, cat).cuda()
+    C = KC.NNClassifier(17, 4).cuda().eval()
+    gs, _, cs = T.kc_shapes()
+    assert [k for k, _ in G.named_parameters()] == list(gs.keys())
+    assert [k for k, _ in C.named_parameters()] == list(cs.keys())
+    x, y, t, mask, noise = T.kc_batch(32, 3)
+    cont, logits, samples = G(x.cuda(), torch.nn.functional.one_hot(t, 4).float().cuda(), mask.cuda())
+    assert cont.shape == (32, 10) and samples[1].shape == (32, 30) and abs(samples[8].sum(1).mean().item() - 1) < 1e-5
+    cfg = {"cuda": "cuda", "seed": 1, "epochs": 1, "batch_size": 64, "lr_G": 1e-3, "lr_D": 1e-3, "lambda_cls": 2.0,
+           "lambda_reg": 1.0, "lambda_mask": 1.0, "input_dim": 17, "hidden_dim": 32, "gumbel_tau": 0.5, "scaler": None,
+           "categorical_info": cat, "continuous_idx": T.KC_CONT, "immutable_idx": T.KC_IMMUTABLE,
+           "out_dir": str(tmp_path), "generator_path": str(tmp_path / "g.pt")}
+    X = torch.cat([T.kc_batch(64, 200 + i)[0] for i in range(3)]).numpy()
+    yv = np.random.RandomState(1).randint(0, 4, len(X))
+    d, g = KC.train_countergan(G, cfg, X, yv, C)
+    assert np.isfinite(d).all() and np.isfinite(g).all()
+    assert list(torch.load(cfg["generator_path"]).keys()) == list(G.state_dict().keys())
