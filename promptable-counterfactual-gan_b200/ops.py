@@ -63,10 +63,14 @@ def conv_dgrad(dout, N, H, W, Cin, wd, Cout, k, stride, pad, din, add_src=None, 
                                    _f(ref_slope), P(din), _s()))
 
 
-def conv_wgrad_scratch(N, H, W, Cin, Cout, k, stride, pad, device):
+def conv_wgrad_scratch_floats(N, H, W, Cin, Cout, k, stride, pad):
     L = _L()
     L.pcg_conv_wgrad_scratch.restype = ctypes.c_longlong
-    return torch.zeros(int(L.pcg_conv_wgrad_scratch(N, H, W, Cin, Cout, k, stride, pad)), device=device)
+    return int(L.pcg_conv_wgrad_scratch(N, H, W, Cin, Cout, k, stride, pad))
+
+
+def conv_wgrad_scratch(N, H, W, Cin, Cout, k, stride, pad, device):
+    return torch.zeros(conv_wgrad_scratch_floats(N, H, W, Cin, Cout, k, stride, pad), device=device)
 
 
 def conv_wgrad(x, dout, N, H, W, Cin, Cout, k, stride, pad, scratch, dw):

@@ -12,7 +12,19 @@ class Ctx:
     def __init__(self, B, dev, max_dim=256):
         self.B, self.dev = B, dev
         self.stat = K.stat_scratch(max(max_dim, 4), dev)
-        self.wsc = torch.zeros(int(K.conv_wgrad_scratch(B, 1, 1, max_dim, max_dim, 1, 1, 0, dev).numel()) + 1024, device=dev)
+        self._wsc_need, self._wsc = K.conv_wgrad_scratch_floats(B, 1, 1, max_dim, max_dim, 1, 1, 0), None
+
+    def reserve_wgrad(self, k_in, n_out):
+        """Every layer registers its wgrad geometry: the split-K partial buffer depends on the shape (the Cout==1 path
+        keeps one partial row per block), so the shared scratch is sized for the largest request."""
+        assert self._wsc is None, "layers must be created before the first wgrad"
+        self._wsc_need = max(self._wsc_need, K.conv_wgrad_scratch_floats(self.B, 1, 1, k_in, n_out, 1, 1, 0))
+
+    @property
+    def wsc(self):
+        if self._wsc is None:
+            self._wsc = torch.zeros(self._wsc_need + 1024, device=self.dev)
+        return self._wsc
 
     def z(self, *s):
         return torch.zeros(*s, device=self.dev)
@@ -22,6 +34,7 @@ class Dense:
     def __init__(self, ctx, flat, name, k_in, n_out):
         self.ctx, self.flat, self.name, self.k, self.n = ctx, flat, name, k_in, n_out
         self.wT = ctx.z(k_in, n_out)
+        ctx.reserve_wgrad(k_in, n_out)
 
     def W(self):
         return self.flat.p(self.name + ".weight")
@@ -74,6 +87,7 @@ class SNDense:
     def __init__(self, ctx, flat, name, k_in, n_out, passes=2):
         self.ctx, self.flat, self.name, self.k, self.n = ctx, flat, name, k_in, n_out
         z = ctx.z
+        ctx.reserve_wgrad(k_in, n_out)
         self.u, self.v = z(n_out), z(k_in)
         self.Wn = [z(n_out, k_in) for _ in range(passes)]
         self.WnT = [z(k_in, n_out) for _ in range(passes)]
