@@ -99,6 +99,23 @@ CUtensorMap make_tmap_nhwc_box(const bf16* base, int N, int H, int W, int C, int
   if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string(int(r)));
   return m;
 }
+// Same with `box_c` (16, 32 or 64) channels per pixel: 32/64/128-byte rows, matching swizzle.
+CUtensorMap make_tmap_nhwc_box_c(const bf16* base, int N, int H, int W, int C, int box_c, int box_w, int box_h) {
+  load_driver_entry_points();
+  PCG_REQUIRE(box_c == 16 || box_c == 32 || box_c == 64, "box_c must be 16, 32 or 64");
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                            : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled(4d, box_c) failed: " + std::to_string(int(r)));
+  return m;
+}
 // Convolution window: lower = -pad, upper = pad - (k-1)  (dilation 1).
 static CUtensorMap make_tmap_im2col(const bf16* base, int N, int H, int W, int C, int ksize, int stride, int pad) {
   return make_tmap_im2col_box(base, N, H, W, C, -pad, -pad, pad - (ksize - 1), pad - (ksize - 1), stride);

@@ -66,6 +66,7 @@ CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, uint32_
 CUtensorMap make_tmap_im2col_box(const bf16* base, int N, int H, int W, int C, int lower_w, int lower_h,
                                  int upper_w, int upper_h, int stride);
 CUtensorMap make_tmap_nhwc_box(const bf16* base, int N, int H, int W, int C, int box_w, int box_h);
+CUtensorMap make_tmap_nhwc_box_c(const bf16* base, int N, int H, int W, int C, int box_c, int box_w, int box_h);
 
 // ---- 64 -> 64, 3x3, stride 1, pad 1 convolutions with a shared-memory halo tile (conv_tc64.cu) ----------
 // One TMA box per tile brings (R+2) x (W+2) zero-padded pixels; the nine filter taps are shifted views of that

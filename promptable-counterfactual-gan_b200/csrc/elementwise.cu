@@ -1,10 +1,14 @@
 // HBM-bound kernels of the GAN step (see elementwise.cuh for the reference call sites).
 #include "elementwise.cuh"
 
+#include <initializer_list>
+
 namespace pcg {
 
 // ---------------------------------------------------------------------------------------------
-// vector helpers: 4 consecutive channels
+// vector helpers: V (4 or 8) consecutive channels per thread.  V = 8 makes every bf16 access 16 bytes
+// (fp32: 2 x 16), which together with two rows in flight per thread is what it takes to keep
+// enough bytes outstanding for HBM3e (~5 MB at 6.5 TB/s x 800 ns).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
   const float4 f = *reinterpret_cast<const float4*>(p);
@@ -26,6 +30,37 @@ __device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
   u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
 }
+__device__ __forceinline__ void ldv(const float* p, float (&v)[4]) { ld4(p, v); }
+__device__ __forceinline__ void ldv(const bf16* p, float (&v)[4]) { ld4(p, v); }
+__device__ __forceinline__ void stv(float* p, const float (&v)[4]) { st4(p, v); }
+__device__ __forceinline__ void stv(bf16* p, const float (&v)[4]) { st4(p, v); }
+__device__ __forceinline__ void ldv(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ldv(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void stv(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void stv(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&a);
+  }
+  *reinterpret_cast<uint4*>(p) = u;
+}
 
 __device__ __forceinline__ float act_fwd(float v, int act, float slope) {
   if (act == ACT_LRELU) return v > 0.f ? v : v * slope;
@@ -40,8 +75,8 @@ __device__ __forceinline__ float act_grad(float out, int act, float slope) {
 
 // ---------------------------------------------------------------------------------------------
 // Column reductions over a row slice of an [M][C] matrix.
-// Block = 256 threads; C/4 threads span a row (4 channels each); 256/(C/4) rows per pass.
-// Each block writes part[blockIdx.x][NV*C].
+// Block = 256 threads; C/V threads span a row (V channels each); 256/(C/V) rows per pass, two passes in
+// flight per thread.  Each block writes part[blockIdx.x][NV*C].
 // ---------------------------------------------------------------------------------------------
 struct RowSlice {
   long long begin, end;
@@ -54,26 +89,28 @@ __device__ __forceinline__ RowSlice row_slice(long long M) {
   return r;
 }
 
-template <int NV>
-__device__ __forceinline__ void block_col_reduce(float (&acc)[NV][4], int C, float* part_row) {
-  // threads with the same (threadIdx.x % (C/4)) own the same 4 channels
-  __shared__ float red[256 * 4];
-  const int lpr = C >> 2;
+template <int NV, int V>
+__device__ __forceinline__ void block_col_reduce(float (&acc)[NV][V], int C, float* part_row) {
+  // threads with the same (threadIdx.x % (C/V)) own the same V channels
+  __shared__ float red[256 * V];
+  const int lpr = C / V;
   const int cg = threadIdx.x % lpr;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[threadIdx.x * 4 + j] = acc[v][j];
+    for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = acc[v][j];
     __syncthreads();
     if (threadIdx.x < lpr) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      float s[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) s[j] = 0.f;
       for (int r = threadIdx.x; r < 256; r += lpr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] += red[r * 4 + j];
+        for (int j = 0; j < V; ++j) s[j] += red[r * V + j];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) part_row[v * C + cg * 4 + j] = s[j];
+      for (int j = 0; j < V; ++j) part_row[v * C + cg * V + j] = s[j];
     }
   }
 }
@@ -81,31 +118,58 @@ __device__ __forceinline__ void block_col_reduce(float (&acc)[NV][4], int C, flo
 static void check_colshape(int C) {
   PCG_REQUIRE(C % 4 == 0 && C <= 1024 && (256 % (C / 4)) == 0, "channel count must be 4*2^k <= 1024");
 }
-
+// 8-wide vectors need C % 8 == 0, a power-of-two lane group and (V * sizeof(T))-byte aligned rows
 template <typename T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, long long M, int C,
+static bool wide_ok(int C, std::initializer_list<const void*> ptrs) {
+  if (C % 8 != 0 || (256 % (C / 8)) != 0) return false;
+  for (const void* p : ptrs)
+    if (p != nullptr && (reinterpret_cast<uintptr_t>(p) % (8 * sizeof(T))) != 0) return false;
+  return true;
+}
+
+// Walks the block's row slice two rows at a time: body(r) is called for each row with its loads issued
+// back to back (the compiler hoists both rows' loads above the arithmetic).
+#define PCG_ROWS2(sl, r0, rpp, BODY)                                   \
+  {                                                                    \
+    long long r = (sl).begin + (r0);                                   \
+    for (; r + (rpp) < (sl).end; r += 2 * (rpp)) { BODY(r, r + (rpp)) } \
+    if (r < (sl).end) { BODY(r, -1) }                                  \
+  }
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256, 4) bn_stats_kernel(const T* __restrict__ y, long long M, int C,
                                                       float* __restrict__ part) {
-  const int lpr = C >> 2, rpp = 256 / lpr;
+  const int lpr = C / V, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
   const RowSlice sl = row_slice(M);
-  float acc[2][4] = {};
-  for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
-    float v[4];
-    ld4(y + r * C + cg * 4, v);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      acc[0][j] += v[j];
-      acc[1][j] = fmaf(v[j], v[j], acc[1][j]);
-    }
+  float acc[2][V] = {};
+#define BODY(ra, rb)                                                   \
+  {                                                                    \
+    float va[V], vb[V];                                                \
+    ldv(y + (ra) * C + cg * V, va);                                    \
+    if ((rb) >= 0) ldv(y + (rb) * C + cg * V, vb);                     \
+    _Pragma("unroll") for (int j = 0; j < V; ++j) {                    \
+      acc[0][j] += va[j];                                              \
+      acc[1][j] = fmaf(va[j], va[j], acc[1][j]);                       \
+    }                                                                  \
+    if ((rb) >= 0) {                                                   \
+      _Pragma("unroll") for (int j = 0; j < V; ++j) {                  \
+        acc[0][j] += vb[j];                                            \
+        acc[1][j] = fmaf(vb[j], vb[j], acc[1][j]);                     \
+      }                                                                \
+    }                                                                  \
   }
-  block_col_reduce<2>(acc, C, part + (size_t)blockIdx.x * 2 * C);
+  PCG_ROWS2(sl, r0, rpp, BODY)
+#undef BODY
+  block_col_reduce<2, V>(acc, C, part + (size_t)blockIdx.x * 2 * C);
 }
 
 template <typename T>
 void bn_stats_partial(const T* y, long long M, int C, float* part, cudaStream_t s) {
   PCG_PROFILE("bn_stats", s);
   check_colshape(C);
-  bn_stats_kernel<T><<<STAT_PARTS, 256, 0, s>>>(y, M, C, part);
+  if (wide_ok<T>(C, {y})) bn_stats_kernel<T, 8><<<STAT_PARTS, 256, 0, s>>>(y, M, C, part);
+  else bn_stats_kernel<T, 4><<<STAT_PARTS, 256, 0, s>>>(y, M, C, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -154,24 +218,47 @@ void bn_finalize(const float* part, int nparts, long long M, int C, const float*
   PCG_LAUNCH_CHECK();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, long long n4, int C,
-                                                          int act, float slope, T* __restrict__ z) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % C);
-    float v[4];
-    ld4(y + i * 4, v);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = act_fwd(fmaf(v[j], __ldg(scale + c + j), __ldg(shift + c + j)), act, slope);
-    st4(z + i * 4, v);
-  }
-}
-
 static int ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// Element-wise BatchNorm-apply kernels: thread i owns vectors i, i + S, ... of V channels where the stride S (total
+// threads) is a multiple of C/V, so a thread always sees the same channels and keeps scale/shift in registers;
+// two vectors in flight; the activation is a template parameter.
+template <typename T, int V, int ACT>
+__global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, long long nv, int C,
+                                                          float slope, T* __restrict__ z) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)((i0 * V) % C);
+  float a[V], b[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { a[j] = scale[c0 + j]; b[j] = shift[c0 + j]; }
+  for (long long i = i0; i < nv; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < nv;
+    float va[V], vb[V];
+    ldv(y + i * V, va);
+    if (two) ldv(y + i2 * V, vb);
+#pragma unroll
+    for (int j = 0; j < V; ++j) va[j] = act_fwd(fmaf(va[j], a[j], b[j]), ACT, slope);
+    stv(z + i * V, va);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) vb[j] = act_fwd(fmaf(vb[j], a[j], b[j]), ACT, slope);
+      stv(z + i2 * V, vb);
+    }
+  }
+}
+
+// grid whose total thread count is a multiple of `period` vectors (so a thread's channel group never changes)
+static int ew_blocks_periodic(long long nvec, int period) {
+  int blocks = ew_blocks((nvec + 1) / 2);
+  while (((long long)blocks * 256) % period != 0) ++blocks;
+  return blocks;
 }
 
 template <typename T>
@@ -179,25 +266,46 @@ void bn_apply_act(const T* y, const float* scale, const float* shift, long long 
                   cudaStream_t s) {
   PCG_PROFILE("bn_apply", s);
   PCG_REQUIRE(C % 4 == 0, "C % 4");
-  const long long n4 = M * C / 4;
-  bn_apply_act_kernel<T><<<ew_blocks(n4), 256, 0, s>>>(y, scale, shift, n4, C, act, slope, z);
+#define PCG_L(V, A) bn_apply_act_kernel<T, V, A><<<ew_blocks_periodic(nv, C / V), 256, 0, s>>>(y, scale, shift, nv, C, slope, z)
+#define PCG_LA(V) { if (act == ACT_LRELU) PCG_L(V, ACT_LRELU); else if (act == ACT_RELU) PCG_L(V, ACT_RELU); else PCG_L(V, ACT_NONE); }
+  if (C % 8 == 0 && wide_ok<T>(8, {y, z})) {
+    const long long nv = M * C / 8;
+    PCG_LA(8)
+  } else {
+    const long long nv = M * C / 4;
+    PCG_LA(4)
+  }
+#undef PCG_LA
+#undef PCG_L
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 bn_apply_residual_kernel(const T* __restrict__ y, const T* __restrict__ h, const float* __restrict__ scale,
-                         const float* __restrict__ shift, float res_scale, long long n4, int C, T* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % C);
-    float v[4], hv[4];
-    ld4(y + i * 4, v);
-    ld4(h + i * 4, hv);
+                         const float* __restrict__ shift, float res_scale, long long nv, int C, T* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)((i0 * V) % C);
+  float a[V], b[V];          // out = h + (res_scale*scale)*y + res_scale*shift
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      v[j] = hv[j] + res_scale * fmaf(v[j], __ldg(scale + c + j), __ldg(shift + c + j));
-    st4(out + i * 4, v);
+  for (int j = 0; j < V; ++j) { a[j] = res_scale * scale[c0 + j]; b[j] = res_scale * shift[c0 + j]; }
+  for (long long i = i0; i < nv; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < nv;
+    float va[V], ha[V], vb[V], hb[V];
+    ldv(y + i * V, va);
+    ldv(h + i * V, ha);
+    if (two) { ldv(y + i2 * V, vb); ldv(h + i2 * V, hb); }
+#pragma unroll
+    for (int j = 0; j < V; ++j) va[j] = ha[j] + fmaf(va[j], a[j], b[j]);
+    stv(out + i * V, va);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) vb[j] = hb[j] + fmaf(vb[j], a[j], b[j]);
+      stv(out + i2 * V, vb);
+    }
   }
 }
 
@@ -206,39 +314,85 @@ void bn_apply_residual(const T* y, const T* h, const float* scale, const float* 
                        int C, T* out, cudaStream_t s) {
   PCG_PROFILE("bn_apply", s);
   PCG_REQUIRE(C % 4 == 0, "C % 4");
-  const long long n4 = M * C / 4;
-  bn_apply_residual_kernel<T><<<ew_blocks(n4), 256, 0, s>>>(y, h, scale, shift, res_scale, n4, C, out);
+  if (C % 8 == 0 && wide_ok<T>(8, {y, h, out})) {
+    const long long nv = M * C / 8;
+    bn_apply_residual_kernel<T, 8><<<ew_blocks_periodic(nv, C / 8), 256, 0, s>>>(y, h, scale, shift, res_scale, nv, C, out);
+  } else {
+    const long long nv = M * C / 4;
+    bn_apply_residual_kernel<T, 4><<<ew_blocks_periodic(nv, C / 4), 256, 0, s>>>(y, h, scale, shift, res_scale, nv, C, out);
+  }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 
-// g = gscale * dsrc * act'(scale*y + shift)
+// ---- BatchNorm backward.  These kernels are instruction-issue bound before they are HBM bound (bf16 unpacking plus
+// ~10 operations per element), so: the activation is a template parameter, the per-channel algebra is folded into
+// as few constants as possible, each thread owns 4 channels (constants stay in registers under 64 registers =
+// four resident blocks per SM) and keeps four rows in flight as raw (still packed) loads.
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { typedef float4 type; };
+template <> struct Raw4<bf16> { typedef uint2 type; };
+__device__ __forceinline__ void unpack4(const float4& r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+__device__ __forceinline__ void unpack4(const uint2& r, float (&v)[4]) {
+  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
 template <typename T>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ typename Raw4<T>::type ldraw(const T* p) {
+  return *reinterpret_cast<const typename Raw4<T>::type*>(p);
+}
+template <typename T>
+__device__ __forceinline__ typename Raw4<T>::type zero_raw() {
+  typename Raw4<T>::type z;
+  memset(&z, 0, sizeof(z));
+  return z;
+}
+constexpr int BNB_UN = 4;    // rows in flight per thread
+
+// g = gscale * dsrc * act'(scale*y + shift);  part[.][2C] = (sum g, sum g*xhat)
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_partial_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const float* __restrict__ mean,
                       const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
-                      float gscale, int act, float slope, long long M, int C, float* __restrict__ part) {
+                      float gscale, float slope, long long M, int C, float* __restrict__ part) {
   const int lpr = C >> 2, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
   const RowSlice sl = row_slice(M);
-  float mu[4], rs[4], a[4], b[4];
+  float rs[4], nmr[4], a[4], b[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    mu[j] = mean[cg * 4 + j]; rs[j] = rstd[cg * 4 + j]; a[j] = scale[cg * 4 + j]; b[j] = shift[cg * 4 + j];
+    const int c = cg * 4 + j;
+    rs[j] = rstd[c]; nmr[j] = -mean[c] * rstd[c];        // xhat = v*rs + nmr
+    a[j] = scale[c]; b[j] = shift[c];
   }
   float acc[2][4] = {};
-  for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
-    float d[4], v[4];
-    ld4(dsrc + r * C + cg * 4, d);
-    ld4(y + r * C + cg * 4, v);
+  for (long long r = sl.begin + r0; r < sl.end; r += BNB_UN * rpp) {
+    typename Raw4<T>::type rd[BNB_UN], rv[BNB_UN];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float g = gscale * d[j] * act_grad(fmaf(v[j], a[j], b[j]), act, slope);
-      acc[0][j] += g;
-      acc[1][j] = fmaf(g, (v[j] - mu[j]) * rs[j], acc[1][j]);
+    for (int u = 0; u < BNB_UN; ++u) {
+      const long long rr = r + u * rpp;
+      const bool ok = rr < sl.end;
+      rd[u] = ok ? ldraw<T>(dsrc + rr * C + cg * 4) : zero_raw<T>();
+      rv[u] = ok ? ldraw<T>(y + rr * C + cg * 4) : zero_raw<T>();
+    }
+#pragma unroll
+    for (int u = 0; u < BNB_UN; ++u) {
+      float d[4], v[4];
+      unpack4(rd[u], d);
+      unpack4(rv[u], v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float g = d[j];
+        if (ACT == ACT_LRELU) g = fmaf(v[j], a[j], b[j]) > 0.f ? g : g * slope;
+        if (ACT == ACT_RELU) g = fmaf(v[j], a[j], b[j]) > 0.f ? g : 0.f;
+        acc[0][j] += g;
+        acc[1][j] = fmaf(g, fmaf(v[j], rs[j], nmr[j]), acc[1][j]);
+      }
     }
   }
-  block_col_reduce<2>(acc, C, part + (size_t)blockIdx.x * 2 * C);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { acc[0][j] *= gscale; acc[1][j] *= gscale; }
+  block_col_reduce<2, 4>(acc, C, part + (size_t)blockIdx.x * 2 * C);
 }
 
 template <typename T>
@@ -247,7 +401,11 @@ void bn_bwd_partial(const T* dsrc, const T* y, const float* mean, const float* r
                     cudaStream_t s) {
   PCG_PROFILE("bn_bwd_reduce", s);
   check_colshape(C);
-  bn_bwd_partial_kernel<T><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, gscale, act, slope, M, C, part);
+#define PCG_L(A) bn_bwd_partial_kernel<T, A><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, gscale, slope, M, C, part)
+  if (act == ACT_LRELU) PCG_L(ACT_LRELU);
+  else if (act == ACT_RELU) PCG_L(ACT_RELU);
+  else PCG_L(ACT_NONE);
+#undef PCG_L
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -273,36 +431,57 @@ void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* d
   PCG_LAUNCH_CHECK();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// dy = gamma*rstd * (g - c1 - xhat*c2) with g as above, folded per channel into
+//   dy = ag * (dsrc * act') + nk2 * y + k0,   ag = a*gscale, nk2 = -a*c2*rstd, k0 = a*(c2*rstd*mean - c1), a = gamma*rstd
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
-                    const float* __restrict__ c12, float gscale, int act, float slope, long long M, int C,
+                    const float* __restrict__ c12, float gscale, float slope, long long M, int C,
                     T* __restrict__ dy, float* __restrict__ part_db) {
   const int lpr = C >> 2, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
   const RowSlice sl = row_slice(M);
-  float mu[4], rs[4], a[4], b[4], c1[4], c2[4];
+  float a[4], b[4], ag[4], nk2[4], k0[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = cg * 4 + j;
-    mu[j] = mean[c]; rs[j] = rstd[c]; a[j] = scale[c]; b[j] = shift[c]; c1[j] = c12[c]; c2[j] = c12[C + c];
+    a[j] = scale[c]; b[j] = shift[c];
+    const float c2rs = c12[C + c] * rstd[c];
+    ag[j] = a[j] * gscale;
+    nk2[j] = -a[j] * c2rs;
+    k0[j] = a[j] * (c2rs * mean[c] - c12[c]);
   }
   float acc[1][4] = {};
-  for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
-    float d[4], v[4], o[4];
-    ld4(dsrc + r * C + cg * 4, d);
-    ld4(y + r * C + cg * 4, v);
+  for (long long r = sl.begin + r0; r < sl.end; r += BNB_UN * rpp) {
+    typename Raw4<T>::type rd[BNB_UN], rv[BNB_UN];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float g = gscale * d[j] * act_grad(fmaf(v[j], a[j], b[j]), act, slope);
-      const float xhat = (v[j] - mu[j]) * rs[j];
-      o[j] = a[j] * (g - c1[j] - xhat * c2[j]);     // a = gamma * rstd
-      acc[0][j] += o[j];
+    for (int u = 0; u < BNB_UN; ++u) {
+      const long long rr = r + u * rpp;
+      const bool ok = rr < sl.end;
+      rd[u] = ok ? ldraw<T>(dsrc + rr * C + cg * 4) : zero_raw<T>();
+      rv[u] = ok ? ldraw<T>(y + rr * C + cg * 4) : zero_raw<T>();
     }
-    st4(dy + r * C + cg * 4, o);
+#pragma unroll
+    for (int u = 0; u < BNB_UN; ++u) {
+      const long long rr = r + u * rpp;
+      if (rr < sl.end) {
+        float d[4], v[4], o[4];
+        unpack4(rd[u], d);
+        unpack4(rv[u], v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float g = d[j];
+          if (ACT == ACT_LRELU) g = fmaf(v[j], a[j], b[j]) > 0.f ? g : g * slope;
+          if (ACT == ACT_RELU) g = fmaf(v[j], a[j], b[j]) > 0.f ? g : 0.f;
+          o[j] = fmaf(ag[j], g, fmaf(nk2[j], v[j], k0[j]));
+          acc[0][j] += o[j];
+        }
+        st4(dy + rr * C + cg * 4, o);
+      }
+    }
   }
-  block_col_reduce<1>(acc, C, part_db + (size_t)blockIdx.x * C);
+  block_col_reduce<1, 4>(acc, C, part_db + (size_t)blockIdx.x * C);
 }
 
 template <typename T>
@@ -312,8 +491,11 @@ void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rst
   PCG_PROFILE("bn_bwd_apply", s);
   (void)gamma;
   check_colshape(C);
-  bn_bwd_apply_kernel<T><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, c12, gscale, act, slope, M, C, dy,
-                                                   part_db);
+#define PCG_L(A) bn_bwd_apply_kernel<T, A><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, c12, gscale, slope, M, C, dy, part_db)
+  if (act == ACT_LRELU) PCG_L(ACT_LRELU);
+  else if (act == ACT_RELU) PCG_L(ACT_RELU);
+  else PCG_L(ACT_NONE);
+#undef PCG_L
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -331,42 +513,55 @@ void colsum_finalize(const float* part, int nparts, int stride, int C, float* ou
   PCG_LAUNCH_CHECK();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, long long M, int C,
+template <typename T, int V>
+__global__ void __launch_bounds__(256, 4) colsum_kernel(const T* __restrict__ a, long long M, int C,
                                                     float* __restrict__ part) {
   const RowSlice sl = row_slice(M);
-  if ((C & 3) == 0 && (256 % (C >> 2)) == 0 && C <= 1024) {
-    const int lpr = C >> 2, rpp = 256 / lpr;
+  if (V > 1) {
+    const int lpr = C / V, rpp = 256 / lpr;
     const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
-    float acc[1][4] = {};
-    for (long long r = sl.begin + r0; r < sl.end; r += rpp) {
-      float v[4];
-      ld4(a + r * C + cg * 4, v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[0][j] += v[j];
-    }
-    block_col_reduce<1>(acc, C, part + (size_t)blockIdx.x * C);
-  } else {
-    // tiny / odd channel counts (e.g. C = 1): one column at a time, block tree reduction
-    __shared__ float red[256];
-    for (int c = 0; c < C; ++c) {
-      float s = 0.f;
-      for (long long r = sl.begin + threadIdx.x; r < sl.end; r += 256) s += to_f(a[r * C + c]);
-      red[threadIdx.x] = s;
+    float acc[1][V] = {};
+#define BODY(ra, rb)                                                   \
+  {                                                                    \
+    float va[V], vb[V];                                                \
+    ldv(a + (ra) * C + cg * V, va);                                    \
+    if ((rb) >= 0) ldv(a + (rb) * C + cg * V, vb);                     \
+    _Pragma("unroll") for (int j = 0; j < V; ++j) acc[0][j] += va[j];  \
+    if ((rb) >= 0) {                                                   \
+      _Pragma("unroll") for (int j = 0; j < V; ++j) acc[0][j] += vb[j]; \
+    }                                                                  \
+  }
+    PCG_ROWS2(sl, r0, rpp, BODY)
+#undef BODY
+    block_col_reduce<1, V>(acc, C, part + (size_t)blockIdx.x * C);
+  }
+}
+// tiny / odd channel counts (e.g. C = 1): one column at a time, block tree reduction
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict__ a, long long M, int C,
+                                                           float* __restrict__ part) {
+  const RowSlice sl = row_slice(M);
+  __shared__ float red[256];
+  for (int c = 0; c < C; ++c) {
+    float s = 0.f;
+    for (long long r = sl.begin + threadIdx.x; r < sl.end; r += 256) s += to_f(a[r * C + c]);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
       __syncthreads();
-      for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) part[(size_t)blockIdx.x * C + c] = red[0];
-      __syncthreads();
     }
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * C + c] = red[0];
+    __syncthreads();
   }
 }
 template <typename T>
 void colsum_partial(const T* a, long long M, int C, float* part, cudaStream_t s) {
   PCG_PROFILE("colsum", s);
-  colsum_kernel<T><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
+  if (wide_ok<T>(C, {a})) colsum_kernel<T, 8><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
+  else if ((C & 3) == 0 && (256 % (C >> 2)) == 0 && C <= 1024 && (reinterpret_cast<uintptr_t>(a) % (4 * sizeof(T))) == 0)
+    colsum_kernel<T, 4><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
+  else colsum_scalar_kernel<T><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -413,9 +608,10 @@ void d_input(const float* x, const float* embed, const long long* label, int B, 
   PCG_LAUNCH_CHECK();
 }
 
+// Generic fallback: one thread per (class, pixel), serial over the batch.
 template <typename T>
-__global__ void embed_grad_kernel(const T* __restrict__ src, int nch, int ch, const long long* __restrict__ label,
-                                  int B, int HW, float* __restrict__ dE) {
+__global__ void embed_grad_serial_kernel(const T* __restrict__ src, int nch, int ch, const long long* __restrict__ label,
+                                         int B, int HW, float* __restrict__ dE) {
   const int cls = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
@@ -425,12 +621,57 @@ __global__ void embed_grad_kernel(const T* __restrict__ src, int nch, int ch, co
   }
   dE[(size_t)cls * HW + p] = s;
 }
+// <= 16 classes: a block owns 32 pixels (one per lane); warp w walks samples w, w+16, ... with one register
+// accumulator per class (predicated adds, 8 loads in flight), then the 16 warps are summed in fixed order.
+constexpr int EG_WARPS = 16, EG_CLS = 16;
+template <typename T>
+__global__ void __launch_bounds__(EG_WARPS * 32)
+embed_grad_kernel(const T* __restrict__ src, int nch, int ch, const long long* __restrict__ label, int B, int HW,
+                  int num_classes, float* __restrict__ dE) {
+  __shared__ float red[EG_WARPS][EG_CLS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane;
+  const bool ok = p < HW;
+  float acc[EG_CLS];
+#pragma unroll
+  for (int c = 0; c < EG_CLS; ++c) acc[c] = 0.f;
+  for (int n0 = warp; n0 < B; n0 += EG_WARPS * 8) {
+    float v[8];
+    int lab[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int n = n0 + u * EG_WARPS;
+      const bool in = n < B;
+      lab[u] = in ? (int)label[n] : -1;
+      v[u] = (in && ok) ? to_f(src[((size_t)n * HW + p) * nch + ch]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int c = 0; c < EG_CLS; ++c) acc[c] += (lab[u] == c) ? v[u] : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < EG_CLS; ++c) red[warp][c][lane] = acc[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_classes * 32; i += blockDim.x) {
+    const int c = i >> 5, l = i & 31;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < EG_WARPS; ++w) s += red[w][c][l];
+    const int pp = blockIdx.x * 32 + l;
+    if (pp < HW) dE[(size_t)c * HW + pp] = s;
+  }
+}
 template <typename T>
 void embed_grad(const T* src, int nch, int ch, const long long* label, int B, int HW, int num_classes, float* dE,
                 cudaStream_t s) {
   PCG_PROFILE("embed_grad", s);
-  dim3 grid(cdiv(HW, 128), num_classes);
-  embed_grad_kernel<T><<<grid, 128, 0, s>>>(src, nch, ch, label, B, HW, dE);
+  if (num_classes <= EG_CLS) {
+    embed_grad_kernel<T><<<cdiv(HW, 32), EG_WARPS * 32, 0, s>>>(src, nch, ch, label, B, HW, num_classes, dE);
+  } else {
+    dim3 grid(cdiv(HW, 128), num_classes);
+    embed_grad_serial_kernel<T><<<grid, 128, 0, s>>>(src, nch, ch, label, B, HW, dE);
+  }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -583,24 +824,24 @@ __global__ void d_head_bwd_kernel(const T* __restrict__ z, const float* __restri
     g[(size_t)n * HW * C + i] = from_f<T>(dl * w[c] * (zz > 0.f ? 1.f : slope));
   }
 }
+// part[blockIdx.x][c] = sum over the block's sample slice of dlogit[n] * mean_hw z[n][.][c]; one thread per channel
+// (coalesced over c), fixed order within the slice; the slices are summed by colsum_finalize.
+constexpr int DHW_SLICES = 64;
 template <typename T>
-__global__ void d_head_wgrad_kernel(const T* __restrict__ z, const float* __restrict__ dlogit, int B, int HW, int C,
-                                    float* __restrict__ dw, float* __restrict__ db) {
-  // block = 64 channels x 4 sample-lanes; fixed-order reduction over the 4 sample-lanes in shared memory
-  __shared__ float red[4][64];
-  const int cl = threadIdx.x & 63, ns = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cl;
-  float s = 0.f;
-  if (c < C) {
-    for (int n = ns; n < B; n += 4) {
+__global__ void __launch_bounds__(256)
+d_head_wgrad_kernel(const T* __restrict__ z, const float* __restrict__ dlogit, int B, int HW, int C,
+                    float* __restrict__ part, float* __restrict__ db) {
+  const int per = (B + gridDim.x - 1) / gridDim.x;
+  const int n0 = blockIdx.x * per, n1 = n0 + per < B ? n0 + per : B;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int n = n0; n < n1; ++n) {
       float m = 0.f;
       for (int p = 0; p < HW; ++p) m += to_f(z[((size_t)n * HW + p) * C + c]);
       s = fmaf(dlogit[n], m / (float)HW, s);
     }
+    part[(size_t)blockIdx.x * C + c] = s;
   }
-  red[ns][cl] = s;
-  __syncthreads();
-  if (ns == 0 && c < C) dw[c] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     float t = 0.f;
     for (int n = threadIdx.x; n < B; n += 32) t += dlogit[n];
@@ -610,16 +851,19 @@ __global__ void d_head_wgrad_kernel(const T* __restrict__ z, const float* __rest
 }
 template <typename T>
 void d_head_bwd(const T* z, const float* dlogit, int B, int HW, int C, const float* w, float slope, T* g, float* dw,
-                float* db, cudaStream_t s) {
-  PCG_PROFILE("small", s);
-  d_head_bwd_kernel<T><<<B, 256, 0, s>>>(z, dlogit, HW, C, w, slope, g);
-  PCG_COUNT_LAUNCH();
-  PCG_LAUNCH_CHECK();
-  if (dw != nullptr) {
-    d_head_wgrad_kernel<T><<<cdiv(C, 64), 256, 0, s>>>(z, dlogit, B, HW, C, dw, db);
+                float* db, float* scratch, cudaStream_t s) {
+  {
+    PCG_PROFILE("small", s);
+    d_head_bwd_kernel<T><<<B, 256, 0, s>>>(z, dlogit, HW, C, w, slope, g);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
+    if (dw != nullptr) {
+      d_head_wgrad_kernel<T><<<DHW_SLICES, 256, 0, s>>>(z, dlogit, B, HW, C, scratch, db);
+      PCG_COUNT_LAUNCH();
+      PCG_LAUNCH_CHECK();
+    }
   }
+  if (dw != nullptr) colsum_finalize(scratch, DHW_SLICES, C, C, dw, s);
 }
 
 __global__ void ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int B, int NC,
@@ -762,7 +1006,7 @@ void convert_from_f32(const float* src, long long n, T* dst, cudaStream_t s) {
                                      float, float, float, long long, T*, cudaStream_t);                            \
   template void d_head_fwd<T>(const T*, int, int, int, const float*, const float*, float*, cudaStream_t);          \
   template void d_head_bwd<T>(const T*, const float*, int, int, int, const float*, float, T*, float*, float*,      \
-                              cudaStream_t);                                                                       \
+                              float*, cudaStream_t);                                                                       \
   template void fill_zero<T>(T*, long long, cudaStream_t);                                                         \
   template void convert_from_f32<T>(const float*, long long, T*, cudaStream_t);
 INST(float)

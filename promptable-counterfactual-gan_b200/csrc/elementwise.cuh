@@ -5,7 +5,7 @@
 
 namespace pcg {
 
-constexpr int STAT_PARTS = 592;   // 4 x 148 row-slices for two-stage column reductions
+constexpr int STAT_PARTS = 592;   // 4 x 148 row-slices (4 resident 256-thread blocks per SM) for two-stage column reductions
 
 // ---- BatchNorm2d, train mode (generator.py:12,15; torch native_batch_norm) ------------------
 // Column statistics of y[M][C]: part[STAT_PARTS][2*C] (sum, sum of squares) per row slice.
@@ -79,10 +79,10 @@ void d_head_fwd(const T* z, int B, int HW, int C, const float* w, const float* b
 void bce_logits(const float* logits, int seg, int nseg, float t0, float t1, float w0, float w1, float* out_loss,
                 float* out_p, float* dlogit, cudaStream_t s);
 // g[n][hw][c] = dlogit[n]*w[c]/HW * lrelu'(z);  dw[c] = sum_n dlogit[n]*mean_hw z ; db = sum dlogit
-// (dw/db only if dw != nullptr)
+// (dw/db only if dw != nullptr; `scratch` then holds 64*C floats of per-slice partial sums)
 template <typename T>
 void d_head_bwd(const T* z, const float* dlogit, int B, int HW, int C, const float* w, float slope, T* g, float* dw,
-                float* db, cudaStream_t s);
+                float* db, float* scratch, cudaStream_t s);
 
 // ---- classifier loss (trainer.py:118) ----------------------------------------------------------------
 // loss = mean_n (logsumexp(l[n]) - l[n][t[n]]);  dl = wgt * (softmax - onehot) / B

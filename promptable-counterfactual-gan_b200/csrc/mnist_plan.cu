@@ -16,6 +16,7 @@
 #include "../../include/pcg.h"
 #include "common.cuh"
 #include "conv_generic.cuh"
+#include "conv_small.cuh"
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
 
@@ -58,6 +59,68 @@ static std::vector<TensorSpec> net_layout(int net, int ch, int nres, long long* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Weight re-packing after an Adam update: ONE launch per network walks a device-resident table of layers and
+// writes every layout the step's kernels read (fp32 [Cout][tap][Cin] / [Cin][tap][Cout] for the CUDA-core kernels,
+// bf16 [Cout][tap][Cin], 180-degree-rotated [Cin][tap][Cout] and the stride-2 parity-class matrices for tcgen05).
+struct PackDesc {
+  const float* w;
+  float *wf, *wd;
+  bf16 *tcf, *tcd, *tcs2;
+  int Cout, Cin, taps, perm_hw;
+  int begin;                 // first flat element of this layer in the table-wide index space
+};
+constexpr int PACK_MAX_LAYERS = 40;
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int nlayers, int total) {
+  __shared__ PackDesc d[PACK_MAX_LAYERS];
+  for (int i = threadIdx.x; i < nlayers * (int)(sizeof(PackDesc) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(table)[i];
+  __syncthreads();
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    int l = 0;
+    while (l + 1 < nlayers && g >= d[l + 1].begin) ++l;
+    const PackDesc& L = d[l];
+    const int i = g - L.begin;
+    const int taps = L.taps, Cin = L.Cin, Cout = L.Cout;
+    const int tap = i % taps, ci0 = (i / taps) % Cin, co = i / (taps * Cin);
+    int ci = ci0;
+    if (L.perm_hw > 0) {         // torch flatten index c*HW + hw  ->  NHWC flatten index hw*C + c
+      const int C = Cin / L.perm_hw;
+      const int c = ci / L.perm_hw, hw = ci - c * L.perm_hw;
+      ci = hw * C + c;
+    }
+    const float v = L.w[i];
+    const bf16 vb = __float2bfloat16_rn(v);
+    const size_t f = ((size_t)co * taps + tap) * Cin + ci;
+    if (L.wf) L.wf[f] = v;
+    if (L.wd) L.wd[((size_t)ci * taps + tap) * Cout + co] = v;
+    if (L.tcf) L.tcf[f] = vb;
+    if (L.tcd) L.tcd[((size_t)ci * taps + (taps - 1 - tap)) * Cout + co] = vb;
+    if (L.tcs2) {                // parity classes of the stride-2 data gradient (conv_tc.cu: pack_dgrad_s2_kernel)
+      const int s2 = tap % 3, r = tap / 3;
+      const int ph = (r == 1) ? 0 : 1, pw = (s2 == 1) ? 0 : 1;
+      const int oh = (r == 0) ? 1 : 0, ow = (s2 == 0) ? 1 : 0;
+      const int taps_w = pw ? 2 : 1, ntap = (ph ? 2 : 1) * taps_w;
+      const size_t u = (size_t)Cout * Cin;
+      bf16* dst = L.tcs2 + (ph ? (pw ? 5 * u : 3 * u) : (pw ? u : 0));
+      dst[((size_t)ci * ntap + oh * taps_w + ow) * Cout + co] = vb;
+    }
+  }
+}
+struct PackTable {
+  PackDesc* dev = nullptr;
+  int nlayers = 0, total = 0;
+  void launch(cudaStream_t s) const {
+    if (nlayers == 0) return;
+    PCG_PROFILE("pack_weights", s);
+    int blocks = cdiv(total, 256 * 4);
+    if (blocks > 1184) blocks = 1184;
+    pack_multi_kernel<<<blocks, 256, 0, s>>>(dev, nlayers, total);
+    PCG_COUNT_LAUNCH();
+    PCG_LAUNCH_CHECK();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 template <typename T>
 struct ConvLayer {
   ConvGeom g{};
@@ -73,19 +136,22 @@ struct ConvLayer {
   bool tc_fprop = false, tc_dgrad = false, tc_wgrad = false, tc_dgrad_s2 = false;
   bool tc64 = false;          // 64->64 3x3 s1 p1: halo-tile kernels (conv_tc64.cu)
   bool tc_wgrad_gen = false;  // general tensor-core wgrad (conv_tc.cu)
+  bool to1_fprop = false;     // Cout == 1: conv_to1 on tcf (conv_small.cu)
+  bool to1_dgrad = false;     // Cin <= 4: one input channel's data gradient = conv_to1 on a row of tcd
   int perm_hw = 0;
   std::string name, tag_f, tag_d, tag_w;
 
-  void pack(cudaStream_t s) const {
-    pack_conv_weights_generic(w, g.Cout, g.Cin, g.ksize, perm_hw, wf, wd, s);
-    // the fprop tensor-core packing is the bf16 image of wf (same [Cout][taps][Cin] order, incl. the
-    // NHWC-flatten permutation of fc.1); the dgrad packing additionally rotates the taps.
-    if (tcf) convert_from_f32<bf16>(wf, (long long)g.Cout * g.Cin * g.ksize * g.ksize, tcf, s);
-    if (tcd) {
-      PCG_REQUIRE(perm_hw == 0, "permuted tc dgrad packing unsupported");
-      pack_conv_weights_tc(w, g.Cout, g.Cin, g.ksize, nullptr, tcd, s);
-    }
-    if (tcs2) pack_dgrad_s2_tc(w, g.Cout, g.Cin, tcs2, s);
+  // Only the layouts a kernel of this plan actually reads are written: the fprop tensor-core packing is the bf16
+  // image of wf (same [Cout][taps][Cin] order, incl. the NHWC-flatten permutation of fc.1); the dgrad packing
+  // additionally rotates the taps.  `wd_generic_too`: a channel-select data gradient runs on the CUDA cores.
+  PackDesc desc(bool wd_generic_too) const {
+    PCG_REQUIRE(!(tcd || tcs2) || perm_hw == 0, "permuted tc dgrad packing unsupported");
+    PackDesc d;
+    d.w = w; d.Cout = g.Cout; d.Cin = g.Cin; d.taps = g.ksize * g.ksize; d.perm_hw = perm_hw; d.begin = 0;
+    d.wf = (tc_fprop || to1_fprop) ? nullptr : wf;
+    d.wd = (((tc_dgrad || tc_dgrad_s2) && !wd_generic_too) || to1_dgrad) ? nullptr : wd;
+    d.tcf = tcf; d.tcd = tcd; d.tcs2 = tcs2;
+    return d;
   }
 };
 
@@ -197,6 +263,16 @@ struct MnistPlan : PlanBase {
         if (sc > wg_scratch_elems) wg_scratch_elems = sc;
       }
     }
+    if (kBf16 && cfg.use_tensor_cores && k == 3 && stride == 1 && pad == 1 && perm_hw == 0) {
+      if (Cout == 1 && conv_to1_supported(H, W, Cin)) {
+        L.tcf = alloc<bf16>(n);
+        L.to1_fprop = true;
+      }
+      if (Cin <= 4 && need_wd && conv_to1_supported(H, W, Cout)) {
+        L.tcd = alloc<bf16>(n);
+        L.to1_dgrad = true;
+      }
+    }
     if (kBf16 && cfg.use_tensor_cores && stride == 2 && k == 3 && pad == 1 && Cout % 64 == 0 && Cin % 32 == 0 &&
         need_wd && perm_hw == 0) {
       L.tcs2 = alloc<bf16>(conv_tc_dgrad_s2_pack_elems(Cout, Cin));
@@ -301,6 +377,7 @@ struct MnistPlan : PlanBase {
     l1_part = alloc<float>(STAT_PARTS * 2);
     scal_tmp = alloc<float>(16);
     dbg["dinp"] = {dinp, {MG * 3, PCG_F32}};
+    build_pack_tables();
   }
 
   ~MnistPlan() override {
@@ -326,6 +403,12 @@ struct MnistPlan : PlanBase {
         return;
       }
     }
+    if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, float>::value) {
+      if (L.to1_fprop && e.act == ACT_NONE && e.add_src == nullptr && e.act_ref == nullptr && stats == nullptr) {
+        conv_to1(in, g.N, g.H, g.W, g.Cin, L.tcf, e.bias, out, s);
+        return;
+      }
+    }
     conv_fprop_generic<TIn, TOut>(in, g, L.wf, e, out, s);
     if (stats) {
       if constexpr (std::is_same<TOut, T>::value) bn_stats_partial<T>(out, g.Mout(), g.Cout, stats, s);
@@ -338,6 +421,14 @@ struct MnistPlan : PlanBase {
     ProfTag _tag(L.tag_d.c_str());
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
+    if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, float>::value) {
+      if (L.to1_dgrad && (ch_select >= 0 || g.Cin == 1) && e.bias == nullptr && e.act == ACT_NONE &&
+          e.add_src == nullptr && e.act_ref == nullptr) {
+        const int ci = ch_select >= 0 ? ch_select : 0;
+        conv_to1(dout, g.N, g.H, g.W, g.Cout, L.tcd + (size_t)ci * 9 * g.Cout, nullptr, din, s);
+        return;
+      }
+    }
     if (ch_select >= 0) {
       conv_dgrad_generic<TIn, TOut>(dout, g, L.wd, e, din, s, ch_select);
       return;
@@ -388,18 +479,37 @@ struct MnistPlan : PlanBase {
     colsum_finalize(stat_part2, STAT_PARTS, C, C, db, s);
   }
 
-  void refresh_g(cudaStream_t s) {
-    g_in.pack(s);
-    for (int i = 0; i < nres; ++i) { g_c1[i].pack(s); g_c2[i].pack(s); }
-    g_mid.pack(s); g_out.pack(s);
+  PackTable pack_g, pack_d, pack_c;
+  PackTable make_pack_table(const std::vector<PackDesc>& layers) {
+    PCG_REQUIRE((int)layers.size() <= PACK_MAX_LAYERS, "too many layers for one pack table");
+    std::vector<PackDesc> v = layers;
+    long long off = 0;
+    for (auto& d : v) {
+      d.begin = (int)off;
+      off += (long long)d.Cout * d.Cin * d.taps;
+    }
+    PackTable t;
+    t.nlayers = (int)v.size(); t.total = (int)off;
+    t.dev = alloc<PackDesc>(v.size());
+    PCG_CHECK_CUDA(cudaMemcpy(t.dev, v.data(), v.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
+    return t;
   }
-  void refresh_d(cudaStream_t s) {
-    for (int l = 0; l < 4; ++l) d_conv[l].pack(s);
+  void build_pack_tables() {
+    std::vector<PackDesc> g{g_in.desc(true)};
+    for (int i = 0; i < nres; ++i) { g.push_back(g_c1[i].desc(false)); g.push_back(g_c2[i].desc(false)); }
+    g.push_back(g_mid.desc(false)); g.push_back(g_out.desc(false));
+    pack_g = make_pack_table(g);
+    std::vector<PackDesc> d;
+    for (int l = 0; l < 4; ++l) d.push_back(d_conv[l].desc(l == 0));
+    pack_d = make_pack_table(d);
+    pack_c = make_pack_table({c_conv[0].desc(false), c_conv[1].desc(false), c_conv[2].desc(false), c_fc1.desc(false),
+                              c_fc2.desc(false)});
   }
+  void refresh_g(cudaStream_t s) { pack_g.launch(s); }
+  void refresh_d(cudaStream_t s) { pack_d.launch(s); }
   void refresh_weights(cudaStream_t s) override {
     refresh_g(s); refresh_d(s);
-    for (int l = 0; l < 3; ++l) c_conv[l].pack(s);
-    c_fc1.pack(s); c_fc2.pack(s);
+    pack_c.launch(s);
   }
 
   // ---------------------------------------------------------------- generator forward
@@ -453,7 +563,8 @@ struct MnistPlan : PlanBase {
   // backward from ddlogit; weight grads written when `wg`; dxd[n][784] = gradient wrt input channel `in_ch`
   // (0 = image, needed by the G step; 1 = label-embedding map, needed by the D step)
   void d_bwd(int n, bool wg, int in_ch, cudaStream_t s) {
-    d_head_bwd<T>(dz[3], ddlogit, n, 4, 256, d_head_w, 0.2f, dg[3], wg ? d_dhead_w : nullptr, wg ? d_dhead_b : nullptr, s);
+    d_head_bwd<T>(dz[3], ddlogit, n, 4, 256, d_head_w, 0.2f, dg[3], wg ? d_dhead_w : nullptr, wg ? d_dhead_b : nullptr,
+                  stat_part2, s);
     for (int l = 3; l >= 1; --l) {
       if (wg) wgrad<T, T>(d_conv[l], dz[l - 1], dg[l], s, n);
       GenEpilogue<T> e; e.act_ref = dz[l - 1]; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f;
