@@ -158,4 +158,182 @@ void conv_to1(const bf16* in, int N, int H, int W, int Cin, const bf16* w9, cons
   PCG_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------
+// 1-3 input channels -> 32/64 output channels, 3x3, pad 1, stride 1|2.
+// K = 9*Cs <= 27 is padded to 16 or 32; the A fragments (im2col rows) are assembled in registers from scalar loads
+// of the tiny input (L1/L2 resident), the B fragments (all weights) live in registers, a warp owns 16 consecutive
+// output pixels.  The kernel is bound by writing the Cout-channel output: the accumulators are staged through
+// shared memory so that every lane stores 16 contiguous bytes of a 128-byte pixel row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16_bits(float v) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ uint32_t load_bits(const bf16* p) { return (uint32_t)*reinterpret_cast<const uint16_t*>(p); }
+__device__ __forceinline__ uint32_t load_bits(const float* p) { return bf16_bits(*p); }
+
+constexpr int FEW_STAGE_LD = 72;   // floats per staged row: 64 + 8 keeps the float2 writes and float4 reads conflict-free
+
+template <typename TIn, int CS, int COUT, int STRIDE>
+__global__ void __launch_bounds__(256)
+conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const float* __restrict__ bias, int act,
+                float slope, const bf16* __restrict__ act_ref, float ref_neg, bf16* __restrict__ out, int H, int W,
+                int Ho, int Wo, long long M) {
+  constexpr int K = 9 * CS, KS = (K + 15) / 16, NT = COUT / 8, CH = COUT / 8;
+  __shared__ __align__(16) float stage[8][16][FEW_STAGE_LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane & 3, rr = lane >> 2;
+
+  // B fragments: b0 = B[k = ks*16 + 2q + {0,1}][n = j*8 + rr], b1 = same at k + 8;  B[k][n] = wnk[n*K + k]
+  uint32_t breg[KS][NT][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        const int k = ks * 16 + 2 * q + hb * 8, n = j * 8 + rr;
+        const uint32_t lo = k < K ? load_bits(wnk + n * K + k) : 0u;
+        const uint32_t hi = k + 1 < K ? load_bits(wnk + n * K + k + 1) : 0u;
+        breg[ks][j][hb] = lo | (hi << 16);
+      }
+  // this thread's im2col columns: k = ks*16 + 2q + {0, 1, 8, 9} -> (tap, c) -> element offset relative to the window corner
+  int kdelta[KS * 4], kdr[KS * 4], kds[KS * 4];
+#pragma unroll
+  for (int e = 0; e < KS * 4; ++e) {
+    const int k = (e >> 2) * 16 + 2 * q + (e & 1) + ((e >> 1) & 1) * 8;
+    const int tap = k / CS, c = k - tap * CS;
+    kdr[e] = k < K ? tap / 3 : -100000;          // pushes invalid columns out of range
+    kds[e] = tap % 3;
+    kdelta[e] = ((tap / 3) * W + (tap % 3)) * CS + c;
+  }
+  float bcol[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    bcol[j][0] = bias != nullptr ? __ldg(bias + j * 8 + 2 * q) : 0.f;
+    bcol[j][1] = bias != nullptr ? __ldg(bias + j * 8 + 2 * q + 1) : 0.f;
+  }
+
+  const long long nblk = (M + 15) / 16;
+  for (long long blk = (long long)blockIdx.x * 8 + warp; blk < nblk; blk += (long long)gridDim.x * 8) {
+    const long long m0 = blk * 16;
+    // two rows per thread: rr and rr + 8
+    int hb_[2], wb_[2];
+    long long base[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      long long m = m0 + rr + t * 8;
+      if (m >= M) m = M - 1;
+      const int wo = (int)(m % Wo);
+      const long long t2 = m / Wo;
+      const int ho = (int)(t2 % Ho);
+      const long long n = t2 / Ho;
+      hb_[t] = ho * STRIDE - 1;
+      wb_[t] = wo * STRIDE - 1;
+      base[t] = ((n * H + hb_[t]) * W + wb_[t]) * CS;
+    }
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const int t = r4 & 1;                    // a0/a2: row rr, a1/a3: row rr + 8
+        const int e0 = ks * 4 + (r4 >> 1) * 2;   // a0/a1: k pair 0, a2/a3: k pair +8
+        uint32_t bits[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = e0 + u;
+          const int hi = hb_[t] + kdr[e], wi = wb_[t] + kds[e];
+          const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+          bits[u] = ok ? load_bits(in + base[t] + kdelta[e]) : 0u;
+        }
+        a[ks][r4] = bits[0] | (bits[1] << 16);
+      }
+    float c[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) mma_bf16_16816(c[j], a[ks], breg[ks][j][0], breg[ks][j][1]);
+    }
+    // phase 1: bias + activation, stage as fp32
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float v0 = c[j][t * 2] + bcol[j][0], v1 = c[j][t * 2 + 1] + bcol[j][1];
+        if (act == ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * slope; v1 = v1 > 0.f ? v1 : v1 * slope; }
+        else if (act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        *reinterpret_cast<float2*>(&stage[warp][rr + t * 8][j * 8 + 2 * q]) = make_float2(v0, v1);
+      }
+    __syncwarp();
+    // phase 2: 16 bytes (8 channels) per lane
+#pragma unroll
+    for (int it = 0; it < 16 * CH / 32; ++it) {
+      const int id = it * 32 + lane;
+      const int row = id / CH, cc = id - row * CH;
+      const long long m = m0 + row;
+      const float4 f0 = *reinterpret_cast<const float4*>(&stage[warp][row][cc * 8]);
+      const float4 f1 = *reinterpret_cast<const float4*>(&stage[warp][row][cc * 8 + 4]);
+      float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+      if (m < M) {
+        if (act_ref != nullptr) {
+          const uint4 u = *reinterpret_cast<const uint4*>(act_ref + m * COUT + cc * 8);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(w4[e] << 16), hi = __uint_as_float(w4[e] & 0xffff0000u);
+            v[2 * e] *= lo > 0.f ? 1.f : ref_neg;
+            v[2 * e + 1] *= hi > 0.f ? 1.f : ref_neg;
+          }
+        }
+        uint4 o;
+        o.x = bf16_bits(v[0]) | (bf16_bits(v[1]) << 16);
+        o.y = bf16_bits(v[2]) | (bf16_bits(v[3]) << 16);
+        o.z = bf16_bits(v[4]) | (bf16_bits(v[5]) << 16);
+        o.w = bf16_bits(v[6]) | (bf16_bits(v[7]) << 16);
+        *reinterpret_cast<uint4*>(out + m * COUT + cc * 8) = o;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+bool conv_few_supported(int Cs, int Cout, int ksize, int stride, int pad) {
+  return Cs >= 1 && Cs <= 3 && (Cout == 32 || Cout == 64) && ksize == 3 && pad == 1 && (stride == 1 || stride == 2);
+}
+
+template <typename TIn, int CS, int COUT, int STRIDE>
+static void launch_few(const TIn* in, int N, int H, int W, const bf16* wnk, const FewEpilogue& e, bf16* out,
+                       cudaStream_t stream) {
+  const int Ho = (H + 2 - 3) / STRIDE + 1, Wo = (W + 2 - 3) / STRIDE + 1;
+  const long long M = (long long)N * Ho * Wo;
+  long long blocks = ((M + 15) / 16 + 7) / 8;
+  const long long cap = (long long)sm_count() * 6;
+  if (blocks > cap) blocks = cap;
+  const float ref_neg = e.ref_act == ACT_LRELU ? e.ref_slope : 0.f;
+  conv_few_kernel<TIn, CS, COUT, STRIDE><<<(int)blocks, 256, 0, stream>>>(
+      in, wnk, e.bias, e.act, e.slope, e.ref_act != ACT_NONE ? e.act_ref : nullptr, ref_neg, out, H, W, Ho, Wo, M);
+}
+
+template <typename TIn>
+void conv_few(const TIn* in, int N, int H, int W, int Cs, const bf16* wnk, int Cout, int stride, const FewEpilogue& epi,
+              bf16* out, cudaStream_t stream) {
+  PCG_PROFILE("conv_small", stream);
+  PCG_REQUIRE(conv_few_supported(Cs, Cout, 3, stride, 1), "conv_few: unsupported geometry");
+#define PCG_F(CS_, CO_, ST_) launch_few<TIn, CS_, CO_, ST_>(in, N, H, W, wnk, epi, out, stream)
+  const int key = Cs * 1000 + Cout * 10 + stride;
+  switch (key) {
+    case 1000 + 320 + 1: PCG_F(1, 32, 1); break;
+    case 1000 + 640 + 1: PCG_F(1, 64, 1); break;
+    case 2000 + 640 + 2: PCG_F(2, 64, 2); break;
+    case 3000 + 640 + 1: PCG_F(3, 64, 1); break;
+    default: throw Error(1, "conv_few: this (Cs, Cout, stride) combination is not instantiated");
+  }
+#undef PCG_F
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+template void conv_few<bf16>(const bf16*, int, int, int, int, const bf16*, int, int, const FewEpilogue&, bf16*, cudaStream_t);
+template void conv_few<float>(const float*, int, int, int, int, const bf16*, int, int, const FewEpilogue&, bf16*, cudaStream_t);
+
 }  // namespace pcg

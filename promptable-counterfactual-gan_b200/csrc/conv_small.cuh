@@ -16,4 +16,22 @@ bool conv_to1_supported(int H, int W, int Cin);
 void conv_to1(const bf16* in, int N, int H, int W, int Cin, const bf16* w9, const float* bias, float* out,
               cudaStream_t stream);
 
+// out[M][Cout] (bf16 NHWC) = epi( sum_{tap, c} in[n][ho*stride - 1 + r][wo*stride - 1 + s][c] * wnk[co][tap*Cs + c] )
+//   in  : NHWC with Cs = 1, 2 or 3 channels, bf16 or fp32;  wnk : bf16 [Cout][9*Cs];  Cout = 32 or 64; stride 1 or 2; pad 1
+//   epi : v = acc + bias ; v = act(v) ; v *= act'(act_ref) (LeakyReLU/ReLU derivative from the sign of act_ref[M][Cout])
+// Serves conv_in's and the discriminator's / classifier's first forward convolutions (wnk = the fprop packing) and
+// conv_out's data gradient (Cs = 1, wnk = the rotated dgrad packing [ci][8 - tap]).
+struct FewEpilogue {
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  float slope = 0.2f;
+  const bf16* act_ref = nullptr;
+  int ref_act = ACT_NONE;
+  float ref_slope = 0.2f;
+};
+bool conv_few_supported(int Cs, int Cout, int ksize, int stride, int pad);
+template <typename TIn>
+void conv_few(const TIn* in, int N, int H, int W, int Cs, const bf16* wnk, int Cout, int stride, const FewEpilogue& epi,
+              bf16* out, cudaStream_t stream);
+
 }  // namespace pcg

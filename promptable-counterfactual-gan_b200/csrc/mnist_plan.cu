@@ -138,6 +138,8 @@ struct ConvLayer {
   bool tc_wgrad_gen = false;  // general tensor-core wgrad (conv_tc.cu)
   bool to1_fprop = false;     // Cout == 1: conv_to1 on tcf (conv_small.cu)
   bool to1_dgrad = false;     // Cin <= 4: one input channel's data gradient = conv_to1 on a row of tcd
+  bool few_fprop = false;     // Cin <= 3: conv_few on tcf
+  bool few_dgrad = false;     // Cout <= 3: data gradient = conv_few on tcd
   int perm_hw = 0;
   std::string name, tag_f, tag_d, tag_w;
 
@@ -148,8 +150,8 @@ struct ConvLayer {
     PCG_REQUIRE(!(tcd || tcs2) || perm_hw == 0, "permuted tc dgrad packing unsupported");
     PackDesc d;
     d.w = w; d.Cout = g.Cout; d.Cin = g.Cin; d.taps = g.ksize * g.ksize; d.perm_hw = perm_hw; d.begin = 0;
-    d.wf = (tc_fprop || to1_fprop) ? nullptr : wf;
-    d.wd = (((tc_dgrad || tc_dgrad_s2) && !wd_generic_too) || to1_dgrad) ? nullptr : wd;
+    d.wf = (tc_fprop || to1_fprop || few_fprop) ? nullptr : wf;
+    d.wd = (((tc_dgrad || tc_dgrad_s2) && !wd_generic_too) || to1_dgrad || few_dgrad) ? nullptr : wd;
     d.tcf = tcf; d.tcd = tcd; d.tcs2 = tcs2;
     return d;
   }
@@ -272,6 +274,14 @@ struct MnistPlan : PlanBase {
         L.tcd = alloc<bf16>(n);
         L.to1_dgrad = true;
       }
+      if (Cout <= 3 && need_wd && conv_few_supported(Cout, Cin, k, 1, pad)) {
+        if (!L.tcd) L.tcd = alloc<bf16>(n);
+        L.few_dgrad = true;
+      }
+    }
+    if (kBf16 && cfg.use_tensor_cores && perm_hw == 0 && conv_few_supported(Cin, Cout, k, stride, pad)) {
+      if (!L.tcf) L.tcf = alloc<bf16>(n);
+      L.few_fprop = true;
     }
     if (kBf16 && cfg.use_tensor_cores && stride == 2 && k == 3 && pad == 1 && Cout % 64 == 0 && Cin % 32 == 0 &&
         need_wd && perm_hw == 0) {
@@ -403,6 +413,15 @@ struct MnistPlan : PlanBase {
         return;
       }
     }
+    if constexpr (kBf16 && std::is_same<TOut, bf16>::value) {
+      if (L.few_fprop && e.add_src == nullptr && stats == nullptr) {
+        FewEpilogue fe;
+        fe.bias = e.bias; fe.act = e.act; fe.slope = e.slope;
+        fe.act_ref = e.act_ref; fe.ref_act = e.ref_act; fe.ref_slope = e.ref_slope;
+        conv_few<TIn>(in, g.N, g.H, g.W, g.Cin, L.tcf, g.Cout, g.stride, fe, out, s);
+        return;
+      }
+    }
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, float>::value) {
       if (L.to1_fprop && e.act == ACT_NONE && e.add_src == nullptr && e.act_ref == nullptr && stats == nullptr) {
         conv_to1(in, g.N, g.H, g.W, g.Cin, L.tcf, e.bias, out, s);
@@ -426,6 +445,14 @@ struct MnistPlan : PlanBase {
           e.add_src == nullptr && e.act_ref == nullptr) {
         const int ci = ch_select >= 0 ? ch_select : 0;
         conv_to1(dout, g.N, g.H, g.W, g.Cout, L.tcd + (size_t)ci * 9 * g.Cout, nullptr, din, s);
+        return;
+      }
+    }
+    if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, bf16>::value) {
+      if (L.few_dgrad && ch_select < 0 && e.bias == nullptr && e.act == ACT_NONE && e.add_src == nullptr) {
+        FewEpilogue fe;
+        fe.act_ref = e.act_ref; fe.ref_act = e.ref_act; fe.ref_slope = e.ref_slope;
+        conv_few<bf16>(dout, g.N, g.H, g.W, g.Cout, L.tcd, g.Cin, 1, fe, din, s);
         return;
       }
     }

@@ -242,7 +242,8 @@ def test_tensor_core_path_matches_cuda_core_path_in_bf16():
         out.append((gD, gG, H.plan.debug_tensor("hm"), H.plan.debug_tensor("x_cf")))
     (gDa, gGa, hma, xa), (gDb, gGb, hmb, xb) = out
     worst = []
-    assert relerr(hma, hmb) < 8e-3 and relerr(xa, xb) < 1e-3
+    # x_cf: the tensor-core plan rounds conv_out's weights to bf16 (conv_small.cu), the CUDA-core plan keeps them fp32
+    assert relerr(hma, hmb) < 8e-3 and relerr(xa, xb) < 2e-3
     for k in gDa:
         worst.append((relerr(gDa[k], gDb[k]), "D/" + k))
     for k in gGa:
