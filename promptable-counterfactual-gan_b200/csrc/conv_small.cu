@@ -336,4 +336,350 @@ void conv_few(const TIn* in, int N, int H, int W, int Cs, const bf16* wnk, int C
 template void conv_few<bf16>(const bf16*, int, int, int, int, const bf16*, int, int, const FewEpilogue&, bf16*, cudaStream_t);
 template void conv_few<float>(const float*, int, int, int, int, const bf16*, int, int, const FewEpilogue&, bf16*, cudaStream_t);
 
+// ------------------------------------------------------------------------------------------
+// Weight gradients of the skinny layers.  Both kernels stream the 64-channel tensor ([M][64] bf16, M = pixels) through
+// a TMA ring of 192-row tiles; the 12 consumer warps each contract 16 pixels per tile on the warp-level tensor path
+// with fp32 accumulators that live in registers for the whole kernel, are summed in a fixed order inside the block
+// and written as one partial row per block; a small second kernel adds the rows (fixed order) and writes torch's
+// OIHW layout.
+// ------------------------------------------------------------------------------------------
+constexpr int WG_TILE = 192, WG_STAGES = 4, WG_CONSUMERS = 12, WG_THREADS = 32 * (WG_CONSUMERS + 1);
+constexpr int WG_SMEM = 1024 + WG_STAGES * WG_TILE * 128 + 64 + 32 * 64 * 4;
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t swz128(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
+
+struct WgRing {
+  uint8_t* tiles;
+  uint64_t *full, *empty;
+  float* red;
+};
+__device__ __forceinline__ WgRing wg_setup(uint8_t* smem_raw, const CUtensorMap* tm) {
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  WgRing r;
+  r.tiles = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  r.full = reinterpret_cast<uint64_t*>(r.tiles + WG_STAGES * WG_TILE * 128);
+  r.empty = r.full + WG_STAGES;
+  r.red = reinterpret_cast<float*>(r.empty + WG_STAGES);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(tm);
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&r.full[s], 1); mbar_init(&r.empty[s], WG_CONSUMERS); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  return r;
+}
+// producer warp: one 192-row box per tile (rows past M arrive as zeros)
+__device__ __forceinline__ void wg_produce(const WgRing& r, const CUtensorMap* tm, int ntiles) {
+  if ((threadIdx.x & 31) != 0) return;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(&r.empty[stage], phase ^ 1);
+    mbar_expect_tx(&r.full[stage], WG_TILE * 128);
+    tma_load_2d(tm, &r.full[stage], r.tiles + stage * WG_TILE * 128, 0, tile * WG_TILE);
+    if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
+__device__ __forceinline__ void decode_pixel(long long m, int Ho, int Wo, int& n, int& ho, int& wo) {
+  wo = (int)(m % Wo);
+  const long long t = m / Wo;
+  ho = (int)(t % Ho);
+  n = (int)(t / Ho);
+}
+
+template <typename TIn, int CS, int STRIDE>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_few_kernel(const __grid_constant__ CUtensorMap tmDY, const TIn* __restrict__ in, int H, int W, int Ho, int Wo,
+                 long long M, int ntiles, float* __restrict__ part) {
+  constexpr int K = 9 * CS;                       // rows 0..K-1 of D: (tap, c); row K: the bias gradient; K + 1 <= 32
+  extern __shared__ uint8_t smem_raw[];
+  const WgRing ring = wg_setup(smem_raw, &tmDY);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == WG_CONSUMERS) { wg_produce(ring, &tmDY, ntiles); return; }
+  const int q = lane & 3, rr = lane >> 2;
+
+  // this thread's four D rows: k = rr + 8*i  -> window offsets
+  int kdelta[4], kdr[4], kds[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = rr + 8 * i;
+    const int tap = k / CS, c = k - tap * CS;
+    kdr[i] = k < K ? tap / 3 : (k == K ? 100000 : -100000);   // +100000 marks the constant-1 column
+    kds[i] = tap % 3;
+    kdelta[i] = ((tap / 3) * W + (tap % 3)) * CS + c;
+  }
+  float acc[2][8][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[a][j][0] = acc[a][j][1] = acc[a][j][2] = acc[a][j][3] = 0.f;
+
+  int stage = 0;
+  uint32_t phase = 0;
+  const uint32_t one = 0x3f80u;                   // bf16 1.0
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long m0 = (long long)tile * WG_TILE + warp * 16;
+    // A^T fragments: element (k, m) for m = m0 + 2q + {0, 1, 8, 9}
+    uint32_t bits[4][4];                          // [k index i][pixel index u]
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long m = m0 + 2 * q + (u & 1) + (u >> 1) * 8;
+      const bool mok = m < M;
+      int n, ho, wo;
+      decode_pixel(mok ? m : 0, Ho, Wo, n, ho, wo);
+      const int hb = ho * STRIDE - 1, wb = wo * STRIDE - 1;
+      const long long base = (((long long)n * H + hb) * W + wb) * CS;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int hi = hb + kdr[i], wi = wb + kds[i];
+        const bool ok = mok && hi >= 0 && hi < H && wi >= 0 && wi < W;
+        uint32_t v = ok ? load_bits(in + base + kdelta[i]) : 0u;
+        if (kdr[i] == 100000 && mok) v = one;
+        bits[i][u] = v;
+      }
+    }
+    uint32_t a[2][4];
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      a[kb][0] = bits[2 * kb][0] | (bits[2 * kb][1] << 16);          // row k = kb*16 + rr,     m = 2q, 2q+1
+      a[kb][1] = bits[2 * kb + 1][0] | (bits[2 * kb + 1][1] << 16);  // row k = kb*16 + rr + 8
+      a[kb][2] = bits[2 * kb][2] | (bits[2 * kb][3] << 16);          // m = 2q+8, 2q+9
+      a[kb][3] = bits[2 * kb + 1][2] | (bits[2 * kb + 1][3] << 16);
+    }
+    mbar_wait(&ring.full[stage], phase);
+    const uint32_t tbase = smem_u32(ring.tiles + stage * WG_TILE * 128);
+    const int j8 = lane >> 3;                     // matrix index supplied by this lane
+    const uint32_t rowoff = (uint32_t)(warp * 16 + (j8 & 1) * 8 + (lane & 7)) * 128u;
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(tbase + swz128(rowoff + (uint32_t)(np * 2 + (j8 >> 1)) * 16u), b);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        mma_bf16_16816(acc[kb][2 * np], a[kb], b[0], b[1]);
+        mma_bf16_16816(acc[kb][2 * np + 1], a[kb], b[2], b[3]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[stage]);
+    if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+  }
+  // fixed-order sum of the 12 warps' fragments into red[32][64]
+  for (int w = 0; w < WG_CONSUMERS; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            float2* p = reinterpret_cast<float2*>(&ring.red[(kb * 16 + rr + t * 8) * 64 + j * 8 + 2 * q]);
+            float2 v = make_float2(acc[kb][j][2 * t], acc[kb][j][2 * t + 1]);
+            if (w > 0) { const float2 o = *p; v.x += o.x; v.y += o.y; }
+            *p = v;
+          }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(WG_CONSUMERS * 32) : "memory");
+  }
+  for (int i = threadIdx.x; i < 32 * 64; i += WG_CONSUMERS * 32) part[(size_t)blockIdx.x * 2048 + i] = ring.red[i];
+}
+
+// dw[co][c][tap] = sum_b part[b][(tap*Cs + c)*64 + co];  db[co] = sum_b part[b][K*64 + co]
+__global__ void wgrad_few_reduce_kernel(const float* __restrict__ part, int nparts, int Cs, float* __restrict__ dw,
+                                        float* __restrict__ db) {
+  const int K = 9 * Cs;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (K + 1) * 64) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 3 < nparts; b += 4) {
+    s0 += part[(size_t)b * 2048 + i];
+    s1 += part[(size_t)(b + 1) * 2048 + i];
+    s2 += part[(size_t)(b + 2) * 2048 + i];
+    s3 += part[(size_t)(b + 3) * 2048 + i];
+  }
+  for (; b < nparts; ++b) s0 += part[(size_t)b * 2048 + i];
+  const float s = (s0 + s1) + (s2 + s3);
+  const int k = i >> 6, co = i & 63;
+  if (k == K) {
+    if (db != nullptr) db[co] = s;
+  } else {
+    const int tap = k / Cs, c = k - tap * Cs;
+    dw[((size_t)co * Cs + c) * 9 + tap] = s;
+  }
+}
+
+int wgrad_few_parts() { return sm_count(); }
+bool wgrad_few_supported(int Cs, int Cout, int ksize, int stride, int pad) {
+  return Cs >= 1 && Cs <= 3 && Cout == 64 && ksize == 3 && pad == 1 && (stride == 1 || stride == 2);
+}
+
+template <typename TIn, int CS, int STRIDE>
+static void launch_wgrad_few(const TIn* in, const bf16* dy, int N, int H, int W, float* part, int grid, cudaStream_t stream) {
+  const int Ho = (H + 2 - 3) / STRIDE + 1, Wo = (W + 2 - 3) / STRIDE + 1;
+  const long long M = (long long)N * Ho * Wo;
+  const int ntiles = (int)((M + WG_TILE - 1) / WG_TILE);
+  CUtensorMap tm = make_tmap_2d(dy, (uint64_t)M, 64, WG_TILE);
+  static bool configured = false;
+  if (!configured) {
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_few_kernel<TIn, CS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    configured = true;
+  }
+  wgrad_few_kernel<TIn, CS, STRIDE><<<grid, WG_THREADS, WG_SMEM, stream>>>(tm, in, H, W, Ho, Wo, M, ntiles, part);
+}
+
+template <typename TIn>
+void wgrad_few(const TIn* in, const bf16* dy, int N, int H, int W, int Cs, int stride, float* part, float* dw, float* db,
+               cudaStream_t stream) {
+  PCG_PROFILE("wgrad_small", stream);
+  PCG_REQUIRE(wgrad_few_supported(Cs, 64, 3, stride, 1), "wgrad_few: unsupported geometry");
+  const int grid = wgrad_few_parts();
+  const int key = Cs * 10 + stride;
+  switch (key) {
+    case 31: launch_wgrad_few<TIn, 3, 1>(in, dy, N, H, W, part, grid, stream); break;
+    case 22: launch_wgrad_few<TIn, 2, 2>(in, dy, N, H, W, part, grid, stream); break;
+    default: throw Error(1, "wgrad_few: this (Cs, stride) combination is not instantiated");
+  }
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+  wgrad_few_reduce_kernel<<<cdiv((9 * Cs + 1) * 64, 128), 128, 0, stream>>>(part, grid, Cs, dw, db);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+template void wgrad_few<bf16>(const bf16*, const bf16*, int, int, int, int, int, float*, float*, float*, cudaStream_t);
+
+// ---- 64 -> 1: D[ci][tap] = sum_q x[q][ci] * G[q][tap],  G[q][tap = (r, s)] = g[n][h - (r-1)][w - (s-1)] (0 outside)
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict__ g, int H, int W, long long M,
+                 int ntiles, float* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  const WgRing ring = wg_setup(smem_raw, &tmX);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == WG_CONSUMERS) { wg_produce(ring, &tmX, ntiles); return; }
+  const int q = lane & 3, rr = lane >> 2;
+  // this thread's G columns: tap = rr (n-tile 0) and tap = 8 when rr == 0 (n-tile 1)
+  const int dr0 = rr / 3 - 1, ds0 = rr % 3 - 1;
+  float acc[4][2][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[a][j][0] = acc[a][j][1] = acc[a][j][2] = acc[a][j][3] = 0.f;
+  float gsum = 0.f;                               // lanes with rr == 4 (centre tap) see every g[q] exactly once
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long m0 = (long long)tile * WG_TILE + warp * 16;
+    uint32_t gb[2][4];                            // [n-tile][pixel u]
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long m = m0 + 2 * q + (u & 1) + (u >> 1) * 8;
+      const bool mok = m < M;
+      int n, h, w;
+      decode_pixel(mok ? m : 0, H, W, n, h, w);
+      {
+        const int hh = h - dr0, ww = w - ds0;
+        const bool ok = mok && hh >= 0 && hh < H && ww >= 0 && ww < W;
+        gb[0][u] = ok ? load_bits(g + ((long long)n * H + hh) * W + ww) : 0u;
+      }
+      {
+        const int hh = h - 1, ww = w - 1;         // tap 8 = (r, s) = (2, 2)
+        const bool ok = mok && rr == 0 && hh >= 0 && ww >= 0;
+        gb[1][u] = ok ? load_bits(g + ((long long)n * H + hh) * W + ww) : 0u;
+      }
+      if (rr == 4) gsum += __uint_as_float(gb[0][u] << 16);
+    }
+    uint32_t b[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      b[j][0] = gb[j][0] | (gb[j][1] << 16);
+      b[j][1] = gb[j][2] | (gb[j][3] << 16);
+    }
+    mbar_wait(&ring.full[stage], phase);
+    const uint32_t tbase = smem_u32(ring.tiles + stage * WG_TILE * 128);
+    const int j8 = lane >> 3;
+    // A = x^T: matrix j8 -> pixel rows (j8 >> 1)*8 + lane%8, channel chunk mt*2 + (j8 & 1)
+    const uint32_t rowoff = (uint32_t)(warp * 16 + (j8 >> 1) * 8 + (lane & 7)) * 128u;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      uint32_t a[4];
+      ldmatrix_x4_trans(tbase + swz128(rowoff + (uint32_t)(mt * 2 + (j8 & 1)) * 16u), a);
+      mma_bf16_16816(acc[mt][0], a, b[0][0], b[0][1]);
+      mma_bf16_16816(acc[mt][1], a, b[1][0], b[1][1]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[stage]);
+    if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+  }
+  // red[64 ci][16 taps] + red[1024 + warp*32 + lane] for the bias-gradient partials
+  for (int w = 0; w < WG_CONSUMERS; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            float2* p = reinterpret_cast<float2*>(&ring.red[(mt * 16 + rr + t * 8) * 16 + j * 8 + 2 * q]);
+            float2 v = make_float2(acc[mt][j][2 * t], acc[mt][j][2 * t + 1]);
+            if (w > 0) { const float2 o = *p; v.x += o.x; v.y += o.y; }
+            *p = v;
+          }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(WG_CONSUMERS * 32) : "memory");
+  }
+  ring.red[1024 + warp * 32 + lane] = gsum;
+  asm volatile("bar.sync 1, %0;" ::"n"(WG_CONSUMERS * 32) : "memory");
+  for (int i = threadIdx.x; i < 1024; i += WG_CONSUMERS * 32) part[(size_t)blockIdx.x * 1088 + i] = ring.red[i];
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < WG_CONSUMERS * 32; ++i) s += ring.red[1024 + i];
+    part[(size_t)blockIdx.x * 1088 + 1024] = s;
+  }
+}
+__global__ void wgrad_to1_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
+                                        float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > 1024) return;
+  float s0 = 0.f, s1 = 0.f;
+  int b = 0;
+  for (; b + 1 < nparts; b += 2) {
+    s0 += part[(size_t)b * 1088 + i];
+    s1 += part[(size_t)(b + 1) * 1088 + i];
+  }
+  if (b < nparts) s0 += part[(size_t)b * 1088 + i];
+  const float s = s0 + s1;
+  if (i == 1024) {
+    if (db != nullptr) db[0] = s;
+  } else {
+    const int ci = i >> 4, tap = i & 15;
+    if (tap < 9) dw[ci * 9 + tap] = s;
+  }
+}
+int wgrad_to1_parts() { return sm_count(); }
+void wgrad_to1(const bf16* x, const bf16* g, int N, int H, int W, float* part, float* dw, float* db, cudaStream_t stream) {
+  PCG_PROFILE("wgrad_small", stream);
+  const long long M = (long long)N * H * W;
+  const int ntiles = (int)((M + WG_TILE - 1) / WG_TILE);
+  CUtensorMap tm = make_tmap_2d(x, (uint64_t)M, 64, WG_TILE);
+  static bool configured = false;
+  if (!configured) {
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_to1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    configured = true;
+  }
+  const int grid = wgrad_to1_parts();
+  wgrad_to1_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(tm, g, H, W, M, ntiles, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+  wgrad_to1_reduce_kernel<<<cdiv(1025, 128), 128, 0, stream>>>(part, grid, dw, db);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 }  // namespace pcg

@@ -34,4 +34,20 @@ template <typename TIn>
 void conv_few(const TIn* in, int N, int H, int W, int Cs, const bf16* wnk, int Cout, int stride, const FewEpilogue& epi,
               bf16* out, cudaStream_t stream);
 
+// Weight gradient of a convolution with Cs = 1..3 input channels and 64 output channels (3x3, pad 1, stride 1|2):
+//   dw[co][c][r][s] (torch OIHW fp32) = sum_m dy[m][co] * in[n][ho*stride - 1 + r][wo*stride - 1 + s][c]
+//   db[co] = sum_m dy[m][co]           (only if db != nullptr; costs nothing: a constant-1 im2col column)
+// `part` must hold wgrad_few_parts() * 2048 floats.
+int wgrad_few_parts();
+bool wgrad_few_supported(int Cs, int Cout, int ksize, int stride, int pad);
+template <typename TIn>
+void wgrad_few(const TIn* in, const bf16* dy, int N, int H, int W, int Cs, int stride, float* part, float* dw, float* db,
+               cudaStream_t stream);
+
+// Weight gradient of a 64 -> 1 convolution (3x3, stride 1, pad 1):
+//   dw[0][ci][r][s] = sum_p g[p] * x[n][h + r - 1][w + s - 1][ci];   db[0] = sum_p g[p]
+//   x : NHWC bf16 [N*H*W][64];  g : bf16 [N*H*W].  `part` must hold wgrad_to1_parts() * 1088 floats.
+int wgrad_to1_parts();
+void wgrad_to1(const bf16* x, const bf16* g, int N, int H, int W, float* part, float* dw, float* db, cudaStream_t stream);
+
 }  // namespace pcg

@@ -140,6 +140,8 @@ struct ConvLayer {
   bool to1_dgrad = false;     // Cin <= 4: one input channel's data gradient = conv_to1 on a row of tcd
   bool few_fprop = false;     // Cin <= 3: conv_few on tcf
   bool few_dgrad = false;     // Cout <= 3: data gradient = conv_few on tcd
+  bool few_wgrad = false;     // Cin <= 3, Cout == 64: wgrad_few (also produces the bias gradient)
+  bool to1_wgrad = false;     // 64 -> 1: wgrad_to1 (also produces the bias gradient)
   int perm_hw = 0;
   std::string name, tag_f, tag_d, tag_w;
 
@@ -225,7 +227,7 @@ struct MnistPlan : PlanBase {
   float *clogits, *cdlogits, *dxc;
   T *cdf1, *cd3, *cd2, *cd1;
   // scratch
-  float *stat_part, *stat_part2, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp;
+  float *stat_part, *stat_part2, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp, *small_part;
   size_t wg_scratch_elems = 0;
 
   template <typename U>
@@ -278,6 +280,10 @@ struct MnistPlan : PlanBase {
         if (!L.tcd) L.tcd = alloc<bf16>(n);
         L.few_dgrad = true;
       }
+    }
+    if (kBf16 && cfg.use_tensor_cores && dw != nullptr) {
+      L.few_wgrad = wgrad_few_supported(Cin, Cout, k, stride, pad) && ((Cin == 3 && stride == 1) || (Cin == 2 && stride == 2));
+      L.to1_wgrad = Cin == 64 && Cout == 1 && k == 3 && stride == 1 && pad == 1;
     }
     if (kBf16 && cfg.use_tensor_cores && perm_hw == 0 && conv_few_supported(Cin, Cout, k, stride, pad)) {
       if (!L.tcf) L.tcf = alloc<bf16>(n);
@@ -385,6 +391,7 @@ struct MnistPlan : PlanBase {
     wg_scratch = alloc<float>(wg_scratch_elems);
     tc_part = kBf16 ? alloc<float>((size_t)148 * 9 * 64 * 64) : nullptr;
     l1_part = alloc<float>(STAT_PARTS * 2);
+    small_part = alloc<float>((size_t)sm_count() * 2048);
     scal_tmp = alloc<float>(16);
     dbg["dinp"] = {dinp, {MG * 3, PCG_F32}};
     build_pack_tables();
@@ -482,6 +489,14 @@ struct MnistPlan : PlanBase {
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TDy, bf16>::value) {
+      if (L.few_wgrad) {
+        wgrad_few<bf16>(in, dout, g.N, g.H, g.W, g.Cin, g.stride, small_part, L.dw, L.db, s);
+        return;
+      }
+      if (L.to1_wgrad) {
+        wgrad_to1(in, dout, g.N, g.H, g.W, small_part, L.dw, L.db, s);
+        return;
+      }
       if (L.tc_wgrad && L.tc64) {
         conv_tc64_wgrad(in, dout, g.N, g.H, g.W, tc_part, s);
         wgrad_reduce_tc(tc_part, conv_tc64_grid(g.N, g.H, g.W), L.dw, s);
@@ -661,7 +676,7 @@ struct MnistPlan : PlanBase {
                          g_c, s);
     // --- generator backward
     wgrad<T, T>(g_out, hm, g_c, s);
-    bias_grad(g_c, MG, 1, g_out.db, s);
+    if (!g_out.to1_wgrad) bias_grad(g_c, MG, 1, g_out.db, s);
     T* g_hm = dz1;
     {
       GenEpilogue<T> e; e.act_ref = hm; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f;
@@ -710,7 +725,7 @@ struct MnistPlan : PlanBase {
     }
     // dh now holds d loss / d (pre-activation of conv_in)
     wgrad<T, T>(g_in, inp3, dh, s);
-    bias_grad(dh, MG, ch, g_in.db, s);
+    if (!g_in.few_wgrad) bias_grad(dh, MG, ch, g_in.db, s);
     {
       GenEpilogue<float> e;
       dgrad<T, float>(g_in, dh, e, dinp, s, 0, /*ch_select=*/1);    // only the label-embedding channel
