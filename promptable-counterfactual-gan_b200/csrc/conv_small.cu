@@ -682,4 +682,128 @@ void wgrad_to1(const bf16* x, const bf16* g, int N, int H, int W, float* part, f
   PCG_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------
+// Stride-2 data gradient towards one input channel (discriminator conv0 -> the image / the label map).
+// ------------------------------------------------------------------------------------------
+constexpr int S2_ROWS = 208, S2_STAGES = 3, S2_THREADS = 288;
+constexpr int S2_SMEM = 1024 + S2_STAGES * S2_ROWS * 128 + 64 + S2_ROWS * 9 * 4;
+
+__global__ void __launch_bounds__(S2_THREADS, 2)
+dgrad_s2_to1_kernel(const __grid_constant__ CUtensorMap tmDY, const bf16* __restrict__ wrot, float* __restrict__ dx,
+                    int N, int H, int W, int Ho, int Wo) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S2_STAGES * S2_ROWS * 128);
+  uint64_t* empty = full + S2_STAGES;
+  float* P = reinterpret_cast<float*>(empty + S2_STAGES + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npos = Ho * Wo;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < S2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < S2_STAGES * S2_ROWS * 128 / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int img = blockIdx.x; img < N; img += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], npos * 128);
+        tma_load_2d(&tmDY, &full[stage], smem + stage * S2_ROWS * 128, 0, img * npos);
+        if (++stage == S2_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+  const int q = lane & 3, rr = lane >> 2;
+  // B[k = co][n = tap] = wrot[8 - tap][co]
+  uint32_t breg[4][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const int co = ks * 16 + 2 * q + hb * 8;
+      breg[ks][0][hb] = *reinterpret_cast<const uint32_t*>(wrot + (8 - rr) * 64 + co);
+      breg[ks][1][hb] = rr == 0 ? *reinterpret_cast<const uint32_t*>(wrot + co) : 0u;     // tap 8 -> row 0
+    }
+  const int nblk = (npos + 15) / 16;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int img = blockIdx.x; img < N; img += gridDim.x) {
+    mbar_wait(&full[stage], phase);
+    const uint32_t base = smem_u32(smem + stage * S2_ROWS * 128);
+    for (int blk = warp; blk < nblk; blk += 8) {
+      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const uint32_t rowoff = (uint32_t)(blk * 16 + (lane & 15)) * 128u;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4(base + swz128(rowoff + (uint32_t)(ks * 2 + (lane >> 4)) * 16u), a);
+        mma_bf16_16816(c[0], a, breg[ks][0][0], breg[ks][0][1]);
+        mma_bf16_16816(c[1], a, breg[ks][1][0], breg[ks][1][1]);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float* row = P + (blk * 16 + rr + t * 8) * 9;
+        row[2 * q] = c[0][2 * t];
+        row[2 * q + 1] = c[0][2 * t + 1];
+        if (q == 0) row[8] = c[1][2 * t];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* o = dx + (size_t)img * H * W;
+    for (int i = threadIdx.x; i < H * W; i += 256) {
+      const int hi = i / W, wi = i - hi * W;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int th = hi + 1 - r;
+        if (th < 0 || (th & 1)) continue;
+        const int ho = th >> 1;
+        if (ho >= Ho) continue;
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+          const int tw = wi + 1 - sx;
+          if (tw < 0 || (tw & 1)) continue;
+          const int wo = tw >> 1;
+          if (wo >= Wo) continue;
+          s += P[(ho * Wo + wo) * 9 + r * 3 + sx];
+        }
+      }
+      o[i] = s;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (++stage == S2_STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
+bool dgrad_s2_to1_supported(int H, int W, int Cout) {
+  return Cout == 64 && H % 2 == 0 && W % 2 == 0 && (H / 2) * (W / 2) <= 196 && (H / 2) * (W / 2) >= 1;
+}
+void dgrad_s2_to1(const bf16* dy, int N, int H, int W, const bf16* wrot, float* dx, cudaStream_t stream) {
+  PCG_PROFILE("conv_small", stream);
+  PCG_REQUIRE(dgrad_s2_to1_supported(H, W, 64), "dgrad_s2_to1: unsupported geometry");
+  const int Ho = H / 2, Wo = W / 2;
+  CUtensorMap tm = make_tmap_2d(dy, (uint64_t)N * Ho * Wo, 64, Ho * Wo);
+  static bool configured = false;
+  if (!configured) {
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(dgrad_s2_to1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+    configured = true;
+  }
+  int grid = 2 * sm_count();
+  if (grid > N) grid = N;
+  dgrad_s2_to1_kernel<<<grid, S2_THREADS, S2_SMEM, stream>>>(tm, wrot, dx, N, H, W, Ho, Wo);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 }  // namespace pcg

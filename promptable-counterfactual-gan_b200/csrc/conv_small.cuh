@@ -50,4 +50,12 @@ void wgrad_few(const TIn* in, const bf16* dy, int N, int H, int W, int Cs, int s
 int wgrad_to1_parts();
 void wgrad_to1(const bf16* x, const bf16* g, int N, int H, int W, float* part, float* dw, float* db, cudaStream_t stream);
 
+// One input channel of the data gradient of a 64-output-channel 3x3 / stride-2 / pad-1 convolution:
+//   dx[n][hi][wi] (fp32) = sum_{r,s,co : hi+1-r, wi+1-s even} dy[n][(hi+1-r)/2][(wi+1-s)/2][co] * wrot[8 - (r*3+s)][co]
+//   dy : NHWC bf16 [N][Ho][Wo][64] with Ho = H/2, Wo = W/2 (H, W even, Ho*Wo <= 208);  wrot : bf16 [9][64], that input
+//   channel's row of the rotated dgrad packing ([ci][8 - tap][co]).
+// Per image: P[pos][tap] = dy[pos][:] . w[:][tap] on the tensor path, then a col2im gather of <= 4 taps per pixel.
+bool dgrad_s2_to1_supported(int H, int W, int Cout);
+void dgrad_s2_to1(const bf16* dy, int N, int H, int W, const bf16* wrot, float* dx, cudaStream_t stream);
+
 }  // namespace pcg

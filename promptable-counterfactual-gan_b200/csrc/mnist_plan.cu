@@ -140,6 +140,7 @@ struct ConvLayer {
   bool to1_dgrad = false;     // Cin <= 4: one input channel's data gradient = conv_to1 on a row of tcd
   bool few_fprop = false;     // Cin <= 3: conv_few on tcf
   bool few_dgrad = false;     // Cout <= 3: data gradient = conv_few on tcd
+  bool s2_to1_dgrad = false;  // Cin <= 4, stride 2: one input channel's data gradient = dgrad_s2_to1 on a row of tcd
   bool few_wgrad = false;     // Cin <= 3, Cout == 64: wgrad_few (also produces the bias gradient)
   bool to1_wgrad = false;     // 64 -> 1: wgrad_to1 (also produces the bias gradient)
   int perm_hw = 0;
@@ -149,11 +150,11 @@ struct ConvLayer {
   // image of wf (same [Cout][taps][Cin] order, incl. the NHWC-flatten permutation of fc.1); the dgrad packing
   // additionally rotates the taps.  `wd_generic_too`: a channel-select data gradient runs on the CUDA cores.
   PackDesc desc(bool wd_generic_too) const {
-    PCG_REQUIRE(!(tcd || tcs2) || perm_hw == 0, "permuted tc dgrad packing unsupported");
+    PCG_REQUIRE(!tcs2 || perm_hw == 0, "permuted stride-2 dgrad packing unsupported");
     PackDesc d;
     d.w = w; d.Cout = g.Cout; d.Cin = g.Cin; d.taps = g.ksize * g.ksize; d.perm_hw = perm_hw; d.begin = 0;
     d.wf = (tc_fprop || to1_fprop || few_fprop) ? nullptr : wf;
-    d.wd = (((tc_dgrad || tc_dgrad_s2) && !wd_generic_too) || to1_dgrad || few_dgrad) ? nullptr : wd;
+    d.wd = (((tc_dgrad || tc_dgrad_s2) && !wd_generic_too) || to1_dgrad || few_dgrad || s2_to1_dgrad) ? nullptr : wd;
     d.tcf = tcf; d.tcd = tcd; d.tcs2 = tcs2;
     return d;
   }
@@ -255,7 +256,9 @@ struct MnistPlan : PlanBase {
     if (kBf16 && cfg.use_tensor_cores && Cin % 64 == 0 && Cout % 64 == 0) {
       L.tcf = alloc<bf16>(n);
       L.tc_fprop = true;
-      if (stride == 1 && k == 3 && pad == 1 && need_wd && perm_hw == 0) {
+      // stride-1 data gradient = the same implicit GEMM on dY with transposed (and, for 3x3, rotated) weights;
+      // a Linear (k = 1) may carry the NHWC-flatten permutation, which the packing applies to the Cin index
+      if (stride == 1 && need_wd && ((k == 3 && pad == 1 && perm_hw == 0) || (k == 1 && pad == 0))) {
         L.tcd = alloc<bf16>(n);
         L.tc_dgrad = true;
       }
@@ -280,6 +283,11 @@ struct MnistPlan : PlanBase {
         if (!L.tcd) L.tcd = alloc<bf16>(n);
         L.few_dgrad = true;
       }
+    }
+    if (kBf16 && cfg.use_tensor_cores && k == 3 && stride == 2 && pad == 1 && Cin <= 4 && need_wd && perm_hw == 0 &&
+        dgrad_s2_to1_supported(H, W, Cout)) {
+      if (!L.tcd) L.tcd = alloc<bf16>(n);
+      L.s2_to1_dgrad = true;
     }
     if (kBf16 && cfg.use_tensor_cores && dw != nullptr) {
       L.few_wgrad = wgrad_few_supported(Cin, Cout, k, stride, pad) && ((Cin == 3 && stride == 1) || (Cin == 2 && stride == 2));
@@ -448,6 +456,12 @@ struct MnistPlan : PlanBase {
     ConvGeom g = L.g;
     if (n_override) g.N = n_override;
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, float>::value) {
+      if (L.s2_to1_dgrad && (ch_select >= 0 || g.Cin == 1) && e.bias == nullptr && e.act == ACT_NONE &&
+          e.add_src == nullptr && e.act_ref == nullptr) {
+        const int ci = ch_select >= 0 ? ch_select : 0;
+        dgrad_s2_to1(dout, g.N, g.H, g.W, L.tcd + (size_t)ci * 9 * g.Cout, din, s);
+        return;
+      }
       if (L.to1_dgrad && (ch_select >= 0 || g.Cin == 1) && e.bias == nullptr && e.act == ACT_NONE &&
           e.add_src == nullptr && e.act_ref == nullptr) {
         const int ci = ch_select >= 0 ? ch_select : 0;
