@@ -22,21 +22,26 @@ void conv_tc64_set_variant(int v) { g_variant = v; }
 
 constexpr int C64 = 64;
 constexpr int W_BYTES = 9 * 64 * 128;            // resident weights: 9 taps x [64 rows][64 k] bf16
-constexpr int IN_STAGE_BYTES = 24576;            // >= (127 + 2*(W+2) + 2 + 1) * 128 for W <= 28
-constexpr int F_STAGES = 4;
-constexpr int F_THREADS = 320;                   // warp0 TMA, warp1 MMA, warps 2-9 epilogue
-constexpr int F_SMEM_BYTES = 1024 + W_BYTES + F_STAGES * IN_STAGE_BYTES + 8 * 2 * 64 * 4 + 256;
+constexpr int IN_STAGE_BYTES = 24576;            // wgrad: >= (127 + 2*(W+2) + 2 + 1) * 128 for W <= 28
+constexpr int F_EPI_WARPS = 16;                  // 4 TMEM lane quarters x 4 column quarters (16 columns per thread)
+constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
+constexpr int F_EPI_WARP0 = 3;                  // warp0 TMA (input), warps 1-2 MMA (even / odd tiles), warps 3-18 epilogue,
+constexpr int F_THREADS = 32 * (F_EPI_WARP0 + F_EPI_WARPS + 1);   // warp19 TMA (epilogue operand)
+constexpr int F_TAIL_BYTES = (16 * 2 * 16 + 64) * 4 + 256;   // statistics scratch + bias, mbarriers + TMEM pointer
+constexpr int SMEM_LIMIT = 232448;               // 227 KB opt-in maximum per CTA
 
 struct F64Params {
   int N, H, W, WP, R, tiles_per_img, total_tiles;
+  int in_stages, in_stage_bytes, out_tile_bytes; // shared-memory ring geometry (host-computed)
+  int n_extra;                                   // 1: one epilogue operand tile per output tile arrives by TMA
+  int extra_is_add;                              // that operand is add_src (else act_ref)
   const float* bias;
   int act;
   float slope;
-  const bf16* add_src;
+  const bf16* add_src;                           // read from global only when it is not the TMA operand
   const bf16* act_ref;
   int ref_act;
   float ref_slope;
-  bf16* out;
   float* stats;
   int variant;
 };
@@ -73,37 +78,77 @@ __device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// 16-column variant: lanes l and l ^ 16 end up holding column (l & 15) summed over the warp's 32 rows
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+  for (int off = 8, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < cnt / 2; ++j) {
+      const float send = upper ? v[j] : v[j + cnt / 2];
+      const float keep = upper ? v[j + cnt / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 __device__ __forceinline__ uint64_t a_desc(uint32_t addr, uint32_t lbo, int variant) {
   // variant 0: swizzle phase taken from the absolute shared-memory address (base_offset = 0)
   // variant 1: base_offset = (address >> 7) & 7, for starts that are not 1024-byte aligned
   return umma_smem_desc(addr, lbo, 1024, variant == 1 ? ((addr >> 7) & 7u) : 0u);
 }
 
+// Epilogue I/O goes through shared memory: a thread owns one accumulator row (= one pixel), so direct global
+// accesses would touch 32 different 128-byte lines per warp instruction (32 LSU transactions each, ~1000 cycles per
+// tile and per tensor - more than the tile's MMAs).  Instead the output tile is written to a 128B-swizzled staging
+// buffer (conflict-free) and leaves by one TMA store; the residual / activation-reference tile of the same pixels
+// arrives by TMA into a two-slot ring.
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
                        const F64Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sw = smem;                                   // weights
   uint8_t* sin = smem + W_BYTES;                        // input halo tiles
-  float* stats_smem = reinterpret_cast<float*>(sin + F_STAGES * IN_STAGE_BYTES);   // [8 warps][2][32]... see below
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + 8 * 2 * 64 * 4);
-  uint64_t* full = bars;                 // [F_STAGES]
-  uint64_t* empty = bars + F_STAGES;     // [F_STAGES]
-  uint64_t* wfull = bars + 2 * F_STAGES; // [1]
+  uint8_t* sout = sin + p.in_stages * p.in_stage_bytes; // output staging, 2 slots
+  uint8_t* sx = sout + 2 * p.out_tile_bytes;            // epilogue operand ring, 2 slots (if n_extra)
+  float* stats_smem = reinterpret_cast<float*>(sx + (p.n_extra ? 2 : 0) * p.out_tile_bytes);   // [16][2][16] + bias[64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + (16 * 2 * 16 + 64) * 4);
+  uint64_t* full = bars;                 // [4]
+  uint64_t* empty = bars + 4;            // [4]
+  uint64_t* wfull = bars + 8;            // [1]
   uint64_t* tfull = wfull + 1;           // [2]
   uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* xfull = tempty + 2;          // [2]
+  uint64_t* xempty = xfull + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    for (int s = 0; s < F_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    tma_prefetch_desc(&tmOut);
+    if (p.n_extra) tma_prefetch_desc(&tmExtra);
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(wfull, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1); mbar_init(&tempty[s], F_EPI_THREADS);
+      mbar_init(&xfull[s], 1); mbar_init(&xempty[s], F_EPI_THREADS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -111,14 +156,17 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     tmem_relinquish();
   }
   // rows of a halo tile beyond the TMA box are read by the (discarded) padding rows of the MMA: keep them finite
-  for (int i = threadIdx.x; i < F_STAGES * IN_STAGE_BYTES / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(sin)[i] = make_uint4(0, 0, 0, 0);
+  {
+    const int zbytes = (int)(reinterpret_cast<uint8_t*>(stats_smem) - sin);
+    for (int i = threadIdx.x; i < zbytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sin)[i] = make_uint4(0, 0, 0, 0);
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int box_bytes = (p.R + 2) * p.WP * 128;
+  const int tile_bytes = p.R * p.W * 128;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -129,170 +177,246 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.R;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], box_bytes);
-        tma_load_4d(&tmX, &full[stage], sin + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n);
-        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        if (p.variant & 16) {                      // experiment: no input traffic
+          mbar_arrive(&full[stage]);
+        } else {
+          mbar_expect_tx(&full[stage], box_bytes);
+          tma_load_4d(&tmX, &full[stage], sin + stage * p.in_stage_bytes, 0, -1, h0 - 1, n);
+        }
+        if (++stage == p.in_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == F_EPI_WARP0 + F_EPI_WARPS) {
+    if (lane == 0 && p.n_extra) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.R;
+        const int slot = it & 1;
+        mbar_wait(&xempty[slot], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&xfull[slot], tile_bytes);
+        tma_load_4d(&tmExtra, &xfull[slot], sx + slot * p.out_tile_bytes, 0, 0, h0, n);
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
     {
-      // the whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
-      // one elected lane issues the MMAs and commits
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      // Two MMA warps: issuing one M128xN64xK16 tcgen05.mma costs the issuing warp ~70 cycles (descriptor moves into
+      // uniform registers) while the tensor core needs ~48, so warp 1 issues the even tiles of this CTA into
+      // accumulator 0 and warp 2 the odd tiles into accumulator 1; the two instruction streams are independent.
+      // The whole warp walks the loop (warp-uniform control flow), one elected lane issues and commits.
+      const int mw = warp - 1;
+      const int nsel = (p.variant >> 6) & 3;       // experiment: MMA N = 64 / 16 / 32 / 128
+      const uint32_t idesc = nsel == 1 ? umma_idesc_bf16(128, 16, 0, 0) : nsel == 2 ? umma_idesc_bf16(128, 32, 0, 0)
+                             : nsel == 3 ? umma_idesc_bf16(128, 128, 0, 0) : umma_idesc_bf16(128, 64, 0, 0);
       mbar_wait(wfull, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
       const uint64_t b0 = umma_smem_desc(smem_u32(sw), 16, 1024);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+      const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
+      const uint32_t d_tmem = tmem_base + mw * 64;
+      const int ntap = (p.variant & 4) ? 1 : 9;    // experiment: one tap only
+      int it = mw;                                 // CTA-local tile counter
+      for (int tile = blockIdx.x + mw * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+        const int stage = it % p.in_stages;
+        const uint32_t phase = (uint32_t)(it / p.in_stages) & 1u, acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tempty[mw], acc_phase ^ 1);
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 64;
-        // descriptors: constant upper bits, only the start-address field moves (3 instructions per MMA)
-        const uint64_t a0 = a_desc(smem_u32(sin + stage * IN_STAGE_BYTES), 16, p.variant);
+        const uint64_t a0 = a_desc(smem_u32(sin + stage * p.in_stage_bytes), 16, p.variant & 1);
+        const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
         if (elect_one()) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t at = a0 + (uint64_t)(((tap / 3) * p.WP + (tap % 3)) * 8);     // (r*WP+s)*128 B >> 4
-            const uint64_t bt = b0 + (uint64_t)(tap * 512);                               // tap*8192 B >> 4
+            if (tap >= ntap) break;
+            const uint32_t at = a_lo + (uint32_t)(((tap / 3) * p.WP + (tap % 3)) * 8);     // (r*WP+s)*128 B >> 4
+            const uint32_t bt = b_lo + (uint32_t)(tap * 512);                               // tap*8192 B >> 4
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, at + 2 * k, bt + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_f16_lohi(d_tmem, at + 2 * k, a_hi, bt + 2 * k, b_hi, idesc, (tap | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          umma_commit(&tfull[acc]);
+          umma_commit(&tfull[mw]);
         }
         __syncwarp();
-        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
-    // ---- epilogue: 8 warps; warp e -> TMEM lane quarter (warp & 3), column half (e >> 2)
-    const int e = warp - 2;
-    const int q = warp & 3, half = e >> 2;
+    // ---- epilogue: 16 warps; warp e -> TMEM lane quarter (warp & 3), column quarter (e >> 2); four warps per
+    // scheduler hide the TMEM-load / shared-memory latencies, so an epilogue pass costs less than the tile's MMAs
+    const int e = warp - F_EPI_WARP0;
+    const int q = warp & 3, cq = e >> 2;
     const int row = q * 32 + lane;                  // accumulator row = padded position hh*WP + ww
     const int hh = row / p.WP, ww = row - hh * p.WP;
     const bool row_ok = hh < p.R && ww < p.W;
-    const int col0 = half * 32;
-    // bias lives in shared memory (read as 8 broadcast float4 per tile) to keep registers for the statistics
-    float* bias_s = stats_smem + 8 * 2 * 32;        // [64], behind the [8][2][32] statistics block
+    const int col0 = cq * 16;
+    const int drow = hh * p.W + ww;                 // row of the dense [R*W][64] staging / operand tiles
+    uint32_t soff[2];                               // 128B-swizzled byte offsets of this thread's two 16-byte chunks
+#pragma unroll
+    for (int j2 = 0; j2 < 2; ++j2) soff[j2] = (uint32_t)drow * 128u + ((uint32_t)((cq * 2 + j2) ^ (drow & 7)) << 4);
+    const bool issuer = threadIdx.x == F_EPI_WARP0 * 32;
+    // bias lives in shared memory (read as broadcast float4) to keep registers for the statistics
+    float* bias_s = stats_smem + 16 * 2 * 16;       // [64], behind the [16][2][16] statistics block
     if (e == 0) {
       bias_s[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
       bias_s[lane + 32] = p.bias ? __ldg(p.bias + lane + 32) : 0.f;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    // BatchNorm statistics: per-thread running sums of the raw accumulators over all tiles of this CTA (64 FP ops
-    // per tile); the bias is folded in analytically and the cross-row reduction runs once, after the last tile.
-    float acc_s[32], acc_q[32];
+    asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+    // BatchNorm statistics: per-thread running sums of the raw accumulators over all tiles of this CTA; the bias is
+    // folded in analytically and the cross-row reduction runs once, after the last tile.
+    float acc_s[16], acc_q[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc_s[j] = acc_q[j] = 0.f;
+    for (int j = 0; j < 16; ++j) acc_s[j] = acc_q[j] = 0.f;
     int nvalid = 0;
     const bool want_stats = p.stats != nullptr;
-    int acc = 0;
+    const bf16* g_add = (p.n_extra && p.extra_is_add) ? nullptr : p.add_src;    // operands still read from global
+    const bf16* g_ref = (p.n_extra && !p.extra_is_add) ? nullptr : p.act_ref;
+    const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
+    int acc = 0, it = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.R;
+    int n = blockIdx.x / p.tiles_per_img, tin = blockIdx.x % p.tiles_per_img;   // tile -> (image, row block), advanced incrementally
+    const int dn = gridDim.x / p.tiles_per_img, dt = gridDim.x % p.tiles_per_img;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int h0 = tin * p.R;
+      const int slot = it & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * 64 + col0, r);
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + (uint32_t(q * 32) << 16) + acc * 64 + col0, r);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&tempty[acc]);                    // accumulator is in registers: release TMEM early
+      if (p.variant & 2) {                          // experiment: no epilogue work
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       const bool valid = row_ok && (h0 + hh) < p.H;
-      const long long pix = ((long long)n * p.H + h0 + hh) * p.W + ww;
+      float v[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + j4 * 4);
+        v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
+        v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+        v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
+        v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+      }
+      if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+      } else if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.n_extra) {
+        mbar_wait(&xfull[slot], (it >> 1) & 1);
+        if (valid) {
+          const uint8_t* xt = sx + slot * p.out_tile_bytes;
+#pragma unroll
+          for (int j2 = 0; j2 < 2; ++j2) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xt + soff[j2]);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float lo = __uint_as_float(w4[t] << 16), hi = __uint_as_float(w4[t] & 0xffff0000u);
+              if (p.extra_is_add) {
+                v[j2 * 8 + t * 2] += lo;
+                v[j2 * 8 + t * 2 + 1] += hi;
+              } else {
+                v[j2 * 8 + t * 2] *= (lo > 0.f ? 1.f : neg);
+                v[j2 * 8 + t * 2 + 1] *= (hi > 0.f ? 1.f : neg);
+              }
+            }
+          }
+        }
+        mbar_arrive(&xempty[slot]);
+      }
+      if (valid && (g_add != nullptr || g_ref != nullptr)) {
+        const long long pix = ((long long)n * p.H + h0 + hh) * p.W + ww;
+        if (g_add != nullptr) {
+          const uint4* src = reinterpret_cast<const uint4*>(g_add + pix * C64 + col0);
+#pragma unroll
+          for (int j2 = 0; j2 < 2; ++j2) {
+            const uint4 u = __ldg(src + j2);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(h2[t]);
+              v[j2 * 8 + t * 2] += f.x;
+              v[j2 * 8 + t * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (g_ref != nullptr) {
+          const uint4* src = reinterpret_cast<const uint4*>(g_ref + pix * C64 + col0);
+#pragma unroll
+          for (int j2 = 0; j2 < 2; ++j2) {
+            const uint4 u = __ldg(src + j2);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(h2[t]);
+              v[j2 * 8 + t * 2] *= (f.x > 0.f ? 1.f : neg);
+              v[j2 * 8 + t * 2 + 1] *= (f.y > 0.f ? 1.f : neg);
+            }
+          }
+        }
+      }
+      // staging slot `slot` was last read by the TMA store issued two tiles ago
+      if (issuer) tma_store_wait_read<1>();
+      asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
       if (valid) {
-        float v[32];
+        uint8_t* st = sout + slot * p.out_tile_bytes;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + j4 * 4);
-          v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
-          v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
-          v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
-          v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
-        }
-        if (p.act == ACT_LRELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-        } else if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.add_src != nullptr) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.add_src + pix * C64 + col0);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 u = __ldg(src + j4);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = __bfloat1622float2(h2[t]);
-              v[j4 * 8 + t * 2] += f.x;
-              v[j4 * 8 + t * 2 + 1] += f.y;
-            }
-          }
-        }
-        if (p.act_ref != nullptr) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.act_ref + pix * C64 + col0);
-          const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 u = __ldg(src + j4);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = __bfloat1622float2(h2[t]);
-              v[j4 * 8 + t * 2] *= (f.x > 0.f ? 1.f : neg);
-              v[j4 * 8 + t * 2 + 1] *= (f.y > 0.f ? 1.f : neg);
-            }
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * C64 + col0);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
+        for (int j2 = 0; j2 < 2; ++j2) {
           uint4 u;
-          u.x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1]);
-          u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3]);
-          u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5]);
-          u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7]);
-          dst[j4] = u;
+          u.x = pack2(v[j2 * 8 + 0], v[j2 * 8 + 1]);
+          u.y = pack2(v[j2 * 8 + 2], v[j2 * 8 + 3]);
+          u.z = pack2(v[j2 * 8 + 4], v[j2 * 8 + 5]);
+          u.w = pack2(v[j2 * 8 + 6], v[j2 * 8 + 7]);
+          *reinterpret_cast<uint4*>(st + soff[j2]) = u;
         }
         if (want_stats) {           // statistics are only requested with act == NONE and no add/act_ref
           ++nvalid;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const float a = __uint_as_float(r[j]);
             acc_s[j] += a;
             acc_q[j] = fmaf(a, a, acc_q[j]);
           }
         }
       }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+      if (issuer) {
+        tma_store_4d(&tmOut, sout + slot * p.out_tile_bytes, 0, 0, h0, n);
+        tma_store_commit();
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      n += dn; tin += dt;
+      if (tin >= p.tiles_per_img) { tin -= p.tiles_per_img; ++n; }
     }
+    if (issuer) tma_store_wait<0>();
     if (want_stats) {
       // sum(a+b) = sum a + n b ; sum (a+b)^2 = sum a^2 + 2 b sum a + n b^2
       const float nv = (float)nvalid;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < 16; ++j) {
         const float b = bias_s[col0 + j], sa = acc_s[j];
         acc_q[j] = acc_q[j] + 2.f * b * sa + nv * b * b;
         acc_s[j] = sa + nv * b;
       }
-      const float ts = colsum32(acc_s, lane);      // lane l now holds column col0 + l over this warp's 32 rows
-      const float tq = colsum32(acc_q, lane);
-      // stats_smem[e][2][32]: per epilogue warp (sum, sumsq) of its 32 columns; fixed-order add over the 4 quarters
-      stats_smem[(e * 2 + 0) * 32 + lane] = ts;
-      stats_smem[(e * 2 + 1) * 32 + lane] = tq;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int t = threadIdx.x - 64;              // 0..255
+      const float ts = colsum16(acc_s, lane);      // lanes l, l^16 hold column col0 + (l & 15) over this warp's 32 rows
+      const float tq = colsum16(acc_q, lane);
+      // stats_smem[e][2][16]: per epilogue warp (sum, sumsq) of its 16 columns; fixed-order add over the 4 lane quarters
+      if (lane < 16) {
+        stats_smem[(e * 2 + 0) * 16 + lane] = ts;
+        stats_smem[(e * 2 + 1) * 16 + lane] = tq;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+      const int t = threadIdx.x - F_EPI_WARP0 * 32;   // 0..511
       if (t < 128) {
         const int which = t >> 6, col = t & 63;    // which: 0 sum, 1 sumsq
-        const int hf = col >> 5, l = col & 31;
+        const int c4 = col >> 4, l = col & 15;
         float s = 0.f;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) s += stats_smem[(((hf * 4 + qq) * 2) + which) * 32 + l];
+        for (int qq = 0; qq < 4; ++qq) s += stats_smem[(((c4 * 4 + qq) * 2) + which) * 16 + l];
         p.stats[(size_t)blockIdx.x * 128 + which * 64 + col] = s;
       }
     }
@@ -316,17 +440,32 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.total_tiles = N * p.tiles_per_img;
   p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
   p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
-  p.out = out; p.stats = epi.stats; p.variant = g_variant;
+  p.stats = epi.stats; p.variant = g_variant;
   PCG_REQUIRE(epi.stats == nullptr || (epi.act == ACT_NONE && epi.add_src == nullptr && p.act_ref == nullptr),
               "BatchNorm statistics are taken of (accumulator + bias) only");
+  // one epilogue operand travels by TMA (the residual if there is one, else the activation reference)
+  p.n_extra = (p.add_src != nullptr || p.act_ref != nullptr) ? 1 : 0;
+  p.extra_is_add = p.add_src != nullptr ? 1 : 0;
+  const bf16* extra = p.add_src != nullptr ? p.add_src : p.act_ref;
+  auto round1k = [](int b) { return (b + 1023) / 1024 * 1024; };
+  p.in_stage_bytes = round1k((p.R + 2) * p.WP * 128);
+  p.out_tile_bytes = round1k(p.R * p.W * 128);
+  p.in_stages = 4;
+  auto total = [&]() {
+    return 1024 + W_BYTES + p.in_stages * p.in_stage_bytes + (2 + 2 * p.n_extra) * p.out_tile_bytes + F_TAIL_BYTES;
+  };
+  while (total() > SMEM_LIMIT && p.in_stages > 2) --p.in_stages;
+  PCG_REQUIRE(total() <= SMEM_LIMIT, "halo-tile kernel: shared-memory budget exceeded");
   CUtensorMap tmX = make_tmap_nhwc_box(in, N, H, W, 64, p.WP, p.R + 2);
   CUtensorMap tmW = make_tmap_2d(wpk, 64, 576, 64);
+  CUtensorMap tmOut = make_tmap_nhwc_box(out, N, H, W, 64, W, p.R);
+  CUtensorMap tmExtra = make_tmap_nhwc_box(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
   static bool configured = false;
   if (!configured) {
-    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
-  conv_tc64_fprop_kernel<<<conv_tc64_grid(N, H, W), F_THREADS, F_SMEM_BYTES, stream>>>(tmX, tmW, p);
+  conv_tc64_fprop_kernel<<<conv_tc64_grid(N, H, W), F_THREADS, total(), stream>>>(tmX, tmW, tmOut, tmExtra, p);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
