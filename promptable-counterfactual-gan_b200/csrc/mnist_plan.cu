@@ -213,7 +213,14 @@ struct MnistPlan : PlanBase {
   std::vector<T*> y1, z1, y2;
   T* hm;
   float *cimg, *raw, *masked, *x_cf;
-  T *dhA, *dhB, *dyb, *dz1;      // backward ping-pong
+  T *dhA, *dhB, *dz1;            // backward ping-pong
+  T* g_hm;                       // gradient wrt conv_mid's output
+  std::vector<T*> dy1, dy2;      // per-block gradients wrt the conv outputs (own buffers: the weight-gradient
+                                 // stream reads them while the main stream runs ahead)
+  // side streams: weight gradients (off the data-gradient critical path) and the classifier branch of the G step
+  cudaStream_t side_w = nullptr, side_c = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
   T* g_c;                        // [B][784] gradient wrt conv_out output
   float* dinp;                   // [B][784][3]
   // D (sized for 2B)
@@ -371,7 +378,15 @@ struct MnistPlan : PlanBase {
     hm = alloc<T>(act, "hm");
     cimg = alloc<float>(MG, "cimg"); raw = alloc<float>(MG, "raw"); masked = alloc<float>(MG, "masked");
     x_cf = alloc<float>(MG, "x_cf");
-    dhA = alloc<T>(act, "dhA"); dhB = alloc<T>(act, "dhB"); dyb = alloc<T>(act, "dy"); dz1 = alloc<T>(act, "dz1");
+    dhA = alloc<T>(act, "dhA"); dhB = alloc<T>(act, "dhB"); dz1 = alloc<T>(act, "dz1");
+    g_hm = alloc<T>(act, "g_hm");
+    dy1.resize(nres); dy2.resize(nres);
+    for (int i = 0; i < nres; ++i) { dy1[i] = alloc<T>(act); dy2[i] = alloc<T>(act); }
+    dbg["dy"] = {nres ? dy1[0] : nullptr, {(long long)act, kBf16 ? PCG_BF16 : PCG_F32}};
+    PCG_CHECK_CUDA(cudaStreamCreateWithFlags(&side_w, cudaStreamNonBlocking));
+    PCG_CHECK_CUDA(cudaStreamCreateWithFlags(&side_c, cudaStreamNonBlocking));
+    ev_pool.resize(96);
+    for (auto& e : ev_pool) PCG_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_c = alloc<T>(MG, "g_c");
     dinp = alloc<float>((size_t)MG * 3, "dinp");
     a0 = alloc<T>((size_t)2 * MG * 2, "a0");
@@ -407,6 +422,15 @@ struct MnistPlan : PlanBase {
 
   ~MnistPlan() override {
     for (void* p : owned) cudaFree(p);
+    for (auto e : ev_pool) cudaEventDestroy(e);
+    if (side_w) cudaStreamDestroy(side_w);
+    if (side_c) cudaStreamDestroy(side_c);
+  }
+  // `to` continues after everything enqueued on `from` so far (a graph edge under stream capture)
+  void after(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = ev_pool[ev_next++ % ev_pool.size()];
+    PCG_CHECK_CUDA(cudaEventRecord(e, from));
+    PCG_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
   }
 
   // ---------------------------------------------------------------- conv dispatch
@@ -618,15 +642,23 @@ struct MnistPlan : PlanBase {
   }
   // backward from ddlogit; weight grads written when `wg`; dxd[n][784] = gradient wrt input channel `in_ch`
   // (0 = image, needed by the G step; 1 = label-embedding map, needed by the D step)
+  // Weight gradients run on side_w: each only needs dg[l] (written once per pass) and a forward activation, so the
+  // data-gradient chain on `s` never waits for them; the caller joins side_w before the optimizer step.
   void d_bwd(int n, bool wg, int in_ch, cudaStream_t s) {
     d_head_bwd<T>(dz[3], ddlogit, n, 4, 256, d_head_w, 0.2f, dg[3], wg ? d_dhead_w : nullptr, wg ? d_dhead_b : nullptr,
                   stat_part2, s);
     for (int l = 3; l >= 1; --l) {
-      if (wg) wgrad<T, T>(d_conv[l], dz[l - 1], dg[l], s, n);
+      if (wg) {
+        after(s, side_w);
+        wgrad<T, T>(d_conv[l], dz[l - 1], dg[l], side_w, n);
+      }
       GenEpilogue<T> e; e.act_ref = dz[l - 1]; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f;
       dgrad<T, T>(d_conv[l], dg[l], e, dg[l - 1], s, n);
     }
-    if (wg) wgrad<T, T>(d_conv[0], a0, dg[0], s, n);
+    if (wg) {
+      after(s, side_w);
+      wgrad<T, T>(d_conv[0], a0, dg[0], side_w, n);
+    }
     GenEpilogue<float> e0;
     dgrad<T, float>(d_conv[0], dg[0], e0, dxd, s, n, in_ch);
   }
@@ -645,6 +677,7 @@ struct MnistPlan : PlanBase {
                    scal + PCG_S_D_LOSS_REAL, 1.f, 1.f, 0.f, 0.f, scal + PCG_S_D_LOSS, s);
     d_bwd(2 * B, true, 1, s);
     embed_grad<float>(dxd, 1, 0, labels2, 2 * B, 784, 10, d_dembed, s);
+    after(side_w, s);
   }
 
   void step_d_update(cudaStream_t s) override {
@@ -667,36 +700,40 @@ struct MnistPlan : PlanBase {
 
   void step_g_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override {
     // --- adversarial path through the UPDATED discriminator (trainer.py:116-117)
+    // --- classifier path (trainer.py:118) on side_c: independent of the discriminator path until the two input
+    //     gradients meet in residual_head_bwd; both are chains of small kernels that do not fill the GPU alone
+    after(s, side_c);
+    {
+      cudaStream_t c = side_c;
+      c_fwd(x_cf, c);
+      ce_loss(clogits, in.target, B, 10, cfg.lambda_cls, scal + PCG_S_G_CLS, cdlogits, c);
+      GenEpilogue<T> e; e.ref_act = ACT_RELU;
+      e.act_ref = cf1; dgrad<float, T>(c_fc2, cdlogits, e, cdf1, c);
+      e.act_ref = cz[2]; dgrad<T, T>(c_fc1, cdf1, e, cd3, c);
+      e.act_ref = cz[1]; dgrad<T, T>(c_conv[2], cd3, e, cd2, c);
+      e.act_ref = cz[0]; dgrad<T, T>(c_conv[1], cd2, e, cd1, c);
+      GenEpilogue<float> e0;
+      dgrad<T, float>(c_conv[0], cd1, e0, dxc, c);
+    }
     d_input<T>(x_cf, d_embed, in.target, B, 784, a0, s);
     d_fwd(B, s);
     bce_logits(dlogits_d, B, 1, 1.f, 1.f, cfg.lambda_adv, cfg.lambda_adv, scal + PCG_S_G_ADV, scal_tmp, ddlogit, s);
     d_bwd(B, cfg.pollute_d_grads != 0, 0, s);
-    // --- classifier path (trainer.py:118)
-    c_fwd(x_cf, s);
-    ce_loss(clogits, in.target, B, 10, cfg.lambda_cls, scal + PCG_S_G_CLS, cdlogits, s);
-    {
-      GenEpilogue<T> e; e.ref_act = ACT_RELU;
-      e.act_ref = cf1; dgrad<float, T>(c_fc2, cdlogits, e, cdf1, s);
-      e.act_ref = cz[2]; dgrad<T, T>(c_fc1, cdf1, e, cd3, s);
-      e.act_ref = cz[1]; dgrad<T, T>(c_conv[2], cd3, e, cd2, s);
-      e.act_ref = cz[0]; dgrad<T, T>(c_conv[1], cd2, e, cd1, s);
-      GenEpilogue<float> e0;
-      dgrad<T, float>(c_conv[0], cd1, e0, dxc, s);
-    }
+    after(side_c, s);
     g_loss_combine(scal + PCG_S_G_ADV, scal + PCG_S_G_CLS, scal + PCG_S_REG_L1, scal + PCG_S_MASK_PEN, cfg.lambda_adv,
                    cfg.lambda_cls, cfg.lambda_reg, cfg.lambda_mask, scal + PCG_S_G_LOSS, s);
     // --- through clamp / mask / scaling (trainer.py:97,99,119; generator.py:80-82)
     residual_head_bwd<T>(dxd, 1, dxc, raw, in.x, in.mask, cfg.residual_scaling, cfg.lambda_reg, cfg.lambda_mask, MG,
                          g_c, s);
     // --- generator backward
-    wgrad<T, T>(g_out, hm, g_c, s);
+    // weight gradients go to side_w (see d_bwd); every dY they read has its own buffer
+    after(s, side_w);
+    wgrad<T, T>(g_out, hm, g_c, side_w);
     if (!g_out.to1_wgrad) bias_grad(g_c, MG, 1, g_out.db, s);
-    T* g_hm = dz1;
     {
       GenEpilogue<T> e; e.act_ref = hm; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f;
       dgrad<T, T>(g_out, g_c, e, g_hm, s);
     }
-    wgrad<T, T>(g_mid, h[nres], g_hm, s);
     bias_grad(g_hm, MG, ch, g_mid.db, s);
     T* dh = dhA;
     T* dh_other = dhB;
@@ -704,32 +741,38 @@ struct MnistPlan : PlanBase {
       GenEpilogue<T> e;
       dgrad<T, T>(g_mid, g_hm, e, dh, s);
     }
+    after(s, side_w);
+    wgrad<T, T>(g_mid, h[nres], g_hm, side_w);
     for (int i = nres - 1; i >= 0; --i) {
       // BN2 backward: upstream = 0.1 * dh (generator.py:22)
       const BN& q2 = bn2[i];
       bn_bwd_partial<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, 0.1f, ACT_NONE, 0.f, MG, ch, stat_part, s);
       bn_bwd_finalize(stat_part, STAT_PARTS, MG, ch, q2.dgamma, q2.dbeta, c12, s);
-      bn_bwd_apply<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, q2.gamma, c12, 0.1f, ACT_NONE, 0.f, MG, ch, dyb,
+      bn_bwd_apply<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, q2.gamma, c12, 0.1f, ACT_NONE, 0.f, MG, ch, dy2[i],
                       stat_part2, s);
       colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c2[i].db, s);
-      wgrad<T, T>(g_c2[i], z1[i], dyb, s);
       {
         GenEpilogue<T> e;
-        dgrad<T, T>(g_c2[i], dyb, e, dz1, s);
+        dgrad<T, T>(g_c2[i], dy2[i], e, dz1, s);
       }
+      // forked AFTER the data gradient: the two tcgen05 kernels cannot share an SM (shared memory), and this order
+      // makes the weight gradient overlap the HBM-bound BatchNorm kernels that follow on the main stream
+      after(s, side_w);
+      wgrad<T, T>(g_c2[i], z1[i], dy2[i], side_w);
       // LeakyReLU + BN1 backward
       const BN& q1 = bn1[i];
       bn_bwd_partial<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, 1.f, ACT_LRELU, 0.2f, MG, ch, stat_part, s);
       bn_bwd_finalize(stat_part, STAT_PARTS, MG, ch, q1.dgamma, q1.dbeta, c12, s);
       bn_bwd_apply<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, q1.gamma, c12, 1.f, ACT_LRELU, 0.2f, MG, ch,
-                      dyb, stat_part2, s);
+                      dy1[i], stat_part2, s);
       colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c1[i].db, s);
-      wgrad<T, T>(g_c1[i], h[i], dyb, s);
       {
         GenEpilogue<T> e; e.add_src = dh;
         if (i == 0) { e.act_ref = h[0]; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f; }
-        dgrad<T, T>(g_c1[i], dyb, e, dh_other, s);
+        dgrad<T, T>(g_c1[i], dy1[i], e, dh_other, s);
       }
+      after(s, side_w);
+      wgrad<T, T>(g_c1[i], h[i], dy1[i], side_w);
       T* t = dh; dh = dh_other; dh_other = t;
     }
     if (nres == 0) {
@@ -738,12 +781,14 @@ struct MnistPlan : PlanBase {
       throw Error(1, "n_resblocks == 0 is not supported by the fused backward");
     }
     // dh now holds d loss / d (pre-activation of conv_in)
-    wgrad<T, T>(g_in, inp3, dh, s);
+    after(s, side_w);
+    wgrad<T, T>(g_in, inp3, dh, side_w);
     if (!g_in.few_wgrad) bias_grad(dh, MG, ch, g_in.db, s);
     {
       GenEpilogue<float> e;
       dgrad<T, float>(g_in, dh, e, dinp, s, 0, /*ch_select=*/1);    // only the label-embedding channel
     }
+    after(side_w, s);
     embed_grad<float>(dinp, 1, 0, in.target, B, 784, 10, g_dembed, s);
   }
 
