@@ -490,7 +490,7 @@ void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStrea
 }
 
 void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, const bf16* packed,
-                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream) {
+                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream, const cudaStream_t* class_streams) {
   PCG_REQUIRE(Cout % 64 == 0 && Cin % 32 == 0, "strided tensor-core dgrad needs Cout % 64 == 0, Cin % 32 == 0");
   PCG_REQUIRE(epi.stats == nullptr && epi.bias == nullptr, "no bias / statistics in the dgrad epilogue");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
@@ -516,11 +516,17 @@ void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, co
     CUtensorMap tmB = make_tmap_2d(packed + cls_off[cls], Cin, (uint64_t)th * tw * Cout, bn);
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    if (bn == 256) launch_fprop<256>(tmA, tmB, p, grid, stream);
-    else if (bn == 128) launch_fprop<128>(tmA, tmB, p, grid, stream);
-    else if (bn == 64) launch_fprop<64>(tmA, tmB, p, grid, stream);
-    else launch_fprop<32>(tmA, tmB, p, grid, stream);
+    cudaStream_t cs = class_streams != nullptr ? class_streams[cls] : stream;
+    if (bn == 256) launch_fprop<256>(tmA, tmB, p, grid, cs);
+    else if (bn == 128) launch_fprop<128>(tmA, tmB, p, grid, cs);
+    else if (bn == 64) launch_fprop<64>(tmA, tmB, p, grid, cs);
+    else launch_fprop<32>(tmA, tmB, p, grid, cs);
   }
+}
+int conv_tc_dgrad_s2_class_ctas(int N, int H, int W, int Cin) {
+  const int bn = pick_bn(Cin);
+  const long long tiles = (((long long)N * ((H + 1) / 2) * ((W + 1) / 2) + TILE_M - 1) / TILE_M) * (Cin / bn);
+  return (int)(tiles < sm_count() ? tiles : sm_count());
 }
 
 // ------------------------------------------------------------------------------------------

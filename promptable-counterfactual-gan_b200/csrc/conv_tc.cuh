@@ -37,8 +37,12 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
 // output rows scatter to every other pixel of dx.  Epilogue: act / add_src / act_ref as in fprop (no bias/stats).
 size_t conv_tc_dgrad_s2_pack_elems(int Cout, int Cin);
 void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStream_t stream);
+// `class_streams` (optional, 4 entries): the four parity classes write disjoint pixels, so they may run on different
+// streams; the caller orders those streams around the call.  conv_tc_dgrad_s2_class_ctas = CTAs of the largest class.
 void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, const bf16* packed,
-                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream);
+                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream,
+                      const cudaStream_t* class_streams = nullptr);
+int conv_tc_dgrad_s2_class_ctas(int N, int H, int W, int Cin);
 
 // dW partials of a 3x3 / stride-1 / pad-1 convolution with Cin = Cout = 64:
 //   part[cta][tap][ci][co] (fp32) = sum over the CTA's pixels of x[p + tap][ci] * dy[p][co]

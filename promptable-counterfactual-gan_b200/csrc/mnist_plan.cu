@@ -66,7 +66,8 @@ struct PackDesc {
   const float* w;
   float *wf, *wd;
   bf16 *tcf, *tcd, *tcs2;
-  int Cout, Cin, taps, perm_hw;
+  int Cout, Cin, taps, perm_hw;   // dimensions of the torch tensor
+  int ld_cout, ld_cin;            // channel counts of the packed layouts (>= Cout / Cin: zero-padded layers)
   int begin;                 // first flat element of this layer in the table-wide index space
 };
 constexpr int PACK_MAX_LAYERS = 40;
@@ -90,19 +91,20 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
     }
     const float v = L.w[i];
     const bf16 vb = __float2bfloat16_rn(v);
-    const size_t f = ((size_t)co * taps + tap) * Cin + ci;
+    const int ldi = L.ld_cin, ldo = L.ld_cout;
+    const size_t f = ((size_t)co * taps + tap) * ldi + ci;
     if (L.wf) L.wf[f] = v;
-    if (L.wd) L.wd[((size_t)ci * taps + tap) * Cout + co] = v;
+    if (L.wd) L.wd[((size_t)ci * taps + tap) * ldo + co] = v;
     if (L.tcf) L.tcf[f] = vb;
-    if (L.tcd) L.tcd[((size_t)ci * taps + (taps - 1 - tap)) * Cout + co] = vb;
+    if (L.tcd) L.tcd[((size_t)ci * taps + (taps - 1 - tap)) * ldo + co] = vb;
     if (L.tcs2) {                // parity classes of the stride-2 data gradient (conv_tc.cu: pack_dgrad_s2_kernel)
       const int s2 = tap % 3, r = tap / 3;
       const int ph = (r == 1) ? 0 : 1, pw = (s2 == 1) ? 0 : 1;
       const int oh = (r == 0) ? 1 : 0, ow = (s2 == 0) ? 1 : 0;
       const int taps_w = pw ? 2 : 1, ntap = (ph ? 2 : 1) * taps_w;
-      const size_t u = (size_t)Cout * Cin;
+      const size_t u = (size_t)ldo * ldi;
       bf16* dst = L.tcs2 + (ph ? (pw ? 5 * u : 3 * u) : (pw ? u : 0));
-      dst[((size_t)ci * ntap + oh * taps_w + ow) * Cout + co] = vb;
+      dst[((size_t)ci * ntap + oh * taps_w + ow) * ldo + co] = vb;
     }
   }
 }
@@ -144,6 +146,7 @@ struct ConvLayer {
   bool few_wgrad = false;     // Cin <= 3, Cout == 64: wgrad_few (also produces the bias gradient)
   bool to1_wgrad = false;     // 64 -> 1: wgrad_to1 (also produces the bias gradient)
   int perm_hw = 0;
+  int src_cin = 0, src_cout = 0;   // channel counts of the torch weight (g.Cin / g.Cout may be zero-padded)
   std::string name, tag_f, tag_d, tag_w;
 
   // Only the layouts a kernel of this plan actually reads are written: the fprop tensor-core packing is the bf16
@@ -152,7 +155,8 @@ struct ConvLayer {
   PackDesc desc(bool wd_generic_too) const {
     PCG_REQUIRE(!tcs2 || perm_hw == 0, "permuted stride-2 dgrad packing unsupported");
     PackDesc d;
-    d.w = w; d.Cout = g.Cout; d.Cin = g.Cin; d.taps = g.ksize * g.ksize; d.perm_hw = perm_hw; d.begin = 0;
+    d.w = w; d.Cout = src_cout; d.Cin = src_cin; d.taps = g.ksize * g.ksize; d.perm_hw = perm_hw; d.begin = 0;
+    d.ld_cout = g.Cout; d.ld_cin = g.Cin;
     d.wf = (tc_fprop || to1_fprop || few_fprop) ? nullptr : wf;
     d.wd = (((tc_dgrad || tc_dgrad_s2) && !wd_generic_too) || to1_dgrad || few_dgrad || s2_to1_dgrad) ? nullptr : wd;
     d.tcf = tcf; d.tcd = tcd; d.tcs2 = tcs2;
@@ -218,7 +222,7 @@ struct MnistPlan : PlanBase {
   std::vector<T*> dy1, dy2;      // per-block gradients wrt the conv outputs (own buffers: the weight-gradient
                                  // stream reads them while the main stream runs ahead)
   // side streams: weight gradients (off the data-gradient critical path) and the classifier branch of the G step
-  cudaStream_t side_w = nullptr, side_c = nullptr;
+  cudaStream_t side_w = nullptr, side_c = nullptr, aux[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   T* g_c;                        // [B][784] gradient wrt conv_out output
@@ -249,8 +253,22 @@ struct MnistPlan : PlanBase {
   }
 
   void setup_conv(ConvLayer<T>& L, const std::string& name, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                  int pad, const float* w, const float* b, float* dw, float* db, bool need_wd, int perm_hw = 0) {
+                  int pad, const float* w, const float* b, float* dw, float* db, bool need_wd, int perm_hw = 0,
+                  int cin_pad = 0, int cout_pad = 0) {
     L.name = name; L.tag_f = name + ".fprop"; L.tag_d = name + ".dgrad"; L.tag_w = name + ".wgrad";
+    // cin_pad / cout_pad: the kernels see zero-padded channel counts (the packed weights and the activation maps
+    // carry zero channels) so that a 32-channel layer can use the 64-channel tensor-core kernels
+    L.src_cin = Cin; L.src_cout = Cout;
+    if (cin_pad > Cin) Cin = cin_pad;
+    if (cout_pad > Cout) {
+      PCG_REQUIRE(dw == nullptr, "output-channel padding is for frozen layers");
+      if (b != nullptr) {
+        float* bp = alloc<float>(cout_pad);
+        padded_bias.push_back({bp, b, Cout});
+        b = bp;
+      }
+      Cout = cout_pad;
+    }
     L.g = ConvGeom{N, H, W, Cin, Cout, k, stride, pad};
     L.w = w; L.b = b; L.dw = dw; L.db = db; L.perm_hw = perm_hw;
     const size_t n = (size_t)Cout * Cin * k * k;
@@ -358,8 +376,11 @@ struct MnistPlan : PlanBase {
     }
     d_head_w = DP(5); d_head_b = DP(6); d_dhead_w = DG(5); d_dhead_b = DG(6);
     // ---- classifier (frozen; data gradients only)
-    setup_conv(c_conv[0], "c.conv0", B, 28, 28, 1, 32, 3, 1, 1, CP(0), CP(1), nullptr, nullptr, true);
-    setup_conv(c_conv[1], "c.conv1", B, 28, 28, 32, 64, 3, 2, 1, CP(2), CP(3), nullptr, nullptr, true);
+    // the classifier's 32-channel map is carried as 64 channels (upper half zero) in tensor-core mode: conv1 then is a
+    // 64 -> 64 stride-2 convolution the tcgen05 im2col kernel takes
+    const int c1 = (kBf16 && cfg.use_tensor_cores) ? 64 : 32;
+    setup_conv(c_conv[0], "c.conv0", B, 28, 28, 1, 32, 3, 1, 1, CP(0), CP(1), nullptr, nullptr, true, 0, 0, c1);
+    setup_conv(c_conv[1], "c.conv1", B, 28, 28, 32, 64, 3, 2, 1, CP(2), CP(3), nullptr, nullptr, true, 0, c1, 0);
     setup_conv(c_conv[2], "c.conv2", B, 14, 14, 64, 128, 3, 2, 1, CP(4), CP(5), nullptr, nullptr, true);
     setup_conv(c_fc1, "c.fc1", B, 1, 1, 6272, 256, 1, 1, 0, CP(6), CP(7), nullptr, nullptr, true, /*perm_hw=*/49);
     setup_conv(c_fc2, "c.fc2", B, 1, 1, 256, 10, 1, 1, 0, CP(8), CP(9), nullptr, nullptr, true);
@@ -385,7 +406,8 @@ struct MnistPlan : PlanBase {
     dbg["dy"] = {nres ? dy1[0] : nullptr, {(long long)act, kBf16 ? PCG_BF16 : PCG_F32}};
     PCG_CHECK_CUDA(cudaStreamCreateWithFlags(&side_w, cudaStreamNonBlocking));
     PCG_CHECK_CUDA(cudaStreamCreateWithFlags(&side_c, cudaStreamNonBlocking));
-    ev_pool.resize(96);
+    for (auto& a : aux) PCG_CHECK_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    ev_pool.resize(256);
     for (auto& e : ev_pool) PCG_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_c = alloc<T>(MG, "g_c");
     dinp = alloc<float>((size_t)MG * 3, "dinp");
@@ -401,12 +423,12 @@ struct MnistPlan : PlanBase {
     dlogits_d = alloc<float>(2 * B, "d_logits"); ddlogit = alloc<float>(2 * B, "d_dlogit");
     dxd = alloc<float>((size_t)2 * MG * 2, "dxd");
     labels2 = alloc<long long>(2 * B);
-    cz[0] = alloc<T>((size_t)MG * 32, "c.0"); cz[1] = alloc<T>((size_t)B * 196 * 64, "c.1");
+    cz[0] = alloc<T>((size_t)MG * c_conv[0].g.Cout, "c.0"); cz[1] = alloc<T>((size_t)B * 196 * 64, "c.1");
     cz[2] = alloc<T>((size_t)B * 49 * 128, "c.2"); cf1 = alloc<T>((size_t)B * 256, "c.f1");
     clogits = alloc<float>((size_t)B * 10, "c_logits"); cdlogits = alloc<float>((size_t)B * 10, "c_dlogits");
     dxc = alloc<float>(MG, "dxc");
     cdf1 = alloc<T>((size_t)B * 256); cd3 = alloc<T>((size_t)B * 49 * 128); cd2 = alloc<T>((size_t)B * 196 * 64);
-    cd1 = alloc<T>((size_t)MG * 32);
+    cd1 = alloc<T>((size_t)MG * c_conv[0].g.Cout);
     const int maxC = ch > 256 ? ch : 256;
     stat_part = alloc<float>((size_t)STAT_PARTS * 2 * maxC);
     stat_part2 = alloc<float>((size_t)STAT_PARTS * 2 * maxC);
@@ -425,6 +447,7 @@ struct MnistPlan : PlanBase {
     for (auto e : ev_pool) cudaEventDestroy(e);
     if (side_w) cudaStreamDestroy(side_w);
     if (side_c) cudaStreamDestroy(side_c);
+    for (auto a : aux) if (a) cudaStreamDestroy(a);
   }
   // `to` continues after everything enqueued on `from` so far (a graph edge under stream capture)
   void after(cudaStream_t from, cudaStream_t to) {
@@ -515,7 +538,15 @@ struct MnistPlan : PlanBase {
         return;
       }
       if (L.tc_dgrad_s2) {
-        conv_tc_dgrad_s2(dout, g.N, g.H, g.W, g.Cin, g.Cout, L.tcs2, to_tc(e, nullptr), din, s);
+        // small problems (a class needs at most a quarter of the SMs): the four parity classes side by side
+        if (!g_profile_on && 4 * conv_tc_dgrad_s2_class_ctas(g.N, g.H, g.W, g.Cin) <= sm_count() + 20) {
+          cudaStream_t cs[4] = {s, aux[0], aux[1], aux[2]};
+          for (int i = 0; i < 3; ++i) after(s, aux[i]);
+          conv_tc_dgrad_s2(dout, g.N, g.H, g.W, g.Cin, g.Cout, L.tcs2, to_tc(e, nullptr), din, s, cs);
+          for (int i = 0; i < 3; ++i) after(aux[i], s);
+        } else {
+          conv_tc_dgrad_s2(dout, g.N, g.H, g.W, g.Cin, g.Cout, L.tcs2, to_tc(e, nullptr), din, s);
+        }
         return;
       }
     }
@@ -560,6 +591,8 @@ struct MnistPlan : PlanBase {
   }
 
   PackTable pack_g, pack_d, pack_c;
+  struct PaddedBias { float* dst; const float* src; int n; };
+  std::vector<PaddedBias> padded_bias;
   PackTable make_pack_table(const std::vector<PackDesc>& layers) {
     PCG_REQUIRE((int)layers.size() <= PACK_MAX_LAYERS, "too many layers for one pack table");
     std::vector<PackDesc> v = layers;
@@ -590,6 +623,8 @@ struct MnistPlan : PlanBase {
   void refresh_weights(cudaStream_t s) override {
     refresh_g(s); refresh_d(s);
     pack_c.launch(s);
+    for (const auto& pb : padded_bias)
+      PCG_CHECK_CUDA(cudaMemcpyAsync(pb.dst, pb.src, pb.n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
 
   // ---------------------------------------------------------------- generator forward
