@@ -264,9 +264,15 @@ def run_native(args):
             flops_per_step = 26 * CONV_FLOPS
             achieved = flops_per_step / (k["ms_per_step"] * 1e-3) / 1e12
             peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tp):                  # dram bytes (read + write) per launch from the committed ncu capture
+                traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
             roof = {"bound": "tensor",
                     "kernel": "conv_tc64_fprop_kernel (tcgen05 halo-tile conv 64->64, 13 fprop + 13 dgrad per step)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                    "algorithmic_bytes_per_launch": 2 * BATCH * 784 * 64 * 2,
                     "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside the step)",
                     "avg_launch_us": k["ms"] / k["launches"] * 1e3}
 
