@@ -96,17 +96,26 @@ conv_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict_
     const int n = tile / tiles_per_img, h0 = (tile % tiles_per_img) * R;
     mbar_wait(&full[stage], phase);
     const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    // one accumulator chain per filter row: mma.sync results feed the next mma of the same chain, three chains
+    // keep the tensor pipe busy while one waits
+    float c3[3][4];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const uint32_t rowoff = (uint32_t)(arow + (tap / 3) * WP + (tap % 3)) * ROWB;
+    for (int r = 0; r < 3; ++r) c3[r][0] = c3[r][1] = c3[r][2] = c3[r][3] = 0.f;
 #pragma unroll
-      for (int kq = 0; kq < KQ; ++kq) {
-        uint32_t a[4];
-        ldmatrix_x4(base + c1_swizzle<CIN>(rowoff + (uint32_t)(kq * 2 + ahalf) * 16u), a);
-        mma_bf16_16816(c, a, breg[tap * KQ + kq][0], breg[tap * KQ + kq][1]);
-      }
-    }
+    for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+      for (int kq = 0; kq < KQ; ++kq)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int tap = r * 3 + sx;
+          const uint32_t rowoff = (uint32_t)(arow + r * WP + sx) * ROWB;
+          uint32_t a[4];
+          ldmatrix_x4(base + c1_swizzle<CIN>(rowoff + (uint32_t)(kq * 2 + ahalf) * 16u), a);
+          mma_bf16_16816(c3[r], a, breg[tap * KQ + kq][0], breg[tap * KQ + kq][1]);
+        }
+    float c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (c3[0][i] + c3[1][i]) + c3[2][i];
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
     if ((lane & 3) == 0) {
@@ -174,7 +183,7 @@ __device__ __forceinline__ uint32_t load_bits(const float* p) { return bf16_bits
 constexpr int FEW_STAGE_LD = 72;   // floats per staged row: 64 + 8 keeps the float2 writes and float4 reads conflict-free
 
 template <typename TIn, int CS, int COUT, int STRIDE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const float* __restrict__ bias, int act,
                 float slope, const bf16* __restrict__ act_ref, float ref_neg, bf16* __restrict__ out, int H, int W,
                 int Ho, int Wo, long long M) {
@@ -214,14 +223,14 @@ conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const 
   }
 
   const long long nblk = (M + 15) / 16;
-  for (long long blk = (long long)blockIdx.x * 8 + warp; blk < nblk; blk += (long long)gridDim.x * 8) {
-    const long long m0 = blk * 16;
-    // two rows per thread: rr and rr + 8
+  // im2col fragment of one 16-pixel block (two rows per thread: rr and rr + 8)
+  auto load_a = [&](long long blk_, uint32_t (&a)[KS][4]) {
+    const long long m0_ = blk_ * 16;
     int hb_[2], wb_[2];
     long long base[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      long long m = m0 + rr + t * 8;
+      long long m = m0_ + rr + t * 8;
       if (m >= M) m = M - 1;
       const int wo = (int)(m % Wo);
       const long long t2 = m / Wo;
@@ -231,7 +240,6 @@ conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const 
       wb_[t] = wo * STRIDE - 1;
       base[t] = ((n * H + hb_[t]) * W + wb_[t]) * CS;
     }
-    uint32_t a[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -248,6 +256,15 @@ conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const 
         }
         a[ks][r4] = bits[0] | (bits[1] << 16);
       }
+  };
+  const long long bstride = (long long)gridDim.x * 8;
+  long long blk = (long long)blockIdx.x * 8 + warp;
+  uint32_t a[KS][4], a_next[KS][4];
+  if (blk < nblk) load_a(blk, a);
+  for (; blk < nblk; blk += bstride) {
+    const long long m0 = blk * 16;
+    // the next block's (L2-latency) loads are in flight while this block is computed and stored
+    if (blk + bstride < nblk) load_a(blk + bstride, a_next);
     float c[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -295,6 +312,10 @@ conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const 
       }
     }
     __syncwarp();
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) a[ks][r4] = a_next[ks][r4];
   }
 }
 
