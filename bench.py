@@ -303,6 +303,185 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------- other BASELINE configs
+# (SURVEY.md §8a a8-a16).  Same JSON line; the default workload (and the one the driver benches) stays the MNIST step.
+OTHER = {
+    "dcgan": dict(batch=256, name="dconv_gan/mnist DCGAN, synthetic 1x64x64 (28x28 source resized, mnist_dcgan.py:43), batch 256",
+                  flops=2.243e9, bytes=None),
+    "kc": dict(batch=4096, name="conditional_counteRGAN/house_sales_kc_usa tabular CounteRGAN, synthetic KC-shaped features, batch 4096",
+               flops=0.79e6, bytes=424.0),
+    "moons_cf": dict(batch=64, name="conditional_counteRGAN/moons tabular CounteRGAN, batch 64", flops=None, bytes=None),
+    "cgan_moons": dict(batch=1024, name="conditional_gan/moons class-conditional MLP GAN, batch 1024", flops=47e3, bytes=280.0),
+    "simple_moons": dict(batch=128, name="simple_gan/moons MLP GAN on make_moons 2-D points, batch 128", flops=47e3, bytes=280.0),
+}
+
+
+def _other_setup(kind, B, dev):
+    """Returns (native_step(i), cpu_step(i)) closures on identical synthetic state; the CPU side is the oracle port."""
+    import torch
+    from collections import OrderedDict
+    import pcg_b200  # noqa: F401
+    cu = lambda t: None if t is None else t.to(dev).contiguous()  # noqa: E731
+    if kind == "dcgan":
+        from oracle import dcgan as O
+        from pcg_b200.dcgan import DcganPlan
+        PG, PD = O.synth_params(O.g_shapes(), 5), O.synth_params(O.d_shapes(), 6)
+        S = O.make_state(PG, O.buffers(O.g_shapes()), PD, O.buffers(O.d_shapes()))
+        plan = DcganPlan(B, dev) if dev is not None else None
+        if plan is not None:
+            plan.G.load(PG); plan.D.load(PD); plan.refresh()
+        ring = [O.synth_batch(B, 70 + i) for i in range(4)]
+        dring = [tuple(cu(t) for t in b) for b in ring] if plan is not None else None
+        cpu_ring = [O.synth_batch(16, 90 + i) for i in range(2)]
+        return (lambda i: plan.step(*dring[i % 4])), (lambda i: O.dcgan_step(S, *cpu_ring[i % 2])), 16
+    if kind in ("kc", "moons_cf"):
+        from oracle import tabular_countergan as T
+        if kind == "kc":
+            from pcg_b200.tabular.kc import KcPlan
+            gs, ds, cs = T.kc_shapes()
+            PG, PD, PC = T.synth_params(gs, 1), T.synth_params(ds, 2), T.synth_params(cs, 3)
+            BD, BC = T.sn_buffers(T.kc_d_dims(), 4), T.bn_buffers(cs, 5, randomize=True)
+            S = T.make_state(PG, T.bn_buffers(gs), PD, BD, PC, BC)
+            nv = T.kc_norm_vals()
+            plan = None
+            if dev is not None:
+                cat = OrderedDict((f, {"n": n, "raw_values": T.KC_RAW[f]}) for f, n in T.KC_CAT.items())
+                plan = KcPlan(B, dev, cat, T.KC_CONT)
+                plan.G.load(PG); plan.C.load(PC)
+                for j, nm in enumerate(plan.c_bn_names):
+                    plan.c_rm[j].copy_(BC[nm + ".running_mean"]); plan.c_rv[j].copy_(BC[nm + ".running_var"])
+                plan.D.flat.load(PD)
+                for i, L in enumerate(plan.D.layers):
+                    L.u.copy_(BD[f"net.{2 * i}.weight_u"]); L.v.copy_(BD[f"net.{2 * i}.weight_v"])
+                plan.refresh()
+            ring = [T.kc_batch(B, 80 + i) for i in range(4)]
+            dring = [(cu(x), cu(y), cu(t), cu(m), [cu(e) for e in noise]) for x, y, t, m, noise in ring] if plan else None
+            return (lambda i: plan.step(*dring[i % 4])), (lambda i: T.kc_step(S, *ring[i % 4], nv)), B
+        from pcg_b200.tabular.moons import MoonsPlan
+        gs, ds, cs = T.moons_shapes()
+        PG, PD, PC = T.synth_params(gs, 1), T.synth_params(ds, 2), T.synth_params(cs, 3)
+        BD = T.sn_buffers(T.moons_d_dims(), 4)
+        S = T.make_state(PG, T.bn_buffers(gs), PD, BD, PC)
+        plan = None
+        if dev is not None:
+            plan = MoonsPlan(B, dev)
+            plan.G.load(PG); plan.C.load(PC); plan.D.flat.load(PD)
+            for i, L in enumerate(plan.D.layers):
+                L.u.copy_(BD[f"net.{2 * i}.weight_u"]); L.v.copy_(BD[f"net.{2 * i}.weight_v"])
+            plan.refresh()
+        ring = [T.moons_batch(B, 50 + i) for i in range(4)]
+        dring = [tuple(cu(t) for t in b) for b in ring] if plan else None
+        return (lambda i: plan.step(*dring[i % 4])), (lambda i: T.moons_step(S, *ring[i % 4])), B
+    from oracle import moons_gan as M
+    from pcg_b200.moons.gan import MlpGanPlan
+    label_dim = 2 if kind == "cgan_moons" else 0
+    gs, ds = M.shapes(label_dim=label_dim)
+    PG, PD = M.synth_params(gs, 1), M.synth_params(ds, 2)
+    S = M.make_state(PG, PD)
+    plan = None
+    if dev is not None:
+        plan = MlpGanPlan(B, 32, label_dim, 128, dev)
+        plan.G.load({"net." + k: v for k, v in PG.items()}); plan.D.load({"net." + k: v for k, v in PD.items()})
+        plan.refresh()
+    ring = [M.synth_batch(B, 300 + i, label_dim=label_dim) for i in range(4)]
+    dring = [tuple(cu(t) for t in b) for b in ring] if plan else None
+    return (lambda i: plan.step(*dring[i % 4])), (lambda i: M.gan_step(S, *ring[i % 4])), B
+
+
+def run_other(args):
+    import torch
+    spec = OTHER[args.workload]
+    B = spec["batch"]
+    metric = "GAN train samples/sec (G+D step) on " + args.workload
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        _, cpu_step, cb = _other_setup(args.workload, B, None)
+        steps = min(max(args.steps, 1), 40)
+        cpu_step(0)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            cpu_step(i)
+        dt = time.perf_counter() - t0
+        rate = cb * steps / dt
+        print(json.dumps({"impl": "reference", "metric": metric, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
+                          "steps": steps, "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": spec["name"], "cpu_batch_per_step": cb},
+                          "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": f"oracle port, {steps} steps of B={cb}"},
+                          "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: libpcg has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from pcg_b200 import _lib
+    native_step, cpu_step, cb = _other_setup(args.workload, B, dev)
+    n0 = _lib.launch_count()
+    native_step(0)                                   # eager pass + graph capture
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - n0
+    for i in range(max(args.warmup, 3)):
+        native_step(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        sc = native_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    value = B * world * args.steps / (ms * 1e-3)      # replicas only (SURVEY §8e): every rank runs the same step
+    # e2e: the same step with the scalars read back every step (inputs of these plans are copied in by step())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        host = native_step(i).cpu()
+    e2e = B * world * args.steps / (time.perf_counter() - t0)
+    if rank != 0:
+        return
+    cpu = None
+    if not args.skip_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_step(0)
+        n = 3 if args.workload == "dcgan" else 10
+        t0 = time.perf_counter()
+        for i in range(n):
+            cpu_step(i)
+        cpu = {"value": cb * n / (time.perf_counter() - t0), "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle port, {n} steps of B={cb} after 1 warm-up"}
+    pk, which = peaks()
+    step_s = ms * 1e-3 / args.steps
+    if spec["flops"] and args.workload == "dcgan":
+        ach = spec["flops"] * B / step_s / 1e12
+        roof = {"bound": "tensor", "kernel": "whole step (fp32 CUDA-core convolutions; tcgen05 path not yet wired for k=4)",
+                "achieved": ach, "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "unit": "TFLOP/s",
+                "frac": ach / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "traffic": None}
+    else:
+        by = (spec["bytes"] or 0.0) * B
+        ach = by / step_s / 1e9
+        roof = {"bound": "hbm", "kernel": "whole step (launch/latency bound: %d kernels in one CUDA graph)" % launches,
+                "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None}
+    print(json.dumps({"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": spec["name"], "global_batch": B * world, "parallelism": "replicas",
+                                 "cuda_graph": True, "l2": "working set fits L2 for the MLP configs (state < 1 MB); "
+                                 "4 rotating input batches"},
+                      "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": 0,
+                              "d2h_bytes_per_step": int(host.numel() * 4)},
+                      "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches),
+                      "roofline": roof, "cpu_baseline": cpu, "clocks": clk}), flush=True)
+
+
 def flops_tc_fprop_per_step():
     """Algorithmic FLOPs executed by conv_tc_fprop launches in one step at B=512 (bf16 plan):
     G: 13 fprop + 13 dgrad of the 64->64 conv; D (3 tensor-core layers): fwd on 2B + fwd on B; C: conv.4 + fc.1."""
@@ -322,8 +501,11 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PCG_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--workload", default="mnist", choices=["mnist"] + sorted(OTHER))
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload != "mnist":
+        run_other(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)
