@@ -199,6 +199,13 @@ int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int 
                    int pad, float* scratch, float* dw /*torch OIHW*/, void* stream);
 int pcg_pack_conv_weights(const float* w /*torch OIHW*/, int Cout, int Cin, int k, int perm_hw, float* wf, float* wd,
                           void* stream);
+/* Tensor-core mode of the three convolution entry points above (default off = exact fp32 on the CUDA cores): layers
+ * with 64-multiple channel counts (fprop: any k/stride/pad; dgrad: 4x4 stride 2 pad 1 on even sizes, i.e. the
+ * ConvTranspose2d forward and Conv2d input gradient of mnist_dcgan.py:72-116; wgrad: 3x3 / 4x4, stride 1|2) round their
+ * operands to bf16 into library-owned scratch and run the tcgen05 implicit-GEMM kernels with fp32 accumulation.
+ * Scratch is sized by the first (eager) call, so run one un-captured pass before CUDA-graph capture. */
+int pcg_set_conv_tensor_cores(int on);
+int pcg_get_conv_tensor_cores(void);
 long long pcg_stat_scratch_floats(int C);
 int pcg_colsum(const float* a, long long M, int C, float* scratch, float* out, void* stream);
 /* nn.BatchNorm{1,2}d in train mode over M rows x C channels (+ fused activation), and its backward

@@ -3,6 +3,7 @@
 #include "../../include/pcg.h"
 
 #include "common.cuh"
+#include "conv_auto.cuh"
 #include "conv_generic.cuh"
 #include "elementwise.cuh"
 #include "ops.cuh"
@@ -34,6 +35,7 @@ int pcg_conv_fprop(const float* in, int N, int H, int W, int Cin, const float* w
   PCG_API_BEGIN
   GenEpilogue<float> e;
   e.bias = bias; e.act = act; e.slope = slope; e.add_src = add_src;
+  if (conv_fprop_auto(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, e, out, ST)) return 0;
   conv_fprop_generic<float, float>(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, e, out, ST);
   PCG_API_END
 }
@@ -42,6 +44,7 @@ int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float*
   PCG_API_BEGIN
   GenEpilogue<float> e;
   e.add_src = add_src; e.act_ref = act_ref; e.ref_act = ref_act; e.ref_slope = ref_slope;
+  if (conv_dgrad_auto(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, e, din, ST)) return 0;
   conv_dgrad_generic<float, float>(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, e, din, ST);
   PCG_API_END
 }
@@ -51,6 +54,7 @@ long long pcg_conv_wgrad_scratch(int N, int H, int W, int Cin, int Cout, int k, 
 int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                    float* scratch, float* dw, void* stream) {
   PCG_API_BEGIN
+  if (conv_wgrad_auto(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), dw, ST)) return 0;
   conv_wgrad_generic<float, float>(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), scratch, dw, ST);
   PCG_API_END
 }
@@ -65,6 +69,11 @@ int pcg_colsum(const float* a, long long M, int C, float* scratch, float* out, v
   colsum_finalize(scratch, STAT_PARTS, C, C, out, ST);
   PCG_API_END
 }
+int pcg_set_conv_tensor_cores(int on) {
+  conv_auto_set_tensor_cores(on != 0);
+  return 0;
+}
+int pcg_get_conv_tensor_cores(void) { return conv_auto_tensor_cores() ? 1 : 0; }
 long long pcg_stat_scratch_floats(int C) { return (long long)STAT_PARTS * 2 * C; }
 
 int pcg_bn_train_fwd(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,

@@ -1,0 +1,17 @@
+// fp32-storage front end of the tensor-core convolution kernels (see conv_auto.cu).  Each function returns false
+// when the layer is not eligible (or the mode is off); the caller then runs the CUDA-core kernel.
+#pragma once
+#include "common.cuh"
+#include "conv_generic.cuh"
+
+namespace pcg {
+
+void conv_auto_set_tensor_cores(bool on);
+bool conv_auto_tensor_cores();
+bool conv_fprop_auto(const float* in, const ConvGeom& g, const float* wf, const GenEpilogue<float>& e, float* out,
+                     cudaStream_t s);
+bool conv_dgrad_auto(const float* dout, const ConvGeom& g, const float* wd, const GenEpilogue<float>& e, float* din,
+                     cudaStream_t s);
+bool conv_wgrad_auto(const float* in, const float* dout, const ConvGeom& g, float* dw, cudaStream_t s);
+
+}  // namespace pcg

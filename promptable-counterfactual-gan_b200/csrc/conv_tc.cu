@@ -144,6 +144,7 @@ struct FpropParams {
   int ref_act;
   float ref_slope;
   bf16* out;
+  float* out_f32;                // if set, results are stored here as fp32 instead of bf16 into `out`
   float* stats;
 };
 
@@ -353,7 +354,11 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
         }
-        if (valid) {
+        if (valid && p.out_f32 != nullptr) {          // fp32 result (fp32-storage callers, conv_auto.cu)
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        } else if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + col0);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -450,7 +455,7 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
   p.num_n_tiles = Cout / bn;
   p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
   p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
-  p.out = out; p.stats = epi.stats;
+  p.out = out; p.out_f32 = epi.out_f32; p.stats = epi.stats;
   CUtensorMap tmA = make_tmap_im2col(in, N, H, W, Cin, ksize, stride, pad);
   CUtensorMap tmB = make_tmap_2d(wpk, Cout, (uint64_t)ksize * ksize * Cin, bn);
   const int grid = conv_tc_grid(M, Cout);
@@ -480,6 +485,37 @@ __global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, int Cout, int 
 
 size_t conv_tc_dgrad_s2_pack_elems(int Cout, int Cin) { return (size_t)Cout * Cin * 9; }
 
+// 4x4 / stride 2 / pad 1: every parity class has 2 x 2 taps; window offset oh -> filter row r = (ph ? 2 : 3) - 2*oh.
+// Source layout wd fp32 [Cin][16][Cout] (taps not rotated); packed = four [Cin][4][Cout] bf16 matrices.
+// `dup` = 3: every [Cout] run becomes [W_hi | W_hi | W_lo] (3*Cout per tap) for a dY operand split into hi | lo | hi
+// (bf16x3 emulation of an fp32 product: hi*W_hi + lo*W_hi + hi*W_lo).
+__global__ void pack_dgrad_s2_k4_kernel(const float* __restrict__ wd, int Cout, int Cin, int dup,
+                                        bf16* __restrict__ packed) {
+  const int total = Cout * Cin * 16;
+  const int ld = dup * Cout;
+  const size_t u4 = (size_t)ld * Cin * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Cout, tap = (i / Cout) % 16, ci = i / (Cout * 16);
+    const int r = tap >> 2, s = tap & 3;
+    const int ph = (r & 1) ? 0 : 1, pw = (s & 1) ? 0 : 1;     // r in {1,3} serves even rows, {0,2} odd rows
+    const int oh = ((ph ? 2 : 3) - r) >> 1, ow = ((pw ? 2 : 3) - s) >> 1;
+    const bf16 v = __float2bfloat16_rn(wd[i]);
+    bf16* dst = packed + (size_t)(ph * 2 + pw) * u4 + ((size_t)ci * 4 + oh * 2 + ow) * ld + co;
+    dst[0] = v;
+    if (dup == 3) {
+      dst[Cout] = v;
+      dst[2 * Cout] = __float2bfloat16_rn(wd[i] - __bfloat162float(v));
+    }
+  }
+}
+void pack_dgrad_s2_k4_tc(const float* wd, int Cout, int Cin, bf16* packed, cudaStream_t stream, int dup) {
+  PCG_PROFILE("pack_weights", stream);
+  const long long total = (long long)Cout * Cin * 16;
+  pack_dgrad_s2_k4_kernel<<<cdiv(total, 256) > 1184 ? 1184 : cdiv(total, 256), 256, 0, stream>>>(wd, Cout, Cin, dup, packed);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStream_t stream) {
   PCG_PROFILE("pack_weights", stream);
   const size_t u = (size_t)Cout * Cin;
@@ -490,20 +526,25 @@ void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStrea
 }
 
 void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, const bf16* packed,
-                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream, const cudaStream_t* class_streams) {
+                      const ConvEpilogue& epi, bf16* dx, cudaStream_t stream, const cudaStream_t* class_streams,
+                      int ksize) {
   PCG_REQUIRE(Cout % 64 == 0 && Cin % 32 == 0, "strided tensor-core dgrad needs Cout % 64 == 0, Cin % 32 == 0");
   PCG_REQUIRE(epi.stats == nullptr && epi.bias == nullptr, "no bias / statistics in the dgrad epilogue");
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  PCG_REQUIRE(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "stride-2 dgrad: 3x3, or 4x4 on even sizes");
+  const int Ho = (H + 2 - ksize) / 2 + 1, Wo = (W + 2 - ksize) / 2 + 1;
   const size_t u = (size_t)Cout * Cin;
-  const size_t cls_off[4] = {0, u, 3 * u, 5 * u};
+  const size_t cls_off3[4] = {0, u, 3 * u, 5 * u};
   const int bn = pick_bn(Cin);
   for (int cls = 0; cls < 4; ++cls) {
     const int ph = cls >> 1, pw = cls & 1;
     const int Ah = (H + 1 - ph) / 2, Aw = (W + 1 - pw) / 2;
     if (Ah <= 0 || Aw <= 0) continue;
-    const int th = ph ? 2 : 1, tw = pw ? 2 : 1;
+    // 3x3: 1 or 2 taps per dimension, windows start at the class pixel; 4x4: always 2 taps, even rows look one back
+    const int th = ksize == 4 ? 2 : (ph ? 2 : 1), tw = ksize == 4 ? 2 : (pw ? 2 : 1);
+    const int lo_h = (ksize == 4 && ph == 0) ? -1 : 0, lo_w = (ksize == 4 && pw == 0) ? -1 : 0;
+    const size_t cls_off = ksize == 4 ? (size_t)cls * 4 * u : cls_off3[cls];
     FpropParams p;
-    p.M = N * Ah * Aw; p.Ho = Ah; p.Wo = Aw; p.tstride = 1; p.lower_h = 0; p.lower_w = 0;
+    p.M = N * Ah * Aw; p.Ho = Ah; p.Wo = Aw; p.tstride = 1; p.lower_h = lo_h; p.lower_w = lo_w;
     p.taps_h = th; p.taps_w = tw;
     p.OH = H; p.OW = W; p.os = 2; p.oh0 = ph; p.ow0 = pw;
     p.cin_blocks = Cout / 64; p.Cout = Cin;
@@ -511,9 +552,9 @@ void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, co
     p.num_n_tiles = Cin / bn;
     p.bias = nullptr; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
     p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
-    p.out = dx; p.stats = nullptr;
-    CUtensorMap tmA = make_tmap_im2col_box(dy, N, Ho, Wo, Cout, 0, 0, Aw - Wo, Ah - Ho, 1);
-    CUtensorMap tmB = make_tmap_2d(packed + cls_off[cls], Cin, (uint64_t)th * tw * Cout, bn);
+    p.out = dx; p.out_f32 = epi.out_f32; p.stats = nullptr;
+    CUtensorMap tmA = make_tmap_im2col_box(dy, N, Ho, Wo, Cout, lo_w, lo_h, Aw - Wo + lo_w, Ah - Ho + lo_h, 1);
+    CUtensorMap tmB = make_tmap_2d(packed + cls_off, Cin, (uint64_t)th * tw * Cout, bn);
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     cudaStream_t cs = class_streams != nullptr ? class_streams[cls] : stream;
@@ -693,7 +734,8 @@ struct WggCfg {
 };
 
 struct WggParams {
-  int P, Ho, Wo, stride, cin_blocks, Cout, K;       // K = 9 * Cin
+  int P, Ho, Wo, stride, cin_blocks, Cout, K;       // K = ksize^2 * Cin
+  int ksize, pad;
   int units, pairs, n_tiles, ksplit, kb_per_split, num_kb;
   float* part;
 };
@@ -746,15 +788,15 @@ conv_tc_wgrad_general_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
       for (int kb = kb0; kb < kb1; ++kb) {
         const int p0 = kb * TILE_M;
         const int n_img = p0 / hw, rem = p0 % hw;
-        const int cw = (rem % p.Wo) * p.stride - 1, ch = (rem / p.Wo) * p.stride - 1;
+        const int cw = (rem % p.Wo) * p.stride - p.pad, ch = (rem / p.Wo) * p.stride - p.pad;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
         uint8_t* dst = smem + stage * Cfg::STAGE_BYTES;
         for (int h = 0; h < 2; ++h) {
           const int u = h ? u1 : u0;
           const int tap = u / p.cin_blocks, cb = u % p.cin_blocks;
-          tma_load_im2col_4d(&tmX, &full[stage], dst + h * A_STAGE_BYTES, cb * 64, cw, ch, n_img, (uint16_t)(tap % 3),
-                             (uint16_t)(tap / 3));
+          tma_load_im2col_4d(&tmX, &full[stage], dst + h * A_STAGE_BYTES, cb * 64, cw, ch, n_img,
+                             (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
         }
         for (int nb = 0; nb < NT / 64; ++nb)
           tma_load_2d(&tmDY, &full[stage], dst + (2 + nb) * A_STAGE_BYTES, nt * NT + nb * 64, p0);
@@ -818,11 +860,12 @@ conv_tc_wgrad_general_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
   }
 }
 
-static void wgg_plan(int N, int H, int W, int Cin, int Cout, int stride, WggParams& p, int& nt_size) {
-  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  p.P = N * Ho * Wo; p.Ho = Ho; p.Wo = Wo; p.stride = stride;
-  p.cin_blocks = Cin / 64; p.Cout = Cout; p.K = 9 * Cin;
-  p.units = 9 * p.cin_blocks; p.pairs = (p.units + 1) / 2;
+static void wgg_plan(int N, int H, int W, int Cin, int Cout, int stride, WggParams& p, int& nt_size, int ksize = 3,
+                     int pad = 1) {
+  const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+  p.P = N * Ho * Wo; p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.ksize = ksize; p.pad = pad;
+  p.cin_blocks = Cin / 64; p.Cout = Cout; p.K = ksize * ksize * Cin;
+  p.units = ksize * ksize * p.cin_blocks; p.pairs = (p.units + 1) / 2;
   nt_size = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
   p.n_tiles = Cout / nt_size;
   p.num_kb = (p.P + TILE_M - 1) / TILE_M;
@@ -833,20 +876,20 @@ static void wgg_plan(int N, int H, int W, int Cin, int Cout, int stride, WggPara
   p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
 }
 
-int conv_tc_wgrad_general_splits(int N, int H, int W, int Cin, int Cout, int stride) {
+int conv_tc_wgrad_general_splits(int N, int H, int W, int Cin, int Cout, int stride, int ksize, int pad) {
   WggParams p; int nt;
-  wgg_plan(N, H, W, Cin, Cout, stride, p, nt);
+  wgg_plan(N, H, W, Cin, Cout, stride, p, nt, ksize, pad);
   return p.ksplit;
 }
 
 void conv_tc_wgrad_general(const bf16* x, const bf16* dy, int N, int H, int W, int Cin, int Cout, int stride,
-                           float* part, cudaStream_t stream) {
+                           float* part, cudaStream_t stream, int ksize, int pad) {
   PCG_PROFILE("conv_tc_wgrad_general", stream);
   PCG_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && (stride == 1 || stride == 2), "unsupported wgrad shape");
   WggParams p; int nt;
-  wgg_plan(N, H, W, Cin, Cout, stride, p, nt);
+  wgg_plan(N, H, W, Cin, Cout, stride, p, nt, ksize, pad);
   p.part = part;
-  CUtensorMap tmX = make_tmap_im2col(x, N, H, W, Cin, 3, stride, 1);
+  CUtensorMap tmX = make_tmap_im2col(x, N, H, W, Cin, ksize, stride, pad);
   CUtensorMap tmDY = make_tmap_2d(dy, (uint64_t)p.P, (uint64_t)Cout, 128);
   const int grid = p.pairs * p.n_tiles * p.ksplit;
 #define PCG_WGG(NTV)                                                                                               \

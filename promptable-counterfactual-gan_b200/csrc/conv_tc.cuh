@@ -15,6 +15,7 @@ struct ConvEpilogue {
   const bf16* act_ref = nullptr; // [M][Cout] bf16: result is multiplied by d act/d pre evaluated at
   int ref_act = ACT_NONE;        // act_ref (the activation OUTPUT; LReLU/ReLU derivative from its sign)
   float ref_slope = 0.2f;
+  float* out_f32 = nullptr;      // conv_tc_fprop / conv_tc_dgrad_s2 only: store the result as fp32 here (same shape)
   float* stats = nullptr;        // [grid][2*Cout] fp32 per-CTA partial (sum, sum of squares) of the
                                  // pre-rounding output values, for train-mode BatchNorm
 };
@@ -41,7 +42,11 @@ void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStrea
 // streams; the caller orders those streams around the call.  conv_tc_dgrad_s2_class_ctas = CTAs of the largest class.
 void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, const bf16* packed,
                       const ConvEpilogue& epi, bf16* dx, cudaStream_t stream,
-                      const cudaStream_t* class_streams = nullptr);
+                      const cudaStream_t* class_streams = nullptr, int ksize = 3);
+// 4x4 / stride 2 / pad 1 variant of the packing: wd = fp32 [Cin][16][Cout] (the CUDA-core dgrad layout), packed =
+// 16*Cout*Cin bf16 (four [Cin][2x2][Cout] class matrices); use with conv_tc_dgrad_s2(..., ksize = 4).
+// dup = 3: packed = 48*Cout*Cin bf16, every Cout run as [W_hi | W_hi | W_lo], for a dY split into hi | lo | hi (3*Cout channels).
+void pack_dgrad_s2_k4_tc(const float* wd, int Cout, int Cin, bf16* packed, cudaStream_t stream, int dup = 1);
 int conv_tc_dgrad_s2_class_ctas(int N, int H, int W, int Cin);
 
 // dW partials of a 3x3 / stride-1 / pad-1 convolution with Cin = Cout = 64:
@@ -56,9 +61,9 @@ void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stre
 
 // General tensor-core wgrad (3x3, pad 1, stride 1|2, Cin % 64 == 0, Cout % 64 == 0):
 //   part[z][co][(tap, ci)] fp32, z < conv_tc_wgrad_general_splits(...); reduce with wgrad_reduce_generic().
-int conv_tc_wgrad_general_splits(int N, int H, int W, int Cin, int Cout, int stride);
+int conv_tc_wgrad_general_splits(int N, int H, int W, int Cin, int Cout, int stride, int ksize = 3, int pad = 1);
 void conv_tc_wgrad_general(const bf16* x, const bf16* dy, int N, int H, int W, int Cin, int Cout, int stride,
-                           float* part, cudaStream_t stream);
+                           float* part, cudaStream_t stream, int ksize = 3, int pad = 1);
 
 // fp32 OIHW [Cout][Cin][k][k] -> bf16 [Cout][k*k][Cin] (fprop) and, if dgrad != nullptr,
 // bf16 [Cin][k*k][Cout] with the taps rotated by 180 degrees (dgrad of a stride-1 conv).

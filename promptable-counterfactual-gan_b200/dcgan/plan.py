@@ -11,6 +11,8 @@ shares its weight tensor ([Cin][Cout][k][k] in both views); its input gradient i
 BatchNorm runs in train mode in all three discriminator passes (separate batch statistics for real and fake,
 running buffers updated three times per iteration), exactly as the reference's module calls do.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -93,8 +95,11 @@ class _ConvT:
 
 
 class DcganPlan:
-    def __init__(self, batch, device, lr=2e-4, betas=(0.5, 0.999), use_graph=True):
+    def __init__(self, batch, device, lr=2e-4, betas=(0.5, 0.999), use_graph=True, tensor_cores=None):
+        """tensor_cores: the 64..512-channel convolutions (12 of the 15 conv passes' FLOPs) on the tcgen05 kernels with
+        bf16 operands; None = follow PCG_PRECISION (default bf16 -> on), False = exact fp32 on the CUDA cores."""
         self.B, self.lr, self.betas = batch, lr, betas
+        self.tc = (os.environ.get("PCG_PRECISION", "bf16") != "fp32") if tensor_cores is None else bool(tensor_cores)
         dev = self.dev = torch.device(device)
         B = batch
         z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
@@ -272,8 +277,12 @@ class DcganPlan:
 
     # ------------------------------------------------------------------ one iteration
     def _body(self):
-        self._d_phase()
-        self._g_phase()
+        K.set_conv_tensor_cores(self.tc)
+        try:
+            self._d_phase()
+            self._g_phase()
+        finally:
+            K.set_conv_tensor_cores(False)
 
     def _d_phase(self):
         B, D, G = self.B, self.D, self.G

@@ -41,6 +41,12 @@ def stat_scratch(C, device):
     return torch.zeros(int(L.pcg_stat_scratch_floats(C)), device=device)
 
 
+def set_conv_tensor_cores(on):
+    """Routes eligible conv_fprop / conv_dgrad / conv_wgrad calls to the tcgen05 kernels (bf16 operands, fp32
+    accumulation); off = exact fp32 on the CUDA cores.  See include/pcg.h pcg_set_conv_tensor_cores."""
+    _lib.check(_L().pcg_set_conv_tensor_cores(1 if on else 0))
+
+
 # ---------------------------------------------------------------- convolution / linear
 def pack_weights(w, k, wf=None, wd=None, perm_hw=0):
     """torch OIHW (or [out,in] with k=1) -> wf [Cout][k*k][Cin], wd [Cin][k*k][Cout]."""

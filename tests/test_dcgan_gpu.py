@@ -23,12 +23,12 @@ def l2(a, b):
     return ((a - b).norm() / (b.norm() + 1e-300)).item()
 
 
-def _fresh(B, graph):
+def _fresh(B, graph, tc=False):
     import pcg_b200  # noqa: F401
     from pcg_b200.dcgan import DcganPlan
     PG, PD = O.synth_params(O.g_shapes(), 5), O.synth_params(O.d_shapes(), 6)
     S = O.make_state(PG, O.buffers(O.g_shapes()), PD, O.buffers(O.d_shapes()))
-    plan = DcganPlan(B, "cuda", use_graph=graph)
+    plan = DcganPlan(B, "cuda", use_graph=graph, tensor_cores=tc)
     plan.G.load(PG)
     plan.D.load(PD)
     plan.refresh()
@@ -115,3 +115,50 @@ def test_mirror_modules_forward_and_train_loop():
     gl, dl = DC.train_dcgan(netG, netD, loader, cfg)
     assert len(gl) == 1 and gl[0] == gl[0] and dl[0] == dl[0]
     assert int(netG.main[1].num_batches_tracked) >= 3
+
+
+def test_dcgan_tensor_core_phases_match_oracle():
+    """The phase-by-phase parity test above with the 64..512-channel convolutions on the tcgen05 kernels in the bf16x3
+    (fp32-equivalent) operand mode of conv_auto.cu: the SAME tolerances as the fp32 CUDA-core plan (relative L2 1e-2 on
+    gradients) - plain bf16 operands (PCG_TC_TERMS=1) miss them by an order of magnitude on this network."""
+    from pcg_b200 import ops as K
+    B = 8
+    S, plan = _fresh(B, False, tc=True)
+    real, noise = O.synth_batch(B, 70)
+    sc, gr = O.dcgan_step(S, real, noise)
+    plan.real.view(-1).copy_(real.cuda().reshape(-1))
+    plan.noise.view(-1).copy_(noise.cuda().reshape(-1))
+    K.set_conv_tensor_cores(True)
+    try:
+        plan._d_phase()
+        torch.cuda.synchronize()
+        got = plan.scal.tolist()
+        for i, k in ((0, "errD"), (4, "D_x"), (5, "D_G_z1")):
+            assert abs(got[i] - sc[k]) <= 1e-4 * abs(sc[k]) + 1e-6, (k, got[i], sc[k])
+        assert l2(plan.ga[4].view(B, 1, 64, 64), gr["fake"]) < 1e-4
+        for k in gr["D"]:
+            assert l2(plan.D.g(k), gr["D"][k]) < 1e-2, (k, l2(plan.D.g(k), gr["D"][k]))
+        plan.D.load({k: v.detach() for k, v in S["D"].items()})
+        plan.refresh()
+        plan._g_phase()
+        torch.cuda.synchronize()
+    finally:
+        K.set_conv_tensor_cores(False)
+    got = plan.scal.tolist()
+    assert abs(got[1] - sc["errG"]) <= 1e-3 * abs(sc["errG"])
+    for k in gr["G"]:
+        assert l2(plan.G.g(k), gr["G"][k]) < 1e-2, (k, l2(plan.G.g(k), gr["G"][k]))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_dcgan_tensor_core_step_runs_in_graph(graph):
+    """Full iteration (D update, G through the updated D, G update) in tensor-core mode, eager and graph-replayed."""
+    B = 16
+    S, plan = _fresh(B, graph, tc=True)
+    for step in range(2):
+        real, noise = O.synth_batch(B, 170 + step)
+        sc, gr = O.dcgan_step(S, real, noise)
+        got = plan.step(real.cuda(), noise.cuda()).tolist()
+        tol = 1e-3 if step == 0 else 3e-2
+        for i, k in ((0, "errD"), (1, "errG"), (4, "D_x"), (5, "D_G_z1")):
+            assert abs(got[i] - sc[k]) <= tol * abs(sc[k]) + 1e-6, (step, k, got[i], sc[k])
