@@ -177,9 +177,16 @@ void bn_stats_partial(const T* y, long long M, int C, float* part, cudaStream_t 
 // Fixed-order parallel sum of column c over `nparts` partial rows by one warp (lane l takes rows
 // l, l+32, ... then a shuffle tree): deterministic and ~30x shorter dependency chain than a serial loop.
 __device__ __forceinline__ double warp_colsum(const float* __restrict__ part, int nparts, size_t stride, int c) {
-  double s = 0.0;
-  for (int i = threadIdx.x & 31; i < nparts; i += 32) s += (double)part[(size_t)i * stride + c];
-  return warp_sum(s);
+  // four loads in flight per lane: these kernels are pure L2-latency chains (a lane reads up to 19 rows)
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = threadIdx.x & 31;
+  for (; i + 96 < nparts; i += 128) {
+    const float a = part[(size_t)i * stride + c], b = part[(size_t)(i + 32) * stride + c];
+    const float d = part[(size_t)(i + 64) * stride + c], e = part[(size_t)(i + 96) * stride + c];
+    s0 += (double)a; s1 += (double)b; s2 += (double)d; s3 += (double)e;
+  }
+  for (; i < nparts; i += 32) s0 += (double)part[(size_t)i * stride + c];
+  return warp_sum((s0 + s1) + (s2 + s3));
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C,
