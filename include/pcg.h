@@ -248,6 +248,13 @@ int pcg_ce_loss(const float* logits, const long long* target, int B, int NC, flo
 int pcg_adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
                   float beta2, float eps, float grad_scale, void* stream);
 
+/* On-device input pipeline, replaces DataLoader + transforms.ToTensor() + transforms.Normalize((mean,), (std,)) of
+ * conditional_counteRGAN/mnist/data_utils.py:9-12,26 for a dataset kept resident in HBM as uint8 [N][HW] (HW % 16 == 0):
+ *   x[b][.] = (float(images[index[b]][.]) / 255 - mean) / std  (bit-identical to torchvision),  y[b] = labels[index[b]];
+ * index == NULL gathers rows 0..B-1, y / labels may be NULL. */
+int pcg_u8_batch(const unsigned char* images, const long long* labels, const long long* index, int B, int HW, float mean,
+                 float stdv, float* x, long long* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

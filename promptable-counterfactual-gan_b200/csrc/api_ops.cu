@@ -188,6 +188,12 @@ int pcg_ce_loss(const float* logits, const long long* target, int B, int NC, flo
   ce_loss(logits, target, B, NC, wgt, loss, dlogits, ST);
   PCG_API_END
 }
+int pcg_u8_batch(const unsigned char* images, const long long* labels, const long long* index, int B, int HW, float mean,
+                 float stdv, float* x, long long* y, void* stream) {
+  PCG_API_BEGIN
+  u8_batch(images, labels, index, B, HW, mean, stdv, x, y, ST);
+  PCG_API_END
+}
 int pcg_adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
                   float beta2, float eps, float grad_scale, void* stream) {
   PCG_API_BEGIN

@@ -394,4 +394,38 @@ void scale_cols(const float* dy, long long rows, int C, const float* scale, floa
   PCG_LAUNCH_CHECK();
 }
 
+// ---- on-device input pipeline (conditional_counteRGAN/mnist/data_utils.py:9-12,26): the uint8 dataset stays resident
+// in HBM; a batch is gathered through an index vector and normalised exactly as torchvision does it:
+// ToTensor = float(u8) / 255 (true division), Normalize = (x - mean) / std.  16 pixels (one 16-byte load) per thread.
+__global__ void u8_batch_kernel(const uint8_t* __restrict__ images, const long long* __restrict__ labels,
+                                const long long* __restrict__ index, int B, int HW, float mean, float stdv,
+                                float* __restrict__ x, long long* __restrict__ y) {
+  const int v16 = HW / 16;                                   // HW % 16 == 0 (784 = 49 * 16)
+  const long long total = (long long)B * v16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / v16), c = (int)(i - (long long)b * v16);
+    const long long src = index != nullptr ? index[b] : b;
+    const uint4 u = *reinterpret_cast<const uint4*>(images + src * HW + c * 16);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float4* dst = reinterpret_cast<float4*>(x + (long long)b * HW + c * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        f[j] = __fdiv_rn(__fdiv_rn((float)((w[k] >> (8 * j)) & 0xffu), 255.f) - mean, stdv);
+      dst[k] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+    if (c == 0 && y != nullptr) y[b] = labels[src];
+  }
+}
+void u8_batch(const uint8_t* images, const long long* labels, const long long* index, int B, int HW, float mean, float stdv,
+              float* x, long long* y, cudaStream_t s) {
+  PCG_PROFILE("input_pipeline", s);
+  PCG_REQUIRE(HW % 16 == 0 && (reinterpret_cast<uintptr_t>(images) & 15) == 0, "image size must be a multiple of 16 bytes");
+  u8_batch_kernel<<<blocks_for((long long)B * (HW / 16)), 256, 0, s>>>(images, labels, index, B, HW, mean, stdv, x, y);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 }  // namespace pcg

@@ -33,5 +33,8 @@ void softmax_bwd(const float* dy, const float* y, long long rows, int n, float t
 void bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,
              const float* rv, float eps, float* y, float* scale_out, cudaStream_t s);
 void scale_cols(const float* dy, long long rows, int C, const float* scale, float* dx, cudaStream_t s);
+// x[b][HW] = (float(images[index[b]][.]) / 255 - mean) / std ; y[b] = labels[index[b]]  (index == nullptr: identity)
+void u8_batch(const uint8_t* images, const long long* labels, const long long* index, int B, int HW, float mean, float stdv,
+              float* x, long long* y, cudaStream_t s);
 
 }  // namespace pcg
