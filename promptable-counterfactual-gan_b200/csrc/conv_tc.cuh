@@ -18,6 +18,13 @@ struct ConvEpilogue {
   float* out_f32 = nullptr;      // conv_tc_fprop / conv_tc_dgrad_s2 only: store the result as fp32 here (same shape)
   float* stats = nullptr;        // [grid][2*Cout] fp32 per-CTA partial (sum, sum of squares) of the
                                  // pre-rounding output values, for train-mode BatchNorm
+  // conv_tc64_fprop only - reduction pass of the BatchNorm backward that consumes this data gradient, fused into the
+  // epilogue: with v = the result, y = bn_y[pixel][c], g = v * act'(scale*y + shift):
+  //   stats[cta][c] = sum g,  stats[cta][64 + c] = sum g * (y - mean) * rstd        (bn_y == nullptr: off)
+  const bf16* bn_y = nullptr;
+  const float *bn_mean = nullptr, *bn_rstd = nullptr, *bn_scale = nullptr, *bn_shift = nullptr;
+  int bn_act = ACT_NONE;
+  float bn_slope = 0.2f;
 };
 
 // Number of CTAs conv_tc_fprop launches for a problem (rows of the `stats` partial buffer).

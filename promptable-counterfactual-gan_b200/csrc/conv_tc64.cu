@@ -27,7 +27,7 @@ constexpr int F_EPI_WARPS = 16;                  // 4 TMEM lane quarters x 4 col
 constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
 constexpr int F_EPI_WARP0 = 3;                  // warp0 TMA (input), warps 1-2 MMA (even / odd tiles), warps 3-18 epilogue,
 constexpr int F_THREADS = 32 * (F_EPI_WARP0 + F_EPI_WARPS + 1);   // warp19 TMA (epilogue operand)
-constexpr int F_TAIL_BYTES = (16 * 2 * 16 + 64) * 4 + 256;   // statistics scratch + bias, mbarriers + TMEM pointer
+constexpr int F_TAIL_BYTES = (16 * 2 * 16 + 64 + 4 * 64) * 4 + 256;   // statistics scratch, bias, BN constants; barriers   // statistics scratch + bias, mbarriers + TMEM pointer
 constexpr int SMEM_LIMIT = 232448;               // 227 KB opt-in maximum per CTA
 
 struct F64Params {
@@ -35,6 +35,10 @@ struct F64Params {
   int in_stages, in_stage_bytes, out_tile_bytes; // shared-memory ring geometry (host-computed)
   int n_extra;                                   // 1: one epilogue operand tile per output tile arrives by TMA
   int extra_is_add;                              // that operand is add_src (else act_ref)
+  int bn_bwd;                                    // the operand is the BatchNorm input y: fused backward reduction
+  const float *bn_mean, *bn_rstd, *bn_scale, *bn_shift;
+  int bn_act;
+  float bn_slope;
   const float* bias;
   int act;
   float slope;
@@ -126,7 +130,7 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   uint8_t* sout = sin + p.in_stages * p.in_stage_bytes; // output staging, 2 slots
   uint8_t* sx = sout + 2 * p.out_tile_bytes;            // epilogue operand ring, 2 slots (if n_extra)
   float* stats_smem = reinterpret_cast<float*>(sx + (p.n_extra ? 2 : 0) * p.out_tile_bytes);   // [16][2][16] + bias[64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + (16 * 2 * 16 + 64) * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + (16 * 2 * 16 + 64 + 4 * 64) * 4);
   uint64_t* full = bars;                 // [4]
   uint64_t* empty = bars + 4;            // [4]
   uint64_t* wfull = bars + 8;            // [1]
@@ -252,9 +256,20 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const bool issuer = threadIdx.x == F_EPI_WARP0 * 32;
     // bias lives in shared memory (read as broadcast float4) to keep registers for the statistics
     float* bias_s = stats_smem + 16 * 2 * 16;       // [64], behind the [16][2][16] statistics block
+    float* bnc = bias_s + 64;                       // [4][64]: scale, shift, mean, rstd
     if (e == 0) {
       bias_s[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
       bias_s[lane + 32] = p.bias ? __ldg(p.bias + lane + 32) : 0.f;
+    }
+    if (e == 1 && p.bn_bwd) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        bnc[c] = __ldg(p.bn_scale + c);
+        bnc[64 + c] = __ldg(p.bn_shift + c);
+        bnc[128 + c] = __ldg(p.bn_mean + c);
+        bnc[192 + c] = __ldg(p.bn_rstd + c);
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
     // BatchNorm statistics: per-thread running sums of the raw accumulators over all tiles of this CTA; the bias is
@@ -265,7 +280,7 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     int nvalid = 0;
     const bool want_stats = p.stats != nullptr;
     const bf16* g_add = (p.n_extra && p.extra_is_add) ? nullptr : p.add_src;    // operands still read from global
-    const bf16* g_ref = (p.n_extra && !p.extra_is_add) ? nullptr : p.act_ref;
+    const bf16* g_ref = (p.n_extra && !p.extra_is_add && !p.bn_bwd) ? nullptr : p.act_ref;
     const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
@@ -311,15 +326,41 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           for (int j2 = 0; j2 < 2; ++j2) {
             const uint4 u = *reinterpret_cast<const uint4*>(xt + soff[j2]);
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            if (p.bn_bwd) {
+              // the operand is y of the BatchNorm this gradient enters next: g = v * act'(scale*y + shift);
+              // accumulate sum g and sum g*(y - mean) (scaled by rstd once, at the end).  Constants come as
+              // warp-broadcast 16-byte shared-memory loads (6 per 8 columns), not per element.
+              float ca[8], cb[8], cm[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float lo = __uint_as_float(w4[t] << 16), hi = __uint_as_float(w4[t] & 0xffff0000u);
-              if (p.extra_is_add) {
-                v[j2 * 8 + t * 2] += lo;
-                v[j2 * 8 + t * 2 + 1] += hi;
-              } else {
-                v[j2 * 8 + t * 2] *= (lo > 0.f ? 1.f : neg);
-                v[j2 * 8 + t * 2 + 1] *= (hi > 0.f ? 1.f : neg);
+              for (int h = 0; h < 2; ++h) {
+                const int c = col0 + j2 * 8 + h * 4;
+                const float4 fa = *reinterpret_cast<const float4*>(bnc + c);
+                const float4 fb = *reinterpret_cast<const float4*>(bnc + 64 + c);
+                const float4 fm = *reinterpret_cast<const float4*>(bnc + 128 + c);
+                ca[h * 4] = fa.x; ca[h * 4 + 1] = fa.y; ca[h * 4 + 2] = fa.z; ca[h * 4 + 3] = fa.w;
+                cb[h * 4] = fb.x; cb[h * 4 + 1] = fb.y; cb[h * 4 + 2] = fb.z; cb[h * 4 + 3] = fb.w;
+                cm[h * 4] = fm.x; cm[h * 4 + 1] = fm.y; cm[h * 4 + 2] = fm.z; cm[h * 4 + 3] = fm.w;
+              }
+              const float neg_bn = p.bn_act == ACT_LRELU ? p.bn_slope : (p.bn_act == ACT_RELU ? 0.f : 1.f);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
+                const int j = j2 * 8 + t;
+                const float g = fmaf(yv, ca[t], cb[t]) > 0.f ? v[j] : v[j] * neg_bn;
+                acc_s[j] += g;
+                acc_q[j] = fmaf(g, yv - cm[t], acc_q[j]);
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float lo = __uint_as_float(w4[t] << 16), hi = __uint_as_float(w4[t] & 0xffff0000u);
+                if (p.extra_is_add) {
+                  v[j2 * 8 + t * 2] += lo;
+                  v[j2 * 8 + t * 2 + 1] += hi;
+                } else {
+                  v[j2 * 8 + t * 2] *= (lo > 0.f ? 1.f : neg);
+                  v[j2 * 8 + t * 2 + 1] *= (hi > 0.f ? 1.f : neg);
+                }
               }
             }
           }
@@ -371,7 +412,7 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           u.w = pack2(v[j2 * 8 + 6], v[j2 * 8 + 7]);
           *reinterpret_cast<uint4*>(st + soff[j2]) = u;
         }
-        if (want_stats) {           // statistics are only requested with act == NONE and no add/act_ref
+        if (want_stats && !p.bn_bwd) {   // forward statistics are only requested with act == NONE and no add/act_ref
           ++nvalid;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -396,11 +437,16 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (want_stats) {
       // sum(a+b) = sum a + n b ; sum (a+b)^2 = sum a^2 + 2 b sum a + n b^2
       const float nv = (float)nvalid;
+      if (p.bn_bwd) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float b = bias_s[col0 + j], sa = acc_s[j];
-        acc_q[j] = acc_q[j] + 2.f * b * sa + nv * b * b;
-        acc_s[j] = sa + nv * b;
+        for (int j = 0; j < 16; ++j) acc_q[j] *= bnc[192 + col0 + j];      // sum g*(y - mean) -> sum g*xhat
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float b = bias_s[col0 + j], sa = acc_s[j];
+          acc_q[j] = acc_q[j] + 2.f * b * sa + nv * b * b;
+          acc_s[j] = sa + nv * b;
+        }
       }
       const float ts = colsum16(acc_s, lane);      // lanes l, l^16 hold column col0 + (l & 15) over this warp's 32 rows
       const float tq = colsum16(acc_q, lane);
@@ -443,10 +489,17 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.stats = epi.stats; p.variant = g_variant;
   PCG_REQUIRE(epi.stats == nullptr || (epi.act == ACT_NONE && epi.add_src == nullptr && p.act_ref == nullptr),
               "BatchNorm statistics are taken of (accumulator + bias) only");
-  // one epilogue operand travels by TMA (the residual if there is one, else the activation reference)
-  p.n_extra = (p.add_src != nullptr || p.act_ref != nullptr) ? 1 : 0;
-  p.extra_is_add = p.add_src != nullptr ? 1 : 0;
-  const bf16* extra = p.add_src != nullptr ? p.add_src : p.act_ref;
+  p.bn_bwd = epi.bn_y != nullptr ? 1 : 0;
+  p.bn_mean = epi.bn_mean; p.bn_rstd = epi.bn_rstd; p.bn_scale = epi.bn_scale; p.bn_shift = epi.bn_shift;
+  p.bn_act = epi.bn_act; p.bn_slope = epi.bn_slope;
+  PCG_REQUIRE(!p.bn_bwd || (epi.stats != nullptr && epi.bias == nullptr && epi.act == ACT_NONE && p.add_src == nullptr &&
+                            p.act_ref == nullptr && epi.bn_mean && epi.bn_rstd && epi.bn_scale && epi.bn_shift),
+              "fused BatchNorm-backward reduction: partial buffer and the four per-channel vectors are required");
+  // one epilogue operand travels by TMA (the BatchNorm input, else the residual if there is one, else the activation
+  // reference)
+  p.n_extra = (p.bn_bwd || p.add_src != nullptr || p.act_ref != nullptr) ? 1 : 0;
+  p.extra_is_add = (!p.bn_bwd && p.add_src != nullptr) ? 1 : 0;
+  const bf16* extra = p.bn_bwd ? epi.bn_y : (p.add_src != nullptr ? p.add_src : p.act_ref);
   auto round1k = [](int b) { return (b + 1023) / 1024 * 1024; };
   p.in_stage_bytes = round1k((p.R + 2) * p.WP * 128);
   p.out_tile_bytes = round1k(p.R * p.W * 128);

@@ -449,8 +449,12 @@ struct MnistPlan : PlanBase {
     if (side_c) cudaStreamDestroy(side_c);
     for (auto a : aux) if (a) cudaStreamDestroy(a);
   }
+  // Per-launcher profiling (bench.py roofline pass) times kernels one at a time: everything stays on the caller's stream.
+  cudaStream_t wstream(cudaStream_t s) const { return g_profile_on ? s : side_w; }
+  cudaStream_t cstream(cudaStream_t s) const { return g_profile_on ? s : side_c; }
   // `to` continues after everything enqueued on `from` so far (a graph edge under stream capture)
   void after(cudaStream_t from, cudaStream_t to) {
+    if (from == to) return;
     cudaEvent_t e = ev_pool[ev_next++ % ev_pool.size()];
     PCG_CHECK_CUDA(cudaEventRecord(e, from));
     PCG_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
@@ -680,6 +684,7 @@ struct MnistPlan : PlanBase {
   // Weight gradients run on side_w: each only needs dg[l] (written once per pass) and a forward activation, so the
   // data-gradient chain on `s` never waits for them; the caller joins side_w before the optimizer step.
   void d_bwd(int n, bool wg, int in_ch, cudaStream_t s) {
+    cudaStream_t side_w = wstream(s);
     d_head_bwd<T>(dz[3], ddlogit, n, 4, 256, d_head_w, 0.2f, dg[3], wg ? d_dhead_w : nullptr, wg ? d_dhead_b : nullptr,
                   stat_part2, s);
     for (int l = 3; l >= 1; --l) {
@@ -700,6 +705,7 @@ struct MnistPlan : PlanBase {
 
   // ---------------------------------------------------------------- phases
   void step_d_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override {
+    cudaStream_t side_w = wstream(s);
     g_fwd(in.x, in.target, in.mask, true, s);
     l1_finalize(l1_part, STAT_PARTS, 1.f / (float)MG, scal + PCG_S_REG_L1, s);   // writes REG_L1, MASK_PEN
     d_input<T>(in.x, d_embed, in.y, B, 784, a0, s);
@@ -734,6 +740,7 @@ struct MnistPlan : PlanBase {
   }
 
   void step_g_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override {
+    cudaStream_t side_w = wstream(s), side_c = cstream(s);
     // --- adversarial path through the UPDATED discriminator (trainer.py:116-117)
     // --- classifier path (trainer.py:118) on side_c: independent of the discriminator path until the two input
     //     gradients meet in residual_head_bwd; both are chains of small kernels that do not fill the GPU alone
@@ -786,7 +793,22 @@ struct MnistPlan : PlanBase {
       bn_bwd_apply<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, q2.gamma, c12, 0.1f, ACT_NONE, 0.f, MG, ch, dy2[i],
                       stat_part2, s);
       colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c2[i].db, s);
-      {
+      // data gradient of conv2; on the tensor-core path its epilogue also does the reduction pass of BN1's backward
+      // (sum g, sum g*xhat with g = dz1 * LReLU'(BN1(y1))), which saves one full read of dz1 and y1
+      int bn1_parts = 0;
+      if constexpr (kBf16) {
+        if (g_c2[i].tc_dgrad && g_c2[i].tc64) {
+          ProfTag _tag(g_c2[i].tag_d.c_str());
+          const BN& qb = bn1[i];
+          ConvEpilogue c;
+          c.stats = stat_part;
+          c.bn_y = y1[i]; c.bn_mean = qb.mean; c.bn_rstd = qb.rstd; c.bn_scale = qb.scale; c.bn_shift = qb.shift;
+          c.bn_act = ACT_LRELU; c.bn_slope = 0.2f;
+          conv_tc64_fprop(dy2[i], B, 28, 28, g_c2[i].tcd, c, dz1, s);
+          bn1_parts = conv_tc64_grid(B, 28, 28);
+        }
+      }
+      if (bn1_parts == 0) {
         GenEpilogue<T> e;
         dgrad<T, T>(g_c2[i], dy2[i], e, dz1, s);
       }
@@ -796,8 +818,11 @@ struct MnistPlan : PlanBase {
       wgrad<T, T>(g_c2[i], z1[i], dy2[i], side_w);
       // LeakyReLU + BN1 backward
       const BN& q1 = bn1[i];
-      bn_bwd_partial<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, 1.f, ACT_LRELU, 0.2f, MG, ch, stat_part, s);
-      bn_bwd_finalize(stat_part, STAT_PARTS, MG, ch, q1.dgamma, q1.dbeta, c12, s);
+      if (bn1_parts == 0) {
+        bn_bwd_partial<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, 1.f, ACT_LRELU, 0.2f, MG, ch, stat_part, s);
+        bn1_parts = STAT_PARTS;
+      }
+      bn_bwd_finalize(stat_part, bn1_parts, MG, ch, q1.dgamma, q1.dbeta, c12, s);
       bn_bwd_apply<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, q1.gamma, c12, 1.f, ACT_LRELU, 0.2f, MG, ch,
                       dy1[i], stat_part2, s);
       colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c1[i].db, s);
