@@ -422,6 +422,11 @@ def run_other(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from pcg_b200 import _lib
+    dist = None
+    if world > 1 and args.workload == "dcgan":       # data parallel (the plan picks the process group up); the MLP
+        import torch.distributed as dist             # configs are replicas only
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     native_step, cpu_step, cb = _other_setup(args.workload, B, dev)
     n0 = _lib.launch_count()
     native_step(0)                                   # eager pass + graph capture
@@ -429,6 +434,8 @@ def run_other(args):
     launches = _lib.launch_count() - n0
     for i in range(max(args.warmup, 3)):
         native_step(i)
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -436,8 +443,14 @@ def run_other(args):
     for i in range(args.steps):
         sc = native_step(i)
     e1.record()
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    if dist is not None:                             # max over ranks
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
     clk = clocks.stop() if clocks else None
     value = B * world * args.steps / (ms * 1e-3)      # replicas only: every rank runs the same step
     # e2e: the same step with the scalars read back every step (inputs of these plans are copied in by step())
@@ -446,6 +459,9 @@ def run_other(args):
     for i in range(args.steps):
         host = native_step(i).cpu()
     e2e = B * world * args.steps / (time.perf_counter() - t0)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     cpu = None
@@ -474,7 +490,8 @@ def run_other(args):
                       "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32-equivalent)" if args.workload == "dcgan" else "f32",
                       "data": "synthetic",
-                      "config": {"workload": spec["name"], "global_batch": B * world, "parallelism": "replicas",
+                      "config": {"workload": spec["name"], "global_batch": B * world,
+                                 "parallelism": ("dp%d" % world) if args.workload == "dcgan" else "replicas",
                                  "cuda_graph": True, "l2": "working set fits L2 for the MLP configs (state < 1 MB); "
                                  "4 rotating input batches"},
                       "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": 0,

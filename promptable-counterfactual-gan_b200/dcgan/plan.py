@@ -100,6 +100,12 @@ class DcganPlan:
         bf16 operands; None = follow PCG_PRECISION (default bf16 -> on), False = exact fp32 on the CUDA cores."""
         self.B, self.lr, self.betas = batch, lr, betas
         self.tc = (os.environ.get("PCG_PRECISION", "bf16") != "fp32") if tensor_cores is None else bool(tensor_cores)
+        # data parallel (SURVEY §8e): one process per GPU, per-replica BatchNorm statistics, gradients summed by an
+        # all-reduce before each optimizer step (D's before the G phase, which sees the updated D), 1/world folded
+        # into Adam
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist is not None else 1
         dev = self.dev = torch.device(device)
         B = batch
         z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
@@ -276,17 +282,37 @@ class DcganPlan:
             dout = self.ddy[i - 1]
 
     # ------------------------------------------------------------------ one iteration
-    def _body(self):
+    def _tc(self, fn):
         K.set_conv_tensor_cores(self.tc)
         try:
-            self._d_phase()
-            self._g_phase()
+            fn()
         finally:
             K.set_conv_tensor_cores(False)
 
+    def _body(self):
+        def both():
+            self._d_phase()
+            self._g_phase()
+        self._tc(both)
+
+    def _segments(self):
+        """The iteration cut at the two gradient reductions: [D grads] all-reduce [D update, G grads] all-reduce
+        [G update]."""
+        def mid():
+            self._d_update()
+            self._g_grads()
+        return [lambda: self._tc(self._d_grads), lambda: self._tc(mid), lambda: self._tc(self._g_update)]
+
     def _d_phase(self):
+        self._d_grads()
+        self._d_update()
+
+    def _g_phase(self):
+        self._g_grads()
+        self._g_update()
+
+    def _d_grads(self):
         B, D, G = self.B, self.D, self.G
-        b1, b2 = self.betas
         g1 = lambda n: D.g(n)  # noqa: E731
         g2 = lambda n: D._view(self.D_grad2, n)  # noqa: E731
         # (1) D on real (:147-153)
@@ -300,19 +326,26 @@ class DcganPlan:
         self._d_bwd(self.ga[4], 1, g2, True, False)
         K.binary(D.grad, self.D_grad2, K.ADD, D.grad)                 # gradients accumulate over the two backward calls
         K.combine([(1.0, self.scal[2:3]), (1.0, self.scal[3:4])], self.scal[0:1])
-        K.adam(D.data, D.grad, D.m, D.v, D.step, self.lr, b1, b2)     # optimizerD.step() :164
+
+    def _d_update(self):
+        D = self.D
+        b1, b2 = self.betas
+        K.adam(D.data, D.grad, D.m, D.v, D.step, self.lr, b1, b2, grad_scale=1.0 / self.world)   # optimizerD.step() :164
         self._pack_d()
 
-    def _g_phase(self):
+    def _g_grads(self):
         B, D, G = self.B, self.D, self.G
-        b1, b2 = self.betas
         g2 = lambda n: D._view(self.D_grad2, n)  # noqa: E731
         # (2) G through the updated D (:169-175)
         self._d_fwd(self.ga[4], 1)
         K.gan_loss(self.dy[1][4].view(-1), K.GAN_BCE, 1.0, self.scal[1:2], self.dz, out_aux=self.scal[6:7])
         self._d_bwd(self.ga[4], 1, g2, False, True)
         self._g_bwd()
-        K.adam(G.data, G.grad, G.m, G.v, G.step, self.lr, b1, b2)
+
+    def _g_update(self):
+        G = self.G
+        b1, b2 = self.betas
+        K.adam(G.data, G.grad, G.m, G.v, G.step, self.lr, b1, b2, grad_scale=1.0 / self.world)
         self._pack_g()
 
     def _state(self):
@@ -325,21 +358,47 @@ class DcganPlan:
         """real [B,1,64,64] (NCHW == NHWC for one channel), noise [B,100,1,1]; returns the scalar block."""
         self.real.view(-1).copy_(real.reshape(-1), non_blocking=True)
         self.noise.view(-1).copy_(noise.reshape(-1), non_blocking=True)
+        if self.dist is not None:
+            return self._step_dp()
         if not self.use_graph:
             self._body()
             return self.scal
         if self.graph is None:
-            snap = [t.clone() for t in self._state()]
-            self._body()
-            torch.cuda.synchronize()
-            for dst, src in zip(self._state(), snap):
-                dst.copy_(src)
-            self.refresh()
-            torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                self._body()
+            self._dry_run()
+            self.graph = self._capture(self._body)
         self.graph.replay()
+        return self.scal
+
+    def _dry_run(self):
+        """One eager iteration on a state snapshot (sizes the library scratch, sets function attributes)."""
+        snap = [t.clone() for t in self._state()]
+        self._body()
+        torch.cuda.synchronize()
+        for dst, src in zip(self._state(), snap):
+            dst.copy_(src)
+        self.refresh()
+        torch.cuda.synchronize()
+
+    @staticmethod
+    def _capture(fn):
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            fn()
+        return g
+
+    def _step_dp(self):
+        segs = self._segments()
+        if self.use_graph:
+            if self.graph is None:
+                self._dry_run()
+                self.graph = [self._capture(f) for f in segs]
+            segs = [g.replay for g in self.graph]
+        segs[0]()
+        self.dist.all_reduce(self.D.grad)
+        segs[1]()
+        self.dist.all_reduce(self.G.grad)
+        segs[2]()
         return self.scal
 
     # ------------------------------------------------------------------ module forwards
