@@ -122,6 +122,29 @@ struct PackTable {
   }
 };
 
+// Eval-mode BatchNorm folded into the convolution in front of it (inference forward):
+//   BN(conv(x) + b) * extra = conv'(x) + b'  with  w'[co] = w[co] * s[co] * extra,  b'[co] = extra * ((b[co] - rm[co]) * s[co] + beta[co]),
+//   s = gamma / sqrt(running_var + eps).  One launch folds every (conv, BN) pair of the generator's residual blocks
+//   into bf16 [Cout][tap][Cin] weights + fp32 biases, so the eval forward is conv -> conv with fused epilogues only.
+struct FoldDesc {
+  const float *w, *b, *gamma, *beta, *rm, *rv;
+  bf16* wq;
+  float* bq;
+  float extra;
+  int Cout, Cin, taps;
+};
+__global__ void __launch_bounds__(256) fold_bn_kernel(const FoldDesc* __restrict__ table, float eps) {
+  const FoldDesc L = table[blockIdx.y];
+  const int total = L.Cout * L.Cin * L.taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % L.taps, ci = (i / L.taps) % L.Cin, co = i / (L.taps * L.Cin);
+    const float sc = L.gamma[co] / sqrtf(L.rv[co] + eps) * L.extra;
+    L.wq[((size_t)co * L.taps + tap) * L.Cin + ci] = __float2bfloat16_rn(L.w[i] * sc);
+    if (tap == 0 && ci == 0)
+      L.bq[co] = L.extra * ((L.b[co] - L.rm[co]) * (L.gamma[co] / sqrtf(L.rv[co] + eps)) + L.beta[co]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct ConvLayer {
@@ -138,6 +161,8 @@ struct ConvLayer {
   bool tc_fprop = false, tc_dgrad = false, tc_wgrad = false, tc_dgrad_s2 = false;
   bool tc64 = false;          // 64->64 3x3 s1 p1: halo-tile kernels (conv_tc64.cu)
   bool tc_wgrad_gen = false;  // general tensor-core wgrad (conv_tc.cu)
+  bf16* tcf_eval = nullptr;   // eval-mode BatchNorm folded in (fold_bn_kernel)
+  float* b_eval = nullptr;
   bool to1_fprop = false;     // Cout == 1: conv_to1 on tcf (conv_small.cu)
   bool to1_dgrad = false;     // Cin <= 4: one input channel's data gradient = conv_to1 on a row of tcd
   bool few_fprop = false;     // Cin <= 3: conv_few on tcf
@@ -440,6 +465,7 @@ struct MnistPlan : PlanBase {
     scal_tmp = alloc<float>(16);
     dbg["dinp"] = {dinp, {MG * 3, PCG_F32}};
     build_pack_tables();
+    build_fold_table();
   }
 
   ~MnistPlan() override {
@@ -621,6 +647,55 @@ struct MnistPlan : PlanBase {
     pack_d = make_pack_table(d);
     pack_c = make_pack_table({c_conv[0].desc(false), c_conv[1].desc(false), c_conv[2].desc(false), c_fc1.desc(false),
                               c_fc2.desc(false)});
+  }
+  // ---- eval-mode forward with folded BatchNorm (tensor-core plans with the halo-tile kernels only)
+  FoldDesc* fold_dev = nullptr;
+  int fold_n = 0;
+  void build_fold_table() {
+    if (!kBf16 || nres == 0 || !g_c1[0].tc64) return;
+    std::vector<FoldDesc> v;
+    for (int i = 0; i < nres; ++i)
+      for (int j = 0; j < 2; ++j) {
+        ConvLayer<T>& L = j ? g_c2[i] : g_c1[i];
+        const BN& q = j ? bn2[i] : bn1[i];
+        L.tcf_eval = alloc<bf16>((size_t)ch * ch * 9);
+        L.b_eval = alloc<float>(ch);
+        FoldDesc d;
+        d.w = L.w; d.b = L.b; d.gamma = q.gamma; d.beta = q.beta; d.rm = q.running_mean; d.rv = q.running_var;
+        d.wq = L.tcf_eval; d.bq = L.b_eval; d.extra = j ? 0.1f : 1.f;      // generator.py:22: x + 0.1 * out
+        d.Cout = ch; d.Cin = ch; d.taps = 9;
+        v.push_back(d);
+      }
+    fold_n = (int)v.size();
+    fold_dev = alloc<FoldDesc>(v.size());
+    PCG_CHECK_CUDA(cudaMemcpy(fold_dev, v.data(), v.size() * sizeof(FoldDesc), cudaMemcpyHostToDevice));
+  }
+  void g_fwd_eval(const float* x, const long long* target, const float* mask, cudaStream_t s) {
+    {
+      PCG_PROFILE("pack_weights", s);
+      fold_bn_kernel<<<dim3(36, fold_n), 256, 0, s>>>(fold_dev, 1e-5f);
+      PCG_COUNT_LAUNCH();
+      PCG_LAUNCH_CHECK();
+    }
+    g_input<T>(x, g_embed, target, mask, B, 784, inp3, s);
+    GenEpilogue<T> e;
+    e.bias = g_in.b; e.act = ACT_LRELU; e.slope = 0.2f;
+    fprop<T, T>(g_in, inp3, e, h[0], s);
+    if constexpr (kBf16) {
+      for (int i = 0; i < nres; ++i) {
+        ConvEpilogue e1;                               // z1 = LReLU(BN1(conv1(h)))
+        e1.bias = g_c1[i].b_eval; e1.act = ACT_LRELU; e1.slope = 0.2f;
+        conv_tc64_fprop(h[i], B, 28, 28, g_c1[i].tcf_eval, e1, z1[i], s);
+        ConvEpilogue e2;                               // h' = h + 0.1 * BN2(conv2(z1))
+        e2.bias = g_c2[i].b_eval; e2.add_src = h[i];
+        conv_tc64_fprop(z1[i], B, 28, 28, g_c2[i].tcf_eval, e2, h[i + 1], s);
+      }
+    }
+    GenEpilogue<T> em; em.bias = g_mid.b; em.act = ACT_LRELU; em.slope = 0.2f;
+    fprop<T, T>(g_mid, h[nres], em, hm, s);
+    GenEpilogue<float> eo; eo.bias = g_out.b;
+    fprop<T, float>(g_out, hm, eo, cimg, s);
+    residual_head_fwd(cimg, x, mask, cfg.residual_scaling, MG, raw, masked, x_cf, l1_part, s);
   }
   void refresh_g(cudaStream_t s) { pack_g.launch(s); }
   void refresh_d(cudaStream_t s) { pack_d.launch(s); }
@@ -863,7 +938,8 @@ struct MnistPlan : PlanBase {
   // ---------------------------------------------------------------- module forwards
   void g_forward(const float* x, const long long* target, const float* mask, int training, float* raw_o, float* masked_o,
                  cudaStream_t s) override {
-    g_fwd(x, target, mask, training != 0, s);
+    if (training == 0 && fold_n > 0) g_fwd_eval(x, target, mask, s);
+    else g_fwd(x, target, mask, training != 0, s);
     PCG_CHECK_CUDA(cudaMemcpyAsync(raw_o, raw, MG * sizeof(float), cudaMemcpyDeviceToDevice, s));
     PCG_CHECK_CUDA(cudaMemcpyAsync(masked_o, masked, MG * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
