@@ -189,16 +189,43 @@ __device__ __forceinline__ double warp_colsum(const float* __restrict__ part, in
   return warp_sum((s0 + s1) + (s2 + s3));
 }
 
+// One 128-thread block per channel: every thread reads at most ceil(nparts/128) rows per column (one L2 round trip
+// instead of a 19-deep chain per lane), then a fixed-order tree (warp shuffles, 4 warps through shared memory):
+// deterministic.  These kernels sit on the critical path 36 times per step.
+constexpr int FIN_THREADS = 128;
+template <int NS>
+__device__ __forceinline__ void block_colsum(const float* __restrict__ part, int nparts, size_t stride,
+                                             const int (&cols)[NS], double (&out)[NS]) {
+  __shared__ double red[FIN_THREADS / 32][NS];
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += FIN_THREADS) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) s[k] += (double)part[(size_t)i * stride + cols[k]];
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = warp_sum(s[k]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) red[threadIdx.x >> 5][k] = s[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NS; ++k) out[k] = (red[0][k] + red[1][k]) + (red[2][k] + red[3][k]);
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, long long* nbt,
                                    float* mean_o, float* rstd_o, float* scale, float* shift) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
+  const int c = blockIdx.x;                                        // one block per channel
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
-  if (c >= C) return;
-  const double s = warp_colsum(part, nparts, 2 * (size_t)C, c);
-  const double q = warp_colsum(part, nparts, 2 * (size_t)C, C + c);
-  if ((threadIdx.x & 31) != 0) return;
+  const int cols[2] = {c, C + c};
+  double sums[2];
+  block_colsum<2>(part, nparts, 2 * (size_t)C, cols, sums);
+  const double s = sums[0], q = sums[1];
+  if (threadIdx.x != 0) return;
   const double mean = s / (double)M;
   double var = q / (double)M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -219,7 +246,7 @@ void bn_finalize(const float* part, int nparts, long long M, int C, const float*
                  float eps, float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
                  float* rstd, float* scale, float* shift, cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  bn_finalize_kernel<<<cdiv(C, 8), 256, 0, s>>>(part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
+  bn_finalize_kernel<<<C, FIN_THREADS, 0, s>>>(part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
                                                running_var, nbt, mean, rstd, scale, shift);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -419,11 +446,12 @@ void bn_bwd_partial(const T* dsrc, const T* y, const float* mean, const float* r
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, float* dgamma,
                                        float* dbeta, float* c12) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= C) return;
-  const double s1 = warp_colsum(part, nparts, 2 * (size_t)C, c);
-  const double s2 = warp_colsum(part, nparts, 2 * (size_t)C, C + c);
-  if ((threadIdx.x & 31) != 0) return;
+  const int c = blockIdx.x;
+  const int cols[2] = {c, C + c};
+  double sums[2];
+  block_colsum<2>(part, nparts, 2 * (size_t)C, cols, sums);
+  const double s1 = sums[0], s2 = sums[1];
+  if (threadIdx.x != 0) return;
   dbeta[c] = (float)s1;
   dgamma[c] = (float)s2;
   c12[c] = (float)(s1 / (double)M);
@@ -433,7 +461,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
 void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* dgamma, float* dbeta, float* c12,
                      cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  bn_bwd_finalize_kernel<<<cdiv(C, 8), 256, 0, s>>>(part, nparts, M, C, dgamma, dbeta, c12);
+  bn_bwd_finalize_kernel<<<C, FIN_THREADS, 0, s>>>(part, nparts, M, C, dgamma, dbeta, c12);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -508,14 +536,15 @@ void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rst
 }
 
 __global__ void colsum_finalize_kernel(const float* __restrict__ part, int nparts, int stride, int C, float* out) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= C) return;
-  const double s = warp_colsum(part, nparts, (size_t)stride, c);
-  if ((threadIdx.x & 31) == 0) out[c] = (float)s;
+  const int c = blockIdx.x;
+  const int cols[1] = {c};
+  double sums[1];
+  block_colsum<1>(part, nparts, (size_t)stride, cols, sums);
+  if (threadIdx.x == 0) out[c] = (float)sums[0];
 }
 void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  colsum_finalize_kernel<<<cdiv(C, 8), 256, 0, s>>>(part, nparts, stride, C, out);
+  colsum_finalize_kernel<<<C, FIN_THREADS, 0, s>>>(part, nparts, stride, C, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
