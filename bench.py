@@ -268,8 +268,16 @@ def run_native(args):
             tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tp):                  # dram bytes (read + write) per launch from the committed ncu capture
                 traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
+            # the 6 data-gradient launches whose epilogue also does a BatchNorm-backward reduction are epilogue-paced;
+            # the other 20 (13 forward, 7 data gradient) are the plain convolution
+            plain = [v for n_, v in detail.items() if n_ in ("conv_tc64_fprop:g.res.fprop", "conv_tc64_fprop:g.res.dgrad")]
+            plain_ms = sum(v["ms"] for v in plain)
+            plain_n = sum(v["launches"] for v in plain)
+            frac_plain = (plain_n * CONV_FLOPS / (plain_ms * 1e-3) / 1e12 / peak) if plain_ms > 0 else None
             roof = {"bound": "tensor",
                     "kernel": "conv_tc64_fprop_kernel (tcgen05 halo-tile conv 64->64, 13 fprop + 13 dgrad per step)",
+                    "frac_plain_conv_launches": frac_plain,
+                    "plain_conv_avg_launch_us": (plain_ms / plain_n * 1e3) if plain_n else None,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                     "algorithmic_bytes_per_launch": 2 * BATCH * 784 * 64 * 2,

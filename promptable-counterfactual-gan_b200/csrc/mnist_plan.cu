@@ -873,7 +873,7 @@ struct MnistPlan : PlanBase {
       int bn1_parts = 0;
       if constexpr (kBf16) {
         if (g_c2[i].tc_dgrad && g_c2[i].tc64) {
-          ProfTag _tag(g_c2[i].tag_d.c_str());
+          ProfTag _tag("g.res.dgrad_bnred");
           const BN& qb = bn1[i];
           ConvEpilogue c;
           c.stats = stat_part;
