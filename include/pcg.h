@@ -85,6 +85,27 @@ int pcg_conv_tc64_wgrad(const void* x, const void* dy, int N, int H, int W, floa
                         void* stream);
 int pcg_conv_tc64_set_variant(int v);
 
+/* Skinny layers of the MNIST step on the warp-level tensor path (conv_small.cu); 3x3, pad 1, NHWC bf16 activations.
+ * Replace nn.Conv2d forward / ConvolutionBackward0 of conv_in (3->64), conv_out (64->1) (generator.py:39,50),
+ * Discriminator main.0 (2->64, stride 2; discriminator.py:15) and CNNClassifier conv.0 (1->32; classifier.py:8).
+ *   pcg_conv_to1     out[N*H*W] f32 = bias + sum_{tap,c} in[..][c] * w9[tap][c]                (Cin = 32 | 64)
+ *   pcg_conv_few     out bf16 [M][Cout] = epi(sum in[..][c] * wnk[co][tap*Cs + c]), Cs = 1..3, Cout = 32 | 64, stride 1|2;
+ *                    epi: + bias, act, * act'(act_ref)
+ *   pcg_dgrad_s2_to1 dx[N][H][W] f32 = one input channel of the data gradient of a 64-output-channel stride-2 conv;
+ *                    wrot = that channel's row of the rotated packing, bf16 [9][64]
+ *   pcg_wgrad_few    dw [64][Cs][3][3] f32 (+ db[64] if not NULL) from in [N][H][W][Cs] and dy [M][64]
+ *   pcg_wgrad_to1    dw [1][64][3][3], db[1] from x [N][H][W][64] and g [N*H*W]
+ *   part: pcg_wgrad_small_parts() * 2048 floats of scratch. */
+int pcg_conv_to1(const void* in, int N, int H, int W, int Cin, const void* w9, const float* bias, float* out, void* stream);
+int pcg_conv_few(const void* in, int in_is_f32, int N, int H, int W, int Cs, const void* wnk, int Cout, int stride,
+                 const float* bias, int act, float slope, const void* act_ref, int ref_act, float ref_slope, void* out,
+                 void* stream);
+int pcg_dgrad_s2_to1(const void* dy, int N, int H, int W, const void* wrot, float* dx, void* stream);
+int pcg_wgrad_small_parts(void);
+int pcg_wgrad_few(const void* in, const void* dy, int N, int H, int W, int Cs, int stride, float* part, float* dw, float* db,
+                  void* stream);
+int pcg_wgrad_to1(const void* x, const void* g, int N, int H, int W, float* part, float* dw, float* db, void* stream);
+
 /* fp32 OIHW -> bf16 [Cout][taps][Cin] (fprop) and rotated [Cin][taps][Cout] (dgrad; may be NULL). */
 int pcg_pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, void* fprop, void* dgrad,
                              void* stream);

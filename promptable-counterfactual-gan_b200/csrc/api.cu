@@ -2,6 +2,7 @@
 #include "../../include/pcg.h"
 
 #include "common.cuh"
+#include "conv_small.cuh"
 #include "conv_tc.cuh"
 
 #include <string.h>
@@ -138,6 +139,42 @@ int pcg_conv_tc64_grid(int N, int H, int W) {
   try { return conv_tc64_grid(N, H, W); } catch (const std::exception& e) { set_last_error(e.what()); return -1; }
 }
 int pcg_conv_tc64_set_variant(int v) { conv_tc64_set_variant(v); return 0; }
+
+// ---- skinny-layer kernels (conv_small.cu): test entry points
+int pcg_conv_to1(const void* in, int N, int H, int W, int Cin, const void* w9, const float* bias, float* out, void* stream) {
+  PCG_API_BEGIN
+  conv_to1((const bf16*)in, N, H, W, Cin, (const bf16*)w9, bias, out, (cudaStream_t)stream);
+  PCG_API_END
+}
+int pcg_conv_few(const void* in, int in_is_f32, int N, int H, int W, int Cs, const void* wnk, int Cout, int stride,
+                 const float* bias, int act, float slope, const void* act_ref, int ref_act, float ref_slope, void* out,
+                 void* stream) {
+  PCG_API_BEGIN
+  FewEpilogue e;
+  e.bias = bias; e.act = act; e.slope = slope; e.act_ref = (const bf16*)act_ref; e.ref_act = ref_act; e.ref_slope = ref_slope;
+  if (in_is_f32) conv_few<float>((const float*)in, N, H, W, Cs, (const bf16*)wnk, Cout, stride, e, (bf16*)out, (cudaStream_t)stream);
+  else conv_few<bf16>((const bf16*)in, N, H, W, Cs, (const bf16*)wnk, Cout, stride, e, (bf16*)out, (cudaStream_t)stream);
+  PCG_API_END
+}
+int pcg_dgrad_s2_to1(const void* dy, int N, int H, int W, const void* wrot, float* dx, void* stream) {
+  PCG_API_BEGIN
+  dgrad_s2_to1((const bf16*)dy, N, H, W, (const bf16*)wrot, dx, (cudaStream_t)stream);
+  PCG_API_END
+}
+int pcg_wgrad_small_parts(void) {
+  try { return wgrad_few_parts(); } catch (const std::exception& e) { set_last_error(e.what()); return -1; }
+}
+int pcg_wgrad_few(const void* in, const void* dy, int N, int H, int W, int Cs, int stride, float* part, float* dw, float* db,
+                  void* stream) {
+  PCG_API_BEGIN
+  wgrad_few<bf16>((const bf16*)in, (const bf16*)dy, N, H, W, Cs, stride, part, dw, db, (cudaStream_t)stream);
+  PCG_API_END
+}
+int pcg_wgrad_to1(const void* x, const void* g, int N, int H, int W, float* part, float* dw, float* db, void* stream) {
+  PCG_API_BEGIN
+  wgrad_to1((const bf16*)x, (const bf16*)g, N, H, W, part, dw, db, (cudaStream_t)stream);
+  PCG_API_END
+}
 int pcg_conv_tc64_fprop(const void* in, int N, int H, int W, const void* wpk, const float* bias, int act, float slope,
                         const void* add_src, const void* act_ref, int ref_act, void* out, float* stats, void* stream) {
   PCG_API_BEGIN

@@ -253,3 +253,29 @@ def test_tensor_core_path_matches_cuda_core_path_in_bf16():
     print("tc vs cuda-core (bf16 storage), worst rel-L2:", worst[:6])
     # two independent bf16 realisations of the same step differ by ~sqrt(2) x the noise floor (<= 0.1 here)
     assert worst[0][0] < 0.15, worst[:6]
+
+
+def test_loss_curves_track_oracle_over_many_steps():
+    """north_star: 'loss curves tracking the reference over N steps'.  40 iterations of the default (bf16 tensor-core)
+    plan against the fp32 oracle from the same state and batches, with learning rates 20x the reference's so that the
+    curves actually move: every loss scalar stays within 5 % of the oracle's at every step, and the curves move in the
+    same direction (the discriminator loss falls by the same amount within 10 %)."""
+    hp = O.Hyper()
+    hp.g_lr, hp.d_lr = 1e-3, 2e-4
+    B, ch, nres, steps = 32, 64, 2, 40
+    H = Harness(B, ch, nres, "bf16", seed=11, hp=hp)
+    curves = {"native": [], "oracle": []}
+    keys = ("d_loss", "g_loss", "g_adv", "g_cls")
+    for i in range(steps):
+        x, y, t, mask = O.synth_batch(B, 5000 + i, mnist_like=(i % 3 == 1))
+        sc, _ = O.countergan_step(H.S, x, y, t, mask, n_resblocks=nres, hp=hp)
+        H.plan.step(x.cuda(), y.cuda(), t.cuda(), mask.cuda().contiguous())
+        torch.cuda.synchronize()
+        got = H.plan.scalars_dict()
+        curves["native"].append([got[k] for k in keys])
+        curves["oracle"].append([sc[k] for k in keys])
+    nat, ora = torch.tensor(curves["native"]), torch.tensor(curves["oracle"])
+    rel = ((nat - ora).abs() / ora.abs().clamp_min(1e-3)).max(0).values
+    assert torch.all(rel < 5e-2), dict(zip(keys, rel.tolist()))
+    drop_n, drop_o = nat[0, 0] - nat[-1, 0], ora[0, 0] - ora[-1, 0]
+    assert drop_o > 0.01 and abs(drop_n - drop_o) < 0.1 * abs(drop_o), (drop_n.item(), drop_o.item())
