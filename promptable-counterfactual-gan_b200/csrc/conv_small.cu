@@ -265,6 +265,17 @@ conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const 
     const long long m0 = blk * 16;
     // the next block's (L2-latency) loads are in flight while this block is computed and stored
     if (blk + bstride < nblk) load_a(blk + bstride, a_next);
+    // the activation-reference rows of THIS block (only their signs are used) are fetched now, under the MMAs
+    uint4 aref[16 * CH / 32];
+    if (act_ref != nullptr) {
+#pragma unroll
+      for (int it = 0; it < 16 * CH / 32; ++it) {
+        const int id = it * 32 + lane;
+        const int row = id / CH, cc = id - row * CH;
+        const long long m = m0 + row;
+        aref[it] = m < M ? *reinterpret_cast<const uint4*>(act_ref + m * COUT + cc * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
     float c[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -294,7 +305,7 @@ conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const 
       float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
       if (m < M) {
         if (act_ref != nullptr) {
-          const uint4 u = *reinterpret_cast<const uint4*>(act_ref + m * COUT + cc * 8);
+          const uint4 u = aref[it];
           const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
