@@ -23,14 +23,16 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 // ------------------------------------------------------------------------------------------
 // Cin -> 1, 3x3, stride 1, pad 1.
 // A tile = R output rows of one image: one TMA box brings the (R+2) x (W+2) zero-padded input pixels (Cin bf16 per
-// row, hardware swizzle); output position i = hh*(W+2) + ww reads tile row i + r*(W+2) + s for tap (r, s), so every
-// tap's A fragment is an ldmatrix at a shifted row of the same tile.  The single output channel occupies column 0
-// of the m16n8k16 B fragment (lanes 0-3 hold the weights, the rest zeros); the 128 positions of a tile are the
-// 8 consumer warps' m16 blocks.
+// row, hardware swizzle).  Legacy mma.sync is ~16x slower than tcgen05 on this part (measured ~32 cycles per
+// m16n8k16 and sub-core), so the contraction is arranged to need as few of them as possible: instead of one dot
+// product of 9*Cin per output pixel (36 k-steps, 1 of 8 B columns used), every INPUT pixel q of the halo tile gets
+//   P[q][tap] = sum_c x[q][c] * w[tap][c]      (K = Cin: 4 k-steps, 9 of 16 B columns used)
+// and an output is the 9-term gather out[i] = bias + sum_{r,s} P[i + r*(W+2) + s][r*3 + s] from shared memory.
 // ------------------------------------------------------------------------------------------
 constexpr int C1_STAGES = 3;
-constexpr int C1_ROWS = 192;                 // >= 127 + 2*(W+2) + 2 + 1 for W <= 28
-constexpr int C1_THREADS = 288;              // warp 0: TMA producer, warps 1-8: consumers
+constexpr int C1_ROWS = 192;                 // halo rows padded to 12 m16 blocks; >= (R+2)*(W+2) for W <= 28
+constexpr int C1_CONSUMERS = 12;             // one m16 block of the halo tile per warp
+constexpr int C1_THREADS = 32 * (C1_CONSUMERS + 1);   // + warp 12: TMA producer
 
 template <int CIN>
 __device__ __forceinline__ uint32_t c1_swizzle(uint32_t off) {
@@ -47,11 +49,12 @@ conv_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C1_STAGES * STAGE_BYTES);
   uint64_t* empty = full + C1_STAGES;
+  float* P = reinterpret_cast<float*>(empty + C1_STAGES + 2);       // [2][C1_ROWS][9]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
-    for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], C1_CONSUMERS); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < C1_STAGES * STAGE_BYTES / 16; i += blockDim.x)
@@ -60,7 +63,7 @@ conv_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict_
   __syncthreads();
   const int box_bytes = (R + 2) * WP * ROWB;
 
-  if (warp == 0) {
+  if (warp == C1_CONSUMERS) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -75,56 +78,56 @@ conv_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict_
     return;
   }
 
-  // B fragments of all 9*KQ k-steps: b0 = W[k = 2*(lane%4) + {0,1}][n = lane/4], b1 = same at k + 8; only n = 0 is real
-  uint32_t breg[9 * KQ][2];
-  {
-    const int kb = (lane & 3) * 2;
-    const bool real = (lane >> 2) == 0;
+  const int q = lane & 3, rr = lane >> 2;
+  // B[k = channel][n = tap]: n-tile 0 holds taps 0..7 (column rr), n-tile 1 tap 8 in column 0
+  uint32_t breg[KQ][2][2];
 #pragma unroll
-    for (int ks = 0; ks < 9 * KQ; ++ks) {
-      const bf16* p = w9 + ks * 16 + kb;            // (tap, kq) -> tap*CIN + kq*16 == ks*16
-      breg[ks][0] = real ? *reinterpret_cast<const uint32_t*>(p) : 0u;
-      breg[ks][1] = real ? *reinterpret_cast<const uint32_t*>(p + 8) : 0u;
+  for (int ks = 0; ks < KQ; ++ks)
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const int c = ks * 16 + 2 * q + hb * 8;
+      breg[ks][0][hb] = *reinterpret_cast<const uint32_t*>(w9 + rr * CIN + c);
+      breg[ks][1][hb] = rr == 0 ? *reinterpret_cast<const uint32_t*>(w9 + 8 * CIN + c) : 0u;
     }
-  }
   const float bv = bias != nullptr ? __ldg(bias) : 0.f;
-  const int i0 = (warp - 1) * 16;
-  const int arow = i0 + (lane & 15), ahalf = lane >> 4;
-  int stage = 0;
+  int stage = 0, it = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     const int n = tile / tiles_per_img, h0 = (tile % tiles_per_img) * R;
+    float* Pt = P + (it & 1) * C1_ROWS * 9;
     mbar_wait(&full[stage], phase);
     const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
-    // one accumulator chain per filter row: mma.sync results feed the next mma of the same chain, three chains
-    // keep the tensor pipe busy while one waits
-    float c3[3][4];
+    float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const uint32_t rowoff = (uint32_t)(warp * 16 + (lane & 15)) * ROWB;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) c3[r][0] = c3[r][1] = c3[r][2] = c3[r][3] = 0.f;
-#pragma unroll
-    for (int sx = 0; sx < 3; ++sx)
-#pragma unroll
-      for (int kq = 0; kq < KQ; ++kq)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int tap = r * 3 + sx;
-          const uint32_t rowoff = (uint32_t)(arow + r * WP + sx) * ROWB;
-          uint32_t a[4];
-          ldmatrix_x4(base + c1_swizzle<CIN>(rowoff + (uint32_t)(kq * 2 + ahalf) * 16u), a);
-          mma_bf16_16816(c3[r], a, breg[tap * KQ + kq][0], breg[tap * KQ + kq][1]);
-        }
-    float c[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = (c3[0][i] + c3[1][i]) + c3[2][i];
+    for (int ks = 0; ks < KQ; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4(base + c1_swizzle<CIN>(rowoff + (uint32_t)(ks * 2 + (lane >> 4)) * 16u), a);
+      mma_bf16_16816(c[0], a, breg[ks][0][0], breg[ks][0][1]);
+      mma_bf16_16816(c[1], a, breg[ks][1][0], breg[ks][1][1]);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
-    if ((lane & 3) == 0) {
 #pragma unroll
-      for (int hsel = 0; hsel < 2; ++hsel) {
-        const int row = i0 + (lane >> 2) + hsel * 8;
-        const int hh = row / WP, ww = row - hh * WP;
-        if (hh < R && ww < W && h0 + hh < H)
-          out[((long long)n * H + h0 + hh) * W + ww] = c[hsel * 2] + bv;
+    for (int t = 0; t < 2; ++t) {
+      float* row = Pt + (warp * 16 + rr + t * 8) * 9;
+      row[2 * q] = c[0][2 * t];
+      row[2 * q + 1] = c[0][2 * t + 1];
+      if (q == 0) row[8] = c[1][2 * t];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(C1_CONSUMERS * 32) : "memory");
+    // gather: P is double-buffered, so the next tile's writes (other buffer) need no second barrier; the buffer
+    // written two tiles later is protected by the barrier of the tile in between
+    if (threadIdx.x < 128) {
+      const int i = threadIdx.x;
+      const int hh = i / WP, ww = i - hh * WP;
+      if (hh < R && ww < W && h0 + hh < H) {
+        float s = bv;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx) s += Pt[(i + r * WP + sx) * 9 + r * 3 + sx];
+        out[((long long)n * H + h0 + hh) * W + ww] = s;
       }
     }
     if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
@@ -135,7 +138,7 @@ bool conv_to1_supported(int H, int W, int Cin) {
   const int WP = W + 2;
   if (WP > 128 || (Cin != 32 && Cin != 64)) return false;
   const int R = 128 / WP;
-  return R >= 1 && 127 + 2 * WP + 3 <= C1_ROWS && R + 2 <= 256;
+  return R >= 1 && 127 + 2 * WP + 3 <= C1_ROWS && (R + 2) * WP <= C1_ROWS && R + 2 <= 256;
 }
 
 void conv_to1(const bf16* in, int N, int H, int W, int Cin, const bf16* w9, const float* bias, float* out,
@@ -145,7 +148,7 @@ void conv_to1(const bf16* in, int N, int H, int W, int Cin, const bf16* w9, cons
   const int WP = W + 2, R = 128 / WP;
   const int tiles_per_img = (H + R - 1) / R, total = N * tiles_per_img;
   CUtensorMap tmX = make_tmap_nhwc_box_c(in, N, H, W, Cin, Cin, WP, R + 2);
-  const int smem = 1024 + C1_STAGES * C1_ROWS * Cin * 2 + 64;
+  const int smem = 1024 + C1_STAGES * C1_ROWS * Cin * 2 + 64 + 2 * C1_ROWS * 9 * 4;
   int grid = 2 * sm_count();
   if (grid > total) grid = total;
   if (Cin == 64) {
