@@ -508,6 +508,117 @@ def run_other(args):
                       "roofline": roof, "cpu_baseline": cpu, "clocks": clk}), flush=True)
 
 
+# --------------------------------------------------------------------------------------------- widened rows
+def run_widened(args):
+    """--workload mnist_infer: eval-mode generator forward (BatchNorm folded), batch 512.
+    --workload mnist_loader: on-device input pipeline, one shuffled epoch of 54,000 uint8 images, batch 512."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pk, which = peaks()
+    if args.impl == "reference" or not torch.cuda.is_available():
+        if args.impl != "reference":
+            raise SystemExit("bench.py (native arm) needs a CUDA device: libpcg has no CPU fallback")
+    cpu = None
+    torch.set_num_threads(os.cpu_count() or 1)
+    if args.workload == "mnist_infer":
+        from oracle import mnist_countergan as O
+        B = 512
+        metric, unit = "MNIST CounteRGAN generator inference samples/sec (eval forward)", "samples/s"
+        if not args.skip_cpu or args.impl == "reference":
+            PG, BG = O.synth_params(O.g_param_shapes(), 1, "G"), O.g_buffers()
+            xb = O.synth_batch(128, 5)
+            with torch.no_grad():
+                O.g_forward(PG, BG, xb[0], xb[2], xb[3], training=False)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    O.g_forward(PG, BG, xb[0], xb[2], xb[3], training=False)
+            cpu = {"value": 3 * 128 / (time.perf_counter() - t0), "unit": unit, "cores": os.cpu_count(), "kind": "port",
+                   "sample": "oracle eval forward, 3 batches of 128"}
+        if args.impl == "reference":
+            line = {"impl": "reference", "metric": metric, "value": cpu["value"], "unit": unit, "cpu_baseline": cpu}
+        else:
+            import pcg_b200  # noqa: F401
+            from pcg_b200.mnist.models.generator import ResidualGenerator
+            torch.manual_seed(0)
+            G = ResidualGenerator().cuda().eval()
+            x, y, t, m = (v.cuda().contiguous() for v in O.synth_batch(B, 5))
+            with torch.no_grad():
+                for _ in range(max(args.warmup, 3)):
+                    G(x, t, m)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    G(x, t, m)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            ach = 2 * 377.524224e6 * B / (ms * 1e-3) / 1e12
+            peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            line = {"metric": metric, "value": B / (ms * 1e-3), "unit": unit, "ms_per_step": ms, "dtype": "bf16",
+                    "config": {"workload": "conditional_counteRGAN/mnist ResidualGenerator.eval() forward, batch 512"},
+                    "roofline": {"bound": "tensor", "kernel": "whole forward (15 convolutions, BatchNorm folded)",
+                                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None},
+                    "cpu_baseline": cpu}
+    else:
+        metric, unit = "MNIST input pipeline samples/sec (shuffled epoch, batch 512)", "samples/s"
+        N, B = 54000, 512
+        g = torch.Generator().manual_seed(0)
+        u8 = torch.randint(0, 256, (N, 28, 28), generator=g, dtype=torch.uint8)
+        yv = torch.randint(0, 10, (N,), generator=g)
+        if not args.skip_cpu or args.impl == "reference":
+            try:
+                from torchvision import transforms
+                from PIL import Image
+                tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.5,), (0.5,))])
+
+                class DS(torch.utils.data.Dataset):
+                    def __len__(self):
+                        return 8192
+
+                    def __getitem__(self, i):
+                        return tf(Image.fromarray(u8[i].numpy(), mode="L")), int(yv[i])
+                dl = torch.utils.data.DataLoader(DS(), batch_size=128, shuffle=True, num_workers=4)
+                for _ in dl:
+                    break
+                t0, n = time.perf_counter(), 0
+                for xb, _ in dl:
+                    n += xb.shape[0]
+                cpu = {"value": n / (time.perf_counter() - t0), "unit": unit, "cores": 4, "kind": "reference",
+                       "sample": "data_utils.py:9-12,26 as written: torchvision transforms on PIL images, "
+                                 "DataLoader(batch 128, 4 workers), 8192 images"}
+            except Exception as e:      # torchvision / PIL missing
+                cpu = {"value": None, "unit": unit, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        if args.impl == "reference":
+            line = {"impl": "reference", "metric": metric, "value": cpu["value"], "unit": unit, "cpu_baseline": cpu}
+        else:
+            import pcg_b200  # noqa: F401
+            from pcg_b200.mnist import data_utils as DU
+            loader = DU.DeviceLoader(u8.cuda(), yv.cuda(), None, B, shuffle=True)
+            for _ in loader:
+                pass
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in loader:
+                pass
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            ach = N * 3936 / (ms * 1e-3) / 1e9
+            line = {"metric": metric, "value": N / (ms * 1e-3), "unit": unit, "ms_per_step": ms / len(loader), "dtype": "u8->f32",
+                    "config": {"workload": "54,000 resident uint8 28x28 images, shuffled epoch, batch 512"},
+                    "roofline": {"bound": "hbm", "kernel": "u8_batch_kernel (launch-bound: 1 launch + index slice per batch)",
+                                 "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                                 "traffic": None},
+                    "cpu_baseline": cpu}
+    line.update({"n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+                 "scaling": "weak", "vs_baseline": None, "data": "synthetic"})
+    print(json.dumps(line), flush=True)
+
+
 def flops_tc_fprop_per_step():
     """Algorithmic FLOPs executed by conv_tc_fprop launches in one step at B=512 (bf16 plan):
     G: 13 fprop + 13 dgrad of the 64->64 conv; D (3 tensor-core layers): fwd on 2B + fwd on B; C: conv.4 + fc.1."""
@@ -527,9 +638,11 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PCG_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workload", default="mnist", choices=["mnist"] + sorted(OTHER))
+    ap.add_argument("--workload", default="mnist", choices=["mnist", "mnist_infer", "mnist_loader"] + sorted(OTHER))
     args = ap.parse_args()
-    if args.workload != "mnist":
+    if args.workload in ("mnist_infer", "mnist_loader"):
+        run_widened(args)
+    elif args.workload != "mnist":
         run_other(args)
     elif args.impl == "reference":
         run_reference(args)
