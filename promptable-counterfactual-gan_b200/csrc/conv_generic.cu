@@ -601,7 +601,8 @@ static int wgrad_slices(const ConvGeom& g) {
   const long long P = g.Mout();
   const int tiles = cdiv(g.Cout, GT) * cdiv(g.K(), GT);
   long long want = (4LL * 148 + tiles - 1) / tiles;
-  long long maxz = (P + 255) / 256;       // at least 256 pixels per slice
+  long long maxz = (P + 31) / 32;         // at least 32 pixels per slice (a 4096-row Linear layer has ONE output tile:
+                                          // 16 slices of 256 rows left 132 SMs idle and cost 34 us per weight gradient)
   if (want > maxz) want = maxz;
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;
