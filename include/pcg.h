@@ -246,6 +246,16 @@ int pcg_scale_cols(const float* dy, long long rows, int C, const float* scale, f
 int pcg_unary(const float* x, long long n, int op, float a, float* y, void* stream);
 int pcg_unary_bwd(const float* dy, const float* y, long long n, int op, float a, float* dx, void* stream);
 int pcg_binary(const float* a, const float* b, long long n, int op, float alpha, float beta, float* out, void* stream);
+/* FiLM modulation (house_sales_kc_usa/models/generator.py:13-16,28-35) in one launch each way:
+ *   fwd: out = [relu](gamma * n + beta) [+ res]          (res may be NULL)
+ *   bwd: dn = df * gamma ; dgamma (+)= df * n ; dbeta (+)= df   (accumulate != 0 adds: the same FiLM is used twice per block) */
+int pcg_film_fwd(const float* gamma, const float* n_, const float* beta, const float* res, long long n, int relu,
+                 float* out, void* stream);
+int pcg_film_bwd(const float* df, const float* gamma, const float* n_, long long n, int accumulate, float* dn,
+                 float* dgamma, float* dbeta, void* stream);
+/* dst[i] = src[i]^T (src[i] is [rows[i]][cols[i]]) for n <= 64 small matrices in one launch; the pointer / size arrays
+ * are HOST arrays (copied into the kernel arguments). */
+int pcg_transpose_multi(int n, const float* const* src, float* const* dst, const int* rows, const int* cols, void* stream);
 int pcg_copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows,
                   int ncols, float alpha, int accumulate, void* stream);
 int pcg_onehot(const long long* lab, long long rows, int nc, float* dst, int dst_ld, int c0, void* stream);
@@ -259,6 +269,10 @@ int pcg_gan_loss(const float* z, int n, int kind, float t, float wgt, float* out
 int pcg_combine_scalars(int n, const float* host_coeffs, const float* const* host_ptrs, float* out, void* stream);
 int pcg_spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
                           float* sigma, void* stream);
+/* Same with the extra outputs a training pass needs in the same launch: WnT = Wn^T [K][N] (operand of the data
+ * gradient), us / vs = copies of u / v after the power iteration (any of the three may be NULL). */
+int pcg_spectral_norm_fwd2(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
+                           float* WnT, float* us, float* vs, float* sigma, void* stream);
 int pcg_spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
                           const float* sigma, float* dW, void* stream);
 int pcg_gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y,

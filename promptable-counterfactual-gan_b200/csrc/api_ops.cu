@@ -123,6 +123,32 @@ int pcg_binary(const float* a, const float* b, long long n, int op, float alpha,
   binary(a, b, n, op, alpha, beta, out, ST);
   PCG_API_END
 }
+int pcg_film_fwd(const float* gamma, const float* n_, const float* beta, const float* res, long long n, int relu,
+                 float* out, void* stream) {
+  PCG_API_BEGIN
+  film_fwd(gamma, n_, beta, res, n, relu, out, ST);
+  PCG_API_END
+}
+int pcg_film_bwd(const float* df, const float* gamma, const float* n_, long long n, int accumulate, float* dn,
+                 float* dgamma, float* dbeta, void* stream) {
+  PCG_API_BEGIN
+  film_bwd(df, gamma, n_, n, accumulate, dn, dgamma, dbeta, ST);
+  PCG_API_END
+}
+int pcg_transpose_multi(int n, const float* const* src, float* const* dst, const int* rows, const int* cols, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(n >= 1 && n <= TRANSPOSE_MAX, "1..64 matrices per call");
+  TransposeTable t;
+  t.n = n;
+  int off = 0;
+  for (int i = 0; i < n; ++i) {
+    t.src[i] = src[i]; t.dst[i] = dst[i]; t.rows[i] = rows[i]; t.cols[i] = cols[i]; t.begin[i] = off;
+    off += rows[i] * cols[i];
+  }
+  t.begin[n] = off;
+  transpose_multi(t, ST);
+  PCG_API_END
+}
 int pcg_copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows, int ncols,
                   float alpha, int accumulate, void* stream) {
   PCG_API_BEGIN
@@ -164,6 +190,12 @@ int pcg_spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, floa
                           float* sigma, void* stream) {
   PCG_API_BEGIN
   spectral_norm_fwd(W, N, K, u, v, eps, do_iter, Wn, sigma, ST);
+  PCG_API_END
+}
+int pcg_spectral_norm_fwd2(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
+                           float* WnT, float* us, float* vs, float* sigma, void* stream) {
+  PCG_API_BEGIN
+  spectral_norm_fwd(W, N, K, u, v, eps, do_iter, Wn, sigma, ST, WnT, us, vs);
   PCG_API_END
 }
 int pcg_spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,

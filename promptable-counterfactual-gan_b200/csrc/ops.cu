@@ -77,6 +77,60 @@ void binary(const float* a, const float* b, long long n, int op, float alpha, fl
   PCG_LAUNCH_CHECK();
 }
 
+// FiLM (house_sales_kc_usa/models/generator.py:13-16,28-35): one launch for  out = [relu](gamma * n + beta) [+ res]
+__global__ void film_fwd_kernel(const float* __restrict__ gamma, const float* __restrict__ n_, const float* __restrict__ beta,
+                                const float* __restrict__ res, long long n, int relu, float* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    float v = fmaf(gamma[i], n_[i], beta[i]);
+    if (relu) v = fmaxf(v, 0.f);
+    out[i] = res != nullptr ? res[i] + v : v;
+  }
+}
+void film_fwd(const float* gamma, const float* n_, const float* beta, const float* res, long long n, int relu, float* out,
+              cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  film_fwd_kernel<<<blocks_for(n), 256, 0, s>>>(gamma, n_, beta, res, n, relu, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+// ... and its backward for an upstream gradient df:  dn = df * gamma ;  dgamma (+)= df * n ;  dbeta (+)= df
+__global__ void film_bwd_kernel(const float* __restrict__ df, const float* __restrict__ gamma, const float* __restrict__ n_,
+                                long long n, int accumulate, float* __restrict__ dn, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta) {
+  GRID_STRIDE(i, n) {
+    const float d = df[i];
+    dn[i] = d * gamma[i];
+    const float dg = d * n_[i];
+    dgamma[i] = accumulate ? dgamma[i] + dg : dg;
+    dbeta[i] = accumulate ? dbeta[i] + d : d;
+  }
+}
+void film_bwd(const float* df, const float* gamma, const float* n_, long long n, int accumulate, float* dn, float* dgamma,
+              float* dbeta, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  film_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(df, gamma, n_, n, accumulate, dn, dgamma, dbeta);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// dst_i = src_i^T for up to TRANSPOSE_MAX small matrices in one launch (the dgrad operands of every Linear layer of a
+// tabular net after its Adam update)
+__global__ void transpose_multi_kernel(const TransposeTable t) {
+  GRID_STRIDE(g, (long long)t.begin[t.n]) {
+    int l = 0;
+    while (l + 1 < t.n && g >= t.begin[l + 1]) ++l;
+    const int i = (int)g - t.begin[l];
+    const int r = i / t.cols[l], c = i - r * t.cols[l];
+    t.dst[l][(size_t)c * t.rows[l] + r] = t.src[l][i];
+  }
+}
+void transpose_multi(const TransposeTable& t, cudaStream_t s) {
+  PCG_PROFILE("pack_weights", s);
+  transpose_multi_kernel<<<blocks_for(t.begin[t.n]), 256, 0, s>>>(t);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 // out[r][c0_out + j] = src[r][c0_src + j], j < ncols  (column block copy between matrices of different widths);
 // accumulate != 0 adds instead of overwriting (gradient of a tensor used twice).
 __global__ void copy_cols_kernel(const float* __restrict__ src, int src_ld, int c0_src, float* __restrict__ dst,
@@ -240,8 +294,11 @@ void combine_scalars(const ScalarTerms& t, float* out, cudaStream_t s) {
 // ------------------------------------------------------------------ spectral norm (torch/nn/utils/spectral_norm.py:62-113)
 // One power iteration in place on (u, v) (train mode), sigma = u^T W v, Wn = W / sigma.  Single block: the
 // matrices are at most 128 x 64.
+// Optional extra outputs save three launches per layer and pass: WnT = Wn^T ([K][N], the dgrad operand) and the
+// snapshots us / vs of u / v that this pass's backward needs (torch's graph holds clones taken at call time).
 __global__ void spectral_norm_fwd_kernel(const float* __restrict__ W, int N, int K, float* u, float* v, float eps,
-                                         int do_iter, float* __restrict__ Wn, float* sigma_out) {
+                                         int do_iter, float* __restrict__ Wn, float* sigma_out,
+                                         float* __restrict__ WnT, float* __restrict__ us, float* __restrict__ vs) {
   extern __shared__ float sm[];     // u[N], v[K], red[32]
   float* su = sm;
   float* sv = sm + N;
@@ -292,13 +349,24 @@ __global__ void spectral_norm_fwd_kernel(const float* __restrict__ W, int N, int
   if (threadIdx.x == 0) { s_sigma = sg; sigma_out[0] = sg; }
   __syncthreads();
   const float inv = 1.f / s_sigma;
-  for (int i = threadIdx.x; i < N * K; i += blockDim.x) Wn[i] = W[i] * inv;
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+    const float w = W[i] * inv;
+    Wn[i] = w;
+    if (WnT != nullptr) {
+      const int n = i / K, k = i - n * K;
+      WnT[(size_t)k * N + n] = w;
+    }
+  }
+  if (us != nullptr)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) us[i] = su[i];
+  if (vs != nullptr)
+    for (int i = threadIdx.x; i < K; i += blockDim.x) vs[i] = sv[i];
 }
 void spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
-                       float* sigma, cudaStream_t s) {
+                       float* sigma, cudaStream_t s, float* WnT, float* us, float* vs) {
   PCG_PROFILE("ops_small", s);
   const size_t sm = (size_t)(N + K + 40) * sizeof(float);
-  spectral_norm_fwd_kernel<<<1, 256, sm, s>>>(W, N, K, u, v, eps, do_iter, Wn, sigma);
+  spectral_norm_fwd_kernel<<<1, 256, sm, s>>>(W, N, K, u, v, eps, do_iter, Wn, sigma, WnT, us, vs);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

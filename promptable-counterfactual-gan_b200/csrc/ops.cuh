@@ -10,6 +10,18 @@ enum BinaryOp { OP_ADD = 0, OP_MUL = 1 };
 void unary(const float* x, long long n, int op, float a, float* y, cudaStream_t s);
 void unary_bwd(const float* dy, const float* y, long long n, int op, float a, float* dx, cudaStream_t s);
 void binary(const float* a, const float* b, long long n, int op, float alpha, float beta, float* out, cudaStream_t s);
+void film_fwd(const float* gamma, const float* n_, const float* beta, const float* res, long long n, int relu, float* out,
+              cudaStream_t s);
+void film_bwd(const float* df, const float* gamma, const float* n_, long long n, int accumulate, float* dn, float* dgamma,
+              float* dbeta, cudaStream_t s);
+constexpr int TRANSPOSE_MAX = 64;
+struct TransposeTable {
+  int n;
+  const float* src[TRANSPOSE_MAX];     // [rows][cols]
+  float* dst[TRANSPOSE_MAX];           // [cols][rows]
+  int rows[TRANSPOSE_MAX], cols[TRANSPOSE_MAX], begin[TRANSPOSE_MAX + 1];
+};
+void transpose_multi(const TransposeTable& t, cudaStream_t s);
 void copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows, int ncols,
                float alpha, int accumulate, cudaStream_t s);
 void onehot(const long long* lab, long long rows, int nc, float* dst, int dst_ld, int c0, cudaStream_t s);
@@ -25,7 +37,7 @@ struct ScalarTerms {
 };
 void combine_scalars(const ScalarTerms& t, float* out, cudaStream_t s);
 void spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
-                       float* sigma, cudaStream_t s);
+                       float* sigma, cudaStream_t s, float* WnT = nullptr, float* us = nullptr, float* vs = nullptr);
 void spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
                        const float* sigma, float* dW, cudaStream_t s);
 void gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y, cudaStream_t s);

@@ -163,6 +163,31 @@ def binary(a, b, op, out, alpha=1.0, beta=1.0):
     _lib.check(_L().pcg_binary(P(a), P(b), _ll(a.numel()), op, _f(alpha), _f(beta), P(out), _s()))
 
 
+def film_fwd(gamma, n, beta, out, relu=False, res=None):
+    """out = [relu](gamma * n + beta) [+ res], one launch."""
+    _chk(gamma, n, beta, out, res)
+    _lib.check(_L().pcg_film_fwd(P(gamma), P(n), P(beta), P(res), _ll(n.numel()), 1 if relu else 0, P(out), _s()))
+
+
+def film_bwd(df, gamma, n, dn, dgamma, dbeta, accumulate=False):
+    """dn = df * gamma ; dgamma (+)= df * n ; dbeta (+)= df, one launch."""
+    _chk(df, gamma, n, dn, dgamma, dbeta)
+    _lib.check(_L().pcg_film_bwd(P(df), P(gamma), P(n), _ll(n.numel()), 1 if accumulate else 0, P(dn), P(dgamma),
+                                 P(dbeta), _s()))
+
+
+def transpose_multi(pairs):
+    """pairs: list of (W [rows, cols], WT [cols, rows]); one launch per 64 matrices."""
+    for i in range(0, len(pairs), 64):
+        chunk = pairs[i:i + 64]
+        n = len(chunk)
+        src = (ctypes.c_void_p * n)(*[w.data_ptr() for w, _ in chunk])
+        dst = (ctypes.c_void_p * n)(*[t.data_ptr() for _, t in chunk])
+        rows = (ctypes.c_int * n)(*[w.shape[0] for w, _ in chunk])
+        cols = (ctypes.c_int * n)(*[w.shape[1] for w, _ in chunk])
+        _lib.check(_L().pcg_transpose_multi(n, src, dst, rows, cols, _s()))
+
+
 def copy_cols(src, c0_src, dst, c0_dst, ncols, alpha=1.0, accumulate=False):
     _chk(src, dst)
     rows = src.shape[0]
@@ -198,10 +223,12 @@ def combine(terms, out):
     _lib.check(_L().pcg_combine_scalars(n, coeffs, ptrs, P(out), _s()))
 
 
-def spectral_norm_fwd(W, u, v, Wn, sigma, do_iter=True, eps=1e-12):
+def spectral_norm_fwd(W, u, v, Wn, sigma, do_iter=True, eps=1e-12, WnT=None, us=None, vs=None):
+    """One power iteration (in place on u, v), sigma, Wn = W / sigma; optionally Wn^T and snapshots of u, v."""
     N, K = W.shape
-    _chk(W, u, v, Wn, sigma)
-    _lib.check(_L().pcg_spectral_norm_fwd(P(W), N, K, P(u), P(v), _f(eps), 1 if do_iter else 0, P(Wn), P(sigma), _s()))
+    _chk(W, u, v, Wn, sigma, WnT, us, vs)
+    _lib.check(_L().pcg_spectral_norm_fwd2(P(W), N, K, P(u), P(v), _f(eps), 1 if do_iter else 0, P(Wn), P(WnT), P(us),
+                                           P(vs), P(sigma), _s()))
 
 
 def spectral_norm_bwd(dWn, Wn, u, v, sigma, dW):

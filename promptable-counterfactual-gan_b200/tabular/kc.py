@@ -221,8 +221,7 @@ class KcPlan:
         return out
 
     def refresh(self):
-        for L in self._all_dense():
-            L.refresh()
+        K.transpose_multi([(L.W(), L.wT) for L in self._all_dense()])
 
     def _state(self):
         t = [self.G.data, self.G.m, self.G.v, self.G.step, self.D.flat.data, self.D.flat.m, self.D.flat.v, self.D.flat.step]
@@ -248,14 +247,10 @@ class KcPlan:
             b["fb"].fwd(self.cond, b["b"])
             b["fc1"].fwd(hcur, b["u1"])
             b["bn1"].fwd(b["u1"], b["n1"], training=training)
-            K.binary(b["g"], b["n1"], K.MUL, b["f1"])
-            K.binary(b["f1"], b["b"], K.ADD, b["f1"])
-            K.unary(b["f1"], K.RELU, b["r1"])
+            K.film_fwd(b["g"], b["n1"], b["b"], b["r1"], relu=True)                   # r1 = ReLU(FiLM(BN1(fc1 h)))
             b["fc2"].fwd(b["r1"], b["u2"])
             b["bn2"].fwd(b["u2"], b["n2"], training=training)
-            K.binary(b["g"], b["n2"], K.MUL, b["f2"])
-            K.binary(b["f2"], b["b"], K.ADD, b["f2"])
-            K.binary(hcur, b["f2"], K.ADD, b["hout"])
+            K.film_fwd(b["g"], b["n2"], b["b"], b["hout"], res=hcur)                  # h' = h + FiLM(BN2(fc2 r1))
             hcur = b["hout"]
         self.hlast = hcur
         self.fc_cont.fwd(hcur, self.contp)
@@ -329,11 +324,10 @@ class KcPlan:
         K.binary(self.d_res, self.d_pen, K.ADD, self.d_res)
         self._g_bwd()
         self.G.adam_step(self.lr_g)
-        for L in self._all_dense()[:2 + len(self.heads)]:
-            L.refresh()
+        g_layers = self._all_dense()[:2 + len(self.heads)]
         for b in self.blk:
-            for k in ("fc1", "fc2", "fg", "fb"):
-                b[k].refresh()
+            g_layers += [b[k] for k in ("fc1", "fc2", "fg", "fb")]
+        K.transpose_multi([(L.W(), L.wT) for L in g_layers])            # dgrad operands of the updated generator
         # ---- diagnostics of trainer.py:319-343 that need an extra classifier pass are left to the caller
 
     def _g_bwd(self):
@@ -352,16 +346,11 @@ class KcPlan:
         dh, other = self.dhA, self.dhB
         for b in reversed(self.blk):
             # f2 = g*n2 + b ; h' = h + f2
-            K.binary(dh, b["g"], K.MUL, self.dn)                 # d n2
-            K.binary(dh, b["n2"], K.MUL, b["dg"])                # d g (first use)
-            K.unary(dh, K.COPY, b["db"])                         # d b (first use)
+            K.film_bwd(dh, b["g"], b["n2"], self.dn, b["dg"], b["db"])               # d n2, d g / d b (first use)
             b["bn2"].bwd(self.dn, b["u2"], self.du)
             b["fc2"].wgrad(b["r1"], self.du)
             b["fc2"].dgrad(self.du, self.df, act_ref=b["r1"], ref_act=K.ACT_RELU)     # d f1 (through the ReLU)
-            K.binary(self.df, b["g"], K.MUL, self.dn)            # d n1
-            K.binary(self.df, b["n1"], K.MUL, self.tmp_h)
-            K.binary(b["dg"], self.tmp_h, K.ADD, b["dg"])        # d g (second use)
-            K.binary(b["db"], self.df, K.ADD, b["db"])           # d b (second use)
+            K.film_bwd(self.df, b["g"], b["n1"], self.dn, b["dg"], b["db"], accumulate=True)   # d n1, d g / d b (+=)
             b["bn1"].bwd(self.dn, b["u1"], self.du)
             b["fc1"].wgrad(b["hin"], self.du)
             b["fc1"].dgrad(self.du, other, add_src=dh)           # skip connection

@@ -103,10 +103,8 @@ class SNDense:
         return self.flat.p(self.name + ".bias")
 
     def normalise(self, p, iterate=True):
-        K.spectral_norm_fwd(self.W(), self.u, self.v, self.Wn[p], self.sigma[p], do_iter=iterate)
-        K.unary(self.u, K.COPY, self.us[p])
-        K.unary(self.v, K.COPY, self.vs[p])
-        K.pack_weights(self.Wn[p], 1, wd=self.WnT[p])
+        K.spectral_norm_fwd(self.W(), self.u, self.v, self.Wn[p], self.sigma[p], do_iter=iterate, WnT=self.WnT[p],
+                            us=self.us[p], vs=self.vs[p])
 
     def fwd(self, x, out, p, act=K.ACT_NONE, slope=0.2):
         K.linear_fwd(x, self.Wn[p], out, self.b(), act, slope)
