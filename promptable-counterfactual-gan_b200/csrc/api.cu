@@ -138,6 +138,9 @@ int pcg_conv_tc_wgrad64(const void* x, const void* dy, int N, int H, int W, floa
 int pcg_conv_tc64_grid(int N, int H, int W) {
   try { return conv_tc64_grid(N, H, W); } catch (const std::exception& e) { set_last_error(e.what()); return -1; }
 }
+int pcg_conv_tc64_fprop_grid(int N, int H, int W) {
+  try { return conv_tc64_fprop_grid(N, H, W); } catch (const std::exception& e) { set_last_error(e.what()); return -1; }
+}
 int pcg_conv_tc64_set_variant(int v) { conv_tc64_set_variant(v); return 0; }
 
 // ---- skinny-layer kernels (conv_small.cu): test entry points

@@ -99,6 +99,22 @@ CUtensorMap make_tmap_nhwc_box(const bf16* base, int N, int H, int W, int C, int
   if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string(int(r)));
   return m;
 }
+// Row-class view of an NHWC tensor with H % 4 == 0: dims (C, W, class = h % 4, idx = h / 4, N); box = 64 channels x
+// box_w x one class x box_rows consecutive rows of that class x 1 image (conv_tc64s_fprop_kernel).
+CUtensorMap make_tmap_nhwc_rowclass(const bf16* base, int N, int H, int W, int C, int box_w, int box_rows) {
+  load_driver_entry_points();
+  PCG_REQUIRE(H % 4 == 0, "row-class tensor map: H must be a multiple of 4");
+  CUtensorMap m;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, 4, (cuuint64_t)(H / 4), (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)4 * W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled(5d row classes) failed: " + std::to_string(int(r)));
+  return m;
+}
 // Same with `box_c` (16, 32 or 64) channels per pixel: 32/64/128-byte rows, matching swizzle.
 CUtensorMap make_tmap_nhwc_box_c(const bf16* base, int N, int H, int W, int C, int box_c, int box_w, int box_h) {
   load_driver_entry_points();

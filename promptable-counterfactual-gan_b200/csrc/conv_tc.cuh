@@ -82,14 +82,16 @@ CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, uint32_
 CUtensorMap make_tmap_im2col_box(const bf16* base, int N, int H, int W, int C, int lower_w, int lower_h,
                                  int upper_w, int upper_h, int stride);
 CUtensorMap make_tmap_nhwc_box(const bf16* base, int N, int H, int W, int C, int box_w, int box_h);
+CUtensorMap make_tmap_nhwc_rowclass(const bf16* base, int N, int H, int W, int C, int box_w, int box_rows);
 CUtensorMap make_tmap_nhwc_box_c(const bf16* base, int N, int H, int W, int C, int box_c, int box_w, int box_h);
 
 // ---- 64 -> 64, 3x3, stride 1, pad 1 convolutions with a shared-memory halo tile (conv_tc64.cu) ----------
 // One TMA box per tile brings (R+2) x (W+2) zero-padded pixels; the nine filter taps are shifted views of that
 // tile (UMMA descriptors offset by (r*(W+2)+s) rows), the 72 KB of weights stay resident in shared memory.
 // L2->SM traffic per output tile drops from 216 KB (im2col per tap + weights) to ~23 KB.
-int conv_tc64_grid(int N, int H, int W);             // CTAs launched = rows of the BN-statistics partial buffer
+int conv_tc64_grid(int N, int H, int W);             // CTAs conv_tc64_wgrad launches = slices of its `part` buffer
 bool conv_tc64_supported(int H, int W);
+int conv_tc64_fprop_grid(int N, int H, int W);       // CTAs conv_tc64_fprop launches = rows of its `stats` partial buffer
 void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const ConvEpilogue& epi, bf16* out,
                      cudaStream_t stream);
 // part[conv_tc64_grid][9][64 ci][64 co] fp32; reduce with wgrad_reduce_tc().

@@ -476,6 +476,413 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-class stacked variant (H % 4 == 0).  The M=128 x N=64 MMAs above are bound by the A-operand read (a 4 KB pixel
+// block streamed from shared memory per instruction, ~64 cycles against 32 cycles of math), so the lever is to use
+// every A read for more output columns.  Image rows are split into four classes h % 4 (a 5-D tensor-map view of the same
+// NHWC tensor: no data movement); a super-tile is R consecutive rows of EACH class of one image and its accumulator is
+// M=128 positions x N=256 = four 64-channel blocks, one per output class.  An input block of class c (same row index)
+// is the tap-row  r = c - co + 1  operand of the output classes co = c-1, c, c+1, so ONE MMA with the three tap
+// matrices stacked along N (resident weights ordered [s][r = 2, 1, 0]) feeds three output blocks:
+//     class 1 -> co 0,1,2 (N=192)    class 2 -> co 1,2,3 (N=192)    class 0 -> co 0,1 (N=128)    class 3 -> co 2,3 (N=128)
+// plus the two wrap-arounds, class 0 one row further down -> co 3 (r = 2) and class 3 one row further up -> co 0 (r = 0), N=64.
+// 72 MMAs per 512 positions instead of 144.  The epilogue is the one above, run once per output class.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(F_THREADS, 1)
+conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
+                        const F64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sw = smem;                                   // weights, slot s*3 + (2 - r)
+  uint8_t* sin = smem + W_BYTES;                        // ring of class regions ((R+1) x (W+2) pixels each)
+  uint8_t* sout = sin + p.in_stages * p.in_stage_bytes; // output staging, 2 slots
+  uint8_t* sx = sout + 2 * p.out_tile_bytes;            // epilogue operand ring, 2 slots (if n_extra)
+  float* stats_smem = reinterpret_cast<float*>(sx + (p.n_extra ? 2 : 0) * p.out_tile_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + (16 * 2 * 16 + 64 + 4 * 64) * 4);
+  uint64_t* full = bars;                 // [2][4]: one set per MMA warp (a warp only ever waits on its own set, in order)
+  uint64_t* empty = bars + 8;            // [4]
+  uint64_t* wfull = bars + 12;           // [1]
+  uint64_t* tfull = wfull + 1;           // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* xfull = tempty + 2;          // [2]
+  uint64_t* xempty = xfull + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmOut);
+    if (p.n_extra) tma_prefetch_desc(&tmExtra);
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&full[4 + s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1); mbar_init(&tempty[s], F_EPI_THREADS);
+      mbar_init(&xfull[s], 1); mbar_init(&xempty[s], F_EPI_THREADS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  // rows of a class region beyond the TMA box are read by the (discarded) padding rows of the MMA: keep them finite
+  {
+    const int zbytes = (int)(reinterpret_cast<uint8_t*>(stats_smem) - sin);
+    for (int i = threadIdx.x; i < zbytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sin)[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int box_bytes = (p.R + 1) * p.WP * 128;
+  const int tile_bytes = p.R * p.W * 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, W_BYTES);
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_2d(&tmW, wfull, sw + ((tap % 3) * 3 + (2 - tap / 3)) * 8192, tap * 64, 0);
+      int it = 0;                                                  // CTA-local super-tile counter; region j lives in stage j
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cls = j == 0 ? 1 : (j == 1 ? 0 : j);          // class order 1, 0, 2, 3 (first touches of the accumulator)
+          uint64_t* fb = &full[(it & 1) * 4 + j];
+          mbar_wait(&empty[j], (uint32_t)(it & 1) ^ 1u);
+          if (p.variant & 16) {                      // experiment: no input traffic
+            mbar_arrive(fb);
+            continue;
+          }
+          mbar_expect_tx(fb, box_bytes);
+          tma_load_5d(&tmX, fb, sin + j * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n);
+        }
+      }
+    }
+  } else if (warp == F_EPI_WARP0 + F_EPI_WARPS) {
+    if (lane == 0 && p.n_extra) {
+      int sub = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
+        for (int co = 0; co < 4; ++co, ++sub) {
+          const int slot = sub & 1;
+          mbar_wait(&xempty[slot], ((sub >> 1) & 1) ^ 1);
+          mbar_expect_tx(&xfull[slot], tile_bytes);
+          tma_load_5d(&tmExtra, &xfull[slot], sx + slot * p.out_tile_bytes, 0, 0, co, i0, n);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // warp 1: even super-tiles of this CTA into accumulator 0 (TMEM columns 0-255), warp 2: odd ones into accumulator 1
+    const int mw = warp - 1;
+    constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0), idesc128 = umma_idesc_bf16(128, 128, 0, 0),
+                       idesc192 = umma_idesc_bf16(128, 192, 0, 0);
+    mbar_wait(wfull, 0);
+    const uint64_t b0 = umma_smem_desc(smem_u32(sw), 16, 1024);
+    const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
+    const uint32_t d_tmem = tmem_base + mw * 256;
+    const uint32_t row_adv = (uint32_t)(p.WP * 8);          // one region row further down: WP * 128 B >> 4
+    int it = mw;                                            // CTA-local super-tile counter
+    for (int tile = blockIdx.x + mw * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+      mbar_wait(&tempty[mw], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int stage = j;
+        mbar_wait(&full[mw * 4 + j], (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        const uint64_t a0 = a_desc(smem_u32(sin + stage * p.in_stage_bytes), 16, 0);
+        const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
+        if (elect_one()) {
+          if (j == 0) {                                     // class 1 -> co 0,1,2
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lohi(d_tmem, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc192, (s | k) != 0 ? 1u : 0u);
+          } else if (p.variant & 8) {                       // experiment: 12 of the 72 MMAs
+          } else if (j == 1) {                              // class 0: one row down -> co 3 (r = 2); same row -> co 0,1 (r = 1, 0)
+            if (!(p.variant & 4))                           // experiment bit 4: no wrap-around MMAs
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lohi(d_tmem + 192, a_lo + row_adv + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc64,
+                              (s | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lohi(d_tmem, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 512 + 2 * k, b_hi, idesc128, 1u);
+          } else if (j == 2) {                              // class 2 -> co 1,2,3
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lohi(d_tmem + 64, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc192, 1u);
+          } else {                                          // class 3 (region starts one row up): same row -> co 2,3; one row up -> co 0 (r = 0)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lohi(d_tmem + 128, a_lo + row_adv + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc128, 1u);
+            if (!(p.variant & 4))
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lohi(d_tmem, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 1024 + 2 * k, b_hi, idesc64, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (j == 3) umma_commit(&tfull[mw]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- epilogue: as in conv_tc64_fprop_kernel, one pass per output class (TMEM columns acc*256 + co*64 + ...)
+    const int e = warp - F_EPI_WARP0;
+    const int q = warp & 3, cq = e >> 2;
+    const int row = q * 32 + lane;                  // accumulator row = padded position hh*WP + ww
+    const int hh = row / p.WP, ww = row - hh * p.WP;
+    const bool row_ok = hh < p.R && ww < p.W;
+    const int col0 = cq * 16;
+    const int drow = hh * p.W + ww;
+    uint32_t soff[2];
+#pragma unroll
+    for (int j2 = 0; j2 < 2; ++j2) soff[j2] = (uint32_t)drow * 128u + ((uint32_t)((cq * 2 + j2) ^ (drow & 7)) << 4);
+    const bool issuer = threadIdx.x == F_EPI_WARP0 * 32;
+    float* bias_s = stats_smem + 16 * 2 * 16;
+    float* bnc = bias_s + 64;
+    if (e == 0) {
+      bias_s[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
+      bias_s[lane + 32] = p.bias ? __ldg(p.bias + lane + 32) : 0.f;
+    }
+    if (e == 1 && p.bn_bwd) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        bnc[c] = __ldg(p.bn_scale + c);
+        bnc[64 + c] = __ldg(p.bn_shift + c);
+        bnc[128 + c] = __ldg(p.bn_mean + c);
+        bnc[192 + c] = __ldg(p.bn_rstd + c);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+    float acc_s[16], acc_q[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc_s[j] = acc_q[j] = 0.f;
+    int nvalid = 0;
+    const bool want_stats = p.stats != nullptr;
+    const bf16* g_add = (p.n_extra && p.extra_is_add) ? nullptr : p.add_src;
+    const bf16* g_ref = (p.n_extra && !p.extra_is_add && !p.bn_bwd) ? nullptr : p.act_ref;
+    const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
+    const int nidx = p.H >> 2;                      // rows per class
+    int acc = 0, sub = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
+      const bool valid = row_ok && (i0 + hh) < nidx;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int co = 0; co < 4; ++co, ++sub) {
+        const int slot = sub & 1;
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + (uint32_t(q * 32) << 16) + acc * 256 + co * 64 + col0, r);
+        tmem_ld_wait();
+        if (co == 3) {
+          tc_fence_before();
+          mbar_arrive(&tempty[acc]);                // the last block is in registers: release the accumulator
+        }
+        if (p.variant & 2) continue;                // experiment: no epilogue work
+        float v[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + j4 * 4);
+          v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
+          v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+          v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
+          v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+        }
+        if (p.act == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        } else if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.n_extra) {
+          mbar_wait(&xfull[slot], (sub >> 1) & 1);
+          if (valid) {
+            const uint8_t* xt = sx + slot * p.out_tile_bytes;
+#pragma unroll
+            for (int j2 = 0; j2 < 2; ++j2) {
+              const uint4 u = *reinterpret_cast<const uint4*>(xt + soff[j2]);
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+              if (p.bn_bwd) {
+                float ca[8], cb[8], cm[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int c = col0 + j2 * 8 + h * 4;
+                  const float4 fa = *reinterpret_cast<const float4*>(bnc + c);
+                  const float4 fb = *reinterpret_cast<const float4*>(bnc + 64 + c);
+                  const float4 fm = *reinterpret_cast<const float4*>(bnc + 128 + c);
+                  ca[h * 4] = fa.x; ca[h * 4 + 1] = fa.y; ca[h * 4 + 2] = fa.z; ca[h * 4 + 3] = fa.w;
+                  cb[h * 4] = fb.x; cb[h * 4 + 1] = fb.y; cb[h * 4 + 2] = fb.z; cb[h * 4 + 3] = fb.w;
+                  cm[h * 4] = fm.x; cm[h * 4 + 1] = fm.y; cm[h * 4 + 2] = fm.z; cm[h * 4 + 3] = fm.w;
+                }
+                const float neg_bn = p.bn_act == ACT_LRELU ? p.bn_slope : (p.bn_act == ACT_RELU ? 0.f : 1.f);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
+                  const int j = j2 * 8 + t;
+                  const float g = fmaf(yv, ca[t], cb[t]) > 0.f ? v[j] : v[j] * neg_bn;
+                  acc_s[j] += g;
+                  acc_q[j] = fmaf(g, yv - cm[t], acc_q[j]);
+                }
+              } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float lo = __uint_as_float(w4[t] << 16), hi = __uint_as_float(w4[t] & 0xffff0000u);
+                  if (p.extra_is_add) {
+                    v[j2 * 8 + t * 2] += lo;
+                    v[j2 * 8 + t * 2 + 1] += hi;
+                  } else {
+                    v[j2 * 8 + t * 2] *= (lo > 0.f ? 1.f : neg);
+                    v[j2 * 8 + t * 2 + 1] *= (hi > 0.f ? 1.f : neg);
+                  }
+                }
+              }
+            }
+          }
+          mbar_arrive(&xempty[slot]);
+        }
+        if (valid && (g_add != nullptr || g_ref != nullptr)) {
+          const long long pix = ((long long)n * p.H + 4 * (i0 + hh) + co) * p.W + ww;
+          if (g_add != nullptr) {
+            const uint4* src = reinterpret_cast<const uint4*>(g_add + pix * C64 + col0);
+#pragma unroll
+            for (int j2 = 0; j2 < 2; ++j2) {
+              const uint4 u = __ldg(src + j2);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(h2[t]);
+                v[j2 * 8 + t * 2] += f.x;
+                v[j2 * 8 + t * 2 + 1] += f.y;
+              }
+            }
+          }
+          if (g_ref != nullptr) {
+            const uint4* src = reinterpret_cast<const uint4*>(g_ref + pix * C64 + col0);
+#pragma unroll
+            for (int j2 = 0; j2 < 2; ++j2) {
+              const uint4 u = __ldg(src + j2);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(h2[t]);
+                v[j2 * 8 + t * 2] *= (f.x > 0.f ? 1.f : neg);
+                v[j2 * 8 + t * 2 + 1] *= (f.y > 0.f ? 1.f : neg);
+              }
+            }
+          }
+        }
+        // staging slot `slot` was last read by the TMA store issued two passes ago
+        if (issuer) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+        if (valid) {
+          uint8_t* st = sout + slot * p.out_tile_bytes;
+#pragma unroll
+          for (int j2 = 0; j2 < 2; ++j2) {
+            uint4 u;
+            u.x = pack2(v[j2 * 8 + 0], v[j2 * 8 + 1]);
+            u.y = pack2(v[j2 * 8 + 2], v[j2 * 8 + 3]);
+            u.z = pack2(v[j2 * 8 + 4], v[j2 * 8 + 5]);
+            u.w = pack2(v[j2 * 8 + 6], v[j2 * 8 + 7]);
+            *reinterpret_cast<uint4*>(st + soff[j2]) = u;
+          }
+          if (want_stats && !p.bn_bwd) {
+            ++nvalid;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = __uint_as_float(r[j]);
+              acc_s[j] += a;
+              acc_q[j] = fmaf(a, a, acc_q[j]);
+            }
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+        if (issuer) {
+          tma_store_5d(&tmOut, sout + slot * p.out_tile_bytes, 0, 0, co, i0, n);
+          tma_store_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (issuer) tma_store_wait<0>();
+    if (want_stats) {
+      const float nv = (float)nvalid;
+      if (p.bn_bwd) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc_q[j] *= bnc[192 + col0 + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float b = bias_s[col0 + j], sa = acc_s[j];
+          acc_q[j] = acc_q[j] + 2.f * b * sa + nv * b * b;
+          acc_s[j] = sa + nv * b;
+        }
+      }
+      const float ts = colsum16(acc_s, lane);
+      const float tq = colsum16(acc_q, lane);
+      if (lane < 16) {
+        stats_smem[(e * 2 + 0) * 16 + lane] = ts;
+        stats_smem[(e * 2 + 1) * 16 + lane] = tq;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+      const int t = threadIdx.x - F_EPI_WARP0 * 32;
+      if (t < 128) {
+        const int which = t >> 6, col = t & 63;
+        const int c4 = col >> 4, l = col & 15;
+        float s = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) s += stats_smem[(((c4 * 4 + qq) * 2) + which) * 16 + l];
+        p.stats[(size_t)blockIdx.x * 128 + which * 64 + col] = s;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// variant bit 512 selects the stacked kernel.  It is parity-green but NOT the default: measured at B=512, 28x28
+// (profiles/exp_tc64_stacked_r1.md) it halves the MMA count (MMA-only time 35.5 -> 28.1 us) yet ends at 35.4 us against
+// 36.0 us (forward + statistics) and 39.5 against 37.3 us (data gradient + skip add): with four output classes per
+// accumulator the epilogue (four passes before the accumulator is released) and the one-super-tile-deep operand ring
+// are exposed instead of the MMAs.
+static bool use_stacked(int H, int W) { return (g_variant & 512) != 0 && H % 4 == 0 && conv_tc64_supported(H, W); }
+
+int conv_tc64_fprop_grid(int N, int H, int W) {
+  if (!use_stacked(H, W)) return conv_tc64_grid(N, H, W);
+  const int R = 128 / (W + 2);
+  const long long tiles = (long long)N * ((H / 4 + R - 1) / R);
+  const int sms = sm_count();
+  return (int)(tiles < sms ? tiles : sms);
+}
+
 void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const ConvEpilogue& epi, bf16* out,
                      cudaStream_t stream) {
   PCG_PROFILE("conv_tc64_fprop", stream);
@@ -501,7 +908,13 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.extra_is_add = (!p.bn_bwd && p.add_src != nullptr) ? 1 : 0;
   const bf16* extra = p.bn_bwd ? epi.bn_y : (p.add_src != nullptr ? p.add_src : p.act_ref);
   auto round1k = [](int b) { return (b + 1023) / 1024 * 1024; };
-  p.in_stage_bytes = round1k((p.R + 2) * p.WP * 128);
+  const bool stacked = use_stacked(H, W);
+  if (stacked) {                                   // a tile is a super-tile: R rows of each of the four row classes
+    p.tiles_per_img = (H / 4 + p.R - 1) / p.R;
+    p.total_tiles = N * p.tiles_per_img;
+  }
+  // stacked: a class region holds R+1 rows, and the last view starts WP + 2 rows in and spans 128 rows
+  p.in_stage_bytes = stacked ? round1k((128 + p.WP + 2) * 128) : round1k((p.R + 2) * p.WP * 128);
   p.out_tile_bytes = round1k(p.R * p.W * 128);
   p.in_stages = 4;
   auto total = [&]() {
@@ -509,15 +922,26 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   };
   while (total() > SMEM_LIMIT && p.in_stages > 2) --p.in_stages;
   PCG_REQUIRE(total() <= SMEM_LIMIT, "halo-tile kernel: shared-memory budget exceeded");
-  CUtensorMap tmX = make_tmap_nhwc_box(in, N, H, W, 64, p.WP, p.R + 2);
   CUtensorMap tmW = make_tmap_2d(wpk, 64, 576, 64);
-  CUtensorMap tmOut = make_tmap_nhwc_box(out, N, H, W, 64, W, p.R);
-  CUtensorMap tmExtra = make_tmap_nhwc_box(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
   static bool configured = false;
   if (!configured) {
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
+  if (stacked) {
+    PCG_REQUIRE(p.in_stages == 4, "stacked halo-tile kernel: four class regions must fit the ring");
+    CUtensorMap tmX = make_tmap_nhwc_rowclass(in, N, H, W, 64, p.WP, p.R + 1);
+    CUtensorMap tmOut = make_tmap_nhwc_rowclass(out, N, H, W, 64, W, p.R);
+    CUtensorMap tmExtra = make_tmap_nhwc_rowclass(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
+    conv_tc64s_fprop_kernel<<<conv_tc64_fprop_grid(N, H, W), F_THREADS, total(), stream>>>(tmX, tmW, tmOut, tmExtra, p);
+    PCG_COUNT_LAUNCH();
+    PCG_LAUNCH_CHECK();
+    return;
+  }
+  CUtensorMap tmX = make_tmap_nhwc_box(in, N, H, W, 64, p.WP, p.R + 2);
+  CUtensorMap tmOut = make_tmap_nhwc_box(out, N, H, W, 64, W, p.R);
+  CUtensorMap tmExtra = make_tmap_nhwc_box(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
   conv_tc64_fprop_kernel<<<conv_tc64_grid(N, H, W), F_THREADS, total(), stream>>>(tmX, tmW, tmOut, tmExtra, p);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();

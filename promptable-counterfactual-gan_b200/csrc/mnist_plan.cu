@@ -496,7 +496,7 @@ struct MnistPlan : PlanBase {
     if constexpr (kBf16 && std::is_same<TIn, bf16>::value && std::is_same<TOut, bf16>::value) {
       if (L.tc_fprop && L.tc64) {
         conv_tc64_fprop(in, g.N, g.H, g.W, L.tcf, to_tc(e, stats), out, s);
-        if (nparts) *nparts = conv_tc64_grid(g.N, g.H, g.W);
+        if (nparts) *nparts = conv_tc64_fprop_grid(g.N, g.H, g.W);
         return;
       }
       if (L.tc_fprop) {
@@ -880,7 +880,7 @@ struct MnistPlan : PlanBase {
           c.bn_y = y1[i]; c.bn_mean = qb.mean; c.bn_rstd = qb.rstd; c.bn_scale = qb.scale; c.bn_shift = qb.shift;
           c.bn_act = ACT_LRELU; c.bn_slope = 0.2f;
           conv_tc64_fprop(dy2[i], B, 28, 28, g_c2[i].tcd, c, dz1, s);
-          bn1_parts = conv_tc64_grid(B, 28, 28);
+          bn1_parts = conv_tc64_fprop_grid(B, 28, 28);
         }
       }
       if (bn1_parts == 0) {

@@ -83,6 +83,21 @@ __device__ __forceinline__ void tma_store_4d(const void* desc, const void* src, 
       "r"(smem_u32(src)), "r"(c), "r"(w), "r"(h), "r"(n)
       : "memory");
 }
+// 5-D tiled load / store (row-class view of an NHWC tensor): coordinates (c, w, class, idx, n).
+__device__ __forceinline__ void tma_load_5d(const void* desc, uint64_t* bar, void* dst, int c, int w, int k, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(k), "r"(h), "r"(n)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void* desc, const void* src, int c, int w, int k, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(desc)),
+      "r"(smem_u32(src)), "r"(c), "r"(w), "r"(k), "r"(h), "r"(n)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // waits until at most N of this thread's bulk groups are still READING shared memory / are incomplete
 template <int N>

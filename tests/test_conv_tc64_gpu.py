@@ -1,0 +1,130 @@
+"""Direct parity of the 64->64 halo-tile tcgen05 kernels (csrc/conv_tc64.cu) through their C-ABI entry points against a
+plain PyTorch fp32 reference of the same op on the same bf16-rounded operands (only the accumulation order and the final
+bf16 rounding differ: tolerance 1e-2 relative to the tensor's max, 2e-3 on the fp32 statistics / weight gradients).
+
+Both forward kernels are covered: the one-class-per-tile one (default) and the row-class stacked one (variant bit 512,
+H % 4 == 0; other heights fall back to the default kernel).  Replaces nn.Conv2d(64, 64, 3, padding=1) forward and
+ConvolutionBackward0 of conditional_counteRGAN/mnist/models/generator.py:11,14,49.  Ragged batch sizes exercise
+super-tiles whose last rows fall outside the image and grids smaller / larger than the SM count."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+_f = ctypes.c_float
+
+
+def _env():
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import _lib
+    return _lib.load(), _lib.ptr, _lib.stream_ptr(), _lib.check
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-30)).item()
+
+
+def nhwc_bf16(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2)
+
+
+def pack(L, P, st, check, w):
+    Cout, Cin, k, _ = w.shape
+    f = torch.empty(Cout, k * k, Cin, dtype=torch.bfloat16, device="cuda")
+    d = torch.empty(Cin, k * k, Cout, dtype=torch.bfloat16, device="cuda")
+    check(L.pcg_pack_conv_weights_tc(P(w), Cout, Cin, k, P(f), P(d), st))
+    return f, d
+
+
+@pytest.mark.parametrize("variant", [0, 512])
+@pytest.mark.parametrize("N,HW", [(3, 28), (8, 28), (301, 28), (5, 12), (5, 14)])
+def test_fprop_bias_stats_and_epilogues(N, HW, variant):
+    L, P, st, check = _env()
+    L.pcg_conv_tc64_set_variant(variant)
+    try:
+        torch.manual_seed(N * 100 + HW)
+        x = torch.randn(N, 64, HW, HW, device="cuda")
+        w = torch.randn(64, 64, 3, 3, device="cuda") * (2.0 / 576) ** 0.5
+        b = torch.randn(64, device="cuda") * 0.1
+        xn = nhwc_bf16(x)
+        wf, wd = pack(L, P, st, check, w)
+        wb = w.to(torch.bfloat16).float()
+        rows = L.pcg_conv_tc64_fprop_grid(N, HW, HW)
+        assert rows >= 1
+        # forward + bias + BatchNorm statistics
+        out = torch.full((N, HW, HW, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+        stats = torch.full((rows, 128), 1e9, device="cuda")
+        check(L.pcg_conv_tc64_fprop(P(xn), N, HW, HW, P(wf), P(b), 0, _f(0.2), None, None, 0, P(out), P(stats), st))
+        torch.cuda.synchronize()
+        ref = F.conv2d(nchw(xn), wb, b, padding=1)
+        assert rel(nchw(out), ref) < 1e-2
+        s = stats.double().sum(0)
+        assert rel(s[:64], ref.double().sum(dim=(0, 2, 3))) < 2e-3
+        assert rel(s[64:], (ref.double() ** 2).sum(dim=(0, 2, 3))) < 2e-3
+        # forward + bias + LeakyReLU + residual add (eval-mode residual block epilogue)
+        res = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda"))
+        out2 = torch.empty_like(out)
+        check(L.pcg_conv_tc64_fprop(P(xn), N, HW, HW, P(wf), P(b), 1, _f(0.2), P(res), None, 0, P(out2), None, st))
+        torch.cuda.synchronize()
+        ref2 = F.leaky_relu(ref, 0.2) + nchw(res)
+        assert rel(nchw(out2), ref2) < 1e-2
+        # data gradient (rotated packing) times the LeakyReLU derivative taken from an activation reference
+        dy = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda") * 0.1)
+        aref = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda"))
+        dx = torch.empty_like(out)
+        check(L.pcg_conv_tc64_fprop(P(dy), N, HW, HW, P(wd), None, 0, _f(0.2), None, P(aref), 1, P(dx), None, st))
+        torch.cuda.synchronize()
+        gref = F.conv_transpose2d(nchw(dy), wb, None, padding=1)
+        gref = gref * torch.where(nchw(aref) > 0, 1.0, 0.2)
+        assert rel(nchw(dx), gref) < 1e-2
+        # data gradient + skip-connection gradient
+        dx2 = torch.empty_like(out)
+        check(L.pcg_conv_tc64_fprop(P(dy), N, HW, HW, P(wd), None, 0, _f(0.2), P(res), None, 0, P(dx2), None, st))
+        torch.cuda.synchronize()
+        assert rel(nchw(dx2), F.conv_transpose2d(nchw(dy), wb, None, padding=1) + nchw(res)) < 1e-2
+    finally:
+        L.pcg_conv_tc64_set_variant(0)
+
+
+def test_stacked_and_one_class_kernels_agree():
+    """Same products, same fp32 accumulation per output element up to the order of the nine taps: the two kernels
+    must agree to bf16 rounding of identical fp32 sums almost everywhere (<= 1 bf16 ulp)."""
+    L, P, st, check = _env()
+    torch.manual_seed(5)
+    N, HW = 16, 28
+    xn = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda"))
+    w = torch.randn(64, 64, 3, 3, device="cuda") * 0.05
+    wf, _ = pack(L, P, st, check, w)
+    outs = []
+    for variant in (0, 512):
+        L.pcg_conv_tc64_set_variant(variant)
+        out = torch.empty(N, HW, HW, 64, dtype=torch.bfloat16, device="cuda")
+        check(L.pcg_conv_tc64_fprop(P(xn), N, HW, HW, P(wf), None, 0, _f(0.2), None, None, 0, P(out), None, st))
+        torch.cuda.synchronize()
+        outs.append(out.float())
+    L.pcg_conv_tc64_set_variant(0)
+    assert rel(outs[0], outs[1]) < 1e-2
+    assert (outs[0] != outs[1]).float().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("N,HW", [(3, 28), (8, 28), (5, 14)])
+def test_wgrad(N, HW):
+    L, P, st, check = _env()
+    torch.manual_seed(N)
+    xn = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda"))
+    dyn = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda") * 0.1)
+    grid = L.pcg_conv_tc64_grid(N, HW, HW)
+    part = torch.zeros(grid, 9 * 64 * 64, device="cuda")
+    dw = torch.zeros(64, 64, 3, 3, device="cuda")
+    check(L.pcg_conv_tc64_wgrad(P(xn), P(dyn), N, HW, HW, P(part), P(dw), st))
+    torch.cuda.synchronize()
+    wz = torch.zeros(64, 64, 3, 3, device="cuda", requires_grad=True)
+    yy = F.conv2d(nchw(xn), wz, None, padding=1)
+    (gw,) = torch.autograd.grad(yy, wz, nchw(dyn))
+    assert rel(dw, gw) < 2e-3
