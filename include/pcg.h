@@ -271,6 +271,19 @@ int pcg_rownorm_mean(const float* x, long long rows, int cols, int p, float* out
 int pcg_gan_loss(const float* z, int n, int kind, float t, float wgt, float* out_loss, float* out_aux, float* dz,
                  void* stream);
 int pcg_combine_scalars(int n, const float* host_coeffs, const float* const* host_ptrs, float* out, void* stream);
+/* One whole iteration of the two-layer MLP GANs on 2-D points in ONE launch (mlp_gan.cu): replaces the loop bodies of
+ * conditional_gan/moons/make_moons_cgan.py:90-129 and simple_gan/moons/make_moons_gan.py:61-88 - generator forward on
+ * (z1, oh1), discriminator on real + fake, loss_D = -mean(log D(real) + log(1 - D(fake))), Adam on D, generator forward on
+ * (z2, oh2), loss_G = -mean(log D(fake2)) through the UPDATED discriminator, Adam on G (lr, betas 0.9/0.999, eps 1e-8).
+ * A cluster of up to 8 CTAs, all weights in shared memory, gradients summed over the cluster in rank order.
+ *   hidden = 128, label_dim <= 2 (0: unconditional, the *_oh pointers may be NULL), z_dim + label_dim <= 36, B <= 1024.
+ *   *_param / *_grad / *_m / *_v: flat fp32 buffers [0.weight | 0.bias | 2.weight | 2.bias], every slice padded to a
+ *   multiple of 4 floats; *_step: int32 Adam step counters (incremented); scal[8]: 0 loss_D, 1 loss_G, 2 real term,
+ *   3 fake term, 4 mean D(real), 5 mean D(fake). */
+int pcg_mlp_gan_step(int B, int z_dim, int label_dim, int hidden, const float* real, const float* real_oh,
+                     const float* z1, const float* oh1, const float* z2, const float* oh2, float* g_param, float* g_grad,
+                     float* g_m, float* g_v, int* g_step, float* d_param, float* d_grad, float* d_m, float* d_v,
+                     int* d_step, float lr, float* scal, void* stream);
 int pcg_spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
                           float* sigma, void* stream);
 /* Same with the extra outputs a training pass needs in the same launch: WnT = Wn^T [K][N] (operand of the data

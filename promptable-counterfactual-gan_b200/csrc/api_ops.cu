@@ -186,6 +186,15 @@ int pcg_combine_scalars(int n, const float* coeffs, const float* const* ptrs, fl
   combine_scalars(t, out, ST);
   PCG_API_END
 }
+int pcg_mlp_gan_step(int B, int z_dim, int label_dim, int hidden, const float* real, const float* real_oh,
+                     const float* z1, const float* oh1, const float* z2, const float* oh2, float* g_param, float* g_grad,
+                     float* g_m, float* g_v, int* g_step, float* d_param, float* d_grad, float* d_m, float* d_v,
+                     int* d_step, float lr, float* scal, void* stream) {
+  PCG_API_BEGIN
+  mlp_gan_step(B, z_dim, label_dim, hidden, real, real_oh, z1, oh1, z2, oh2, g_param, g_grad, g_m, g_v, g_step, d_param,
+               d_grad, d_m, d_v, d_step, lr, scal, ST);
+  PCG_API_END
+}
 int pcg_spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float eps, int do_iter, float* Wn,
                           float* sigma, void* stream) {
   PCG_API_BEGIN

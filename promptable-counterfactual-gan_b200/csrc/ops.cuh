@@ -40,6 +40,12 @@ void spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float e
                        float* sigma, cudaStream_t s, float* WnT = nullptr, float* us = nullptr, float* vs = nullptr);
 void spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
                        const float* sigma, float* dW, cudaStream_t s);
+// Whole iteration of the two-layer MLP GANs (make_moons_cgan.py:90-129, make_moons_gan.py:61-88) in one cluster launch
+// (mlp_gan.cu); parameter / gradient / moment buffers use the flat layout of ops.py FlatParams (slices padded to 4).
+void mlp_gan_step(int B, int z_dim, int label_dim, int hidden, const float* real, const float* real_oh, const float* z1,
+                  const float* oh1, const float* z2, const float* oh2, float* g_param, float* g_grad, float* g_m,
+                  float* g_v, int* g_step, float* d_param, float* d_grad, float* d_m, float* d_v, int* d_step, float lr,
+                  float* scal, cudaStream_t stream);
 void gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y, cudaStream_t s);
 void softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, cudaStream_t s);
 void bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,

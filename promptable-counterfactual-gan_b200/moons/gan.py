@@ -6,7 +6,10 @@
     simple_gan/moons/make_moons_gan.py         build_generator / build_discriminator / train_gan                  :33-93
 
 One iteration = generator forward, discriminator forward on real+fake (batched), saturating log losses, both
-backward passes and both Adam updates, composed from libpcg operators and replayed as ONE CUDA graph.
+backward passes and both Adam updates.  Default: ONE launch of ``pcg_mlp_gan_step`` (csrc/mlp_gan.cu: a thread-block
+cluster with all weights in shared memory, warp-shuffle reductions, gradients summed through distributed shared
+memory).  Shapes outside that kernel's envelope (hidden != 128, batch > 1024, ...) and ``fused=False`` use the same
+iteration composed from libpcg's primitive operators and replayed as one CUDA graph.
 """
 import numpy as np
 import torch
@@ -68,8 +71,13 @@ def build_discriminator(hidden_dim, device="cuda"):
 class MlpGanPlan:
     """Fixed-batch native plan of one G+D iteration; ``label_dim = 0`` gives the unconditional GAN."""
 
-    def __init__(self, batch, z_dim, label_dim, hidden, device, lr=1e-3, use_graph=True):
+    def __init__(self, batch, z_dim, label_dim, hidden, device, lr=1e-3, use_graph=True, fused=None):
         self.B, self.zd, self.ld, self.H, self.lr = batch, z_dim, label_dim, hidden, lr
+        can_fuse = hidden == 128 and label_dim <= 2 and z_dim + label_dim <= 36 and batch <= 1024
+        if fused and not can_fuse:
+            raise ValueError("pcg_mlp_gan_step needs hidden == 128, label_dim <= 2, z_dim + label_dim <= 36, batch <= 1024")
+        self.fused = can_fuse if fused is None else fused
+        self._fn = None
         dev = self.dev = torch.device(device)
         gi, di = z_dim + label_dim, 2 + label_dim
         self.gi, self.di = gi, di
@@ -150,7 +158,31 @@ class MlpGanPlan:
         K.pack_weights(G.p("net.2.weight"), 1, wd=self.GW2t)
 
     def step(self, real, real_oh, z1, oh1, z2, oh2):
-        """Copies the injected draws into the static buffers and runs one iteration; returns the scalar block."""
+        """Runs one iteration on the injected draws; returns the scalar block."""
+        if self.fused:
+            # the iteration is ~15 us on the device: keep the host side of the call short (prepared argument tuple,
+            # raw data_ptr()s) so the step stays device-bound
+            if self._fn is None:
+                import ctypes
+                from .. import _lib
+                self._check = _lib.check
+                self._fn = _lib.load().pcg_mlp_gan_step
+                vp = ctypes.c_void_p
+                self._fn.argtypes = [ctypes.c_int] * 4 + [vp] * 16 + [ctypes.c_float, vp, vp]
+                G, D = self.G, self.D
+                self._static = tuple(t.data_ptr() for t in (G.data, G.grad, G.m, G.v, G.step, D.data, D.grad, D.m, D.v,
+                                                            D.step))
+                self._keep = []
+            ins = [real, real_oh, z1, oh1, z2, oh2]
+            for i, t in enumerate(ins):
+                if t is not None and not (t.dtype is torch.float32 and t.is_cuda and t.is_contiguous()):
+                    if not t.is_cuda:
+                        raise RuntimeError("pcg_b200: inputs must be CUDA tensors (there is no CPU fallback)")
+                    ins[i] = t.detach().float().contiguous()
+            self._keep = ins            # converted copies stay alive until the next call has been enqueued
+            self._check(self._fn(self.B, self.zd, self.ld, self.H, *[None if t is None else t.data_ptr() for t in ins],
+                                 *self._static, self.lr, self.scal.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            return self.scal
         for dst, src in ((self.real, real), (self.z1, z1), (self.z2, z2), (self.real_oh, real_oh), (self.oh1, oh1),
                          (self.oh2, oh2)):
             if dst is not None:

@@ -223,6 +223,14 @@ def combine(terms, out):
     _lib.check(_L().pcg_combine_scalars(n, coeffs, ptrs, P(out), _s()))
 
 
+def mlp_gan_step(B, z_dim, label_dim, hidden, real, real_oh, z1, oh1, z2, oh2, G, D, lr, scal):
+    """One whole iteration of the two-layer MLP GAN in one cluster launch (csrc/mlp_gan.cu); G, D are FlatParams."""
+    _chk(real, real_oh, z1, oh1, z2, oh2, G.data, G.grad, G.m, G.v, D.data, D.grad, D.m, D.v, scal)
+    _lib.check(_L().pcg_mlp_gan_step(B, z_dim, label_dim, hidden, P(real), P(real_oh), P(z1), P(oh1), P(z2), P(oh2),
+                                     P(G.data), P(G.grad), P(G.m), P(G.v), P(G.step), P(D.data), P(D.grad), P(D.m), P(D.v),
+                                     P(D.step), _f(lr), P(scal), _s()))
+
+
 def spectral_norm_fwd(W, u, v, Wn, sigma, do_iter=True, eps=1e-12, WnT=None, us=None, vs=None):
     """One power iteration (in place on u, v), sigma, Wn = W / sigma; optionally Wn^T and snapshots of u, v."""
     N, K = W.shape

@@ -12,14 +12,17 @@ def rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
-@pytest.mark.parametrize("label_dim,B,graph", [(2, 1024, True), (0, 128, True), (2, 50, False)])
-def test_gan_step_matches_oracle(label_dim, B, graph):
+@pytest.mark.parametrize("label_dim,B,graph,fused", [(2, 1024, True, False), (0, 128, True, False), (2, 50, False, False),
+                                                     (2, 1024, True, True), (0, 128, True, True), (2, 50, True, True),
+                                                     (2, 777, True, True), (0, 7, True, True)])
+def test_gan_step_matches_oracle(label_dim, B, graph, fused):
+    """fused = the whole iteration in one cluster launch (pcg_mlp_gan_step); else the operator-composed plan."""
     import pcg_b200  # noqa: F401
     from pcg_b200.moons.gan import MlpGanPlan
     gs, ds = M.shapes(label_dim=label_dim)
     PG, PD = M.synth_params(gs, 1), M.synth_params(ds, 2)
     S = M.make_state(PG, PD)
-    plan = MlpGanPlan(B, 32, label_dim, 128, "cuda", use_graph=graph)
+    plan = MlpGanPlan(B, 32, label_dim, 128, "cuda", use_graph=graph, fused=fused)
     plan.G.load({"net." + k: v for k, v in PG.items()})
     plan.D.load({"net." + k: v for k, v in PD.items()})
     plan.refresh()
