@@ -76,9 +76,10 @@ int pcg_conv_tc_wgrad64(const void* x, const void* dy, int N, int H, int W, floa
                         void* stream);
 /* Halo-tile variants for the 64->64 / 3x3 / stride-1 / pad-1 case (conv_tc64.cu): one TMA box per tile,
  * weights resident in shared memory, the nine taps are shifted views of the tile.  Same operand layouts as
- * pcg_conv_tc_fprop / pcg_conv_tc_wgrad64.  Variant bit 512 of pcg_conv_tc64_set_variant selects, when H % 4 == 0, the
- * row-class stacked forward / data-gradient kernel (four output row classes per accumulator, tap matrices stacked
- * along N: half the MMA instructions; same results, not faster end to end - see profiles/exp_tc64_stacked_r1.md).
+ * pcg_conv_tc_fprop / pcg_conv_tc_wgrad64.  When H % 4 == 0 the forward / data-gradient kernel is the row-class stacked
+ * one (four output row classes per accumulator, tap matrices stacked along N: half the MMA instructions, 27 % less
+ * shared-memory traffic; profiles/exp_tc64_stacked_r1.md); variant bit 256 of pcg_conv_tc64_set_variant selects the
+ * one-class-per-tile kernel (same results).
  * stats rows = pcg_conv_tc64_fprop_grid(N, H, W); wgrad part slices = pcg_conv_tc64_grid(N, H, W). */
 int pcg_conv_tc64_grid(int N, int H, int W);
 int pcg_conv_tc64_fprop_grid(int N, int H, int W);

@@ -11,13 +11,19 @@
 //
 // Replaces: nn.Conv2d(64, 64, 3, padding=1) forward and ConvolutionBackward0 (dgrad with rotated weights,
 // wgrad) of conditional_counteRGAN/mnist/models/generator.py:11,14,49.
+#include <cstdlib>
+
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 
 namespace pcg {
 using namespace tc;
 
-static int g_variant = 0;
+static int env_variant() {
+  const char* e = getenv("PCG_TC64_VARIANT");      // A/B switch for bench runs (same bits as pcg_conv_tc64_set_variant)
+  return e ? atoi(e) : 0;
+}
+static int g_variant = env_variant();
 void conv_tc64_set_variant(int v) { g_variant = v; }
 
 constexpr int C64 = 64;
@@ -27,7 +33,7 @@ constexpr int F_EPI_WARPS = 16;                  // 4 TMEM lane quarters x 4 col
 constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
 constexpr int F_EPI_WARP0 = 3;                  // warp0 TMA (input), warps 1-2 MMA (even / odd tiles), warps 3-18 epilogue,
 constexpr int F_THREADS = 32 * (F_EPI_WARP0 + F_EPI_WARPS + 1);   // warp19 TMA (epilogue operand)
-constexpr int F_TAIL_BYTES = (16 * 2 * 16 + 64 + 4 * 64) * 4 + 256;   // statistics scratch, bias, BN constants; barriers   // statistics scratch + bias, mbarriers + TMEM pointer
+constexpr int F_TAIL_BYTES = (16 * 2 * 16 + 64 + 4 * 64) * 4 + 512;   // statistics scratch, bias, BN constants; barriers   // statistics scratch + bias, mbarriers + TMEM pointer
 constexpr int SMEM_LIMIT = 232448;               // 227 KB opt-in maximum per CTA
 
 struct F64Params {
@@ -501,14 +507,16 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   uint8_t* sx = sout + 2 * p.out_tile_bytes;            // epilogue operand ring, 2 slots (if n_extra)
   float* stats_smem = reinterpret_cast<float*>(sx + (p.n_extra ? 2 : 0) * p.out_tile_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + (16 * 2 * 16 + 64 + 4 * 64) * 4);
-  uint64_t* full = bars;                 // [2][4]: one set per MMA warp (a warp only ever waits on its own set, in order)
-  uint64_t* empty = bars + 8;            // [4]
-  uint64_t* wfull = bars + 12;           // [1]
-  uint64_t* tfull = wfull + 1;           // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* full = bars;                 // [<= 8] ring of class regions
+  uint64_t* empty = bars + 8;            // [<= 8]
+  uint64_t* wfull = bars + 16;           // [1]
+  uint64_t* tfull = wfull + 1;           // [2][4] accumulator, output class: committed as soon as the class is complete
+  uint64_t* tempty = tfull + 8;          // [2]
   uint64_t* xfull = tempty + 2;          // [2]
   uint64_t* xempty = xfull + 2;          // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xempty + 2);
+  uint64_t* sfull = xempty + 2;          // [2] output staging slot written by all epilogue threads
+  uint64_t* sempty = sfull + 2;          // [2] ... and read out by its TMA store
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -517,11 +525,12 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmOut);
     if (p.n_extra) tma_prefetch_desc(&tmExtra);
-    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&full[4 + s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&tfull[s], 1); }
     mbar_init(wfull, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull[s], 1); mbar_init(&tempty[s], F_EPI_THREADS);
+      mbar_init(&tempty[s], F_EPI_THREADS);
       mbar_init(&xfull[s], 1); mbar_init(&xempty[s], F_EPI_THREADS);
+      mbar_init(&sfull[s], F_EPI_THREADS); mbar_init(&sempty[s], 1);
     }
     fence_barrier_init();
   }
@@ -547,20 +556,21 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       mbar_expect_tx(wfull, W_BYTES);
       for (int tap = 0; tap < 9; ++tap)
         tma_load_2d(&tmW, wfull, sw + ((tap % 3) * 3 + (2 - tap / 3)) * 8192, tap * 64, 0);
-      int it = 0;                                                  // CTA-local super-tile counter; region j lives in stage j
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int cls = j == 0 ? 1 : (j == 1 ? 0 : j);          // class order 1, 0, 2, 3 (first touches of the accumulator)
-          uint64_t* fb = &full[(it & 1) * 4 + j];
-          mbar_wait(&empty[j], (uint32_t)(it & 1) ^ 1u);
+          mbar_wait(&empty[stage], phase ^ 1);
           if (p.variant & 16) {                      // experiment: no input traffic
-            mbar_arrive(fb);
-            continue;
+            mbar_arrive(&full[stage]);
+          } else {
+            mbar_expect_tx(&full[stage], box_bytes);
+            tma_load_5d(&tmX, &full[stage], sin + stage * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n);
           }
-          mbar_expect_tx(fb, box_bytes);
-          tma_load_5d(&tmX, fb, sin + j * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n);
+          if (++stage == p.in_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -569,7 +579,8 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       int sub = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
-        for (int co = 0; co < 4; ++co, ++sub) {
+        for (int c = 0; c < 4; ++c, ++sub) {
+          const int co = c < 2 ? 1 - c : c;                        // the epilogue's class order 1, 0, 2, 3
           const int slot = sub & 1;
           mbar_wait(&xempty[slot], ((sub >> 1) & 1) ^ 1);
           mbar_expect_tx(&xfull[slot], tile_bytes);
@@ -577,23 +588,46 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // warp 1: even super-tiles of this CTA into accumulator 0 (TMEM columns 0-255), warp 2: odd ones into accumulator 1
-    const int mw = warp - 1;
+  } else if (warp == 2) {
+    // Store warp: the epilogue warps never meet at a CTA-wide barrier; each thread writes its 32 bytes of the staging
+    // slot, fences and arrives on sfull, this thread sends the slot off and hands it back through sempty once the
+    // TMA engine has read it, so the sixteen epilogue warps drift apart and hide each other's latencies.
+    if (lane == 0 && !(p.variant & 2)) {
+      int sub = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
+        for (int c = 0; c < 4; ++c, ++sub) {
+          const int co = c < 2 ? 1 - c : c;
+          const int slot = sub & 1;
+          mbar_wait(&sfull[slot], (sub >> 1) & 1);
+          tma_store_5d(&tmOut, sout + slot * p.out_tile_bytes, 0, 0, co, i0, n);
+          tma_store_commit();
+          if (sub >= 1) {
+            tma_store_wait_read<1>();                 // the previous store has read its slot
+            mbar_arrive(&sempty[slot ^ 1]);
+          }
+        }
+      }
+      tma_store_wait<0>();
+    }
+  } else if (warp == 1) {
+    // one MMA-issuing warp (the stacked MMAs last ~100 cycles, more than their issue cost): even super-tiles of this
+    // CTA into accumulator 0 (TMEM columns 0-255), odd ones into accumulator 1
     constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0), idesc128 = umma_idesc_bf16(128, 128, 0, 0),
                        idesc192 = umma_idesc_bf16(128, 192, 0, 0);
     mbar_wait(wfull, 0);
     const uint64_t b0 = umma_smem_desc(smem_u32(sw), 16, 1024);
     const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
-    const uint32_t d_tmem = tmem_base + mw * 256;
     const uint32_t row_adv = (uint32_t)(p.WP * 8);          // one region row further down: WP * 128 B >> 4
-    int it = mw;                                            // CTA-local super-tile counter
-    for (int tile = blockIdx.x + mw * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+    int it = 0, stage = 0;                                  // CTA-local super-tile counter, ring position
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int mw = it & 1;
+      const uint32_t d_tmem = tmem_base + mw * 256;
       mbar_wait(&tempty[mw], ((uint32_t)(it >> 1) & 1u) ^ 1u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int stage = j;
-        mbar_wait(&full[mw * 4 + j], (uint32_t)(it >> 1) & 1u);
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint64_t a0 = a_desc(smem_u32(sin + stage * p.in_stage_bytes), 16, 0);
         const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
@@ -624,23 +658,26 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16_lohi(d_tmem + 64, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc192, 1u);
-          } else {                                          // class 3 (region starts one row up): same row -> co 2,3; one row up -> co 0 (r = 0)
-#pragma unroll
-            for (int s = 0; s < 3; ++s)
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_lohi(d_tmem + 128, a_lo + row_adv + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc128, 1u);
+          } else {                                          // class 3 (region starts one row up): one row up -> co 0 (r = 0); same row -> co 2,3
             if (!(p.variant & 4))
 #pragma unroll
             for (int s = 0; s < 3; ++s)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16_lohi(d_tmem, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 1024 + 2 * k, b_hi, idesc64, 1u);
+            umma_commit(&tfull[mw * 4 + 0]);                // class 0 is complete
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lohi(d_tmem + 128, a_lo + row_adv + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc128, 1u);
           }
           umma_commit(&empty[stage]);
-          if (j == 3) umma_commit(&tfull[mw]);
+          if (j == 2) umma_commit(&tfull[mw * 4 + 1]);      // class 1 is complete after the class-2 input block
+          if (j == 3) { umma_commit(&tfull[mw * 4 + 2]); umma_commit(&tfull[mw * 4 + 3]); }
         }
         __syncwarp();
+        if (++stage == p.in_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -655,7 +692,6 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     uint32_t soff[2];
 #pragma unroll
     for (int j2 = 0; j2 < 2; ++j2) soff[j2] = (uint32_t)drow * 128u + ((uint32_t)((cq * 2 + j2) ^ (drow & 7)) << 4);
-    const bool issuer = threadIdx.x == F_EPI_WARP0 * 32;
     float* bias_s = stats_smem + 16 * 2 * 16;
     float* bnc = bias_s + 64;
     if (e == 0) {
@@ -687,11 +723,12 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
       const bool valid = row_ok && (i0 + hh) < nidx;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
 #pragma unroll 1
-      for (int co = 0; co < 4; ++co, ++sub) {
+      for (int c = 0; c < 4; ++c, ++sub) {
+        const int co = c < 2 ? 1 - c : c;           // classes in the order the MMA warp completes them: 1, 0, 2, 3
         const int slot = sub & 1;
+        mbar_wait(&tfull[acc * 4 + co], acc_phase);
+        tc_fence_after();
         uint32_t r[16];
         tmem_ld_32x16(tmem_base + (uint32_t(q * 32) << 16) + acc * 256 + co * 64 + col0, r);
         tmem_ld_wait();
@@ -794,8 +831,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           }
         }
         // staging slot `slot` was last read by the TMA store issued two passes ago
-        if (issuer) tma_store_wait_read<1>();
-        asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+        mbar_wait(&sempty[slot], ((sub >> 1) & 1) ^ 1);
         if (valid) {
           uint8_t* st = sout + slot * p.out_tile_bytes;
 #pragma unroll
@@ -818,16 +854,11 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           }
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
-        if (issuer) {
-          tma_store_5d(&tmOut, sout + slot * p.out_tile_bytes, 0, 0, co, i0, n);
-          tma_store_commit();
-        }
+        mbar_arrive(&sfull[slot]);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (issuer) tma_store_wait<0>();
     if (want_stats) {
       const float nv = (float)nvalid;
       if (p.bn_bwd) {
@@ -868,12 +899,12 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   }
 }
 
-// variant bit 512 selects the stacked kernel.  It is parity-green but NOT the default: measured at B=512, 28x28
-// (profiles/exp_tc64_stacked_r1.md) it halves the MMA count (MMA-only time 35.5 -> 28.1 us) yet ends at 35.4 us against
-// 36.0 us (forward + statistics) and 39.5 against 37.3 us (data gradient + skip add): with four output classes per
-// accumulator the epilogue (four passes before the accumulator is released) and the one-super-tile-deep operand ring
-// are exposed instead of the MMAs.
-static bool use_stacked(int H, int W) { return (g_variant & 512) != 0 && H % 4 == 0 && conv_tc64_supported(H, W); }
+// The stacked kernel is the default wherever it applies (H % 4 == 0); variant bit 256 selects the one-class-per-tile
+// kernel.  Measured at B=512, 28x28 (profiles/exp_tc64_stacked_r1.md): forward + statistics 34.1-35.4 us against
+// 35.9-36.0 us, data gradient + skip add 37.3 against 37.4 us, whole MNIST step 3.207 against 3.249 ms.  Both kernels
+// sit on the shared-memory bandwidth of the SM (operand reads of the MMAs + staging + TMA fills: ~790 KB against
+// ~1090 KB per 512 positions), not on the MMA count.
+static bool use_stacked(int H, int W) { return (g_variant & 256) == 0 && H % 4 == 0 && conv_tc64_supported(H, W); }
 
 int conv_tc64_fprop_grid(int N, int H, int W) {
   if (!use_stacked(H, W)) return conv_tc64_grid(N, H, W);
@@ -916,7 +947,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   // stacked: a class region holds R+1 rows, and the last view starts WP + 2 rows in and spans 128 rows
   p.in_stage_bytes = stacked ? round1k((128 + p.WP + 2) * 128) : round1k((p.R + 2) * p.WP * 128);
   p.out_tile_bytes = round1k(p.R * p.W * 128);
-  p.in_stages = 4;
+  p.in_stages = stacked ? 5 : 4;
   auto total = [&]() {
     return 1024 + W_BYTES + p.in_stages * p.in_stage_bytes + (2 + 2 * p.n_extra) * p.out_tile_bytes + F_TAIL_BYTES;
   };
@@ -930,7 +961,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     configured = true;
   }
   if (stacked) {
-    PCG_REQUIRE(p.in_stages == 4, "stacked halo-tile kernel: four class regions must fit the ring");
+    PCG_REQUIRE(p.in_stages >= 4, "stacked halo-tile kernel: four class regions must fit the ring");
     CUtensorMap tmX = make_tmap_nhwc_rowclass(in, N, H, W, 64, p.WP, p.R + 1);
     CUtensorMap tmOut = make_tmap_nhwc_rowclass(out, N, H, W, 64, W, p.R);
     CUtensorMap tmExtra = make_tmap_nhwc_rowclass(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);

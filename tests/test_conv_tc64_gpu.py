@@ -2,8 +2,8 @@
 plain PyTorch fp32 reference of the same op on the same bf16-rounded operands (only the accumulation order and the final
 bf16 rounding differ: tolerance 1e-2 relative to the tensor's max, 2e-3 on the fp32 statistics / weight gradients).
 
-Both forward kernels are covered: the one-class-per-tile one (default) and the row-class stacked one (variant bit 512,
-H % 4 == 0; other heights fall back to the default kernel).  Replaces nn.Conv2d(64, 64, 3, padding=1) forward and
+Both forward kernels are covered: the row-class stacked one (default when H % 4 == 0) and the one-class-per-tile one
+(variant bit 256, and every other height).  Replaces nn.Conv2d(64, 64, 3, padding=1) forward and
 ConvolutionBackward0 of conditional_counteRGAN/mnist/models/generator.py:11,14,49.  Ragged batch sizes exercise
 super-tiles whose last rows fall outside the image and grids smaller / larger than the SM count."""
 import ctypes
@@ -42,7 +42,7 @@ def pack(L, P, st, check, w):
     return f, d
 
 
-@pytest.mark.parametrize("variant", [0, 512])
+@pytest.mark.parametrize("variant", [0, 256])
 @pytest.mark.parametrize("N,HW", [(3, 28), (8, 28), (301, 28), (5, 12), (5, 14)])
 def test_fprop_bias_stats_and_epilogues(N, HW, variant):
     L, P, st, check = _env()
@@ -102,7 +102,7 @@ def test_stacked_and_one_class_kernels_agree():
     w = torch.randn(64, 64, 3, 3, device="cuda") * 0.05
     wf, _ = pack(L, P, st, check, w)
     outs = []
-    for variant in (0, 512):
+    for variant in (0, 256):
         L.pcg_conv_tc64_set_variant(variant)
         out = torch.empty(N, HW, HW, 64, dtype=torch.bfloat16, device="cuda")
         check(L.pcg_conv_tc64_fprop(P(xn), N, HW, HW, P(wf), None, 0, _f(0.2), None, None, 0, P(out), None, st))
