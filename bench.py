@@ -275,7 +275,7 @@ def run_native(args):
             plain_n = sum(v["launches"] for v in plain)
             frac_plain = (plain_n * CONV_FLOPS / (plain_ms * 1e-3) / 1e12 / peak) if plain_ms > 0 else None
             roof = {"bound": "tensor",
-                    "kernel": "conv_tc64_fprop_kernel (tcgen05 halo-tile conv 64->64, 13 fprop + 13 dgrad per step)",
+                    "kernel": "conv_tc64s_fprop_kernel (tcgen05 halo-tile conv 64->64, row-class stacked MMAs; 13 fprop + 13 dgrad per step)",
                     "frac_plain_conv_launches": frac_plain,
                     "plain_conv_avg_launch_us": (plain_ms / plain_n * 1e3) if plain_n else None,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,

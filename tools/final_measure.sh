@@ -1,0 +1,9 @@
+#!/bin/bash
+# round-end measurement batch (run under gpurun): bench lines, ncu launch list, ncu --set full of the dominant kernel
+R=${1:-r1e}
+mkdir -p gpurun_out
+python bench.py --steps 50 --warmup 5 > gpurun_out/bench_${R}_native.json 2> gpurun_out/bench_${R}_native.err; tail -c 600 gpurun_out/bench_${R}_native.json
+for w in cgan_moons simple_moons kc; do python bench.py --workload $w --steps 300 --warmup 30 2>/dev/null | tail -1; done > gpurun_out/bench_${R}_mlp_gan.jsonl
+cut -c1-200 gpurun_out/bench_${R}_mlp_gan.jsonl
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_${R}.csv python bench.py --steps 2 --warmup 1 --skip-cpu > gpurun_out/ncu_launch_${R}.log 2>&1; tail -2 gpurun_out/ncu_launch_${R}.log | cut -c1-200
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:conv_tc64s_fprop -s 30 -c 3 -o gpurun_out/prof_tc64s_fprop_${R} -f python bench.py --steps 2 --warmup 1 --skip-cpu > gpurun_out/ncu_full_${R}.log 2>&1; tail -2 gpurun_out/ncu_full_${R}.log | cut -c1-200
