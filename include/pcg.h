@@ -37,6 +37,13 @@ const char* pcg_last_error(void);
 int pcg_version(void);
 /* Kernels launched by this library since load (bench.py "gpu_launches"). */
 unsigned long long pcg_launch_count(void);
+/* Programmatic dependent launch: every kernel of the library lets its successor in the stream be launched early and
+ * waits for its predecessor's completion before touching global memory (griddepcontrol), hiding launch latency and
+ * prologues in the 100-1000-kernel steps.  Off by default (as a blanket policy it measured ~3 % slower on the MNIST
+ * step and 17 % slower on the 1000-node KC graph, profiles/exp_pdl_r1.md); env PCG_PDL=1 enables; returns the previous
+ * setting.
+ * A step captured into a CUDA graph keeps the mode it was captured with. */
+int pcg_set_pdl(int on);
 
 /* Per-launcher device timing: begin() enables CUDA-event brackets around every kernel launcher
  * (not usable during graph capture); end() synchronises, disables, and writes a JSON object

@@ -16,6 +16,11 @@ void set_last_error(const std::string& msg) { t_last_error = msg; }
 unsigned long long g_launch_count = 0;
 
 bool g_profile_on = false;
+static int env_pdl() {
+  const char* e = getenv("PCG_PDL");
+  return e ? (atoi(e) != 0) : 0;      // off by default: measured slower as a blanket policy (profiles/exp_pdl_r1.md)
+}
+int g_pdl = env_pdl();
 const char* g_prof_tag = nullptr;
 struct ProfRec { std::string name; cudaEvent_t e0, e1; };
 static std::vector<ProfRec> g_prof;
@@ -62,6 +67,7 @@ extern "C" {
 const char* pcg_last_error(void) { return t_last_error.c_str(); }
 int pcg_version(void) { return PCG_VERSION; }
 unsigned long long pcg_launch_count(void) { return g_launch_count; }
+int pcg_set_pdl(int on) { const int prev = g_pdl; g_pdl = on ? 1 : 0; return prev; }
 
 int pcg_profile_begin(void) {
   PCG_API_BEGIN

@@ -5,8 +5,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace pcg {
 
@@ -36,6 +38,39 @@ struct Error : std::runtime_error {
   } while (0)
 
 #define PCG_LAUNCH_CHECK() PCG_CHECK_CUDA(cudaGetLastError())
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Steps are chains of 100-1000 short dependent kernels; between two of them the GPU idles for the launch latency, the
+// CTA ramp and the successor's prologue.  Every kernel of this library therefore starts with pdl_enter(): it lets the
+// NEXT kernel of the stream be launched right away (griddepcontrol.launch_dependents) and then waits until the PREVIOUS
+// kernel has completed and flushed (griddepcontrol.wait) before touching global memory.  launch_k() launches with the
+// programmatic-stream-serialization attribute when PDL is on (env PCG_PDL=1 or pcg_set_pdl(1)); otherwise both
+// instructions are no-ops.  Works in eager streams and in captured graphs (programmatic kernel-node edges; all 70 GPU
+// parity tests pass in that mode).  OFF by default: with the wait at the top of every kernel there is no prologue to
+// overlap and a programmatic graph edge costs ~0.4 us more than a plain one (profiles/exp_pdl_r1.md: MNIST step 3.22
+// -> 3.32 ms, KC 2.18 -> 2.62 ms).  It pays only for kernels that do real work before pdl_wait().
+// Rule for kernel authors: no global-memory access before pdl_enter() / pdl_wait().
+extern int g_pdl;
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  PCG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
 
 // Number of SMs of the current device (cached).
 int sm_count();

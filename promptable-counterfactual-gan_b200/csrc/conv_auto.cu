@@ -76,6 +76,7 @@ static int terms() {
 // src fp32 [M][C] -> dst bf16 [M][T*C]; T = 3: (hi | lo | hi) or, with lo_last, (hi | hi | lo); T = 1: (hi)
 __global__ void split_bf16_kernel(const float* __restrict__ src, long long M, int C, int T, int lo_last,
                                   bf16* __restrict__ dst) {
+  pdl_enter();
   const long long n4 = M * C / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 4, row = e / C;
@@ -102,13 +103,14 @@ static bf16* split(int slot, const float* src, long long M, int C, int T, bool l
   PCG_PROFILE("convert", s);
   long long b = (M * C / 4 + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
-  split_bf16_kernel<<<(int)(b < cap ? (b > 0 ? b : 1) : cap), 256, 0, s>>>(src, M, C, T, lo_last ? 1 : 0, dst);
+  launch_k(split_bf16_kernel, dim3((int)(b < cap ? (b > 0 ? b : 1) : cap)), dim3(256), 0, s, src, M, C, T, lo_last ? 1 : 0, dst);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
   return dst;
 }
 // batch-tripled variant for wgrad: src fp32 [n] -> dst bf16 [T][n]; blocks (hi, lo, hi) or (hi, hi, lo)
 __global__ void split_batch_kernel(const float* __restrict__ src, long long n, int T, int lo_last, bf16* __restrict__ dst) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float f = src[i];
     const bf16 hi = __float2bfloat16_rn(f);
@@ -125,7 +127,7 @@ static bf16* split_batch(int slot, const float* src, long long n, int T, bool lo
   PCG_PROFILE("convert", s);
   long long b = (n + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
-  split_batch_kernel<<<(int)(b < cap ? (b > 0 ? b : 1) : cap), 256, 0, s>>>(src, n, T, lo_last ? 1 : 0, dst);
+  launch_k(split_batch_kernel, dim3((int)(b < cap ? (b > 0 ? b : 1) : cap)), dim3(256), 0, s, src, n, T, lo_last ? 1 : 0, dst);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
   return dst;

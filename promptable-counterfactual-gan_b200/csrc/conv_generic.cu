@@ -90,6 +90,7 @@ template <int MODE, typename TIn, typename TOut, bool VEC>
 __global__ void __launch_bounds__(256)
 gemm_conv_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt, TOut* __restrict__ dst,
                  long long M, int Nc, int K, int outH, int outW, Gather<MODE> ga, EpiDev<TOut> epi) {
+  pdl_enter();
   __shared__ float As[2][GK][GT + GPAD];
   __shared__ float Bs[2][GK][GT + GPAD];
   const int tid = threadIdx.x;
@@ -194,6 +195,7 @@ template <int MODE, typename TIn, typename TOut, int NC>
 __global__ void __launch_bounds__(256)
 skinny_conv_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt, TOut* __restrict__ dst,
                    long long M, int K, int outH, int outW, Gather<MODE> ga, EpiDev<TOut> epi) {
+  pdl_enter();
   extern __shared__ float wsm[];   // [NC][K]
   for (int i = threadIdx.x; i < NC * K; i += blockDim.x) wsm[i] = wgt[i];
   __syncthreads();
@@ -252,6 +254,7 @@ template <int MODE, typename TIn, typename TOut, int NC, int LPP>
 __global__ void __launch_bounds__(256)
 skinny_conv_v2_kernel(const TIn* __restrict__ src, const float* __restrict__ wgt, TOut* __restrict__ dst,
                       long long M, int K, int outH, int outW, Gather<MODE> ga, EpiDev<TOut> epi) {
+  pdl_enter();
   extern __shared__ float wsm[];   // [NC][K]
   for (int i = threadIdx.x; i < NC * K; i += blockDim.x) wsm[i] = wgt[i];
   __syncthreads();
@@ -319,7 +322,7 @@ static bool launch_skinny_v2(const TIn* src, const float* wgt, TOut* dst, long l
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-#define PCG_SK(L) skinny_conv_v2_kernel<MODE, TIn, TOut, NC, L><<<(int)blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e)
+#define PCG_SK(L) launch_k(skinny_conv_v2_kernel<MODE, TIn, TOut, NC, L>, dim3((int)blocks), dim3(256), sm, stream, src, wgt, dst, M, K, outH, outW, ga, e)
   switch (lpp) {
     case 1: PCG_SK(1); break;
     case 2: PCG_SK(2); break;
@@ -361,17 +364,17 @@ static void launch_conv(const TIn* src, const float* wgt, TOut* dst, long long M
     const size_t sm = (size_t)Nc * K * sizeof(float);
     PCG_REQUIRE(sm <= 48 * 1024, "skinny conv weights must fit 48 KB of shared memory");
     switch (Nc) {
-      case 1: skinny_conv_kernel<MODE, TIn, TOut, 1><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
-      case 2: skinny_conv_kernel<MODE, TIn, TOut, 2><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
-      case 3: skinny_conv_kernel<MODE, TIn, TOut, 3><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
-      default: skinny_conv_kernel<MODE, TIn, TOut, 4><<<blocks, 256, sm, stream>>>(src, wgt, dst, M, K, outH, outW, ga, e); break;
+      case 1: launch_k(skinny_conv_kernel<MODE, TIn, TOut, 1>, dim3(blocks), dim3(256), sm, stream, src, wgt, dst, M, K, outH, outW, ga, e); break;
+      case 2: launch_k(skinny_conv_kernel<MODE, TIn, TOut, 2>, dim3(blocks), dim3(256), sm, stream, src, wgt, dst, M, K, outH, outW, ga, e); break;
+      case 3: launch_k(skinny_conv_kernel<MODE, TIn, TOut, 3>, dim3(blocks), dim3(256), sm, stream, src, wgt, dst, M, K, outH, outW, ga, e); break;
+      default: launch_k(skinny_conv_kernel<MODE, TIn, TOut, 4>, dim3(blocks), dim3(256), sm, stream, src, wgt, dst, M, K, outH, outW, ga, e); break;
     }
   } else {
     dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((Nc + GT - 1) / GT));
     const bool vec = (ga.srcC % 4 == 0) && (K % 4 == 0) && (((uintptr_t)src & 15) == 0) &&
                      (((uintptr_t)wgt & 15) == 0);
-    if (vec) gemm_conv_kernel<MODE, TIn, TOut, true><<<grid, 256, 0, stream>>>(src, wgt, dst, M, Nc, K, outH, outW, ga, e);
-    else gemm_conv_kernel<MODE, TIn, TOut, false><<<grid, 256, 0, stream>>>(src, wgt, dst, M, Nc, K, outH, outW, ga, e);
+    if (vec) launch_k(gemm_conv_kernel<MODE, TIn, TOut, true>, dim3(grid), dim3(256), 0, stream, src, wgt, dst, M, Nc, K, outH, outW, ga, e);
+    else launch_k(gemm_conv_kernel<MODE, TIn, TOut, false>, dim3(grid), dim3(256), 0, stream, src, wgt, dst, M, Nc, K, outH, outW, ga, e);
   }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -408,6 +411,7 @@ template <typename TIn, typename TDy, bool VEC>
 __global__ void __launch_bounds__(256)
 wgrad_gemm_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, float* __restrict__ part, long long P,
                   int Cout, int K, int outH, int outW, long long slice, Gather<MODE_FPROP> ga) {
+  pdl_enter();
   __shared__ float As[2][GK][GT + GPAD];   // [pixel][co]
   __shared__ float Bs[2][GK][GT + GPAD];   // [pixel][k]
   const int tid = threadIdx.x;
@@ -510,6 +514,7 @@ template <typename TIn, typename TDy, int NC, int LPP>
 __global__ void __launch_bounds__(256)
 wgrad_skinny_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, float* __restrict__ part, long long P,
                     int K, int outH, int outW, Gather<MODE_FPROP> ga) {
+  pdl_enter();
   constexpr int PPW = 32 / LPP;
   constexpr int MAXTAPS = 9;
   extern __shared__ float red[];    // [8 warps][NC][K]
@@ -572,6 +577,7 @@ wgrad_skinny_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, float
 // part[z][co][(tap,ci)] -> dw[co][ci][tap] (torch OIHW), fixed order over z.
 __global__ void wgrad_reduce_generic_kernel(const float* __restrict__ part, int nz, int Cout, int Cin, int taps,
                                             float* __restrict__ dw) {
+  pdl_enter();
   const int K = taps * Cin;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * K) return;
@@ -584,7 +590,7 @@ __global__ void wgrad_reduce_generic_kernel(const float* __restrict__ part, int 
 
 void wgrad_reduce_generic(const float* part, int nz, int Cout, int Cin, int taps, float* dw, cudaStream_t stream) {
   PCG_PROFILE("wgrad_reduce", stream);
-  wgrad_reduce_generic_kernel<<<cdiv((long long)Cout * Cin * taps, 256), 256, 0, stream>>>(part, nz, Cout, Cin, taps, dw);
+  launch_k(wgrad_reduce_generic_kernel, dim3(cdiv((long long)Cout * Cin * taps, 256)), dim3(256), 0, stream, part, nz, Cout, Cin, taps, dw);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -623,7 +629,7 @@ void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float
   const int nz = wgrad_slices(g);
   if (wgrad_is_skinny(g) && (((uintptr_t)in) & 31) == 0) {
     const size_t sm = (size_t)8 * g.Cout * g.K() * sizeof(float);
-#define PCG_WS(L) wgrad_skinny_kernel<TIn, TDy, 1, L><<<WG_SKINNY_BLOCKS, 256, sm, stream>>>(in, dout, scratch, P, g.K(), g.Ho(), g.Wo(), ga)
+#define PCG_WS(L) launch_k(wgrad_skinny_kernel<TIn, TDy, 1, L>, dim3(WG_SKINNY_BLOCKS), dim3(256), sm, stream, in, dout, scratch, P, g.K(), g.Ho(), g.Wo(), ga)
     switch (g.Cin / 8) {
       case 1: PCG_WS(1); break;
       case 2: PCG_WS(2); break;
@@ -635,7 +641,7 @@ void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float
 #undef PCG_WS
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
-    wgrad_reduce_generic_kernel<<<cdiv((long long)g.Cout * g.K(), 256), 256, 0, stream>>>(scratch, nz, g.Cout, g.Cin,
+    launch_k(wgrad_reduce_generic_kernel, dim3(cdiv((long long)g.Cout * g.K(), 256)), dim3(256), 0, stream, scratch, nz, g.Cout, g.Cin,
                                                                                           g.ksize * g.ksize, dw);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
@@ -645,11 +651,11 @@ void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float
   dim3 grid(cdiv(g.Cout, GT), cdiv(g.K(), GT), nz);
   const bool vec = (g.Cin % 4 == 0) && (g.Cout % 4 == 0) && (((uintptr_t)in & 15) == 0) &&
                    (((uintptr_t)dout & 15) == 0);
-  if (vec) wgrad_gemm_kernel<TIn, TDy, true><<<grid, 256, 0, stream>>>(in, dout, scratch, P, g.Cout, g.K(), g.Ho(), g.Wo(), slice, ga);
-  else wgrad_gemm_kernel<TIn, TDy, false><<<grid, 256, 0, stream>>>(in, dout, scratch, P, g.Cout, g.K(), g.Ho(), g.Wo(), slice, ga);
+  if (vec) launch_k(wgrad_gemm_kernel<TIn, TDy, true>, dim3(grid), dim3(256), 0, stream, in, dout, scratch, P, g.Cout, g.K(), g.Ho(), g.Wo(), slice, ga);
+  else launch_k(wgrad_gemm_kernel<TIn, TDy, false>, dim3(grid), dim3(256), 0, stream, in, dout, scratch, P, g.Cout, g.K(), g.Ho(), g.Wo(), slice, ga);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
-  wgrad_reduce_generic_kernel<<<cdiv((long long)g.Cout * g.K(), 256), 256, 0, stream>>>(scratch, nz, g.Cout, g.Cin,
+  launch_k(wgrad_reduce_generic_kernel, dim3(cdiv((long long)g.Cout * g.K(), 256)), dim3(256), 0, stream, scratch, nz, g.Cout, g.Cin,
                                                                                         g.ksize * g.ksize, dw);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -658,6 +664,7 @@ void conv_wgrad_generic(const TIn* in, const TDy* dout, const ConvGeom& g, float
 // ------------------------------------------------------------------------------------------
 __global__ void pack_generic_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int perm_hw,
                                     float* __restrict__ wf, float* __restrict__ wd) {
+  pdl_enter();
   const int total = Cout * Cin * taps;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i % taps;
@@ -680,7 +687,7 @@ void pack_conv_weights_generic(const float* w, int Cout, int Cin, int ksize, int
   const int total = Cout * Cin * ksize * ksize;
   int blocks = cdiv(total, 256);
   if (blocks > 1184) blocks = 1184;
-  pack_generic_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, ksize * ksize, perm_hw, wf, wd);
+  launch_k(pack_generic_kernel, dim3(blocks), dim3(256), 0, stream, w, Cout, Cin, ksize * ksize, perm_hw, wf, wd);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

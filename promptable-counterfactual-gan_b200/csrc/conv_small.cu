@@ -43,6 +43,7 @@ template <int CIN>
 __global__ void __launch_bounds__(C1_THREADS, 2)
 conv_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict__ w9, const float* __restrict__ bias,
                 float* __restrict__ out, int H, int W, int WP, int R, int tiles_per_img, int total_tiles) {
+  pdl_enter();
   constexpr int ROWB = CIN * 2, KQ = CIN / 16, STAGE_BYTES = C1_ROWS * ROWB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -157,14 +158,14 @@ void conv_to1(const bf16* in, int N, int H, int W, int Cin, const bf16* w9, cons
       PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_to1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured = true;
     }
-    conv_to1_kernel<64><<<grid, C1_THREADS, smem, stream>>>(tmX, w9, bias, out, H, W, WP, R, tiles_per_img, total);
+    launch_k(conv_to1_kernel<64>, dim3(grid), dim3(C1_THREADS), smem, stream, tmX, w9, bias, out, H, W, WP, R, tiles_per_img, total);
   } else {
     static bool configured = false;
     if (!configured) {
       PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_to1_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured = true;
     }
-    conv_to1_kernel<32><<<grid, C1_THREADS, smem, stream>>>(tmX, w9, bias, out, H, W, WP, R, tiles_per_img, total);
+    launch_k(conv_to1_kernel<32>, dim3(grid), dim3(C1_THREADS), smem, stream, tmX, w9, bias, out, H, W, WP, R, tiles_per_img, total);
   }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(256, 2)
 conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const float* __restrict__ bias, int act,
                 float slope, const bf16* __restrict__ act_ref, float ref_neg, bf16* __restrict__ out, int H, int W,
                 int Ho, int Wo, long long M) {
+  pdl_enter();
   constexpr int K = 9 * CS, KS = (K + 15) / 16, NT = COUT / 8, CH = COUT / 8;
   __shared__ __align__(16) float stage[8][16][FEW_STAGE_LD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -346,7 +348,7 @@ static void launch_few(const TIn* in, int N, int H, int W, const bf16* wnk, cons
   const long long cap = (long long)sm_count() * 6;
   if (blocks > cap) blocks = cap;
   const float ref_neg = e.ref_act == ACT_LRELU ? e.ref_slope : 0.f;
-  conv_few_kernel<TIn, CS, COUT, STRIDE><<<(int)blocks, 256, 0, stream>>>(
+  launch_k(conv_few_kernel<TIn, CS, COUT, STRIDE>, dim3((int)blocks), dim3(256), 0, stream, 
       in, wnk, e.bias, e.act, e.slope, e.ref_act != ACT_NONE ? e.act_ref : nullptr, ref_neg, out, H, W, Ho, Wo, M);
 }
 
@@ -432,6 +434,7 @@ template <typename TIn, int CS, int STRIDE>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_few_kernel(const __grid_constant__ CUtensorMap tmDY, const TIn* __restrict__ in, int H, int W, int Ho, int Wo,
                  long long M, int ntiles, float* __restrict__ part) {
+  pdl_enter();
   constexpr int K = 9 * CS;                       // rows 0..K-1 of D: (tap, c); row K: the bias gradient; K + 1 <= 32
   extern __shared__ uint8_t smem_raw[];
   const WgRing ring = wg_setup(smem_raw, &tmDY);
@@ -528,6 +531,7 @@ wgrad_few_kernel(const __grid_constant__ CUtensorMap tmDY, const TIn* __restrict
 // dw[co][c][tap] = sum_b part[b][(tap*Cs + c)*64 + co];  db[co] = sum_b part[b][K*64 + co]
 __global__ void wgrad_few_reduce_kernel(const float* __restrict__ part, int nparts, int Cs, float* __restrict__ dw,
                                         float* __restrict__ db) {
+  pdl_enter();
   const int K = 9 * Cs;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (K + 1) * 64) return;
@@ -566,7 +570,7 @@ static void launch_wgrad_few(const TIn* in, const bf16* dy, int N, int H, int W,
     PCG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_few_kernel<TIn, CS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     configured = true;
   }
-  wgrad_few_kernel<TIn, CS, STRIDE><<<grid, WG_THREADS, WG_SMEM, stream>>>(tm, in, H, W, Ho, Wo, M, ntiles, part);
+  launch_k(wgrad_few_kernel<TIn, CS, STRIDE>, dim3(grid), dim3(WG_THREADS), WG_SMEM, stream, tm, in, H, W, Ho, Wo, M, ntiles, part);
 }
 
 template <typename TIn>
@@ -583,7 +587,7 @@ void wgrad_few(const TIn* in, const bf16* dy, int N, int H, int W, int Cs, int s
   }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
-  wgrad_few_reduce_kernel<<<cdiv((9 * Cs + 1) * 64, 128), 128, 0, stream>>>(part, grid, Cs, dw, db);
+  launch_k(wgrad_few_reduce_kernel, dim3(cdiv((9 * Cs + 1) * 64, 128)), dim3(128), 0, stream, part, grid, Cs, dw, db);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -593,6 +597,7 @@ template void wgrad_few<bf16>(const bf16*, const bf16*, int, int, int, int, int,
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict__ g, int H, int W, long long M,
                  int ntiles, float* __restrict__ part) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const WgRing ring = wg_setup(smem_raw, &tmX);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -680,6 +685,7 @@ wgrad_to1_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict
 }
 __global__ void wgrad_to1_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
                                         float* __restrict__ db) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > 1024) return;
   float s0 = 0.f, s1 = 0.f;
@@ -709,10 +715,10 @@ void wgrad_to1(const bf16* x, const bf16* g, int N, int H, int W, float* part, f
     configured = true;
   }
   const int grid = wgrad_to1_parts();
-  wgrad_to1_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(tm, g, H, W, M, ntiles, part);
+  launch_k(wgrad_to1_kernel, dim3(grid), dim3(WG_THREADS), WG_SMEM, stream, tm, g, H, W, M, ntiles, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
-  wgrad_to1_reduce_kernel<<<cdiv(1025, 128), 128, 0, stream>>>(part, grid, dw, db);
+  launch_k(wgrad_to1_reduce_kernel, dim3(cdiv(1025, 128)), dim3(128), 0, stream, part, grid, dw, db);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -726,6 +732,7 @@ constexpr int S2_SMEM = 1024 + S2_STAGES * S2_ROWS * 128 + 64 + S2_ROWS * 9 * 4;
 __global__ void __launch_bounds__(S2_THREADS, 2)
 dgrad_s2_to1_kernel(const __grid_constant__ CUtensorMap tmDY, const bf16* __restrict__ wrot, float* __restrict__ dx,
                     int N, int H, int W, int Ho, int Wo) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -836,7 +843,7 @@ void dgrad_s2_to1(const bf16* dy, int N, int H, int W, const bf16* wrot, float* 
   }
   int grid = 2 * sm_count();
   if (grid > N) grid = N;
-  dgrad_s2_to1_kernel<<<grid, S2_THREADS, S2_SMEM, stream>>>(tm, wrot, dx, N, H, W, Ho, Wo);
+  launch_k(dgrad_s2_to1_kernel, dim3(grid), dim3(S2_THREADS), S2_SMEM, stream, tm, wrot, dx, N, H, W, Ho, Wo);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

@@ -198,6 +198,7 @@ template <int BN>
 __global__ void __launch_bounds__(FPROP_THREADS, 1)
 conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const FpropParams p) {
+  pdl_enter();
   using Cfg = FpropCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -447,7 +448,7 @@ static void launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const F
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  conv_tc_fprop_kernel<BN><<<grid, FPROP_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_k(conv_tc_fprop_kernel<BN>, dim3(grid), dim3(FPROP_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -487,6 +488,7 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
 // ------------------------------------------------------------------------------------------
 __global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ c00,
                                      bf16* __restrict__ c01, bf16* __restrict__ c10, bf16* __restrict__ c11) {
+  pdl_enter();
   // class (ph,pw): taps_h = ph ? 2 : 1; window offset oh -> filter row r = ph ? (oh == 0 ? 2 : 0) : 1
   const int total = Cout * Cin * 9;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -507,6 +509,7 @@ size_t conv_tc_dgrad_s2_pack_elems(int Cout, int Cin) { return (size_t)Cout * Ci
 // (bf16x3 emulation of an fp32 product: hi*W_hi + lo*W_hi + hi*W_lo).
 __global__ void pack_dgrad_s2_k4_kernel(const float* __restrict__ wd, int Cout, int Cin, int dup,
                                         bf16* __restrict__ packed) {
+  pdl_enter();
   const int total = Cout * Cin * 16;
   const int ld = dup * Cout;
   const size_t u4 = (size_t)ld * Cin * 4;
@@ -527,7 +530,7 @@ __global__ void pack_dgrad_s2_k4_kernel(const float* __restrict__ wd, int Cout, 
 void pack_dgrad_s2_k4_tc(const float* wd, int Cout, int Cin, bf16* packed, cudaStream_t stream, int dup) {
   PCG_PROFILE("pack_weights", stream);
   const long long total = (long long)Cout * Cin * 16;
-  pack_dgrad_s2_k4_kernel<<<cdiv(total, 256) > 1184 ? 1184 : cdiv(total, 256), 256, 0, stream>>>(wd, Cout, Cin, dup, packed);
+  launch_k(pack_dgrad_s2_k4_kernel, dim3(cdiv(total, 256) > 1184 ? 1184 : cdiv(total, 256)), dim3(256), 0, stream, wd, Cout, Cin, dup, packed);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -535,7 +538,7 @@ void pack_dgrad_s2_k4_tc(const float* wd, int Cout, int Cin, bf16* packed, cudaS
 void pack_dgrad_s2_tc(const float* w, int Cout, int Cin, bf16* packed, cudaStream_t stream) {
   PCG_PROFILE("pack_weights", stream);
   const size_t u = (size_t)Cout * Cin;
-  pack_dgrad_s2_kernel<<<cdiv((long long)u * 9, 256) > 1184 ? 1184 : cdiv((long long)u * 9, 256), 256, 0, stream>>>(
+  launch_k(pack_dgrad_s2_kernel, dim3(cdiv((long long)u * 9, 256) > 1184 ? 1184 : cdiv((long long)u * 9, 256)), dim3(256), 0, stream, 
       w, Cout, Cin, packed, packed + u, packed + 3 * u, packed + 5 * u);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -599,6 +602,7 @@ constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_X_STAGE + 2 * WG_DY_BYTES + 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                        int M, int H, int W, int num_pblocks, float* __restrict__ part) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -760,6 +764,7 @@ template <int NT>
 __global__ void __launch_bounds__(WGG_THREADS, 1)
 conv_tc_wgrad_general_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                              const WggParams p) {
+  pdl_enter();
   using Cfg = WggCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -916,7 +921,7 @@ void conv_tc_wgrad_general(const bf16* x, const bf16* dy, int N, int H, int W, i
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, WggCfg<NTV>::SMEM_BYTES)); \
       configured = true;                                                                                           \
     }                                                                                                              \
-    conv_tc_wgrad_general_kernel<NTV><<<grid, WGG_THREADS, WggCfg<NTV>::SMEM_BYTES, stream>>>(tmX, tmDY, p);       \
+    launch_k(conv_tc_wgrad_general_kernel<NTV>, dim3(grid), dim3(WGG_THREADS), WggCfg<NTV>::SMEM_BYTES, stream, tmX, tmDY, p);       \
   }
   if (nt == 256) PCG_WGG(256) else if (nt == 128) PCG_WGG(128) else PCG_WGG(64)
 #undef PCG_WGG
@@ -944,13 +949,14 @@ void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* 
   }
   const int nb = (int)((M + TILE_M - 1) / TILE_M);
   const int grid = conv_tc_wgrad_grid(M);
-  conv_tc_wgrad64_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(tmX, tmDY, (int)M, H, W, nb, part);
+  launch_k(conv_tc_wgrad64_kernel, dim3(grid), dim3(WG_THREADS), WG_SMEM_BYTES, stream, tmX, tmDY, (int)M, H, W, nb, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 
 // part[cta][tap][ci][co] -> dw[co][ci][tap]; fixed summation order (deterministic).
 __global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (tap, ci, co), co fastest
   if (idx >= 9 * 64 * 64) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -968,7 +974,7 @@ __global__ void wgrad_reduce_tc_kernel(const float* __restrict__ part, int npart
 
 void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream) {
   PCG_PROFILE("wgrad_reduce_tc", stream);
-  wgrad_reduce_tc_kernel<<<cdiv(36864, 256), 256, 0, stream>>>(part, nparts, dw);
+  launch_k(wgrad_reduce_tc_kernel, dim3(cdiv(36864, 256)), dim3(256), 0, stream, part, nparts, dw);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -978,6 +984,7 @@ void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stre
 // ------------------------------------------------------------------------------------------
 __global__ void pack_conv_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int ksize,
                                             bf16* __restrict__ fprop, bf16* __restrict__ dgrad) {
+  pdl_enter();
   const int taps = ksize * ksize;
   const int total = Cout * Cin * taps;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -992,7 +999,7 @@ void pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, bf16* fp
                           cudaStream_t stream) {
   PCG_PROFILE("pack_weights", stream);
   const int total = Cout * Cin * ksize * ksize;
-  pack_conv_weights_tc_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, Cout, Cin, ksize, fprop, dgrad);
+  launch_k(pack_conv_weights_tc_kernel, dim3(cdiv(total, 256)), dim3(256), 0, stream, w, Cout, Cin, ksize, fprop, dgrad);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -1002,6 +1009,7 @@ void pack_conv_weights_tc(const float* w, int Cout, int Cin, int ksize, bf16* fp
 // ------------------------------------------------------------------------------------------
 __global__ void debug_im2col_kernel(const __grid_constant__ CUtensorMap tmA, int cblock, int cw, int ch,
                                     int n_img, int s, int r, bf16* __restrict__ out) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -1033,7 +1041,7 @@ void debug_im2col_tile(const bf16* in, int N, int H, int W, int Cin, int ksize, 
   const int hw = Ho * Wo;
   const int n_img = first_pixel / hw, rem = first_pixel % hw;
   const int cw = (rem % Wo) * stride - pad, ch = (rem / Wo) * stride - pad;
-  debug_im2col_kernel<<<1, 128, A_STAGE_BYTES + 1024 + 64, stream>>>(tmA, cblock, cw, ch, n_img, tap_s,
+  launch_k(debug_im2col_kernel, dim3(1), dim3(128), A_STAGE_BYTES + 1024 + 64, stream, tmA, cblock, cw, ch, n_img, tap_s,
                                                                       tap_r, out128x64);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();

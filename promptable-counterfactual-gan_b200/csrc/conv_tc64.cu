@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
                        const F64Params p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -498,6 +499,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
                         const F64Params p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -965,7 +967,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     CUtensorMap tmX = make_tmap_nhwc_rowclass(in, N, H, W, 64, p.WP, p.R + 1);
     CUtensorMap tmOut = make_tmap_nhwc_rowclass(out, N, H, W, 64, W, p.R);
     CUtensorMap tmExtra = make_tmap_nhwc_rowclass(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
-    conv_tc64s_fprop_kernel<<<conv_tc64_fprop_grid(N, H, W), F_THREADS, total(), stream>>>(tmX, tmW, tmOut, tmExtra, p);
+    launch_k(conv_tc64s_fprop_kernel, dim3(conv_tc64_fprop_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra, p);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
     return;
@@ -973,7 +975,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   CUtensorMap tmX = make_tmap_nhwc_box(in, N, H, W, 64, p.WP, p.R + 2);
   CUtensorMap tmOut = make_tmap_nhwc_box(out, N, H, W, 64, W, p.R);
   CUtensorMap tmExtra = make_tmap_nhwc_box(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
-  conv_tc64_fprop_kernel<<<conv_tc64_grid(N, H, W), F_THREADS, total(), stream>>>(tmX, tmW, tmOut, tmExtra, p);
+  launch_k(conv_tc64_fprop_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra, p);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -990,6 +992,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, int N, int H,
                        int W, int WP, int R, int tiles_per_img, int total_tiles, int variant,
                        float* __restrict__ part) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -1117,7 +1120,7 @@ void conv_tc64_wgrad(const bf16* x, const bf16* dy, int N, int H, int W, float* 
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
     configured = true;
   }
-  conv_tc64_wgrad_kernel<<<conv_tc64_grid(N, H, W), G_THREADS, G_SMEM_BYTES, stream>>>(
+  launch_k(conv_tc64_wgrad_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(G_THREADS), G_SMEM_BYTES, stream, 
       tmX, tmDY, N, H, W, WP, R, tiles_per_img, N * tiles_per_img, g_variant, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();

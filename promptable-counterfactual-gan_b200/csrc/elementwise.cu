@@ -139,6 +139,7 @@ static bool wide_ok(int C, std::initializer_list<const void*> ptrs) {
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 4) bn_stats_kernel(const T* __restrict__ y, long long M, int C,
                                                       float* __restrict__ part) {
+  pdl_enter();
   const int lpr = C / V, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
   const RowSlice sl = row_slice(M);
@@ -168,8 +169,8 @@ template <typename T>
 void bn_stats_partial(const T* y, long long M, int C, float* part, cudaStream_t s) {
   PCG_PROFILE("bn_stats", s);
   check_colshape(C);
-  if (wide_ok<T>(C, {y})) bn_stats_kernel<T, 8><<<STAT_PARTS, 256, 0, s>>>(y, M, C, part);
-  else bn_stats_kernel<T, 4><<<STAT_PARTS, 256, 0, s>>>(y, M, C, part);
+  if (wide_ok<T>(C, {y})) launch_k(bn_stats_kernel<T, 8>, dim3(STAT_PARTS), dim3(256), 0, s, y, M, C, part);
+  else launch_k(bn_stats_kernel<T, 4>, dim3(STAT_PARTS), dim3(256), 0, s, y, M, C, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -219,6 +220,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, l
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, long long* nbt,
                                    float* mean_o, float* rstd_o, float* scale, float* shift) {
+  pdl_enter();
   const int c = blockIdx.x;                                        // one block per channel
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
   const int cols[2] = {c, C + c};
@@ -246,7 +248,7 @@ void bn_finalize(const float* part, int nparts, long long M, int C, const float*
                  float eps, float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
                  float* rstd, float* scale, float* shift, cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  bn_finalize_kernel<<<C, FIN_THREADS, 0, s>>>(part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
+  launch_k(bn_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
                                                running_var, nbt, mean, rstd, scale, shift);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -265,6 +267,7 @@ template <typename T, int V, int ACT>
 __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, long long nv, int C,
                                                           float slope, T* __restrict__ z) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)((i0 * V) % C);
@@ -300,7 +303,7 @@ void bn_apply_act(const T* y, const float* scale, const float* shift, long long 
                   cudaStream_t s) {
   PCG_PROFILE("bn_apply", s);
   PCG_REQUIRE(C % 4 == 0, "C % 4");
-#define PCG_L(V, A) bn_apply_act_kernel<T, V, A><<<ew_blocks_periodic(nv, C / V), 256, 0, s>>>(y, scale, shift, nv, C, slope, z)
+#define PCG_L(V, A) launch_k(bn_apply_act_kernel<T, V, A>, dim3(ew_blocks_periodic(nv, C / V)), dim3(256), 0, s, y, scale, shift, nv, C, slope, z)
 #define PCG_LA(V) { if (act == ACT_LRELU) PCG_L(V, ACT_LRELU); else if (act == ACT_RELU) PCG_L(V, ACT_RELU); else PCG_L(V, ACT_NONE); }
   if (C % 8 == 0 && wide_ok<T>(8, {y, z})) {
     const long long nv = M * C / 8;
@@ -319,6 +322,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 bn_apply_residual_kernel(const T* __restrict__ y, const T* __restrict__ h, const float* __restrict__ scale,
                          const float* __restrict__ shift, float res_scale, long long nv, int C, T* __restrict__ out) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)((i0 * V) % C);
@@ -350,10 +354,10 @@ void bn_apply_residual(const T* y, const T* h, const float* scale, const float* 
   PCG_REQUIRE(C % 4 == 0, "C % 4");
   if (C % 8 == 0 && wide_ok<T>(8, {y, h, out})) {
     const long long nv = M * C / 8;
-    bn_apply_residual_kernel<T, 8><<<ew_blocks_periodic(nv, C / 8), 256, 0, s>>>(y, h, scale, shift, res_scale, nv, C, out);
+    launch_k(bn_apply_residual_kernel<T, 8>, dim3(ew_blocks_periodic(nv, C / 8)), dim3(256), 0, s, y, h, scale, shift, res_scale, nv, C, out);
   } else {
     const long long nv = M * C / 4;
-    bn_apply_residual_kernel<T, 4><<<ew_blocks_periodic(nv, C / 4), 256, 0, s>>>(y, h, scale, shift, res_scale, nv, C, out);
+    launch_k(bn_apply_residual_kernel<T, 4>, dim3(ew_blocks_periodic(nv, C / 4)), dim3(256), 0, s, y, h, scale, shift, res_scale, nv, C, out);
   }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -389,6 +393,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_bwd_partial_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const float* __restrict__ mean,
                       const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
                       float gscale, float slope, long long M, int C, float* __restrict__ part) {
+  pdl_enter();
   const int lpr = C >> 2, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
   const RowSlice sl = row_slice(M);
@@ -435,7 +440,7 @@ void bn_bwd_partial(const T* dsrc, const T* y, const float* mean, const float* r
                     cudaStream_t s) {
   PCG_PROFILE("bn_bwd_reduce", s);
   check_colshape(C);
-#define PCG_L(A) bn_bwd_partial_kernel<T, A><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, gscale, slope, M, C, part)
+#define PCG_L(A) launch_k(bn_bwd_partial_kernel<T, A>, dim3(STAT_PARTS), dim3(256), 0, s, dsrc, y, mean, rstd, scale, shift, gscale, slope, M, C, part)
   if (act == ACT_LRELU) PCG_L(ACT_LRELU);
   else if (act == ACT_RELU) PCG_L(ACT_RELU);
   else PCG_L(ACT_NONE);
@@ -446,6 +451,7 @@ void bn_bwd_partial(const T* dsrc, const T* y, const float* mean, const float* r
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, long long M, int C, float* dgamma,
                                        float* dbeta, float* c12) {
+  pdl_enter();
   const int c = blockIdx.x;
   const int cols[2] = {c, C + c};
   double sums[2];
@@ -461,7 +467,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
 void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* dgamma, float* dbeta, float* c12,
                      cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  bn_bwd_finalize_kernel<<<C, FIN_THREADS, 0, s>>>(part, nparts, M, C, dgamma, dbeta, c12);
+  launch_k(bn_bwd_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, M, C, dgamma, dbeta, c12);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -474,6 +480,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const f
                     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ c12, float gscale, float slope, long long M, int C,
                     T* __restrict__ dy, float* __restrict__ part_db) {
+  pdl_enter();
   const int lpr = C >> 2, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
   const RowSlice sl = row_slice(M);
@@ -526,7 +533,7 @@ void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rst
   PCG_PROFILE("bn_bwd_apply", s);
   (void)gamma;
   check_colshape(C);
-#define PCG_L(A) bn_bwd_apply_kernel<T, A><<<STAT_PARTS, 256, 0, s>>>(dsrc, y, mean, rstd, scale, shift, c12, gscale, slope, M, C, dy, part_db)
+#define PCG_L(A) launch_k(bn_bwd_apply_kernel<T, A>, dim3(STAT_PARTS), dim3(256), 0, s, dsrc, y, mean, rstd, scale, shift, c12, gscale, slope, M, C, dy, part_db)
   if (act == ACT_LRELU) PCG_L(ACT_LRELU);
   else if (act == ACT_RELU) PCG_L(ACT_RELU);
   else PCG_L(ACT_NONE);
@@ -536,6 +543,7 @@ void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rst
 }
 
 __global__ void colsum_finalize_kernel(const float* __restrict__ part, int nparts, int stride, int C, float* out) {
+  pdl_enter();
   const int c = blockIdx.x;
   const int cols[1] = {c};
   double sums[1];
@@ -544,7 +552,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ part, int npart
 }
 void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  colsum_finalize_kernel<<<C, FIN_THREADS, 0, s>>>(part, nparts, stride, C, out);
+  launch_k(colsum_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, stride, C, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -552,6 +560,7 @@ void colsum_finalize(const float* part, int nparts, int stride, int C, float* ou
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 4) colsum_kernel(const T* __restrict__ a, long long M, int C,
                                                     float* __restrict__ part) {
+  pdl_enter();
   const RowSlice sl = row_slice(M);
   if (V > 1) {
     const int lpr = C / V, rpp = 256 / lpr;
@@ -576,6 +585,7 @@ __global__ void __launch_bounds__(256, 4) colsum_kernel(const T* __restrict__ a,
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict__ a, long long M, int C,
                                                            float* __restrict__ part) {
+  pdl_enter();
   const RowSlice sl = row_slice(M);
   __shared__ float red[256];
   for (int c = 0; c < C; ++c) {
@@ -594,10 +604,10 @@ __global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict_
 template <typename T>
 void colsum_partial(const T* a, long long M, int C, float* part, cudaStream_t s) {
   PCG_PROFILE("colsum", s);
-  if (wide_ok<T>(C, {a})) colsum_kernel<T, 8><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
+  if (wide_ok<T>(C, {a})) launch_k(colsum_kernel<T, 8>, dim3(STAT_PARTS), dim3(256), 0, s, a, M, C, part);
   else if ((C & 3) == 0 && (256 % (C >> 2)) == 0 && C <= 1024 && (reinterpret_cast<uintptr_t>(a) % (4 * sizeof(T))) == 0)
-    colsum_kernel<T, 4><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
-  else colsum_scalar_kernel<T><<<STAT_PARTS, 256, 0, s>>>(a, M, C, part);
+    launch_k(colsum_kernel<T, 4>, dim3(STAT_PARTS), dim3(256), 0, s, a, M, C, part);
+  else launch_k(colsum_scalar_kernel<T>, dim3(STAT_PARTS), dim3(256), 0, s, a, M, C, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -609,6 +619,7 @@ template <typename T>
 __global__ void g_input_kernel(const float* __restrict__ x, const float* __restrict__ embed,
                                const long long* __restrict__ label, const float* __restrict__ mask, long long total,
                                int HW, T* __restrict__ out) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / HW), p = (int)(i - (long long)n * HW);
     out[i * 3 + 0] = from_f<T>(x[i]);
@@ -621,7 +632,7 @@ void g_input(const float* x, const float* embed, const long long* label, const f
              cudaStream_t s) {
   PCG_PROFILE("small", s);
   const long long total = (long long)B * HW;
-  g_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(x, embed, label, mask, total, HW, out);
+  launch_k(g_input_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, s, x, embed, label, mask, total, HW, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -629,6 +640,7 @@ void g_input(const float* x, const float* embed, const long long* label, const f
 template <typename T>
 __global__ void d_input_kernel(const float* __restrict__ x, const float* __restrict__ embed,
                                const long long* __restrict__ label, long long total, int HW, T* __restrict__ out) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / HW), p = (int)(i - (long long)n * HW);
     out[i * 2 + 0] = from_f<T>(x[i]);
@@ -639,7 +651,7 @@ template <typename T>
 void d_input(const float* x, const float* embed, const long long* label, int B, int HW, T* out, cudaStream_t s) {
   PCG_PROFILE("small", s);
   const long long total = (long long)B * HW;
-  d_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(x, embed, label, total, HW, out);
+  launch_k(d_input_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, s, x, embed, label, total, HW, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -648,6 +660,7 @@ void d_input(const float* x, const float* embed, const long long* label, int B, 
 template <typename T>
 __global__ void embed_grad_serial_kernel(const T* __restrict__ src, int nch, int ch, const long long* __restrict__ label,
                                          int B, int HW, float* __restrict__ dE) {
+  pdl_enter();
   const int cls = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
@@ -664,6 +677,7 @@ template <typename T>
 __global__ void __launch_bounds__(EG_WARPS * 32)
 embed_grad_kernel(const T* __restrict__ src, int nch, int ch, const long long* __restrict__ label, int B, int HW,
                   int num_classes, float* __restrict__ dE) {
+  pdl_enter();
   __shared__ float red[EG_WARPS][EG_CLS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + lane;
@@ -703,10 +717,10 @@ void embed_grad(const T* src, int nch, int ch, const long long* label, int B, in
                 cudaStream_t s) {
   PCG_PROFILE("embed_grad", s);
   if (num_classes <= EG_CLS) {
-    embed_grad_kernel<T><<<cdiv(HW, 32), EG_WARPS * 32, 0, s>>>(src, nch, ch, label, B, HW, num_classes, dE);
+    launch_k(embed_grad_kernel<T>, dim3(cdiv(HW, 32)), dim3(EG_WARPS * 32), 0, s, src, nch, ch, label, B, HW, num_classes, dE);
   } else {
     dim3 grid(cdiv(HW, 128), num_classes);
-    embed_grad_serial_kernel<T><<<grid, 128, 0, s>>>(src, nch, ch, label, B, HW, dE);
+    launch_k(embed_grad_serial_kernel<T>, dim3(grid), dim3(128), 0, s, src, nch, ch, label, B, HW, dE);
   }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -719,6 +733,7 @@ __global__ void __launch_bounds__(256)
 residual_head_fwd_kernel(const float* __restrict__ c, const float* __restrict__ x, const float* __restrict__ mask,
                          float rs, long long n, float* __restrict__ raw, float* __restrict__ masked,
                          float* __restrict__ x_cf, float* __restrict__ part) {
+  pdl_enter();
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long b = (long long)blockIdx.x * per, e = b + per < n ? b + per : n;
   float s0 = 0.f, s1 = 0.f;
@@ -746,7 +761,7 @@ residual_head_fwd_kernel(const float* __restrict__ c, const float* __restrict__ 
 void residual_head_fwd(const float* c, const float* x, const float* mask, float rs, long long n, float* raw,
                        float* masked, float* x_cf, float* part, cudaStream_t s) {
   PCG_PROFILE("residual_head", s);
-  residual_head_fwd_kernel<<<STAT_PARTS, 256, 0, s>>>(c, x, mask, rs, n, raw, masked, x_cf, part);
+  launch_k(residual_head_fwd_kernel, dim3(STAT_PARTS), dim3(256), 0, s, c, x, mask, rs, n, raw, masked, x_cf, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -758,6 +773,7 @@ __global__ void residual_head_bwd_kernel(const float* __restrict__ dxd, int dxd_
                                          const float* __restrict__ raw, const float* __restrict__ x,
                                          const float* __restrict__ mask, float rs, float lreg, float lmask,
                                          long long n, T* __restrict__ g_c) {
+  pdl_enter();
   const float inv_n = 1.f / (float)n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float r = raw[i], m = mask[i];
@@ -774,7 +790,7 @@ template <typename T>
 void residual_head_bwd(const float* dxd, int dxd_ch, const float* dxc, const float* raw, const float* x,
                        const float* mask, float rs, float lreg, float lmask, long long n, T* g_c, cudaStream_t s) {
   PCG_PROFILE("residual_head", s);
-  residual_head_bwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>(dxd, dxd_ch, dxc, raw, x, mask, rs, lreg, lmask, n, g_c);
+  launch_k(residual_head_bwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), 0, s, dxd, dxd_ch, dxc, raw, x, mask, rs, lreg, lmask, n, g_c);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -785,6 +801,7 @@ void residual_head_bwd(const float* dxd, int dxd_ch, const float* dxc, const flo
 template <typename T>
 __global__ void d_head_fwd_kernel(const T* __restrict__ z, int B, int HW, int C, const float* __restrict__ w,
                                   const float* __restrict__ b, float* __restrict__ logits) {
+  pdl_enter();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= B) return;
@@ -800,7 +817,7 @@ __global__ void d_head_fwd_kernel(const T* __restrict__ z, int B, int HW, int C,
 template <typename T>
 void d_head_fwd(const T* z, int B, int HW, int C, const float* w, const float* b, float* logits, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  d_head_fwd_kernel<T><<<cdiv(B, 8), 256, 0, s>>>(z, B, HW, C, w, b, logits);
+  launch_k(d_head_fwd_kernel<T>, dim3(cdiv(B, 8)), dim3(256), 0, s, z, B, HW, C, w, b, logits);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -821,6 +838,7 @@ __device__ __forceinline__ float block_sum_1024(float v, float* red) {
 // one block per segment
 __global__ void bce_logits_kernel(const float* __restrict__ logits, int seg, float t0, float t1, float w0, float w1,
                                   float* out_loss, float* out_p, float* __restrict__ dlogit) {
+  pdl_enter();
   __shared__ float red[32];
   const int sidx = blockIdx.x;
   const float t = sidx == 0 ? t0 : t1, wgt = sidx == 0 ? w0 : w1;
@@ -843,7 +861,7 @@ void bce_logits(const float* logits, int seg, int nseg, float t0, float t1, floa
                 float* out_p, float* dlogit, cudaStream_t s) {
   PCG_PROFILE("small", s);
   PCG_REQUIRE(nseg == 1 || nseg == 2, "1 or 2 segments");
-  bce_logits_kernel<<<nseg, 256, 0, s>>>(logits, seg, t0, t1, w0, w1, out_loss, out_p, dlogit);
+  launch_k(bce_logits_kernel, dim3(nseg), dim3(256), 0, s, logits, seg, t0, t1, w0, w1, out_loss, out_p, dlogit);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -852,6 +870,7 @@ void bce_logits(const float* logits, int seg, int nseg, float t0, float t1, floa
 template <typename T>
 __global__ void d_head_bwd_kernel(const T* __restrict__ z, const float* __restrict__ dlogit, int HW, int C,
                                   const float* __restrict__ w, float slope, T* __restrict__ g) {
+  pdl_enter();
   const int n = blockIdx.x;
   const float dl = dlogit[n] / (float)HW;
   for (int i = threadIdx.x; i < HW * C; i += blockDim.x) {
@@ -867,6 +886,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 d_head_wgrad_kernel(const T* __restrict__ z, const float* __restrict__ dlogit, int B, int HW, int C,
                     float* __restrict__ part, float* __restrict__ db) {
+  pdl_enter();
   const int per = (B + gridDim.x - 1) / gridDim.x;
   const int n0 = blockIdx.x * per, n1 = n0 + per < B ? n0 + per : B;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -890,11 +910,11 @@ void d_head_bwd(const T* z, const float* dlogit, int B, int HW, int C, const flo
                 float* db, float* scratch, cudaStream_t s) {
   {
     PCG_PROFILE("small", s);
-    d_head_bwd_kernel<T><<<B, 256, 0, s>>>(z, dlogit, HW, C, w, slope, g);
+    launch_k(d_head_bwd_kernel<T>, dim3(B), dim3(256), 0, s, z, dlogit, HW, C, w, slope, g);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
     if (dw != nullptr) {
-      d_head_wgrad_kernel<T><<<DHW_SLICES, 256, 0, s>>>(z, dlogit, B, HW, C, scratch, db);
+      launch_k(d_head_wgrad_kernel<T>, dim3(DHW_SLICES), dim3(256), 0, s, z, dlogit, B, HW, C, scratch, db);
       PCG_COUNT_LAUNCH();
       PCG_LAUNCH_CHECK();
     }
@@ -904,6 +924,7 @@ void d_head_bwd(const T* z, const float* dlogit, int B, int HW, int C, const flo
 
 __global__ void ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int B, int NC,
                                float wgt, float* loss, float* __restrict__ dlogits) {
+  pdl_enter();
   __shared__ float red[32];
   float sl = 0.f;
   for (int n = threadIdx.x; n < B; n += blockDim.x) {
@@ -926,12 +947,13 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, const long long
 void ce_loss(const float* logits, const long long* target, int B, int NC, float wgt, float* loss, float* dlogits,
              cudaStream_t s) {
   PCG_PROFILE("small", s);
-  ce_loss_kernel<<<1, 256, 0, s>>>(logits, target, B, NC, wgt, loss, dlogits);
+  launch_k(ce_loss_kernel, dim3(1), dim3(256), 0, s, logits, target, B, NC, wgt, loss, dlogits);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 
 __global__ void l1_finalize_kernel(const float* __restrict__ part, int nparts, float inv_n, float* out2) {
+  pdl_enter();
   const int c = threadIdx.x >> 5;
   if (c < 2) {
     const double s = warp_colsum(part, nparts, 2, c);
@@ -940,19 +962,20 @@ __global__ void l1_finalize_kernel(const float* __restrict__ part, int nparts, f
 }
 void l1_finalize(const float* part, int nparts, float inv_n, float* out2, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  l1_finalize_kernel<<<1, 64, 0, s>>>(part, nparts, inv_n, out2);
+  launch_k(l1_finalize_kernel, dim3(1), dim3(64), 0, s, part, nparts, inv_n, out2);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 
 __global__ void g_loss_combine_kernel(const float* g_adv, const float* g_cls, const float* reg, const float* mpen,
                                       float la, float lc, float lr, float lm, float* out) {
+  pdl_enter();
   out[0] = la * g_adv[0] + lc * g_cls[0] + lr * reg[0] + lm * mpen[0];
 }
 void g_loss_combine(const float* g_adv, const float* g_cls, const float* reg, const float* mpen, float la, float lc,
                     float lr, float lm, float* out, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  g_loss_combine_kernel<<<1, 1, 0, s>>>(g_adv, g_cls, reg, mpen, la, lc, lr, lm, out);
+  launch_k(g_loss_combine_kernel, dim3(1), dim3(1), 0, s, g_adv, g_cls, reg, mpen, la, lc, lr, lm, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -964,6 +987,7 @@ __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  long long n, const int* __restrict__ step, float lr, float beta1, float beta2, float eps,
                  float grad_scale) {
+  pdl_enter();
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const double t = (double)(*step + 1);
@@ -985,40 +1009,43 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     v[i] = vi;
   }
 }
-__global__ void adam_step_inc_kernel(int* step) { *step += 1; }
+__global__ void adam_step_inc_kernel(int* step) {
+  pdl_enter(); *step += 1; }
 
 void adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
                float beta2, float eps, float grad_scale, cudaStream_t s) {
   PCG_PROFILE("adam", s);
-  adam_flat_kernel<<<ew_blocks(n), 256, 0, s>>>(p, g, m, v, n, step, lr, beta1, beta2, eps, grad_scale);
+  launch_k(adam_flat_kernel, dim3(ew_blocks(n)), dim3(256), 0, s, p, g, m, v, n, step, lr, beta1, beta2, eps, grad_scale);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
-  adam_step_inc_kernel<<<1, 1, 0, s>>>(step);
+  launch_k(adam_step_inc_kernel, dim3(1), dim3(1), 0, s, step);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 
 template <typename T>
 __global__ void fill_zero_kernel(T* p, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = from_f<T>(0.f);
 }
 template <typename T>
 void fill_zero(T* p, long long n, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  fill_zero_kernel<T><<<ew_blocks(n), 256, 0, s>>>(p, n);
+  launch_k(fill_zero_kernel<T>, dim3(ew_blocks(n)), dim3(256), 0, s, p, n);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 template <typename T>
 __global__ void convert_kernel(const float* __restrict__ src, long long n, T* __restrict__ dst) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f<T>(src[i]);
 }
 template <typename T>
 void convert_from_f32(const float* src, long long n, T* dst, cudaStream_t s) {
   PCG_PROFILE("pack_weights", s);
-  convert_kernel<T><<<ew_blocks(n), 256, 0, s>>>(src, n, dst);
+  launch_k(convert_kernel<T>, dim3(ew_blocks(n)), dim3(256), 0, s, src, n, dst);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

@@ -72,6 +72,7 @@ struct PackDesc {
 };
 constexpr int PACK_MAX_LAYERS = 40;
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int nlayers, int total) {
+  pdl_enter();
   __shared__ PackDesc d[PACK_MAX_LAYERS];
   for (int i = threadIdx.x; i < nlayers * (int)(sizeof(PackDesc) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(table)[i];
@@ -116,7 +117,7 @@ struct PackTable {
     PCG_PROFILE("pack_weights", s);
     int blocks = cdiv(total, 256 * 4);
     if (blocks > 1184) blocks = 1184;
-    pack_multi_kernel<<<blocks, 256, 0, s>>>(dev, nlayers, total);
+    launch_k(pack_multi_kernel, dim3(blocks), dim3(256), 0, s, dev, nlayers, total);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
   }
@@ -134,6 +135,7 @@ struct FoldDesc {
   int Cout, Cin, taps;
 };
 __global__ void __launch_bounds__(256) fold_bn_kernel(const FoldDesc* __restrict__ table, float eps) {
+  pdl_enter();
   const FoldDesc L = table[blockIdx.y];
   const int total = L.Cout * L.Cin * L.taps;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -673,7 +675,7 @@ struct MnistPlan : PlanBase {
   void g_fwd_eval(const float* x, const long long* target, const float* mask, cudaStream_t s) {
     {
       PCG_PROFILE("pack_weights", s);
-      fold_bn_kernel<<<dim3(36, fold_n), 256, 0, s>>>(fold_dev, 1e-5f);
+      launch_k(fold_bn_kernel, dim3(dim3(36, fold_n)), dim3(256), 0, s, fold_dev, 1e-5f);
       PCG_COUNT_LAUNCH();
       PCG_LAUNCH_CHECK();
     }
@@ -961,6 +963,7 @@ struct MnistPlan : PlanBase {
 
 __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                       int C, float* mean, float* rstd, float* scale, float* shift) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float r = 1.0f / sqrtf(rv[c] + eps);
@@ -970,7 +973,7 @@ __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, con
 }
 template <typename T>
 void MnistPlan<T>::bn_eval_coeffs(const BN& q, cudaStream_t s) {
-  bn_eval_coeffs_kernel<<<cdiv(ch, 64), 64, 0, s>>>(q.gamma, q.beta, q.running_mean, q.running_var, 1e-5f, ch, q.mean,
+  launch_k(bn_eval_coeffs_kernel, dim3(cdiv(ch, 64)), dim3(64), 0, s, q.gamma, q.beta, q.running_mean, q.running_var, 1e-5f, ch, q.mean,
                                                    q.rstd, q.scale, q.shift);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();

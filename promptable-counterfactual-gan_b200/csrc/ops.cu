@@ -16,6 +16,7 @@ static int blocks_for(long long n) {
 
 // ------------------------------------------------------------------ elementwise
 __global__ void unary_kernel(const float* __restrict__ x, long long n, int op, float a, float* __restrict__ y) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     const float v = x[i];
     float r;
@@ -33,7 +34,7 @@ __global__ void unary_kernel(const float* __restrict__ x, long long n, int op, f
 }
 void unary(const float* x, long long n, int op, float a, float* y, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  unary_kernel<<<blocks_for(n), 256, 0, s>>>(x, n, op, a, y);
+  launch_k(unary_kernel, dim3(blocks_for(n)), dim3(256), 0, s, x, n, op, a, y);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -41,6 +42,7 @@ void unary(const float* x, long long n, int op, float a, float* y, cudaStream_t 
 // dx = dy * f'(.) evaluated from the activation OUTPUT y
 __global__ void unary_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n, int op,
                                  float a, float* __restrict__ dx) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     const float o = y[i], g = dy[i];
     float r;
@@ -57,7 +59,7 @@ __global__ void unary_bwd_kernel(const float* __restrict__ dy, const float* __re
 }
 void unary_bwd(const float* dy, const float* y, long long n, int op, float a, float* dx, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  unary_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(dy, y, n, op, a, dx);
+  launch_k(unary_bwd_kernel, dim3(blocks_for(n)), dim3(256), 0, s, dy, y, n, op, a, dx);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -65,6 +67,7 @@ void unary_bwd(const float* dy, const float* y, long long n, int op, float a, fl
 // out = alpha * a (op) b   with op in {add, mul}; b may broadcast over rows when b_cols > 0 (b is [cols])
 __global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int op,
                               float alpha, float beta, float* __restrict__ out) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     const float x = a[i], y = b[i];
     out[i] = op == OP_MUL ? alpha * x * y : alpha * x + beta * y;
@@ -72,7 +75,7 @@ __global__ void binary_kernel(const float* __restrict__ a, const float* __restri
 }
 void binary(const float* a, const float* b, long long n, int op, float alpha, float beta, float* out, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  binary_kernel<<<blocks_for(n), 256, 0, s>>>(a, b, n, op, alpha, beta, out);
+  launch_k(binary_kernel, dim3(blocks_for(n)), dim3(256), 0, s, a, b, n, op, alpha, beta, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -80,6 +83,7 @@ void binary(const float* a, const float* b, long long n, int op, float alpha, fl
 // FiLM (house_sales_kc_usa/models/generator.py:13-16,28-35): one launch for  out = [relu](gamma * n + beta) [+ res]
 __global__ void film_fwd_kernel(const float* __restrict__ gamma, const float* __restrict__ n_, const float* __restrict__ beta,
                                 const float* __restrict__ res, long long n, int relu, float* __restrict__ out) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     float v = fmaf(gamma[i], n_[i], beta[i]);
     if (relu) v = fmaxf(v, 0.f);
@@ -89,7 +93,7 @@ __global__ void film_fwd_kernel(const float* __restrict__ gamma, const float* __
 void film_fwd(const float* gamma, const float* n_, const float* beta, const float* res, long long n, int relu, float* out,
               cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  film_fwd_kernel<<<blocks_for(n), 256, 0, s>>>(gamma, n_, beta, res, n, relu, out);
+  launch_k(film_fwd_kernel, dim3(blocks_for(n)), dim3(256), 0, s, gamma, n_, beta, res, n, relu, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -97,6 +101,7 @@ void film_fwd(const float* gamma, const float* n_, const float* beta, const floa
 __global__ void film_bwd_kernel(const float* __restrict__ df, const float* __restrict__ gamma, const float* __restrict__ n_,
                                 long long n, int accumulate, float* __restrict__ dn, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     const float d = df[i];
     dn[i] = d * gamma[i];
@@ -108,7 +113,7 @@ __global__ void film_bwd_kernel(const float* __restrict__ df, const float* __res
 void film_bwd(const float* df, const float* gamma, const float* n_, long long n, int accumulate, float* dn, float* dgamma,
               float* dbeta, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  film_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(df, gamma, n_, n, accumulate, dn, dgamma, dbeta);
+  launch_k(film_bwd_kernel, dim3(blocks_for(n)), dim3(256), 0, s, df, gamma, n_, n, accumulate, dn, dgamma, dbeta);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -116,6 +121,7 @@ void film_bwd(const float* df, const float* gamma, const float* n_, long long n,
 // dst_i = src_i^T for up to TRANSPOSE_MAX small matrices in one launch (the dgrad operands of every Linear layer of a
 // tabular net after its Adam update)
 __global__ void transpose_multi_kernel(const TransposeTable t) {
+  pdl_enter();
   GRID_STRIDE(g, (long long)t.begin[t.n]) {
     int l = 0;
     while (l + 1 < t.n && g >= t.begin[l + 1]) ++l;
@@ -126,7 +132,7 @@ __global__ void transpose_multi_kernel(const TransposeTable t) {
 }
 void transpose_multi(const TransposeTable& t, cudaStream_t s) {
   PCG_PROFILE("pack_weights", s);
-  transpose_multi_kernel<<<blocks_for(t.begin[t.n]), 256, 0, s>>>(t);
+  launch_k(transpose_multi_kernel, dim3(blocks_for(t.begin[t.n])), dim3(256), 0, s, t);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -135,6 +141,7 @@ void transpose_multi(const TransposeTable& t, cudaStream_t s) {
 // accumulate != 0 adds instead of overwriting (gradient of a tensor used twice).
 __global__ void copy_cols_kernel(const float* __restrict__ src, int src_ld, int c0_src, float* __restrict__ dst,
                                  int dst_ld, int c0_dst, long long rows, int ncols, float alpha, int accumulate) {
+  pdl_enter();
   const long long n = rows * ncols;
   GRID_STRIDE(i, n) {
     const long long r = i / ncols;
@@ -147,7 +154,7 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int src_ld, int 
 void copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld, int c0_dst, long long rows, int ncols,
                float alpha, int accumulate, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  copy_cols_kernel<<<blocks_for(rows * ncols), 256, 0, s>>>(src, src_ld, c0_src, dst, dst_ld, c0_dst, rows, ncols, alpha,
+  launch_k(copy_cols_kernel, dim3(blocks_for(rows * ncols)), dim3(256), 0, s, src, src_ld, c0_src, dst, dst_ld, c0_dst, rows, ncols, alpha,
                                                            accumulate);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -155,6 +162,7 @@ void copy_cols(const float* src, int src_ld, int c0_src, float* dst, int dst_ld,
 
 __global__ void onehot_kernel(const long long* __restrict__ lab, long long rows, int nc, float* __restrict__ dst,
                               int dst_ld, int c0) {
+  pdl_enter();
   const long long n = rows * nc;
   GRID_STRIDE(i, n) {
     const long long r = i / nc;
@@ -164,7 +172,7 @@ __global__ void onehot_kernel(const long long* __restrict__ lab, long long rows,
 }
 void onehot(const long long* lab, long long rows, int nc, float* dst, int dst_ld, int c0, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  onehot_kernel<<<blocks_for(rows * nc), 256, 0, s>>>(lab, rows, nc, dst, dst_ld, c0);
+  launch_k(onehot_kernel, dim3(blocks_for(rows * nc)), dim3(256), 0, s, lab, rows, nc, dst, dst_ld, c0);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -186,6 +194,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // out = scale * sum_i f(x_i), f in {id, abs}; optional dx_i = gscale * f'(x_i)   (sign(0) = 0 as torch.abs backward)
 __global__ void reduce_scalar_kernel(const float* __restrict__ x, long long n, int absval, float scale, float* out,
                                      float gscale, float* __restrict__ dx) {
+  pdl_enter();
   __shared__ float red[32];
   float s = 0.f;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
@@ -199,7 +208,7 @@ __global__ void reduce_scalar_kernel(const float* __restrict__ x, long long n, i
 void reduce_scalar(const float* x, long long n, int absval, float scale, float* out, float gscale, float* dx,
                    cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  reduce_scalar_kernel<<<1, 1024, 0, s>>>(x, n, absval, scale, out, gscale, dx);
+  launch_k(reduce_scalar_kernel, dim3(1), dim3(1024), 0, s, x, n, absval, scale, out, gscale, dx);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -207,6 +216,7 @@ void reduce_scalar(const float* x, long long n, int absval, float scale, float* 
 // out = mean_r ||x_r||_p (p = 1 or 2); dx_r = gscale/rows * d||x_r||_p / dx   (zero sub-gradient at x_r = 0 for p=2)
 __global__ void rownorm_mean_kernel(const float* __restrict__ x, long long rows, int cols, int p, float* out,
                                     float gscale, float* __restrict__ dx) {
+  pdl_enter();
   __shared__ float red[32];
   float s = 0.f;
   for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -232,7 +242,7 @@ __global__ void rownorm_mean_kernel(const float* __restrict__ x, long long rows,
 }
 void rownorm_mean(const float* x, long long rows, int cols, int p, float* out, float gscale, float* dx, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  rownorm_mean_kernel<<<1, 1024, 0, s>>>(x, rows, cols, p, out, gscale, dx);
+  launch_k(rownorm_mean_kernel, dim3(1), dim3(1024), 0, s, x, rows, cols, p, out, gscale, dx);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -245,6 +255,7 @@ void rownorm_mean(const float* x, long long rows, int cols, int p, float* out, f
 // kind 2 (Wasserstein, moons/trainer.py:77,83): loss = sign * mean z ; dz = wgt * sign / n   (t=1 -> sign=-1)
 __global__ void gan_loss_kernel(const float* __restrict__ z, int n, int kind, float t, float wgt, float* out_loss,
                                 float* out_aux, float* __restrict__ dz) {
+  pdl_enter();
   __shared__ float red[32];
   float sl = 0.f, sp = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -273,20 +284,21 @@ __global__ void gan_loss_kernel(const float* __restrict__ z, int n, int kind, fl
 void gan_loss(const float* z, int n, int kind, float t, float wgt, float* out_loss, float* out_aux, float* dz,
               cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  gan_loss_kernel<<<1, 256, 0, s>>>(z, n, kind, t, wgt, out_loss, out_aux, dz);
+  launch_k(gan_loss_kernel, dim3(1), dim3(256), 0, s, z, n, kind, t, wgt, out_loss, out_aux, dz);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 
 // out[0] = sum_i c_i * in_i[0]  (up to 6 scalar terms)
 __global__ void combine_kernel(ScalarTerms t, float* out) {
+  pdl_enter();
   float s = 0.f;
   for (int i = 0; i < t.n; ++i) s += t.c[i] * t.p[i][0];
   out[0] = s;
 }
 void combine_scalars(const ScalarTerms& t, float* out, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  combine_kernel<<<1, 1, 0, s>>>(t, out);
+  launch_k(combine_kernel, dim3(1), dim3(1), 0, s, t, out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -299,6 +311,7 @@ void combine_scalars(const ScalarTerms& t, float* out, cudaStream_t s) {
 __global__ void spectral_norm_fwd_kernel(const float* __restrict__ W, int N, int K, float* u, float* v, float eps,
                                          int do_iter, float* __restrict__ Wn, float* sigma_out,
                                          float* __restrict__ WnT, float* __restrict__ us, float* __restrict__ vs) {
+  pdl_enter();
   extern __shared__ float sm[];     // u[N], v[K], red[32]
   float* su = sm;
   float* sv = sm + N;
@@ -366,7 +379,7 @@ void spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float e
                        float* sigma, cudaStream_t s, float* WnT, float* us, float* vs) {
   PCG_PROFILE("ops_small", s);
   const size_t sm = (size_t)(N + K + 40) * sizeof(float);
-  spectral_norm_fwd_kernel<<<1, 256, sm, s>>>(W, N, K, u, v, eps, do_iter, Wn, sigma, WnT, us, vs);
+  launch_k(spectral_norm_fwd_kernel, dim3(1), dim3(256), sm, s, W, N, K, u, v, eps, do_iter, Wn, sigma, WnT, us, vs);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -374,6 +387,7 @@ void spectral_norm_fwd(const float* W, int N, int K, float* u, float* v, float e
 __global__ void spectral_norm_bwd_kernel(const float* __restrict__ dWn, const float* __restrict__ Wn, int N, int K,
                                          const float* __restrict__ u, const float* __restrict__ v,
                                          const float* __restrict__ sigma, float* __restrict__ dW) {
+  pdl_enter();
   __shared__ float red[32];
   __shared__ float s_dot;
   float part = 0.f;
@@ -390,7 +404,7 @@ __global__ void spectral_norm_bwd_kernel(const float* __restrict__ dWn, const fl
 void spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const float* u, const float* v,
                        const float* sigma, float* dW, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  spectral_norm_bwd_kernel<<<1, 256, 0, s>>>(dWn, Wn, N, K, u, v, sigma, dW);
+  launch_k(spectral_norm_bwd_kernel, dim3(1), dim3(256), 0, s, dWn, Wn, N, K, u, v, sigma, dW);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -399,6 +413,7 @@ void spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const fl
 // y = softmax((logits + g) / tau) ; backward dlogits = y .* (dy - sum_j dy_j y_j) / tau
 __global__ void gumbel_softmax_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ g, long long rows,
                                           int n, float tau, float* __restrict__ y) {
+  pdl_enter();
   GRID_STRIDE(r, rows) {
     const float* l = logits + r * n;
     const float* gg = g + r * n;
@@ -411,12 +426,13 @@ __global__ void gumbel_softmax_fwd_kernel(const float* __restrict__ logits, cons
 }
 void gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  gumbel_softmax_fwd_kernel<<<blocks_for(rows), 256, 0, s>>>(logits, g, rows, n, tau, y);
+  launch_k(gumbel_softmax_fwd_kernel, dim3(blocks_for(rows)), dim3(256), 0, s, logits, g, rows, n, tau, y);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 __global__ void softmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long rows, int n,
                                    float tau, float* __restrict__ dl) {
+  pdl_enter();
   GRID_STRIDE(r, rows) {
     float dot = 0.f;
     for (int j = 0; j < n; ++j) dot = fmaf(dy[r * n + j], y[r * n + j], dot);
@@ -425,7 +441,7 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ dy, const float* __
 }
 void softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  softmax_bwd_kernel<<<blocks_for(rows), 256, 0, s>>>(dy, y, rows, n, tau, dl);
+  launch_k(softmax_bwd_kernel, dim3(blocks_for(rows)), dim3(256), 0, s, dy, y, rows, n, tau, dl);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -434,6 +450,7 @@ void softmax_bwd(const float* dy, const float* y, long long rows, int n, float t
 __global__ void bn_eval_kernel(const float* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ rm,
                                const float* __restrict__ rv, float eps, float* __restrict__ y, float* __restrict__ scale_out) {
+  pdl_enter();
   const long long n = rows * C;
   GRID_STRIDE(i, n) {
     const int c = (int)(i % C);
@@ -445,19 +462,20 @@ __global__ void bn_eval_kernel(const float* __restrict__ x, long long rows, int 
 void bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,
              const float* rv, float eps, float* y, float* scale_out, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  bn_eval_kernel<<<blocks_for(rows * C), 256, 0, s>>>(x, rows, C, gamma, beta, rm, rv, eps, y, scale_out);
+  launch_k(bn_eval_kernel, dim3(blocks_for(rows * C)), dim3(256), 0, s, x, rows, C, gamma, beta, rm, rv, eps, y, scale_out);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 // dx = dy * scale[c]
 __global__ void scale_cols_kernel(const float* __restrict__ dy, long long rows, int C, const float* __restrict__ scale,
                                   float* __restrict__ dx) {
+  pdl_enter();
   const long long n = rows * C;
   GRID_STRIDE(i, n) dx[i] = dy[i] * scale[i % C];
 }
 void scale_cols(const float* dy, long long rows, int C, const float* scale, float* dx, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  scale_cols_kernel<<<blocks_for(rows * C), 256, 0, s>>>(dy, rows, C, scale, dx);
+  launch_k(scale_cols_kernel, dim3(blocks_for(rows * C)), dim3(256), 0, s, dy, rows, C, scale, dx);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -468,6 +486,7 @@ void scale_cols(const float* dy, long long rows, int C, const float* scale, floa
 __global__ void u8_batch_kernel(const uint8_t* __restrict__ images, const long long* __restrict__ labels,
                                 const long long* __restrict__ index, int B, int HW, float mean, float stdv,
                                 float* __restrict__ x, long long* __restrict__ y) {
+  pdl_enter();
   const int v16 = HW / 16;                                   // HW % 16 == 0 (784 = 49 * 16)
   const long long total = (long long)B * v16;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -491,7 +510,7 @@ void u8_batch(const uint8_t* images, const long long* labels, const long long* i
               float* x, long long* y, cudaStream_t s) {
   PCG_PROFILE("input_pipeline", s);
   PCG_REQUIRE(HW % 16 == 0 && (reinterpret_cast<uintptr_t>(images) & 15) == 0, "image size must be a multiple of 16 bytes");
-  u8_batch_kernel<<<blocks_for((long long)B * (HW / 16)), 256, 0, s>>>(images, labels, index, B, HW, mean, stdv, x, y);
+  launch_k(u8_batch_kernel, dim3(blocks_for((long long)B * (HW / 16))), dim3(256), 0, s, images, labels, index, B, HW, mean, stdv, x, y);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
