@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Tensor-core convolution kernels for sm_100a.
 //
 //  * conv_tc_fprop_kernel<BN>: persistent, warp-specialised implicit GEMM
@@ -429,6 +430,16 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 static int pick_bn(int Cout) { return (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : (Cout % 64 == 0) ? 64 : 32; }
+// Small-M problems (the last discriminator layers: 16-64 M tiles) leave most SMs idle while each busy CTA streams the
+// whole K extent of a 256-wide weight panel through one SM's TMA path (1.7 MB per CTA for 256->256: ~25 us for 1 us of
+// math).  Narrower N tiles put more SMs to work on the same bytes: halve the tile while the launch still fits `budget`
+// CTAs (one wave).
+static int pick_bn_parallel(long long m_tiles, int Cout, int budget) {
+  static const bool narrow = [] { const char* e = getenv("PCG_TC_NARROW"); return e == nullptr || atoi(e) != 0; }();
+  int bn = pick_bn(Cout);
+  while (narrow && bn > 64 && m_tiles * (Cout / (bn / 2)) <= budget) bn /= 2;
+  return bn;
+}
 
 int conv_tc_grid(long long M, int Cout) {
   int bn = pick_bn(Cout);
@@ -461,7 +472,7 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
   const int Ho = (H + 2 * pad - ksize) / stride + 1;
   const int Wo = (W + 2 * pad - ksize) / stride + 1;
   const long long M = (long long)N * Ho * Wo;
-  const int bn = pick_bn(Cout);
+  const int bn = epi.stats != nullptr ? pick_bn(Cout) : pick_bn_parallel((M + TILE_M - 1) / TILE_M, Cout, sm_count());
   PCG_REQUIRE(epi.stats == nullptr || Cout == bn, "BN statistics need a single N tile");
   FpropParams p;
   p.M = (int)M; p.Ho = Ho; p.Wo = Wo; p.tstride = stride; p.lower_h = -pad; p.lower_w = -pad;
@@ -475,7 +486,8 @@ void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk
   p.out = out; p.out_f32 = epi.out_f32; p.stats = epi.stats;
   CUtensorMap tmA = make_tmap_im2col(in, N, H, W, Cin, ksize, stride, pad);
   CUtensorMap tmB = make_tmap_2d(wpk, Cout, (uint64_t)ksize * ksize * Cin, bn);
-  const int grid = conv_tc_grid(M, Cout);
+  const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());     // == conv_tc_grid(M, Cout) when statistics are taken
   if (bn == 256) launch_fprop<256>(tmA, tmB, p, grid, stream);
   else if (bn == 128) launch_fprop<128>(tmA, tmB, p, grid, stream);
   else launch_fprop<64>(tmA, tmB, p, grid, stream);
@@ -553,7 +565,9 @@ void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, co
   const int Ho = (H + 2 - ksize) / 2 + 1, Wo = (W + 2 - ksize) / 2 + 1;
   const size_t u = (size_t)Cout * Cin;
   const size_t cls_off3[4] = {0, u, 3 * u, 5 * u};
-  const int bn = pick_bn(Cin);
+  // side by side (four streams) the classes share the SMs: a quarter of them each
+  const int bn = pick_bn_parallel(((long long)N * ((H + 1) / 2) * ((W + 1) / 2) + TILE_M - 1) / TILE_M, Cin,
+                                  class_streams != nullptr ? sm_count() / 4 : sm_count());
   for (int cls = 0; cls < 4; ++cls) {
     const int ph = cls >> 1, pw = cls & 1;
     const int Ah = (H + 1 - ph) / 2, Aw = (W + 1 - pw) / 2;
@@ -584,8 +598,9 @@ void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, co
   }
 }
 int conv_tc_dgrad_s2_class_ctas(int N, int H, int W, int Cin) {
-  const int bn = pick_bn(Cin);
-  const long long tiles = (((long long)N * ((H + 1) / 2) * ((W + 1) / 2) + TILE_M - 1) / TILE_M) * (Cin / bn);
+  const long long m_tiles = ((long long)N * ((H + 1) / 2) * ((W + 1) / 2) + TILE_M - 1) / TILE_M;
+  const int bn = pick_bn_parallel(m_tiles, Cin, sm_count() / 4);
+  const long long tiles = m_tiles * (Cin / bn);
   return (int)(tiles < sm_count() ? tiles : sm_count());
 }
 
