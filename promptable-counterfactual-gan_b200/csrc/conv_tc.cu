@@ -165,6 +165,15 @@ struct FpropParams {
   float* stats;
 };
 
+// One launch can carry NC independent implicit GEMMs that share the tile shape (the four parity classes of a stride-2
+// data gradient): tiles [tile_end[c-1], tile_end[c]) belong to problem c.
+template <int NC>
+struct FpropArgs {
+  CUtensorMap a[NC], b[NC];
+  FpropParams c[NC];
+  int tile_end[NC];
+};
+
 template <int BN>
 struct FpropCfg {
   static constexpr int B_STAGE_BYTES = BN * 128;
@@ -195,10 +204,9 @@ __device__ __forceinline__ float butterfly_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN>
+template <int BN, int NC>
 __global__ void __launch_bounds__(FPROP_THREADS, 1)
-conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const FpropParams p) {
+conv_tc_fprop_kernel(const __grid_constant__ FpropArgs<NC> P) {
   pdl_enter();
   using Cfg = FpropCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -215,13 +223,22 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int taps = p.taps_h * p.taps_w;
-  const int num_kb = taps * p.cin_blocks;
+  const int total_tiles = P.tile_end[NC - 1];
+  // problem of a tile and the tile's index inside it
+  auto locate = [&](int tile, int& lt) {
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < NC; ++k) c += tile >= P.tile_end[k] ? 1 : 0;
+    lt = tile - (c > 0 ? P.tile_end[c > 0 ? c - 1 : 0] : 0);
+    return c;
+  };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      tma_prefetch_desc(&P.a[k]);
+      tma_prefetch_desc(&P.b[k]);
+    }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -246,9 +263,14 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int hw = p.Ho * p.Wo;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        int lt;
+        const int cls = locate(tile, lt);
+        const FpropParams& p = P.c[cls];
+        const CUtensorMap& tmA = P.a[cls];
+        const CUtensorMap& tmB = P.b[cls];
+        const int hw = p.Ho * p.Wo, taps = p.taps_h * p.taps_w;
+        const int m_tile = lt / p.num_n_tiles, n_tile = lt % p.num_n_tiles;
         const int p0 = m_tile * TILE_M;
         const int n_img = p0 / hw, rem = p0 % hw;
         const int cw = (rem % p.Wo) * p.tstride + p.lower_w;
@@ -276,6 +298,9 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int lt;
+        const FpropParams& p = P.c[locate(tile, lt)];
+        const int num_kb = p.taps_h * p.taps_w * p.cin_blocks;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -312,7 +337,9 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int i = 0; i < BN / 32; ++i) acc_s[i] = acc_q[i] = 0.f;
 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+      int lt;
+      const FpropParams& p = P.c[locate(tile, lt)];
+      const int m_tile = lt / p.num_n_tiles, n_tile = lt % p.num_n_tiles;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const long long mrow = (long long)m_tile * TILE_M + row;
@@ -405,6 +432,7 @@ conv_tc_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (acc == 0) acc_phase ^= 1;
     }
 
+    const FpropParams& p = P.c[0];            // statistics: single-problem launches only
     if (p.stats != nullptr) {
       // stats_smem[q][2*BN]: (sum[BN], sumsq[BN]) per epilogue warp, then a fixed-order 4-way add.
 #pragma unroll
@@ -448,20 +476,30 @@ int conv_tc_grid(long long M, int Cout) {
   return (int)(tiles < sms ? tiles : sms);
 }
 
-template <int BN>
-static void launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int grid,
-                         cudaStream_t stream) {
+template <int BN, int NC>
+static void launch_fprop_args(const FpropArgs<NC>& args, cudaStream_t stream) {
   PCG_PROFILE("conv_tc_fprop", stream);
   using Cfg = FpropCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fprop_kernel<BN>,
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fprop_kernel<BN, NC>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  launch_k(conv_tc_fprop_kernel<BN>, dim3(grid), dim3(FPROP_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
+  const int tiles = args.tile_end[NC - 1];
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  launch_k(conv_tc_fprop_kernel<BN, NC>, dim3(grid), dim3(FPROP_THREADS), Cfg::SMEM_BYTES, stream, args);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
+}
+template <int BN>
+static void launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int grid,
+                         cudaStream_t stream) {
+  (void)grid;                                   // == min(tiles, SMs)
+  FpropArgs<1> args;
+  args.a[0] = tmA; args.b[0] = tmB; args.c[0] = p;
+  args.tile_end[0] = p.num_m_tiles * p.num_n_tiles;
+  launch_fprop_args<BN, 1>(args, stream);
 }
 
 void conv_tc_fprop(const bf16* in, int N, int H, int W, int Cin, const bf16* wpk, int Cout, int ksize,
@@ -565,13 +603,19 @@ void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, co
   const int Ho = (H + 2 - ksize) / 2 + 1, Wo = (W + 2 - ksize) / 2 + 1;
   const size_t u = (size_t)Cout * Cin;
   const size_t cls_off3[4] = {0, u, 3 * u, 5 * u};
-  // side by side (four streams) the classes share the SMs: a quarter of them each
-  const int bn = pick_bn_parallel(((long long)N * ((H + 1) / 2) * ((W + 1) / 2) + TILE_M - 1) / TILE_M, Cin,
-                                  class_streams != nullptr ? sm_count() / 4 : sm_count());
-  for (int cls = 0; cls < 4; ++cls) {
+  // The four parity classes go out as ONE launch (tiles of the class with the most taps first): one graph node instead
+  // of four and one tile queue, so the tail of a class overlaps the head of the next.
+  (void)class_streams;
+  long long all_m_tiles = 0;
+  for (int cls = 0; cls < 4; ++cls)
+    all_m_tiles += ((long long)N * ((H + 1 - (cls >> 1)) / 2) * ((W + 1 - (cls & 1)) / 2) + TILE_M - 1) / TILE_M;
+  const int bn = pick_bn_parallel(all_m_tiles, Cin, sm_count());
+  FpropArgs<4> args;
+  int slot = 0, tile_end = 0;
+  for (int cls = 3; cls >= 0; --cls) {
     const int ph = cls >> 1, pw = cls & 1;
     const int Ah = (H + 1 - ph) / 2, Aw = (W + 1 - pw) / 2;
-    if (Ah <= 0 || Aw <= 0) continue;
+    PCG_REQUIRE(Ah > 0 && Aw > 0, "stride-2 dgrad: every parity class needs at least one pixel");
     // 3x3: 1 or 2 taps per dimension, windows start at the class pixel; 4x4: always 2 taps, even rows look one back
     const int th = ksize == 4 ? 2 : (ph ? 2 : 1), tw = ksize == 4 ? 2 : (pw ? 2 : 1);
     const int lo_h = (ksize == 4 && ph == 0) ? -1 : 0, lo_w = (ksize == 4 && pw == 0) ? -1 : 0;
@@ -586,22 +630,21 @@ void conv_tc_dgrad_s2(const bf16* dy, int N, int H, int W, int Cin, int Cout, co
     p.bias = nullptr; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
     p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
     p.out = dx; p.out_f32 = epi.out_f32; p.stats = nullptr;
-    CUtensorMap tmA = make_tmap_im2col_box(dy, N, Ho, Wo, Cout, lo_w, lo_h, Aw - Wo + lo_w, Ah - Ho + lo_h, 1);
-    CUtensorMap tmB = make_tmap_2d(packed + cls_off, Cin, (uint64_t)th * tw * Cout, bn);
-    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    cudaStream_t cs = class_streams != nullptr ? class_streams[cls] : stream;
-    if (bn == 256) launch_fprop<256>(tmA, tmB, p, grid, cs);
-    else if (bn == 128) launch_fprop<128>(tmA, tmB, p, grid, cs);
-    else if (bn == 64) launch_fprop<64>(tmA, tmB, p, grid, cs);
-    else launch_fprop<32>(tmA, tmB, p, grid, cs);
+    args.a[slot] = make_tmap_im2col_box(dy, N, Ho, Wo, Cout, lo_w, lo_h, Aw - Wo + lo_w, Ah - Ho + lo_h, 1);
+    args.b[slot] = make_tmap_2d(packed + cls_off, Cin, (uint64_t)th * tw * Cout, bn);
+    args.c[slot] = p;
+    tile_end += p.num_m_tiles * p.num_n_tiles;
+    args.tile_end[slot] = tile_end;
+    ++slot;
   }
+  if (bn == 256) launch_fprop_args<256, 4>(args, stream);
+  else if (bn == 128) launch_fprop_args<128, 4>(args, stream);
+  else if (bn == 64) launch_fprop_args<64, 4>(args, stream);
+  else launch_fprop_args<32, 4>(args, stream);
 }
 int conv_tc_dgrad_s2_class_ctas(int N, int H, int W, int Cin) {
-  const long long m_tiles = ((long long)N * ((H + 1) / 2) * ((W + 1) / 2) + TILE_M - 1) / TILE_M;
-  const int bn = pick_bn_parallel(m_tiles, Cin, sm_count() / 4);
-  const long long tiles = m_tiles * (Cin / bn);
-  return (int)(tiles < sm_count() ? tiles : sm_count());
+  (void)N; (void)H; (void)W; (void)Cin;
+  return sm_count();                            // the four classes are one launch: nothing to run side by side
 }
 
 // ------------------------------------------------------------------------------------------
