@@ -781,9 +781,27 @@ struct MnistPlan : PlanBase {
   }
 
   // ---------------------------------------------------------------- phases
+  // Frozen classifier forward + input gradient (trainer.py:118, 121): lambda_cls * CE(C(x_cf), target) -> G_CLS, dxc.
+  // It needs nothing but x_cf (the classifier is in eval mode and is never updated), so it runs on side_c beside the
+  // whole discriminator step instead of in front of the generator backward: both are chains of small kernels that do
+  // not fill the GPU alone.
+  void c_branch(const pcg_mnist_inputs& in, float* scal, cudaStream_t c) {
+    c_fwd(x_cf, c);
+    ce_loss(clogits, in.target, B, 10, cfg.lambda_cls, scal + PCG_S_G_CLS, cdlogits, c);
+    GenEpilogue<T> e; e.ref_act = ACT_RELU;
+    e.act_ref = cf1; dgrad<float, T>(c_fc2, cdlogits, e, cdf1, c);
+    e.act_ref = cz[2]; dgrad<T, T>(c_fc1, cdf1, e, cd3, c);
+    e.act_ref = cz[1]; dgrad<T, T>(c_conv[2], cd3, e, cd2, c);
+    e.act_ref = cz[0]; dgrad<T, T>(c_conv[1], cd2, e, cd1, c);
+    GenEpilogue<float> e0;
+    dgrad<T, float>(c_conv[0], cd1, e0, dxc, c);
+  }
+
   void step_d_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override {
-    cudaStream_t side_w = wstream(s);
+    cudaStream_t side_w = wstream(s), side_c = cstream(s);
     g_fwd(in.x, in.target, in.mask, true, s);
+    after(s, side_c);
+    c_branch(in, scal, side_c);
     l1_finalize(l1_part, STAT_PARTS, 1.f / (float)MG, scal + PCG_S_REG_L1, s);   // writes REG_L1, MASK_PEN
     d_input<T>(in.x, d_embed, in.y, B, 784, a0, s);
     d_input<T>(x_cf, d_embed, in.target, B, 784, a0 + (size_t)MG * 2, s);
@@ -796,6 +814,7 @@ struct MnistPlan : PlanBase {
     d_bwd(2 * B, true, 1, s);
     embed_grad<float>(dxd, 1, 0, labels2, 2 * B, 784, 10, d_dembed, s);
     after(side_w, s);
+    after(side_c, s);
   }
 
   void step_d_update(cudaStream_t s) override {
@@ -817,28 +836,15 @@ struct MnistPlan : PlanBase {
   }
 
   void step_g_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override {
-    cudaStream_t side_w = wstream(s), side_c = cstream(s);
+    cudaStream_t side_w = wstream(s);
     // --- adversarial path through the UPDATED discriminator (trainer.py:116-117)
-    // --- classifier path (trainer.py:118) on side_c: independent of the discriminator path until the two input
-    //     gradients meet in residual_head_bwd; both are chains of small kernels that do not fill the GPU alone
-    after(s, side_c);
-    {
-      cudaStream_t c = side_c;
-      c_fwd(x_cf, c);
-      ce_loss(clogits, in.target, B, 10, cfg.lambda_cls, scal + PCG_S_G_CLS, cdlogits, c);
-      GenEpilogue<T> e; e.ref_act = ACT_RELU;
-      e.act_ref = cf1; dgrad<float, T>(c_fc2, cdlogits, e, cdf1, c);
-      e.act_ref = cz[2]; dgrad<T, T>(c_fc1, cdf1, e, cd3, c);
-      e.act_ref = cz[1]; dgrad<T, T>(c_conv[2], cd3, e, cd2, c);
-      e.act_ref = cz[0]; dgrad<T, T>(c_conv[1], cd2, e, cd1, c);
-      GenEpilogue<float> e0;
-      dgrad<T, float>(c_conv[0], cd1, e0, dxc, c);
-    }
+    // --- classifier path (trainer.py:118): independent of the discriminator path until the two input gradients meet
+    //     in residual_head_bwd
+    //     ... has already run beside the discriminator step (c_branch in step_d_grads): dxc and G_CLS are ready
     d_input<T>(x_cf, d_embed, in.target, B, 784, a0, s);
     d_fwd(B, s);
     bce_logits(dlogits_d, B, 1, 1.f, 1.f, cfg.lambda_adv, cfg.lambda_adv, scal + PCG_S_G_ADV, scal_tmp, ddlogit, s);
     d_bwd(B, cfg.pollute_d_grads != 0, 0, s);
-    after(side_c, s);
     g_loss_combine(scal + PCG_S_G_ADV, scal + PCG_S_G_CLS, scal + PCG_S_REG_L1, scal + PCG_S_MASK_PEN, cfg.lambda_adv,
                    cfg.lambda_cls, cfg.lambda_reg, cfg.lambda_mask, scal + PCG_S_G_LOSS, s);
     // --- through clamp / mask / scaling (trainer.py:97,99,119; generator.py:80-82)
