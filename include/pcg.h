@@ -191,11 +191,13 @@ int pcg_mnist_refresh_weights(pcg_mnist_plan* plan, void* stream);
 
 /* One full iteration = the four phases below in order.  scalars: device float[PCG_MNIST_NSCALARS]. */
 int pcg_mnist_step(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream);
-/* phase 1: G forward, x_cf, D forward/backward on (x,y) and (x_cf.detach(), target) -> d_grads */
+/* phase 1: G forward, x_cf, D forward/backward on (x,y) and (x_cf.detach(), target) -> d_grads; beside it (side
+ *          stream, joined before the phase returns) the frozen classifier's forward / input gradient on x_cf, which
+ *          needs nothing else: scalars[PCG_S_G_CLS] and the plan-owned d CE / d x_cf are consumed by phase 3 */
 int pcg_mnist_step_d_grads(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream);
 /* phase 2: Adam on D (gradient all-reduce, if any, happens between phase 1 and 2) */
 int pcg_mnist_step_d_update(pcg_mnist_plan* plan, void* stream);
-/* phase 3: D forward with the updated D, classifier forward/backward, losses, G backward -> g_grads */
+/* phase 3: D forward with the updated D, losses, G backward -> g_grads (same `in` and `scalars` as phase 1) */
 int pcg_mnist_step_g_grads(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream);
 /* phase 4: Adam on G */
 int pcg_mnist_step_g_update(pcg_mnist_plan* plan, void* stream);
