@@ -984,7 +984,8 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
 // wgrad: dW[tap][ci][co] = sum_p x[p@tap][ci] * dy[p][co]; K = the 128 padded positions of a tile
 // ------------------------------------------------------------------------------------------
 constexpr int G_STAGES = 4;
-constexpr int DY_STAGE_BYTES = 16384;            // 128 rows x 128 B (rows >= R*(W+2) stay zero)
+constexpr int DY_PAD_BYTES = 1024;               // eight zero rows in front of the dY tile (read by its shifted views)
+constexpr int DY_STAGE_BYTES = DY_PAD_BYTES + 16384;   // + 128 rows x 128 B (rows >= R*(W+2) stay zero)
 constexpr int G_THREADS = 192;
 constexpr int G_SMEM_BYTES = 1024 + G_STAGES * (IN_STAGE_BYTES + DY_STAGE_BYTES) + 256;
 
@@ -1036,13 +1037,22 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], xbytes + dybytes);
         tma_load_4d(&tmX, &full[stage], sx + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n);
-        tma_load_4d(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES, 0, 0, h0, n);
+        tma_load_4d(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES + DY_PAD_BYTES, 0, 0, h0, n);
         if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);     // A, B both MN-major
+      constexpr uint32_t idesc192 = umma_idesc_bf16(128, 192, 1, 1);
+      // Default: BOTH operands carry shifted views.  dW[r][s] = sum_pos X[pos + r*WP + s] dY[pos] = sum_p X[p + r*WP] dY[p - s]
+      // (p = pos + s; dY is zero outside its tile), so the column shift moves to the dY side: B = the dY tile started
+      // 2, 1, 0 rows early, stacked along N (three 64-channel blocks 128 B apart, N = 192), A = the X views of tap rows
+      // r = 0, 1 stacked along M.  One M128 x N192 MMA per k-step covers six taps, a second one (A = the r = 2 view; its
+      // upper 64 rows are a dummy view) the other three: 16 MMAs per tile instead of 40.  Accumulator 0 (TMEM columns
+      // 0-191): lanes (r, ci), columns (2 - s, co); accumulator 1 (columns 192-383): lanes ci (r = 2).
+      // variant bit 1024: the original scheme (five M128 x N64 accumulators, two taps each).
+      const bool stacked = (variant & 1024) == 0;
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
@@ -1050,24 +1060,31 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t x_base = smem_u32(sx + stage * IN_STAGE_BYTES);
-        const uint64_t b0 = umma_smem_desc(smem_u32(sdy + stage * DY_STAGE_BYTES), 16, 1024);
+        const uint32_t dy_base = smem_u32(sdy + stage * DY_STAGE_BYTES + DY_PAD_BYTES);
         if (elect_one()) {
+          const uint32_t acc0 = first ? 0u : 1u;
+          if (stacked) {
+            const uint64_t a1 = a_desc(x_base, (uint32_t)WP * 128u, 0);
+            const uint64_t a2 = a_desc(x_base + 2u * (uint32_t)WP * 128u, 128u, 0);
+            const uint64_t b3 = umma_smem_desc(dy_base - 256u, 128, 1024);
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int t0 = 2 * j, t1 = (j < 4) ? t0 + 1 : t0;
-          const uint32_t o0 = (uint32_t)((t0 / 3) * WP + (t0 % 3)) * 128u;
-          const uint32_t o1 = (uint32_t)((t1 / 3) * WP + (t1 % 3)) * 128u;
-          const uint32_t lbo = (j < 4) ? (o1 - o0) : 128u;            // distance between the two 64-channel M blocks
-          const uint64_t aj = a_desc(x_base + o0, lbo, variant);
-          if (first) {
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base, a1 + 128 * k, b3 + 128 * k, idesc192, k != 0 ? 1u : acc0);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + j * 64, aj + 128 * k, b0 + 128 * k, idesc, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + 192, a2 + 128 * k, b3 + 128 * k, idesc192, k != 0 ? 1u : acc0);
           } else {
+            const uint64_t b0 = umma_smem_desc(dy_base, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + j * 64, aj + 128 * k, b0 + 128 * k, idesc, 1u);
+            for (int j = 0; j < 5; ++j) {
+              const int t0 = 2 * j, t1 = (j < 4) ? t0 + 1 : t0;
+              const uint32_t o0 = (uint32_t)((t0 / 3) * WP + (t0 % 3)) * 128u;
+              const uint32_t o1 = (uint32_t)((t1 / 3) * WP + (t1 % 3)) * 128u;
+              const uint32_t lbo = (j < 4) ? (o1 - o0) : 128u;            // distance between the two 64-channel M blocks
+              const uint64_t aj = a_desc(x_base + o0, lbo, variant & 1);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) umma_f16(tmem_base + j * 64, aj + 128 * k, b0 + 128 * k, idesc, k != 0 ? 1u : acc0);
+            }
           }
-        }
-        umma_commit(&empty[stage]);
+          umma_commit(&empty[stage]);
         }
         __syncwarp();
         first = false;
@@ -1082,20 +1099,45 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     mbar_wait(done, 0);
     tc_fence_after();
     float* my = part + (size_t)blockIdx.x * 9 * 64 * 64;
+    if ((variant & 1024) == 0) {
 #pragma unroll 1
-    for (int j = 0; j < 5; ++j) {
-      const int tap = 2 * j + (row >> 6), ci = row & 63;
+      for (int a = 0; a < 2; ++a) {
+        const int r = a == 0 ? (row >> 6) : 2, ci = row & 63;
+        const bool live = a == 0 || row < 64;                     // accumulator 1: lanes 64-127 hold the dummy view
+#pragma unroll 1
+        for (int jb = 0; jb < 3; ++jb) {
+          const int tap = r * 3 + (2 - jb);
 #pragma unroll
-      for (int chunk = 0; chunk < 2; ++chunk) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + j * 64 + chunk * 32, r);
-        tmem_ld_wait();
-        if (tap < 9) {
-          float4* dst = reinterpret_cast<float4*>(my + ((size_t)tap * 64 + ci) * 64 + chunk * 32);
+          for (int chunk = 0; chunk < 2; ++chunk) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + a * 192 + jb * 64 + chunk * 32, v);
+            tmem_ld_wait();
+            if (live) {
+              float4* dst = reinterpret_cast<float4*>(my + ((size_t)tap * 64 + ci) * 64 + chunk * 32);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            dst[j4] = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
-                                  __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+              for (int j4 = 0; j4 < 8; ++j4)
+                dst[j4] = make_float4(__uint_as_float(v[j4 * 4]), __uint_as_float(v[j4 * 4 + 1]),
+                                      __uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3]));
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 5; ++j) {
+        const int tap = 2 * j + (row >> 6), ci = row & 63;
+#pragma unroll
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + j * 64 + chunk * 32, r);
+          tmem_ld_wait();
+          if (tap < 9) {
+            float4* dst = reinterpret_cast<float4*>(my + ((size_t)tap * 64 + ci) * 64 + chunk * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              dst[j4] = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
+                                    __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+          }
         }
       }
     }

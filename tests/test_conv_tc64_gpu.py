@@ -113,9 +113,12 @@ def test_stacked_and_one_class_kernels_agree():
     assert (outs[0] != outs[1]).float().mean().item() < 0.05
 
 
-@pytest.mark.parametrize("N,HW", [(3, 28), (8, 28), (5, 14)])
-def test_wgrad(N, HW):
+@pytest.mark.parametrize("variant", [0, 1024])
+@pytest.mark.parametrize("N,HW", [(3, 28), (8, 28), (301, 28), (5, 14), (5, 12)])
+def test_wgrad(N, HW, variant):
+    """variant 0: shifted views on both operands (16 MMAs per tile); 1024: two taps per accumulator (40 MMAs)."""
     L, P, st, check = _env()
+    L.pcg_conv_tc64_set_variant(variant)
     torch.manual_seed(N)
     xn = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda"))
     dyn = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda") * 0.1)
@@ -127,4 +130,5 @@ def test_wgrad(N, HW):
     wz = torch.zeros(64, 64, 3, 3, device="cuda", requires_grad=True)
     yy = F.conv2d(nchw(xn), wz, None, padding=1)
     (gw,) = torch.autograd.grad(yy, wz, nchw(dyn))
+    L.pcg_conv_tc64_set_variant(0)
     assert rel(dw, gw) < 2e-3
