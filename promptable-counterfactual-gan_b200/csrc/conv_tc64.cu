@@ -1044,13 +1044,14 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   } else if (warp == 1) {
     {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);     // A, B both MN-major
-      constexpr uint32_t idesc192 = umma_idesc_bf16(128, 192, 1, 1);
+      constexpr uint32_t idesc192 = umma_idesc_bf16(128, 192, 1, 1), idesc128 = umma_idesc_bf16(128, 128, 1, 1);
       // Default: BOTH operands carry shifted views.  dW[r][s] = sum_pos X[pos + r*WP + s] dY[pos] = sum_p X[p + r*WP] dY[p - s]
       // (p = pos + s; dY is zero outside its tile), so the column shift moves to the dY side: B = the dY tile started
       // 2, 1, 0 rows early, stacked along N (three 64-channel blocks 128 B apart, N = 192), A = the X views of tap rows
-      // r = 0, 1 stacked along M.  One M128 x N192 MMA per k-step covers six taps, a second one (A = the r = 2 view; its
-      // upper 64 rows are a dummy view) the other three: 16 MMAs per tile instead of 40.  Accumulator 0 (TMEM columns
-      // 0-191): lanes (r, ci), columns (2 - s, co); accumulator 1 (columns 192-383): lanes ci (r = 2).
+      // r = 0, 1 stacked along M.  One M128 x N192 MMA per k-step covers six taps; for r = 2 the column shift is split
+      // between the operands, s = a + b: A = the r = 2 view shifted by a = 0, 1 pixels (M = 128), B = dY started b = 2, 0
+      // rows early (N = 128), which yields s = 2, 3 (unused), 0, 1.  16 MMAs per tile instead of 40.  Accumulator 0 (TMEM
+      // columns 0-191): lanes (r, ci), columns (2 - s, co); accumulator 1 (columns 192-319): lanes (a, ci), columns (b, co).
       // variant bit 1024: the original scheme (five M128 x N64 accumulators, two taps each).
       const bool stacked = (variant & 1024) == 0;
       int stage = 0;
@@ -1067,10 +1068,11 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const uint64_t a1 = a_desc(x_base, (uint32_t)WP * 128u, 0);
             const uint64_t a2 = a_desc(x_base + 2u * (uint32_t)WP * 128u, 128u, 0);
             const uint64_t b3 = umma_smem_desc(dy_base - 256u, 128, 1024);
+            const uint64_t b2 = umma_smem_desc(dy_base - 256u, 256, 1024);      // blocks b = 2, 0
 #pragma unroll
             for (int k = 0; k < 8; ++k) umma_f16(tmem_base, a1 + 128 * k, b3 + 128 * k, idesc192, k != 0 ? 1u : acc0);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + 192, a2 + 128 * k, b3 + 128 * k, idesc192, k != 0 ? 1u : acc0);
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + 192, a2 + 128 * k, b2 + 128 * k, idesc128, k != 0 ? 1u : acc0);
           } else {
             const uint64_t b0 = umma_smem_desc(dy_base, 16, 1024);
 #pragma unroll
@@ -1102,11 +1104,13 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if ((variant & 1024) == 0) {
 #pragma unroll 1
       for (int a = 0; a < 2; ++a) {
-        const int r = a == 0 ? (row >> 6) : 2, ci = row & 63;
-        const bool live = a == 0 || row < 64;                     // accumulator 1: lanes 64-127 hold the dummy view
+        const int ci = row & 63, hi = row >> 6;
 #pragma unroll 1
-        for (int jb = 0; jb < 3; ++jb) {
-          const int tap = r * 3 + (2 - jb);
+        for (int jb = 0; jb < (a == 0 ? 3 : 2); ++jb) {
+          // accumulator 0: tap (r = hi, s = 2 - jb); accumulator 1: tap (2, s = hi + (jb == 0 ? 2 : 0)), s = 3 unused
+          const int sc = a == 0 ? 2 - jb : hi + (jb == 0 ? 2 : 0);
+          const bool live = sc < 3;
+          const int tap = (a == 0 ? hi : 2) * 3 + sc;
 #pragma unroll
           for (int chunk = 0; chunk < 2; ++chunk) {
             uint32_t v[32];
