@@ -11,6 +11,16 @@
 //
 // Replaces: nn.Conv2d(64, 64, 3, padding=1) forward and ConvolutionBackward0 (dgrad with rotated weights,
 // wgrad) of conditional_counteRGAN/mnist/models/generator.py:11,14,49.
+//
+// Kernels in this file (profiles/exp_tc64_stacked_r1.md):
+//   conv_tc64s_fprop_kernel  forward / data gradient, default when H % 4 == 0: row classes h % 4, tap matrices stacked
+//                            along N (72 instead of 144 MMAs per 512 positions), store warp + mbarrier-handed staging
+//   conv_tc64_fprop_kernel   forward / data gradient, one output class per tile: every other height, and the A/B
+//                            partner of the stacked kernel (variant bit 256); same epilogue contract
+//   conv_tc64_wgrad_kernel   weight gradient: shifted views on both operands (16 instead of 40 MMAs per tile;
+//                            variant bit 1024 = the two-taps-per-accumulator scheme)
+// Variant bits (pcg_conv_tc64_set_variant / PCG_TC64_VARIANT): 1 descriptor base-offset policy (bring-up), 2 / 4 / 8 /
+// 16 / 64 / 128 timing experiments (results invalid), 256 one-class forward kernel, 1024 original weight-gradient scheme.
 #include <cstdlib>
 
 #include "conv_tc.cuh"
