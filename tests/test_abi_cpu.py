@@ -82,3 +82,32 @@ def test_mirror_modules_match_reference_state_dict_and_init():
         # the shipped generator checkpoint loads
         ck = torch.load("/root/reference/conditional_counteRGAN/mnist/results/generator.pt", map_location="cpu")
         ResidualGenerator().load_state_dict(ck)
+
+
+def test_mlp_gan_step_rejects_shapes_outside_its_envelope():
+    """pcg_mlp_gan_step validates before it touches the device: error code + message, no crash (and no fallback)."""
+    L = _lib.load()
+    f = ctypes.c_float(1e-3)
+    args = [None] * 6 + [None] * 10
+    assert L.pcg_mlp_gan_step(64, 32, 2, 64, *args, f, None, None) != 0
+    assert b"hidden width must be 128" in L.pcg_last_error()
+    assert L.pcg_mlp_gan_step(64, 32, 3, 128, *args, f, None, None) != 0
+    assert b"label_dim <= 2" in L.pcg_last_error()
+    assert L.pcg_mlp_gan_step(64, 40, 2, 128, *args, f, None, None) != 0
+    assert b"z_dim + label_dim <= 36" in L.pcg_last_error()
+
+
+def test_flat_parameter_layout_is_the_one_the_fused_mlp_gan_kernel_indexes():
+    """csrc/mlp_gan.cu addresses the caller's flat buffers as [0.weight | 0.bias | 2.weight | 2.bias] with every slice
+    padded to a multiple of 4 floats: ob1 = r4(H * in), ow2 = ob1 + H, ob2 = ow2 + out * H, total = ob2 + 4."""
+    from pcg_b200.ops import FlatParams
+    r4 = lambda n: (n + 3) // 4 * 4  # noqa: E731
+    H = 128
+    for in_dim, out_dim in ((34, 2), (32, 2), (4, 1), (2, 1)):
+        fp = FlatParams([("net.0.weight", (H, in_dim)), ("net.0.bias", (H,)), ("net.2.weight", (out_dim, H)),
+                         ("net.2.bias", (out_dim,))], "cpu")
+        ob1 = r4(H * in_dim)
+        ow2 = ob1 + H
+        ob2 = ow2 + out_dim * H
+        assert [fp.offsets[k] for k in fp.names] == [0, ob1, ow2, ob2]
+        assert fp.size == ob2 + 4
