@@ -94,3 +94,45 @@ def test_weight_gradient_shifted_views_on_both_operands():
                     if a + b < 3:
                         dw[2, a + b] += A.t() @ dt[PAD - b:PAD - b + K]
     assert torch.allclose(dw.permute(3, 2, 0, 1), ref, atol=1e-10)
+
+
+def _dgrad_s2_by_parity_classes(dy, w, H, W, ksize):
+    """The geometry conv_tc_dgrad_s2 (csrc/conv_tc.cu) hands to the implicit-GEMM kernel, replayed densely: the data
+    gradient of a stride-2 / pad-1 convolution as four stride-1 problems, one per (hi % 2, wi % 2) class of input
+    pixels.  Class (ph, pw) has Ah x Aw pixels; pixel (a, b) reads a th x tw window of dY starting at (a + lo_h, b + lo_w)
+    (zero outside), and window element (t, u) carries the filter tap (r, s) that maps it onto input row 2a + ph:
+    hi + 1 - r = 2 * ho  ->  r = hi + 1 - 2 * (a + lo_h + t)."""
+    N, Cout, Ho, Wo = dy.shape
+    Cin = w.shape[1]
+    dx = torch.zeros(N, Cin, H, W, dtype=dy.dtype)
+    for cls in range(4):
+        ph, pw = cls >> 1, cls & 1
+        Ah, Aw = (H + 1 - ph) // 2, (W + 1 - pw) // 2
+        th = 2 if ksize == 4 else (2 if ph else 1)
+        tw = 2 if ksize == 4 else (2 if pw else 1)
+        lo_h = -1 if (ksize == 4 and ph == 0) else 0
+        lo_w = -1 if (ksize == 4 and pw == 0) else 0
+        for a in range(Ah):
+            for b in range(Aw):
+                acc = torch.zeros(N, Cin, dtype=dy.dtype)
+                for t in range(th):
+                    for u in range(tw):
+                        ho, wo = a + lo_h + t, b + lo_w + u
+                        r, s = 2 * a + ph + 1 - 2 * ho, 2 * b + pw + 1 - 2 * wo
+                        assert 0 <= r < ksize and 0 <= s < ksize          # every window element is a real filter tap
+                        if 0 <= ho < Ho and 0 <= wo < Wo:
+                            acc += dy[:, :, ho, wo] @ w[:, :, r, s]
+                dx[:, :, 2 * a + ph, 2 * b + pw] = acc
+    return dx
+
+
+def test_stride2_data_gradient_parity_classes():
+    torch.manual_seed(2)
+    for ksize, H in ((3, 7), (3, 14), (4, 8), (4, 16)):       # 3x3: MNIST discriminator / classifier; 4x4: DCGAN
+        N, Cin, Cout, W = 2, 3, 4, H
+        Ho = (H + 2 - ksize) // 2 + 1
+        x = torch.zeros(N, Cin, H, W, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(Cout, Cin, ksize, ksize, dtype=torch.float64)
+        dy = torch.randn(N, Cout, Ho, Ho, dtype=torch.float64)
+        (ref,) = torch.autograd.grad(F.conv2d(x, w, stride=2, padding=1), x, dy)
+        assert torch.allclose(_dgrad_s2_by_parity_classes(dy, w, H, W, ksize), ref, atol=1e-10), (ksize, H)
