@@ -10,6 +10,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
 
@@ -33,6 +35,10 @@ struct Slot {
   size_t cap = 0;
 };
 static Slot g_slots[SL_COUNT];
+// Blocks replaced by a larger one are retired, not freed: a CUDA graph captured by an earlier plan of this process
+// (another batch size: the tail batch of an epoch, a second model) still holds their addresses.  Growth is geometric,
+// so the retired blocks of a slot add up to less than its final size.
+static std::vector<void*> g_retired;
 
 static void* scratch(int slot, size_t bytes, cudaStream_t stream) {
   Slot& s = g_slots[slot];
@@ -41,9 +47,8 @@ static void* scratch(int slot, size_t bytes, cudaStream_t stream) {
   cudaStreamIsCapturing(stream, &st);
   if (st != cudaStreamCaptureStatusNone)
     throw Error(5, "tensor-core scratch must be sized by an eager pass before stream capture");
-  PCG_CHECK_CUDA(cudaDeviceSynchronize());          // earlier launches may still read the old buffer
-  if (s.p) PCG_CHECK_CUDA(cudaFree(s.p));
-  const size_t cap = bytes + bytes / 4 + 4096;
+  if (s.p) g_retired.push_back(s.p);
+  const size_t cap = bytes > 2 * s.cap ? bytes + bytes / 4 + 4096 : 2 * s.cap;
   PCG_CHECK_CUDA(cudaMalloc(&s.p, cap));
   s.cap = cap;
   return s.p;

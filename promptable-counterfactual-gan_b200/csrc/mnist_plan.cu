@@ -461,7 +461,8 @@ struct MnistPlan : PlanBase {
     stat_part2 = alloc<float>((size_t)STAT_PARTS * 2 * maxC);
     c12 = alloc<float>(2 * maxC);
     wg_scratch = alloc<float>(wg_scratch_elems);
-    tc_part = kBf16 ? alloc<float>((size_t)148 * 9 * 64 * 64) : nullptr;
+    PCG_REQUIRE(sm_count() <= STAT_PARTS, "more SMs than partial-row slots (STAT_PARTS)");
+    tc_part = kBf16 ? alloc<float>((size_t)sm_count() * 9 * 64 * 64) : nullptr;   // one weight-gradient partial per CTA (grid <= SMs)
     l1_part = alloc<float>(STAT_PARTS * 2);
     small_part = alloc<float>((size_t)sm_count() * 2048);
     scal_tmp = alloc<float>(16);

@@ -16,6 +16,7 @@ import os
 import torch
 import torch.nn as nn
 
+from .. import graphs
 from .. import ops as K
 
 config = {'batch_size': 128, 'image_channel': 1, 'z_dim': 100, 'g_hidden': 64, 'd_hidden': 64, 'x_dim': 64,
@@ -71,6 +72,8 @@ class Discriminator(nn.Module):
 def _forward_plan(module, batch, which):
     cache = module.__dict__.setdefault("_pcg_plans", {})
     p = cache.get(batch)
+    if p is not None and not (p.G if which == "G" else p.D).aliases(module):
+        p = None                        # a training plan re-adopted the module since: this plan's arena is stale
     if p is None:
         dev = next(module.parameters()).device
         if dev.type != "cuda":
@@ -95,8 +98,11 @@ class _ConvT:
 
 
 class DcganPlan:
-    def __init__(self, batch, device, lr=2e-4, betas=(0.5, 0.999), use_graph=True, tensor_cores=None):
-        """tensor_cores: the 64..512-channel convolutions (12 of the 15 conv passes' FLOPs) on the tcgen05 kernels with
+    def __init__(self, batch, device, lr=2e-4, betas=(0.5, 0.999), use_graph=True, tensor_cores=None, share=None):
+        """share: another DcganPlan (any batch size) whose parameter arenas, Adam state, BatchNorm buffers and packed
+        weights this plan uses too — the reference keeps ONE optimizer state for the whole run (mnist_dcgan.py:133-134),
+        so the tail batch of an epoch (60000 % 128 = 96) must not get fresh moments.
+        tensor_cores: the 64..512-channel convolutions (12 of the 15 conv passes' FLOPs) on the tcgen05 kernels with
         bf16 operands; None = follow PCG_PRECISION (default bf16 -> on), False = exact fp32 on the CUDA cores."""
         self.B, self.lr, self.betas = batch, lr, betas
         self.tc = (os.environ.get("PCG_PRECISION", "bf16") != "fp32") if tensor_cores is None else bool(tensor_cores)
@@ -126,8 +132,11 @@ class DcganPlan:
             idx += 3
         dnames.append(("main.11.weight", (1, 512, 4, 4)))
         self.d_conv_names.append("main.11")
-        self.G, self.D = K.FlatParams(gnames, dev), K.FlatParams(dnames, dev)
-        self.D_grad2 = torch.zeros_like(self.D.grad)
+        if share is not None:
+            self.G, self.D, self.D_grad2 = share.G, share.D, share.D_grad2
+        else:
+            self.G, self.D = K.FlatParams(gnames, dev), K.FlatParams(dnames, dev)
+            self.D_grad2 = torch.zeros_like(self.D.grad)
         # BN buffers: running_mean / running_var / num_batches_tracked
         self.g_bn = [dict(rm=z(G_CH[i + 1]), rv=torch.ones(G_CH[i + 1], device=dev),
                           nbt=torch.zeros((), dtype=torch.int64, device=dev), st=K.BNState(G_CH[i + 1], dev))
@@ -137,10 +146,14 @@ class DcganPlan:
                                    st=[K.BNState(D_CH[i + 1], dev) for _ in range(2)]) for i in range(1, 4)]
         # ---- packed weights
         self.convt = [_ConvT(i, B) for i in range(5)]
-        self.g_wf = [z(G_CH[i] * G_CH[i + 1] * 16) for i in range(5)]
-        self.g_wd = [z(G_CH[i] * G_CH[i + 1] * 16) for i in range(5)]
-        self.d_wf = [z(D_CH[i] * D_CH[i + 1] * 16) for i in range(5)]
-        self.d_wd = [z(D_CH[i] * D_CH[i + 1] * 16) for i in range(5)]
+        if share is not None:
+            self.g_bn, self.d_bn = share.g_bn, share.d_bn           # batch-size independent (per-channel vectors)
+            self.g_wf, self.g_wd, self.d_wf, self.d_wd = share.g_wf, share.g_wd, share.d_wf, share.d_wd
+        else:
+            self.g_wf = [z(G_CH[i] * G_CH[i + 1] * 16) for i in range(5)]
+            self.g_wd = [z(G_CH[i] * G_CH[i + 1] * 16) for i in range(5)]
+            self.d_wf = [z(D_CH[i] * D_CH[i + 1] * 16) for i in range(5)]
+            self.d_wd = [z(D_CH[i] * D_CH[i + 1] * 16) for i in range(5)]
         # ---- static inputs / activations (NHWC)
         self.real, self.noise = z(B, 64, 64, 1), z(B, 1, 1, 100)
         self.gy = [z(B, G_HW[i + 1], G_HW[i + 1], G_CH[i + 1]) for i in range(5)]       # ConvT outputs (pre-BN)
@@ -381,11 +394,7 @@ class DcganPlan:
 
     @staticmethod
     def _capture(fn):
-        g = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            fn()
-        return g
+        return graphs.capture(fn)
 
     def _step_dp(self):
         segs = self._segments()
@@ -419,7 +428,7 @@ class DcganPlan:
 
 def train_dcgan(netG, netD, dataloader, cfg, device="cuda"):
     """The training loop of mnist_dcgan.py:140-193 as a function.  Returns (G_losses, D_losses) per epoch."""
-    plan = None
+    plans = {}            # one plan per batch size; all share the first plan's arenas, Adam state and BN buffers
     epoch_G, epoch_D = [], []
     for epoch in range(cfg['epochs']):
         acc = torch.zeros(8, device=device)
@@ -427,10 +436,13 @@ def train_dcgan(netG, netD, dataloader, cfg, device="cuda"):
         for i, data in enumerate(dataloader):
             real = data[0].to(device, non_blocking=True).float()
             b = real.size(0)
-            if plan is None or plan.B != b:
-                plan = DcganPlan(b, device, cfg['lr'])
-                plan.adopt_g(netG)
-                plan.adopt_d(netD)
+            plan = plans.get(b)
+            if plan is None:
+                first = next(iter(plans.values()), None)
+                plan = plans[b] = DcganPlan(b, device, cfg['lr'], share=first)
+                if first is None:
+                    plan.adopt_g(netG)
+                    plan.adopt_d(netD)
             noise = torch.randn(b, cfg['z_dim'], 1, 1, device=device)
             sc = plan.step(real, noise)
             acc += sc

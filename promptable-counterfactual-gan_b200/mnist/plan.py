@@ -11,6 +11,7 @@ from dataclasses import dataclass
 import torch
 
 from .. import _lib
+from .. import graphs
 
 PCG_F32, PCG_BF16 = 0, 1
 SCALAR_NAMES = ["d_loss", "g_loss", "g_adv", "g_cls", "reg_l1", "mask_pen", "d_real_p", "d_fake_p",
@@ -143,8 +144,10 @@ class MnistStepPlan:
 
     def close(self):
         if getattr(self, "_plan", None) is not None and self._plan.value:
-            self.L.pcg_mnist_plan_destroy(self._plan)
+            handle, L = self._plan, self.L
             self._plan = ctypes.c_void_p()
+            # cudaFree / cudaStreamDestroy are illegal while this thread captures a graph (a finaliser can run then)
+            graphs.defer_destroy(lambda: L.pcg_mnist_plan_destroy(handle))
 
     def __del__(self):
         try:

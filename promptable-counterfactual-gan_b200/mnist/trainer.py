@@ -17,6 +17,7 @@ import os
 import torch
 import torch.nn.functional as F
 
+from .. import graphs
 from . import binding
 from . import plan as P
 
@@ -70,6 +71,7 @@ class CounterGanTrainer:
         self.plans = {}
         self.graphs = {}
         self.static = {}
+        self._last_bs = None
 
     def _step_cfg_grad_scale(self):
         """Gradients are summed by the all-reduce; the 1/world_size average is folded into Adam."""
@@ -109,6 +111,16 @@ class CounterGanTrainer:
         """One iteration on device tensors; returns the plan whose ``scalars`` hold the losses."""
         bs = x.shape[0]
         p = self.plan(bs)
+        if self._last_bs is not None and self._last_bs != bs:
+            # every plan owns packed copies of the conv weights, refreshed by ITS OWN Adam phases only: the loader has
+            # no drop_last (data_utils.py:27; 54000 % 128 = 112), so the tail-batch plan and the full-batch plan
+            # alternate and each must re-pack what the other one updated before its forward runs
+            p.refresh_weights()
+        self._last_bs = bs
+        for m in (self.G, self.D, self.C):
+            # forward-only plans cached on the modules (models/_native.py) re-pack on their next call: the native Adam
+            # writes below do not bump torch's parameter version counters
+            m.__dict__["_pcg_seen"] = None
         if not self.use_graph:
             self._run_phases(p, x, y, target, mask)
             return p
@@ -148,12 +160,8 @@ class CounterGanTrainer:
 
     @staticmethod
     def _capture_fn(fn):
-        g = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize()
-        # thread_local: other threads (e.g. the NCCL watchdog polling events) must not invalidate the capture
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            fn()
-        return g
+        # thread_local capture: other threads (e.g. the NCCL watchdog polling events) must not invalidate it
+        return graphs.capture(fn)
 
 
 def _warm_plan(tr, bs):
@@ -206,8 +214,9 @@ def train_countergan(generator, discriminator, classifier, train_loader, cfg, de
         g_losses.append(tot[1] / n)
         d_losses.append(tot[0] / n)
         g_cls_losses.append(tot[3] / n)
-        g_grad_norm = tr.ga.grad.norm().item()
-        d_grad_norm = tr.da.grad.norm().item()
+        # the arenas hold the all-reduced SUM of the per-rank gradients; the reference logs the norm of the averaged ones
+        g_grad_norm = tr.ga.grad.norm().item() / tr.world
+        d_grad_norm = tr.da.grad.norm().item() / tr.world
         print(f"[GAN] Epoch {epoch+1}/{cfg.num_epochs_gan} | "
               f"G: {g_losses[-1]:.4f}, D: {d_losses[-1]:.4f}, "
               f"G_cls: {g_cls_losses[-1]:.4f}, G_grad: {g_grad_norm:.4f}, D_grad: {d_grad_norm:.4f}")
@@ -217,6 +226,10 @@ def train_countergan(generator, discriminator, classifier, train_loader, cfg, de
         import matplotlib
         matplotlib.use("Agg")
         import matplotlib.pyplot as plt
+    except ImportError:       # matplotlib is optional here (absent in the build image)
+        plt = None
+        print("matplotlib unavailable: skipped the loss-curve plot")
+    if plt is not None:
         plt.figure(figsize=(8, 6))
         plt.plot(g_losses, label="Generator Loss")
         plt.plot(d_losses, label="Discriminator Loss")
@@ -228,8 +241,6 @@ def train_countergan(generator, discriminator, classifier, train_loader, cfg, de
         plt.savefig(save_path)
         plt.close()
         print(f"Saved GAN loss curves to {save_path}")
-    except Exception:       # matplotlib is optional here (absent in the build image)
-        print("matplotlib unavailable: skipped the loss-curve plot")
 
     torch.save(generator.state_dict(), cfg.generator_path)
     print(f"Generator saved to {cfg.generator_path}")

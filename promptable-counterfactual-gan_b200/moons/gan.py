@@ -15,6 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import graphs
 from .. import ops as K
 
 
@@ -201,9 +202,7 @@ class MlpGanPlan:
                 dst.copy_(src)
             self.refresh()
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                self._body()
+            self.graph = graphs.capture(self._body)
         self.graph.replay()
         return self.scal
 

@@ -314,5 +314,13 @@ class FlatParams:
                 prm.grad = self.g(n)
         return self
 
+    def aliases(self, module):
+        """True while every parameter of ``module`` still points into this arena (a later plan may have re-adopted
+        the module into its own arena: a forward-only plan cached on the module must not be reused then)."""
+        try:
+            return all(prm.data_ptr() == self.p(n).data_ptr() for n, prm in module.named_parameters())
+        except KeyError:
+            return False
+
     def adam_step(self, lr, grad_scale=1.0):
         adam(self.data, self.grad, self.m, self.v, self.step, lr, grad_scale=grad_scale)

@@ -94,6 +94,8 @@ class NNClassifier(nn.Module):
 def _forward_plan(gen, batch):
     cache = gen.__dict__.setdefault("_pcg_plans", {})
     p = cache.get(batch)
+    if p is not None and not p.G.aliases(gen):
+        p = None                        # a training plan re-adopted the module since: this plan's arena is stale
     if p is None:
         dev = next(gen.parameters()).device
         if dev.type != "cuda":

@@ -3,6 +3,7 @@ BatchNorm1d, the spectral-norm MLP critic shared by both tabular CounteRGANs, gr
 enqueues libpcg kernels (pcg_b200.ops); gradients are written into FlatParams arenas."""
 import torch
 
+from .. import graphs
 from .. import ops as K
 
 
@@ -197,7 +198,5 @@ class GraphStep:
                 dst.copy_(src)
             self.refresh()
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                self.body()
+            self.graph = graphs.capture(self.body)
         self.graph.replay()

@@ -120,6 +120,62 @@ def test_train_countergan_matches_oracle(tmp_path, use_graph, monkeypatch):
     assert int(saved["resblocks.0.bn1.num_batches_tracked"]) == n_steps
 
 
+def test_train_countergan_ragged_tail_batch_two_epochs(tmp_path, monkeypatch):
+    """The reference loader has no drop_last (data_utils.py:27): every epoch ends with a smaller batch, so the trainer
+    alternates between two native plans.  Each plan keeps its own packed conv weights; they must be re-packed when the
+    other plan updated the parameters.  Two epochs of batches 8, 8, 5 against the oracle."""
+    from pcg_b200.mnist import trainer as T
+    monkeypatch.setenv("PCG_PRECISION", "fp32")
+    monkeypatch.setenv("PCG_NO_GRAPH", "0")
+    G, D, C = _mods(16, 2, seed=7)
+    S = _cpu_state(G, D, C)
+    G, D, C = G.cuda(), D.cuda(), C.cuda()
+    sizes = [8, 8, 5]
+    epoch = [O.synth_batch(b, 700 + i) for i, b in enumerate(sizes)]
+    draws = [O.synth_batch(b, 800 + i) for i, b in enumerate(sizes * 2)]      # targets / masks of the 6 iterations
+    # large steps: a stale weight copy (one epoch old) must be visible above the tolerances
+    cfg = types.SimpleNamespace(g_lr=2e-3, d_lr=2e-3, num_epochs_gan=2, num_classes=10, patch_size=7,
+                                num_modifiable_patches=10, lambda_adv=1.0, lambda_cls=1.0, lambda_reg=2.5,
+                                lambda_mask=2.0, save_dir=str(tmp_path), generator_path=str(tmp_path / "generator.pt"))
+    it = {"i": 0}
+    real_randint = torch.randint
+
+    def fake_randint(*a, **k):
+        return draws[it["i"]][2].clone().to(k.get("device", "cpu"))
+
+    def fake_build_mask(x, ps, device, n=None):
+        m = draws[it["i"]][3].clone().to(device)
+        it["i"] += 1
+        return m
+
+    monkeypatch.setattr(T, "build_mask", fake_build_mask)
+    monkeypatch.setattr(torch, "randint", fake_randint)
+    out = T.train_countergan(G, D, C, [(b[0], b[1]) for b in epoch], cfg, "cuda")
+    monkeypatch.setattr(torch, "randint", real_randint)
+    per_epoch = []
+    for e in range(2):
+        tot = 0.0
+        for j, (x, y, _, _) in enumerate(epoch):
+            sc, _ = O.countergan_step(S, x, y, draws[3 * e + j][2], draws[3 * e + j][3], n_resblocks=2,
+                                      hp=O.Hyper(g_lr=cfg.g_lr, d_lr=cfg.d_lr))
+            tot += sc["g_loss"]
+        per_epoch.append(tot / 3)
+    for e in range(2):
+        assert abs(out["g_losses"][e] - per_epoch[e]) < 5e-3 * abs(per_epoch[e]), (e, out["g_losses"], per_epoch)
+    saved = torch.load(cfg.generator_path, map_location="cpu")
+    for k, v in saved.items():
+        if k in S["G"] and not O.is_bn_shadowed_bias(k):
+            assert ((v.float() - S["G"][k].detach().float()).abs().mean() / cfg.g_lr).item() < 0.25, k
+    # the module's own forward (forward-only plan cached before training) sees the trained weights
+    x, y, t, m = epoch[0]
+    G.precision = "fp32"
+    G.eval()
+    with torch.no_grad():
+        raw, _ = G(x.cuda(), t.cuda(), m.cuda())
+        raw_o, _ = O.g_forward(S["G"], S["GB"], x, t, m, n_resblocks=2, training=False)
+    assert ((raw.cpu() - raw_o).abs().max() / raw_o.abs().max()).item() < 1e-3
+
+
 def test_build_mask_distribution():
     from pcg_b200.mnist.trainer import build_mask
     x = torch.zeros(4096, 1, 28, 28, device="cuda")

@@ -151,3 +151,32 @@ def test_kc_mirror_and_trainer(tmp_path):
     d, g = KC.train_countergan(G, cfg, X, yv, C)
     assert np.isfinite(d).all() and np.isfinite(g).all()
     assert list(torch.load(cfg["generator_path"]).keys()) == list(G.state_dict().keys())
+
+
+def test_capture_survives_cyclic_garbage():
+    """Regression (round-1 GPUTEST failure): a dead plan is a reference cycle (plan <-> GraphStep) that holds a
+    ``torch.cuda.CUDAGraph``; if Python's cyclic collector frees it while another plan is capturing, the graph's
+    destructor (cudaGraphExecDestroy) invalidates that capture.  ``pcg_b200.graphs.capture`` collects before and keeps
+    the collector off during the capture."""
+    import gc
+    import pcg_b200  # noqa: F401
+    from pcg_b200.tabular.moons import MoonsPlan
+    b = [t.cuda() for t in T.moons_batch(32, 1)]
+    gc.collect()
+    old = gc.get_threshold()
+    gc.disable()
+    try:
+        dead = MoonsPlan(32, "cuda", use_graph=True)
+        dead.step(*b)                      # captured: the plan now owns a CUDAGraph
+        torch.cuda.synchronize()
+        del dead                           # unreachable, but only the cyclic collector can free it
+        gc.enable()
+        gc.set_threshold(1, 1, 1)          # a collection at (nearly) every allocation, also inside the capture
+        plan = MoonsPlan(32, "cuda", use_graph=True)
+        sc = plan.step(*b)
+        sc2 = plan.step(*b)
+        torch.cuda.synchronize()
+        assert torch.isfinite(sc).all() and torch.isfinite(sc2).all()
+    finally:
+        gc.set_threshold(*old)
+        gc.enable()
