@@ -40,7 +40,8 @@ def peaks():
 
 # --------------------------------------------------------------------------------------------- CPU arm
 def cpu_step_rate(steps, warmup, batch=CPU_SAMPLE_BATCH, threads=None):
-    """Times the oracle port of the reference step (oracle/mnist_countergan.py) on the host cores."""
+    """Times the oracle port of the reference step (oracle/mnist_countergan.py) on the host cores.  Fallback of
+    ``reference_step_rate`` when ``baseline/_ref`` was not staged."""
     import torch
     from oracle import mnist_countergan as O
     threads = threads or os.cpu_count() or 1
@@ -59,26 +60,114 @@ def cpu_step_rate(steps, warmup, batch=CPU_SAMPLE_BATCH, threads=None):
     return batch * steps / dt, dt / steps * 1e3, threads
 
 
+class _TimedLoader:
+    """The ``train_loader`` handed to the reference's train_countergan: yields ``warmup + steps`` synthetic (x, y)
+    batches and stamps the wall clock each time the loop asks for the next one, i.e. exactly between two iterations of
+    trainer.py:89.  Stops early (never before ``min_steps`` timed iterations) once ``budget_s`` is used up."""
+
+    def __init__(self, batches, warmup, steps, budget_s, min_steps=3):
+        self.batches, self.warmup, self.steps, self.budget_s, self.min_steps = batches, warmup, steps, budget_s, min_steps
+        self.stamps = []
+
+    def __iter__(self):
+        t_begin = time.perf_counter()
+        for i in range(self.warmup + self.steps):
+            now = time.perf_counter()
+            self.stamps.append(now)
+            if i >= self.warmup + self.min_steps and now - t_begin > self.budget_s:
+                return
+            yield self.batches[i % len(self.batches)]
+        self.stamps.append(time.perf_counter())
+
+    def timed(self):
+        """(iterations, seconds) of the timed region: from the request of batch ``warmup`` to the last stamp."""
+        n = len(self.stamps) - 1 - self.warmup
+        return n, self.stamps[-1] - self.stamps[self.warmup]
+
+
+def reference_step_rate(steps, warmup, batch=BATCH, threads=None, budget_s=240.0):
+    """Drives the UNMODIFIED reference ``train_countergan`` (conditional_counteRGAN/mnist/trainer.py:76-163, staged at
+    baseline/_ref by baseline/vendor_ref.py) with the reference's own modules on the host cores: device="cpu", fp32,
+    hyper-parameters of config.py:10-15, synthetic batches of the bench workload.  Returns None when nothing is staged.
+    matplotlib (trainer.py:5) is absent from this image and stubbed; nothing else is touched."""
+    import contextlib
+    import importlib
+    import tempfile
+    import types
+    from unittest import mock
+    import torch
+    from baseline import vendor_ref
+    from oracle import mnist_countergan as O      # synthetic batch generator only
+    d = vendor_ref.staged_dir()
+    if d is None:
+        return None
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, mock.MagicMock())
+    for k in [k for k in sys.modules if k in ("trainer", "models", "config") or k.startswith("models.")]:
+        del sys.modules[k]
+    # models/discriminator.py:3,6 reads ONE default from the experiment's config module (Config.num_classes); config.py
+    # itself is not staged (it holds a hard-coded API key), so the bench supplies the values of config.py:4-27 it needs
+    cfg_mod = types.ModuleType("config")
+    cfg_mod.Config = type("Config", (), dict(batch_size=128, d_lr=1e-5, g_lr=5e-5, lambda_adv=1.0, lambda_cls=1.0,
+                                             lambda_reg=2.5, lambda_mask=2.0, patch_size=7, num_modifiable_patches=10,
+                                             img_shape=(1, 28, 28), num_classes=10))
+    sys.modules["config"] = cfg_mod
+    sys.path.insert(0, d)
+    try:
+        trainer = importlib.import_module("trainer")
+        Gm = importlib.import_module("models.generator")
+        Dm = importlib.import_module("models.discriminator")
+        Cm = importlib.import_module("models.classifier")
+    finally:
+        sys.path.remove(d)
+    torch.manual_seed(0)
+    G, D, C = Gm.ResidualGenerator(), Dm.Discriminator(), Cm.CNNClassifier().eval()      # main.py:24-33
+    for p in C.parameters():
+        p.requires_grad = False
+    batches = [O.synth_batch(batch, 10 + i)[:2] for i in range(2)]
+    loader = _TimedLoader(batches, warmup, steps, budget_s)
+    with tempfile.TemporaryDirectory() as tmp:
+        K = cfg_mod.Config
+        cfg = types.SimpleNamespace(g_lr=K.g_lr, d_lr=K.d_lr, num_epochs_gan=1, num_classes=K.num_classes,
+                                    patch_size=K.patch_size, num_modifiable_patches=K.num_modifiable_patches,
+                                    lambda_adv=K.lambda_adv, lambda_cls=K.lambda_cls, lambda_reg=K.lambda_reg,
+                                    lambda_mask=K.lambda_mask, save_dir=tmp, generator_path=os.path.join(tmp, "generator.pt"))
+        with contextlib.redirect_stdout(sys.stderr):          # the reference prints; stdout carries the JSON line only
+            trainer.train_countergan(G, D, C, loader, cfg, "cpu")
+    n, dt = loader.timed()
+    return batch * n / dt, dt / n * 1e3, threads, n
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
-    # bound the whole run to a few minutes regardless of K: ~2 s per B=128 step on 8 cores
-    steps = min(steps, 40)
-    warmup = min(warmup, 3)
-    rate, ms, threads = cpu_step_rate(steps, warmup)
-    sample = (f"oracle port of trainer.py:89-132 (torch CPU fp32), {steps} steps of B={CPU_SAMPLE_BATCH} "
-              f"after {warmup} warm-up, {threads} threads")
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    ref = reference_step_rate(steps, warmup)
+    if ref is not None:
+        rate, ms, threads, done = ref
+        kind, batch = "reference", BATCH
+        sample = (f"unmodified reference train_countergan (trainer.py:76-163, torch CPU fp32, staged at baseline/_ref), "
+                  f"{done} timed iterations of B={BATCH} after {warmup} warm-up, {threads} threads")
+    else:                                          # baseline/_ref not staged: the oracle port, bounded
+        done, warmup = min(steps, 40), min(warmup, 3)
+        rate, ms, threads = cpu_step_rate(done, warmup)
+        kind, batch = "port", CPU_SAMPLE_BATCH
+        sample = (f"oracle port of trainer.py:89-132 (torch CPU fp32), {done} steps of B={CPU_SAMPLE_BATCH} "
+                  f"after {warmup} warm-up, {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": done, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cpu_batch_per_step": CPU_SAMPLE_BATCH},
-        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "global_batch": batch, "cpu_batch_per_step": batch},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if done != steps:
+        line["steps_requested"] = steps           # the CPU arm stops after ~4 minutes of timed iterations
     print(json.dumps(line), flush=True)
 
 
@@ -189,17 +278,23 @@ def run_native(args):
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        p = tr.step(*ring[i % 4])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    # A block is EXACTLY K steps between barrier + synchronize; with a ~3 ms step a small K is a very short region, so
+    # the block is repeated until >= 100 steps were timed and the median block is reported (every block max over ranks).
+    blocks = max(1, -(-100 // args.steps))
+    block_ms = []
+    for _ in range(blocks):
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            p = tr.step(*ring[i % 4])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        block_ms.append(t.item())
     clk = clocks.stop() if clocks else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+    ms = sorted(block_ms)[len(block_ms) // 2]
     value = BATCH * world * args.steps / (ms * 1e-3)
     scal = p.scalars_dict()
 
@@ -287,9 +382,16 @@ def run_native(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.skip_cpu:
-            rate, _, threads = cpu_step_rate(3, 1)
-            cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": f"oracle port of trainer.py:89-132, 3 steps of B={CPU_SAMPLE_BATCH} after 1 warm-up"}
+            ref = reference_step_rate(5, 1, budget_s=30.0)
+            if ref is not None:
+                rate, _, threads, done = ref
+                cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "reference",
+                       "sample": f"unmodified reference train_countergan (baseline/_ref), {done} iterations of B={BATCH} "
+                                 "after 1 warm-up"}
+            else:
+                rate, _, threads = cpu_step_rate(3, 1)
+                cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                       "sample": f"oracle port of trainer.py:89-132, 3 steps of B={CPU_SAMPLE_BATCH} after 1 warm-up"}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -298,6 +400,7 @@ def run_native(args):
                        "cuda_graph": tr.use_graph, "l2": "working set (~3 GB of saved activations per step) >> 126 MB L2; "
                        "4 rotating input batches"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "timed_blocks": blocks, "block_ms": [round(b, 3) for b in block_ms],
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,

@@ -173,8 +173,13 @@ def test_capture_survives_cyclic_garbage():
         gc.enable()
         gc.set_threshold(1, 1, 1)          # a collection at (nearly) every allocation, also inside the capture
         plan = MoonsPlan(32, "cuda", use_graph=True)
-        sc = plan.step(*b)
-        sc2 = plan.step(*b)
+        gs, ds, cs = T.moons_shapes()
+        plan.G.load(T.synth_params(gs, 1))
+        plan.C.load(T.synth_params(cs, 3))
+        _load_critic(plan.D, T.synth_params(ds, 2), T.sn_buffers(T.moons_d_dims(), 4))
+        plan.refresh()
+        sc = plan.step(*b).clone()
+        sc2 = plan.step(*b).clone()
         torch.cuda.synchronize()
         assert torch.isfinite(sc).all() and torch.isfinite(sc2).all()
     finally:
