@@ -298,33 +298,50 @@ def run_native(args):
     value = BATCH * world * args.steps / (ms * 1e-3)
     scal = p.scalars_dict()
 
-    # ---- e2e: pinned host batches -> H2D -> device-side target/mask draw -> step -> D2H scalars, every step
+    # ---- e2e: the user-facing call (CounterGanTrainer.step_auto, what train_countergan runs per batch) with pinned HOST
+    # batches: every step copies x, y host->device, replays ONE graph (target / mask draw + the whole iteration) and
+    # reads the step's loss scalars device->host.  Two flavours: `e2e` reads asynchronously into pinned memory and
+    # consumes the values one step later (the GPU never waits for the host); `e2e_blocking` synchronises on every
+    # step's read like the reference's .item() calls (trainer.py:127-129).
     hx = [r[0].cpu().pin_memory() for r in ring]
     hy = [r[1].cpu().pin_memory() for r in ring]
-    e2e_steps = max(args.steps, 5)
+    e2e_steps = max(args.steps, 100)
+    host_scal = [torch.empty(p.scalars.numel(), dtype=torch.float32).pin_memory() for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    seen = []
 
-    def e2e_iter(i):
-        x = hx[i % 4].to(dev, non_blocking=True)
-        y = hy[i % 4].to(dev, non_blocking=True)
-        tgt = torch.randint(0, 10, (BATCH,), device=dev)          # trainer.py:94
-        mask = T.build_mask(x, 7, dev, 10)                        # trainer.py:95
-        p_ = tr.step(x, y, tgt, mask)
-        return p_, p_.scalars.cpu()               # D2H read of the losses (sync), as the reference's .item() calls
+    def e2e_iter(i, blocking):
+        p_ = tr.step_auto(hx[i % 4], hy[i % 4])
+        slot = i & 1
+        host_scal[slot].copy_(p_.scalars, non_blocking=True)
+        evs[slot].record()
+        if blocking:
+            evs[slot].synchronize()
+            seen.append(float(host_scal[slot][1]))
+        elif i >= 1:
+            evs[slot ^ 1].synchronize()           # the previous step's losses are on the host now
+            seen.append(float(host_scal[slot ^ 1][1]))
+        return p_
 
-    for i in range(3):                            # warm-up of the torch-side ops (lazy module loads, cuRAND init)
-        e2e_iter(i)
-    barrier()
-    e0.record()
-    for i in range(e2e_steps):
-        p, host_scal = e2e_iter(i)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = BATCH * world * e2e_steps / (t.item() * 1e-3)
+    def e2e_run(blocking):
+        for i in range(3):                        # warm-up (graph capture of the draw + step on first use)
+            e2e_iter(i, blocking)
+        barrier()
+        e0.record()
+        for i in range(e2e_steps):
+            e2e_iter(i, blocking)
+        e1.record()
+        barrier()
+        t_ = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return BATCH * world * e2e_steps / (t_.item() * 1e-3)
+
+    e2e_value = e2e_run(False)
+    e2e_blocking = e2e_run(True)
+    assert all(v == v for v in seen), "non-finite loss read back in the e2e loop"
     h2d = hx[0].numel() * 4 + hy[0].numel() * 8
-    d2h = host_scal.numel() * 4
+    d2h = host_scal[0].numel() * 4
 
     # ---- per-launcher device time inside the step (eager, CUDA events on the launching stream)
     prof, roof, detail = None, None, None
@@ -399,7 +416,9 @@ def run_native(args):
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                        "cuda_graph": tr.use_graph, "l2": "working set (~3 GB of saved activations per step) >> 126 MB L2; "
                        "4 rotating input batches"},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "read": "losses copied to pinned host memory every step, consumed one step later",
+                    "blocking_read_value": e2e_blocking},
             "timed_blocks": blocks, "block_ms": [round(b, 3) for b in block_ms],
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),

@@ -317,6 +317,20 @@ int pcg_adam_flat(float* p, const float* g, float* m, float* v, long long n, int
 int pcg_u8_batch(const unsigned char* images, const long long* labels, const long long* index, int B, int HW, float mean,
                  float stdv, float* x, long long* y, void* stream);
 
+/* Random patch mask and target draw of one iteration, replaces build_mask (conditional_counteRGAN/mnist/trainer.py:45-72:
+ * a Python loop of B randperm calls + F.interpolate + repeat) and `target_y = torch.randint(0, num_classes, (bs,))`
+ * (trainer.py:94) by ONE launch:
+ *   mask[B][C][H][W] (fp32, 0/1): per sample a uniformly random subset of `num_modifiable_patches` of the
+ *   (H / patch) x (W / patch) patches (at most 64) is set to 1 - independent fair coins per patch when
+ *   num_modifiable_patches < 0 or >= the patch count (trainer.py:59-61) - then nearest-upsampled to H x W
+ *   (source index = floor(dst * patches / size), as F.interpolate(mode="nearest")) and repeated over the C channels;
+ *   target[b] uniform in [0, num_classes) (target == NULL: not drawn).
+ * Randomness: Philox4x32-10, key = seed, counter = (sample, draw, stream offset).  rng_state points at two device
+ * uint64 {stream offset, 0}: the kernel uses the offset and advances it, so the launch may be replayed inside a CUDA
+ * graph; NULL = offset 0 (deterministic, for tests).  Same distribution as the reference, not the same stream. */
+int pcg_build_mask(int B, int C, int H, int W, int patch, int num_modifiable_patches, int num_classes,
+                   unsigned long long seed, unsigned long long* rng_state, float* mask, long long* target, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,6 +235,12 @@ int pcg_u8_batch(const unsigned char* images, const long long* labels, const lon
   u8_batch(images, labels, index, B, HW, mean, stdv, x, y, ST);
   PCG_API_END
 }
+int pcg_build_mask(int B, int C, int H, int W, int patch, int num_modifiable_patches, int num_classes,
+                   unsigned long long seed, unsigned long long* rng_state, float* mask, long long* target, void* stream) {
+  PCG_API_BEGIN
+  build_mask(B, C, H, W, patch, num_modifiable_patches, num_classes, seed, rng_state, mask, target, ST);
+  PCG_API_END
+}
 int pcg_adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
                   float beta2, float eps, float grad_scale, void* stream) {
   PCG_API_BEGIN

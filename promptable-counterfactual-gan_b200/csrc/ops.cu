@@ -515,4 +515,126 @@ void u8_batch(const uint8_t* images, const long long* labels, const long long* i
   PCG_LAUNCH_CHECK();
 }
 
+// ---- random patch mask + target draw (conditional_counteRGAN/mnist/trainer.py:45-72 build_mask, :94 target_y) -------
+// Philox4x32-10 counter-based generator (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter =
+// (sample index, draw index, stream offset lo, hi), key = seed.  The stream offset lives in device memory (rng[0]) and
+// is advanced by the last block to finish, so the launch can sit inside a replayed CUDA graph and still draw fresh
+// numbers every replay.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// uniform integer in [0, n) from a 32-bit draw (multiply-shift; bias < n / 2^32)
+__device__ __forceinline__ uint32_t bounded(uint32_t r, uint32_t n) { return __umulhi(r, n); }
+
+constexpr int MASK_SPB = 8;          // samples per block
+__global__ void build_mask_kernel(int B, int C, int H, int W, int nph, int npw, int k_sel, int num_classes,
+                                  unsigned long long seed, unsigned long long* __restrict__ rng,
+                                  float* __restrict__ mask, long long* __restrict__ target) {
+  pdl_enter();
+  __shared__ unsigned long long words[MASK_SPB];
+  const unsigned long long offset = rng != nullptr ? rng[0] : 0ull;
+  const int b0 = blockIdx.x * MASK_SPB;
+  const int total = nph * npw;
+  if (threadIdx.x < MASK_SPB && b0 + (int)threadIdx.x < B) {
+    const int b = b0 + threadIdx.x;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t olo = (uint32_t)offset, ohi = (uint32_t)(offset >> 32);
+    unsigned long long word = 0ull;
+    if (k_sel < 0 || k_sel >= total) {
+      // trainer.py:59-61: every patch an independent fair coin
+      for (int i = 0; i < total; i += 32) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)b, 1u + (uint32_t)(i >> 5), olo, ohi), key);
+        word |= (unsigned long long)r.x << i;
+      }
+      if (total < 64) word &= (1ull << total) - 1ull;
+    } else {
+      // trainer.py:63-65: randperm(total)[:k] = a uniformly random k-subset; partial Fisher-Yates over a patch list
+      // packed in registers is replaced by selection sampling on the bit set: the j-th pick is the (r mod remaining)-th
+      // still-free patch, which is the same distribution
+      unsigned long long free_bits = total < 64 ? (1ull << total) - 1ull : ~0ull;
+      uint4 r = make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < k_sel; ++j) {
+        if ((j & 3) == 0) r = philox4x32_10(make_uint4((uint32_t)b, 1u + (uint32_t)(j >> 2), olo, ohi), key);
+        const uint32_t draw = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
+        int nth = (int)bounded(draw, (uint32_t)(total - j));
+        unsigned long long f = free_bits;
+        for (int t = 0; t < nth; ++t) f &= f - 1ull;           // drop the nth lowest free bits
+        const unsigned long long pick = f & (~f + 1ull);       // lowest remaining free bit
+        word |= pick;
+        free_bits &= ~pick;
+      }
+    }
+    words[threadIdx.x] = word;
+    if (target != nullptr) {
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)b, 0u, olo, ohi), key);
+      target[b] = (long long)bounded(r.x, (uint32_t)num_classes);           // trainer.py:94 randint(0, num_classes)
+    }
+  }
+  __syncthreads();
+  // nearest up-sampling (F.interpolate(..., size=(h, w), mode="nearest"), trainer.py:68-70: source = floor(dst * in / out))
+  // and the repeat over channels; one float4 (four pixels of a row) per thread iteration when W % 4 == 0
+  const int nb = min(MASK_SPB, B - b0);
+  const long long per = (long long)C * H * W;
+  if ((W & 3) == 0) {
+    const long long n4 = nb * per / 4;
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+      const long long e = i * 4;
+      const int sb = (int)(e / per);
+      const int rem = (int)(e - sb * per);
+      const int hw = rem % (H * W), h = hw / W, w0 = hw - h * W;
+      const unsigned long long word = words[sb];
+      const int ph = min((h * nph) / H, nph - 1);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pw = min(((w0 + j) * npw) / W, npw - 1);
+        v[j] = (float)((word >> (ph * npw + pw)) & 1ull);
+      }
+      *reinterpret_cast<float4*>(mask + (long long)b0 * per + e) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    for (long long e = threadIdx.x; e < nb * per; e += blockDim.x) {
+      const int sb = (int)(e / per);
+      const int rem = (int)(e - sb * per);
+      const int hw = rem % (H * W), h = hw / W, w = hw - h * W;
+      const int ph = min((h * nph) / H, nph - 1), pw = min((w * npw) / W, npw - 1);
+      mask[(long long)b0 * per + e] = (float)((words[sb] >> (ph * npw + pw)) & 1ull);
+    }
+  }
+  if (rng != nullptr) {
+    // advance the stream offset once per launch: the last block to arrive does it (every block read rng[0] above)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long ticket = atomicAdd(rng + 1, 1ull);
+      if (ticket == (unsigned long long)gridDim.x - 1ull) {
+        rng[1] = 0ull;
+        rng[0] = offset + 1ull;
+        __threadfence();
+      }
+    }
+  }
+}
+void build_mask(int B, int C, int H, int W, int patch, int k_sel, int num_classes, unsigned long long seed,
+                unsigned long long* rng, float* mask, long long* target, cudaStream_t s) {
+  PCG_PROFILE("build_mask", s);
+  PCG_REQUIRE(B >= 1 && C >= 1 && patch >= 1 && H >= patch && W >= patch, "mask geometry");
+  const int nph = H / patch, npw = W / patch;
+  PCG_REQUIRE(nph * npw <= 64, "at most 64 patches per image (one 64-bit word per sample)");
+  PCG_REQUIRE(target == nullptr || num_classes >= 1, "num_classes");
+  PCG_REQUIRE((reinterpret_cast<uintptr_t>(mask) & 15) == 0, "mask must be 16-byte aligned");
+  launch_k(build_mask_kernel, dim3((B + MASK_SPB - 1) / MASK_SPB), dim3(256), 0, s, B, C, H, W, nph, npw, k_sel, num_classes,
+           seed, rng, mask, target);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 }  // namespace pcg

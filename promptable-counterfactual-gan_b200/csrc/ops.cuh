@@ -54,5 +54,10 @@ void scale_cols(const float* dy, long long rows, int C, const float* scale, floa
 // x[b][HW] = (float(images[index[b]][.]) / 255 - mean) / std ; y[b] = labels[index[b]]  (index == nullptr: identity)
 void u8_batch(const uint8_t* images, const long long* labels, const long long* index, int B, int HW, float mean, float stdv,
               float* x, long long* y, cudaStream_t s);
+// mask[B][C][H][W] in {0,1}: k_sel of the (H/patch)*(W/patch) patches per sample chosen uniformly at random (k_sel < 0 or
+// >= total: independent fair coins), nearest-upsampled; target[b] ~ U{0..num_classes-1} (nullptr: no draw).
+// rng = device {stream offset, ticket} (advanced by the kernel) or nullptr (offset 0).
+void build_mask(int B, int C, int H, int W, int patch, int k_sel, int num_classes, unsigned long long seed,
+                unsigned long long* rng, float* mask, long long* target, cudaStream_t s);
 
 }  // namespace pcg

@@ -15,9 +15,9 @@ G step uses the updated D (trainer.py:112 -> :116), G's before ``opt_g.step()`` 
 import os
 
 import torch
-import torch.nn.functional as F
 
 from .. import graphs
+from .. import ops as K
 from . import binding
 from . import plan as P
 
@@ -27,21 +27,57 @@ def grad_norm(parameters):
     return torch.sqrt(sum((p.grad.data.norm() ** 2) for p in parameters if p.grad is not None)).item()
 
 
+class _Rng:
+    """Per-device Philox stream state of the native mask / target kernel: ``seed`` follows torch's global seed
+    (``torch.manual_seed`` restarts the stream, as it would restart the reference's draws), the device-side offset is
+    advanced by every launch, so a launch captured in a CUDA graph draws fresh numbers at every replay."""
+    _states = {}
+
+    @classmethod
+    def get(cls, device):
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        seed = torch.initial_seed()
+        st = cls._states.get(device)
+        if st is None or st[0] != seed:
+            rank = 0
+            dist, world = _world()
+            if dist is not None:
+                rank = dist.get_rank()                     # per-rank sub-streams (SURVEY 8e)
+            st = (seed, (seed + 0x9E3779B97F4A7C15 * rank) & (2 ** 63 - 1), torch.zeros(2, dtype=torch.int64, device=device))
+            cls._states[device] = st
+        return st[1], st[2]
+
+
 def build_mask(x, patch_size, device, num_modifiable_patches=None):
-    """Random binary patch mask, same distribution as trainer.py:45-72 (uniformly random subset of
-    ``num_modifiable_patches`` patches per sample, nearest-upsampled), without the per-sample Python
-    loop: one batched argsort of uniform keys instead of ``bs`` randperm calls."""
+    """Random binary patch mask with the distribution of trainer.py:45-72 - per sample a uniformly random subset of
+    ``num_modifiable_patches`` patches (fair coins per patch when that is None or >= the patch count), nearest-upsampled
+    and repeated over the channels - in ONE native launch (``pcg_build_mask``, Philox) instead of the reference's Python
+    loop of ``bs`` randperm calls."""
     bs, c, h, w = x.shape
-    nh, nw = h // patch_size, w // patch_size
-    total = nh * nw
-    if num_modifiable_patches is None or num_modifiable_patches >= total:
-        patch_mask = torch.randint(0, 2, (bs, 1, nh, nw), device=device).float()
-    else:
-        keys = torch.rand(bs, total, device=device)
-        idx = keys.argsort(dim=1)[:, :num_modifiable_patches]
-        patch_mask = torch.zeros(bs, total, device=device).scatter_(1, idx, 1.0).view(bs, 1, nh, nw)
-    mask = F.interpolate(patch_mask, size=(h, w), mode="nearest").repeat(1, c, 1, 1)
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("pcg_b200.mnist.trainer.build_mask needs a CUDA device (there is no CPU fallback)")
+    mask = torch.empty(bs, c, h, w, dtype=torch.float32, device=device)
+    seed, state = _Rng.get(device)
+    with torch.cuda.device(mask.device):
+        K.build_mask(bs, c, h, w, patch_size, num_modifiable_patches, mask, None, seed=seed, rng_state=state)
     return mask
+
+
+def draw_target_and_mask(x, cfg, device):
+    """trainer.py:94-95 (``target_y = torch.randint(0, num_classes, (bs,))`` and ``build_mask``) as one launch."""
+    bs, c, h, w = x.shape
+    mask = torch.empty(bs, c, h, w, dtype=torch.float32, device=device)
+    target = torch.empty(bs, dtype=torch.int64, device=device)
+    seed, state = _Rng.get(device)
+    with torch.cuda.device(mask.device):
+        K.build_mask(bs, c, h, w, cfg.patch_size, cfg.num_modifiable_patches, mask, target, cfg.num_classes, seed=seed,
+                     rng_state=state)
+    return target, mask
+
+
+_NATIVE_DRAW = draw_target_and_mask
 
 
 def _world():
@@ -110,17 +146,7 @@ class CounterGanTrainer:
     def step(self, x, y, target, mask):
         """One iteration on device tensors; returns the plan whose ``scalars`` hold the losses."""
         bs = x.shape[0]
-        p = self.plan(bs)
-        if self._last_bs is not None and self._last_bs != bs:
-            # every plan owns packed copies of the conv weights, refreshed by ITS OWN Adam phases only: the loader has
-            # no drop_last (data_utils.py:27; 54000 % 128 = 112), so the tail-batch plan and the full-batch plan
-            # alternate and each must re-pack what the other one updated before its forward runs
-            p.refresh_weights()
-        self._last_bs = bs
-        for m in (self.G, self.D, self.C):
-            # forward-only plans cached on the modules (models/_native.py) re-pack on their next call: the native Adam
-            # writes below do not bump torch's parameter version counters
-            m.__dict__["_pcg_seen"] = None
+        p = self._prepare(bs)
         if not self.use_graph:
             self._run_phases(p, x, y, target, mask)
             return p
@@ -139,11 +165,57 @@ class CounterGanTrainer:
         g()
         return p
 
-    def _capture(self, p, st):
+    def _prepare(self, bs):
+        """The plan of this batch size, with its packed weights and the modules' forward plans made consistent."""
+        p = self.plan(bs)
+        if self._last_bs is not None and self._last_bs != bs:
+            # every plan owns packed copies of the conv weights, refreshed by ITS OWN Adam phases only: the loader has
+            # no drop_last (data_utils.py:27; 54000 % 128 = 112), so the tail-batch plan and the full-batch plan
+            # alternate and each must re-pack what the other one updated before its forward runs
+            p.refresh_weights()
+        self._last_bs = bs
+        for m in (self.G, self.D, self.C):
+            # forward-only plans cached on the modules (models/_native.py) re-pack on their next call: the native Adam
+            # writes below do not bump torch's parameter version counters
+            m.__dict__["_pcg_seen"] = None
+        return p
+
+    def step_auto(self, x, y):
+        """One iteration as the reference loop runs it: x, y may be (pinned) host or device tensors; the target classes
+        and the patch mask (trainer.py:94-95) are drawn on the device by the first node of the replayed graph."""
+        bs = x.shape[0]
+        if not self.use_graph or draw_target_and_mask is not _NATIVE_DRAW:
+            # eager mode, or a caller replaced the draw (tests inject the reference's draws): explicit inputs
+            xd = x.to(self.device, non_blocking=True).float().contiguous()
+            yd = y.to(self.device, non_blocking=True).long().contiguous()
+            target, mask = draw_target_and_mask(xd, self.cfg, self.device)
+            return self.step(xd, yd, target, mask)
+        p = self._prepare(bs)
+        st = self.static.get(bs)
+        if st is None:
+            st = (torch.empty(bs, 1, 28, 28, device=self.device), torch.empty(bs, dtype=torch.int64, device=self.device),
+                  torch.empty(bs, dtype=torch.int64, device=self.device), torch.empty(bs, 1, 28, 28, device=self.device))
+            self.static[bs] = st
+        st[0].copy_(x.reshape(bs, 1, 28, 28), non_blocking=True)
+        st[1].copy_(y, non_blocking=True)
+        g = self.graphs.get((bs, "auto"))
+        if g is None:
+            seed, state = _Rng.get(self.device)
+            cfg = self.cfg
+
+            def draw():
+                K.build_mask(bs, 1, 28, 28, cfg.patch_size, cfg.num_modifiable_patches, st[3], st[2], cfg.num_classes,
+                             seed=seed, rng_state=state)
+            g = self._capture(p, st, draw)
+            self.graphs[(bs, "auto")] = g
+        g()
+        return p
+
+    def _capture(self, p, st, pre=None):
         if self.dist is not None:
             # NCCL collectives sit between the phases: capture the three kernel-only segments
             segs = []
-            for fn in (lambda: p.step_d_grads(*st),
+            for fn in (lambda: ((pre() if pre else None), p.step_d_grads(*st)),
                        lambda: (p.step_d_update(), p.step_g_grads(*st)),
                        lambda: p.step_g_update()):
                 segs.append(self._capture_fn(fn))
@@ -155,7 +227,7 @@ class CounterGanTrainer:
                 self._allreduce(self.ga.grad)
                 segs[2].replay()
             return run
-        g = self._capture_fn(lambda: p.step(*st))
+        g = self._capture_fn(lambda: ((pre() if pre else None), p.step(*st)))
         return g.replay
 
     @staticmethod
@@ -193,16 +265,12 @@ def train_countergan(generator, discriminator, classifier, train_loader, cfg, de
         num_batches = 0
         p = None
         for batch_idx, (x, y) in enumerate(train_loader):
-            x = x.to(tr.device, non_blocking=True).float().contiguous()
-            y = y.to(tr.device, non_blocking=True).long().contiguous()
             bs = x.size(0)
             num_batches += 1
             if bs not in warmed:
                 _warm_plan(tr, bs)
                 warmed.add(bs)
-            target_y = torch.randint(0, cfg.num_classes, (bs,), device=tr.device)            # trainer.py:94
-            mask = build_mask(x, cfg.patch_size, tr.device, cfg.num_modifiable_patches)      # trainer.py:95
-            p = tr.step(x, y, target_y, mask.contiguous())
+            p = tr.step_auto(x, y)            # target / mask draw (trainer.py:94-95) + the whole iteration: one replay
             acc += p.scalars
             if batch_idx % 100 == 0:
                 s = p.scalars_dict()                                                        # one sync / 100 steps

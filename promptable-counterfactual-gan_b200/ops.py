@@ -259,6 +259,14 @@ def ce_loss(logits, target, loss, dlogits, wgt=1.0):
     _lib.check(_L().pcg_ce_loss(P(logits), P(target), B, NC, _f(wgt), P(loss), P(dlogits), _s()))
 
 
+def build_mask(B, C, H, W, patch, num_modifiable_patches, mask, target=None, num_classes=10, seed=0, rng_state=None):
+    """One launch: random patch mask [B,C,H,W] (+ target draw [B] int64); see include/pcg.h pcg_build_mask."""
+    _chk(mask, target, rng_state)
+    k = -1 if num_modifiable_patches is None else int(num_modifiable_patches)
+    _lib.check(_L().pcg_build_mask(B, C, H, W, patch, k, num_classes, ctypes.c_ulonglong(seed & (2 ** 64 - 1)),
+                                   P(rng_state), P(mask), P(target), _s()))
+
+
 def adam(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     _chk(p, g, m, v, step)
     _lib.check(_L().pcg_adam_flat(P(p), P(g), P(m), P(v), _ll(p.numel()), P(step), _f(lr), _f(beta1), _f(beta2), _f(eps),

@@ -150,15 +150,31 @@ def test_dcgan_tensor_core_phases_match_oracle():
         assert l2(plan.G.g(k), gr["G"][k]) < 1e-2, (k, l2(plan.G.g(k), gr["G"][k]))
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_dcgan_tensor_core_step_runs_in_graph(graph):
-    """Full iteration (D update, G through the updated D, G update) in tensor-core mode, eager and graph-replayed."""
-    B = 16
+@pytest.mark.parametrize("graph,B", [(False, 16), (True, 16), (True, 256)])       # 256 = BASELINE configs[3]
+def test_dcgan_tensor_core_step_runs_in_graph(graph, B):
+    """Full iteration (D update, G through the updated D, G update) in tensor-core mode, eager and graph-replayed, at a
+    small batch and at the benchmarked one: loss scalars, the fake batch, every discriminator and generator gradient
+    (relative L2; the generator's are taken through the natively UPDATED discriminator, so they also carry the Adam
+    step's +-lr flips of noise-level elements) and the first Adam update of every tensor in units of lr."""
     S, plan = _fresh(B, graph, tc=True)
     for step in range(2):
         real, noise = O.synth_batch(B, 170 + step)
+        pG0 = {k: v.detach().clone() for k, v in S["G"].items()}
+        pD0 = {k: v.detach().clone() for k, v in S["D"].items()}
         sc, gr = O.dcgan_step(S, real, noise)
         got = plan.step(real.cuda(), noise.cuda()).tolist()
+        torch.cuda.synchronize()
         tol = 1e-3 if step == 0 else 3e-2
         for i, k in ((0, "errD"), (1, "errG"), (4, "D_x"), (5, "D_G_z1")):
             assert abs(got[i] - sc[k]) <= tol * abs(sc[k]) + 1e-6, (step, k, got[i], sc[k])
+        if step == 0:
+            assert l2(plan.ga[4].view(B, 1, 64, 64), gr["fake"]) < 1e-4
+            for k in gr["D"]:
+                assert l2(plan.D.g(k), gr["D"][k]) < 1e-2, ("dD", k, l2(plan.D.g(k), gr["D"][k]))
+            for k in gr["G"]:
+                assert l2(plan.G.g(k), gr["G"][k]) < 3e-2, ("dG", k, l2(plan.G.g(k), gr["G"][k]))
+            for net, P0, key, flat in ((S["D"], pD0, "D", plan.D), (S["G"], pG0, "G", plan.G)):
+                for k in P0:
+                    d_nat = flat.p(k).cpu() - P0[k]
+                    d_or = net[k].detach() - P0[k]
+                    assert ((d_nat - d_or).abs().mean() / 2e-4).item() < 0.1, (key, k)

@@ -131,3 +131,54 @@ def test_native_fp32_reproduces_reference_goldens(name):
         i = names.index(k)
         return da.view(i, dk[i][1])
     _check_train_summaries(z, get, n_steps, 5e-5, 0.05)
+
+
+@pytest.mark.gpu
+def test_native_bf16_plan_against_reference_golden():
+    """The BENCHMARKED precision (bf16 storage, tcgen05 convolutions) against the vectors the reference itself produced
+    (full architecture): forwards to bf16 tolerance (relative L2 1e-2), and after the training iterations every sampled
+    parameter within the Adam bound 2*lr*steps of the reference's, half of them within 0.5*lr, absolute sums to 1e-3."""
+    import pcg_b200  # noqa: F401
+    from pcg_b200.mnist import plan as P
+    z, ch, nres, B, n_steps = _load("full")
+    PG, BG, PD, PC = _params(ch, nres)
+    ga = P.Arena(0, ch, nres, "cuda").load_dict([v.cuda() for v in PG.values()])
+    da = P.Arena(1, ch, nres, "cuda").load_dict([v.cuda() for v in PD.values()])
+    ca = P.Arena(2, ch, nres, "cuda").load_dict([v.cuda() for v in PC.values()])
+    running = torch.zeros(2 * nres, 2, ch, device="cuda")
+    running[:, 1] = 1
+    nbt = torch.zeros(2 * nres, dtype=torch.int64, device="cuda")
+    plan = P.MnistStepPlan(B, ga, da, ca, running, nbt, P.StepConfig(precision="bf16"), ch, nres)
+    x, y, t, mask = (v.cuda().contiguous() for v in O.synth_batch(B, 700))
+
+    def l2(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300)
+    raw, masked = plan.g_forward(x, t, mask, True)
+    assert l2(raw.cpu().numpy(), z["fwd_raw"]) < 1e-2 and l2(masked.cpu().numpy(), z["fwd_masked"]) < 1e-2
+    assert l2(plan.d_forward(x, y).cpu().numpy(), z["fwd_d_logits"]) < 2e-2
+    assert l2(plan.c_forward(x).cpu().numpy(), z["fwd_c_logits"]) < 2e-2
+    ga.load_dict([v.cuda() for v in PG.values()])
+    running.zero_()
+    running[:, 1] = 1
+    nbt.zero_()
+    plan.refresh_weights()
+    for i in range(n_steps):
+        b = O.synth_batch(B, 800 + i, mnist_like=(i % 2 == 1))
+        plan.step(*(v.cuda().contiguous() for v in b))
+    torch.cuda.synchronize()
+    gk, dk = list(O.g_param_shapes(ch, nres).items()), list(O.d_param_shapes().items())
+    for key in z.files:
+        if not key.startswith("train_"):
+            continue
+        net, k = key[6], key[8:]
+        names = [n for n, _ in (gk if net == "G" else dk)]
+        if k not in names or O.is_bn_shadowed_bias(k):
+            continue
+        i = names.index(k)
+        got = _summary((ga if net == "G" else da).view(i, (gk if net == "G" else dk)[i][1]))
+        ref, lr = z[key], (5e-5 if net == "G" else 1e-5)
+        d = np.abs(got[2:] - ref[2:])
+        assert d.max() <= 2.02 * lr * n_steps + 1e-7, (key, d.max())
+        assert np.median(d) <= 0.5 * lr + 1e-7, (key, np.median(d))
+        assert abs(got[1] - ref[1]) <= 1e-3 * abs(ref[1]) + 1e-6, key

@@ -213,6 +213,14 @@ def test_step_bf16_full_arch():
     _run_step_compare(B=32, ch=64, nres=6, n_steps=2, **BF16)
 
 
+def test_step_bf16_benchmark_batch_512():
+    """The benchmarked configuration itself (BASELINE configs[4]: batch 512, ch 64, 6 residual blocks, bf16 tensor-core
+    plan): every saved activation, x_cf, the logits, all D and G gradients, the first Adam update and the BatchNorm
+    running statistics against the oracle.  Exercises what the small batches cannot: the weight-gradient split over
+    148 CTAs, the multi-wave tile queues and the statistics finalize over 148 partial rows."""
+    _run_step_compare(B=512, ch=64, nres=6, n_steps=1, **BF16)
+
+
 def test_step_bf16_ragged_batch():
     _run_step_compare(B=5, ch=64, nres=2, n_steps=1, mnist_like=True, **BF16)
 
@@ -253,6 +261,47 @@ def test_tensor_core_path_matches_cuda_core_path_in_bf16():
     print("tc vs cuda-core (bf16 storage), worst rel-L2:", worst[:6])
     # two independent bf16 realisations of the same step differ by ~sqrt(2) x the noise floor (<= 0.1 here)
     assert worst[0][0] < 0.15, worst[:6]
+
+
+def test_loss_curves_full_architecture_200_steps_reference_lrs():
+    """'loss curves over N=200 steps'.  The REAL architecture (ch 64, 6 residual blocks) at the reference's
+    own learning rates (config.py:10-11), bf16 tensor-core plan against the fp32 oracle from the same state and the same
+    200 batches: every loss scalar within 5 % of the oracle's at every step, and after the 200 Adam steps the cumulative
+    parameter movement of every convolution weight points the same way (cosine > 0.9) with the same length (10 %)."""
+    hp = O.Hyper()
+    B, ch, nres, steps = 16, 64, 6, 200
+    H = Harness(B, ch, nres, "bf16", seed=21, hp=hp)
+    keys = ("d_loss", "g_loss", "g_adv", "g_cls", "reg_l1")
+    p0 = {k: v.detach().clone() for k, v in H.S["G"].items()}
+    d0 = {k: v.detach().clone() for k, v in H.S["D"].items()}
+    nat, ora = [], []
+    for i in range(steps):
+        x, y, t, mask = O.synth_batch(B, 9000 + i, mnist_like=(i % 3 == 1))
+        sc, _ = O.countergan_step(H.S, x, y, t, mask, n_resblocks=nres, hp=hp)
+        H.plan.step(x.cuda(), y.cuda(), t.cuda(), mask.cuda().contiguous())
+        nat.append(H.plan.scalars.clone())
+        ora.append([sc[k] for k in keys])
+    torch.cuda.synchronize()
+    from pcg_b200.mnist.plan import SCALAR_NAMES
+    idx = [SCALAR_NAMES.index(k) for k in keys]
+    nat = torch.stack(nat).cpu()[:, idx].double()
+    ora = torch.tensor(ora).double()
+    rel = ((nat - ora).abs() / ora.abs().clamp_min(1e-3)).max(0).values
+    print("200-step curve, worst relative deviation per scalar:", dict(zip(keys, rel.tolist())))
+    assert torch.all(rel < 5e-2), dict(zip(keys, rel.tolist()))
+    worst = []
+    for arena, shapes, ref0, net in ((H.ga, H.g_shapes(), p0, "G"), (H.da, O.d_param_shapes(), d0, "D")):
+        now = H.arena_dict(arena, shapes)
+        for k in now:
+            if now[k].dim() != 4:
+                continue
+            a, b = (now[k] - ref0[k]).double().flatten(), (H.S[net][k].detach() - ref0[k]).double().flatten()
+            cos = (a @ b / (a.norm() * b.norm() + 1e-300)).item()
+            worst.append((cos, (a.norm() / b.norm()).item(), net + "/" + k))
+    worst.sort()
+    print("200-step parameter movement, lowest cosines (cos, |native|/|oracle|, tensor):", worst[:4])
+    assert worst[0][0] > 0.9, worst[:4]
+    assert all(0.9 < w[1] < 1.1 for w in worst), worst[:4]
 
 
 def test_loss_curves_track_oracle_over_many_steps():

@@ -85,20 +85,14 @@ def test_train_countergan_matches_oracle(tmp_path, use_graph, monkeypatch):
                                 num_modifiable_patches=10, lambda_adv=1.0, lambda_cls=1.0, lambda_reg=2.5,
                                 lambda_mask=2.0, save_dir=str(tmp_path), generator_path=str(tmp_path / "generator.pt"))
     it = {"i": 0}
-    real_randint = torch.randint
 
-    def fake_randint(*a, **k):
-        return batches[it["i"]][2].clone().to(k.get("device", "cpu"))
-
-    def fake_build_mask(x, ps, device, n=None):
-        m = batches[it["i"]][3].clone().to(device)
+    def fake_draw(x, cfg_, device):          # the reference's draws (trainer.py:94-95), injected
+        t, m = batches[it["i"]][2].clone().to(device), batches[it["i"]][3].clone().to(device)
         it["i"] += 1
-        return m
+        return t, m
 
-    monkeypatch.setattr(T, "build_mask", fake_build_mask)
-    monkeypatch.setattr(torch, "randint", fake_randint)
+    monkeypatch.setattr(T, "draw_target_and_mask", fake_draw)
     out = T.train_countergan(G, D, C, [(b[0], b[1]) for b in batches], cfg, "cuda")
-    monkeypatch.setattr(torch, "randint", real_randint)
     sums = {"g_loss": 0.0, "d_loss": 0.0, "g_cls": 0.0}
     for (x, y, t, m) in batches:
         sc, _ = O.countergan_step(S, x, y, t, m, n_resblocks=2)
@@ -138,20 +132,14 @@ def test_train_countergan_ragged_tail_batch_two_epochs(tmp_path, monkeypatch):
                                 num_modifiable_patches=10, lambda_adv=1.0, lambda_cls=1.0, lambda_reg=2.5,
                                 lambda_mask=2.0, save_dir=str(tmp_path), generator_path=str(tmp_path / "generator.pt"))
     it = {"i": 0}
-    real_randint = torch.randint
 
-    def fake_randint(*a, **k):
-        return draws[it["i"]][2].clone().to(k.get("device", "cpu"))
-
-    def fake_build_mask(x, ps, device, n=None):
-        m = draws[it["i"]][3].clone().to(device)
+    def fake_draw(x, cfg_, device):
+        t, m = draws[it["i"]][2].clone().to(device), draws[it["i"]][3].clone().to(device)
         it["i"] += 1
-        return m
+        return t, m
 
-    monkeypatch.setattr(T, "build_mask", fake_build_mask)
-    monkeypatch.setattr(torch, "randint", fake_randint)
+    monkeypatch.setattr(T, "draw_target_and_mask", fake_draw)
     out = T.train_countergan(G, D, C, [(b[0], b[1]) for b in epoch], cfg, "cuda")
-    monkeypatch.setattr(torch, "randint", real_randint)
     per_epoch = []
     for e in range(2):
         tot = 0.0
@@ -177,12 +165,71 @@ def test_train_countergan_ragged_tail_batch_two_epochs(tmp_path, monkeypatch):
 
 
 def test_build_mask_distribution():
-    from pcg_b200.mnist.trainer import build_mask
-    x = torch.zeros(4096, 1, 28, 28, device="cuda")
+    """Properties of trainer.py:45-72 / :94 the native Philox kernel must reproduce (same distribution, not the same
+    stream): exactly num_modifiable_patches * patch^2 ones per sample, every patch equally likely, every PAIR of patches
+    equally likely (a uniformly random subset, not just uniform marginals), uniform targets, fresh draws per launch."""
+    from pcg_b200.mnist import trainer as T
+    import types
+    B = 8192
+    x = torch.zeros(B, 1, 28, 28, device="cuda")
     torch.manual_seed(0)
-    m = build_mask(x, 7, "cuda", 10)
-    assert m.shape == x.shape and torch.all(m.sum(dim=(1, 2, 3)) == 490)       # trainer.py:63-65 semantics
-    pm = m[:, 0, ::7, ::7].reshape(4096, 16)
+    m = T.build_mask(x, 7, "cuda", 10)
+    assert m.shape == x.shape and m.dtype == torch.float32
+    assert torch.all(m.sum(dim=(1, 2, 3)) == 490)                              # trainer.py:63-65 semantics
+    assert torch.equal(m, m.round()) and m.min() == 0 and m.max() == 1
+    pm = m[:, 0, ::7, ::7].reshape(B, 16)
+    assert torch.equal(torch.nn.functional.interpolate(pm.view(B, 1, 4, 4), size=(28, 28), mode="nearest"), m)
     freq = pm.mean(0)                                                          # each patch chosen w.p. 10/16
-    assert torch.all((freq - 10 / 16).abs() < 0.04)
-    assert torch.equal(m, m[:, :, :, :].round())
+    assert torch.all((freq - 10 / 16).abs() < 0.03), freq
+    pair = (pm.t() @ pm) / B                                                   # P(i and j) = 10/16 * 9/15 = 0.375
+    off = pair[~torch.eye(16, dtype=torch.bool, device="cuda")]
+    assert torch.all((off - 0.375).abs() < 0.03), (off.min(), off.max())
+    # consecutive launches advance the stream; re-seeding restarts it
+    m2 = T.build_mask(x, 7, "cuda", 10)
+    assert not torch.equal(m, m2)
+    torch.manual_seed(0)
+    assert torch.equal(T.build_mask(x, 7, "cuda", 10), m)
+    # target draw in the same launch: uniform over the classes, independent of the mask
+    cfg = types.SimpleNamespace(patch_size=7, num_modifiable_patches=10, num_classes=10)
+    t, m3 = T.draw_target_and_mask(x, cfg, "cuda")
+    assert t.dtype == torch.int64 and t.min() >= 0 and t.max() <= 9 and torch.all(m3.sum(dim=(1, 2, 3)) == 490)
+    hist = torch.bincount(t, minlength=10).float() / B
+    assert torch.all((hist - 0.1).abs() < 0.015), hist
+    # None / >= total: independent fair coins per patch (trainer.py:59-61)
+    mb = T.build_mask(x, 7, "cuda", None)
+    pb = mb[:, 0, ::7, ::7].reshape(B, 16)
+    assert torch.all((pb.mean(0) - 0.5).abs() < 0.03) and (pb.sum(1).float().var() - 4.0).abs() < 0.4
+    # general geometry: 3 channels, sizes that are not multiples of the patch: nearest up-sampling as F.interpolate
+    xg = torch.zeros(33, 3, 30, 33, device="cuda")
+    mg = T.build_mask(xg, 7, "cuda", 5)
+    ih = [-(-ph * 30 // 4) for ph in range(4)]
+    iw = [-(-pw * 33 // 4) for pw in range(4)]
+    pg = mg[:, 0][:, ih][:, :, iw]
+    assert torch.all(pg.sum(dim=(1, 2)) == 5)
+    want = torch.nn.functional.interpolate(pg.unsqueeze(1), size=(30, 33), mode="nearest").repeat(1, 3, 1, 1)
+    assert torch.equal(mg, want)
+
+
+def test_step_auto_draws_inside_the_graph(tmp_path):
+    """``step_auto`` (what train_countergan calls): host batches in, target + mask drawn by the first node of the replayed
+    graph, fresh at every replay; the losses stay finite and the step counter advances."""
+    from pcg_b200.mnist import trainer as T
+    G, D, C = _mods(64, 2, seed=3)
+    G, D, C = G.cuda(), D.cuda(), C.cuda()
+    cfg = types.SimpleNamespace(g_lr=5e-5, d_lr=1e-5, num_classes=10, patch_size=7, num_modifiable_patches=10,
+                                lambda_adv=1.0, lambda_cls=1.0, lambda_reg=2.5, lambda_mask=2.0)
+    tr = T.CounterGanTrainer(G, D, C, cfg, "cuda", precision="bf16")
+    T._warm_plan(tr, 16)
+    x, y, _, _ = O.synth_batch(16, 11)
+    hx, hy = x.pin_memory(), y.pin_memory()
+    masks, targets = [], []
+    for _ in range(3):
+        p = tr.step_auto(hx, hy)
+        torch.cuda.synchronize()
+        st = tr.static[16]
+        masks.append(st[3].clone())
+        targets.append(st[2].clone())
+        assert torch.isfinite(p.scalars[:10]).all()
+        assert torch.all(st[3].sum(dim=(1, 2, 3)) == 490) and torch.equal(st[0].cpu(), x)
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    assert int(p.adam["g_step"]) == 3

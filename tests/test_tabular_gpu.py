@@ -89,7 +89,7 @@ def _kc_plan(B, graph):
     return KcPlan(B, "cuda", cat, T.KC_CONT, use_graph=graph)
 
 
-@pytest.mark.parametrize("graph,B", [(False, 64), (True, 256)])
+@pytest.mark.parametrize("graph,B", [(False, 64), (True, 256), (True, 4096)])      # 4096 = BASELINE configs[2]
 def test_kc_step_matches_oracle(graph, B):
     gs, ds, cs = T.kc_shapes()
     PG, PD, PC = T.synth_params(gs, 1), T.synth_params(ds, 2), T.synth_params(cs, 3)
