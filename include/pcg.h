@@ -325,9 +325,10 @@ int pcg_u8_batch(const unsigned char* images, const long long* labels, const lon
  *   num_modifiable_patches < 0 or >= the patch count (trainer.py:59-61) - then nearest-upsampled to H x W
  *   (source index = floor(dst * patches / size), as F.interpolate(mode="nearest")) and repeated over the C channels;
  *   target[b] uniform in [0, num_classes) (target == NULL: not drawn).
- * Randomness: Philox4x32-10, key = seed, counter = (sample, draw, stream offset).  rng_state points at two device
- * uint64 {stream offset, 0}: the kernel uses the offset and advances it, so the launch may be replayed inside a CUDA
- * graph; NULL = offset 0 (deterministic, for tests).  Same distribution as the reference, not the same stream. */
+ * Randomness: Philox4x32-10, counter = (sample, draw, stream offset).  rng_state points at three device uint64
+ * {stream offset, 0, key}: the kernel uses key' = seed + key and the offset, and advances the offset, so the launch may
+ * be replayed inside a CUDA graph and re-seeded without re-capturing; NULL = key seed, offset 0 (deterministic, for
+ * tests).  Same distribution as the reference, not the same stream. */
 int pcg_build_mask(int B, int C, int H, int W, int patch, int num_modifiable_patches, int num_classes,
                    unsigned long long seed, unsigned long long* rng_state, float* mask, long long* target, void* stream);
 

@@ -541,6 +541,7 @@ __global__ void build_mask_kernel(int B, int C, int H, int W, int nph, int npw, 
   pdl_enter();
   __shared__ unsigned long long words[MASK_SPB];
   const unsigned long long offset = rng != nullptr ? rng[0] : 0ull;
+  if (rng != nullptr) seed += rng[2];                        // the key may live in device memory too (graph replays)
   const int b0 = blockIdx.x * MASK_SPB;
   const int total = nph * npw;
   if (threadIdx.x < MASK_SPB && b0 + (int)threadIdx.x < B) {

@@ -28,9 +28,11 @@ def grad_norm(parameters):
 
 
 class _Rng:
-    """Per-device Philox stream state of the native mask / target kernel: ``seed`` follows torch's global seed
-    (``torch.manual_seed`` restarts the stream, as it would restart the reference's draws), the device-side offset is
-    advanced by every launch, so a launch captured in a CUDA graph draws fresh numbers at every replay."""
+    """Per-device Philox state of the native mask / target kernel: three device uint64 {stream offset, ticket, key}.
+    The key follows torch's CUDA generator seed and ``torch.manual_seed`` restarts the stream (as it would restart the
+    reference's draws): a re-seed is recognised by the generator's seed changing or its offset falling back below the
+    mark this class left on it.  The state lives in device memory and is reset IN PLACE, so a launch captured in a CUDA
+    graph draws fresh numbers at every replay and follows a re-seed without being re-captured."""
     _states = {}
 
     @classmethod
@@ -38,16 +40,28 @@ class _Rng:
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        seed = torch.initial_seed()
+        seed, gen, off = torch.initial_seed(), None, 0
+        try:
+            gen = torch.cuda.default_generators[device.index]
+            seed, off = gen.initial_seed(), gen.get_offset()
+        except Exception:                                   # generator offsets unavailable: seed changes only
+            gen = None
         st = cls._states.get(device)
-        if st is None or st[0] != seed:
+        if st is None or st["seed"] != seed or off < st["mark"]:
             rank = 0
-            dist, world = _world()
+            dist, _ = _world()
             if dist is not None:
                 rank = dist.get_rank()                     # per-rank sub-streams
-            st = (seed, (seed + 0x9E3779B97F4A7C15 * rank) & (2 ** 63 - 1), torch.zeros(2, dtype=torch.int64, device=device))
-            cls._states[device] = st
-        return st[1], st[2]
+            key = (seed + 0x9E3779B97F4A7C15 * rank) & (2 ** 63 - 1)
+            if st is None:
+                st = cls._states[device] = {"state": torch.zeros(3, dtype=torch.int64, device=device)}
+            st["state"].copy_(torch.tensor([0, 0, key], dtype=torch.int64))
+            st["seed"] = seed
+            if gen is not None:
+                off = (off + 4) // 4 * 4
+                gen.set_offset(off)                         # leave a mark: manual_seed() puts the offset back to 0
+            st["mark"] = off
+        return 0, st["state"]
 
 
 def build_mask(x, patch_size, device, num_modifiable_patches=None):
@@ -198,9 +212,9 @@ class CounterGanTrainer:
             self.static[bs] = st
         st[0].copy_(x.reshape(bs, 1, 28, 28), non_blocking=True)
         st[1].copy_(y, non_blocking=True)
+        seed, state = _Rng.get(self.device)          # every step: a torch.manual_seed() since the last one resets the state
         g = self.graphs.get((bs, "auto"))
         if g is None:
-            seed, state = _Rng.get(self.device)
             cfg = self.cfg
 
             def draw():
