@@ -93,6 +93,15 @@ int pcg_conv_tc64_fprop_grid(int N, int H, int W);
 int pcg_conv_tc64_fprop(const void* in, int N, int H, int W, const void* wpk, const float* bias, int act,
                         float slope, const void* add_src, const void* act_ref, int ref_act, void* out,
                         float* stats, void* stream);
+/* The same kernel with the reduction pass of a train-mode BatchNorm backward fused into its epilogue
+ * (torch native_batch_norm_backward's two column sums; generator.py:12-15,22): v = conv(in) [+ add_src],
+ * g = bn_gscale * v * act'(bn_scale*y + bn_shift) with y = bn_y at the same pixel,
+ *   stats[cta][c] = sum g,  stats[cta][64 + c] = sum g * (y - bn_mean) * bn_rstd      (cta < pcg_conv_tc64_fprop_grid);
+ * out = v as bf16.  add_src together with bn_y needs H % 4 == 0 (row-class kernel: the skip-gradient tile arrives by TMA
+ * in the staging slot the result leaves from). */
+int pcg_conv_tc64_dgrad_bnred(const void* in, int N, int H, int W, const void* wpk, const void* add_src, const void* bn_y,
+                              const float* bn_mean, const float* bn_rstd, const float* bn_scale, const float* bn_shift,
+                              int bn_act, float bn_slope, float bn_gscale, void* out, float* stats, void* stream);
 int pcg_conv_tc64_wgrad(const void* x, const void* dy, int N, int H, int W, float* part, float* dw,
                         void* stream);
 int pcg_conv_tc64_set_variant(int v);

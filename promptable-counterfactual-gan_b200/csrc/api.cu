@@ -193,6 +193,17 @@ int pcg_conv_tc64_fprop(const void* in, int N, int H, int W, const void* wpk, co
   conv_tc64_fprop((const bf16*)in, N, H, W, (const bf16*)wpk, e, (bf16*)out, (cudaStream_t)stream);
   PCG_API_END
 }
+int pcg_conv_tc64_dgrad_bnred(const void* in, int N, int H, int W, const void* wpk, const void* add_src, const void* bn_y,
+                              const float* bn_mean, const float* bn_rstd, const float* bn_scale, const float* bn_shift,
+                              int bn_act, float bn_slope, float bn_gscale, void* out, float* stats, void* stream) {
+  PCG_API_BEGIN
+  ConvEpilogue e;
+  e.add_src = (const bf16*)add_src; e.stats = stats;
+  e.bn_y = (const bf16*)bn_y; e.bn_mean = bn_mean; e.bn_rstd = bn_rstd; e.bn_scale = bn_scale; e.bn_shift = bn_shift;
+  e.bn_act = bn_act; e.bn_slope = bn_slope; e.bn_gscale = bn_gscale;
+  conv_tc64_fprop((const bf16*)in, N, H, W, (const bf16*)wpk, e, (bf16*)out, (cudaStream_t)stream);
+  PCG_API_END
+}
 int pcg_conv_tc64_wgrad(const void* x, const void* dy, int N, int H, int W, float* part, float* dw, void* stream) {
   PCG_API_BEGIN
   conv_tc64_wgrad((const bf16*)x, (const bf16*)dy, N, H, W, part, (cudaStream_t)stream);

@@ -25,6 +25,8 @@ struct ConvEpilogue {
   const float *bn_mean = nullptr, *bn_rstd = nullptr, *bn_scale = nullptr, *bn_shift = nullptr;
   int bn_act = ACT_NONE;
   float bn_slope = 0.2f;
+  float bn_gscale = 1.f;         // the reduction is taken of bn_gscale * v (BN2 of a residual block: 0.1, generator.py:22)
+  // add_src may be combined with bn_y on the row-class kernel (H % 4 == 0): v = accumulator + add_src, reduced as above
 };
 
 // Number of CTAs conv_tc_fprop launches for a problem (rows of the `stats` partial buffer).

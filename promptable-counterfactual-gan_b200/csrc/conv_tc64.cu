@@ -52,6 +52,9 @@ struct F64Params {
   int n_extra;                                   // 1: one epilogue operand tile per output tile arrives by TMA
   int extra_is_add;                              // that operand is add_src (else act_ref)
   int bn_bwd;                                    // the operand is the BatchNorm input y: fused backward reduction
+  int dual;                                      // stacked kernel: bn_bwd AND a residual add; the residual tile arrives by TMA
+                                                 // in the staging slot its result leaves from (three in-place slots)
+  float bn_gscale;                               // the reduction is taken of bn_gscale * result
   const float *bn_mean, *bn_rstd, *bn_scale, *bn_shift;
   int bn_act;
   float bn_slope;
@@ -456,7 +459,10 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       const float nv = (float)nvalid;
       if (p.bn_bwd) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc_q[j] *= bnc[192 + col0 + j];      // sum g*(y - mean) -> sum g*xhat
+        for (int j = 0; j < 16; ++j) {
+          acc_q[j] *= bnc[192 + col0 + j] * p.bn_gscale;      // sum g*(y - mean) -> sum g*xhat
+          acc_s[j] *= p.bn_gscale;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -508,15 +514,20 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
-                        const F64Params p) {
+                        const __grid_constant__ CUtensorMap tmAdd, const F64Params p) {
   pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sw = smem;                                   // weights, slot s*3 + (2 - r)
   uint8_t* sin = smem + W_BYTES;                        // ring of class regions ((R+1) x (W+2) pixels each)
-  uint8_t* sout = sin + p.in_stages * p.in_stage_bytes; // output staging, 2 slots
-  uint8_t* sx = sout + 2 * p.out_tile_bytes;            // epilogue operand ring, 2 slots (if n_extra)
+  // Dual mode (fused BatchNorm-backward reduction AND a residual add: two epilogue operands): the residual tile is
+  // loaded by TMA straight into the staging slot its result will leave from - every thread reads its 32 bytes, adds,
+  // and writes the result back in place - so the slot ring (three deep) replaces a second operand ring that would not
+  // fit: load (afull) -> epilogue in place (sfull) -> TMA store -> read out (sempty) -> next load.
+  const int nst = p.dual ? 3 : 2;
+  uint8_t* sout = sin + p.in_stages * p.in_stage_bytes; // output staging, 2 slots (dual: 3 in-place slots)
+  uint8_t* sx = sout + nst * p.out_tile_bytes;          // epilogue operand ring, 2 slots (if n_extra)
   float* stats_smem = reinterpret_cast<float*>(sx + (p.n_extra ? 2 : 0) * p.out_tile_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + (16 * 2 * 16 + 64 + 4 * 64) * 4);
   uint64_t* full = bars;                 // [<= 8] ring of class regions
@@ -526,9 +537,10 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   uint64_t* tempty = tfull + 8;          // [2]
   uint64_t* xfull = tempty + 2;          // [2]
   uint64_t* xempty = xfull + 2;          // [2]
-  uint64_t* sfull = xempty + 2;          // [2] output staging slot written by all epilogue threads
-  uint64_t* sempty = sfull + 2;          // [2] ... and read out by its TMA store
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty + 2);
+  uint64_t* sfull = xempty + 2;          // [3] output staging slot written by all epilogue threads
+  uint64_t* sempty = sfull + 3;          // [3] ... and read out by its TMA store
+  uint64_t* afull = sempty + 3;          // [3] dual: residual tile landed in the staging slot
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(afull + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -537,13 +549,14 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmOut);
     if (p.n_extra) tma_prefetch_desc(&tmExtra);
+    if (p.dual) tma_prefetch_desc(&tmAdd);
     for (int s = 0; s < 8; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&tfull[s], 1); }
     mbar_init(wfull, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tempty[s], F_EPI_THREADS);
       mbar_init(&xfull[s], 1); mbar_init(&xempty[s], F_EPI_THREADS);
-      mbar_init(&sfull[s], F_EPI_THREADS); mbar_init(&sempty[s], 1);
     }
+    for (int s = 0; s < 3; ++s) { mbar_init(&sfull[s], F_EPI_THREADS); mbar_init(&sempty[s], 1); mbar_init(&afull[s], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -588,12 +601,19 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
   } else if (warp == F_EPI_WARP0 + F_EPI_WARPS) {
     if (lane == 0 && p.n_extra) {
-      int sub = 0;
+      int sub = 0, s3 = 0;
+      uint32_t s3use = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
         for (int c = 0; c < 4; ++c, ++sub) {
           const int co = c < 2 ? 1 - c : c;                        // the epilogue's class order 1, 0, 2, 3
           const int slot = sub & 1;
+          if (p.dual) {                                            // residual tile into the next free in-place slot
+            mbar_wait(&sempty[s3], (s3use & 1u) ^ 1u);
+            mbar_expect_tx(&afull[s3], tile_bytes);
+            tma_load_5d(&tmAdd, &afull[s3], sout + s3 * p.out_tile_bytes, 0, 0, co, i0, n);
+            if (++s3 == 3) { s3 = 0; ++s3use; }
+          }
           mbar_wait(&xempty[slot], ((sub >> 1) & 1) ^ 1);
           mbar_expect_tx(&xfull[slot], tile_bytes);
           tma_load_5d(&tmExtra, &xfull[slot], sx + slot * p.out_tile_bytes, 0, 0, co, i0, n);
@@ -605,19 +625,21 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     // slot, fences and arrives on sfull, this thread sends the slot off and hands it back through sempty once the
     // TMA engine has read it, so the sixteen epilogue warps drift apart and hide each other's latencies.
     if (lane == 0 && !(p.variant & 2)) {
-      int sub = 0;
+      int sub = 0, slot = 0, prev = 0;                // slot = sub % nst, use = sub / nst
+      uint32_t use = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
         for (int c = 0; c < 4; ++c, ++sub) {
           const int co = c < 2 ? 1 - c : c;
-          const int slot = sub & 1;
-          mbar_wait(&sfull[slot], (sub >> 1) & 1);
+          mbar_wait(&sfull[slot], use & 1u);
           tma_store_5d(&tmOut, sout + slot * p.out_tile_bytes, 0, 0, co, i0, n);
           tma_store_commit();
           if (sub >= 1) {
             tma_store_wait_read<1>();                 // the previous store has read its slot
-            mbar_arrive(&sempty[slot ^ 1]);
+            mbar_arrive(&sempty[prev]);
           }
+          prev = slot;
+          if (++slot == nst) { slot = 0; ++use; }
         }
       }
       tma_store_wait<0>();
@@ -730,8 +752,8 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     const bf16* g_ref = (p.n_extra && !p.extra_is_add && !p.bn_bwd) ? nullptr : p.act_ref;
     const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
     const int nidx = p.H >> 2;                      // rows per class
-    int acc = 0, sub = 0;
-    uint32_t acc_phase = 0;
+    int acc = 0, sub = 0, sslot = 0;                // sslot = sub % nst: staging slot
+    uint32_t acc_phase = 0, suse = 0;               // suse = sub / nst
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
       const bool valid = row_ok && (i0 + hh) < nidx;
@@ -748,7 +770,10 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           tc_fence_before();
           mbar_arrive(&tempty[acc]);                // the last block is in registers: release the accumulator
         }
-        if (p.variant & 2) continue;                // experiment: no epilogue work
+        if (p.variant & 2) {                        // experiment: no epilogue work
+          if (++sslot == nst) { sslot = 0; ++suse; }
+          continue;
+        }
         float v[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
@@ -764,6 +789,23 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         } else if (p.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.dual) {
+          // the residual tile sits in the staging slot this pass will write its result to
+          mbar_wait(&afull[sslot], suse & 1u);
+          if (valid) {
+            const uint8_t* at = sout + sslot * p.out_tile_bytes;
+#pragma unroll
+            for (int j2 = 0; j2 < 2; ++j2) {
+              const uint4 u = *reinterpret_cast<const uint4*>(at + soff[j2]);
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[j2 * 8 + t * 2] += __uint_as_float(w4[t] << 16);
+                v[j2 * 8 + t * 2 + 1] += __uint_as_float(w4[t] & 0xffff0000u);
+              }
+            }
+          }
         }
         if (p.n_extra) {
           mbar_wait(&xfull[slot], (sub >> 1) & 1);
@@ -842,10 +884,10 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             }
           }
         }
-        // staging slot `slot` was last read by the TMA store issued two passes ago
-        mbar_wait(&sempty[slot], ((sub >> 1) & 1) ^ 1);
+        // staging slot: last read by the TMA store issued two passes ago (dual: already owned, the residual came in it)
+        if (!p.dual) mbar_wait(&sempty[sslot], (suse & 1u) ^ 1u);
         if (valid) {
-          uint8_t* st = sout + slot * p.out_tile_bytes;
+          uint8_t* st = sout + sslot * p.out_tile_bytes;
 #pragma unroll
           for (int j2 = 0; j2 < 2; ++j2) {
             uint4 u;
@@ -866,7 +908,8 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           }
         }
         fence_proxy_async();
-        mbar_arrive(&sfull[slot]);
+        mbar_arrive(&sfull[sslot]);
+        if (++sslot == nst) { sslot = 0; ++suse; }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -875,7 +918,10 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const float nv = (float)nvalid;
       if (p.bn_bwd) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc_q[j] *= bnc[192 + col0 + j];
+        for (int j = 0; j < 16; ++j) {
+          acc_q[j] *= bnc[192 + col0 + j] * p.bn_gscale;
+          acc_s[j] *= p.bn_gscale;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -937,12 +983,17 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
   p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
   p.stats = epi.stats; p.variant = g_variant;
-  PCG_REQUIRE(epi.stats == nullptr || (epi.act == ACT_NONE && epi.add_src == nullptr && p.act_ref == nullptr),
+  PCG_REQUIRE(epi.stats == nullptr || epi.bn_y != nullptr ||
+                  (epi.act == ACT_NONE && epi.add_src == nullptr && p.act_ref == nullptr),
               "BatchNorm statistics are taken of (accumulator + bias) only");
   p.bn_bwd = epi.bn_y != nullptr ? 1 : 0;
+  p.bn_gscale = epi.bn_gscale;
+  const bool stacked = use_stacked(H, W);
+  p.dual = (p.bn_bwd && p.add_src != nullptr) ? 1 : 0;
+  PCG_REQUIRE(!p.dual || stacked, "reduction + residual in one epilogue needs the row-class kernel (H % 4 == 0)");
   p.bn_mean = epi.bn_mean; p.bn_rstd = epi.bn_rstd; p.bn_scale = epi.bn_scale; p.bn_shift = epi.bn_shift;
   p.bn_act = epi.bn_act; p.bn_slope = epi.bn_slope;
-  PCG_REQUIRE(!p.bn_bwd || (epi.stats != nullptr && epi.bias == nullptr && epi.act == ACT_NONE && p.add_src == nullptr &&
+  PCG_REQUIRE(!p.bn_bwd || (epi.stats != nullptr && epi.bias == nullptr && epi.act == ACT_NONE &&
                             p.act_ref == nullptr && epi.bn_mean && epi.bn_rstd && epi.bn_scale && epi.bn_shift),
               "fused BatchNorm-backward reduction: partial buffer and the four per-channel vectors are required");
   // one epilogue operand travels by TMA (the BatchNorm input, else the residual if there is one, else the activation
@@ -951,7 +1002,8 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.extra_is_add = (!p.bn_bwd && p.add_src != nullptr) ? 1 : 0;
   const bf16* extra = p.bn_bwd ? epi.bn_y : (p.add_src != nullptr ? p.add_src : p.act_ref);
   auto round1k = [](int b) { return (b + 1023) / 1024 * 1024; };
-  const bool stacked = use_stacked(H, W);
+  const bf16* add_tma = p.dual ? p.add_src : nullptr;
+  if (p.dual) p.add_src = nullptr;                 // the kernel takes it from the staging slot, never from global
   if (stacked) {                                   // a tile is a super-tile: R rows of each of the four row classes
     p.tiles_per_img = (H / 4 + p.R - 1) / p.R;
     p.total_tiles = N * p.tiles_per_img;
@@ -961,7 +1013,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.out_tile_bytes = round1k(p.R * p.W * 128);
   p.in_stages = stacked ? 5 : 4;
   auto total = [&]() {
-    return 1024 + W_BYTES + p.in_stages * p.in_stage_bytes + (2 + 2 * p.n_extra) * p.out_tile_bytes + F_TAIL_BYTES;
+    return 1024 + W_BYTES + p.in_stages * p.in_stage_bytes + ((p.dual ? 3 : 2) + 2 * p.n_extra) * p.out_tile_bytes + F_TAIL_BYTES;
   };
   while (total() > SMEM_LIMIT && p.in_stages > 2) --p.in_stages;
   PCG_REQUIRE(total() <= SMEM_LIMIT, "halo-tile kernel: shared-memory budget exceeded");
@@ -977,7 +1029,9 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     CUtensorMap tmX = make_tmap_nhwc_rowclass(in, N, H, W, 64, p.WP, p.R + 1);
     CUtensorMap tmOut = make_tmap_nhwc_rowclass(out, N, H, W, 64, W, p.R);
     CUtensorMap tmExtra = make_tmap_nhwc_rowclass(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
-    launch_k(conv_tc64s_fprop_kernel, dim3(conv_tc64_fprop_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra, p);
+    CUtensorMap tmAdd = make_tmap_nhwc_rowclass(add_tma != nullptr ? add_tma : out, N, H, W, 64, W, p.R);
+    launch_k(conv_tc64s_fprop_kernel, dim3(conv_tc64_fprop_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra,
+             tmAdd, p);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
     return;

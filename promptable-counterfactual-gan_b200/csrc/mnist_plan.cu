@@ -266,7 +266,8 @@ struct MnistPlan : PlanBase {
   float *clogits, *cdlogits, *dxc;
   T *cdf1, *cd3, *cd2, *cd1;
   // scratch
-  float *stat_part, *stat_part2, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp, *small_part;
+  float *stat_part, *stat_part2, *stat_bn2 = nullptr, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp, *small_part;
+  bool fuse_bn2_reduce = true;
   size_t wg_scratch_elems = 0;
 
   template <typename U>
@@ -464,6 +465,11 @@ struct MnistPlan : PlanBase {
     PCG_REQUIRE(sm_count() <= STAT_PARTS, "more SMs than partial-row slots (STAT_PARTS)");
     tc_part = kBf16 ? alloc<float>((size_t)sm_count() * 9 * 64 * 64) : nullptr;   // one weight-gradient partial per CTA (grid <= SMs)
     l1_part = alloc<float>(STAT_PARTS * 2);
+    stat_bn2 = alloc<float>((size_t)STAT_PARTS * 2 * maxC);
+    {
+      const char* e = getenv("PCG_FUSE_BN2");      // A/B switch: 0 = separate bn_bwd_partial pass (round-1 schedule)
+      fuse_bn2_reduce = !(e && atoi(e) == 0);
+    }
     small_part = alloc<float>((size_t)sm_count() * 2048);
     scal_tmp = alloc<float>(16);
     dbg["dinp"] = {dinp, {MG * 3, PCG_F32}};
@@ -863,7 +869,28 @@ struct MnistPlan : PlanBase {
     bias_grad(g_hm, MG, ch, g_mid.db, s);
     T* dh = dhA;
     T* dh_other = dhB;
-    {
+    // The reduction pass of BN2's backward (sum g, sum g*xhat over g = 0.1*dh, generator.py:22) rides in the epilogue of
+    // the tensor-core kernel that PRODUCES dh - conv_mid's data gradient for the last block, conv1's data gradient of
+    // block i+1 (which also adds the skip gradient) for block i - instead of re-reading dh and y2 in a separate pass.
+    int bn2_parts = 0;
+    auto dgrad_bn2 = [&](const ConvLayer<T>& L, const T* dout, const T* add, int blk, T* din) -> bool {
+      if constexpr (kBf16) {
+        if (L.tc_dgrad && L.tc64 && fuse_bn2_reduce) {
+          ProfTag _tag("g.res.dgrad_bnred");
+          const BN& qb = bn2[blk];
+          ConvEpilogue c;
+          c.add_src = add;
+          c.stats = stat_bn2;
+          c.bn_y = y2[blk]; c.bn_mean = qb.mean; c.bn_rstd = qb.rstd; c.bn_scale = qb.scale; c.bn_shift = qb.shift;
+          c.bn_act = ACT_NONE; c.bn_gscale = 0.1f;
+          conv_tc64_fprop(dout, B, 28, 28, L.tcd, c, din, s);
+          bn2_parts = conv_tc64_fprop_grid(B, 28, 28);
+          return true;
+        }
+      }
+      return false;
+    };
+    if (!dgrad_bn2(g_mid, g_hm, nullptr, nres - 1, dh)) {
       GenEpilogue<T> e;
       dgrad<T, T>(g_mid, g_hm, e, dh, s);
     }
@@ -872,8 +899,13 @@ struct MnistPlan : PlanBase {
     for (int i = nres - 1; i >= 0; --i) {
       // BN2 backward: upstream = 0.1 * dh (generator.py:22)
       const BN& q2 = bn2[i];
-      bn_bwd_partial<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, 0.1f, ACT_NONE, 0.f, MG, ch, stat_part, s);
-      bn_bwd_finalize(stat_part, STAT_PARTS, MG, ch, q2.dgamma, q2.dbeta, c12, s);
+      if (bn2_parts > 0) {
+        bn_bwd_finalize(stat_bn2, bn2_parts, MG, ch, q2.dgamma, q2.dbeta, c12, s);
+        bn2_parts = 0;
+      } else {
+        bn_bwd_partial<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, 0.1f, ACT_NONE, 0.f, MG, ch, stat_part, s);
+        bn_bwd_finalize(stat_part, STAT_PARTS, MG, ch, q2.dgamma, q2.dbeta, c12, s);
+      }
       bn_bwd_apply<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, q2.gamma, c12, 0.1f, ACT_NONE, 0.f, MG, ch, dy2[i],
                       stat_part2, s);
       colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c2[i].db, s);
@@ -910,7 +942,7 @@ struct MnistPlan : PlanBase {
       bn_bwd_apply<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, q1.gamma, c12, 1.f, ACT_LRELU, 0.2f, MG, ch,
                       dy1[i], stat_part2, s);
       colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c1[i].db, s);
-      {
+      if (i == 0 || !dgrad_bn2(g_c1[i], dy1[i], dh, i - 1, dh_other)) {
         GenEpilogue<T> e; e.add_src = dh;
         if (i == 0) { e.act_ref = h[0]; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f; }
         dgrad<T, T>(g_c1[i], dy1[i], e, dh_other, s);

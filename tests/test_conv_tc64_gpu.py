@@ -92,6 +92,44 @@ def test_fprop_bias_stats_and_epilogues(N, HW, variant):
         L.pcg_conv_tc64_set_variant(0)
 
 
+@pytest.mark.parametrize("with_add", [False, True])
+@pytest.mark.parametrize("N,HW", [(3, 28), (8, 28), (301, 28), (5, 12)])
+def test_dgrad_with_fused_batchnorm_backward_reduction(N, HW, with_add):
+    """Data gradient whose epilogue also takes the two column sums of the BatchNorm backward that consumes it, with and
+    without the skip-connection gradient added first (two epilogue operands: the in-place staging ring).  Reference:
+    plain torch fp32 on the same bf16 operands; the sums are taken of the fp32 result before its bf16 rounding."""
+    L, P, st, check = _env()
+    torch.manual_seed(N * 7 + HW + int(with_add))
+    dy = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda") * 0.1)
+    y = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda") * 1.5 + 0.3)
+    add = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda") * 0.2) if with_add else None
+    w = torch.randn(64, 64, 3, 3, device="cuda") * (2.0 / 576) ** 0.5
+    _, wd = pack(L, P, st, check, w)
+    wb = w.to(torch.bfloat16).float()
+    mean, var = torch.randn(64, device="cuda") * 0.2, torch.rand(64, device="cuda") + 0.5
+    rstd = (var + 1e-5).rsqrt()
+    gamma, beta = torch.randn(64, device="cuda"), torch.randn(64, device="cuda") * 0.3
+    scale, shift = gamma * rstd, beta - mean * gamma * rstd
+    rows = L.pcg_conv_tc64_fprop_grid(N, HW, HW)
+    for act, gscale in ((1, 1.0), (0, 0.1)):          # BN1 (LeakyReLU in front of it in the backward) / BN2 (0.1 * dh)
+        out = torch.full((N, HW, HW, 64), 3.0, dtype=torch.bfloat16, device="cuda")
+        stats = torch.full((rows, 128), 1e9, device="cuda")
+        check(L.pcg_conv_tc64_dgrad_bnred(P(dy), N, HW, HW, P(wd), P(add), P(y), P(mean), P(rstd), P(scale), P(shift), act,
+                                          _f(0.2), _f(gscale), P(out), P(stats), st))
+        torch.cuda.synchronize()
+        v = F.conv_transpose2d(nchw(dy), wb, None, padding=1)
+        if with_add:
+            v = v + nchw(add)
+        assert rel(nchw(out), v) < 1e-2
+        yn = nchw(y).double()
+        pre = yn * scale.double().view(1, 64, 1, 1) + shift.double().view(1, 64, 1, 1)
+        g = v.double() * gscale * (torch.where(pre > 0, 1.0, 0.2) if act == 1 else 1.0)
+        xhat = (yn - mean.double().view(1, 64, 1, 1)) * rstd.double().view(1, 64, 1, 1)
+        s = stats.double().sum(0)
+        assert rel(s[:64], g.sum(dim=(0, 2, 3))) < 2e-3, (act, rel(s[:64], g.sum(dim=(0, 2, 3))))
+        assert rel(s[64:], (g * xhat).sum(dim=(0, 2, 3))) < 2e-3, (act, rel(s[64:], (g * xhat).sum(dim=(0, 2, 3))))
+
+
 def test_stacked_and_one_class_kernels_agree():
     """Same products, same fp32 accumulation per output element up to the order of the nine taps: the two kernels
     must agree to bf16 rounding of identical fp32 sums almost everywhere (<= 1 bf16 ulp)."""
