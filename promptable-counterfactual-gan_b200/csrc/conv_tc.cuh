@@ -6,6 +6,25 @@
 
 namespace pcg {
 
+// Finalisation of the per-CTA `stats` partial rows, run by the LAST CTA of conv_tc64_fprop to finish (an atomic ticket
+// after its row is written and fenced) instead of by a separate one-block-per-channel launch: the rows are summed per
+// column in CTA order in fp64 (deterministic), then
+//   mode 1 (train-mode BatchNorm forward: rows = sum y, sum y^2): mean, rstd, scale = gamma*rstd, shift = beta - mean*scale,
+//           running_mean / running_var (momentum, unbiased variance) and num_batches_tracked, as bn_finalize;
+//   mode 2 (BatchNorm backward: rows = sum g, sum g*xhat): dbeta, dgamma, c12 = (sum g / M, sum g*xhat / M), as
+//           bn_bwd_finalize.
+struct StatsFinalize {
+  int mode = 0;
+  unsigned int* counter = nullptr;   // device, zero before the first use; the last CTA resets it
+  long long M = 0;                   // elements per channel
+  const float *gamma = nullptr, *beta = nullptr;
+  float eps = 1e-5f, momentum = 0.1f;
+  float *running_mean = nullptr, *running_var = nullptr;
+  long long* nbt = nullptr;
+  float *mean = nullptr, *rstd = nullptr, *scale = nullptr, *shift = nullptr;
+  float *dgamma = nullptr, *dbeta = nullptr, *c12 = nullptr;
+};
+
 // Epilogue description shared by the fprop/dgrad implicit-GEMM kernel.
 struct ConvEpilogue {
   const float* bias = nullptr;   // [Cout] fp32, added before activation
@@ -25,6 +44,7 @@ struct ConvEpilogue {
   const float *bn_mean = nullptr, *bn_rstd = nullptr, *bn_scale = nullptr, *bn_shift = nullptr;
   int bn_act = ACT_NONE;
   float bn_slope = 0.2f;
+  StatsFinalize fin;             // conv_tc64_fprop only: finish the statistics in the same launch (mode 0: off)
   float bn_gscale = 1.f;         // the reduction is taken of bn_gscale * v (BN2 of a residual block: 0.1, generator.py:22)
   // add_src may be combined with bn_y on the row-class kernel (H % 4 == 0): v = accumulator + add_src, reduced as above
 };

@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "conv_tc.cuh"
+#include "elementwise.cuh"
 #include "tc_common.cuh"
 
 namespace pcg {
@@ -66,8 +67,58 @@ struct F64Params {
   int ref_act;
   float ref_slope;
   float* stats;
+  StatsFinalize fin;
   int variant;
 };
+
+// Runs in the epilogue warps (512 threads, named barrier 1) of the last CTA to finish: see StatsFinalize.
+__device__ __forceinline__ void finalize_stats_last_cta(const StatsFinalize& f, const float* __restrict__ stats, int nrows,
+                                                        double* red /* [4][128] shared */, int t) {
+  {
+    // 512 threads: column (t & 127) of [nrows][128] (first sums in columns 0-63, second sums in 64-127), rows
+    // part, part + 4, ... with part = t >> 7; all loads of a thread are independent (L2 round trips overlap)
+    const float* col = stats + (t & 127);
+    const int part = t >> 7;
+    float v[10];
+    double a = 0.0;
+    for (int i0 = part; i0 < nrows; i0 += 40) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] = (i0 + 4 * k) < nrows ? __ldcg(col + (size_t)(i0 + 4 * k) * 128) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) a += (double)v[k];
+    }
+    red[part * 128 + (t & 127)] = a;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+  if (t < 64) {
+    const int c = t;
+    const double s1 = (red[c] + red[128 + c]) + (red[256 + c] + red[384 + c]);
+    const double s2 = (red[64 + c] + red[192 + c]) + (red[320 + c] + red[448 + c]);
+    const double M = (double)f.M;
+    if (f.mode == 1) {
+      const double mean = s1 / M;
+      double var = s2 / M - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)f.eps));
+      const float a = f.gamma[c] * rstd;
+      f.mean[c] = (float)mean;
+      f.rstd[c] = rstd;
+      f.scale[c] = a;
+      f.shift[c] = f.beta[c] - (float)mean * a;
+      if (f.running_mean != nullptr) {
+        const double unbiased = f.M > 1 ? var * (M / (M - 1.0)) : var;
+        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * (float)mean;
+        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+      }
+      if (c == 0 && f.nbt != nullptr) *f.nbt += 1;
+    } else {
+      f.dbeta[c] = (float)s1;
+      f.dgamma[c] = (float)s2;
+      f.c12[c] = (float)(s1 / M);
+      f.c12[64 + c] = (float)(s2 / M);
+    }
+  }
+}
 
 bool conv_tc64_supported(int H, int W) {
   const int WP = W + 2;
@@ -946,6 +997,22 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         for (int qq = 0; qq < 4; ++qq) s += stats_smem[(((c4 * 4 + qq) * 2) + which) * 16 + l];
         p.stats[(size_t)blockIdx.x * 128 + which * 64 + col] = s;
       }
+      if (p.fin.mode != 0) {
+        // the last CTA to get here finishes the statistics (fixed CTA order: deterministic)
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+        uint32_t* flag = reinterpret_cast<uint32_t*>(stats_smem);       // the partial sums in stats_smem are consumed
+        if (t == 0) *flag = atomicAdd(p.fin.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+        asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+        const bool last = *flag != 0u;
+        asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+        if (last) {
+          __threadfence();
+          // scratch: the input ring (every MMA of this CTA has completed, nothing reads it any more)
+          finalize_stats_last_cta(p.fin, p.stats, (int)gridDim.x, reinterpret_cast<double*>(sin), t);
+          if (t == 0) *p.fin.counter = 0u;
+        }
+      }
     }
   }
 
@@ -983,6 +1050,9 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
   p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
   p.stats = epi.stats; p.variant = g_variant;
+  p.fin = epi.fin;
+  PCG_REQUIRE(p.fin.mode == 0 || (epi.stats != nullptr && p.fin.counter != nullptr && p.fin.M > 0),
+              "statistics finalisation needs the partial buffer, a ticket counter and the element count");
   PCG_REQUIRE(epi.stats == nullptr || epi.bn_y != nullptr ||
                   (epi.act == ACT_NONE && epi.add_src == nullptr && p.act_ref == nullptr),
               "BatchNorm statistics are taken of (accumulator + bias) only");
@@ -1036,12 +1106,19 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     PCG_LAUNCH_CHECK();
     return;
   }
+  const StatsFinalize fin = p.fin;                 // the one-class kernel leaves the finalisation to a second launch
+  p.fin.mode = 0;
   CUtensorMap tmX = make_tmap_nhwc_box(in, N, H, W, 64, p.WP, p.R + 2);
   CUtensorMap tmOut = make_tmap_nhwc_box(out, N, H, W, 64, W, p.R);
   CUtensorMap tmExtra = make_tmap_nhwc_box(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
   launch_k(conv_tc64_fprop_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra, p);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
+  if (fin.mode == 1)
+    bn_finalize(p.stats, conv_tc64_grid(N, H, W), fin.M, 64, fin.gamma, fin.beta, fin.eps, fin.momentum, fin.running_mean,
+                fin.running_var, fin.nbt, fin.mean, fin.rstd, fin.scale, fin.shift, stream);
+  else if (fin.mode == 2)
+    bn_bwd_finalize(p.stats, conv_tc64_grid(N, H, W), fin.M, 64, fin.dgamma, fin.dbeta, fin.c12, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -267,7 +267,8 @@ struct MnistPlan : PlanBase {
   T *cdf1, *cd3, *cd2, *cd1;
   // scratch
   float *stat_part, *stat_part2, *stat_bn2 = nullptr, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp, *small_part;
-  bool fuse_bn2_reduce = true;
+  bool fuse_bn2_reduce = true, fuse_finalize = false;
+  unsigned int* fin_counter = nullptr;
   size_t wg_scratch_elems = 0;
 
   template <typename U>
@@ -466,6 +467,11 @@ struct MnistPlan : PlanBase {
     tc_part = kBf16 ? alloc<float>((size_t)sm_count() * 9 * 64 * 64) : nullptr;   // one weight-gradient partial per CTA (grid <= SMs)
     l1_part = alloc<float>(STAT_PARTS * 2);
     stat_bn2 = alloc<float>((size_t)STAT_PARTS * 2 * maxC);
+    fin_counter = alloc<unsigned int>(4);
+    {
+      const char* e = getenv("PCG_FUSE_FINALIZE");  // A/B switch: 1 = the last CTA of the convolution finishes the statistics
+      fuse_finalize = e && atoi(e) == 1;       // default OFF: measured slower (negative results)
+    }
     {
       const char* e = getenv("PCG_FUSE_BN2");      // A/B switch: 0 = separate bn_bwd_partial pass (round-1 schedule)
       fuse_bn2_reduce = !(e && atoi(e) == 0);
@@ -733,17 +739,32 @@ struct MnistPlan : PlanBase {
     GenEpilogue<T> e;
     e.bias = g_in.b; e.act = ACT_LRELU; e.slope = 0.2f;
     fprop<T, T>(g_in, inp3, e, h[0], s);
-    for (int i = 0; i < nres; ++i) {
+    // convolution + the statistics of the BatchNorm behind it; on the tensor-core path the last CTA of the convolution
+    // also finishes them (mean, rstd, scale, shift, running buffers), which removes a launch from the serial chain
+    auto conv_bn = [&](const ConvLayer<T>& L, const T* in, T* out, const BN& q) {
+      if constexpr (kBf16) {
+        if (training && L.tc_fprop && L.tc64 && fuse_finalize) {
+          ProfTag _tag(L.tag_f.c_str());
+          ConvEpilogue c;
+          c.bias = L.b; c.stats = stat_part;
+          c.fin.mode = 1; c.fin.counter = fin_counter; c.fin.M = MG;
+          c.fin.gamma = q.gamma; c.fin.beta = q.beta; c.fin.eps = 1e-5f; c.fin.momentum = 0.1f;
+          c.fin.running_mean = q.running_mean; c.fin.running_var = q.running_var; c.fin.nbt = q.nbt;
+          c.fin.mean = q.mean; c.fin.rstd = q.rstd; c.fin.scale = q.scale; c.fin.shift = q.shift;
+          conv_tc64_fprop(in, B, L.g.H, L.g.W, L.tcf, c, out, s);
+          return;
+        }
+      }
       int np = 0;
-      GenEpilogue<T> e1; e1.bias = g_c1[i].b;
-      if (training) fprop<T, T>(g_c1[i], h[i], e1, y1[i], s, stat_part, &np);
-      else fprop<T, T>(g_c1[i], h[i], e1, y1[i], s);
-      bn_coeffs(bn1[i], stat_part, np, training, s);
+      GenEpilogue<T> e; e.bias = L.b;
+      if (training) fprop<T, T>(L, in, e, out, s, stat_part, &np);
+      else fprop<T, T>(L, in, e, out, s);
+      bn_coeffs(q, stat_part, np, training, s);
+    };
+    for (int i = 0; i < nres; ++i) {
+      conv_bn(g_c1[i], h[i], y1[i], bn1[i]);
       bn_apply_act<T>(y1[i], bn1[i].scale, bn1[i].shift, MG, ch, ACT_LRELU, 0.2f, z1[i], s);
-      GenEpilogue<T> e2; e2.bias = g_c2[i].b;
-      if (training) fprop<T, T>(g_c2[i], z1[i], e2, y2[i], s, stat_part, &np);
-      else fprop<T, T>(g_c2[i], z1[i], e2, y2[i], s);
-      bn_coeffs(bn2[i], stat_part, np, training, s);
+      conv_bn(g_c2[i], z1[i], y2[i], bn2[i]);
       bn_apply_residual<T>(y2[i], h[i], bn2[i].scale, bn2[i].shift, 0.1f, MG, ch, h[i + 1], s);
     }
     GenEpilogue<T> em; em.bias = g_mid.b; em.act = ACT_LRELU; em.slope = 0.2f;
@@ -883,6 +904,10 @@ struct MnistPlan : PlanBase {
           c.stats = stat_bn2;
           c.bn_y = y2[blk]; c.bn_mean = qb.mean; c.bn_rstd = qb.rstd; c.bn_scale = qb.scale; c.bn_shift = qb.shift;
           c.bn_act = ACT_NONE; c.bn_gscale = 0.1f;
+          if (fuse_finalize) {
+            c.fin.mode = 2; c.fin.counter = fin_counter; c.fin.M = MG;
+            c.fin.dgamma = qb.dgamma; c.fin.dbeta = qb.dbeta; c.fin.c12 = c12;
+          }
           conv_tc64_fprop(dout, B, 28, 28, L.tcd, c, din, s);
           bn2_parts = conv_tc64_fprop_grid(B, 28, 28);
           return true;
@@ -900,7 +925,8 @@ struct MnistPlan : PlanBase {
       // BN2 backward: upstream = 0.1 * dh (generator.py:22)
       const BN& q2 = bn2[i];
       if (bn2_parts > 0) {
-        bn_bwd_finalize(stat_bn2, bn2_parts, MG, ch, q2.dgamma, q2.dbeta, c12, s);
+        // c12 still holds this block's BN2 sums: the fused launch finished them, and nothing ran in between
+        if (!fuse_finalize) bn_bwd_finalize(stat_bn2, bn2_parts, MG, ch, q2.dgamma, q2.dbeta, c12, s);
         bn2_parts = 0;
       } else {
         bn_bwd_partial<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, 0.1f, ACT_NONE, 0.f, MG, ch, stat_part, s);
@@ -912,6 +938,7 @@ struct MnistPlan : PlanBase {
       // data gradient of conv2; on the tensor-core path its epilogue also does the reduction pass of BN1's backward
       // (sum g, sum g*xhat with g = dz1 * LReLU'(BN1(y1))), which saves one full read of dz1 and y1
       int bn1_parts = 0;
+      bool bn1_fin_done = false;
       if constexpr (kBf16) {
         if (g_c2[i].tc_dgrad && g_c2[i].tc64) {
           ProfTag _tag("g.res.dgrad_bnred");
@@ -920,6 +947,11 @@ struct MnistPlan : PlanBase {
           c.stats = stat_part;
           c.bn_y = y1[i]; c.bn_mean = qb.mean; c.bn_rstd = qb.rstd; c.bn_scale = qb.scale; c.bn_shift = qb.shift;
           c.bn_act = ACT_LRELU; c.bn_slope = 0.2f;
+          if (fuse_finalize) {
+            c.fin.mode = 2; c.fin.counter = fin_counter; c.fin.M = MG;
+            c.fin.dgamma = qb.dgamma; c.fin.dbeta = qb.dbeta; c.fin.c12 = c12;
+            bn1_fin_done = true;
+          }
           conv_tc64_fprop(dy2[i], B, 28, 28, g_c2[i].tcd, c, dz1, s);
           bn1_parts = conv_tc64_fprop_grid(B, 28, 28);
         }
@@ -938,7 +970,7 @@ struct MnistPlan : PlanBase {
         bn_bwd_partial<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, 1.f, ACT_LRELU, 0.2f, MG, ch, stat_part, s);
         bn1_parts = STAT_PARTS;
       }
-      bn_bwd_finalize(stat_part, bn1_parts, MG, ch, q1.dgamma, q1.dbeta, c12, s);
+      if (!bn1_fin_done) bn_bwd_finalize(stat_part, bn1_parts, MG, ch, q1.dgamma, q1.dbeta, c12, s);
       bn_bwd_apply<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, q1.gamma, c12, 1.f, ACT_LRELU, 0.2f, MG, ch,
                       dy1[i], stat_part2, s);
       colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c1[i].db, s);
