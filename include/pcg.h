@@ -250,6 +250,10 @@ int pcg_pack_conv_weights(const float* w /*torch OIHW*/, int Cout, int Cin, int 
  * Scratch is sized by the first (eager) call, so run one un-captured pass before CUDA-graph capture. */
 int pcg_set_conv_tensor_cores(int on);
 int pcg_get_conv_tensor_cores(void);
+/* Operand precision of that mode: 3 (default) = bf16x3, every fp32 product emulated as hi*hi + lo*hi + hi*lo (fp32-level
+ * results, 3x the tensor work); 1 = plain bf16 operands with fp32 accumulation (what torch autocast runs).  Returns the
+ * previous setting. */
+int pcg_set_conv_tensor_core_terms(int terms);
 long long pcg_stat_scratch_floats(int C);
 int pcg_colsum(const float* a, long long M, int C, float* scratch, float* out, void* stream);
 /* nn.BatchNorm{1,2}d in train mode over M rows x C channels (+ fused activation), and its backward

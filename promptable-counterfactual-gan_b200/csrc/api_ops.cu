@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "conv_auto.cuh"
+#include "conv_c1k4.cuh"
 #include "conv_generic.cuh"
 #include "elementwise.cuh"
 #include "ops.cuh"
@@ -35,6 +36,14 @@ int pcg_conv_fprop(const float* in, int N, int H, int W, int Cin, const float* w
   PCG_API_BEGIN
   GenEpilogue<float> e;
   e.bias = bias; e.act = act; e.slope = slope; e.add_src = add_src;
+  if (bias == nullptr && add_src == nullptr && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+    c1k4_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, act, slope, out, ST);
+    return 0;
+  }
+  if (act == ACT_NONE && add_src == nullptr && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+    full1_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, bias, out, ST);
+    return 0;
+  }
   if (conv_fprop_auto(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, e, out, ST)) return 0;
   conv_fprop_generic<float, float>(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, e, out, ST);
   PCG_API_END
@@ -44,16 +53,36 @@ int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float*
   PCG_API_BEGIN
   GenEpilogue<float> e;
   e.add_src = add_src; e.act_ref = act_ref; e.ref_act = ref_act; e.ref_slope = ref_slope;
+  if (add_src == nullptr && (act_ref == nullptr || ref_act == ACT_NONE) &&
+      c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+    c1k4_dgrad(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, din, ST);
+    return 0;
+  }
+  if (add_src == nullptr && (act_ref == nullptr || ref_act == ACT_NONE) && Cin % 4 == 0 &&
+      full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+    full1_dgrad(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, din, ST);
+    return 0;
+  }
   if (conv_dgrad_auto(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, e, din, ST)) return 0;
   conv_dgrad_generic<float, float>(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, e, din, ST);
   PCG_API_END
 }
 long long pcg_conv_wgrad_scratch(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
-  return (long long)conv_wgrad_generic_scratch(geom(N, H, W, Cin, Cout, k, stride, pad));
+  const size_t generic = conv_wgrad_generic_scratch(geom(N, H, W, Cin, Cout, k, stride, pad));
+  const size_t c1 = c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad)) ? c1k4_wgrad_scratch() : 0;
+  return (long long)(generic > c1 ? generic : c1);
 }
 int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                    float* scratch, float* dw, void* stream) {
   PCG_API_BEGIN
+  if (c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+    c1k4_wgrad(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), scratch, dw, ST);
+    return 0;
+  }
+  if (Cin % 4 == 0 && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+    full1_wgrad(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), dw, ST);
+    return 0;
+  }
   if (conv_wgrad_auto(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), dw, ST)) return 0;
   conv_wgrad_generic<float, float>(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), scratch, dw, ST);
   PCG_API_END
@@ -74,6 +103,11 @@ int pcg_set_conv_tensor_cores(int on) {
   return 0;
 }
 int pcg_get_conv_tensor_cores(void) { return conv_auto_tensor_cores() ? 1 : 0; }
+int pcg_set_conv_tensor_core_terms(int terms) {
+  const int prev = conv_auto_terms();
+  conv_auto_set_terms(terms);
+  return prev;
+}
 long long pcg_stat_scratch_floats(int C) { return (long long)STAT_PARTS * 2 * C; }
 
 int pcg_bn_train_fwd(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,

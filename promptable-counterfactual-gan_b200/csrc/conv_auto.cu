@@ -70,6 +70,8 @@ static bf16* to_bf16(int slot, const float* src, long long n, cudaStream_t s) {
 // own fp32 CUDA-core realisation only agrees to ~1e-2 there); bf16x3 brings the tensor-core path to the fp32 level.
 // PCG_TC_TERMS=1 selects plain bf16 operands (1/3 of the tensor work).
 static int g_terms = -1;
+void conv_auto_set_terms(int t) { g_terms = (t == 1) ? 1 : 3; }
+int conv_auto_terms();
 static int terms() {
   if (g_terms < 0) {
     const char* e = getenv("PCG_TC_TERMS");
@@ -102,6 +104,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long long M, in
     }
   }
 }
+int conv_auto_terms() { return terms(); }
+
 static bf16* split(int slot, const float* src, long long M, int C, int T, bool lo_last, cudaStream_t s) {
   PCG_REQUIRE(C % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0, "split operand: C % 4 and 16-byte alignment");
   bf16* dst = reinterpret_cast<bf16*>(scratch(slot, (size_t)M * T * C * sizeof(bf16), s));

@@ -8,6 +8,9 @@ namespace pcg {
 
 void conv_auto_set_tensor_cores(bool on);
 bool conv_auto_tensor_cores();
+// operand terms of the tensor-core mode: 3 = bf16x3 (fp32-equivalent products), 1 = plain bf16 operands
+void conv_auto_set_terms(int t);
+int conv_auto_terms();
 bool conv_fprop_auto(const float* in, const ConvGeom& g, const float* wf, const GenEpilogue<float>& e, float* out,
                      cudaStream_t s);
 bool conv_dgrad_auto(const float* dout, const ConvGeom& g, const float* wd, const GenEpilogue<float>& e, float* din,

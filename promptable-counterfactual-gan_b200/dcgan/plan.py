@@ -98,7 +98,8 @@ class _ConvT:
 
 
 class DcganPlan:
-    def __init__(self, batch, device, lr=2e-4, betas=(0.5, 0.999), use_graph=True, tensor_cores=None, share=None):
+    def __init__(self, batch, device, lr=2e-4, betas=(0.5, 0.999), use_graph=True, tensor_cores=None, share=None,
+                 operand_terms=None):
         """share: another DcganPlan (any batch size) whose parameter arenas, Adam state, BatchNorm buffers and packed
         weights this plan uses too — the reference keeps ONE optimizer state for the whole run (mnist_dcgan.py:133-134),
         so the tail batch of an epoch (60000 % 128 = 96) must not get fresh moments.
@@ -106,6 +107,11 @@ class DcganPlan:
         bf16 operands; None = follow PCG_PRECISION (default bf16 -> on), False = exact fp32 on the CUDA cores."""
         self.B, self.lr, self.betas = batch, lr, betas
         self.tc = (os.environ.get("PCG_PRECISION", "bf16") != "fp32") if tensor_cores is None else bool(tensor_cores)
+        # operand precision of the tensor-core convolutions: 1 = plain bf16 operands, fp32 accumulation and fp32 storage
+        # (default: over 200 iterations its loss curves leave the fp32 oracle's no faster than the fp32 CUDA-core plan's
+        # own do, profiles/exp_dcgan_precision_r2.md), 3 = bf16x3 (fp32-equivalent products, 3x the tensor work: the mode
+        # the per-step parity tests pin to 1e-2)
+        self.terms = int(os.environ.get("PCG_TC_TERMS", "1")) if operand_terms is None else int(operand_terms)
         # data parallel (SURVEY §8e): one process per GPU, per-replica BatchNorm statistics, gradients summed by an
         # all-reduce before each optimizer step (D's before the G phase, which sees the updated D), 1/world folded
         # into Adam
@@ -297,10 +303,12 @@ class DcganPlan:
     # ------------------------------------------------------------------ one iteration
     def _tc(self, fn):
         K.set_conv_tensor_cores(self.tc)
+        prev = K.set_conv_tensor_core_terms(self.terms)
         try:
             fn()
         finally:
             K.set_conv_tensor_cores(False)
+            K.set_conv_tensor_core_terms(prev)
 
     def _body(self):
         def both():

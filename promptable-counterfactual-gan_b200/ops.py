@@ -47,6 +47,11 @@ def set_conv_tensor_cores(on):
     _lib.check(_L().pcg_set_conv_tensor_cores(1 if on else 0))
 
 
+def set_conv_tensor_core_terms(terms):
+    """3 = bf16x3 operands (fp32-equivalent), 1 = plain bf16 operands; returns the previous setting."""
+    return int(_L().pcg_set_conv_tensor_core_terms(int(terms)))
+
+
 # ---------------------------------------------------------------- convolution / linear
 def pack_weights(w, k, wf=None, wd=None, perm_hw=0):
     """torch OIHW (or [out,in] with k=1) -> wf [Cout][k*k][Cin], wd [Cin][k*k][Cout]."""

@@ -63,7 +63,7 @@ def test_native_plan_reproduces_reference_golden(tc):
     from pcg_b200.dcgan import DcganPlan
     z = np.load(GOLD)
     B, steps, seed0 = (int(v) for v in z["meta"])
-    plan = DcganPlan(B, "cuda", use_graph=False, tensor_cores=tc)
+    plan = DcganPlan(B, "cuda", use_graph=False, tensor_cores=tc, operand_terms=3)      # bf16x3: the fp32-level mode
     plan.G.load(O.synth_params(O.g_shapes(), 5))
     plan.D.load(O.synth_params(O.d_shapes(), 6))
     plan.refresh()
