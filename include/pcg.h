@@ -208,6 +208,18 @@ int pcg_mnist_step_d_grads(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, flo
 int pcg_mnist_step_d_update(pcg_mnist_plan* plan, void* stream);
 /* phase 3: D forward with the updated D, losses, G backward -> g_grads (same `in` and `scalars` as phase 1) */
 int pcg_mnist_step_g_grads(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream);
+/* Data-parallel refinements of phases 1 and 3 ("each [reduction] can be bucketed and overlapped with its own
+ * backward pass (D's also with the classifier fwd/dgrad ...)"):
+ *   pcg_mnist_set_defer_c_bwd(plan, 1): phase 1 stops the frozen classifier's branch after its forward + loss; the caller
+ *     runs pcg_mnist_step_c_bwd (the input-gradient chain) on another stream beside the all-reduce of d_grads and joins
+ *     it before phase 3;
+ *   pcg_mnist_step_g_grads_part(part = 1, split): phase 3 down to and including residual block `split` (weight-gradient
+ *     stream joined): the gradients of [resblocks.split .. conv_out], the tail of the flat arena, are final and can be
+ *     all-reduced while part = 2 (blocks split-1 .. 0, conv_in, embedding) runs.  1 <= split < n_resblocks. */
+int pcg_mnist_set_defer_c_bwd(pcg_mnist_plan* plan, int on);
+int pcg_mnist_step_c_bwd(pcg_mnist_plan* plan, void* stream);
+int pcg_mnist_step_g_grads_part(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, int part, int split_block,
+                                void* stream);
 /* phase 4: Adam on G */
 int pcg_mnist_step_g_update(pcg_mnist_plan* plan, void* stream);
 

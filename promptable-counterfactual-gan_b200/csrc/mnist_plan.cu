@@ -206,6 +206,9 @@ struct PlanBase {
   virtual void step_d_update(cudaStream_t s) = 0;
   virtual void step_g_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) = 0;
   virtual void step_g_update(cudaStream_t s) = 0;
+  virtual void step_c_bwd(cudaStream_t s) = 0;
+  virtual void set_defer_c_bwd(bool on) = 0;
+  virtual void step_g_grads_part(const pcg_mnist_inputs& in, float* scal, cudaStream_t s, int part, int split) = 0;
   virtual void g_forward(const float* x, const long long* target, const float* mask, int training, float* raw,
                          float* masked, cudaStream_t s) = 0;
   virtual void d_forward(const float* x, const long long* cond, float* logits, cudaStream_t s) = 0;
@@ -267,7 +270,7 @@ struct MnistPlan : PlanBase {
   T *cdf1, *cd3, *cd2, *cd1;
   // scratch
   float *stat_part, *stat_part2, *stat_bn2 = nullptr, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp, *small_part;
-  bool fuse_bn2_reduce = true, fuse_finalize = false;
+  bool fuse_bn2_reduce = true, fuse_finalize = false, defer_c_bwd = false;
   unsigned int* fin_counter = nullptr;
   size_t wg_scratch_elems = 0;
 
@@ -813,9 +816,17 @@ struct MnistPlan : PlanBase {
   // It needs nothing but x_cf (the classifier is in eval mode and is never updated), so it runs on side_c beside the
   // whole discriminator step instead of in front of the generator backward: both are chains of small kernels that do
   // not fill the GPU alone.
+  // Data parallel: the input-gradient half can be deferred (defer_c_bwd) and run as its own phase (step_c_bwd) on a side
+  // stream BESIDE the all-reduce of the discriminator's gradients, which nothing else in the step can overlap (the
+  // generator phase needs the updated discriminator).
   void c_branch(const pcg_mnist_inputs& in, float* scal, cudaStream_t c) {
     c_fwd(x_cf, c);
     ce_loss(clogits, in.target, B, 10, cfg.lambda_cls, scal + PCG_S_G_CLS, cdlogits, c);
+    if (!defer_c_bwd) c_branch_bwd(c);
+  }
+  void step_c_bwd(cudaStream_t s) override { c_branch_bwd(s); }
+  void set_defer_c_bwd(bool on) override { defer_c_bwd = on; }
+  void c_branch_bwd(cudaStream_t c) {
     GenEpilogue<T> e; e.ref_act = ACT_RELU;
     e.act_ref = cf1; dgrad<float, T>(c_fc2, cdlogits, e, cdf1, c);
     e.act_ref = cz[2]; dgrad<T, T>(c_fc1, cdf1, e, cd3, c);
@@ -863,8 +874,45 @@ struct MnistPlan : PlanBase {
     fprop<T, float>(c_fc2, cf1, eo, clogits, s);
   }
 
-  void step_g_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override {
+  // part 0: the whole phase.  Data parallel: part 1 = everything down to (and including) residual block `split`, with
+  // the weight-gradient stream joined, so the gradients of [block split .. conv_out] - the tail of the flat arena - can
+  // be all-reduced while part 2 (blocks split-1 .. 0, conv_in, the embedding) still runs.
+  void step_g_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override { g_grads(in, scal, s, 0, 0); }
+  void step_g_grads_part(const pcg_mnist_inputs& in, float* scal, cudaStream_t s, int part, int split) override {
+    PCG_REQUIRE((part == 1 || part == 2) && split >= 1 && split < nres, "g_grads part 1|2, 1 <= split < n_resblocks");
+    g_grads(in, scal, s, part, split);
+  }
+  T* gg_dh = nullptr;
+  T* gg_dh_other = nullptr;
+  int gg_bn2_parts = 0;
+  void g_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s, int part, int split) {
     cudaStream_t side_w = wstream(s);
+    T*& dh = gg_dh;
+    T*& dh_other = gg_dh_other;
+    int& bn2_parts = gg_bn2_parts;
+    auto dgrad_bn2 = [&](const ConvLayer<T>& L, const T* dout, const T* add, int blk, T* din) -> bool {
+      if constexpr (kBf16) {
+        if (L.tc_dgrad && L.tc64 && fuse_bn2_reduce) {
+          ProfTag _tag("g.res.dgrad_bnred");
+          const BN& qb = bn2[blk];
+          ConvEpilogue c;
+          c.add_src = add;
+          c.stats = stat_bn2;
+          c.bn_y = y2[blk]; c.bn_mean = qb.mean; c.bn_rstd = qb.rstd; c.bn_scale = qb.scale; c.bn_shift = qb.shift;
+          c.bn_act = ACT_NONE; c.bn_gscale = 0.1f;
+          if (fuse_finalize) {
+            c.fin.mode = 2; c.fin.counter = fin_counter; c.fin.M = MG;
+            c.fin.dgamma = qb.dgamma; c.fin.dbeta = qb.dbeta; c.fin.c12 = c12;
+          }
+          conv_tc64_fprop(dout, B, 28, 28, L.tcd, c, din, s);
+          bn2_parts = conv_tc64_fprop_grid(B, 28, 28);
+          return true;
+        }
+      }
+      return false;
+    };
+    const int i_hi = part == 2 ? split - 1 : nres - 1, i_lo = part == 1 ? split : 0;
+    if (part != 2) {
     // --- adversarial path through the UPDATED discriminator (trainer.py:116-117)
     // --- classifier path (trainer.py:118): independent of the discriminator path until the two input gradients meet
     //     in residual_head_bwd
@@ -888,40 +936,20 @@ struct MnistPlan : PlanBase {
       dgrad<T, T>(g_out, g_c, e, g_hm, s);
     }
     bias_grad(g_hm, MG, ch, g_mid.db, s);
-    T* dh = dhA;
-    T* dh_other = dhB;
+    dh = dhA;
+    dh_other = dhB;
     // The reduction pass of BN2's backward (sum g, sum g*xhat over g = 0.1*dh, generator.py:22) rides in the epilogue of
     // the tensor-core kernel that PRODUCES dh - conv_mid's data gradient for the last block, conv1's data gradient of
     // block i+1 (which also adds the skip gradient) for block i - instead of re-reading dh and y2 in a separate pass.
-    int bn2_parts = 0;
-    auto dgrad_bn2 = [&](const ConvLayer<T>& L, const T* dout, const T* add, int blk, T* din) -> bool {
-      if constexpr (kBf16) {
-        if (L.tc_dgrad && L.tc64 && fuse_bn2_reduce) {
-          ProfTag _tag("g.res.dgrad_bnred");
-          const BN& qb = bn2[blk];
-          ConvEpilogue c;
-          c.add_src = add;
-          c.stats = stat_bn2;
-          c.bn_y = y2[blk]; c.bn_mean = qb.mean; c.bn_rstd = qb.rstd; c.bn_scale = qb.scale; c.bn_shift = qb.shift;
-          c.bn_act = ACT_NONE; c.bn_gscale = 0.1f;
-          if (fuse_finalize) {
-            c.fin.mode = 2; c.fin.counter = fin_counter; c.fin.M = MG;
-            c.fin.dgamma = qb.dgamma; c.fin.dbeta = qb.dbeta; c.fin.c12 = c12;
-          }
-          conv_tc64_fprop(dout, B, 28, 28, L.tcd, c, din, s);
-          bn2_parts = conv_tc64_fprop_grid(B, 28, 28);
-          return true;
-        }
-      }
-      return false;
-    };
+    bn2_parts = 0;
     if (!dgrad_bn2(g_mid, g_hm, nullptr, nres - 1, dh)) {
       GenEpilogue<T> e;
       dgrad<T, T>(g_mid, g_hm, e, dh, s);
     }
     after(s, side_w);
     wgrad<T, T>(g_mid, h[nres], g_hm, side_w);
-    for (int i = nres - 1; i >= 0; --i) {
+    }   // part != 2
+    for (int i = i_hi; i >= i_lo; --i) {
       // BN2 backward: upstream = 0.1 * dh (generator.py:22)
       const BN& q2 = bn2[i];
       if (bn2_parts > 0) {
@@ -987,6 +1015,10 @@ struct MnistPlan : PlanBase {
       // no residual block consumed h0's activation derivative: apply it here via a copy-free trick
       GenEpilogue<T> e; (void)e;
       throw Error(1, "n_resblocks == 0 is not supported by the fused backward");
+    }
+    if (part == 1) {                               // the caller reduces the finished half of the gradients now
+      after(side_w, s);
+      return;
     }
     // dh now holds d loss / d (pre-activation of conv_in)
     after(s, side_w);
@@ -1144,6 +1176,25 @@ int pcg_mnist_step_d_update(pcg_mnist_plan* plan, void* stream) {
 int pcg_mnist_step_g_grads(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, void* stream) {
   PCG_API_BEGIN
   plan->impl->step_g_grads(*in, scalars, (cudaStream_t)stream);
+  PCG_API_END
+}
+int pcg_mnist_set_defer_c_bwd(pcg_mnist_plan* plan, int on) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(plan, "null plan");
+  plan->impl->set_defer_c_bwd(on != 0);
+  PCG_API_END
+}
+int pcg_mnist_step_c_bwd(pcg_mnist_plan* plan, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(plan, "null plan");
+  plan->impl->step_c_bwd((cudaStream_t)stream);
+  PCG_API_END
+}
+int pcg_mnist_step_g_grads_part(pcg_mnist_plan* plan, const pcg_mnist_inputs* in, float* scalars, int part, int split_block,
+                                void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(plan && in && scalars, "null argument");
+  plan->impl->step_g_grads_part(*in, scalars, (cudaStream_t)stream, part, split_block);
   PCG_API_END
 }
 int pcg_mnist_step_g_update(pcg_mnist_plan* plan, void* stream) {

@@ -185,6 +185,18 @@ class MnistStepPlan:
         _lib.check(self.L.pcg_mnist_step_g_grads(self._plan, ctypes.byref(inp), _lib.ptr(self.scalars),
                                                  _lib.stream_ptr()))
 
+    # data-parallel refinements (include/pcg.h): classifier input gradient as its own phase, generator backward in two parts
+    def set_defer_c_bwd(self, on):
+        _lib.check(self.L.pcg_mnist_set_defer_c_bwd(self._plan, 1 if on else 0))
+
+    def step_c_bwd(self):
+        _lib.check(self.L.pcg_mnist_step_c_bwd(self._plan, _lib.stream_ptr()))
+
+    def step_g_grads_part(self, x, y, target, mask, part, split):
+        inp = self._inputs(x, y, target, mask)
+        _lib.check(self.L.pcg_mnist_step_g_grads_part(self._plan, ctypes.byref(inp), _lib.ptr(self.scalars), part, split,
+                                                      _lib.stream_ptr()))
+
     def step_g_update(self):
         _lib.check(self.L.pcg_mnist_step_g_update(self._plan, _lib.stream_ptr()))
 

@@ -146,16 +146,70 @@ class CounterGanTrainer:
         if self.dist is not None:
             self.dist.all_reduce(t)
 
+    # ---- data parallel: the two gradient reductions the algorithm requires, each hidden behind work that
+    # does not depend on it.  D's runs beside the frozen classifier's input-gradient chain (own stream); G's is bucketed in
+    # two: the gradients of [resblocks.k .. conv_out] - the tail of the flat arena, finished first by the backward pass -
+    # are reduced while blocks k-1 .. 0 are still being differentiated, the head of the arena afterwards.
+    def _dp_split(self):
+        """(residual block k, arena offset of its first parameter), or None when the generator is too shallow."""
+        if self.n_res < 2:
+            return None
+        k = self.n_res // 2
+        return k, self.ga.slots[3 + 8 * k][0]          # parameters(): embed, conv_in w/b, then 8 tensors per block
+
+    def _dp_step(self, p, seg):
+        """seg: dict of callables 'd_grads', 'c_bwd', 'mid1' (D update + G backward part 1), 'mid2' (part 2), 'g_update'
+        (eager phase calls or graph replays)."""
+        on_gpu = getattr(self, "device", None) is not None and self.device.type == "cuda"
+        seg["d_grads"]()
+        if on_gpu:
+            main, side = torch.cuda.current_stream(), self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                seg["c_bwd"]()
+        else:                                          # host-logic tests (gloo on CPU tensors): no streams
+            seg["c_bwd"]()
+        wd = self.dist.all_reduce(self.da.grad, async_op=True)
+        wd.wait()
+        if on_gpu:
+            main.wait_stream(side)
+        split = self._dp_split()
+        if split is None:
+            seg["mid1"]()
+            self.dist.all_reduce(self.ga.grad)
+        else:
+            off = split[1]
+            seg["mid1"]()
+            w_tail = self.dist.all_reduce(self.ga.grad[off:], async_op=True)
+            seg["mid2"]()
+            w_head = self.dist.all_reduce(self.ga.grad[:off], async_op=True)
+            w_tail.wait()
+            w_head.wait()
+        seg["g_update"]()
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def _dp_segments(self, p, x, y, t, m):
+        split = self._dp_split()
+        p.set_defer_c_bwd(True)
+        if split is None:
+            mid1 = lambda: (p.step_d_update(), p.step_g_grads(x, y, t, m))    # noqa: E731
+            mid2 = None
+        else:
+            k = split[0]
+            mid1 = lambda: (p.step_d_update(), p.step_g_grads_part(x, y, t, m, 1, k))    # noqa: E731
+            mid2 = lambda: p.step_g_grads_part(x, y, t, m, 2, k)    # noqa: E731
+        return {"d_grads": lambda: p.step_d_grads(x, y, t, m), "c_bwd": p.step_c_bwd, "mid1": mid1, "mid2": mid2,
+                "g_update": p.step_g_update}
+
     def _run_phases(self, p, x, y, t, m):
         if self.dist is None:
             p.step(x, y, t, m)
         else:
-            p.step_d_grads(x, y, t, m)
-            self._allreduce(self.da.grad)
-            p.step_d_update()
-            p.step_g_grads(x, y, t, m)
-            self._allreduce(self.ga.grad)
-            p.step_g_update()
+            self._dp_step(p, self._dp_segments(p, x, y, t, m))
 
     def step(self, x, y, target, mask):
         """One iteration on device tensors; returns the plan whose ``scalars`` hold the losses."""
@@ -227,20 +281,13 @@ class CounterGanTrainer:
 
     def _capture(self, p, st, pre=None):
         if self.dist is not None:
-            # NCCL collectives sit between the phases: capture the three kernel-only segments
-            segs = []
-            for fn in (lambda: ((pre() if pre else None), p.step_d_grads(*st)),
-                       lambda: (p.step_d_update(), p.step_g_grads(*st)),
-                       lambda: p.step_g_update()):
-                segs.append(self._capture_fn(fn))
-
-            def run():
-                segs[0].replay()
-                self._allreduce(self.da.grad)
-                segs[1].replay()
-                self._allreduce(self.ga.grad)
-                segs[2].replay()
-            return run
+            # NCCL collectives sit between the phases: capture the kernel-only segments, replay them around the reductions
+            seg = self._dp_segments(p, *st)
+            d_grads = seg["d_grads"]
+            seg["d_grads"] = lambda: ((pre() if pre else None), d_grads())
+            graphs_ = {k: self._capture_fn(fn) for k, fn in seg.items() if fn is not None}
+            replay = {k: (graphs_[k].replay if k in graphs_ else None) for k in seg}
+            return lambda: self._dp_step(p, replay)
         g = self._capture_fn(lambda: ((pre() if pre else None), p.step(*st)))
         return g.replay
 
