@@ -430,6 +430,9 @@ def run_native(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        tr.close()                                # captured graphs hold NCCL work: release them first
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -122,6 +122,19 @@ class CounterGanTrainer:
         self.graphs = {}
         self.static = {}
         self._last_bs = None
+        self._dp_graphs = []
+        self._side = torch.cuda.Stream(device=self.device) if self.dist is not None else None
+
+    def close(self):
+        """Drops the captured graphs (they hold NCCL work captured on the process group's stream: release them before
+        ``destroy_process_group``) and the native plans."""
+        self.graphs.clear()
+        self._dp_graphs.clear()
+        for p in self.plans.values():
+            p.close()
+        self.plans.clear()
+        import gc
+        gc.collect()
 
     def _step_cfg_grad_scale(self):
         """Gradients are summed by the all-reduce; the 1/world_size average is folded into Adam."""
@@ -146,13 +159,18 @@ class CounterGanTrainer:
         if self.dist is not None:
             self.dist.all_reduce(t)
 
-    # ---- data parallel: the two gradient reductions the algorithm requires, each hidden behind work that
-    # does not depend on it.  D's runs beside the frozen classifier's input-gradient chain (own stream); G's is bucketed in
-    # two: the gradients of [resblocks.k .. conv_out] - the tail of the flat arena, finished first by the backward pass -
-    # are reduced while blocks k-1 .. 0 are still being differentiated, the head of the arena afterwards.
+    # ---- data parallel: the two gradient reductions the algorithm requires.  Three overlap schemes are
+    # implemented and were measured at 2 x B200 (profiles/exp_dp_overlap_r2.md); none moved the step time (3.05-3.07 ms
+    # against 2.97 ms on one GPU): the messages (3.9 MB and 2.0 MB) are latency-bound, so what is exposed is two NCCL
+    # latencies whatever is scheduled beside them.  They stay as switches, default off:
+    #   PCG_DP_DEFER_CBWD=1  D's reduction runs beside the frozen classifier's input-gradient chain (own stream);
+    #   PCG_DP_SPLIT=1       G's reduction in two buckets: [resblocks.k .. conv_out], the tail of the flat arena that the
+    #                        backward pass finishes first, is reduced while blocks k-1 .. 0 are still differentiated;
+    #   PCG_DP_ONE_GRAPH=1   the whole iteration including the NCCL calls captured as ONE graph (close() before
+    #                        destroy_process_group).
     def _dp_split(self):
         """(residual block k, arena offset of its first parameter), or None when the generator is too shallow."""
-        if self.n_res < 2:
+        if self.n_res < 2 or os.environ.get("PCG_DP_SPLIT", "0") != "1":
             return None
         k = self.n_res // 2
         return k, self.ga.slots[3 + 8 * k][0]          # parameters(): embed, conv_in w/b, then 8 tensors per block
@@ -194,7 +212,8 @@ class CounterGanTrainer:
 
     def _dp_segments(self, p, x, y, t, m):
         split = self._dp_split()
-        p.set_defer_c_bwd(True)
+        defer = os.environ.get("PCG_DP_DEFER_CBWD", "0") == "1"
+        p.set_defer_c_bwd(defer)
         if split is None:
             mid1 = lambda: (p.step_d_update(), p.step_g_grads(x, y, t, m))    # noqa: E731
             mid2 = None
@@ -202,8 +221,8 @@ class CounterGanTrainer:
             k = split[0]
             mid1 = lambda: (p.step_d_update(), p.step_g_grads_part(x, y, t, m, 1, k))    # noqa: E731
             mid2 = lambda: p.step_g_grads_part(x, y, t, m, 2, k)    # noqa: E731
-        return {"d_grads": lambda: p.step_d_grads(x, y, t, m), "c_bwd": p.step_c_bwd, "mid1": mid1, "mid2": mid2,
-                "g_update": p.step_g_update}
+        return {"d_grads": lambda: p.step_d_grads(x, y, t, m), "c_bwd": p.step_c_bwd if defer else (lambda: None),
+                "mid1": mid1, "mid2": mid2, "g_update": p.step_g_update}
 
     def _run_phases(self, p, x, y, t, m):
         if self.dist is None:
@@ -281,10 +300,17 @@ class CounterGanTrainer:
 
     def _capture(self, p, st, pre=None):
         if self.dist is not None:
-            # NCCL collectives sit between the phases: capture the kernel-only segments, replay them around the reductions
             seg = self._dp_segments(p, *st)
             d_grads = seg["d_grads"]
             seg["d_grads"] = lambda: ((pre() if pre else None), d_grads())
+            if os.environ.get("PCG_DP_ONE_GRAPH", "0") == "1" and self.dist.get_backend() == "nccl":
+                # the whole iteration INCLUDING the NCCL all-reduces as one graph: no host round trip and no idle gap
+                # at the five segment boundaries (the collectives are captured on NCCL's own stream, forked from and
+                # joined to the capture stream by the process group).  close() must run before destroy_process_group.
+                g = self._capture_fn(lambda: self._dp_step(p, seg))
+                self._dp_graphs.append(g)
+                return g.replay
+            # otherwise (gloo, or PCG_DP_ONE_GRAPH=0): capture the kernel-only segments, replay them around the reductions
             graphs_ = {k: self._capture_fn(fn) for k, fn in seg.items() if fn is not None}
             replay = {k: (graphs_[k].replay if k in graphs_ else None) for k in seg}
             return lambda: self._dp_step(p, replay)

@@ -76,6 +76,13 @@ def _worker(rank, world, port, ret):
     assert tr.world == world
     log = []
     plan = _FakePlan(tr, rank, log)
+    # default: one reduction after each backward pass
+    tr._run_phases(plan, None, None, None, None)
+    assert plan.deferred is False and log == ["d_grads", "d_update", "g_grads", "g_update"], log
+    assert torch.all(plan.seen_d == 3.0) and torch.all(plan.seen_g == 30.0)
+    # overlap switches: deferred classifier input gradient, generator backward / reduction in two buckets
+    os.environ.update(PCG_DP_DEFER_CBWD="1", PCG_DP_SPLIT="1")
+    log.clear()
     tr._run_phases(plan, None, None, None, None)
     assert plan.deferred is True
     assert log == ["d_grads", "c_bwd", "d_update", "g_grads_1", "g_grads_2", "g_update"], log

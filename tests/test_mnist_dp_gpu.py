@@ -30,7 +30,7 @@ def _mods(seed=0):
     from pcg_b200.mnist.models.discriminator import Discriminator
     from pcg_b200.mnist.models.classifier import CNNClassifier
     torch.manual_seed(seed)
-    G = ResidualGenerator(base_ch=16, n_resblocks=1).cuda()
+    G = ResidualGenerator(base_ch=16, n_resblocks=2).cuda()       # two blocks: the generator backward splits at block 1
     D = Discriminator().cuda()
     C = CNNClassifier().cuda().eval()
     for p in C.parameters():
