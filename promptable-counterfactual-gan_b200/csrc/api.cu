@@ -21,6 +21,11 @@ static int env_pdl() {
   return e ? (atoi(e) != 0) : 0;      // off by default: measured slower as a blanket policy (profiles/exp_pdl_r1.md)
 }
 int g_pdl = env_pdl();
+static int env_pdl_edges() {
+  const char* e = getenv("PCG_PDL_EDGES");
+  return e ? (atoi(e) != 0) : 1;      // on by default: only the tcgen05 64->64 kernels, whose prologue runs before their wait
+}
+int g_pdl_edges = env_pdl_edges();
 const char* g_prof_tag = nullptr;
 struct ProfRec { std::string name; cudaEvent_t e0, e1; };
 static std::vector<ProfRec> g_prof;

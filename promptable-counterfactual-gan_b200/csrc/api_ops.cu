@@ -25,6 +25,12 @@ using namespace pcg;
   }
 #define ST ((cudaStream_t)stream)
 
+// A/B switch: PCG_SKINNY=0 keeps the one-channel / one-output layers on the generic kernels
+static bool skinny_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PCG_SKINNY"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
 static ConvGeom geom(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
   return ConvGeom{N, H, W, Cin, Cout, k, stride, pad};
 }
@@ -36,11 +42,11 @@ int pcg_conv_fprop(const float* in, int N, int H, int W, int Cin, const float* w
   PCG_API_BEGIN
   GenEpilogue<float> e;
   e.bias = bias; e.act = act; e.slope = slope; e.add_src = add_src;
-  if (bias == nullptr && add_src == nullptr && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+  if (bias == nullptr && add_src == nullptr && skinny_on() && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     c1k4_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, act, slope, out, ST);
     return 0;
   }
-  if (act == ACT_NONE && add_src == nullptr && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+  if (act == ACT_NONE && add_src == nullptr && skinny_on() && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     full1_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, bias, out, ST);
     return 0;
   }
@@ -54,12 +60,12 @@ int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float*
   GenEpilogue<float> e;
   e.add_src = add_src; e.act_ref = act_ref; e.ref_act = ref_act; e.ref_slope = ref_slope;
   if (add_src == nullptr && (act_ref == nullptr || ref_act == ACT_NONE) &&
-      c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+      skinny_on() && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     c1k4_dgrad(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, din, ST);
     return 0;
   }
   if (add_src == nullptr && (act_ref == nullptr || ref_act == ACT_NONE) && Cin % 4 == 0 &&
-      full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+      skinny_on() && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     full1_dgrad(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, din, ST);
     return 0;
   }
@@ -69,17 +75,17 @@ int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float*
 }
 long long pcg_conv_wgrad_scratch(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
   const size_t generic = conv_wgrad_generic_scratch(geom(N, H, W, Cin, Cout, k, stride, pad));
-  const size_t c1 = c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad)) ? c1k4_wgrad_scratch() : 0;
+  const size_t c1 = skinny_on() && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad)) ? c1k4_wgrad_scratch() : 0;
   return (long long)(generic > c1 ? generic : c1);
 }
 int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                    float* scratch, float* dw, void* stream) {
   PCG_API_BEGIN
-  if (c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+  if (skinny_on() && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     c1k4_wgrad(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), scratch, dw, ST);
     return 0;
   }
-  if (Cin % 4 == 0 && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+  if (Cin % 4 == 0 && skinny_on() && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     full1_wgrad(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), dw, ST);
     return 0;
   }

@@ -72,6 +72,26 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   PCG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 
+// Per-edge variant for kernels with a real prologue (the tcgen05 convolutions: barrier init, TMEM allocation, shared-memory
+// zero fill - ~2 us that touch no global memory): they call pdl_launch_dependents() first, run the prologue, and only then
+// pdl_wait(); launched with launch_k_pdl the prologue (and the launch latency) overlaps the predecessor's tail.  Switch:
+// g_pdl_edges (env PCG_PDL_EDGES, default on).
+extern int g_pdl_edges;
+template <typename... KArgs, typename... Args>
+inline void launch_k_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (g_pdl || g_pdl_edges) ? 1 : 0;
+  PCG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // Number of SMs of the current device (cached).
 int sm_count();
 

@@ -207,7 +207,7 @@ __device__ __forceinline__ float butterfly_colsum32(float (&v)[32], int lane) {
 template <int BN, int NC>
 __global__ void __launch_bounds__(FPROP_THREADS, 1)
 conv_tc_fprop_kernel(const __grid_constant__ FpropArgs<NC> P) {
-  pdl_enter();
+  pdl_launch_dependents();                        // prologue first (no global memory), pdl_wait() below
   using Cfg = FpropCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -257,6 +257,7 @@ conv_tc_fprop_kernel(const __grid_constant__ FpropArgs<NC> P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                     // the predecessor kernel has completed and flushed
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -488,7 +489,7 @@ static void launch_fprop_args(const FpropArgs<NC>& args, cudaStream_t stream) {
   }
   const int tiles = args.tile_end[NC - 1];
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  launch_k(conv_tc_fprop_kernel<BN, NC>, dim3(grid), dim3(FPROP_THREADS), Cfg::SMEM_BYTES, stream, args);
+  launch_k_pdl(conv_tc_fprop_kernel<BN, NC>, dim3(grid), dim3(FPROP_THREADS), Cfg::SMEM_BYTES, stream, args);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -660,7 +661,7 @@ constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_X_STAGE + 2 * WG_DY_BYTES + 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                        int M, int H, int W, int num_pblocks, float* __restrict__ part) {
-  pdl_enter();
+  pdl_launch_dependents();                        // prologue first (no global memory), pdl_wait() below
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -693,6 +694,7 @@ conv_tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                     // the predecessor kernel has completed and flushed
 
   if (warp == 0) {
     if (lane == 0) {
@@ -822,7 +824,7 @@ template <int NT>
 __global__ void __launch_bounds__(WGG_THREADS, 1)
 conv_tc_wgrad_general_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                              const WggParams p) {
-  pdl_enter();
+  pdl_launch_dependents();                        // prologue first (no global memory), pdl_wait() below
   using Cfg = WggCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -858,6 +860,7 @@ conv_tc_wgrad_general_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                     // the predecessor kernel has completed and flushed
 
   if (warp == 0) {
     if (lane == 0) {
@@ -979,7 +982,7 @@ void conv_tc_wgrad_general(const bf16* x, const bf16* dy, int N, int H, int W, i
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, WggCfg<NTV>::SMEM_BYTES)); \
       configured = true;                                                                                           \
     }                                                                                                              \
-    launch_k(conv_tc_wgrad_general_kernel<NTV>, dim3(grid), dim3(WGG_THREADS), WggCfg<NTV>::SMEM_BYTES, stream, tmX, tmDY, p);       \
+    launch_k_pdl(conv_tc_wgrad_general_kernel<NTV>, dim3(grid), dim3(WGG_THREADS), WggCfg<NTV>::SMEM_BYTES, stream, tmX, tmDY, p);       \
   }
   if (nt == 256) PCG_WGG(256) else if (nt == 128) PCG_WGG(128) else PCG_WGG(64)
 #undef PCG_WGG
@@ -1007,7 +1010,7 @@ void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* 
   }
   const int nb = (int)((M + TILE_M - 1) / TILE_M);
   const int grid = conv_tc_wgrad_grid(M);
-  launch_k(conv_tc_wgrad64_kernel, dim3(grid), dim3(WG_THREADS), WG_SMEM_BYTES, stream, tmX, tmDY, (int)M, H, W, nb, part);
+  launch_k_pdl(conv_tc_wgrad64_kernel, dim3(grid), dim3(WG_THREADS), WG_SMEM_BYTES, stream, tmX, tmDY, (int)M, H, W, nb, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

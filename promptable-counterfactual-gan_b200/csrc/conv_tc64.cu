@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
                        const F64Params p) {
-  pdl_enter();
+  pdl_launch_dependents();                        // the prologue below touches no global memory: see pdl_wait() further down
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -240,6 +240,7 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                     // from here on the predecessor kernel has completed and flushed
   const int box_bytes = (p.R + 2) * p.WP * 128;
   const int tile_bytes = p.R * p.W * 128;
 
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
                         const __grid_constant__ CUtensorMap tmAdd, const F64Params p) {
-  pdl_enter();
+  pdl_launch_dependents();                        // the prologue below touches no global memory: see pdl_wait() further down
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -624,6 +625,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                     // from here on the predecessor kernel has completed and flushed
   const int box_bytes = (p.R + 1) * p.WP * 128;
   const int tile_bytes = p.R * p.W * 128;
 
@@ -1100,7 +1102,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     CUtensorMap tmOut = make_tmap_nhwc_rowclass(out, N, H, W, 64, W, p.R);
     CUtensorMap tmExtra = make_tmap_nhwc_rowclass(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
     CUtensorMap tmAdd = make_tmap_nhwc_rowclass(add_tma != nullptr ? add_tma : out, N, H, W, 64, W, p.R);
-    launch_k(conv_tc64s_fprop_kernel, dim3(conv_tc64_fprop_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra,
+    launch_k_pdl(conv_tc64s_fprop_kernel, dim3(conv_tc64_fprop_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra,
              tmAdd, p);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
@@ -1111,7 +1113,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   CUtensorMap tmX = make_tmap_nhwc_box(in, N, H, W, 64, p.WP, p.R + 2);
   CUtensorMap tmOut = make_tmap_nhwc_box(out, N, H, W, 64, W, p.R);
   CUtensorMap tmExtra = make_tmap_nhwc_box(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
-  launch_k(conv_tc64_fprop_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra, p);
+  launch_k_pdl(conv_tc64_fprop_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra, p);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
   if (fin.mode == 1)
@@ -1134,7 +1136,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, int N, int H,
                        int W, int WP, int R, int tiles_per_img, int total_tiles, int variant,
                        float* __restrict__ part) {
-  pdl_enter();
+  pdl_launch_dependents();                        // the prologue below touches no global memory: see pdl_wait() further down
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -1167,6 +1169,7 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                     // from here on the predecessor kernel has completed and flushed
   const int xbytes = (R + 2) * WP * 128, dybytes = R * WP * 128;
 
   if (warp == 0) {
@@ -1307,7 +1310,7 @@ void conv_tc64_wgrad(const bf16* x, const bf16* dy, int N, int H, int W, float* 
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
     configured = true;
   }
-  launch_k(conv_tc64_wgrad_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(G_THREADS), G_SMEM_BYTES, stream, 
+  launch_k_pdl(conv_tc64_wgrad_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(G_THREADS), G_SMEM_BYTES, stream, 
       tmX, tmDY, N, H, W, WP, R, tiles_per_img, N * tiles_per_img, g_variant, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();

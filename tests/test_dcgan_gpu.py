@@ -210,7 +210,11 @@ def test_dcgan_plain_bf16_operands_default_mode():
     batches = [O.synth_batch(Bc, 1000 + i) for i in range(steps)]
     PG, PD = O.synth_params(O.g_shapes(), 5), O.synth_params(O.d_shapes(), 6)
     So = O.make_state(PG, O.buffers(O.g_shapes()), PD, O.buffers(O.d_shapes()))
-    ora = torch.tensor([[O.dcgan_step(So, *b)[0][k] for k in ("errD", "errG", "D_x", "D_G_z1")] for b in batches]).double()
+    ora = []
+    for b in batches:
+        sc_b, _ = O.dcgan_step(So, *b)
+        ora.append([sc_b[k] for k in ("errD", "errG", "D_x", "D_G_z1")])
+    ora = torch.tensor(ora).double()
     dev = {}
     for name, tc, terms in (("fp32", False, 3), ("bf16", True, 1)):
         p = DcganPlan(Bc, "cuda", use_graph=False, tensor_cores=tc, operand_terms=terms)

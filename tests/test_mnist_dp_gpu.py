@@ -42,8 +42,10 @@ CFG = types.SimpleNamespace(g_lr=5e-5, d_lr=1e-5, num_classes=10, patch_size=7, 
                             lambda_adv=1.0, lambda_cls=1.0, lambda_reg=2.5, lambda_mask=2.0)
 
 
-def _worker(rank, world, port, use_graph, out):
+def _worker(rank, world, port, use_graph, overlap, out):
     import sys
+    if overlap:        # the optional overlap schemes (trainer.py): deferred classifier input gradient, two G buckets
+        os.environ.update(PCG_DP_DEFER_CBWD="1", PCG_DP_SPLIT="1")
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import torch.distributed as dist
     from oracle import mnist_countergan as O
@@ -96,13 +98,13 @@ def _worker(rank, world, port, use_graph, out):
     out.put((rank, err, same, float((single[0] - dp[0]).abs().max()), float((single[1] - dp[1]).abs().max())))
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_two_ranks_match_single_process(use_graph):
+@pytest.mark.parametrize("use_graph,overlap", [(False, False), (True, False), (True, True)])
+def test_two_ranks_match_single_process(use_graph, overlap):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, use_graph, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, use_graph, overlap, out)) for r in range(2)]
     for p in procs:
         p.start()
     res = [out.get(timeout=300) for _ in procs]
