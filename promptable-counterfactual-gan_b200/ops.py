@@ -25,6 +25,55 @@ def _L():
     return _lib.load()
 
 
+# ---------------------------------------------------------------- dataflow recording (pcg_b200.dataflow)
+# Every operator wrapper below is declared with the names of the arguments it WRITES; while a recorder is installed the
+# call is not launched but appended to it with its read set (every tensor reachable from the arguments) and write set,
+# so that the step plans can be re-emitted onto several streams with exactly the dependencies the data flow requires.
+_rec = None
+
+
+def _tensors(v, out):
+    if v is None:
+        return out
+    if isinstance(v, torch.Tensor):
+        out.append(v)
+    elif isinstance(v, tuple) and len(v) == 3 and isinstance(v[0], torch.Tensor) and isinstance(v[1], int):
+        out.append(v)                              # (tensor, first column, end column): a column window of a 2-D tensor
+    elif isinstance(v, (list, tuple)):
+        for e in v:
+            _tensors(e, out)
+    elif isinstance(v, BNState):
+        for e in vars(v).values():
+            _tensors(e, out)
+    return out
+
+
+def _op(*writes, reads=None):
+    """Decorator: ``writes`` are argument names, or callables ``bound_arguments -> iterable of tensors``; ``reads``
+    (optional callable) replaces the default read set, every tensor reachable from the arguments."""
+    import functools
+    import inspect
+
+    def deco(fn):
+        sig = inspect.signature(fn)
+
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            if _rec is None:
+                return fn(*args, **kwargs)
+            b = sig.bind(*args, **kwargs)
+            b.apply_defaults()
+            w = []
+            for name in writes:
+                _tensors(name(b.arguments) if callable(name) else b.arguments[name], w)
+            r = _tensors(reads(b.arguments) if reads is not None else list(b.arguments.values()), [])
+            _rec.add(fn, args, kwargs, r, w)
+            return None
+        wrapper.__wrapped_op__ = fn
+        return wrapper
+    return deco
+
+
 def _s():
     return _lib.stream_ptr()
 
@@ -53,6 +102,7 @@ def set_conv_tensor_core_terms(terms):
 
 
 # ---------------------------------------------------------------- convolution / linear
+@_op("wf", "wd")
 def pack_weights(w, k, wf=None, wd=None, perm_hw=0):
     """torch OIHW (or [out,in] with k=1) -> wf [Cout][k*k][Cin], wd [Cin][k*k][Cout]."""
     Cout, Cin = w.shape[0], w.shape[1]
@@ -60,12 +110,14 @@ def pack_weights(w, k, wf=None, wd=None, perm_hw=0):
     _lib.check(_L().pcg_pack_conv_weights(P(w), Cout, Cin, k, perm_hw, P(wf), P(wd), _s()))
 
 
+@_op("out")
 def conv_fprop(x, N, H, W, Cin, wf, Cout, k, stride, pad, out, bias=None, act=ACT_NONE, slope=0.2, add_src=None):
     _chk(x, wf, out, bias, add_src)
     _lib.check(_L().pcg_conv_fprop(P(x), N, H, W, Cin, P(wf), Cout, k, stride, pad, P(bias), act, _f(slope), P(add_src),
                                    P(out), _s()))
 
 
+@_op("din")
 def conv_dgrad(dout, N, H, W, Cin, wd, Cout, k, stride, pad, din, add_src=None, act_ref=None, ref_act=ACT_NONE,
                ref_slope=0.2):
     """din[N,H,W,Cin] = gradient of conv(geometry N,H,W,Cin -> Cout) wrt its input, given dout."""
@@ -84,6 +136,7 @@ def conv_wgrad_scratch(N, H, W, Cin, Cout, k, stride, pad, device):
     return torch.zeros(conv_wgrad_scratch_floats(N, H, W, Cin, Cout, k, stride, pad), device=device)
 
 
+@_op("scratch", "dw")
 def conv_wgrad(x, dout, N, H, W, Cin, Cout, k, stride, pad, scratch, dw):
     _chk(x, dout, scratch, dw)
     _lib.check(_L().pcg_conv_wgrad(P(x), P(dout), N, H, W, Cin, Cout, k, stride, pad, P(scratch), P(dw), _s()))
@@ -109,6 +162,7 @@ def linear_wgrad(x, dy, scratch, dw, db=None, stat=None):
         colsum(dy, stat, db)
 
 
+@_op("scratch", "out")
 def colsum(a, scratch, out):
     M, C = a.shape[0] if a.dim() == 2 else a.numel() // a.shape[-1], a.shape[-1]
     _chk(a, scratch, out)
@@ -127,6 +181,7 @@ class BNState:
         self.scratch2 = stat_scratch(C, device)
 
 
+@_op("running_mean", "running_var", "nbt", "z", lambda a: [a["st"].mean, a["st"].rstd, a["st"].scale, a["st"].shift, a["st"].scratch])
 def bn_train_fwd(y, M, C, gamma, beta, running_mean, running_var, nbt, st, z, act=ACT_NONE, slope=0.2, eps=1e-5,
                  momentum=0.1):
     _chk(y, gamma, beta, z)
@@ -135,6 +190,7 @@ def bn_train_fwd(y, M, C, gamma, beta, running_mean, running_var, nbt, st, z, ac
                                      _f(slope), P(z), P(st.scratch), _s()))
 
 
+@_op("dy", "dgamma", "dbeta", "dbias_prev", lambda a: [a["st"].c12, a["st"].scratch, a["st"].scratch2])
 def bn_train_bwd(dz, y, M, C, gamma, st, dy, dgamma, dbeta, dbias_prev=None, gscale=1.0, act=ACT_NONE, slope=0.2):
     _chk(dz, y, dy, dgamma, dbeta, dbias_prev)
     _lib.check(_L().pcg_bn_train_bwd(P(dz), P(y), _ll(M), C, P(gamma), P(st.mean), P(st.rstd), P(st.scale), P(st.shift),
@@ -142,38 +198,45 @@ def bn_train_bwd(dz, y, M, C, gamma, st, dy, dgamma, dbeta, dbias_prev=None, gsc
                                      P(st.scratch), P(st.scratch2), _s()))
 
 
+@_op("y", "scale_out")
 def bn_eval(x, gamma, beta, rm, rv, y, scale_out=None, eps=1e-5):
     rows, C = x.numel() // x.shape[-1], x.shape[-1]
     _lib.check(_L().pcg_bn_eval(P(x), _ll(rows), C, P(gamma), P(beta), P(rm), P(rv), _f(eps), P(y), P(scale_out), _s()))
 
 
+@_op("dx")
 def scale_cols(dy, scale, dx):
     rows, C = dy.numel() // dy.shape[-1], dy.shape[-1]
     _lib.check(_L().pcg_scale_cols(P(dy), _ll(rows), C, P(scale), P(dx), _s()))
 
 
 # ---------------------------------------------------------------- elementwise / reductions / losses
+@_op("y")
 def unary(x, op, y, a=0.0):
     _chk(x, y)
     _lib.check(_L().pcg_unary(P(x), _ll(x.numel()), op, _f(a), P(y), _s()))
 
 
+@_op("dx")
 def unary_bwd(dy, y, op, dx, a=0.0):
     _chk(dy, y, dx)
     _lib.check(_L().pcg_unary_bwd(P(dy), P(y), _ll(y.numel()), op, _f(a), P(dx), _s()))
 
 
+@_op("out")
 def binary(a, b, op, out, alpha=1.0, beta=1.0):
     _chk(a, b, out)
     _lib.check(_L().pcg_binary(P(a), P(b), _ll(a.numel()), op, _f(alpha), _f(beta), P(out), _s()))
 
 
+@_op("out")
 def film_fwd(gamma, n, beta, out, relu=False, res=None):
     """out = [relu](gamma * n + beta) [+ res], one launch."""
     _chk(gamma, n, beta, out, res)
     _lib.check(_L().pcg_film_fwd(P(gamma), P(n), P(beta), P(res), _ll(n.numel()), 1 if relu else 0, P(out), _s()))
 
 
+@_op("dn", "dgamma", "dbeta")
 def film_bwd(df, gamma, n, dn, dgamma, dbeta, accumulate=False):
     """dn = df * gamma ; dgamma (+)= df * n ; dbeta (+)= df, one launch."""
     _chk(df, gamma, n, dn, dgamma, dbeta)
@@ -181,6 +244,7 @@ def film_bwd(df, gamma, n, dn, dgamma, dbeta, accumulate=False):
                                  P(dbeta), _s()))
 
 
+@_op(lambda a: [t for _, t in a["pairs"]])
 def transpose_multi(pairs):
     """pairs: list of (W [rows, cols], WT [cols, rows]); one launch per 64 matrices."""
     for i in range(0, len(pairs), 64):
@@ -193,6 +257,9 @@ def transpose_multi(pairs):
         _lib.check(_L().pcg_transpose_multi(n, src, dst, rows, cols, _s()))
 
 
+@_op(lambda a: [(a["dst"], a["c0_dst"], a["c0_dst"] + a["ncols"])],
+     reads=lambda a: [(a["src"], a["c0_src"], a["c0_src"] + a["ncols"])] +
+     ([(a["dst"], a["c0_dst"], a["c0_dst"] + a["ncols"])] if a["accumulate"] else []))
 def copy_cols(src, c0_src, dst, c0_dst, ncols, alpha=1.0, accumulate=False):
     _chk(src, dst)
     rows = src.shape[0]
@@ -200,26 +267,31 @@ def copy_cols(src, c0_src, dst, c0_dst, ncols, alpha=1.0, accumulate=False):
                                   1 if accumulate else 0, _s()))
 
 
+@_op("dst")
 def onehot(labels, nc, dst, c0=0):
     _chk(labels, dst)
     _lib.check(_L().pcg_onehot(P(labels), _ll(labels.numel()), nc, P(dst), dst.shape[1], c0, _s()))
 
 
+@_op("out", "dx")
 def reduce_scalar(x, out, scale=1.0, absval=False, dx=None, gscale=0.0):
     _chk(x, out, dx)
     _lib.check(_L().pcg_reduce_scalar(P(x), _ll(x.numel()), 1 if absval else 0, _f(scale), P(out), _f(gscale), P(dx), _s()))
 
 
+@_op("out", "dx")
 def rownorm_mean(x, p, out, dx=None, gscale=0.0):
     _chk(x, out, dx)
     _lib.check(_L().pcg_rownorm_mean(P(x), _ll(x.shape[0]), x.shape[1], p, P(out), _f(gscale), P(dx), _s()))
 
 
+@_op("out_loss", "dz", "out_aux")
 def gan_loss(z, kind, t, out_loss, dz, wgt=1.0, out_aux=None):
     _chk(z, out_loss, dz, out_aux)
     _lib.check(_L().pcg_gan_loss(P(z), z.numel(), kind, _f(t), _f(wgt), P(out_loss), P(out_aux), P(dz), _s()))
 
 
+@_op("out")
 def combine(terms, out):
     """out[0] = sum coeff * scalar_tensor[0] over up to 6 (coeff, tensor) pairs."""
     n = len(terms)
@@ -228,6 +300,7 @@ def combine(terms, out):
     _lib.check(_L().pcg_combine_scalars(n, coeffs, ptrs, P(out), _s()))
 
 
+@_op(lambda a: [a["G"].data, a["G"].grad, a["G"].m, a["G"].v, a["G"].step, a["D"].data, a["D"].grad, a["D"].m, a["D"].v, a["D"].step, a["scal"]])
 def mlp_gan_step(B, z_dim, label_dim, hidden, real, real_oh, z1, oh1, z2, oh2, G, D, lr, scal):
     """One whole iteration of the two-layer MLP GAN in one cluster launch (csrc/mlp_gan.cu); G, D are FlatParams."""
     _chk(real, real_oh, z1, oh1, z2, oh2, G.data, G.grad, G.m, G.v, D.data, D.grad, D.m, D.v, scal)
@@ -236,6 +309,7 @@ def mlp_gan_step(B, z_dim, label_dim, hidden, real, real_oh, z1, oh1, z2, oh2, G
                                      P(D.step), _f(lr), P(scal), _s()))
 
 
+@_op("u", "v", "Wn", "sigma", "WnT", "us", "vs")
 def spectral_norm_fwd(W, u, v, Wn, sigma, do_iter=True, eps=1e-12, WnT=None, us=None, vs=None):
     """One power iteration (in place on u, v), sigma, Wn = W / sigma; optionally Wn^T and snapshots of u, v."""
     N, K = W.shape
@@ -244,26 +318,31 @@ def spectral_norm_fwd(W, u, v, Wn, sigma, do_iter=True, eps=1e-12, WnT=None, us=
                                            P(vs), P(sigma), _s()))
 
 
+@_op("dW")
 def spectral_norm_bwd(dWn, Wn, u, v, sigma, dW):
     N, K = Wn.shape
     _lib.check(_L().pcg_spectral_norm_bwd(P(dWn), P(Wn), N, K, P(u), P(v), P(sigma), P(dW), _s()))
 
 
+@_op("y")
 def gumbel_softmax_fwd(logits, g, tau, y):
     rows, n = logits.shape
     _lib.check(_L().pcg_gumbel_softmax_fwd(P(logits), P(g), _ll(rows), n, _f(tau), P(y), _s()))
 
 
+@_op("dl")
 def softmax_bwd(dy, y, tau, dl):
     rows, n = y.shape
     _lib.check(_L().pcg_softmax_bwd(P(dy), P(y), _ll(rows), n, _f(tau), P(dl), _s()))
 
 
+@_op("loss", "dlogits")
 def ce_loss(logits, target, loss, dlogits, wgt=1.0):
     B, NC = logits.shape
     _lib.check(_L().pcg_ce_loss(P(logits), P(target), B, NC, _f(wgt), P(loss), P(dlogits), _s()))
 
 
+@_op("mask", "target", "rng_state")
 def build_mask(B, C, H, W, patch, num_modifiable_patches, mask, target=None, num_classes=10, seed=0, rng_state=None):
     """One launch: random patch mask [B,C,H,W] (+ target draw [B] int64); see include/pcg.h pcg_build_mask."""
     _chk(mask, target, rng_state)
@@ -272,6 +351,7 @@ def build_mask(B, C, H, W, patch, num_modifiable_patches, mask, target=None, num
                                    P(rng_state), P(mask), P(target), _s()))
 
 
+@_op("p", "m", "v", "step")
 def adam(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     _chk(p, g, m, v, step)
     _lib.check(_L().pcg_adam_flat(P(p), P(g), P(m), P(v), _ll(p.numel()), P(step), _f(lr), _f(beta1), _f(beta2), _f(eps),

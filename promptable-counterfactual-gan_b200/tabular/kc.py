@@ -186,7 +186,12 @@ class KcPlan:
         self.samples = OrderedDict((f, z(B, n)) for f, n in self.cat.items())
         self.dsamples = OrderedDict((f, z(B, n)) for f, n in self.cat.items())
         self.dlogits = OrderedDict((f, z(B, n)) for f, n in self.cat.items())
-        self.sval, self.dcol = z(B, 1), z(B, 1)
+        # per-head / per-block temporaries (not shared: a shared scratch tensor chains otherwise independent launches,
+        # which the data-flow capture would have to serialise)
+        self.svals = OrderedDict((f, z(B, 1)) for f in self.cat)
+        self.dcols = OrderedDict((f, z(B, 1)) for f in self.cat)
+        self.blk_tmp = [dict(dn2=z(B, h), du2=z(B, h), df=z(B, h), dn1=z(B, h), du1=z(B, h)) for _ in range(n_blocks)]
+        self.dz_r, self.dz_f = z(B, 1), z(B, 1)
         self.res, self.masked, self.xcf, self.om, self.rm = (z(B, d) for _ in range(5))
         self.d_rm, self.d_pen, self.d_l1, self.d_masked, self.d_res, self.dx_adv, self.dx_cls = (z(B, d) for _ in range(7))
         self.d_contp = z(B, len(self.cont))
@@ -265,8 +270,8 @@ class KcPlan:
         for i, f in enumerate(self.cont):
             K.copy_cols(self.cont_out, i, self.res, f, 1)
         for f in self.cat:
-            K.linear_fwd(self.samples[f], self.nv[f], self.sval)                 # onehot-like @ norm_vals
-            K.copy_cols(self.sval, 0, self.res, f, 1)
+            K.linear_fwd(self.samples[f], self.nv[f], self.svals[f])             # onehot-like @ norm_vals
+            K.copy_cols(self.svals[f], 0, self.res, f, 1)
             K.copy_cols(self.x, f, self.res, f, 1, alpha=-1.0, accumulate=True)  # - x[:, f]
         K.binary(self.res, self.mask, K.MUL, self.masked)
         K.binary(self.x, self.masked, K.ADD, self.xcf)
@@ -293,11 +298,11 @@ class KcPlan:
         K.binary(self.d_rm, self.om, K.MUL, self.d_pen)
         # ---- D update (:290-295)
         out_r = D.fwd(self.x, self.y_oh, 0)
-        K.gan_loss(out_r, K.GAN_WASSERSTEIN, 1.0, self.scal[7:8], self.dz, out_aux=self.scal[9:10])
-        D.bwd(self.dz, 0, D.g1)
+        K.gan_loss(out_r, K.GAN_WASSERSTEIN, 1.0, self.scal[7:8], self.dz_r, out_aux=self.scal[9:10])
+        D.bwd(self.dz_r, 0, D.g1)
         out_f = D.fwd(self.xcf, self.t_oh, 1)
-        K.gan_loss(out_f, K.GAN_WASSERSTEIN, 0.0, self.scal[8:9], self.dz)
-        D.bwd(self.dz, 1, D.g2)
+        K.gan_loss(out_f, K.GAN_WASSERSTEIN, 0.0, self.scal[8:9], self.dz_f)
+        D.bwd(self.dz_f, 1, D.g2)
         K.binary(D.flat.grad, D.grad2, K.ADD, D.flat.grad)
         K.combine([(1.0, self.scal[7:8]), (1.0, self.scal[8:9])], self.scal[0:1])
         D.flat.adam_step(self.lr_d)
@@ -340,22 +345,22 @@ class KcPlan:
         self.fc_cont.wgrad(h, self.d_contp)
         self.fc_cont.dgrad(self.d_contp, self.dhA)
         for f, head in self.heads.items():
-            K.copy_cols(self.d_res, f, self.dcol, 0, 1)
-            K.linear_dgrad(self.dcol, self.nv[f].view(-1, 1), self.dsamples[f], self.cat[f])   # d samples = d scalar * norm_vals
+            K.copy_cols(self.d_res, f, self.dcols[f], 0, 1)
+            K.linear_dgrad(self.dcols[f], self.nv[f].view(-1, 1), self.dsamples[f], self.cat[f])   # d samples = d scalar * norm_vals
             K.softmax_bwd(self.dsamples[f], self.samples[f], self.tau, self.dlogits[f])
             head.wgrad(h, self.dlogits[f])
             head.dgrad(self.dlogits[f], self.dhA, add_src=self.dhA)
         dh, other = self.dhA, self.dhB
-        for b in reversed(self.blk):
+        for b, t in zip(reversed(self.blk), reversed(self.blk_tmp)):
             # f2 = g*n2 + b ; h' = h + f2
-            K.film_bwd(dh, b["g"], b["n2"], self.dn, b["dg"], b["db"])               # d n2, d g / d b (first use)
-            b["bn2"].bwd(self.dn, b["u2"], self.du)
-            b["fc2"].wgrad(b["r1"], self.du)
-            b["fc2"].dgrad(self.du, self.df, act_ref=b["r1"], ref_act=K.ACT_RELU)     # d f1 (through the ReLU)
-            K.film_bwd(self.df, b["g"], b["n1"], self.dn, b["dg"], b["db"], accumulate=True)   # d n1, d g / d b (+=)
-            b["bn1"].bwd(self.dn, b["u1"], self.du)
-            b["fc1"].wgrad(b["hin"], self.du)
-            b["fc1"].dgrad(self.du, other, add_src=dh)           # skip connection
+            K.film_bwd(dh, b["g"], b["n2"], t["dn2"], b["dg"], b["db"])              # d n2, d g / d b (first use)
+            b["bn2"].bwd(t["dn2"], b["u2"], t["du2"])
+            b["fc2"].wgrad(b["r1"], t["du2"])
+            b["fc2"].dgrad(t["du2"], t["df"], act_ref=b["r1"], ref_act=K.ACT_RELU)    # d f1 (through the ReLU)
+            K.film_bwd(t["df"], b["g"], b["n1"], t["dn1"], b["dg"], b["db"], accumulate=True)   # d n1, d g / d b (+=)
+            b["bn1"].bwd(t["dn1"], b["u1"], t["du1"])
+            b["fc1"].wgrad(b["hin"], t["du1"])
+            b["fc1"].dgrad(t["du1"], other, add_src=dh)          # skip connection
             b["fg"].wgrad(self.cond, b["dg"])
             b["fb"].wgrad(self.cond, b["db"])
             dh, other = other, dh

@@ -3,6 +3,7 @@ BatchNorm1d, the spectral-norm MLP critic shared by both tabular CounteRGANs, gr
 enqueues libpcg kernels (pcg_b200.ops); gradients are written into FlatParams arenas."""
 import torch
 
+from .. import dataflow
 from .. import graphs
 from .. import ops as K
 
@@ -31,11 +32,21 @@ class Ctx:
         return torch.zeros(*s, device=self.dev)
 
 
-class Dense:
+class _OwnScratch:
+    """Per-layer weight-gradient / column-sum scratch: layers that share one buffer are serialised by it (write after
+    write), and the weight gradients are exactly the launches the data-flow capture can take off the critical path."""
+
+    def _own_scratch(self, ctx, k_in, n_out):
+        self.wsc = torch.zeros(K.conv_wgrad_scratch_floats(ctx.B, 1, 1, k_in, n_out, 1, 1, 0) + 1024, device=ctx.dev)
+        self.stat = K.stat_scratch(max(n_out, 4), ctx.dev)
+
+
+class Dense(_OwnScratch):
     def __init__(self, ctx, flat, name, k_in, n_out):
         self.ctx, self.flat, self.name, self.k, self.n = ctx, flat, name, k_in, n_out
         self.wT = ctx.z(k_in, n_out)
         ctx.reserve_wgrad(k_in, n_out)
+        self._own_scratch(ctx, k_in, n_out)
 
     def W(self):
         return self.flat.p(self.name + ".weight")
@@ -53,8 +64,7 @@ class Dense:
         K.linear_dgrad(dy, self.wT, dx, self.k, **kw)
 
     def wgrad(self, x, dy):
-        K.linear_wgrad(x, dy, self.ctx.wsc, self.flat.g(self.name + ".weight"), self.flat.g(self.name + ".bias"),
-                       self.ctx.stat)
+        K.linear_wgrad(x, dy, self.wsc, self.flat.g(self.name + ".weight"), self.flat.g(self.name + ".bias"), self.stat)
 
 
 class BN1d:
@@ -80,7 +90,7 @@ class BN1d:
                        self.flat.g(self.name + ".weight"), self.flat.g(self.name + ".bias"), act=act)
 
 
-class SNDense:
+class SNDense(_OwnScratch):
     """spectral_norm(nn.Linear) (torch/nn/utils/spectral_norm.py): one power iteration per forward call in train mode,
     in place on the module's u / v; each of the plan's forward passes keeps its own snapshot (u, v, sigma, W/sigma)
     because torch's graph holds clones taken at call time."""
@@ -89,13 +99,14 @@ class SNDense:
         self.ctx, self.flat, self.name, self.k, self.n = ctx, flat, name, k_in, n_out
         z = ctx.z
         ctx.reserve_wgrad(k_in, n_out)
+        self._own_scratch(ctx, k_in, n_out)
         self.u, self.v = z(n_out), z(k_in)
         self.Wn = [z(n_out, k_in) for _ in range(passes)]
         self.WnT = [z(k_in, n_out) for _ in range(passes)]
         self.sigma = [z(1) for _ in range(passes)]
         self.us = [z(n_out) for _ in range(passes)]
         self.vs = [z(k_in) for _ in range(passes)]
-        self.dWn = z(n_out, k_in)
+        self.dWn = [z(n_out, k_in) for _ in range(passes)]
 
     def W(self):
         return self.flat.p(self.name + ".weight_orig")
@@ -115,8 +126,8 @@ class SNDense:
 
     def wgrad(self, x, dy, p, garena):
         """garena(name) -> gradient slot.  dW_orig = (dWn - <dWn, Wn> u v^T) / sigma."""
-        K.linear_wgrad(x, dy, self.ctx.wsc, self.dWn, garena(self.name + ".bias"), self.ctx.stat)
-        K.spectral_norm_bwd(self.dWn, self.Wn[p], self.us[p], self.vs[p], self.sigma[p], garena(self.name + ".weight_orig"))
+        K.linear_wgrad(x, dy, self.wsc, self.dWn[p], garena(self.name + ".bias"), self.stat)
+        K.spectral_norm_bwd(self.dWn[p], self.Wn[p], self.us[p], self.vs[p], self.sigma[p], garena(self.name + ".weight_orig"))
 
 
 class Critic:
@@ -134,7 +145,7 @@ class Critic:
         self.layers = [SNDense(ctx, self.flat, f"net.{2 * i}", a, b) for i, (a, b) in enumerate(dims)]
         self.din = [ctx.z(B, dims[0][0]) for _ in range(2)]
         self.h = [[ctx.z(B, b) for (_, b) in dims] for _ in range(2)]
-        self.dh = [ctx.z(B, b) for (_, b) in dims]
+        self.dh = [[ctx.z(B, b) for (_, b) in dims] for _ in range(2)]
         self.ddin = ctx.z(B, dims[0][0])
 
     def adopt(self, module):
@@ -169,8 +180,8 @@ class Critic:
                 if want_dx:
                     L.dgrad(d, self.ddin, p)
                 break
-            L.dgrad(d, self.dh[i - 1], p, act_ref=self.h[p][i - 1], ref_act=K.ACT_LRELU, ref_slope=0.2)
-            d = self.dh[i - 1]
+            L.dgrad(d, self.dh[p][i - 1], p, act_ref=self.h[p][i - 1], ref_act=K.ACT_LRELU, ref_slope=0.2)
+            d = self.dh[p][i - 1]
         return self.ddin
 
     def g1(self, n):
@@ -181,10 +192,15 @@ class Critic:
 
 
 class GraphStep:
-    """Runs ``body`` eagerly once on a state snapshot (module loads, attribute setting), then replays a CUDA graph."""
+    """Runs ``body`` eagerly once on a state snapshot (module loads, attribute setting), then replays a CUDA graph.
+    ``parallel`` (default, PCG_DATAFLOW=0 turns it off): the graph is captured from the body's recorded data flow
+    (pcg_b200.dataflow) - every operator waits only for the operators whose memory it touches - instead of as one chain."""
 
-    def __init__(self, body, state_tensors, refresh, use_graph=True):
+    def __init__(self, body, state_tensors, refresh, use_graph=True, parallel=None):
+        import os
         self.body, self.state, self.refresh, self.use_graph, self.graph = body, state_tensors, refresh, use_graph, None
+        self.parallel = (os.environ.get("PCG_DATAFLOW", "1") != "0") if parallel is None else bool(parallel)
+        self.program = None
 
     def __call__(self):
         if not self.use_graph:
@@ -198,5 +214,9 @@ class GraphStep:
                 dst.copy_(src)
             self.refresh()
             torch.cuda.synchronize()
-            self.graph = graphs.capture(self.body)
+            if self.parallel:
+                self.program = dataflow.record(self.body)
+                self.graph = graphs.capture(self.program.emit)
+            else:
+                self.graph = graphs.capture(self.body)
         self.graph.replay()

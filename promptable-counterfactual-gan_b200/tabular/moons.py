@@ -108,6 +108,7 @@ class MoonsPlan:
         self.raw, self.masked, self.xcf, self.om, self.rm = (z(B, input_dim) for _ in range(5))
         self.d_rm, self.d_pen, self.d_l1, self.d_l2, self.d_masked, self.d_raw, self.dx_adv, self.dx_cls = (z(B, input_dim) for _ in range(8))
         self.dz = z(B, 1)
+        self.dz_r, self.dz_f = z(B, 1), z(B, 1)
         # classifier activations
         self.c0, self.c1, self.clog, self.cdlog = z(B, h), z(B, h), z(B, nc), z(B, nc)
         self.cd1, self.cd0 = z(B, h), z(B, h)
@@ -169,11 +170,11 @@ class MoonsPlan:
         K.binary(self.d_rm, self.om, K.MUL, self.d_pen)
         # ---- D update (:72-77)
         out_r = D.fwd(self.x, self.y_oh, 0)
-        K.gan_loss(out_r, K.GAN_WASSERSTEIN, 1.0, self.scal[7:8], self.dz, out_aux=self.scal[9:10])
-        D.bwd(self.dz, 0, D.g1)
+        K.gan_loss(out_r, K.GAN_WASSERSTEIN, 1.0, self.scal[7:8], self.dz_r, out_aux=self.scal[9:10])
+        D.bwd(self.dz_r, 0, D.g1)
         out_f = D.fwd(self.xcf, self.t_oh, 1)
-        K.gan_loss(out_f, K.GAN_WASSERSTEIN, 0.0, self.scal[8:9], self.dz, out_aux=self.scal[10:11])
-        D.bwd(self.dz, 1, D.g2)
+        K.gan_loss(out_f, K.GAN_WASSERSTEIN, 0.0, self.scal[8:9], self.dz_f, out_aux=self.scal[10:11])
+        D.bwd(self.dz_f, 1, D.g2)
         K.binary(D.flat.grad, D.grad2, K.ADD, D.flat.grad)
         K.combine([(1.0, self.scal[7:8]), (1.0, self.scal[8:9])], self.scal[0:1])
         D.flat.adam_step(self.lr_d)
