@@ -85,7 +85,10 @@ int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int 
     c1k4_wgrad(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), scratch, dw, ST);
     return 0;
   }
-  if (Cin % 4 == 0 && skinny_on() && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+  // (the weight-gradient kernel parallelises over columns only: it needs K >= 4096 to fill the GPU; a critic's last
+  // Linear(128, 1) over 4096 samples stays on the generic split-K kernel)
+  if (Cin % 4 == 0 && skinny_on() && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad)) &&
+      geom(N, H, W, Cin, Cout, k, stride, pad).K() >= 4096) {
     full1_wgrad(in, dout, geom(N, H, W, Cin, Cout, k, stride, pad), dw, ST);
     return 0;
   }
@@ -120,6 +123,11 @@ int pcg_bn_train_fwd(const float* y, long long M, int C, const float* gamma, con
                      float* running_mean, float* running_var, long long* nbt, float* mean, float* rstd, float* scale,
                      float* shift, int act, float slope, float* z, float* scratch, void* stream) {
   PCG_API_BEGIN
+  if (skinny_on() && bn_cluster_supported(M, C)) {
+    bn_cluster_fwd(y, M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, rstd, scale, shift, act, slope, z,
+                   ST);
+    return 0;
+  }
   bn_stats_partial<float>(y, M, C, scratch, ST);
   bn_finalize(scratch, STAT_PARTS, M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, rstd, scale,
               shift, ST);
@@ -131,6 +139,10 @@ int pcg_bn_train_bwd(const float* dz, const float* y, long long M, int C, const 
                      float* dy, float* dgamma, float* dbeta, float* dbias_prev, float* c12, float* scratch,
                      float* scratch2, void* stream) {
   PCG_API_BEGIN
+  if (skinny_on() && bn_cluster_supported(M, C)) {
+    bn_cluster_bwd(dz, y, M, C, gamma, mean, rstd, scale, shift, gscale, act, slope, dy, dgamma, dbeta, dbias_prev, ST);
+    return 0;
+  }
   bn_bwd_partial<float>(dz, y, mean, rstd, scale, shift, gscale, act, slope, M, C, scratch, ST);
   bn_bwd_finalize(scratch, STAT_PARTS, M, C, dgamma, dbeta, c12, ST);
   bn_bwd_apply<float>(dz, y, mean, rstd, scale, shift, gamma, c12, gscale, act, slope, M, C, dy, scratch2, ST);

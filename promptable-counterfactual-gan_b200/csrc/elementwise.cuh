@@ -108,4 +108,14 @@ void fill_zero(T* p, long long n, cudaStream_t s);
 template <typename T>
 void convert_from_f32(const float* src, long long n, T* dst, cudaStream_t s);
 
+// Train-mode BatchNorm of a small [M][C] problem as ONE cluster launch (bn_cluster.cu); same contract as the three-launch
+// pipelines above.  bn_cluster_supported: C a power of two <= 256 and M small enough for the rows to stay in registers.
+bool bn_cluster_supported(long long M, int C);
+void bn_cluster_fwd(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, long long* nbt, float* mean, float* rstd, float* scale,
+                    float* shift, int act, float slope, float* z, cudaStream_t s);
+void bn_cluster_bwd(const float* dz, const float* y, long long M, int C, const float* gamma, const float* mean,
+                    const float* rstd, const float* scale, const float* shift, float gscale, int act, float slope, float* dy,
+                    float* dgamma, float* dbeta, float* dbias_prev, cudaStream_t s);
+
 }  // namespace pcg
