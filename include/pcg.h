@@ -356,6 +356,13 @@ int pcg_u8_batch(const unsigned char* images, const long long* labels, const lon
  * tests).  Same distribution as the reference, not the same stream. */
 int pcg_build_mask(int B, int C, int H, int W, int patch, int num_modifiable_patches, int num_classes,
                    unsigned long long seed, unsigned long long* rng_state, float* mask, long long* target, void* stream);
+/* Keep-mask of nn.Dropout(p) / nn.Dropout2d(p) in training mode (conditional_counteRGAN/mnist/models/classifier.py:14,19,
+ * house_sales_kc_usa/models/nn_classifier.py): mask[rows][inner][C] (NHWC: inner = H*W) = Bernoulli(1 - p) / (1 - p);
+ * channelwise != 0 draws once per (row, c) and repeats it over `inner` (Dropout2d zeroes whole feature maps).  The
+ * activation is multiplied by the mask in the forward pass and its gradient in the backward pass.  rng_state as in
+ * pcg_build_mask. */
+int pcg_dropout_mask(long long rows, int inner, int C, float p, int channelwise, unsigned long long seed,
+                     unsigned long long* rng_state, float* mask, void* stream);
 
 #ifdef __cplusplus
 }

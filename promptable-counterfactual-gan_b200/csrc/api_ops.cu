@@ -287,6 +287,12 @@ int pcg_u8_batch(const unsigned char* images, const long long* labels, const lon
   u8_batch(images, labels, index, B, HW, mean, stdv, x, y, ST);
   PCG_API_END
 }
+int pcg_dropout_mask(long long rows, int inner, int C, float p, int channelwise, unsigned long long seed,
+                     unsigned long long* rng_state, float* mask, void* stream) {
+  PCG_API_BEGIN
+  dropout_mask(rows, inner, C, p, channelwise, seed, rng_state, mask, ST);
+  PCG_API_END
+}
 int pcg_build_mask(int B, int C, int H, int W, int patch, int num_modifiable_patches, int num_classes,
                    unsigned long long seed, unsigned long long* rng_state, float* mask, long long* target, void* stream) {
   PCG_API_BEGIN

@@ -624,6 +624,61 @@ __global__ void build_mask_kernel(int B, int C, int H, int W, int nph, int npw, 
     }
   }
 }
+// ---- dropout keep-mask (nn.Dropout / nn.Dropout2d in training mode: mnist/models/classifier.py:14,19) ------------------
+// mask[row][inner][c] = Bernoulli(1 - p) / (1 - p); channelwise (Dropout2d): one draw per (row, c), repeated over `inner`.
+// Same Philox stream convention as build_mask (key = seed + rng[2], offset rng[0], advanced by the last block).
+__global__ void dropout_mask_kernel(long long rows, int inner, int C, float p, int channelwise, unsigned long long seed,
+                                    unsigned long long* __restrict__ rng, float* __restrict__ mask) {
+  pdl_enter();
+  const unsigned long long offset = rng != nullptr ? rng[0] : 0ull;
+  if (rng != nullptr) seed += rng[2];
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const float keep = 1.f / (1.f - p);
+  const long long draws = channelwise ? rows * C : rows * inner * C;       // one 32-bit draw each, four per Philox call
+  const long long calls = (draws + 3) / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < calls; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32) | 0x80000000u, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+    const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long d = i * 4 + j;
+      if (d >= draws) break;
+      // uniform in [0, 1): keep when u >= p (torch's bernoulli_(1 - p) keeps with probability 1 - p)
+      const float u = (float)(rv[j] >> 8) * (1.f / 16777216.f);
+      const float v = u >= p ? keep : 0.f;
+      if (channelwise) {
+        const long long row = d / C;
+        const int c = (int)(d - row * C);
+        float* dst = mask + row * inner * C + c;
+        for (int k = 0; k < inner; ++k) dst[(long long)k * C] = v;
+      } else {
+        mask[d] = v;
+      }
+    }
+  }
+  if (rng != nullptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long ticket = atomicAdd(rng + 1, 1ull);
+      if (ticket == (unsigned long long)gridDim.x - 1ull) {
+        rng[1] = 0ull;
+        rng[0] = offset + 1ull;
+        __threadfence();
+      }
+    }
+  }
+}
+void dropout_mask(long long rows, int inner, int C, float p, int channelwise, unsigned long long seed, unsigned long long* rng,
+                  float* mask, cudaStream_t s) {
+  PCG_PROFILE("dropout_mask", s);
+  PCG_REQUIRE(rows >= 1 && inner >= 1 && C >= 1 && p >= 0.f && p < 1.f, "dropout geometry / probability");
+  const long long draws = channelwise ? rows * C : rows * inner * C;
+  launch_k(dropout_mask_kernel, dim3(blocks_for((draws + 3) / 4)), dim3(256), 0, s, rows, inner, C, p, channelwise, seed, rng, mask);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 void build_mask(int B, int C, int H, int W, int patch, int k_sel, int num_classes, unsigned long long seed,
                 unsigned long long* rng, float* mask, long long* target, cudaStream_t s) {
   PCG_PROFILE("build_mask", s);

@@ -57,6 +57,9 @@ void u8_batch(const uint8_t* images, const long long* labels, const long long* i
 // mask[B][C][H][W] in {0,1}: k_sel of the (H/patch)*(W/patch) patches per sample chosen uniformly at random (k_sel < 0 or
 // >= total: independent fair coins), nearest-upsampled; target[b] ~ U{0..num_classes-1} (nullptr: no draw).
 // rng = device {stream offset, ticket} (advanced by the kernel) or nullptr (offset 0).
+// mask[rows][inner][C] = Bernoulli(1 - p) / (1 - p) (nn.Dropout); channelwise: one draw per (row, c) (nn.Dropout2d)
+void dropout_mask(long long rows, int inner, int C, float p, int channelwise, unsigned long long seed, unsigned long long* rng,
+                  float* mask, cudaStream_t s);
 void build_mask(int B, int C, int H, int W, int patch, int k_sel, int num_classes, unsigned long long seed,
                 unsigned long long* rng, float* mask, long long* target, cudaStream_t s);
 

@@ -342,6 +342,16 @@ def ce_loss(logits, target, loss, dlogits, wgt=1.0):
     _lib.check(_L().pcg_ce_loss(P(logits), P(target), B, NC, _f(wgt), P(loss), P(dlogits), _s()))
 
 
+@_op("mask", "rng_state")
+def dropout_mask(mask, p, channelwise=False, seed=0, rng_state=None):
+    """mask [rows, ..., C] = Bernoulli(1 - p) / (1 - p); channelwise: one draw per (row, channel) (nn.Dropout2d on NHWC)."""
+    _chk(mask, rng_state)
+    rows, C = mask.shape[0], mask.shape[-1]
+    inner = mask.numel() // (rows * C)
+    _lib.check(_L().pcg_dropout_mask(_ll(rows), inner, C, _f(p), 1 if channelwise else 0,
+                                     ctypes.c_ulonglong(seed & (2 ** 64 - 1)), P(rng_state), P(mask), _s()))
+
+
 @_op("mask", "target", "rng_state")
 def build_mask(B, C, H, W, patch, num_modifiable_patches, mask, target=None, num_classes=10, seed=0, rng_state=None):
     """One launch: random patch mask [B,C,H,W] (+ target draw [B] int64); see include/pcg.h pcg_build_mask."""
