@@ -335,6 +335,16 @@ int pcg_ce_loss(const float* logits, const long long* target, int B, int NC, flo
 int pcg_adam_flat(float* p, const float* g, float* m, float* v, long long n, int* step, float lr, float beta1,
                   float beta2, float eps, float grad_scale, void* stream);
 
+/* nn.CrossEntropyLoss(weight=class_weights) with mean reduction (house_sales_kc_usa/trainer.py:58): loss =
+ * sum_n w[t_n] nll_n / sum_n w[t_n]; dlogits (may be NULL) its gradient; correct (may be NULL) = number of rows whose
+ * arg-max equals the target (trainer.py:93-95).  class_weights == NULL: unweighted mean. */
+int pcg_ce_loss_weighted(const float* logits, const long long* target, const float* class_weights, int B, int NC,
+                         float* loss, float* dlogits, float* correct, void* stream);
+/* torch.optim.AdamW on a flat buffer (trainer.py:60): p *= 1 - lr*weight_decay, then the Adam update; lr is read from
+ * DEVICE memory (lr_dev[0]) so a scheduler (ReduceLROnPlateau, trainer.py:61) can change it under a captured graph. */
+int pcg_adamw_flat(float* p, const float* g, float* m, float* v, long long n, int* step, const float* lr_dev, float beta1,
+                   float beta2, float eps, float weight_decay, void* stream);
+
 /* On-device input pipeline, replaces DataLoader + transforms.ToTensor() + transforms.Normalize((mean,), (std,)) of
  * conditional_counteRGAN/mnist/data_utils.py:9-12,26 for a dataset kept resident in HBM as uint8 [N][HW] (HW % 16 == 0):
  *   x[b][.] = (float(images[index[b]][.]) / 255 - mean) / std  (bit-identical to torchvision),  y[b] = labels[index[b]];

@@ -281,6 +281,18 @@ int pcg_ce_loss(const float* logits, const long long* target, int B, int NC, flo
   ce_loss(logits, target, B, NC, wgt, loss, dlogits, ST);
   PCG_API_END
 }
+int pcg_ce_loss_weighted(const float* logits, const long long* target, const float* class_weights, int B, int NC,
+                         float* loss, float* dlogits, float* correct, void* stream) {
+  PCG_API_BEGIN
+  ce_loss_weighted(logits, target, class_weights, B, NC, loss, dlogits, correct, ST);
+  PCG_API_END
+}
+int pcg_adamw_flat(float* p, const float* g, float* m, float* v, long long n, int* step, const float* lr_dev, float beta1,
+                   float beta2, float eps, float weight_decay, void* stream) {
+  PCG_API_BEGIN
+  adamw_flat(p, g, m, v, n, step, lr_dev, beta1, beta2, eps, weight_decay, ST);
+  PCG_API_END
+}
 int pcg_u8_batch(const unsigned char* images, const long long* labels, const long long* index, int B, int HW, float mean,
                  float stdv, float* x, long long* y, void* stream) {
   PCG_API_BEGIN

@@ -952,6 +952,55 @@ void ce_loss(const float* logits, const long long* target, int B, int NC, float 
   PCG_LAUNCH_CHECK();
 }
 
+// CrossEntropyLoss(weight = w) with mean reduction (torch: sum_n w[t_n] * nll_n / sum_n w[t_n]; w == nullptr: plain mean)
+// + optionally the number of rows whose arg-max is the target (the accuracy counters of
+// house_sales_kc_usa/trainer.py:92-95,110-112).  One block; deterministic.
+__global__ void ce_loss_weighted_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                        const float* __restrict__ w, int B, int NC, float* loss,
+                                        float* __restrict__ dlogits, float* correct) {
+  pdl_enter();
+  __shared__ float red[32];
+  __shared__ float s_wsum;
+  float sw = 0.f;
+  for (int n = threadIdx.x; n < B; n += blockDim.x) sw += w ? w[(int)target[n]] : 1.f;
+  sw = block_sum_1024(sw, red);
+  if (threadIdx.x == 0) s_wsum = sw;
+  __syncthreads();
+  const float wsum = s_wsum;
+  float sl = 0.f, sc = 0.f;
+  for (int n = threadIdx.x; n < B; n += blockDim.x) {
+    const float* l = logits + (size_t)n * NC;
+    float mx = l[0];
+    int am = 0;
+    for (int j = 1; j < NC; ++j)
+      if (l[j] > mx) { mx = l[j]; am = j; }
+    float se = 0.f;
+    for (int j = 0; j < NC; ++j) se += expf(l[j] - mx);
+    const float lse = mx + logf(se);
+    const int t = (int)target[n];
+    const float wn = w ? w[t] : 1.f;
+    sl += wn * (lse - l[t]);
+    sc += am == t ? 1.f : 0.f;
+    if (dlogits != nullptr)
+      for (int j = 0; j < NC; ++j) dlogits[(size_t)n * NC + j] = wn * (expf(l[j] - lse) - (j == t ? 1.f : 0.f)) / wsum;
+  }
+  __syncthreads();
+  sl = block_sum_1024(sl, red);
+  __syncthreads();
+  sc = block_sum_1024(sc, red);
+  if (threadIdx.x == 0) {
+    loss[0] = sl / wsum;
+    if (correct != nullptr) correct[0] = sc;
+  }
+}
+void ce_loss_weighted(const float* logits, const long long* target, const float* w, int B, int NC, float* loss,
+                      float* dlogits, float* correct, cudaStream_t s) {
+  PCG_PROFILE("small", s);
+  launch_k(ce_loss_weighted_kernel, dim3(1), dim3(256), 0, s, logits, target, w, B, NC, loss, dlogits, correct);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 __global__ void l1_finalize_kernel(const float* __restrict__ part, int nparts, float inv_n, float* out2) {
   pdl_enter();
   const int c = threadIdx.x >> 5;
@@ -1016,6 +1065,45 @@ void adam_flat(float* p, const float* g, float* m, float* v, long long n, int* s
                float beta2, float eps, float grad_scale, cudaStream_t s) {
   PCG_PROFILE("adam", s);
   launch_k(adam_flat_kernel, dim3(ew_blocks(n)), dim3(256), 0, s, p, g, m, v, n, step, lr, beta1, beta2, eps, grad_scale);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+  launch_k(adam_step_inc_kernel, dim3(1), dim3(1), 0, s, step);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// torch.optim.AdamW (decoupled weight decay, optim/adamw.py: param.mul_(1 - lr * weight_decay), then the Adam update).
+// The learning rate is read from device memory so that a scheduler (ReduceLROnPlateau, house_sales_kc_usa/trainer.py:61)
+// can change it between replays of a captured graph.
+__global__ void __launch_bounds__(256)
+adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  long long n, const int* __restrict__ step, const float* __restrict__ lr_dev, float beta1, float beta2,
+                  float eps, float weight_decay) {
+  pdl_enter();
+  __shared__ float s_step_size, s_bc2_sqrt, s_decay;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step + 1), lr = (double)lr_dev[0];
+    s_step_size = (float)(lr / (1.0 - pow((double)beta1, t)));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    s_decay = 1.f - lr_dev[0] * weight_decay;
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt, decay = s_decay;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.f - beta1);
+    vi = vi * beta2 + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] * decay - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+void adamw_flat(float* p, const float* g, float* m, float* v, long long n, int* step, const float* lr_dev, float beta1,
+                float beta2, float eps, float weight_decay, cudaStream_t s) {
+  PCG_PROFILE("adam", s);
+  launch_k(adamw_flat_kernel, dim3(ew_blocks(n)), dim3(256), 0, s, p, g, m, v, n, step, lr_dev, beta1, beta2, eps, weight_decay);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
   launch_k(adam_step_inc_kernel, dim3(1), dim3(1), 0, s, step);

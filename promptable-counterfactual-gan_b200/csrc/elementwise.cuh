@@ -108,6 +108,10 @@ void fill_zero(T* p, long long n, cudaStream_t s);
 template <typename T>
 void convert_from_f32(const float* src, long long n, T* dst, cudaStream_t s);
 
+void ce_loss_weighted(const float* logits, const long long* target, const float* w, int B, int NC, float* loss,
+                      float* dlogits, float* correct, cudaStream_t s);
+void adamw_flat(float* p, const float* g, float* m, float* v, long long n, int* step, const float* lr_dev, float beta1,
+                float beta2, float eps, float weight_decay, cudaStream_t s);
 // Train-mode BatchNorm of a small [M][C] problem as ONE cluster launch (bn_cluster.cu); same contract as the three-launch
 // pipelines above.  bn_cluster_supported: C a power of two <= 256 and M small enough for the rows to stay in registers.
 bool bn_cluster_supported(long long M, int C);

@@ -361,6 +361,20 @@ def build_mask(B, C, H, W, patch, num_modifiable_patches, mask, target=None, num
                                    P(rng_state), P(mask), P(target), _s()))
 
 
+@_op("loss", "dlogits", "correct")
+def ce_loss_weighted(logits, target, class_weights, loss, dlogits=None, correct=None):
+    B, NC = logits.shape
+    _chk(logits, target, class_weights, loss, dlogits, correct)
+    _lib.check(_L().pcg_ce_loss_weighted(P(logits), P(target), P(class_weights), B, NC, P(loss), P(dlogits), P(correct), _s()))
+
+
+@_op("p", "m", "v", "step")
+def adamw(p, g, m, v, step, lr_dev, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2):
+    _chk(p, g, m, v, step, lr_dev)
+    _lib.check(_L().pcg_adamw_flat(P(p), P(g), P(m), P(v), _ll(p.numel()), P(step), P(lr_dev), _f(beta1), _f(beta2), _f(eps),
+                                   _f(weight_decay), _s()))
+
+
 @_op("p", "m", "v", "step")
 def adam(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     _chk(p, g, m, v, step)
