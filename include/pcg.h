@@ -366,6 +366,16 @@ int pcg_u8_batch(const unsigned char* images, const long long* labels, const lon
  * tests).  Same distribution as the reference, not the same stream. */
 int pcg_build_mask(int B, int C, int H, int W, int patch, int num_modifiable_patches, int num_classes,
                    unsigned long long seed, unsigned long long* rng_state, float* mask, long long* target, void* stream);
+/* Counterfactual evaluation metrics of conditional_counteRGAN/mnist/eval_utils.py:46-75 (evaluate_counterfactuals) and
+ * house_sales_kc_usa/eval_utils.py:232-262:  pcg_cf_apply: x_cf = clamp(x + residual, lo, hi) over n elements and the
+ * partial sums of |x_cf - x| into scratch (pcg_cf_scratch_floats() floats);  pcg_cf_metrics (after the classifier ran on
+ * x_cf): out3 = {class-flip rate = mean(argmax logits == y_target), prediction gain = mean(softmax[y_target] -
+ * softmax[y_true]), actionability = sum |x_cf - x| / n_elems}. */
+int pcg_cf_scratch_floats(void);
+int pcg_cf_apply(const float* x, const float* residual, long long n, float lo, float hi, float* x_cf, float* scratch,
+                 void* stream);
+int pcg_cf_metrics(const float* logits, const long long* y_true, const long long* y_target, int B, int NC,
+                   const float* scratch, long long n_elems, float* out3, void* stream);
 /* Keep-mask of nn.Dropout(p) / nn.Dropout2d(p) in training mode (conditional_counteRGAN/mnist/models/classifier.py:14,19,
  * house_sales_kc_usa/models/nn_classifier.py): mask[rows][inner][C] (NHWC: inner = H*W) = Bernoulli(1 - p) / (1 - p);
  * channelwise != 0 draws once per (row, c) and repeats it over `inner` (Dropout2d zeroes whole feature maps).  The

@@ -299,6 +299,19 @@ int pcg_u8_batch(const unsigned char* images, const long long* labels, const lon
   u8_batch(images, labels, index, B, HW, mean, stdv, x, y, ST);
   PCG_API_END
 }
+int pcg_cf_scratch_floats(void) { return cf_parts(); }
+int pcg_cf_apply(const float* x, const float* residual, long long n, float lo, float hi, float* x_cf, float* scratch,
+                 void* stream) {
+  PCG_API_BEGIN
+  cf_apply(x, residual, n, lo, hi, x_cf, scratch, ST);
+  PCG_API_END
+}
+int pcg_cf_metrics(const float* logits, const long long* y_true, const long long* y_target, int B, int NC,
+                   const float* scratch, long long n_elems, float* out3, void* stream) {
+  PCG_API_BEGIN
+  cf_metrics(logits, y_true, y_target, B, NC, scratch, n_elems, out3, ST);
+  PCG_API_END
+}
 int pcg_dropout_mask(long long rows, int inner, int C, float p, int channelwise, unsigned long long seed,
                      unsigned long long* rng_state, float* mask, void* stream) {
   PCG_API_BEGIN

@@ -624,6 +624,76 @@ __global__ void build_mask_kernel(int B, int C, int H, int W, int nph, int npw, 
     }
   }
 }
+// ---- counterfactual evaluation (conditional_counteRGAN/mnist/eval_utils.py:46-75) -----------------------------------
+// x_cf = clamp(x + residual, lo, hi) and the per-block partial of sum |x_cf - x| (actionability numerator)
+__global__ void cf_apply_kernel(const float* __restrict__ x, const float* __restrict__ r, long long n, float lo, float hi,
+                                float* __restrict__ x_cf, float* __restrict__ part) {
+  pdl_enter();
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    const float c = fminf(fmaxf(xv + r[i], lo), hi);
+    x_cf[i] = c;
+    s += fabsf(c - xv);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    part[blockIdx.x] = t;
+  }
+}
+// out[0] = class-flip rate (arg-max of logits == target), out[1] = mean(softmax[target] - softmax[true]),
+// out[2] = mean |x_cf - x| from the partials of cf_apply_kernel.  One block, fixed order.
+__global__ void cf_metrics_kernel(const float* __restrict__ logits, const long long* __restrict__ y_true,
+                                  const long long* __restrict__ y_target, int B, int NC, const float* __restrict__ part,
+                                  int nparts, long long n_elems, float* __restrict__ out) {
+  pdl_enter();
+  __shared__ double red[3][8];
+  double flips = 0.0, gain = 0.0, act = 0.0;
+  for (int n = threadIdx.x; n < B; n += blockDim.x) {
+    const float* l = logits + (size_t)n * NC;
+    float mx = l[0];
+    int am = 0;
+    for (int j = 1; j < NC; ++j)
+      if (l[j] > mx) { mx = l[j]; am = j; }
+    float se = 0.f;
+    for (int j = 0; j < NC; ++j) se += expf(l[j] - mx);
+    const int t = (int)y_target[n], y = (int)y_true[n];
+    flips += am == t ? 1.0 : 0.0;
+    gain += (double)((expf(l[t] - mx) - expf(l[y] - mx)) / se);
+  }
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) act += (double)part[i];
+  flips = warp_sum(flips); gain = warp_sum(gain); act = warp_sum(act);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = flips; red[1][threadIdx.x >> 5] = gain; red[2][threadIdx.x >> 5] = act; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; }
+    out[0] = (float)(a / (double)B);
+    out[1] = (float)(b / (double)B);
+    out[2] = (float)(c / (double)n_elems);
+  }
+}
+constexpr int CF_PARTS = 296;
+void cf_apply(const float* x, const float* r, long long n, float lo, float hi, float* x_cf, float* part, cudaStream_t s) {
+  PCG_PROFILE("cf_eval", s);
+  launch_k(cf_apply_kernel, dim3(CF_PARTS), dim3(256), 0, s, x, r, n, lo, hi, x_cf, part);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+void cf_metrics(const float* logits, const long long* y_true, const long long* y_target, int B, int NC, const float* part,
+                long long n_elems, float* out, cudaStream_t s) {
+  PCG_PROFILE("cf_eval", s);
+  launch_k(cf_metrics_kernel, dim3(1), dim3(256), 0, s, logits, y_true, y_target, B, NC, part, CF_PARTS, n_elems, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+int cf_parts() { return CF_PARTS; }
+
 // ---- dropout keep-mask (nn.Dropout / nn.Dropout2d in training mode: mnist/models/classifier.py:14,19) ------------------
 // mask[row][inner][c] = Bernoulli(1 - p) / (1 - p); channelwise (Dropout2d): one draw per (row, c), repeated over `inner`.
 // Same Philox stream convention as build_mask (key = seed + rng[2], offset rng[0], advanced by the last block).

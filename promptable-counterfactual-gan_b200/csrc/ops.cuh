@@ -57,6 +57,12 @@ void u8_batch(const uint8_t* images, const long long* labels, const long long* i
 // mask[B][C][H][W] in {0,1}: k_sel of the (H/patch)*(W/patch) patches per sample chosen uniformly at random (k_sel < 0 or
 // >= total: independent fair coins), nearest-upsampled; target[b] ~ U{0..num_classes-1} (nullptr: no draw).
 // rng = device {stream offset, ticket} (advanced by the kernel) or nullptr (offset 0).
+// counterfactual evaluation: x_cf = clamp(x + r), partials of sum |x_cf - x| (cf_parts() floats); then flip rate,
+// prediction gain, actionability from the classifier's logits on x_cf
+int cf_parts();
+void cf_apply(const float* x, const float* r, long long n, float lo, float hi, float* x_cf, float* part, cudaStream_t s);
+void cf_metrics(const float* logits, const long long* y_true, const long long* y_target, int B, int NC, const float* part,
+                long long n_elems, float* out, cudaStream_t s);
 // mask[rows][inner][C] = Bernoulli(1 - p) / (1 - p) (nn.Dropout); channelwise: one draw per (row, c) (nn.Dropout2d)
 void dropout_mask(long long rows, int inner, int C, float p, int channelwise, unsigned long long seed, unsigned long long* rng,
                   float* mask, cudaStream_t s);

@@ -342,6 +342,23 @@ def ce_loss(logits, target, loss, dlogits, wgt=1.0):
     _lib.check(_L().pcg_ce_loss(P(logits), P(target), B, NC, _f(wgt), P(loss), P(dlogits), _s()))
 
 
+def cf_scratch(device):
+    return torch.zeros(int(_L().pcg_cf_scratch_floats()), device=device)
+
+
+@_op("x_cf", "scratch")
+def cf_apply(x, residual, x_cf, scratch, lo=-1.0, hi=1.0):
+    _chk(x, residual, x_cf, scratch)
+    _lib.check(_L().pcg_cf_apply(P(x), P(residual), _ll(x.numel()), _f(lo), _f(hi), P(x_cf), P(scratch), _s()))
+
+
+@_op("out3")
+def cf_metrics(logits, y_true, y_target, scratch, n_elems, out3):
+    B, NC = logits.shape
+    _chk(logits, y_true, y_target, scratch, out3)
+    _lib.check(_L().pcg_cf_metrics(P(logits), P(y_true), P(y_target), B, NC, P(scratch), _ll(n_elems), P(out3), _s()))
+
+
 @_op("mask", "rng_state")
 def dropout_mask(mask, p, channelwise=False, seed=0, rng_state=None):
     """mask [rows, ..., C] = Bernoulli(1 - p) / (1 - p); channelwise: one draw per (row, channel) (nn.Dropout2d on NHWC)."""
