@@ -329,6 +329,9 @@ int pcg_spectral_norm_bwd(const float* dWn, const float* Wn, int N, int K, const
                           const float* sigma, float* dW, void* stream);
 int pcg_gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y,
                            void* stream);
+/* y[r] = one_hot(argmax_j x[r][j]) (first maximum): the forward value of F.gumbel_softmax(hard=True) from its soft
+ * sample, house_sales_kc_usa/eval_utils.py:75.  x and y may alias. */
+int pcg_onehot_argmax(const float* x, long long rows, int n, float* y, void* stream);
 int pcg_softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, void* stream);
 int pcg_ce_loss(const float* logits, const long long* target, int B, int NC, float wgt, float* loss, float* dlogits,
                 void* stream);

@@ -344,3 +344,45 @@ def kc_batch(B, seed, nc=4):
     mask[:, KC_IMMUTABLE] = 0.0
     noise = [torch.empty(B, n).exponential_(generator=g) for n in KC_CAT.values()]
     return x, y, t, mask, noise
+
+
+# ---------------------------------------------------------------------------------------------- evaluation
+def kc_build_counterfactuals(P, Bf, x, onehot, exp_noise, norm_vals, immutable_idx=KC_IMMUTABLE, tau=0.5):
+    """house_sales_kc_usa/eval_utils.py:25-181: generator in eval mode with HARD Gumbel-softmax samples, residual
+    assembly, immutable-feature mask; returns (masked_residual, x_cf = clamp(x + masked, 0, 1))."""
+    mask = torch.ones_like(x)
+    if len(immutable_idx):
+        mask[:, list(immutable_idx)] = 0.0
+    with torch.no_grad():
+        cont, soft = kc_g_forward(P, Bf, x, onehot, mask, exp_noise, tau=tau, training=False)
+        hard = OrderedDict((f, F.one_hot(s.argmax(1), s.shape[1]).float()) for f, s in soft.items())
+        res = kc_assemble(x, cont, hard, norm_vals)
+        masked = res * mask
+    return masked, torch.clamp(x + masked, 0.0, 1.0)
+
+
+def kc_metrics_per_target(PG, BG, PC, BC, X, y, norm_vals, noise_fn, batch_size=128, nc=4):
+    """eval_utils.py:185-289 (the three per-target metrics); noise_fn(bs) -> list of Exp(1) tensors."""
+    out = []
+    with torch.no_grad():
+        for target in range(nc):
+            flips, gains, acts = [], [], []
+            for i in range(0, X.shape[0], batch_size):
+                xb, yb = X[i:i + batch_size], y[i:i + batch_size]
+                sel = yb != target
+                if int(sel.sum()) == 0:
+                    continue
+                x = xb[sel]
+                bs = x.shape[0]
+                oh = F.one_hot(torch.full((bs,), target), nc).float()
+                masked, _ = kc_build_counterfactuals(PG, BG, x, oh, noise_fn(bs), norm_vals)
+                x_cf = x + masked
+                po = torch.softmax(kc_c_forward(PC, BC, x), 1)[:, target]
+                lc = kc_c_forward(PC, BC, x_cf)
+                pc = torch.softmax(lc, 1)[:, target]
+                flips.append((lc.argmax(1) == target).float().mean().item())
+                gains.append((pc - po).mean().item())
+                acts.append(masked.abs().mean().item())
+            out.append({"target_class": target, "class_flip": sum(flips) / len(flips), "prediction_gain": sum(gains) / len(gains),
+                        "avg_actionability": sum(acts) / len(acts)})
+    return out

@@ -270,6 +270,11 @@ int pcg_gumbel_softmax_fwd(const float* logits, const float* g, long long rows, 
   gumbel_softmax_fwd(logits, g, rows, n, tau, y, ST);
   PCG_API_END
 }
+int pcg_onehot_argmax(const float* x, long long rows, int n, float* y, void* stream) {
+  PCG_API_BEGIN
+  onehot_argmax(x, rows, n, y, ST);
+  PCG_API_END
+}
 int pcg_softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, void* stream) {
   PCG_API_BEGIN
   softmax_bwd(dy, y, rows, n, tau, dl, ST);

@@ -430,6 +430,24 @@ void gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
+// y = one_hot(argmax_j x[r][j]): the forward value of F.gumbel_softmax(..., hard=True) given its soft sample
+// (house_sales_kc_usa/eval_utils.py:75: the evaluation path asks the generator for hard categorical samples)
+__global__ void onehot_argmax_kernel(const float* __restrict__ x, long long rows, int n, float* __restrict__ y) {
+  pdl_enter();
+  GRID_STRIDE(r, rows) {
+    int am = 0;
+    float mx = x[r * n];
+    for (int j = 1; j < n; ++j)
+      if (x[r * n + j] > mx) { mx = x[r * n + j]; am = j; }
+    for (int j = 0; j < n; ++j) y[r * n + j] = j == am ? 1.f : 0.f;
+  }
+}
+void onehot_argmax(const float* x, long long rows, int n, float* y, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  launch_k(onehot_argmax_kernel, dim3(blocks_for(rows)), dim3(256), 0, s, x, rows, n, y);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
 __global__ void softmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long rows, int n,
                                    float tau, float* __restrict__ dl) {
   pdl_enter();

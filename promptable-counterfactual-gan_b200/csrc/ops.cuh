@@ -47,6 +47,7 @@ void mlp_gan_step(int B, int z_dim, int label_dim, int hidden, const float* real
                   float* g_v, int* g_step, float* d_param, float* d_grad, float* d_m, float* d_v, int* d_step, float lr,
                   float* scal, cudaStream_t stream);
 void gumbel_softmax_fwd(const float* logits, const float* g, long long rows, int n, float tau, float* y, cudaStream_t s);
+void onehot_argmax(const float* x, long long rows, int n, float* y, cudaStream_t s);
 void softmax_bwd(const float* dy, const float* y, long long rows, int n, float tau, float* dl, cudaStream_t s);
 void bn_eval(const float* x, long long rows, int C, const float* gamma, const float* beta, const float* rm,
              const float* rv, float eps, float* y, float* scale_out, cudaStream_t s);

@@ -330,6 +330,13 @@ def gumbel_softmax_fwd(logits, g, tau, y):
     _lib.check(_L().pcg_gumbel_softmax_fwd(P(logits), P(g), _ll(rows), n, _f(tau), P(y), _s()))
 
 
+@_op("y")
+def onehot_argmax(x, y):
+    rows, n = x.shape
+    _chk(x, y)
+    _lib.check(_L().pcg_onehot_argmax(P(x), _ll(rows), n, P(y), _s()))
+
+
 @_op("dl")
 def softmax_bwd(dy, y, tau, dl):
     rows, n = y.shape

@@ -57,16 +57,15 @@ class ResidualGenerator(nn.Module):
         self.tau = tau
 
     def forward(self, x, target_onehot, mask=None, temperature=None, hard=False):
-        """(cont_residual, cat_logits, cat_samples) as generator.py:68-92; soft samples only (``hard=False`` is what
-        the training path uses, trainer.py:259-261)."""
-        if hard:
-            raise NotImplementedError("native forward implements the soft Gumbel-softmax of the training path")
+        """(cont_residual, cat_logits, cat_samples) as generator.py:68-92.  ``hard=False`` is what the training path uses
+        (trainer.py:259-261); ``hard=True`` (the evaluation path, eval_utils.py:75) returns the one-hot of the soft
+        sample's arg-max, the forward value of F.gumbel_softmax(hard=True)."""
         if mask is None:
             mask = torch.ones_like(x)
         plan = _forward_plan(self, x.shape[0])
         tau = self.tau if temperature is None else float(temperature)
         noise = [torch.empty(x.shape[0], info["n"], device=x.device).exponential_() for info in self.categorical_info.values()]
-        return plan.g_forward(x, target_onehot, mask, noise, tau, self.training)
+        return plan.g_forward(x, target_onehot, mask, noise, tau, self.training, hard=hard)
 
 
 class Discriminator(nn.Module):
@@ -380,7 +379,7 @@ class KcPlan:
         self.run()
         return self.scal
 
-    def g_forward(self, x, target_onehot, mask, exp_noise, tau, training):
+    def g_forward(self, x, target_onehot, mask, exp_noise, tau, training, hard=False):
         with torch.no_grad():
             self.x.copy_(x.float())
             self.t_oh.copy_(target_onehot.float())
@@ -390,6 +389,9 @@ class KcPlan:
             old, self.tau = self.tau, tau
             self._g_fwd(training)
             self.tau = old
+            if hard:
+                for f in self.cat:
+                    K.onehot_argmax(self.samples[f], self.samples[f])
             return (self.cont_out.clone(), {f: v.clone() for f, v in self.logits.items()},
                     {f: v.clone() for f, v in self.samples.items()})
 
