@@ -609,9 +609,34 @@ def run_other(args):
                "sample": f"oracle port, {n} steps of B={cb} after 1 warm-up"}
     pk, which = peaks()
     step_s = ms * 1e-3 / args.steps
+    floor = None
+    if args.workload != "dcgan" and launches > 4:
+        # what bounds an operator-composed plan: the kernel -> kernel dependency latency of a CUDA graph.  Measured live:
+        # the same number of (empty) launches as ONE dependency chain, and the plan's own critical path x that latency.
+        from pcg_b200 import graphs, ops as K
+        buf = torch.zeros(256, device=dev)
+        body = lambda: [K.unary(buf, K.SCALE, buf, 1.0) for _ in range(int(launches))]    # noqa: E731
+        body()
+        g = graphs.capture(body)
+        g.replay()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(10):
+            g.replay()
+        f1.record()
+        torch.cuda.synchronize()
+        chain_ms = f0.elapsed_time(f1) / 10
+        floor = {"launches": int(launches), "one_chain_of_empty_nodes_ms": round(chain_ms, 4),
+                 "us_per_dependent_node": round(chain_ms * 1e3 / launches, 3)}
+        plan = next((c.cell_contents for c in (native_step.__closure__ or ()) if hasattr(c.cell_contents, "run")), None)
+        prog = getattr(getattr(plan, "run", None), "program", None)
+        if prog is not None:
+            floor.update({"dataflow_operators": len(prog.ops), "critical_path_operators": prog.critical_path(),
+                          "streams": prog.n_streams})
     if spec["flops"] and args.workload == "dcgan":
         ach = spec["flops"] * B / step_s / 1e12
-        roof = {"bound": "tensor", "kernel": "whole step (64..512-channel convolutions on tcgen05 with bf16x3 operands = 3x the algorithmic MMA work; fp32 storage)",
+        roof = {"bound": "tensor", "kernel": "whole step (64..512-channel convolutions on tcgen05, plain bf16 operands by default - PCG_TC_TERMS=3 selects bf16x3; fp32 storage; one-channel layers on CUDA cores)",
                 "achieved": ach, "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "unit": "TFLOP/s",
                 "frac": ach / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "traffic": None}
     else:
@@ -621,7 +646,7 @@ def run_other(args):
                 "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None}
     print(json.dumps({"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                       "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32-equivalent)" if args.workload == "dcgan" else "f32",
+                      "scaling": "weak", "vs_baseline": None, "dtype": ("bf16" if os.environ.get("PCG_TC_TERMS", "1") == "1" else "bf16x3 (fp32-equivalent)") if args.workload == "dcgan" else "f32",
                       "data": "synthetic",
                       "config": {"workload": spec["name"], "global_batch": B * world,
                                  "parallelism": ("dp%d" % world) if args.workload == "dcgan" else "replicas",
@@ -630,10 +655,124 @@ def run_other(args):
                       "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": 0,
                               "d2h_bytes_per_step": int(host.numel() * 4)},
                       "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches),
-                      "roofline": roof, "cpu_baseline": cpu, "clocks": clk}), flush=True)
+                      "roofline": roof, "graph_launch_floor": floor, "cpu_baseline": cpu, "clocks": clk}), flush=True)
 
 
 # --------------------------------------------------------------------------------------------- widened rows
+def run_widened2(args):
+    """SURVEY 8f rows 2 and 3, same JSON line:
+    --workload mnist_clf_train   classifier pre-training iteration (mnist/trainer.py:8-39), batch 128
+    --workload kc_clf_train      KC classifier pre-training iteration (house_sales_kc_usa/trainer.py:85-96), batch 128
+    --workload mnist_eval        evaluate_generator_per_target sweep (eval_utils.py:78-110): 10 targets x batch 512"""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import mnist_countergan as O
+    w = args.workload
+    cpu, line = None, None
+    if w == "mnist_clf_train":
+        from oracle import mnist_classifier as OC
+        B, metric = 128, "MNIST classifier pre-training samples/sec"
+        PC = O.synth_params(O.c_param_shapes(), 3, "C")
+        batches = [O.synth_batch(B, 60 + i)[:2] for i in range(4)]
+
+        def cpu_run(n):
+            S = OC.make_state(PC)
+            m2, m1 = OC.synth_masks(B, 1)
+            OC.train_step(S, *batches[0], m2, m1)
+            t0 = time.perf_counter()
+            for i in range(n):
+                OC.train_step(S, *batches[i % 4], m2, m1)
+            return B * n / (time.perf_counter() - t0)
+
+        def native():
+            from pcg_b200.mnist.classifier_trainer import ClassifierPlan
+            plan = ClassifierPlan(B, "cuda")
+            plan.C.load(PC)
+            plan.refresh()
+            db = [(x.cuda(), y.cuda()) for x, y in batches]
+            return lambda i: plan.step(*db[i % 4])
+    elif w == "kc_clf_train":
+        from oracle import kc_classifier as OK
+        B, metric = 128, "KC classifier pre-training samples/sec"
+        g = torch.Generator().manual_seed(0)
+        PC = {k: (torch.randn(*s, generator=g) * 0.1 if len(s) == 2 else torch.ones(*s) if ".weight" in k else torch.zeros(*s))
+              for k, s in OK.shapes().items()}
+        xs = [(torch.rand(B, 17, generator=g), torch.randint(0, 4, (B,), generator=g)) for _ in range(4)]
+        cw = torch.ones(4)
+
+        def cpu_run(n):
+            S = OK.make_state(PC)
+            masks = OK.synth_masks(B, 1)
+            OK.train_step(S, *xs[0], masks, cw)
+            t0 = time.perf_counter()
+            for i in range(n):
+                OK.train_step(S, *xs[i % 4], masks, cw)
+            return B * n / (time.perf_counter() - t0)
+
+        def native():
+            from pcg_b200.tabular.kc_classifier import KcClassifierPlan
+            plan = KcClassifierPlan(B, "cuda", class_weights=cw)
+            plan.C.load(PC)
+            plan.refresh()
+            db = [(x.cuda(), y.cuda()) for x, y in xs]
+            return lambda i: plan.step(*db[i % 4])
+    else:
+        from oracle import mnist_eval as OE
+        B, metric = 512, "MNIST per-target counterfactual evaluation samples/sec (10 targets per sample)"
+        x, y, _, _ = O.synth_batch(B, 5)
+
+        def cpu_run(n):
+            S = {"G": O.synth_params(O.g_param_shapes(), 1, "G"), "GB": O.g_buffers(), "C": O.synth_params(O.c_param_shapes(), 3, "C")}
+            xs_, ys_ = x[:64], y[:64]
+            t0 = time.perf_counter()
+            for _ in range(max(n // 10, 1)):
+                OE.per_target(S, [(xs_, ys_)])
+            return 64 * max(n // 10, 1) / (time.perf_counter() - t0)
+
+        def native():
+            from pcg_b200.mnist import eval_utils as EV
+            from pcg_b200.mnist.models.classifier import CNNClassifier
+            from pcg_b200.mnist.models.generator import ResidualGenerator
+            torch.manual_seed(0)
+            G, C = ResidualGenerator().cuda().eval(), CNNClassifier().cuda().eval()
+            xd, yd = x.cuda(), y.cuda()
+
+            def one(i):
+                for t in range(10):
+                    EV.counterfactual_metrics(G, C, xd, yd, torch.full_like(yd, t))
+            return one
+    unit = "samples/s"
+    if not args.skip_cpu or args.impl == "reference":
+        rate = cpu_run(10 if w != "mnist_eval" else 10)
+        cpu = {"value": rate, "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": "oracle port, 10 iterations"}
+    if args.impl == "reference":
+        line = {"impl": "reference", "metric": metric, "value": cpu["value"], "unit": unit, "cpu_baseline": cpu}
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (native arm) needs a CUDA device: libpcg has no CPU fallback")
+        import pcg_b200  # noqa: F401
+        from pcg_b200 import _lib
+        step = native()
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        line = {"metric": metric, "value": B / (ms * 1e-3), "unit": unit, "ms_per_step": ms, "n_gpus": 1, "steps": args.steps,
+                "dtype": "bf16" if w == "mnist_eval" else "f32", "data": "synthetic", "higher_is_better": True,
+                "config": {"workload": w, "batch": B}, "gpu_launches": int(_lib.launch_count() - n0), "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
 def run_widened(args):
     """--workload mnist_infer: eval-mode generator forward (BatchNorm folded), batch 512.
     --workload mnist_loader: on-device input pipeline, one shuffled epoch of 54,000 uint8 images, batch 512."""
@@ -763,8 +902,11 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PCG_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workload", default="mnist", choices=["mnist", "mnist_infer", "mnist_loader"] + sorted(OTHER))
+    ap.add_argument("--workload", default="mnist", choices=["mnist", "mnist_infer", "mnist_loader", "mnist_clf_train", "kc_clf_train", "mnist_eval"] + sorted(OTHER))
     args = ap.parse_args()
+    if args.workload in ("mnist_clf_train", "kc_clf_train", "mnist_eval"):
+        run_widened2(args)
+        return
     if args.workload in ("mnist_infer", "mnist_loader"):
         run_widened(args)
     elif args.workload != "mnist":
