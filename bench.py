@@ -68,15 +68,20 @@ class _TimedLoader:
     def __init__(self, batches, warmup, steps, budget_s, min_steps=3):
         self.batches, self.warmup, self.steps, self.budget_s, self.min_steps = batches, warmup, steps, budget_s, min_steps
         self.stamps = []
+        self.sync = None                          # device synchronisation before each stamp (GPU comparator runs)
 
     def __iter__(self):
         t_begin = time.perf_counter()
         for i in range(self.warmup + self.steps):
+            if self.sync is not None:
+                self.sync()
             now = time.perf_counter()
             self.stamps.append(now)
             if i >= self.warmup + self.min_steps and now - t_begin > self.budget_s:
                 return
             yield self.batches[i % len(self.batches)]
+        if self.sync is not None:
+            self.sync()
         self.stamps.append(time.perf_counter())
 
     def timed(self):
@@ -85,7 +90,7 @@ class _TimedLoader:
         return n, self.stamps[-1] - self.stamps[self.warmup]
 
 
-def reference_step_rate(steps, warmup, batch=BATCH, threads=None, budget_s=240.0):
+def reference_step_rate(steps, warmup, batch=BATCH, threads=None, budget_s=240.0, device="cpu", autocast=None):
     """Drives the UNMODIFIED reference ``train_countergan`` (conditional_counteRGAN/mnist/trainer.py:76-163, staged at
     baseline/_ref by baseline/vendor_ref.py) with the reference's own modules on the host cores: device="cpu", fp32,
     hyper-parameters of config.py:10-15, synthetic batches of the bench workload.  Returns None when nothing is staged.
@@ -134,8 +139,12 @@ def reference_step_rate(steps, warmup, batch=BATCH, threads=None, budget_s=240.0
                                     patch_size=K.patch_size, num_modifiable_patches=K.num_modifiable_patches,
                                     lambda_adv=K.lambda_adv, lambda_cls=K.lambda_cls, lambda_reg=K.lambda_reg,
                                     lambda_mask=K.lambda_mask, save_dir=tmp, generator_path=os.path.join(tmp, "generator.pt"))
-        with contextlib.redirect_stdout(sys.stderr):          # the reference prints; stdout carries the JSON line only
-            trainer.train_countergan(G, D, C, loader, cfg, "cpu")
+        if device != "cpu":                                   # informational comparator: torch eager on the GPU
+            G, D, C = G.to(device), D.to(device), C.to(device)
+            loader.sync = torch.cuda.synchronize
+        ctx = torch.autocast("cuda", dtype=autocast) if autocast is not None else contextlib.nullcontext()
+        with contextlib.redirect_stdout(sys.stderr), ctx:     # the reference prints; stdout carries the JSON line only
+            trainer.train_countergan(G, D, C, loader, cfg, device)
     n, dt = loader.timed()
     return batch * n / dt, dt / n * 1e3, threads, n
 

@@ -7,6 +7,7 @@ for w in cgan_moons simple_moons kc dcgan moons_cf; do python bench.py --workloa
 for w in mnist_infer mnist_loader mnist_clf_train kc_clf_train mnist_eval; do python bench.py --workload $w --steps 100 --warmup 10 2>/dev/null | tail -1; done > gpurun_out/bench_${R}_widened_rows.jsonl
 python bench.py --precision fp32 --steps 20 --warmup 5 --skip-cpu 2>/dev/null | tail -1 > gpurun_out/bench_${R}_native_fp32.json
 python tools/bench_graph_floor.py 896 > gpurun_out/graph_floor_${R}.txt 2>&1
+python tools/bench_torch_eager.py > gpurun_out/bench_${R}_torch_eager_b200.jsonl 2>/dev/null
 cut -c1-200 gpurun_out/bench_${R}_other_configs.jsonl
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_${R}.csv python bench.py --steps 2 --warmup 1 --skip-cpu > gpurun_out/ncu_launch_${R}.log 2>&1; tail -2 gpurun_out/ncu_launch_${R}.log | cut -c1-200
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:conv_tc64s_fprop -s 30 -c 3 -o gpurun_out/prof_tc64s_fprop_${R} -f python bench.py --steps 2 --warmup 1 --skip-cpu > gpurun_out/ncu_full_${R}.log 2>&1; tail -2 gpurun_out/ncu_full_${R}.log | cut -c1-200
