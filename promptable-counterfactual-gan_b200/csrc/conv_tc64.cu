@@ -868,26 +868,34 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             for (int j2 = 0; j2 < 2; ++j2) {
               const uint4 u = *reinterpret_cast<const uint4*>(xt + soff[j2]);
               const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-              if (p.bn_bwd) {
-                float ca[8], cb[8], cm[8];
+              if (p.bn_bwd && p.bn_act == ACT_NONE) {
+                // no activation between the BatchNorm and this gradient (BN2 of a residual block): g = v.  The second
+                // sum is taken as sum g*y and turned into sum g*(y - mean) after the last tile (acc_q -= mean * acc_s)
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
+                  const int j = j2 * 8 + t;
+                  acc_s[j] += v[j];
+                  acc_q[j] = fmaf(v[j], yv, acc_q[j]);
+                }
+              } else if (p.bn_bwd) {
+                float ca[8], cb[8];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   const int c = col0 + j2 * 8 + h * 4;
                   const float4 fa = *reinterpret_cast<const float4*>(bnc + c);
                   const float4 fb = *reinterpret_cast<const float4*>(bnc + 64 + c);
-                  const float4 fm = *reinterpret_cast<const float4*>(bnc + 128 + c);
                   ca[h * 4] = fa.x; ca[h * 4 + 1] = fa.y; ca[h * 4 + 2] = fa.z; ca[h * 4 + 3] = fa.w;
                   cb[h * 4] = fb.x; cb[h * 4 + 1] = fb.y; cb[h * 4 + 2] = fb.z; cb[h * 4 + 3] = fb.w;
-                  cm[h * 4] = fm.x; cm[h * 4 + 1] = fm.y; cm[h * 4 + 2] = fm.z; cm[h * 4 + 3] = fm.w;
                 }
-                const float neg_bn = p.bn_act == ACT_LRELU ? p.bn_slope : (p.bn_act == ACT_RELU ? 0.f : 1.f);
+                const float neg_bn = p.bn_act == ACT_LRELU ? p.bn_slope : 0.f;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                   const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
                   const int j = j2 * 8 + t;
                   const float g = fmaf(yv, ca[t], cb[t]) > 0.f ? v[j] : v[j] * neg_bn;
                   acc_s[j] += g;
-                  acc_q[j] = fmaf(g, yv - cm[t], acc_q[j]);
+                  acc_q[j] = fmaf(g, yv, acc_q[j]);
                 }
               } else {
 #pragma unroll
@@ -970,9 +978,10 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     if (want_stats) {
       const float nv = (float)nvalid;
       if (p.bn_bwd) {
+        // sum g*y -> sum g*(y - mean) * rstd = sum g*xhat; both sums scaled by bn_gscale
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          acc_q[j] *= bnc[192 + col0 + j] * p.bn_gscale;
+          acc_q[j] = (acc_q[j] - bnc[128 + col0 + j] * acc_s[j]) * bnc[192 + col0 + j] * p.bn_gscale;
           acc_s[j] *= p.bn_gscale;
         }
       } else {
