@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "conv_auto.cuh"
 #include "conv_c1k4.cuh"
+#include "linear_small.cuh"
 #include "conv_generic.cuh"
 #include "elementwise.cuh"
 #include "ops.cuh"
@@ -46,6 +47,10 @@ int pcg_conv_fprop(const float* in, int N, int H, int W, int Cin, const float* w
     c1k4_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, act, slope, out, ST);
     return 0;
   }
+  if (skinny_on() && !conv_auto_tensor_cores() && linear_small_supported(geom(N, H, W, Cin, Cout, k, stride, pad), N)) {
+    linear_small(in, N, Cin, Cout, wf, e, out, ST);                         // wf of a 1x1 layer is [Cout][Cin]
+    return 0;
+  }
   if (act == ACT_NONE && add_src == nullptr && skinny_on() && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     full1_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, bias, out, ST);
     return 0;
@@ -62,6 +67,10 @@ int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float*
   if (add_src == nullptr && (act_ref == nullptr || ref_act == ACT_NONE) &&
       skinny_on() && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     c1k4_dgrad(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, din, ST);
+    return 0;
+  }
+  if (skinny_on() && !conv_auto_tensor_cores() && linear_small_supported(geom(N, H, W, Cin, Cout, k, stride, pad), N)) {
+    linear_small(dout, N, Cout, Cin, wd, e, din, ST);                       // wd of a 1x1 layer is [Cin][Cout]: "[out][in]" here
     return 0;
   }
   if (add_src == nullptr && (act_ref == nullptr || ref_act == ACT_NONE) && Cin % 4 == 0 &&

@@ -1,0 +1,42 @@
+"""Small fully connected layers (csrc/linear_small.cu) through pcg_conv_fprop / pcg_conv_dgrad (1x1 geometry) against
+float64 torch: forward with bias + activation, data gradient with skip add and activation derivative, ragged row counts,
+every column-count bucket (1..128); row counts above 2048 take the generic kernel (same contract, same test).  Layers of the tabular generators / critics: house_sales_kc_usa/models/generator.py:13-92,
+discriminator.py:9-20, moons/models/*.py."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("M,K,N", [(4096, 32, 32), (4096, 38, 32), (4096, 21, 32), (4096, 64, 128), (4096, 128, 64),
+                                   (4096, 32, 2), (64, 7, 32), (1000, 32, 30), (37, 16, 2), (4096, 128, 1), (5, 1, 128),
+                                   (777, 100, 70)])
+def test_linear_small_forward_and_data_gradient(M, K, N):
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import ops as Kk
+    torch.manual_seed(M + K + N)
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * K ** -0.5
+    b = torch.randn(N, device="cuda") * 0.1
+    for act, fn in ((Kk.ACT_NONE, lambda t: t), (Kk.ACT_LRELU, lambda t: F.leaky_relu(t, 0.1)), (Kk.ACT_RELU, F.relu)):
+        out = torch.full((M, N), 9.0, device="cuda")
+        Kk.linear_fwd(x, w, out, b, act, 0.1)
+        assert rel(out, fn(x.double() @ w.double().t() + b.double())) < 2e-5, (act,)
+    out = torch.full((M, N), 9.0, device="cuda")
+    Kk.linear_fwd(x, w, out)                                           # no bias
+    assert rel(out, x.double() @ w.double().t()) < 2e-5
+    # data gradient: dx = (dy @ W + skip) * lrelu'(ref)
+    dy = torch.randn(M, N, device="cuda")
+    wT = w.t().contiguous()                                            # [K][N], what pack_weights(..., wd=) produces
+    skip, ref = torch.randn(M, K, device="cuda"), torch.randn(M, K, device="cuda")
+    dx = torch.full((M, K), 9.0, device="cuda")
+    Kk.linear_dgrad(dy, wT, dx, K)
+    assert rel(dx, dy.double() @ w.double()) < 2e-5
+    Kk.linear_dgrad(dy, wT, dx, K, act_ref=ref, ref_act=Kk.ACT_LRELU, ref_slope=0.2, add_src=skip)
+    want = (dy.double() @ w.double() + skip.double()) * torch.where(ref.double() > 0, 1.0, 0.2)
+    assert rel(dx, want) < 2e-5
