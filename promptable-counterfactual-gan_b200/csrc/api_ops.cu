@@ -73,6 +73,12 @@ int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float*
     linear_small(dout, N, Cout, Cin, wd, e, din, ST);                       // wd of a 1x1 layer is [Cin][Cout]: "[out][in]" here
     return 0;
   }
+  if (skinny_on() &&
+      full_window_dgrad_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
+    // ConvTranspose2d on a 1x1 input: [N x Cout] x [Cout x (tap, Cin)], weight rows permuted from wd's [Cin][taps][Cout]
+    linear_small(dout, N, Cout, k * k * Cin, wd, e, din, ST, Cin, k * k);
+    return 0;
+  }
   if (add_src == nullptr && (act_ref == nullptr || ref_act == ACT_NONE) && Cin % 4 == 0 &&
       skinny_on() && full1_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
     full1_dgrad(dout, geom(N, H, W, Cin, Cout, k, stride, pad), wd, din, ST);

@@ -40,3 +40,24 @@ def test_linear_small_forward_and_data_gradient(M, K, N):
     Kk.linear_dgrad(dy, wT, dx, K, act_ref=ref, ref_act=Kk.ACT_LRELU, ref_slope=0.2, add_src=skip)
     want = (dy.double() @ w.double() + skip.double()) * torch.where(ref.double() > 0, 1.0, 0.2)
     assert rel(dx, want) < 2e-5
+
+
+@pytest.mark.parametrize("N,Cin,Cout,k", [(256, 512, 100, 4), (33, 24, 7, 4), (5, 130, 100, 3)])
+def test_full_window_data_gradient_is_a_column_tiled_product(N, Cin, Cout, k):
+    """ConvTranspose2d(100, 512, 4, 1, 0) on a 1x1 latent (mnist_dcgan.py:77) is the data gradient of a full-window
+    convolution: din[n][(tap, ci)] = sum_co dout[n][co] * w[co][ci][tap].  Column tiles of 128 with permuted weight rows."""
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import ops as Kk
+    torch.manual_seed(N + Cin)
+    w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.1                       # Conv2d(Cin -> Cout) layout
+    wf = torch.empty(Cout * k * k * Cin, device="cuda")
+    wd = torch.empty(Cin * k * k * Cout, device="cuda")
+    Kk.pack_weights(w, k, wf=wf, wd=wd)
+    dout = torch.randn(N, Cout, device="cuda")                                  # [N,1,1,Cout]
+    din = torch.full((N, k, k, Cin), 9.0, device="cuda")
+    skip, ref = torch.randn_like(din), torch.randn_like(din)
+    Kk.conv_dgrad(dout, N, k, k, Cin, wd, Cout, k, 1, 0, din)
+    want = torch.einsum("no,ocyx->nyxc", dout.double(), w.double())
+    assert rel(din, want) < 2e-5
+    Kk.conv_dgrad(dout, N, k, k, Cin, wd, Cout, k, 1, 0, din, add_src=skip, act_ref=ref, ref_act=Kk.ACT_RELU)
+    assert rel(din, (want + skip.double()) * (ref.double() > 0)) < 2e-5
