@@ -253,6 +253,8 @@ int pcg_conv_dgrad(const float* dout, int N, int H, int W, int Cin, const float*
 long long pcg_conv_wgrad_scratch(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad);
 int pcg_conv_wgrad(const float* in, const float* dout, int N, int H, int W, int Cin, int Cout, int k, int stride,
                    int pad, float* scratch, float* dw /*torch OIHW*/, void* stream);
+/* perm_hw > 0: Cin is a flattened (c, hw) index in torch's NCHW order, re-ordered to NHWC (hw, c); perm_hw == -1: wd is
+ * written with its taps reversed (the forward weight of the dilated-gradient convolution, see pcg_dilate). */
 int pcg_pack_conv_weights(const float* w /*torch OIHW*/, int Cout, int Cin, int k, int perm_hw, float* wf, float* wd,
                           void* stream);
 /* Tensor-core mode of the three convolution entry points above (default off = exact fp32 on the CUDA cores): layers
@@ -375,6 +377,40 @@ int pcg_build_mask(int B, int C, int H, int W, int patch, int num_modifiable_pat
  * x_cf): out3 = {class-flip rate = mean(argmax logits == y_target), prediction gain = mean(softmax[y_target] -
  * softmax[y_true]), actionability = sum |x_cf - x| / n_elems}. */
 int pcg_cf_scratch_floats(void);
+/* nn.InstanceNorm2d(C, affine=True) of the conditional WGAN-GP critic (conditional_gan/mnist/mnist_wgan_conditional.py:
+ * 87-95) on NHWC activations [N][P = H*W][C], statistics per (sample, channel), biased variance:
+ *   pcg_instnorm_fwd      y = act(gamma * xhat + beta), saves mean / rstd [N][C];
+ *   pcg_instnorm_bwd      p = gy * act'(act_ref) (act_ref = the layer's output, NULL: p = gy);
+ *                         dx = gamma * rstd * (p - mean(p) - xhat * mean(p * xhat)) (+ add_src);
+ *                         dgamma_part / dbeta_part [N][C] per-sample sums (NULL: skipped; reduce with pcg_colsum);
+ *   pcg_instnorm_bwd_bwd  the backward of pcg_instnorm_bwd, which the gradient penalty (:146-150, autograd.grad with
+ *                         create_graph=True) back-propagates through: given q = the cotangent of dx, writes gy_bar (cotangent
+ *                         of gy), x_bar (cotangent of x through xhat and rstd) and per-sample parts of gamma's cotangent.
+ *   pcg_flatten_nchw      dst[b][c0 + c * R + r] = src[b][r][c] (dst rows of ld floats): NHWC features into torch's
+ *                         nn.Flatten (NCHW) column order inside a wider matrix (:106 torch.cat); inverse != 0: the same map
+ *                         read backwards (dst[b][r][c] = src[b][c0 + c * R + r]). */
+int pcg_instnorm_fwd(const float* x, int N, int P, int C, const float* gamma, const float* beta, float eps, int act, float slope,
+                     float* y, float* mean, float* rstd, void* stream);
+int pcg_instnorm_bwd(const float* gy, const float* act_ref, int act, float slope, const float* x, const float* mean,
+                     const float* rstd, const float* gamma, int N, int P, int C, const float* add_src, float* dx,
+                     float* dgamma_part, float* dbeta_part, void* stream);
+int pcg_instnorm_bwd_bwd(const float* q, const float* gy, const float* act_ref, int act, float slope, const float* x,
+                         const float* mean, const float* rstd, const float* gamma, int N, int P, int C, float* gy_bar,
+                         float* x_bar, float* dgamma_part, void* stream);
+int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, int c0, int inverse, void* stream);
+/* y[r][c] = x[r][c] + bias[c], tanh applied when tanh_out != 0: the bias (and final Tanh, mnist_wgan_conditional.py:62-72)
+ * of a ConvTranspose2d whose product was computed as a data gradient.  In place (y == x) allowed. */
+int pcg_bias_act(const float* x, long long rows, int C, const float* bias, int tanh_out, float* y, void* stream);
+/* dst [N][Hp][Wp][C] = zero-dilated, padded copy of src [N][Ho][Wo][C]: dst[n][off + stride*y][off + stride*x] = src[n][y][x],
+ * zero elsewhere.  With off = k - 1 - pad and Hp = H + k - 1 the data gradient of Conv2d(k, stride, pad) on H x W inputs
+ * (= the forward of the mirrored ConvTranspose2d) equals pcg_conv_fprop(dst, N, Hp, Wp, Cout -> Cin, k, stride 1, pad 0)
+ * with the wd packed by pcg_pack_conv_weights(perm_hw = -1) as its forward weight: any geometry on the tensor-core
+ * forward kernel, at stride^2 times the arithmetic.  C % 4 == 0. */
+int pcg_dilate(const float* src, int N, int Ho, int Wo, int C, int stride, int off, int Hp, int Wp, float* dst, void* stream);
+/* Gradient penalty of mnist_wgan_conditional.py:147 on the critic's input gradient g [B][D]: n_b = ||g[b]||_2,
+ * out[0] = lambda * mean_b (n_b - 1)^2, gbar = its cotangent lambda * 2 (n_b - 1) / (B n_b) * g[b], norms[b] = n_b
+ * (NULL: not stored).  Not re-entrant across streams (one internal arrival counter). */
+int pcg_gp_penalty(const float* g, int B, int D, float lambda, float* out, float* gbar, float* norms, void* stream);
 int pcg_cf_apply(const float* x, const float* residual, long long n, float lo, float hi, float* x_cf, float* scratch,
                  void* stream);
 int pcg_cf_metrics(const float* logits, const long long* y_true, const long long* y_target, int B, int NC,

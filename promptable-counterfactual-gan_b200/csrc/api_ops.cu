@@ -9,6 +9,7 @@
 #include "conv_generic.cuh"
 #include "elementwise.cuh"
 #include "ops.cuh"
+#include "instnorm.cuh"
 
 using namespace pcg;
 
@@ -317,6 +318,53 @@ int pcg_u8_batch(const unsigned char* images, const long long* labels, const lon
                  float stdv, float* x, long long* y, void* stream) {
   PCG_API_BEGIN
   u8_batch(images, labels, index, B, HW, mean, stdv, x, y, ST);
+  PCG_API_END
+}
+int pcg_instnorm_fwd(const float* x, int N, int P, int C, const float* gamma, const float* beta, float eps, int act, float slope,
+                     float* y, float* mean, float* rstd, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(x && gamma && beta && y && mean && rstd, "instnorm_fwd: null pointer");
+  instnorm_fwd(x, N, P, C, gamma, beta, eps, act, slope, y, mean, rstd, ST);
+  PCG_API_END
+}
+int pcg_instnorm_bwd(const float* gy, const float* act_ref, int act, float slope, const float* x, const float* mean,
+                     const float* rstd, const float* gamma, int N, int P, int C, const float* add_src, float* dx,
+                     float* dgamma_part, float* dbeta_part, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(gy && x && mean && rstd && gamma && dx, "instnorm_bwd: null pointer");
+  instnorm_bwd(gy, act_ref, act, slope, x, mean, rstd, gamma, N, P, C, add_src, dx, dgamma_part, dbeta_part, ST);
+  PCG_API_END
+}
+int pcg_instnorm_bwd_bwd(const float* q, const float* gy, const float* act_ref, int act, float slope, const float* x,
+                         const float* mean, const float* rstd, const float* gamma, int N, int P, int C, float* gy_bar,
+                         float* x_bar, float* dgamma_part, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(q && gy && x && mean && rstd && gamma && gy_bar && x_bar, "instnorm_bwd_bwd: null pointer");
+  instnorm_bwd_bwd(q, gy, act_ref, act, slope, x, mean, rstd, gamma, N, P, C, gy_bar, x_bar, dgamma_part, ST);
+  PCG_API_END
+}
+int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, int c0, int inverse, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(src && dst, "flatten_nchw: null pointer");
+  flatten_nchw(src, B, R, C, dst, ld, c0, inverse != 0, ST);
+  PCG_API_END
+}
+int pcg_bias_act(const float* x, long long rows, int C, const float* bias, int tanh_out, float* y, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(x && bias && y && rows >= 0 && C >= 1, "bias_act: null pointer / shape");
+  bias_act(x, rows, C, bias, tanh_out, y, ST);
+  PCG_API_END
+}
+int pcg_dilate(const float* src, int N, int Ho, int Wo, int C, int stride, int off, int Hp, int Wp, float* dst, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(src && dst, "dilate: null pointer");
+  dilate(src, N, Ho, Wo, C, stride, off, Hp, Wp, dst, ST);
+  PCG_API_END
+}
+int pcg_gp_penalty(const float* g, int B, int D, float lambda, float* out, float* gbar, float* norms, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(g && out && gbar, "gp_penalty: null pointer");
+  gp_penalty(g, B, D, lambda, out, gbar, norms, ST);
   PCG_API_END
 }
 int pcg_cf_scratch_floats(void) { return cf_parts(); }

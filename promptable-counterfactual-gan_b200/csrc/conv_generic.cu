@@ -705,7 +705,9 @@ __global__ void pack_generic_kernel(const float* __restrict__ w, int Cout, int C
     }
     const float v = w[i];
     if (wf) wf[((size_t)co * taps + tap) * Cin + ci] = v;
-    if (wd) wd[((size_t)ci * taps + tap) * Cout + co] = v;
+    // perm_hw == -1: taps reversed - wd is then the FORWARD weight [Cin][taps][Cout] of the stride-1 convolution over the
+    // zero-dilated output gradient that equals this layer's data gradient (pcg_dilate)
+    if (wd) wd[((size_t)ci * taps + (perm_hw == -1 ? taps - 1 - tap : tap)) * Cout + co] = v;
   }
 }
 

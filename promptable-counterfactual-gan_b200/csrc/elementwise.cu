@@ -601,12 +601,25 @@ __global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict_
     __syncthreads();
   }
 }
+// wide matrices whose column count fits neither vector kernel (e.g. C = 4096): a thread per column, rows of the slice in turn
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_wide_kernel(const T* __restrict__ a, long long M, int C,
+                                                         float* __restrict__ part) {
+  pdl_enter();
+  const RowSlice sl = row_slice(M);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f;
+    for (long long r = sl.begin; r < sl.end; ++r) s += to_f(a[r * C + c]);
+    part[(size_t)blockIdx.x * C + c] = s;
+  }
+}
 template <typename T>
 void colsum_partial(const T* a, long long M, int C, float* part, cudaStream_t s) {
   PCG_PROFILE("colsum", s);
   if (wide_ok<T>(C, {a})) launch_k(colsum_kernel<T, 8>, dim3(STAT_PARTS), dim3(256), 0, s, a, M, C, part);
   else if ((C & 3) == 0 && (256 % (C >> 2)) == 0 && C <= 1024 && (reinterpret_cast<uintptr_t>(a) % (4 * sizeof(T))) == 0)
     launch_k(colsum_kernel<T, 4>, dim3(STAT_PARTS), dim3(256), 0, s, a, M, C, part);
+  else if (C >= 64) launch_k(colsum_wide_kernel<T>, dim3(STAT_PARTS), dim3(256), 0, s, a, M, C, part);
   else launch_k(colsum_scalar_kernel<T>, dim3(STAT_PARTS), dim3(256), 0, s, a, M, C, part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();

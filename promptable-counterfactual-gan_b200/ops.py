@@ -349,6 +349,53 @@ def ce_loss(logits, target, loss, dlogits, wgt=1.0):
     _lib.check(_L().pcg_ce_loss(P(logits), P(target), B, NC, _f(wgt), P(loss), P(dlogits), _s()))
 
 
+@_op("y", "mean", "rstd")
+def instnorm_fwd(x, N, HW, C, gamma, beta, y, mean, rstd, act=ACT_NONE, slope=0.2, eps=1e-5):
+    _chk(x, gamma, beta, y, mean, rstd)
+    _lib.check(_L().pcg_instnorm_fwd(P(x), N, HW, C, P(gamma), P(beta), _f(eps), act, _f(slope), P(y), P(mean), P(rstd),
+                                     _s()))
+
+
+@_op("dx", "dgamma_part", "dbeta_part")
+def instnorm_bwd(gy, x, mean, rstd, gamma, N, HW, C, dx, act_ref=None, act=ACT_NONE, slope=0.2, add_src=None,
+                 dgamma_part=None, dbeta_part=None):
+    _chk(gy, x, mean, rstd, gamma, dx, act_ref, add_src, dgamma_part, dbeta_part)
+    _lib.check(_L().pcg_instnorm_bwd(P(gy), P(act_ref), act, _f(slope), P(x), P(mean), P(rstd), P(gamma), N, HW, C,
+                                     P(add_src), P(dx), P(dgamma_part), P(dbeta_part), _s()))
+
+
+@_op("gy_bar", "x_bar", "dgamma_part")
+def instnorm_bwd_bwd(q, gy, x, mean, rstd, gamma, N, HW, C, gy_bar, x_bar, act_ref=None, act=ACT_NONE, slope=0.2,
+                     dgamma_part=None):
+    _chk(q, gy, x, mean, rstd, gamma, gy_bar, x_bar, act_ref, dgamma_part)
+    _lib.check(_L().pcg_instnorm_bwd_bwd(P(q), P(gy), P(act_ref), act, _f(slope), P(x), P(mean), P(rstd), P(gamma), N,
+                                         HW, C, P(gy_bar), P(x_bar), P(dgamma_part), _s()))
+
+
+@_op(lambda a: [a["dst"] if a.get("inverse") else (a["dst"], a["c0"], a["c0"] + a["R"] * a["C"])])
+def flatten_nchw(src, B, R, C, dst, ld, c0=0, inverse=False):
+    _chk(src, dst)
+    _lib.check(_L().pcg_flatten_nchw(P(src), B, R, C, P(dst), ld, c0, 1 if inverse else 0, _s()))
+
+
+@_op("y")
+def bias_act(x, C, bias, y, tanh_out=False):
+    _chk(x, bias, y)
+    _lib.check(_L().pcg_bias_act(P(x), _ll(x.numel() // C), C, P(bias), 1 if tanh_out else 0, P(y), _s()))
+
+
+@_op("dst")
+def dilate(src, N, Ho, Wo, C, stride, off, Hp, Wp, dst):
+    _chk(src, dst)
+    _lib.check(_L().pcg_dilate(P(src), N, Ho, Wo, C, stride, off, Hp, Wp, P(dst), _s()))
+
+
+@_op("out", "gbar", "norms")
+def gp_penalty(g, B, D, lam, out, gbar, norms=None):
+    _chk(g, out, gbar, norms)
+    _lib.check(_L().pcg_gp_penalty(P(g), B, D, _f(lam), P(out), P(gbar), P(norms), _s()))
+
+
 def cf_scratch(device):
     return torch.zeros(int(_L().pcg_cf_scratch_floats()), device=device)
 
