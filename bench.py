@@ -450,6 +450,12 @@ def run_native(args):
 OTHER = {
     "dcgan": dict(batch=256, name="dconv_gan/mnist DCGAN, synthetic 1x64x64 (28x28 source resized, mnist_dcgan.py:43), batch 256",
                   flops=2.243e9, bytes=None),
+    # conditional WGAN-GP: one "step" = one batch of the loop (critic update with gradient penalty; every n_critic = 5th batch
+    # also the generator update).  Model FLOPs per sample and batch, dense (the dilation zeros of the transposed /
+    # data-gradient convolutions not counted): critic pass 70.2 MMAC; critic update = 3 forward + 3 backward (x2) + gradient
+    # chain + its reverse (x2) + generator forward 196 MMAC = 1036 MMAC; generator update 728 MMAC / 5 -> 1.18 GMAC.
+    "cwgan": dict(batch=128, name="conditional_gan/mnist conditional WGAN-GP (mnist_wgan_conditional.py), widths 1024/1024/1024, "
+                  "synthetic 1x28x28, batch 128, n_critic 5 (4 of 5 steps critic-only)", flops=2.36e9, bytes=None),
     "kc": dict(batch=4096, name="conditional_counteRGAN/house_sales_kc_usa tabular CounteRGAN, synthetic KC-shaped features, batch 4096",
                flops=0.79e6, bytes=424.0),
     "moons_cf": dict(batch=64, name="conditional_counteRGAN/moons tabular CounteRGAN, batch 64", flops=None, bytes=None),
@@ -476,6 +482,30 @@ def _other_setup(kind, B, dev):
         dring = [tuple(cu(t) for t in b) for b in ring] if plan is not None else None
         cpu_ring = [O.synth_batch(16, 90 + i) for i in range(2)]
         return (lambda i: plan.step(*dring[i % 4])), (lambda i: O.dcgan_step(S, *cpu_ring[i % 2])), 16
+    if kind == "cwgan":
+        from oracle import wgan_gp as O
+        from pcg_b200.wgan import Hyperparameter, WganGpPlan
+        ohp = O.Hyper()
+        PG, PC = O.synth_params(O.g_shapes(ohp), 7), O.synth_params(O.c_shapes(ohp), 8)
+        plan = WganGpPlan(Hyperparameter(), B, dev) if dev is not None else None
+        if plan is not None:
+            plan.G.load(PG); plan.C.load(PC); plan.refresh()
+        keys = ("real", "labels", "noise", "alpha", "labels_g", "noise_g")
+        dring = [[cu(O.synth_batch(ohp, B, 70 + i)[k]) for k in keys] for i in range(4)] if plan is not None else None
+        S = O.make_state(PG, O.g_buffers(ohp), PC)
+        cpu_ring = [O.synth_batch(ohp, 16, 90 + i) for i in range(2)]
+        eye = torch.eye(ohp.num_classes)
+
+        def native_step(i):
+            d = dring[i % 4]
+            return plan.step(*d) if i % ohp.n_critic == 0 else plan.step(*d[:4])
+
+        def cpu_step(i):
+            c = cpu_ring[i % 2]
+            O.critic_step(S, ohp, c["real"], eye[c["labels"]], c["noise"], c["alpha"])
+            if i % ohp.n_critic == 0:
+                O.generator_step(S, ohp, c["noise_g"], eye[c["labels_g"]])
+        return native_step, cpu_step, 16
     if kind in ("kc", "moons_cf"):
         from oracle import tabular_countergan as T
         if kind == "kc":
@@ -570,10 +600,19 @@ def run_other(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     native_step, cpu_step, cb = _other_setup(args.workload, B, dev)
-    n0 = _lib.launch_count()
-    native_step(0)                                   # eager pass + graph capture
+    # kernels per replayed step = the launches the plan's capture(s) recorded (the eager dry run before a capture is not
+    # part of a step); cwgan has two graphs, [critic + generator] and [critic only], replayed 1 : 4
+    from pcg_b200 import graphs as _graphs
+    _graphs.capture_log.clear()
+    native_step(0)
+    n1 = _lib.launch_count()
+    native_step(1)
     torch.cuda.synchronize()
-    launches = _lib.launch_count() - n0
+    log = list(_graphs.capture_log)
+    if not log:                                      # a plan that launches its (single) kernel directly every step
+        launches = _lib.launch_count() - n1
+    else:
+        launches = int(round((log[0] + 4 * log[1]) / 5)) if args.workload == "cwgan" else int(sum(log))
     for i in range(max(args.warmup, 3)):
         native_step(i)
     if dist is not None:
@@ -610,7 +649,7 @@ def run_other(args):
     if not args.skip_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_step(0)
-        n = 3 if args.workload == "dcgan" else 10
+        n = 3 if args.workload == "dcgan" else (5 if args.workload == "cwgan" else 10)
         t0 = time.perf_counter()
         for i in range(n):
             cpu_step(i)
@@ -619,7 +658,7 @@ def run_other(args):
     pk, which = peaks()
     step_s = ms * 1e-3 / args.steps
     floor = None
-    if args.workload != "dcgan" and launches > 4:
+    if args.workload not in ("dcgan", "cwgan") and launches > 4:
         # what bounds an operator-composed plan: the kernel -> kernel dependency latency of a CUDA graph.  Measured live:
         # the same number of (empty) launches as ONE dependency chain, and the plan's own critical path x that latency.
         from pcg_b200 import graphs, ops as K
@@ -643,9 +682,10 @@ def run_other(args):
         if prog is not None:
             floor.update({"dataflow_operators": len(prog.ops), "critical_path_operators": prog.critical_path(),
                           "streams": prog.n_streams})
-    if spec["flops"] and args.workload == "dcgan":
+    if spec["flops"] and args.workload in ("dcgan", "cwgan"):
         ach = spec["flops"] * B / step_s / 1e12
-        roof = {"bound": "tensor", "kernel": "whole step (64..512-channel convolutions on tcgen05, plain bf16 operands by default - PCG_TC_TERMS=3 selects bf16x3; fp32 storage; one-channel layers on CUDA cores)",
+        roof = {"bound": "tensor", "kernel": "whole step (64..512-channel convolutions on tcgen05, plain bf16 operands by default - PCG_TC_TERMS=3 selects bf16x3; fp32 storage; one-channel layers on CUDA cores)" if args.workload == "dcgan" else
+                "whole step, model FLOPs (256..1024-channel convolutions and linear layers on the tcgen05 forward / weight-gradient kernels with bf16x3 operands = 3x the tensor work, strided data gradients as dilated forward convolutions = 4x; PCG_TC_TERMS=1 selects plain bf16)",
                 "achieved": ach, "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "unit": "TFLOP/s",
                 "frac": ach / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "traffic": None}
     else:
@@ -655,7 +695,7 @@ def run_other(args):
                 "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None}
     print(json.dumps({"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                       "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": ("bf16" if os.environ.get("PCG_TC_TERMS", "1") == "1" else "bf16x3 (fp32-equivalent)") if args.workload == "dcgan" else "f32",
+                      "scaling": "weak", "vs_baseline": None, "dtype": ("bf16" if os.environ.get("PCG_TC_TERMS", "1") == "1" else "bf16x3 (fp32-equivalent)") if args.workload == "dcgan" else (("bf16" if os.environ.get("PCG_TC_TERMS", "3") == "1" else "bf16x3 (fp32-equivalent)") if args.workload == "cwgan" else "f32"),
                       "data": "synthetic",
                       "config": {"workload": spec["name"], "global_batch": B * world,
                                  "parallelism": ("dp%d" % world) if args.workload == "dcgan" else "replicas",

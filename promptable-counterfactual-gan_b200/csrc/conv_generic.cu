@@ -711,9 +711,42 @@ __global__ void pack_generic_kernel(const float* __restrict__ w, int Cout, int C
   }
 }
 
+// Tiled transpose dst[c][r] = src[r][c] (32 x 32 tiles through shared memory, both sides coalesced).  taps > 1 with
+// rev != 0: the column index is (ci, tap) and lands on row (ci, taps - 1 - tap) - the tap-reversed wd of perm_hw == -1.
+__global__ void __launch_bounds__(256) transpose_tiled_kernel(const float* __restrict__ src, int R, int C, int taps, int rev,
+                                                             float* __restrict__ dst) {
+  pdl_enter();
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8)
+    if (r0 + j < R && c0 + tx < C) tile[j][tx] = src[(size_t)(r0 + j) * C + c0 + tx];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j;
+    if (c < C && r0 + tx < R) {
+      if (rev) c = c / taps * taps + (taps - 1 - c % taps);
+      dst[(size_t)c * R + r0 + tx] = tile[tx][j];
+    }
+  }
+}
+void transpose_tiled(const float* src, int R, int C, float* dst, cudaStream_t stream, int taps, bool rev) {
+  PCG_REQUIRE((C + 31) / 32 <= 2147483647 && (R + 31) / 32 <= 65535, "transpose: at most 2M rows");
+  launch_k(transpose_tiled_kernel, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 0, stream, src, R, C, taps, rev ? 1 : 0, dst);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 void pack_conv_weights_generic(const float* w, int Cout, int Cin, int ksize, int perm_hw, float* wf, float* wd,
                                cudaStream_t stream) {
   PCG_PROFILE("pack_weights", stream);
+  if (wd != nullptr && perm_hw <= 0 && (long long)Cout * Cin * ksize * ksize >= (1 << 16)) {
+    // wd [Cin][taps][Cout] is the transpose of w viewed as [Cout][Cin * taps]: the scatter below would write it 4 bytes
+    // at a time across rows (8.4 M elements for the WGAN critic's Linear(8192, 1024))
+    transpose_tiled(w, Cout, Cin * ksize * ksize, wd, stream, ksize * ksize, perm_hw == -1);
+    wd = nullptr;
+    if (wf == nullptr) return;
+  }
   const int total = Cout * Cin * ksize * ksize;
   int blocks = cdiv(total, 256);
   if (blocks > 1184) blocks = 1184;

@@ -4,6 +4,8 @@
 // 2-3 sweeps a kernel makes over its sample.
 #include "instnorm.cuh"
 
+#include "conv_generic.cuh"
+
 namespace pcg {
 
 constexpr int IN_CX = 32, IN_PY = 8;
@@ -234,6 +236,11 @@ void instnorm_bwd_bwd(const float* q, const float* gy, const float* act_ref, int
 void flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, int c0, bool inverse, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
   PCG_REQUIRE(B >= 1 && B <= 65535 && R >= 1 && C >= 1 && c0 >= 0 && c0 + R * C <= ld, "flatten_nchw: window inside the row");
+  if (B == 1 && (long long)R * C >= (1 << 16)) {          // one big matrix: a plain transpose, tiled through shared memory
+    if (inverse) transpose_tiled(src + c0, C, R, dst, s);
+    else transpose_tiled(src, R, C, dst + c0, s);
+    return;
+  }
   const int blocks = (R * C + 255) / 256;
   const int cap = 64 > 2368 / B ? 64 : 2368 / B;
   launch_k(flatten_nchw_kernel, dim3(blocks < cap ? blocks : cap, B), dim3(256), 0, s, src, R, C, dst, ld, c0, inverse ? 1 : 0);

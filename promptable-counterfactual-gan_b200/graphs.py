@@ -16,6 +16,7 @@ import gc
 import torch
 
 _deferred = []
+capture_log = []          # libpcg kernel launches recorded by each capture() so far (bench.py: launches per replay)
 
 
 def capturing():
@@ -45,12 +46,15 @@ def capture(body, sync=True):
     flush_deferred()
     if sync:
         torch.cuda.synchronize()
+    from . import _lib
     g = torch.cuda.CUDAGraph()
     was_enabled = gc.isenabled()
     gc.disable()
+    n0 = _lib.launch_count()
     try:
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             body()
+        capture_log.append(_lib.launch_count() - n0)
     finally:
         if was_enabled:
             gc.enable()

@@ -236,3 +236,33 @@ def test_reference_sizes_critic_gradients_fp32_and_tensor_cores():
         assert abs(plan.scal[4].item() - sg["generator_loss"]) < tol * abs(sg["generator_loss"]) + 1e-3
         print("generator", _grad_check(plan, plan.G, auxg["G"], tol))
         del plan
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,k,stride,pad", [(3, 13, 64, 128, 3, 2, 0), (2, 6, 16, 8, 3, 2, 0), (4, 7, 32, 64, 3, 2, 1),
+                                                        (2, 4, 256, 256, 4, 1, 0), (2, 28, 8, 4, 3, 2, 0)])
+def test_dilated_forward_convolution_equals_the_data_gradient(N, H, Cin, Cout, k, stride, pad):
+    """pcg_dilate + tap-reversed packing (perm_hw = -1) + pcg_conv_fprop(stride 1) == pcg_conv_dgrad, on the exact fp32
+    kernels, for the geometries of the WGAN-GP critic / generator (incl. the 28 -> 13 and 6 -> 2 layers whose last input
+    row and column receive no gradient); both packing code paths (scatter below 64 K elements, tiled transpose above)."""
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import ops as K
+    torch.manual_seed(H + Cin)
+    Ho = (H + 2 * pad - k) // stride + 1
+    w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.1
+    wd, wdr, wf = (torch.empty(Cout * Cin * k * k, device="cuda") for _ in range(3))
+    K.pack_weights(w, k, wf=wf, wd=wd)
+    K.pack_weights(w, k, wd=wdr, perm_hw=-1)
+    assert torch.equal(wd.view(Cin, k * k, Cout), w.permute(1, 2, 3, 0).reshape(Cin, k * k, Cout))
+    assert torch.equal(wf.view(Cout, k * k, Cin), w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin))
+    assert torch.equal(wdr.view(Cin, k * k, Cout), wd.view(Cin, k * k, Cout).flip(1))
+    dy = torch.randn(N, Ho, Ho, Cout, device="cuda")
+    want = torch.full((N, H, H, Cin), 7.0, device="cuda")
+    K.conv_dgrad(dy, N, H, H, Cin, wd, Cout, k, stride, pad, want)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, H), w.double(), dy.permute(0, 3, 1, 2).double(), stride, pad)
+    assert rel(want, ref.permute(0, 2, 3, 1)) < 1e-5
+    Hp = H + k - 1
+    D = torch.full((N, Hp, Hp, Cout), 7.0, device="cuda")
+    K.dilate(dy, N, Ho, Ho, Cout, stride, k - 1 - pad, Hp, Hp, D)
+    got = torch.full((N, H, H, Cin), 7.0, device="cuda")
+    K.conv_fprop(D, N, Hp, Hp, Cout, wdr, Cin, k, 1, 0, got)
+    assert rel(got, ref.permute(0, 2, 3, 1)) < 1e-5
