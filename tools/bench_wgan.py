@@ -63,5 +63,40 @@ def main():
         torch.cuda.empty_cache()
 
 
+def torch_eager():
+    """The same iteration through torch autograd on this GPU (the oracle's functional restatement moved to cuda: F.conv2d /
+    conv_transpose2d, autograd.grad(create_graph=True), default TF32-off fp32 math), batch 128, n_critic schedule."""
+    from collections import OrderedDict
+    ohp = O.Hyper()
+    B = ohp.batchsize
+    PG, PC = O.synth_params(O.g_shapes(ohp), 7), O.synth_params(O.c_shapes(ohp), 8)
+    S = O.make_state(PG, O.g_buffers(ohp), PC)
+    for k in ("G", "GB", "C"):
+        S[k] = OrderedDict((n, t.detach().cuda().requires_grad_(t.requires_grad)) for n, t in S[k].items())
+    S["adam_g"], S["adam_c"] = O.adam_init(S["G"]), O.adam_init(S["C"])
+    b = {k: v.cuda() for k, v in O.synth_batch(ohp, B, 3).items()}
+    eye = torch.eye(ohp.num_classes, device="cuda")
+
+    def step(i):
+        O.critic_step(S, ohp, b["real"], eye[b["labels"]], b["noise"], b["alpha"])
+        if i % ohp.n_critic == 0:
+            O.generator_step(S, ohp, b["noise_g"], eye[b["labels_g"]])
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for i in range(5):
+            step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 20
+        for i in range(n):
+            step(i)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / n * 1e3
+        print(f"torch eager (autograd, tf32={tf32}): {ms:.3f} ms/batch  {B / ms * 1e3:.0f} samples/s", flush=True)
+
+
 if __name__ == "__main__":
     main()
+    if os.environ.get("PCG_WGAN_TORCH", "1") == "1":
+        torch_eager()
