@@ -264,6 +264,15 @@ int pcg_pack_conv_weights(const float* w /*torch OIHW*/, int Cout, int Cin, int 
  * Scratch is sized by the first (eager) call, so run one un-captured pass before CUDA-graph capture. */
 int pcg_set_conv_tensor_cores(int on);
 int pcg_get_conv_tensor_cores(void);
+/* Operand cache of the tensor-core mode.  Every tensor-core call converts its fp32 operands to bf16; with the cache on
+ * (returns the previous setting) a conversion is kept in its own buffer, keyed by (pointer, size, layout), and reused by
+ * later calls while the source tensor is unchanged - the CALLER says when it changed: pcg_operand_cache_invalidate(ptr,
+ * bytes) after any write into [ptr, ptr + bytes), pcg_operand_cache_clear() to drop everything (start of a step, after
+ * inputs were written outside the library).  Producers that are told nothing stay correct with the cache off (default).
+ * New buffers are cudaMalloc'ed: populate by one eager pass before stream capture. */
+int pcg_set_operand_cache(int on);
+void pcg_operand_cache_clear(void);
+void pcg_operand_cache_invalidate(const void* p, long long bytes);
 /* Operand precision of that mode: 3 (default) = bf16x3, every fp32 product emulated as hi*hi + lo*hi + hi*lo (fp32-level
  * results, 3x the tensor work); 1 = plain bf16 operands with fp32 accumulation (what torch autocast runs).  Returns the
  * previous setting. */

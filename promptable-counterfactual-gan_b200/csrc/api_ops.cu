@@ -127,6 +127,13 @@ int pcg_set_conv_tensor_cores(int on) {
   conv_auto_set_tensor_cores(on != 0);
   return 0;
 }
+int pcg_set_operand_cache(int on) {
+  const int prev = conv_auto_operand_cache() ? 1 : 0;
+  conv_auto_set_operand_cache(on != 0);
+  return prev;
+}
+void pcg_operand_cache_clear(void) { conv_auto_cache_clear(); }
+void pcg_operand_cache_invalidate(const void* p, long long bytes) { conv_auto_cache_invalidate(p, (size_t)bytes); }
 int pcg_get_conv_tensor_cores(void) { return conv_auto_tensor_cores() ? 1 : 0; }
 int pcg_set_conv_tensor_core_terms(int terms) {
   const int prev = conv_auto_terms();

@@ -54,6 +54,69 @@ static void* scratch(int slot, size_t bytes, cudaStream_t stream) {
   return s.p;
 }
 
+// ---- operand cache ----------------------------------------------------------------------------------------------
+// Every tensor-core call converts its fp32 operands to bf16 first; in a training step each activation is an operand twice
+// (the next layer's forward and weight gradient), each gradient twice (data and weight gradient), each weight once per
+// pass.  With the cache on (pcg_set_operand_cache(1), the step plans do), a conversion gets its own buffer keyed by
+// (source pointer, size, layout) and is reused while the source is unchanged.  "Unchanged" is the CALLER's knowledge:
+// pcg_operand_cache_invalidate(ptr, bytes) after every write to a tensor (pcg_b200/ops.py does it for every operator it
+// wraps, from the operator's declared write set), pcg_operand_cache_clear() at the start of a step body (inputs were
+// copied in by torch, outside the library).  The decisions are made when a launch is issued, so a captured graph
+// replays exactly the conversions the capturing pass made.
+struct CacheEntry {
+  const float* src;
+  long long n;
+  int layout;          // T | kind << 4 | lo_last << 8 | C << 12 (C only where the layout depends on it)
+  bf16* buf;
+  size_t cap;
+  bool valid;
+};
+static std::vector<CacheEntry> g_cache;
+static bool g_cache_on = false;
+void conv_auto_set_operand_cache(bool on) { g_cache_on = on; }
+bool conv_auto_operand_cache() { return g_cache_on; }
+void conv_auto_cache_clear() {
+  for (auto& e : g_cache) e.valid = false;
+}
+void conv_auto_cache_invalidate(const void* p, size_t bytes) {
+  const char* lo = static_cast<const char*>(p);
+  const char* hi = lo + bytes;
+  for (auto& e : g_cache) {
+    const char* a = reinterpret_cast<const char*>(e.src);
+    if (e.valid && a < hi && lo < a + e.n * sizeof(float)) e.valid = false;
+  }
+}
+enum { KIND_SPLIT = 0, KIND_DGRAD_PACK = 2 };
+// Returns the entry for this key; *fresh = true when the caller must (re)fill entry->buf.
+static CacheEntry* cache_get(const float* src, long long n, int layout, size_t bytes, cudaStream_t stream, bool* fresh) {
+  for (auto& e : g_cache)
+    if (e.src == src && e.n == n && e.layout == layout && e.cap >= bytes) {
+      *fresh = !e.valid;
+      e.valid = true;
+      return &e;
+    }
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &st);
+  if (st != cudaStreamCaptureStatusNone)
+    throw Error(5, "tensor-core operand cache must be populated by an eager pass before stream capture");
+  CacheEntry e{src, n, layout, nullptr, bytes, true};
+  PCG_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&e.buf), bytes));
+  g_cache.push_back(e);
+  *fresh = true;
+  return &g_cache.back();
+}
+// bf16 side output for a producer kernel: the plain-bf16 (T = 1) conversion buffer some consumer has already asked for
+// this tensor, marked valid - or NULL (cache off, bf16x3 mode, or nobody converts this tensor)
+bf16* conv_auto_cache_producer(const float* dst, long long n) {
+  if (!g_cache_on) return nullptr;
+  for (auto& e : g_cache)
+    if (e.src == dst && e.n == n && e.layout == 1) {
+      e.valid = true;
+      return e.buf;
+    }
+  return nullptr;
+}
+
 static bf16* to_bf16(int slot, const float* src, long long n, cudaStream_t s) {
   bf16* dst = reinterpret_cast<bf16*>(scratch(slot, (size_t)n * sizeof(bf16), s));
   convert_from_f32<bf16>(src, n, dst, s);
@@ -108,7 +171,15 @@ int conv_auto_terms() { return terms(); }
 
 static bf16* split(int slot, const float* src, long long M, int C, int T, bool lo_last, cudaStream_t s) {
   PCG_REQUIRE(C % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0, "split operand: C % 4 and 16-byte alignment");
-  bf16* dst = reinterpret_cast<bf16*>(scratch(slot, (size_t)M * T * C * sizeof(bf16), s));
+  bf16* dst;
+  if (g_cache_on) {
+    bool fresh;
+    const int layout = T == 1 ? 1 : (T | (lo_last ? 1 << 8 : 0) | C << 12);      // T = 1: a plain copy, whatever the shape
+    dst = cache_get(src, M * C, layout, (size_t)M * T * C * sizeof(bf16), s, &fresh)->buf;
+    if (!fresh) return dst;
+  } else {
+    dst = reinterpret_cast<bf16*>(scratch(slot, (size_t)M * T * C * sizeof(bf16), s));
+  }
   PCG_PROFILE("convert", s);
   long long b = (M * C / 4 + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
@@ -132,7 +203,15 @@ __global__ void split_batch_kernel(const float* __restrict__ src, long long n, i
   }
 }
 static bf16* split_batch(int slot, const float* src, long long n, int T, bool lo_last, cudaStream_t s) {
-  bf16* dst = reinterpret_cast<bf16*>(scratch(slot, (size_t)n * T * sizeof(bf16), s));
+  bf16* dst;
+  if (g_cache_on) {
+    bool fresh;
+    const int layout = T == 1 ? 1 : (T | 1 << 4 | (lo_last ? 1 << 8 : 0));
+    dst = cache_get(src, n, layout, (size_t)n * T * sizeof(bf16), s, &fresh)->buf;
+    if (!fresh) return dst;
+  } else {
+    dst = reinterpret_cast<bf16*>(scratch(slot, (size_t)n * T * sizeof(bf16), s));
+  }
   PCG_PROFILE("convert", s);
   long long b = (n + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
@@ -167,8 +246,14 @@ bool conv_dgrad_auto(const float* dout, const ConvGeom& g, const float* wd, cons
   const int T = terms();
   const long long nin = g.Min() * g.Cin;
   const bf16* dyb = split(SL_X, dout, g.Mout(), g.Cout, T, false, s);                                  // [Mout][hi | lo | hi]
-  bf16* packed = reinterpret_cast<bf16*>(scratch(SL_W, (size_t)16 * T * g.Cout * g.Cin * sizeof(bf16), s));
-  pack_dgrad_s2_k4_tc(wd, g.Cout, g.Cin, packed, s, T);
+  bf16* packed;
+  bool fresh = true;
+  if (g_cache_on)
+    packed = cache_get(wd, (long long)16 * g.Cout * g.Cin, T | KIND_DGRAD_PACK << 4, (size_t)16 * T * g.Cout * g.Cin * sizeof(bf16),
+                       s, &fresh)->buf;
+  else
+    packed = reinterpret_cast<bf16*>(scratch(SL_W, (size_t)16 * T * g.Cout * g.Cin * sizeof(bf16), s));
+  if (fresh) pack_dgrad_s2_k4_tc(wd, g.Cout, g.Cin, packed, s, T);
   ConvEpilogue c;
   c.act = e.act; c.slope = e.slope;
   if (e.add_src != nullptr) c.add_src = to_bf16(SL_E, e.add_src, nin, s);

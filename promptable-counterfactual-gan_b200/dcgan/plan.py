@@ -304,11 +304,16 @@ class DcganPlan:
     def _tc(self, fn):
         K.set_conv_tensor_cores(self.tc)
         prev = K.set_conv_tensor_core_terms(self.terms)
+        # bf16 conversions of unchanged operands are reused within this body (ops.set_operand_cache); nothing survives
+        # from before it: the step inputs were written by torch
+        prev_cache = K.set_operand_cache(self.tc and os.environ.get("PCG_OPERAND_CACHE", "1") != "0")
+        K.operand_cache_clear()
         try:
             fn()
         finally:
             K.set_conv_tensor_cores(False)
             K.set_conv_tensor_core_terms(prev)
+            K.set_operand_cache(prev_cache)
 
     def _body(self):
         def both():

@@ -30,6 +30,7 @@ def _L():
 # call is not launched but appended to it with its read set (every tensor reachable from the arguments) and write set,
 # so that the step plans can be re-emitted onto several streams with exactly the dependencies the data flow requires.
 _rec = None
+_cache_on = False       # tensor-core operand cache (set_operand_cache): the wrappers report every operator's writes to it
 
 
 def _tensors(v, out):
@@ -59,13 +60,20 @@ def _op(*writes, reads=None):
 
         @functools.wraps(fn)
         def wrapper(*args, **kwargs):
-            if _rec is None:
+            if _rec is None and not _cache_on:
                 return fn(*args, **kwargs)
             b = sig.bind(*args, **kwargs)
             b.apply_defaults()
             w = []
             for name in writes:
                 _tensors(name(b.arguments) if callable(name) else b.arguments[name], w)
+            if _rec is None:
+                # cached bf16 conversions of the tensors this operator overwrites are stale from here on
+                inval = _L().pcg_operand_cache_invalidate
+                for t in w:
+                    t = t[0] if isinstance(t, tuple) else t
+                    inval(ctypes.c_void_p(t.data_ptr()), _ll(t.numel() * t.element_size()))
+                return fn(*args, **kwargs)
             r = _tensors(reads(b.arguments) if reads is not None else list(b.arguments.values()), [])
             _rec.add(fn, args, kwargs, r, w)
             return None
@@ -94,6 +102,25 @@ def set_conv_tensor_cores(on):
     """Routes eligible conv_fprop / conv_dgrad / conv_wgrad calls to the tcgen05 kernels (bf16 operands, fp32
     accumulation); off = exact fp32 on the CUDA cores.  See include/pcg.h pcg_set_conv_tensor_cores."""
     _lib.check(_L().pcg_set_conv_tensor_cores(1 if on else 0))
+
+
+def set_operand_cache(on):
+    """Tensor-core operand cache (include/pcg.h): on = reuse the bf16 conversions of unchanged operands.  While it is on,
+    every operator wrapper of this module invalidates the conversions of the tensors it writes; tensors written by anything
+    else (torch copies of the step inputs) need ``operand_cache_clear()``.  Returns the previous setting."""
+    global _cache_on
+    L = _L()
+    L.pcg_operand_cache_invalidate.restype = None
+    L.pcg_operand_cache_clear.restype = None
+    prev = bool(L.pcg_set_operand_cache(1 if on else 0))
+    _cache_on = bool(on)
+    return prev
+
+
+def operand_cache_clear():
+    L = _L()
+    L.pcg_operand_cache_clear.restype = None
+    L.pcg_operand_cache_clear()
 
 
 def set_conv_tensor_core_terms(terms):
