@@ -154,7 +154,8 @@ int pcg_bn_train_fwd(const float* y, long long M, int C, const float* gamma, con
   bn_stats_partial<float>(y, M, C, scratch, ST);
   bn_finalize(scratch, STAT_PARTS, M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, rstd, scale,
               shift, ST);
-  bn_apply_act<float>(y, scale, shift, M, C, act, slope, z, ST);
+  // if a tensor-core consumer keeps a bf16 conversion of z (operand cache), write it here instead of in a pass of its own
+  bn_apply_act<float>(y, scale, shift, M, C, act, slope, z, ST, conv_auto_cache_producer(z, M * C));
   PCG_API_END
 }
 int pcg_bn_train_bwd(const float* dz, const float* y, long long M, int C, const float* gamma, const float* mean,
@@ -168,7 +169,8 @@ int pcg_bn_train_bwd(const float* dz, const float* y, long long M, int C, const 
   }
   bn_bwd_partial<float>(dz, y, mean, rstd, scale, shift, gscale, act, slope, M, C, scratch, ST);
   bn_bwd_finalize(scratch, STAT_PARTS, M, C, dgamma, dbeta, c12, ST);
-  bn_bwd_apply<float>(dz, y, mean, rstd, scale, shift, gamma, c12, gscale, act, slope, M, C, dy, scratch2, ST);
+  bn_bwd_apply<float>(dz, y, mean, rstd, scale, shift, gamma, c12, gscale, act, slope, M, C, dy, scratch2, ST,
+                      conv_auto_cache_producer(dy, M * C));
   if (dbias_prev) colsum_finalize(scratch2, STAT_PARTS, C, C, dbias_prev, ST);
   PCG_API_END
 }

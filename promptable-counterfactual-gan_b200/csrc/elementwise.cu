@@ -266,7 +266,7 @@ static int ew_blocks(long long n) {
 template <typename T, int V, int ACT>
 __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, long long nv, int C,
-                                                          float slope, T* __restrict__ z) {
+                                                          float slope, T* __restrict__ z, bf16* __restrict__ side) {
   pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,10 +283,12 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
 #pragma unroll
     for (int j = 0; j < V; ++j) va[j] = act_fwd(fmaf(va[j], a[j], b[j]), ACT, slope);
     stv(z + i * V, va);
+    if (side) stv(side + i * V, va);           // bf16 copy for the tensor-core operand cache (fp32-storage plans)
     if (two) {
 #pragma unroll
       for (int j = 0; j < V; ++j) vb[j] = act_fwd(fmaf(vb[j], a[j], b[j]), ACT, slope);
       stv(z + i2 * V, vb);
+      if (side) stv(side + i2 * V, vb);
     }
   }
 }
@@ -300,10 +302,10 @@ static int ew_blocks_periodic(long long nvec, int period) {
 
 template <typename T>
 void bn_apply_act(const T* y, const float* scale, const float* shift, long long M, int C, int act, float slope, T* z,
-                  cudaStream_t s) {
+                  cudaStream_t s, bf16* side) {
   PCG_PROFILE("bn_apply", s);
   PCG_REQUIRE(C % 4 == 0, "C % 4");
-#define PCG_L(V, A) launch_k(bn_apply_act_kernel<T, V, A>, dim3(ew_blocks_periodic(nv, C / V)), dim3(256), 0, s, y, scale, shift, nv, C, slope, z)
+#define PCG_L(V, A) launch_k(bn_apply_act_kernel<T, V, A>, dim3(ew_blocks_periodic(nv, C / V)), dim3(256), 0, s, y, scale, shift, nv, C, slope, z, side)
 #define PCG_LA(V) { if (act == ACT_LRELU) PCG_L(V, ACT_LRELU); else if (act == ACT_RELU) PCG_L(V, ACT_RELU); else PCG_L(V, ACT_NONE); }
   if (C % 8 == 0 && wide_ok<T>(8, {y, z})) {
     const long long nv = M * C / 8;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ c12, float gscale, float slope, long long M, int C,
-                    T* __restrict__ dy, float* __restrict__ part_db) {
+                    T* __restrict__ dy, float* __restrict__ part_db, bf16* __restrict__ side) {
   pdl_enter();
   const int lpr = C >> 2, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
@@ -520,6 +522,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const f
           acc[0][j] += o[j];
         }
         st4(dy + rr * C + cg * 4, o);
+        if (side) st4(side + rr * C + cg * 4, o);
       }
     }
   }
@@ -529,11 +532,11 @@ bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const f
 template <typename T>
 void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rstd, const float* scale,
                   const float* shift, const float* gamma, const float* c12, float gscale, int act, float slope,
-                  long long M, int C, T* dy, float* part_db, cudaStream_t s) {
+                  long long M, int C, T* dy, float* part_db, cudaStream_t s, bf16* side) {
   PCG_PROFILE("bn_bwd_apply", s);
   (void)gamma;
   check_colshape(C);
-#define PCG_L(A) launch_k(bn_bwd_apply_kernel<T, A>, dim3(STAT_PARTS), dim3(256), 0, s, dsrc, y, mean, rstd, scale, shift, c12, gscale, slope, M, C, dy, part_db)
+#define PCG_L(A) launch_k(bn_bwd_apply_kernel<T, A>, dim3(STAT_PARTS), dim3(256), 0, s, dsrc, y, mean, rstd, scale, shift, c12, gscale, slope, M, C, dy, part_db, side)
   if (act == ACT_LRELU) PCG_L(ACT_LRELU);
   else if (act == ACT_RELU) PCG_L(ACT_RELU);
   else PCG_L(ACT_NONE);
@@ -1154,14 +1157,14 @@ void convert_from_f32(const float* src, long long n, T* dst, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 #define INST(T)                                                                                                    \
   template void bn_stats_partial<T>(const T*, long long, int, float*, cudaStream_t);                               \
-  template void bn_apply_act<T>(const T*, const float*, const float*, long long, int, int, float, T*, cudaStream_t); \
+  template void bn_apply_act<T>(const T*, const float*, const float*, long long, int, int, float, T*, cudaStream_t, bf16*); \
   template void bn_apply_residual<T>(const T*, const T*, const float*, const float*, float, long long, int, T*,    \
                                      cudaStream_t);                                                                \
   template void bn_bwd_partial<T>(const T*, const T*, const float*, const float*, const float*, const float*,      \
                                   float, int, float, long long, int, float*, cudaStream_t);                        \
   template void bn_bwd_apply<T>(const T*, const T*, const float*, const float*, const float*, const float*,        \
                                 const float*, const float*, float, int, float, long long, int, T*, float*,          \
-                                cudaStream_t);                                                                     \
+                                cudaStream_t, bf16*);                                                              \
   template void colsum_partial<T>(const T*, long long, int, float*, cudaStream_t);                                 \
   template void g_input<T>(const float*, const float*, const long long*, const float*, int, int, T*, cudaStream_t); \
   template void d_input<T>(const float*, const float*, const long long*, int, int, T*, cudaStream_t);              \

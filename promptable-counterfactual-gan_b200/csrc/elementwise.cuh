@@ -20,7 +20,7 @@ void bn_finalize(const float* part, int nparts, long long M, int C, const float*
 // z = act(scale*y + shift)
 template <typename T>
 void bn_apply_act(const T* y, const float* scale, const float* shift, long long M, int C, int act, float slope,
-                  T* z, cudaStream_t s);
+                  T* z, cudaStream_t s, bf16* side = nullptr);     // side: optional bf16 copy of z (operand cache)
 // out = h + res_scale * (scale*y + shift)          (generator.py:22)
 template <typename T>
 void bn_apply_residual(const T* y, const T* h, const float* scale, const float* shift, float res_scale,
@@ -38,7 +38,7 @@ void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* d
 template <typename T>
 void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rstd, const float* scale,
                   const float* shift, const float* gamma, const float* c12, float gscale, int act, float slope,
-                  long long M, int C, T* dy, float* part_db, cudaStream_t s);
+                  long long M, int C, T* dy, float* part_db, cudaStream_t s, bf16* side = nullptr);
 // out[C] = sum over `nparts` rows of part[.][stride] (first C columns), fixed order, fp64 accumulate.
 void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s);
 // part[STAT_PARTS][C] = column sums of a[M][C]
