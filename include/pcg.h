@@ -407,6 +407,24 @@ int pcg_instnorm_bwd_bwd(const float* q, const float* gy, const float* act_ref, 
                          const float* mean, const float* rstd, const float* gamma, int N, int P, int C, float* gy_bar,
                          float* x_bar, float* dgamma_part, void* stream);
 int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, int c0, int inverse, void* stream);
+/* One call (two launches: the batch statistics are one grid-wide dependency) per half of a FiLM residual block of the
+ * tabular generator (house_sales_kc_usa/models/generator.py:19-35: nn.Linear(H, H) -> nn.BatchNorm1d(H) in training mode ->
+ * FiLM -> ReLU or residual add), H in {32, 64} (pcg_film_layer_supported), instead of five / six primitive operators.
+ * scratch: pcg_stat_scratch_floats(H) floats private to the call (per-CTA partial sums).
+ *   fwd:  u = x W^T + bias;  n = BN(u) (saves mean / rstd / scale / shift, updates the running buffers like
+ *         pcg_bn_train_fwd);  f = fg * n + fb ([M][H] FiLM tensors);  out = relu ? max(f, 0) : res + f
+ *   bwd:  given d_f = dL/df:  dfg (+)= d_f * n;  dfb (+)= d_f (accumulate != 0: +=);  du = BatchNorm backward of d_f * fg
+ *         (written: the weight gradient needs it), dgamma / dbeta;  dx = du W (+ add_src), zeroed where act_ref <= 0.
+ * W is the torch [out][in] weight in both calls. */
+int pcg_film_layer_supported(long long M, int H);
+int pcg_film_layer_fwd(const float* x, long long M, int H, const float* W, const float* bias, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var, long long* nbt,
+                       float* mean, float* rstd, float* scale, float* shift, const float* fg, const float* fb,
+                       const float* res, int relu, float* u, float* n, float* out, float* scratch, void* stream);
+int pcg_film_layer_bwd(const float* d_f, long long M, int H, const float* fg, const float* n, const float* u,
+                       const float* mean, const float* rstd, const float* gamma, const float* W, const float* add_src,
+                       const float* act_ref, int accumulate, float* dfg, float* dfb, float* du, float* dx, float* dgamma,
+                       float* dbeta, float* scratch, void* stream);
 /* y[r][c] = x[r][c] + bias[c], tanh applied when tanh_out != 0: the bias (and final Tanh, mnist_wgan_conditional.py:62-72)
  * of a ConvTranspose2d whose product was computed as a data gradient.  In place (y == x) allowed. */
 int pcg_bias_act(const float* x, long long rows, int C, const float* bias, int tanh_out, float* y, void* stream);

@@ -10,6 +10,7 @@
 #include "elementwise.cuh"
 #include "ops.cuh"
 #include "instnorm.cuh"
+#include "film_layer.cuh"
 
 using namespace pcg;
 
@@ -45,7 +46,8 @@ int pcg_conv_fprop(const float* in, int N, int H, int W, int Cin, const float* w
   GenEpilogue<float> e;
   e.bias = bias; e.act = act; e.slope = slope; e.add_src = add_src;
   if (bias == nullptr && add_src == nullptr && skinny_on() && c1k4_supported(geom(N, H, W, Cin, Cout, k, stride, pad))) {
-    c1k4_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, act, slope, out, ST);
+    c1k4_fprop(in, geom(N, H, W, Cin, Cout, k, stride, pad), wf, act, slope, out, ST,
+               conv_auto_cache_producer(out, (long long)N * (H / 2) * (W / 2) * Cout));
     return 0;
   }
   if (skinny_on() && !conv_auto_tensor_cores() && linear_small_supported(geom(N, H, W, Cin, Cout, k, stride, pad), N)) {
@@ -356,6 +358,29 @@ int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, 
   PCG_API_BEGIN
   PCG_REQUIRE(src && dst, "flatten_nchw: null pointer");
   flatten_nchw(src, B, R, C, dst, ld, c0, inverse != 0, ST);
+  PCG_API_END
+}
+int pcg_film_layer_supported(long long M, int H) { return film_layer_supported(M, H) ? 1 : 0; }
+int pcg_film_layer_fwd(const float* x, long long M, int H, const float* W, const float* bias, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var, long long* nbt,
+                       float* mean, float* rstd, float* scale, float* shift, const float* fg, const float* fb,
+                       const float* res, int relu, float* u, float* n, float* out, float* scratch, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(x && W && bias && gamma && beta && mean && rstd && scale && shift && fg && fb && u && n && out && scratch,
+              "film_layer_fwd: null pointer");
+  film_layer_fwd(x, M, H, W, bias, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, rstd, scale, shift, fg,
+                 fb, res, relu != 0, u, n, out, scratch, ST);
+  PCG_API_END
+}
+int pcg_film_layer_bwd(const float* d_f, long long M, int H, const float* fg, const float* n, const float* u,
+                       const float* mean, const float* rstd, const float* gamma, const float* W, const float* add_src,
+                       const float* act_ref, int accumulate, float* dfg, float* dfb, float* du, float* dx, float* dgamma,
+                       float* dbeta, float* scratch, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(d_f && fg && n && u && mean && rstd && gamma && W && dfg && dfb && du && dx && dgamma && dbeta && scratch,
+              "film_layer_bwd: null pointer");
+  film_layer_bwd(d_f, M, H, fg, n, u, mean, rstd, gamma, W, add_src, act_ref, accumulate != 0, dfg, dfb, du, dx, dgamma,
+                 dbeta, scratch, ST);
   PCG_API_END
 }
 int pcg_bias_act(const float* x, long long rows, int C, const float* bias, int tanh_out, float* y, void* stream) {

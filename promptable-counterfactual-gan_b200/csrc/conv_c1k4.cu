@@ -31,7 +31,7 @@ bool c1k4_supported(const ConvGeom& g) {
 // stay in registers) and walks the block's output positions; consecutive threads write consecutive 16-byte groups.
 __global__ void __launch_bounds__(256)
 c1k4_fprop_kernel(const float* __restrict__ x, const float* __restrict__ wf, int H, int W, int act, float slope,
-                  float* __restrict__ out) {
+                  float* __restrict__ out, bf16* __restrict__ side) {
   pdl_enter();
   __shared__ __align__(16) float sx[2 * C1_ROWS + 2][68];
   __shared__ __align__(16) float sw[16][C1_C + 4];            // [tap][c]: a thread's four channels are one 16-byte read
@@ -50,6 +50,7 @@ c1k4_fprop_kernel(const float* __restrict__ x, const float* __restrict__ wf, int
 #pragma unroll
   for (int t = 0; t < 16; ++t) w[t] = *reinterpret_cast<const float4*>(&sw[t][c4 * 4]);
   float* o = out + ((size_t)n * Ho + oy0) * Wo * C1_C;
+  bf16* o16 = side ? side + ((size_t)n * Ho + oy0) * Wo * C1_C : nullptr;     // bf16 copy for the tensor-core operand cache
   for (int p = p0; p < C1_ROWS * Wo; p += 16) {
     const int oyl = p / Wo, ox = p - oyl * Wo;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -71,13 +72,18 @@ c1k4_fprop_kernel(const float* __restrict__ x, const float* __restrict__ wf, int
       a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
     }
     *reinterpret_cast<float4*>(o + (size_t)p * C1_C + c4 * 4) = a;
+    if (o16) {
+      __nv_bfloat162 h[2] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w)};
+      *reinterpret_cast<uint2*>(o16 + (size_t)p * C1_C + c4 * 4) = *reinterpret_cast<const uint2*>(h);
+    }
   }
 }
 
-void c1k4_fprop(const float* x, const ConvGeom& g, const float* wf, int act, float slope, float* out, cudaStream_t s) {
+void c1k4_fprop(const float* x, const ConvGeom& g, const float* wf, int act, float slope, float* out, cudaStream_t s,
+                bf16* side) {
   PCG_PROFILE("conv_c1k4", s);
   PCG_REQUIRE(c1k4_supported(g), "c1k4 geometry");
-  launch_k(c1k4_fprop_kernel, dim3(g.N * (g.H / 2 / C1_ROWS)), dim3(256), 0, s, x, wf, g.H, g.W, act, slope, out);
+  launch_k(c1k4_fprop_kernel, dim3(g.N * (g.H / 2 / C1_ROWS)), dim3(256), 0, s, x, wf, g.H, g.W, act, slope, out, side);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

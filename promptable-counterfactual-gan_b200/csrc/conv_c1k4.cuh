@@ -8,7 +8,8 @@ namespace pcg {
 
 bool c1k4_supported(const ConvGeom& g);
 // out[N][H/2][W/2][64] = act(conv(x[N][H][W][1])), wf = [64][16]
-void c1k4_fprop(const float* x, const ConvGeom& g, const float* wf, int act, float slope, float* out, cudaStream_t s);
+void c1k4_fprop(const float* x, const ConvGeom& g, const float* wf, int act, float slope, float* out, cudaStream_t s,
+                bf16* side = nullptr);      // side: optional bf16 copy of out (tensor-core operand cache)
 // dx[N][H][W][1] = data gradient of that convolution, wd = [16][64]
 void c1k4_dgrad(const float* dy, const ConvGeom& g, const float* wd, float* dx, cudaStream_t s);
 // dw[64][1][4][4]; scratch holds c1k4_wgrad_scratch() floats

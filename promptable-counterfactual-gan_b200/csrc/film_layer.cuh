@@ -1,0 +1,17 @@
+// Fused halves of a FiLM residual block (see film_layer.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pcg {
+
+bool film_layer_supported(long long M, int H);
+void film_layer_fwd(const float* x, long long M, int H, const float* W, const float* bias, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var, long long* nbt,
+                    float* mean, float* rstd, float* scale, float* shift, const float* fg, const float* fb, const float* res,
+                    bool relu, float* u, float* n, float* out, float* part, cudaStream_t s);
+void film_layer_bwd(const float* d_f, long long M, int H, const float* fg, const float* n, const float* u, const float* mean,
+                    const float* rstd, const float* gamma, const float* W, const float* add_src, const float* act_ref,
+                    bool accumulate, float* dfg, float* dfb, float* du, float* dx, float* dgamma, float* dbeta, float* part,
+                    cudaStream_t s);   // part: pcg_stat_scratch_floats(H) floats, private to the call
+
+}  // namespace pcg

@@ -153,6 +153,42 @@ class Program:
             depth.append(1 + max((depth[d] for d in op.deps), default=0))
         return max(depth, default=0)
 
+    def timed_critical_path(self, repeats=8):
+        """Times every operator on the device (its own little CUDA graph replayed ``repeats`` times between two events, so
+        that host launch latency is out of the number) and returns (longest dependency path in us, [(op index, name, us)]
+        along it, total us of all operators): what bounds the emitted graph once launch latency is hidden by the parallel
+        branches.  Executes every operator several times in program order: the caller restores any state."""
+        from . import graphs
+        n = len(self.ops)
+        us = [0.0] * n
+        prev, K._rec = K._rec, None
+        try:
+            for i, op in enumerate(self.ops):
+                op.fn(*op.args, **op.kwargs)
+                g = graphs.capture(lambda: [op.fn(*op.args, **op.kwargs) for _ in range(repeats)], sync=True)
+                g.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                us[i] = e0.elapsed_time(e1) * 1e3 / repeats
+                del g
+        finally:
+            K._rec = prev
+        best, back = [0.0] * n, [-1] * n
+        for i, op in enumerate(self.ops):
+            for d in op.deps:
+                if best[d] > best[i]:
+                    best[i], back[i] = best[d], d
+            best[i] += us[i]
+        end = max(range(n), key=lambda i: best[i]) if n else -1
+        path, i = [], end
+        while i >= 0:
+            path.append((i, getattr(self.ops[i].fn, "__name__", "?"), us[i]))
+            i = back[i]
+        return (best[end] if n else 0.0), path[::-1], sum(us)
+
     # ------------------------------------------------------------------ emission
     def emit(self, streams=None):
         """Launches the recorded operators on ``n_streams`` streams (stream 0 = the current one) with event waits for the

@@ -405,6 +405,33 @@ def flatten_nchw(src, B, R, C, dst, ld, c0=0, inverse=False):
     _lib.check(_L().pcg_flatten_nchw(P(src), B, R, C, P(dst), ld, c0, 1 if inverse else 0, _s()))
 
 
+def film_layer_supported(M, H):
+    return bool(_L().pcg_film_layer_supported(_ll(M), H))
+
+
+@_op("running_mean", "running_var", "nbt", "u", "n", "out",
+     lambda a: [a["st"].mean, a["st"].rstd, a["st"].scale, a["st"].shift, a["st"].scratch])
+def film_layer_fwd(x, W, bias, gamma, beta, running_mean, running_var, nbt, st, fg, fb, u, n, out, res=None, relu=False,
+                   eps=1e-5, momentum=0.1):
+    """One call: Linear(H, H) -> BatchNorm1d (training) -> FiLM -> ReLU (relu=True) or ``res +`` (pcg_film_layer_fwd)."""
+    M, H = x.shape
+    _chk(x, W, bias, gamma, beta, running_mean, running_var, fg, fb, u, n, out, res)
+    _lib.check(_L().pcg_film_layer_fwd(P(x), _ll(M), H, P(W), P(bias), P(gamma), P(beta), _f(eps), _f(momentum),
+                                       P(running_mean), P(running_var), P(nbt), P(st.mean), P(st.rstd), P(st.scale),
+                                       P(st.shift), P(fg), P(fb), P(res), 1 if relu else 0, P(u), P(n), P(out),
+                                       P(st.scratch), _s()))
+
+
+@_op("dfg", "dfb", "du", "dx", "dgamma", "dbeta", lambda a: [a["st"].scratch2])
+def film_layer_bwd(d_f, fg, n, u, st, gamma, W, dfg, dfb, du, dx, dgamma, dbeta, add_src=None, act_ref=None,
+                   accumulate=False):
+    M, H = d_f.shape
+    _chk(d_f, fg, n, u, gamma, W, dfg, dfb, du, dx, dgamma, dbeta, add_src, act_ref)
+    _lib.check(_L().pcg_film_layer_bwd(P(d_f), _ll(M), H, P(fg), P(n), P(u), P(st.mean), P(st.rstd), P(gamma), P(W),
+                                       P(add_src), P(act_ref), 1 if accumulate else 0, P(dfg), P(dfb), P(du), P(dx),
+                                       P(dgamma), P(dbeta), P(st.scratch2), _s()))
+
+
 @_op("y")
 def bias_act(x, C, bias, y, tanh_out=False):
     _chk(x, bias, y)

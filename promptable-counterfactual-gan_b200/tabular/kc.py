@@ -167,6 +167,14 @@ class KcPlan:
         self.c_d2 = [z(B, b) for _, b in cdims]
         self.clog, self.cdlog = z(B, nc), z(B, nc)
         self.clog0 = z(B, nc)
+        # the training step sees the frozen classifier with every eval-mode BatchNorm folded into the Linear behind it
+        # (refresh()): W' = W diag(s), b' = b + W t with s = gamma / sqrt(var + eps), t = beta - mean * s; five launches
+        # forward and five backward (LeakyReLU' in the data-gradient epilogue) instead of nine and thirteen
+        cfull = cdims + [(64, nc)]
+        self.cwf = [None] + [z(b, a) for a, b in cfull[1:]]
+        self.cwfT = [None] + [z(a, b) for a, b in cfull[1:]]
+        self.cbf = [None] + [z(b) for _, b in cfull[1:]]
+        self.c_dh = [z(B, b) for _, b in cdims]
         # ---- categorical value maps (trainer.py:205-224); default = the /(n-1) fallback
         self.nv = OrderedDict()
         for f, n in self.cat.items():
@@ -195,8 +203,13 @@ class KcPlan:
         self.d_rm, self.d_pen, self.d_l1, self.d_masked, self.d_res, self.dx_adv, self.dx_cls = (z(B, d) for _ in range(7))
         self.d_contp = z(B, len(self.cont))
         self.dhA, self.dhB, self.tmp_h, self.df, self.dn, self.du = (z(B, h) for _ in range(6))
+        self.dh_parts = [z(B, h) for _ in range(len(self.cat) + 1)]
         self.dz = z(B, 1)
         self.scal = z(16)   # 0 d_loss 1 g_loss 2 g_adv 3 g_cls 4 reg 5 mask_pen 6 pred_gain.. 7/8 d terms 9 D(real) 10 D(fake)
+        # one launch per half residual block (csrc/film_layer.cu) where the shape allows; PCG_FILM_LAYER=0: the five / six
+        # primitive operators
+        import os
+        self.fused = os.environ.get("PCG_FILM_LAYER", "1") != "0" and K.film_layer_supported(B, h)
         self.run = GraphStep(self._body, self._state, self.refresh, use_graph)
         self.refresh()
 
@@ -228,6 +241,15 @@ class KcPlan:
 
     def refresh(self):
         K.transpose_multi([(L.W(), L.wT) for L in self._all_dense()])
+        with torch.no_grad():
+            for j in range(1, 5):
+                nm = self.c_bn_names[j - 1]
+                s = self.C.p(nm + ".weight") * torch.rsqrt(self.c_rv[j - 1] + 1e-5)
+                t = self.C.p(nm + ".bias") - self.c_rm[j - 1] * s
+                W = self.cl[j].W()
+                torch.mul(W, s[None, :], out=self.cwf[j])
+                self.cwfT[j].copy_(self.cwf[j].t())
+                torch.addmv(self.cl[j].b(), W, t, out=self.cbf[j])
 
     def _state(self):
         t = [self.G.data, self.G.m, self.G.v, self.G.step, self.D.flat.data, self.D.flat.m, self.D.flat.v, self.D.flat.step]
@@ -251,6 +273,13 @@ class KcPlan:
             b["hin"] = hcur
             b["fg"].fwd(self.cond, b["g"])
             b["fb"].fwd(self.cond, b["b"])
+            if self.fused and training:
+                for fc, bn, xin, u, n, out, res in ((b["fc1"], b["bn1"], hcur, b["u1"], b["n1"], b["r1"], None),
+                                                    (b["fc2"], b["bn2"], b["r1"], b["u2"], b["n2"], b["hout"], hcur)):
+                    K.film_layer_fwd(xin, fc.W(), fc.b(), bn.flat.p(bn.name + ".weight"), bn.flat.p(bn.name + ".bias"),
+                                     bn.rm, bn.rv, bn.nbt, bn.st, b["g"], b["b"], u, n, out, res=res, relu=res is None)
+                hcur = b["hout"]
+                continue
             b["fc1"].fwd(hcur, b["u1"])
             b["bn1"].fwd(b["u1"], b["n1"], training=training)
             K.film_fwd(b["g"], b["n1"], b["b"], b["r1"], relu=True)                   # r1 = ReLU(FiLM(BN1(fc1 h)))
@@ -310,17 +339,18 @@ class KcPlan:
         K.gan_loss(out_g, K.GAN_WASSERSTEIN, 1.0, self.scal[2:3], self.dz, out_aux=self.scal[10:11])
         ddin = D.bwd(self.dz, 1, None, want_dx=True)
         K.copy_cols(ddin, 0, self.dx_adv, 0, d)
-        self._c_fwd(self.xcf, self.clog)
+        # frozen classifier, BatchNorm folded (see __init__): forward and input gradient
+        self.cl[0].fwd(self.xcf, self.c_act[0], K.ACT_LRELU, 0.1)
+        for j in range(1, 4):
+            K.linear_fwd(self.c_act[j - 1], self.cwf[j], self.c_act[j], self.cbf[j], K.ACT_LRELU, 0.1)
+        K.linear_fwd(self.c_act[3], self.cwf[4], self.clog, self.cbf[4])
         K.ce_loss(self.clog, self.target, self.scal[3:4], self.cdlog, wgt=lam[0])
         dcur = self.cdlog
-        for j in range(4, -1, -1):
-            if j == 0:
-                self.cl[0].dgrad(dcur, self.dx_cls)
-                break
-            self.cl[j].dgrad(dcur, self.c_d[j - 1])                                   # wrt BatchNorm(eval) output j-1
-            K.scale_cols(self.c_d[j - 1], self.c_scale[j - 1], self.c_d2[j - 1])      # through the eval-mode affine
-            K.unary_bwd(self.c_d2[j - 1], self.c_act[j - 1], K.LRELU, self.c_d2[j - 1], 0.1)
-            dcur = self.c_d2[j - 1]
+        for j in range(4, 0, -1):
+            K.linear_dgrad(dcur, self.cwfT[j], self.c_dh[j - 1], self.cwf[j].shape[1], act_ref=self.c_act[j - 1],
+                           ref_act=K.ACT_LRELU, ref_slope=0.1)
+            dcur = self.c_dh[j - 1]
+        self.cl[0].dgrad(dcur, self.dx_cls)
         K.rownorm_mean(self.masked, 1, self.scal[4:5], dx=self.d_l1, gscale=lam[1])   # :305
         K.combine([(1.0, self.scal[2:3]), (lam[0], self.scal[3:4]), (lam[1], self.scal[4:5]), (lam[2], self.scal[5:6])],
                   self.scal[1:2])
@@ -342,15 +372,42 @@ class KcPlan:
         for i, f in enumerate(self.cont):
             K.copy_cols(self.d_res, f, self.d_contp, i, 1, alpha=0.1)                 # * residual_scaling
         self.fc_cont.wgrad(h, self.d_contp)
-        self.fc_cont.dgrad(self.d_contp, self.dhA)
-        for f, head in self.heads.items():
+        parts = self.dh_parts                        # one buffer per head: the eight data gradients run side by side ...
+        self.fc_cont.dgrad(self.d_contp, parts[0])
+        for i, (f, head) in enumerate(self.heads.items()):
             K.copy_cols(self.d_res, f, self.dcols[f], 0, 1)
             K.linear_dgrad(self.dcols[f], self.nv[f].view(-1, 1), self.dsamples[f], self.cat[f])   # d samples = d scalar * norm_vals
             K.softmax_bwd(self.dsamples[f], self.samples[f], self.tau, self.dlogits[f])
             head.wgrad(h, self.dlogits[f])
-            head.dgrad(self.dlogits[f], self.dhA, add_src=self.dhA)
+            head.dgrad(self.dlogits[f], parts[i + 1])
+        live = list(parts[:len(self.heads) + 1])     # ... and meet in a tree of adds (a chain through add_src was 8 deep)
+        while len(live) > 1:
+            nxt = []
+            for a in range(0, len(live) - 1, 2):
+                dst = self.dhA if len(live) <= 2 else live[a]
+                K.binary(live[a], live[a + 1], K.ADD, dst)
+                nxt.append(dst)
+            if len(live) % 2:
+                nxt.append(live[-1])
+            live = nxt
+        if live[0] is not self.dhA:
+            K.unary(live[0], K.COPY, self.dhA)
         dh, other = self.dhA, self.dhB
         for b, t in zip(reversed(self.blk), reversed(self.blk_tmp)):
+            if self.fused:
+                bn1, bn2, G = b["bn1"], b["bn2"], self.G
+                K.film_layer_bwd(dh, b["g"], b["n2"], b["u2"], bn2.st, G.p(bn2.name + ".weight"), b["fc2"].W(), b["dg"],
+                                 b["db"], t["du2"], t["df"], G.g(bn2.name + ".weight"), G.g(bn2.name + ".bias"),
+                                 act_ref=b["r1"])                                     # d f1 (through the ReLU)
+                b["fc2"].wgrad(b["r1"], t["du2"])
+                K.film_layer_bwd(t["df"], b["g"], b["n1"], b["u1"], bn1.st, G.p(bn1.name + ".weight"), b["fc1"].W(), b["dg"],
+                                 b["db"], t["du1"], other, G.g(bn1.name + ".weight"), G.g(bn1.name + ".bias"),
+                                 add_src=dh, accumulate=True)                         # skip connection
+                b["fc1"].wgrad(b["hin"], t["du1"])
+                b["fg"].wgrad(self.cond, b["dg"])
+                b["fb"].wgrad(self.cond, b["db"])
+                dh, other = other, dh
+                continue
             # f2 = g*n2 + b ; h' = h + f2
             K.film_bwd(dh, b["g"], b["n2"], t["dn2"], b["dg"], b["db"])              # d n2, d g / d b (first use)
             b["bn2"].bwd(t["dn2"], b["u2"], t["du2"])
