@@ -407,6 +407,13 @@ int pcg_instnorm_bwd_bwd(const float* q, const float* gy, const float* act_ref, 
                          const float* mean, const float* rstd, const float* gamma, int N, int P, int C, float* gy_bar,
                          float* x_bar, float* dgamma_part, void* stream);
 int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, int c0, int inverse, void* stream);
+/* Weight and bias gradient of a small nn.Linear (K inputs, N outputs, both <= 128) in ONE launch: dw[N][K] = dy^T x (torch
+ * layout), db[N] = column sums of dy (NULL: skipped) - instead of pcg_conv_wgrad + pcg_colsum (four launches).  scratch:
+ * pcg_linear_wgrad_small_scratch(M, K, N) floats (-1: shape not supported), 16-byte aligned, zero-initialised once and
+ * private to the call site (it holds per-CTA partials and an arrival ticket that resets itself); deterministic. */
+long long pcg_linear_wgrad_small_scratch(long long M, int K, int N);
+int pcg_linear_wgrad_small(const float* x, const float* dy, long long M, int K, int N, float* scratch, float* dw, float* db,
+                           void* stream);
 /* One call (two launches: the batch statistics are one grid-wide dependency) per half of a FiLM residual block of the
  * tabular generator (house_sales_kc_usa/models/generator.py:19-35: nn.Linear(H, H) -> nn.BatchNorm1d(H) in training mode ->
  * FiLM -> ReLU or residual add), H in {32, 64} (pcg_film_layer_supported), instead of five / six primitive operators.

@@ -360,6 +360,16 @@ int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, 
   flatten_nchw(src, B, R, C, dst, ld, c0, inverse != 0, ST);
   PCG_API_END
 }
+long long pcg_linear_wgrad_small_scratch(long long M, int K, int N) {
+  return linear_wgrad_small_supported(M, K, N) ? linear_wgrad_small_scratch(M, K, N) : -1;
+}
+int pcg_linear_wgrad_small(const float* x, const float* dy, long long M, int K, int N, float* scratch, float* dw, float* db,
+                           void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(x && dy && scratch && dw, "linear_wgrad_small: null pointer");
+  linear_wgrad_small(x, dy, M, K, N, scratch, dw, db, ST);
+  PCG_API_END
+}
 int pcg_film_layer_supported(long long M, int H) { return film_layer_supported(M, H) ? 1 : 0; }
 int pcg_film_layer_fwd(const float* x, long long M, int H, const float* W, const float* bias, const float* gamma,
                        const float* beta, float eps, float momentum, float* running_mean, float* running_var, long long* nbt,

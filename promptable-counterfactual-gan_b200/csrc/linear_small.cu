@@ -131,4 +131,133 @@ void linear_small(const float* in, long long M, int K, int N, const float* w, co
   PCG_LAUNCH_CHECK();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight AND bias gradient of a small Linear layer in ONE launch:  dw[N][K] = dy^T x,  db[N] = column sums of dy
+// (K, N <= 128; the tabular networks: 21..128 wide, 4096 rows).  As primitive operators this is four launches (split-K
+// product, its reduction, column sums, their reduction) per layer, 37 layers per KC iteration - off the critical path, but
+// they occupy the SMs the critical path needs.  P CTAs take row slices; a thread owns up to 16 float4 outputs
+// (n, k4 .. k4+3); every CTA leaves its partial in scratch and the last one to arrive (device-scope ticket) adds them in
+// CTA order: deterministic.  scratch[0] is the ticket, zero between launches.
+constexpr int LW_TR = 32;            // rows per shared-memory tile
+constexpr int LW_MAXP = 64;          // row slices (CTAs)
+
+static int lw_ctas(long long M) {
+  const long long p = (M + 63) / 64;
+  return (int)(p < 1 ? 1 : (p < LW_MAXP ? p : LW_MAXP));
+}
+bool linear_wgrad_small_supported(long long M, int K, int N) { return M >= 1 && K >= 1 && K <= LS_MAXD && N >= 1 && N <= LS_MAXD; }
+long long linear_wgrad_small_scratch(long long M, int K, int N) {
+  const int K4 = (K + 3) / 4;
+  return 4 + (long long)lw_ctas(M) * ((long long)N * K4 * 4 + LS_MAXD);
+}
+
+template <int J>
+__global__ void __launch_bounds__(LS_THREADS)
+linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long M, int K, int N,
+                          float* __restrict__ scratch, float* __restrict__ dw, float* __restrict__ db) {
+  pdl_enter();
+  extern __shared__ __align__(16) float sm[];
+  __shared__ bool last;
+  const int K4 = (K + 3) >> 2, KP = K4 * 4;
+  float* sx = sm;                       // [LW_TR][KP], zero padded columns
+  float* sdy = sm + LW_TR * KP;         // [LW_TR][N]
+  const int nout4 = N * K4;
+  const long long per = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < M ? r0 + per : M;
+  float4 acc[J];
+  int on[J], ok4[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int o = threadIdx.x + LS_THREADS * j;
+    on[j] = o < nout4 ? o / K4 : -1;
+    ok4[j] = o < nout4 ? o - (o / K4) * K4 : 0;
+  }
+  float bsum = 0.f;
+  for (long long t0 = r0; t0 < r1; t0 += LW_TR) {
+    const int nrows = r1 - t0 < LW_TR ? (int)(r1 - t0) : LW_TR;
+    __syncthreads();
+    for (int i = threadIdx.x; i < LW_TR * KP; i += LS_THREADS) {
+      const int r = i / KP, k = i - r * KP;
+      sx[i] = (r < nrows && k < K) ? x[(t0 + r) * K + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < LW_TR * N; i += LS_THREADS) {
+      const int r = i / N;
+      sdy[i] = r < nrows ? dy[(t0 + r) * N + (i - r * N)] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < LW_TR; ++r) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (on[j] >= 0) {
+          const float d = sdy[r * N + on[j]];
+          const float4 xv = *reinterpret_cast<const float4*>(sx + r * KP + ok4[j] * 4);
+          acc[j].x = fmaf(d, xv.x, acc[j].x); acc[j].y = fmaf(d, xv.y, acc[j].y);
+          acc[j].z = fmaf(d, xv.z, acc[j].z); acc[j].w = fmaf(d, xv.w, acc[j].w);
+        }
+      }
+      if (threadIdx.x < N) bsum += sdy[r * N + threadIdx.x];
+    }
+  }
+  const size_t stride = (size_t)nout4 * 4 + LS_MAXD;
+  float* mine = scratch + 4 + (size_t)blockIdx.x * stride;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (on[j] >= 0) *reinterpret_cast<float4*>(mine + (size_t)(threadIdx.x + LS_THREADS * j) * 4) = acc[j];
+  if (threadIdx.x < N) mine[(size_t)nout4 * 4 + threadIdx.x] = bsum;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int P = gridDim.x;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (on[j] < 0) continue;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t off = 4 + (size_t)(threadIdx.x + LS_THREADS * j) * 4;
+    for (int p = 0; p < P; ++p) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(scratch + off + (size_t)p * stride));
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float* o = dw + (size_t)on[j] * K + ok4[j] * 4;
+    const int left = K - ok4[j] * 4;
+    o[0] = t.x;
+    if (left > 1) o[1] = t.y;
+    if (left > 2) o[2] = t.z;
+    if (left > 3) o[3] = t.w;
+  }
+  if (db != nullptr && threadIdx.x < N) {
+    float t = 0.f;
+    for (int p = 0; p < P; ++p) t += __ldcg(scratch + 4 + (size_t)p * stride + (size_t)nout4 * 4 + threadIdx.x);
+    db[threadIdx.x] = t;
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(scratch) = 0u;
+}
+
+void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int N, float* scratch, float* dw, float* db,
+                        cudaStream_t s) {
+  PCG_PROFILE("wgrad_small", s);
+  PCG_REQUIRE(linear_wgrad_small_supported(M, K, N), "linear_wgrad_small: K, N <= 128");
+  PCG_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "linear_wgrad_small: 16-byte aligned scratch");
+  const int K4 = (K + 3) / 4, nout4 = N * K4;
+  const int J = (nout4 + LS_THREADS - 1) / LS_THREADS;
+  const size_t smem = (size_t)LW_TR * (K4 * 4 + N) * sizeof(float);
+  const dim3 grid(lw_ctas(M));
+#define PCG_LW(JJ) launch_k(linear_wgrad_small_kernel<JJ>, grid, dim3(LS_THREADS), smem, s, x, dy, M, K, N, scratch, dw, db)
+  if (J <= 1) PCG_LW(1);
+  else if (J <= 2) PCG_LW(2);
+  else if (J <= 4) PCG_LW(4);
+  else if (J <= 8) PCG_LW(8);
+  else PCG_LW(16);
+#undef PCG_LW
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
 }  // namespace pcg

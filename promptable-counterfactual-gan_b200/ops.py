@@ -5,6 +5,7 @@ caller-allocated torch tensors (fp32, contiguous).  No torch arithmetic happens 
 these wrappers are captured in a CUDA graph, so the Python overhead is paid once.
 """
 import ctypes
+import os
 
 import torch
 
@@ -181,9 +182,31 @@ def linear_dgrad(dy, wT, dx, K, act_ref=None, ref_act=ACT_NONE, ref_slope=0.2, a
     conv_dgrad(dy, B, 1, 1, K, wT, N, 1, 1, 0, dx, add_src, act_ref, ref_act, ref_slope)
 
 
+def linear_wgrad_small_scratch_floats(M, K, N):
+    L = _L()
+    L.pcg_linear_wgrad_small_scratch.restype = ctypes.c_longlong
+    return int(L.pcg_linear_wgrad_small_scratch(_ll(M), K, N))
+
+
+@_op("scratch", "dw", "db")
+def linear_wgrad_small(x, dy, scratch, dw, db=None):
+    """dw[N][K] = dy^T x and db = column sums of dy in one launch (K, N <= 128; pcg_linear_wgrad_small)."""
+    M, K = x.shape
+    _chk(x, dy, scratch, dw, db)
+    _lib.check(_L().pcg_linear_wgrad_small(P(x), P(dy), _ll(M), K, dy.shape[1], P(scratch), P(dw), P(db), _s()))
+
+
+_SMALL_WGRAD = os.environ.get("PCG_SMALL_WGRAD", "1") != "0"
+
+
 def linear_wgrad(x, dy, scratch, dw, db=None, stat=None):
     B, K = x.shape
     N = dy.shape[1]
+    if _SMALL_WGRAD:
+        need = linear_wgrad_small_scratch_floats(B, K, N)
+        if 0 < need <= scratch.numel() and scratch.data_ptr() % 16 == 0:
+            linear_wgrad_small(x, dy, scratch, dw, db)
+            return
     conv_wgrad(x, dy, B, 1, 1, K, N, 1, 1, 0, scratch, dw)
     if db is not None:
         colsum(dy, stat, db)

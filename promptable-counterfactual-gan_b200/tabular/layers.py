@@ -37,7 +37,9 @@ class _OwnScratch:
     write), and the weight gradients are exactly the launches the data-flow capture can take off the critical path."""
 
     def _own_scratch(self, ctx, k_in, n_out):
-        self.wsc = torch.zeros(K.conv_wgrad_scratch_floats(ctx.B, 1, 1, k_in, n_out, 1, 1, 0) + 1024, device=ctx.dev)
+        need = max(K.conv_wgrad_scratch_floats(ctx.B, 1, 1, k_in, n_out, 1, 1, 0),
+                   K.linear_wgrad_small_scratch_floats(ctx.B, k_in, n_out))       # -1 when the one-launch kernel does not apply
+        self.wsc = torch.zeros(need + 1024, device=ctx.dev)
         self.stat = K.stat_scratch(max(n_out, 4), ctx.dev)
 
 

@@ -61,3 +61,29 @@ def test_full_window_data_gradient_is_a_column_tiled_product(N, Cin, Cout, k):
     assert rel(din, want) < 2e-5
     Kk.conv_dgrad(dout, N, k, k, Cin, wd, Cout, k, 1, 0, din, add_src=skip, act_ref=ref, ref_act=Kk.ACT_RELU)
     assert rel(din, (want + skip.double()) * (ref.double() > 0)) < 2e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(4096, 32, 32), (4096, 38, 32), (4096, 21, 32), (4096, 64, 128), (4096, 128, 64),
+                                   (4096, 128, 128), (4096, 128, 1), (64, 2, 32), (1000, 32, 7), (37, 17, 3), (5, 1, 1)])
+def test_one_launch_weight_and_bias_gradient(M, K, N):
+    """pcg_linear_wgrad_small against float64 torch; repeated launches reuse the scratch (the arrival ticket resets itself)
+    and are bit-identical (fixed summation order)."""
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import ops as Kk
+    torch.manual_seed(M + K + N)
+    x, dy = torch.randn(M, K, device="cuda"), torch.randn(M, N, device="cuda")
+    need = Kk.linear_wgrad_small_scratch_floats(M, K, N)
+    assert need > 0 and Kk.linear_wgrad_small_scratch_floats(M, 129, N) == -1
+    scratch = torch.zeros(need, device="cuda")
+    dw, db = torch.full((N, K), 9.0, device="cuda"), torch.full((N,), 9.0, device="cuda")
+    Kk.linear_wgrad_small(x, dy, scratch, dw, db)
+    assert rel(dw, dy.double().t() @ x.double()) < 2e-5 and rel(db, dy.double().sum(0)) < 2e-5
+    dw2, db2 = torch.empty_like(dw), torch.empty_like(db)
+    Kk.linear_wgrad_small(x, dy, scratch, dw2, db2)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    Kk.linear_wgrad_small(x, dy, scratch, dw2)                          # no bias gradient
+    assert torch.equal(dw, dw2)
+    # the dispatcher of ops.linear_wgrad takes it when the caller's scratch is large enough
+    dw3, db3 = torch.empty_like(dw), torch.empty_like(db)
+    Kk.linear_wgrad(x, dy, scratch, dw3, db3, Kk.stat_scratch(max(N, 4), "cuda"))
+    assert torch.equal(dw, dw3) and torch.equal(db, db3)
