@@ -71,9 +71,10 @@ def record(body):
 
 
 class Program:
-    def __init__(self, ops, max_streams=16):
+    def __init__(self, ops, max_streams=None):
+        import os
         self.ops = ops
-        self.max_streams = max_streams
+        self.max_streams = int(os.environ.get("PCG_DATAFLOW_STREAMS", "32")) if max_streams is None else max_streams
         self._dependencies()
         self._assign_streams()
 
