@@ -11,6 +11,8 @@
 // is the same call with the transposed weight the plans already keep ([K][N] = "[out][in]" of the backward product).
 #include "linear_small.cuh"
 
+#include <unordered_map>
+
 namespace pcg {
 
 constexpr int LS_ROWS = 64, LS_THREADS = 256, LS_MAXD = 128;
@@ -137,7 +139,8 @@ void linear_small(const float* in, long long M, int K, int N, const float* w, co
 // product, its reduction, column sums, their reduction) per layer, 37 layers per KC iteration - off the critical path, but
 // they occupy the SMs the critical path needs.  P CTAs take row slices; a thread owns up to 16 float4 outputs
 // (n, k4 .. k4+3); every CTA leaves its partial in scratch and the last one to arrive (device-scope ticket) adds them in
-// CTA order: deterministic.  scratch[0] is the ticket, zero between launches.
+// CTA order: deterministic.  The ticket is a library-owned counter per scratch buffer (zero between launches, it resets
+// itself), so the scratch may be shared with other operators and needs no initialisation.
 constexpr int LW_TR = 32;            // rows per shared-memory tile
 constexpr int LW_MAXP = 64;          // row slices (CTAs)
 
@@ -154,7 +157,8 @@ long long linear_wgrad_small_scratch(long long M, int K, int N) {
 template <int J>
 __global__ void __launch_bounds__(LS_THREADS)
 linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long M, int K, int N,
-                          float* __restrict__ scratch, float* __restrict__ dw, float* __restrict__ db) {
+                          float* __restrict__ scratch, unsigned int* __restrict__ ticket, float* __restrict__ dw,
+                          float* __restrict__ db) {
   pdl_enter();
   extern __shared__ __align__(16) float sm[];
   __shared__ bool last;
@@ -208,10 +212,7 @@ linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__
   if (threadIdx.x < N) mine[(size_t)nout4 * 4 + threadIdx.x] = bsum;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
-    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  }
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!last) return;
   __threadfence();
@@ -237,7 +238,28 @@ linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__
     for (int p = 0; p < P; ++p) t += __ldcg(scratch + 4 + (size_t)p * stride + (size_t)nout4 * 4 + threadIdx.x);
     db[threadIdx.x] = t;
   }
-  if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(scratch) = 0u;
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// one arrival counter per scratch buffer, from a zeroed block allocated on first use (an eager pass: cudaMalloc is illegal
+// during stream capture; later buffers only take the next index)
+static unsigned int* lw_ticket(const float* scratch, cudaStream_t s) {
+  constexpr int kTickets = 8192;
+  static unsigned int* block = nullptr;
+  static std::unordered_map<const float*, int> index;
+  if (block == nullptr) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &st);
+    if (st != cudaStreamCaptureStatusNone) throw Error(5, "linear_wgrad_small: first use must be an eager pass (allocates its arrival counters)");
+    PCG_CHECK_CUDA(cudaMalloc(&block, kTickets * sizeof(unsigned int)));
+    PCG_CHECK_CUDA(cudaMemset(block, 0, kTickets * sizeof(unsigned int)));
+  }
+  auto it = index.find(scratch);
+  if (it == index.end()) {
+    PCG_REQUIRE((int)index.size() < kTickets, "linear_wgrad_small: more than 8192 distinct scratch buffers");
+    it = index.emplace(scratch, (int)index.size()).first;
+  }
+  return block + it->second;
 }
 
 void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int N, float* scratch, float* dw, float* db,
@@ -249,7 +271,8 @@ void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int
   const int J = (nout4 + LS_THREADS - 1) / LS_THREADS;
   const size_t smem = (size_t)LW_TR * (K4 * 4 + N) * sizeof(float);
   const dim3 grid(lw_ctas(M));
-#define PCG_LW(JJ) launch_k(linear_wgrad_small_kernel<JJ>, grid, dim3(LS_THREADS), smem, s, x, dy, M, K, N, scratch, dw, db)
+  unsigned int* ticket = lw_ticket(scratch, s);
+#define PCG_LW(JJ) launch_k(linear_wgrad_small_kernel<JJ>, grid, dim3(LS_THREADS), smem, s, x, dy, M, K, N, scratch, ticket, dw, db)
   if (J <= 1) PCG_LW(1);
   else if (J <= 2) PCG_LW(2);
   else if (J <= 4) PCG_LW(4);

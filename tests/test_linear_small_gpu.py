@@ -74,7 +74,7 @@ def test_one_launch_weight_and_bias_gradient(M, K, N):
     x, dy = torch.randn(M, K, device="cuda"), torch.randn(M, N, device="cuda")
     need = Kk.linear_wgrad_small_scratch_floats(M, K, N)
     assert need > 0 and Kk.linear_wgrad_small_scratch_floats(M, 129, N) == -1
-    scratch = torch.zeros(need, device="cuda")
+    scratch = torch.full((need,), 123.0, device="cuda")                # no initialisation needed, may hold anything
     dw, db = torch.full((N, K), 9.0, device="cuda"), torch.full((N,), 9.0, device="cuda")
     Kk.linear_wgrad_small(x, dy, scratch, dw, db)
     assert rel(dw, dy.double().t() @ x.double()) < 2e-5 and rel(db, dy.double().sum(0)) < 2e-5
