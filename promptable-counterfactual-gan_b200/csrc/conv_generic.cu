@@ -717,6 +717,8 @@ __global__ void __launch_bounds__(256) transpose_tiled_kernel(const float* __res
                                                              float* __restrict__ dst) {
   pdl_enter();
   __shared__ float tile[32][33];
+  src += (size_t)blockIdx.z * R * C;                 // batch of matrices (wf: one [Cin][taps] -> [taps][Cin] per Cout)
+  dst += (size_t)blockIdx.z * R * C;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int j = ty; j < 32; j += 8)
@@ -730,9 +732,10 @@ __global__ void __launch_bounds__(256) transpose_tiled_kernel(const float* __res
     }
   }
 }
-void transpose_tiled(const float* src, int R, int C, float* dst, cudaStream_t stream, int taps, bool rev) {
-  PCG_REQUIRE((C + 31) / 32 <= 2147483647 && (R + 31) / 32 <= 65535, "transpose: at most 2M rows");
-  launch_k(transpose_tiled_kernel, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 0, stream, src, R, C, taps, rev ? 1 : 0, dst);
+void transpose_tiled(const float* src, int R, int C, float* dst, cudaStream_t stream, int taps, bool rev, int batch) {
+  PCG_REQUIRE((R + 31) / 32 <= 65535 && batch >= 1 && batch <= 65535, "transpose: at most 2M rows, 65535 matrices");
+  launch_k(transpose_tiled_kernel, dim3((C + 31) / 32, (R + 31) / 32, batch), dim3(256), 0, stream, src, R, C, taps,
+           rev ? 1 : 0, dst);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -745,6 +748,11 @@ void pack_conv_weights_generic(const float* w, int Cout, int Cin, int ksize, int
     // at a time across rows (8.4 M elements for the WGAN critic's Linear(8192, 1024))
     transpose_tiled(w, Cout, Cin * ksize * ksize, wd, stream, ksize * ksize, perm_hw == -1);
     wd = nullptr;
+    if (wf != nullptr && perm_hw == 0 && ksize > 1 && Cout <= 65535) {
+      // wf [Cout][taps][Cin]: per output channel the [Cin][taps] block of w transposed
+      transpose_tiled(w, Cin, ksize * ksize, wf, stream, 1, false, Cout);
+      wf = nullptr;
+    }
     if (wf == nullptr) return;
   }
   const int total = Cout * Cin * ksize * ksize;

@@ -53,7 +53,8 @@ void wgrad_reduce_generic(const float* part, int nz, int Cout, int Cin, int taps
 // `perm_hw` > 0: the Cin axis of a Linear that consumes a flattened NCHW [C][perm_hw] map is
 // re-ordered to NHWC flatten order (classifier fc.1, classifier.py:17-18).
 // dst[c][r] = src[r][c]; taps / rev: see conv_generic.cu (tap-reversed weight packing)
-void transpose_tiled(const float* src, int R, int C, float* dst, cudaStream_t stream, int taps = 1, bool rev = false);
+void transpose_tiled(const float* src, int R, int C, float* dst, cudaStream_t stream, int taps = 1, bool rev = false,
+                     int batch = 1);      // batch: that many consecutive [R][C] matrices
 void pack_conv_weights_generic(const float* w, int Cout, int Cin, int ksize, int perm_hw, float* wf,
                                float* wd, cudaStream_t stream);
 
