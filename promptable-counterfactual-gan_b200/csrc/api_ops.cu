@@ -405,6 +405,18 @@ int pcg_dilate(const float* src, int N, int Ho, int Wo, int C, int stride, int o
   dilate(src, N, Ho, Wo, C, stride, off, Hp, Wp, dst, ST);
   PCG_API_END
 }
+int pcg_pack_dgrad_classes(const float* w, int Cout, int Cin, int k, float* wc, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(w && wc, "pack_dgrad_classes: null pointer");
+  pack_dgrad_classes(w, Cout, Cin, k, wc, ST);
+  PCG_API_END
+}
+int pcg_parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, float* dx, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(src && dx, "parity_interleave: null pointer");
+  parity_interleave(src, N, Hc, Wc, C, pad, H, W, dx, ST);
+  PCG_API_END
+}
 int pcg_gp_penalty(const float* g, int B, int D, float lambda, float* out, float* gbar, float* norms, void* stream) {
   PCG_API_BEGIN
   PCG_REQUIRE(g && out && gbar, "gp_penalty: null pointer");

@@ -203,6 +203,42 @@ __global__ void dilate_kernel(const float4* __restrict__ src, int Ho, int Wo, in
   }
 }
 
+// Stride-2 data gradient by parity classes.  With y = 2 i + c - pad (c = (y + pad) & 1) the taps that reach input row y are
+// ky = c, c + 2, and dx_c[i] = sum_{m = 0, 1} dy[i - m] * W[c + 2 m]: per class (cy, cx) a stride-1 2x2 convolution of the
+// UNdilated gradient (pad 1, output (Ho + 1) x (Wo + 1)) with the weights wc[cls][ci][jy * 2 + jx][co] =
+// W[co][ci][cy + 2 (1 - jy)][cx + 2 (1 - jx)] (zero where that tap does not exist, k = 3), then an interleave.
+__global__ void pack_dgrad_classes_kernel(const float* __restrict__ w, int Cout, int Cin, int k, float* __restrict__ wc) {
+  pdl_enter();
+  const long long total = 4LL * Cin * 4 * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long r = i / Cout;
+    const int j = (int)(r % 4); r /= 4;
+    const int ci = (int)(r % Cin);
+    const int cls = (int)(r / Cin);
+    const int ky = (cls >> 1) + 2 * (1 - (j >> 1)), kx = (cls & 1) + 2 * (1 - (j & 1));
+    wc[i] = (ky < k && kx < k) ? w[(((size_t)co * Cin + ci) * k + ky) * k + kx] : 0.f;
+  }
+}
+
+// dx[n][2 i + cy - pad][2 j + cx - pad][:] = src[cls][n][i][j][:] for the positions inside the H x W map; src holds the four
+// class results [4][N][Hc][Wc][C] back to back
+__global__ void parity_interleave_kernel(const float4* __restrict__ src, int N, int Hc, int Wc, int C4, int pad, int H, int W,
+                                         float4* __restrict__ dx, long long total) {
+  pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long r = i / C4;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const long long n = r / H;
+    const int cy = (y + pad) & 1, cx = (x + pad) & 1;
+    const int iy = (y + pad - cy) >> 1, ix = (x + pad - cx) >> 1;
+    const int cls = cy * 2 + cx;
+    dx[i] = src[((((long long)cls * N + n) * Hc + iy) * Wc + ix) * C4 + c];
+  }
+}
+
 static dim3 in_grid(int N, int C) { return dim3((C + IN_CX - 1) / IN_CX, N); }
 
 void instnorm_fwd(const float* x, int N, int P, int C, const float* gamma, const float* beta, float eps, int act, float slope,
@@ -266,6 +302,26 @@ void dilate(const float* src, int N, int Ho, int Wo, int C, int stride, int off,
   const long long blocks = (total + 255) / 256, cap = (long long)sm_count() * 16;
   launch_k(dilate_kernel, dim3((unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap)), dim3(256), 0, s,
            reinterpret_cast<const float4*>(src), Ho, Wo, C / 4, stride, off, Hp, Wp, reinterpret_cast<float4*>(dst), total);
+  PCG_COUNT_LAUNCH();
+}
+
+void pack_dgrad_classes(const float* w, int Cout, int Cin, int k, float* wc, cudaStream_t s) {
+  PCG_PROFILE("pack_weights", s);
+  PCG_REQUIRE(k == 3 || k == 4, "pack_dgrad_classes: k in {3, 4}");
+  const long long total = 16LL * Cin * Cout;
+  const long long blocks = (total + 255) / 256, cap = (long long)sm_count() * 16;
+  launch_k(pack_dgrad_classes_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), 0, s, w, Cout, Cin, k, wc);
+  PCG_COUNT_LAUNCH();
+}
+
+void parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, float* dx, cudaStream_t s) {
+  PCG_PROFILE("ops_small", s);
+  PCG_REQUIRE(C % 4 == 0 && (H - 1 + pad) / 2 < Hc && (W - 1 + pad) / 2 < Wc && pad >= 0,
+              "parity_interleave: C % 4 == 0 and class maps that cover the H x W map");
+  const long long total = (long long)N * H * W * (C / 4);
+  const long long blocks = (total + 255) / 256, cap = (long long)sm_count() * 16;
+  launch_k(parity_interleave_kernel, dim3((unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap)), dim3(256), 0, s,
+           reinterpret_cast<const float4*>(src), N, Hc, Wc, C / 4, pad, H, W, reinterpret_cast<float4*>(dx), total);
   PCG_COUNT_LAUNCH();
 }
 

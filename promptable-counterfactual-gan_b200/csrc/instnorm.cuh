@@ -30,6 +30,12 @@ void bias_act(const float* x, long long rows, int C, const float* bias, int tanh
 // Hp = H + k - 1) with the tap-reversed weight (pcg_pack_conv_weights perm_hw = -1) - a forward convolution, which runs on
 // the tcgen05 kernel for any kernel size / stride.
 void dilate(const float* src, int N, int Ho, int Wo, int C, int stride, int off, int Hp, int Wp, float* dst, cudaStream_t s);
+// Stride-2 data gradient as four stride-1 2x2 forward convolutions of the UNdilated gradient, one per parity class of the
+// input position (no multiplications by the zeros a dilated gradient carries): pack_dgrad_classes builds their weights
+// wc[4][Cin][2*2][Cout] from the torch OIHW weight (k = 3 or 4), parity_interleave merges the four class maps
+// [4][N][Hc][Wc][C] (Hc = Ho + 1) into dx [N][H][W][C].
+void pack_dgrad_classes(const float* w, int Cout, int Cin, int k, float* wc, cudaStream_t s);
+void parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, float* dx, cudaStream_t s);
 // WGAN-GP penalty of mnist_wgan_conditional.py:147: n_b = ||g[b][:]||_2, out[0] = lambda * mean_b (n_b - 1)^2,
 // gbar[b][:] = lambda * 2 (n_b - 1) / (B * n_b) * g[b][:] (the cotangent of g), norms[b] = n_b (optional)
 void gp_penalty(const float* g, int B, int D, float lambda, float* out, float* gbar, float* norms, cudaStream_t s);

@@ -467,6 +467,20 @@ def dilate(src, N, Ho, Wo, C, stride, off, Hp, Wp, dst):
     _lib.check(_L().pcg_dilate(P(src), N, Ho, Wo, C, stride, off, Hp, Wp, P(dst), _s()))
 
 
+@_op("wc")
+def pack_dgrad_classes(w, k, wc):
+    """torch OIHW weight -> wc [4][Cin][2*2][Cout], the forward weights of the four parity-class convolutions whose
+    interleaved results are the stride-2 data gradient (include/pcg.h)."""
+    _chk(w, wc)
+    _lib.check(_L().pcg_pack_dgrad_classes(P(w), w.shape[0], w.shape[1], k, P(wc), _s()))
+
+
+@_op("dx")
+def parity_interleave(src, N, Hc, Wc, C, pad, H, W, dx):
+    _chk(src, dx)
+    _lib.check(_L().pcg_parity_interleave(P(src), N, Hc, Wc, C, pad, H, W, P(dx), _s()))
+
+
 @_op("out", "gbar", "norms")
 def gp_penalty(g, B, D, lam, out, gbar, norms=None):
     _chk(g, out, gbar, norms)

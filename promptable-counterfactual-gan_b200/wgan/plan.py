@@ -158,7 +158,7 @@ class WganGpPlan:
         if share is not None:
             self.G, self.C, self.C_grad2, self.g_bn, self.lr_dev = share.G, share.C, share.C_grad2, share.g_bn, share.lr_dev
             self.g_wf, self.g_wd, self.c_wf, self.c_wd, self.l1t = share.g_wf, share.g_wd, share.c_wf, share.c_wd, share.l1t
-            self.g_wdr, self.c_wdr = share.g_wdr, share.c_wdr
+            self.g_wc, self.c_wc = share.g_wc, share.c_wc
         else:
             self.G, self.C = K.FlatParams(list(g_shapes(hp).items()), dev), K.FlatParams(list(c_shapes(hp).items()), dev)
             self.C_grad2 = torch.zeros_like(self.C.grad)       # second-order (penalty) terms of the gradient chain
@@ -171,9 +171,9 @@ class WganGpPlan:
             self.c_wf = [z(cch[i] * cch[i + 1] * 9) for i in range(3)]
             self.c_wd = [z(cch[i] * cch[i + 1] * 9) for i in range(3)]
             self.l1t = z(8 * c * Hd)                           # Critic_net.0.weight transposed [8c][hidden]
-            # tap-reversed wd: forward weights of the dilated-gradient convolutions (tensor-core mode, see _dgrad)
-            self.g_wdr = [z(gch[i] * gch[i + 1] * G_K[i] ** 2) if i < 2 else None for i in range(4)]
-            self.c_wdr = [z(cch[i] * cch[i + 1] * 9) if i > 0 else None for i in range(3)]
+            # forward weights of the four parity-class convolutions of a stride-2 data gradient (tensor-core mode, _dgrad)
+            self.g_wc = [z(4, gch[i] * 4 * gch[i + 1]) if i == 1 else None for i in range(4)]
+            self.c_wc = [z(4, cch[i] * 4 * cch[i + 1]) if i > 0 else None for i in range(3)]
         # mirrored-convolution geometry of the generator's transposed convolutions
         self.g_geom = [(B, G_HW[i + 1], G_HW[i + 1], gch[i + 1], gch[i], G_K[i], *G_SP[i]) for i in range(4)]
         # ---- inputs
@@ -253,17 +253,27 @@ class WganGpPlan:
         else:
             K.linear_dgrad(dy, w_t, dx, Kd)
 
-    def _dgrad(self, key, dy, geom, wd, wdr, out):
-        """Data gradient of the convolution ``geom`` = (N, H, W, Cin, Cout, k, stride, pad).  Tensor-core mode: the
-        stride-1 forward convolution of the zero-dilated gradient with the tap-reversed weight (pcg_dilate) for the
-        geometries the native tcgen05 data-gradient kernel (k4, s2, p1) does not cover."""
+    def _dgrad(self, key, dy, geom, wd, wc, out):
+        """Data gradient of the convolution ``geom`` = (N, H, W, Cin, Cout, k, stride, pad).  Tensor-core mode, for the
+        geometries the native tcgen05 data-gradient kernel (k4, s2, p1, even sizes) does not cover, as FORWARD
+        convolutions, which the tcgen05 forward kernel takes in any geometry:
+          stride 2 (k3; any padding, odd sizes): one stride-1 2x2 convolution of the gradient per parity class of the input
+            position (weights ``wc``, pcg_pack_dgrad_classes), interleaved by pcg_parity_interleave - 16 tap products per
+            output pixel pair against 36 for the zero-dilated form (pcg_dilate);
+          a full-window layer (ConvTranspose2d on the 1x1 latent): a 1x1 product with wd's rows, (ci, tap) -> (tap, ci)."""
         N, H, W, Cin, Cout, k, stride, pad = geom
         native = k == 4 and stride == 2 and pad == 1 and H % 2 == 0
-        if self.tc and wdr is not None and Cin % 64 == 0 and Cout % 64 == 0 and not native:
-            Ho, Hp = (H + 2 * pad - k) // stride + 1, H + k - 1
-            D = self._buf(("dil", key), N, Hp, Hp, Cout)
-            K.dilate(dy, N, Ho, Ho, Cout, stride, k - 1 - pad, Hp, Hp, D)
-            K.conv_fprop(D, N, Hp, Hp, Cout, wdr, Cin, k, 1, 0, out)
+        Ho = (H + 2 * pad - k) // stride + 1
+        ok = self.tc and Cin % 64 == 0 and Cout % 64 == 0 and not native
+        if ok and stride == 2 and wc is not None:
+            cls = self._buf(("cls", key), 4, N, Ho + 1, Ho + 1, Cin)
+            for c in range(4):
+                K.conv_fprop(dy, N, Ho, Ho, Cout, wc[c], Cin, 2, 1, 1, cls[c])
+            K.parity_interleave(cls, N, Ho + 1, Ho + 1, Cin, pad, H, W, out)
+        elif ok and stride == 1 and pad == 0 and Ho == 1:
+            tmp = self._buf(("fw", key), N, Cin * k * k)
+            K.conv_fprop(dy, N, 1, 1, Cout, wd, Cin * k * k, 1, 1, 0, tmp)
+            K.flatten_nchw(tmp, N, Cin, k * k, out.view(N, k * k * Cin), k * k * Cin, 0)
         else:
             K.conv_dgrad(dy, N, H, W, Cin, wd, Cout, k, stride, pad, out)
 
@@ -292,14 +302,14 @@ class WganGpPlan:
         for i in range(4):
             # ConvT weight [Cin_T][Cout_T][k][k] == mirrored conv weight OIHW with O = Cin_T, I = Cout_T
             K.pack_weights(self.G.p(f"tcnn.{3 * i}.weight"), G_K[i], wf=self.g_wf[i], wd=self.g_wd[i])
-            if self.tc and self.g_wdr[i] is not None:
-                K.pack_weights(self.G.p(f"tcnn.{3 * i}.weight"), G_K[i], wd=self.g_wdr[i], perm_hw=-1)
+            if self.tc and self.g_wc[i] is not None:
+                K.pack_dgrad_classes(self.G.p(f"tcnn.{3 * i}.weight"), G_K[i], self.g_wc[i])
 
     def _pack_c(self):
         for i in range(3):
             K.pack_weights(self.C.p(f"cnn_net.{3 * i}.weight"), 3, wf=self.c_wf[i], wd=self.c_wd[i])
-            if self.tc and self.c_wdr[i] is not None:
-                K.pack_weights(self.C.p(f"cnn_net.{3 * i}.weight"), 3, wd=self.c_wdr[i], perm_hw=-1)
+            if self.tc and self.c_wc[i] is not None:
+                K.pack_dgrad_classes(self.C.p(f"cnn_net.{3 * i}.weight"), 3, self.c_wc[i])
         K.pack_weights(self.C.p("Critic_net.0.weight"), 1, wd=self.l1t)
 
     # ------------------------------------------------------------------ generator
@@ -312,7 +322,7 @@ class WganGpPlan:
         x = self.e
         for i, geom in enumerate(self.g_geom):
             C = self.gch[i + 1]
-            self._dgrad(("g", i), x, geom, self.g_wd[i], self.g_wdr[i], self.gy[i])  # ConvTranspose2d forward
+            self._dgrad(("g", i), x, geom, self.g_wd[i], self.g_wc[i], self.gy[i])  # ConvTranspose2d forward
             if i < 3:
                 K.bias_act(self.gy[i], C, G.p(f"tcnn.{3 * i}.bias"), self.gy[i])
                 bn, nm = self.g_bn[i], f"tcnn.{3 * i + 1}"
@@ -396,7 +406,7 @@ class WganGpPlan:
                 K.conv_wgrad(xin, self.da[i][:N], *geom, self._ws(("c", i, N), *geom), g(f"cnn_net.{3 * i}.weight"))
                 K.colsum(self.da[i][:N], self._ss(("cb", i), Co), g(f"cnn_net.{3 * i}.bias"))
             if i > 0:
-                self._dgrad(("c", i, N), self.da[i][:N], (N, Hh, Hh, Ci, Co, 3, 2, 0), self.c_wd[i], self.c_wdr[i],
+                self._dgrad(("c", i, N), self.da[i][:N], (N, Hh, Hh, Ci, Co, 3, 2, 0), self.c_wd[i], self.c_wc[i],
                             self.dh[i - 1][:N])
             elif want_dx:
                 K.conv_dgrad(self.da[0][:N], N, Hh, Hh, Ci, self.c_wd[0], Co, 3, 2, 0, self.dx[:N])
@@ -416,7 +426,7 @@ class WganGpPlan:
             Hh, Ci, Co, P = C_HW[i], self.cch[i], self.cch[i + 1], C_HW[i + 1] ** 2
             K.instnorm_bwd(self.gh[i], self.a[i][s], self.mean[i][s], self.rstd[i][s], gam(i), B, P, Co, self.ga_c[i],
                            act_ref=self.h[i][s], act=K.ACT_LRELU, slope=0.2)
-            self._dgrad(("p", i), self.ga_c[i], (B, Hh, Hh, Ci, Co, 3, 2, 0), self.c_wd[i], self.c_wdr[i],
+            self._dgrad(("p", i), self.ga_c[i], (B, Hh, Hh, Ci, Co, 3, 2, 0), self.c_wd[i], self.c_wc[i],
                         self.gh[i - 1] if i > 0 else self.gimg)
         K.gp_penalty(self.gimg, B, 784, self.hp.gp_lambda, self.scal[3:4], self.gbar, self.norms)
         # reverse: cotangents of the chain's intermediates, second-order parameter terms into C_grad2

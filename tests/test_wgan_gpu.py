@@ -266,3 +266,25 @@ def test_dilated_forward_convolution_equals_the_data_gradient(N, H, Cin, Cout, k
     got = torch.full((N, H, H, Cin), 7.0, device="cuda")
     K.conv_fprop(D, N, Hp, Hp, Cout, wdr, Cin, k, 1, 0, got)
     assert rel(got, ref.permute(0, 2, 3, 1)) < 1e-5
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,k,pad", [(3, 13, 64, 128, 3, 0), (2, 6, 16, 8, 3, 0), (4, 7, 32, 64, 3, 1), (2, 28, 8, 4, 3, 0),
+                                                 (2, 8, 16, 12, 4, 1), (1, 2, 4, 4, 3, 1)])
+def test_parity_class_convolutions_equal_the_stride_2_data_gradient(N, H, Cin, Cout, k, pad):
+    """pcg_pack_dgrad_classes + four stride-1 2x2 pcg_conv_fprop + pcg_parity_interleave == the data gradient of
+    Conv2d(k, stride 2, pad), on the exact fp32 kernels, incl. odd sizes and rows / columns that receive no gradient."""
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import ops as K
+    torch.manual_seed(H + Cin + k)
+    Ho = (H + 2 * pad - k) // 2 + 1
+    w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.1
+    wc = torch.full((4, Cin * 4 * Cout), 7.0, device="cuda")
+    K.pack_dgrad_classes(w, k, wc)
+    dy = torch.randn(N, Ho, Ho, Cout, device="cuda")
+    cls = torch.full((4, N, Ho + 1, Ho + 1, Cin), 7.0, device="cuda")
+    for c in range(4):
+        K.conv_fprop(dy, N, Ho, Ho, Cout, wc[c], Cin, 2, 1, 1, cls[c])
+    got = torch.full((N, H, H, Cin), 7.0, device="cuda")
+    K.parity_interleave(cls, N, Ho + 1, Ho + 1, Cin, pad, H, H, got)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, H), w.double(), dy.permute(0, 3, 1, 2).double(), 2, pad)
+    assert rel(got, ref.permute(0, 2, 3, 1)) < 1e-5
