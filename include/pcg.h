@@ -447,9 +447,12 @@ int pcg_dilate(const float* src, int N, int Ho, int Wo, int C, int stride, int o
  * gradient,  pcg_conv_fprop(dy, N, Ho, Wo, Cout -> Cin, k 2, stride 1, pad 1, weight wc + cls * Cin * 4 * Cout)
  * -> class map [N][Ho + 1][Wo + 1][Cin],  then pcg_parity_interleave of the four maps (stored back to back) into dx
  * [N][H][W][Cin]:  dx[n][y][x] = class (y + pad) & 1, (x + pad) & 1 at ((y + pad) >> 1, (x + pad) >> 1).
- * pcg_pack_dgrad_classes builds wc [4][Cin][4][Cout] from the torch OIHW weight. */
+ * pcg_pack_dgrad_classes builds wc [4][Cin][4][Cout] from the torch OIHW weight.  stacked != 0: src is the result
+ * [N][Hc][Wc][4][Cin] of ONE forward convolution Cout -> 4 * Cin with the whole of wc as its weight (class-major output
+ * channels) instead of four class maps. */
 int pcg_pack_dgrad_classes(const float* w, int Cout, int Cin, int k, float* wc, void* stream);
-int pcg_parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, float* dx, void* stream);
+int pcg_parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, int stacked, float* dx,
+                          void* stream);
 /* Gradient penalty of mnist_wgan_conditional.py:147 on the critic's input gradient g [B][D]: n_b = ||g[b]||_2,
  * out[0] = lambda * mean_b (n_b - 1)^2, gbar = its cotangent lambda * 2 (n_b - 1) / (B n_b) * g[b], norms[b] = n_b
  * (NULL: not stored).  Not re-entrant across streams (one internal arrival counter). */

@@ -411,10 +411,11 @@ int pcg_pack_dgrad_classes(const float* w, int Cout, int Cin, int k, float* wc, 
   pack_dgrad_classes(w, Cout, Cin, k, wc, ST);
   PCG_API_END
 }
-int pcg_parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, float* dx, void* stream) {
+int pcg_parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, int stacked, float* dx,
+                          void* stream) {
   PCG_API_BEGIN
   PCG_REQUIRE(src && dx, "parity_interleave: null pointer");
-  parity_interleave(src, N, Hc, Wc, C, pad, H, W, dx, ST);
+  parity_interleave(src, N, Hc, Wc, C, pad, H, W, stacked != 0, dx, ST);
   PCG_API_END
 }
 int pcg_gp_penalty(const float* g, int B, int D, float lambda, float* out, float* gbar, float* norms, void* stream) {

@@ -224,7 +224,7 @@ __global__ void pack_dgrad_classes_kernel(const float* __restrict__ w, int Cout,
 // dx[n][2 i + cy - pad][2 j + cx - pad][:] = src[cls][n][i][j][:] for the positions inside the H x W map; src holds the four
 // class results [4][N][Hc][Wc][C] back to back
 __global__ void parity_interleave_kernel(const float4* __restrict__ src, int N, int Hc, int Wc, int C4, int pad, int H, int W,
-                                         float4* __restrict__ dx, long long total) {
+                                         int stacked, float4* __restrict__ dx, long long total) {
   pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4);
@@ -235,7 +235,8 @@ __global__ void parity_interleave_kernel(const float4* __restrict__ src, int N, 
     const int cy = (y + pad) & 1, cx = (x + pad) & 1;
     const int iy = (y + pad - cy) >> 1, ix = (x + pad - cx) >> 1;
     const int cls = cy * 2 + cx;
-    dx[i] = src[((((long long)cls * N + n) * Hc + iy) * Wc + ix) * C4 + c];
+    dx[i] = stacked ? src[(((n * Hc + iy) * Wc + ix) * 4 + cls) * C4 + c]                 // [N][Hc][Wc][4][C]: ONE convolution
+                    : src[((((long long)cls * N + n) * Hc + iy) * Wc + ix) * C4 + c];     // [4][N][Hc][Wc][C]
   }
 }
 
@@ -314,14 +315,16 @@ void pack_dgrad_classes(const float* w, int Cout, int Cin, int k, float* wc, cud
   PCG_COUNT_LAUNCH();
 }
 
-void parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, float* dx, cudaStream_t s) {
+void parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, bool stacked, float* dx,
+                       cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
   PCG_REQUIRE(C % 4 == 0 && (H - 1 + pad) / 2 < Hc && (W - 1 + pad) / 2 < Wc && pad >= 0,
               "parity_interleave: C % 4 == 0 and class maps that cover the H x W map");
   const long long total = (long long)N * H * W * (C / 4);
   const long long blocks = (total + 255) / 256, cap = (long long)sm_count() * 16;
   launch_k(parity_interleave_kernel, dim3((unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap)), dim3(256), 0, s,
-           reinterpret_cast<const float4*>(src), N, Hc, Wc, C / 4, pad, H, W, reinterpret_cast<float4*>(dx), total);
+           reinterpret_cast<const float4*>(src), N, Hc, Wc, C / 4, pad, H, W, stacked ? 1 : 0, reinterpret_cast<float4*>(dx),
+           total);
   PCG_COUNT_LAUNCH();
 }
 

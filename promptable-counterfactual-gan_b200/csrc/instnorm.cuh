@@ -33,9 +33,11 @@ void dilate(const float* src, int N, int Ho, int Wo, int C, int stride, int off,
 // Stride-2 data gradient as four stride-1 2x2 forward convolutions of the UNdilated gradient, one per parity class of the
 // input position (no multiplications by the zeros a dilated gradient carries): pack_dgrad_classes builds their weights
 // wc[4][Cin][2*2][Cout] from the torch OIHW weight (k = 3 or 4), parity_interleave merges the four class maps
-// [4][N][Hc][Wc][C] (Hc = Ho + 1) into dx [N][H][W][C].
+// [4][N][Hc][Wc][C] (Hc = Ho + 1) - or, stacked, the result [N][Hc][Wc][4][C] of ONE convolution with all four weight sets
+// (wc as a whole is the forward weight of a Cout -> 4 * Cin layer) - into dx [N][H][W][C].
 void pack_dgrad_classes(const float* w, int Cout, int Cin, int k, float* wc, cudaStream_t s);
-void parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, float* dx, cudaStream_t s);
+void parity_interleave(const float* src, int N, int Hc, int Wc, int C, int pad, int H, int W, bool stacked, float* dx,
+                       cudaStream_t s);
 // WGAN-GP penalty of mnist_wgan_conditional.py:147: n_b = ||g[b][:]||_2, out[0] = lambda * mean_b (n_b - 1)^2,
 // gbar[b][:] = lambda * 2 (n_b - 1) / (B * n_b) * g[b][:] (the cotangent of g), norms[b] = n_b (optional)
 void gp_penalty(const float* g, int B, int D, float lambda, float* out, float* gbar, float* norms, cudaStream_t s);

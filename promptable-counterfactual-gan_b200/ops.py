@@ -476,9 +476,9 @@ def pack_dgrad_classes(w, k, wc):
 
 
 @_op("dx")
-def parity_interleave(src, N, Hc, Wc, C, pad, H, W, dx):
+def parity_interleave(src, N, Hc, Wc, C, pad, H, W, dx, stacked=False):
     _chk(src, dx)
-    _lib.check(_L().pcg_parity_interleave(P(src), N, Hc, Wc, C, pad, H, W, P(dx), _s()))
+    _lib.check(_L().pcg_parity_interleave(P(src), N, Hc, Wc, C, pad, H, W, 1 if stacked else 0, P(dx), _s()))
 
 
 @_op("out", "gbar", "norms")

@@ -258,18 +258,17 @@ class WganGpPlan:
         geometries the native tcgen05 data-gradient kernel (k4, s2, p1, even sizes) does not cover, as FORWARD
         convolutions, which the tcgen05 forward kernel takes in any geometry:
           stride 2 (k3; any padding, odd sizes): one stride-1 2x2 convolution of the gradient per parity class of the input
-            position (weights ``wc``, pcg_pack_dgrad_classes), interleaved by pcg_parity_interleave - 16 tap products per
-            output pixel pair against 36 for the zero-dilated form (pcg_dilate);
+            position - all four as ONE Cout -> 4 Cin layer (weights ``wc``, pcg_pack_dgrad_classes) - interleaved by
+            pcg_parity_interleave: 16 tap products per output pixel pair against 36 for the zero-dilated form (pcg_dilate);
           a full-window layer (ConvTranspose2d on the 1x1 latent): a 1x1 product with wd's rows, (ci, tap) -> (tap, ci)."""
         N, H, W, Cin, Cout, k, stride, pad = geom
         native = k == 4 and stride == 2 and pad == 1 and H % 2 == 0
         Ho = (H + 2 * pad - k) // stride + 1
         ok = self.tc and Cin % 64 == 0 and Cout % 64 == 0 and not native
         if ok and stride == 2 and wc is not None:
-            cls = self._buf(("cls", key), 4, N, Ho + 1, Ho + 1, Cin)
-            for c in range(4):
-                K.conv_fprop(dy, N, Ho, Ho, Cout, wc[c], Cin, 2, 1, 1, cls[c])
-            K.parity_interleave(cls, N, Ho + 1, Ho + 1, Cin, pad, H, W, out)
+            cls = self._buf(("cls", key), N, Ho + 1, Ho + 1, 4 * Cin)        # the four classes as ONE Cout -> 4 Cin layer
+            K.conv_fprop(dy, N, Ho, Ho, Cout, wc, 4 * Cin, 2, 1, 1, cls)
+            K.parity_interleave(cls, N, Ho + 1, Ho + 1, Cin, pad, H, W, out, stacked=True)
         elif ok and stride == 1 and pad == 0 and Ho == 1:
             tmp = self._buf(("fw", key), N, Cin * k * k)
             K.conv_fprop(dy, N, 1, 1, Cout, wd, Cin * k * k, 1, 1, 0, tmp)

@@ -288,3 +288,9 @@ def test_parity_class_convolutions_equal_the_stride_2_data_gradient(N, H, Cin, C
     K.parity_interleave(cls, N, Ho + 1, Ho + 1, Cin, pad, H, H, got)
     ref = torch.nn.grad.conv2d_input((N, Cin, H, H), w.double(), dy.permute(0, 3, 1, 2).double(), 2, pad)
     assert rel(got, ref.permute(0, 2, 3, 1)) < 1e-5
+    # the four classes as ONE convolution Cout -> 4 Cin (class-major output channels)
+    stacked = torch.full((N, Ho + 1, Ho + 1, 4 * Cin), 7.0, device="cuda")
+    K.conv_fprop(dy, N, Ho, Ho, Cout, wc, 4 * Cin, 2, 1, 1, stacked)
+    got.fill_(7.0)
+    K.parity_interleave(stacked, N, Ho + 1, Ho + 1, Cin, pad, H, H, got, stacked=True)
+    assert rel(got, ref.permute(0, 2, 3, 1)) < 1e-5
