@@ -144,21 +144,24 @@ void linear_small(const float* in, long long M, int K, int N, const float* w, co
 constexpr int LW_TR = 32;            // rows per shared-memory tile
 constexpr int LW_MAXP = 64;          // row slices (CTAs)
 
-static int lw_ctas(long long M) {
+static int lw_ctas(long long M, int, int) {
   const long long p = (M + 63) / 64;
   return (int)(p < 1 ? 1 : (p < LW_MAXP ? p : LW_MAXP));
 }
+// Layers above this many outputs add their partials in a second, wide launch: 64 slices of a 64 x 128 layer are 2 MB for
+// ONE last CTA to add up (56 us measured; fewer, longer slices cost more in the product than they save in the sum).
+constexpr int LW_ONE_LAUNCH_ELEMS = 2048;
 bool linear_wgrad_small_supported(long long M, int K, int N) { return M >= 1 && K >= 1 && K <= LS_MAXD && N >= 1 && N <= LS_MAXD; }
 long long linear_wgrad_small_scratch(long long M, int K, int N) {
   const int K4 = (K + 3) / 4;
-  return 4 + (long long)lw_ctas(M) * ((long long)N * K4 * 4 + LS_MAXD);
+  return 4 + (long long)lw_ctas(M, K, N) * ((long long)N * K4 * 4 + LS_MAXD);
 }
 
 template <int J>
 __global__ void __launch_bounds__(LS_THREADS)
 linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long M, int K, int N,
                           float* __restrict__ scratch, unsigned int* __restrict__ ticket, float* __restrict__ dw,
-                          float* __restrict__ db) {
+                          float* __restrict__ db) {      // ticket == NULL: partials only, linear_wgrad_small_sum_kernel follows
   pdl_enter();
   extern __shared__ __align__(16) float sm[];
   __shared__ bool last;
@@ -210,6 +213,7 @@ linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__
   for (int j = 0; j < J; ++j)
     if (on[j] >= 0) *reinterpret_cast<float4*>(mine + (size_t)(threadIdx.x + LS_THREADS * j) * 4) = acc[j];
   if (threadIdx.x < N) mine[(size_t)nout4 * 4 + threadIdx.x] = bsum;
+  if (ticket == nullptr) return;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
@@ -222,9 +226,14 @@ linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__
     if (on[j] < 0) continue;
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t off = 4 + (size_t)(threadIdx.x + LS_THREADS * j) * 4;
-    for (int p = 0; p < P; ++p) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(scratch + off + (size_t)p * stride));
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    for (int p0 = 0; p0 < P; p0 += 8) {               // eight loads in flight; added in CTA order
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = p0 + u < P ? __ldcg(reinterpret_cast<const float4*>(scratch + off + (size_t)(p0 + u) * stride))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }
     }
     float* o = dw + (size_t)on[j] * K + ok4[j] * 4;
     const int left = K - ok4[j] * 4;
@@ -235,10 +244,51 @@ linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__
   }
   if (db != nullptr && threadIdx.x < N) {
     float t = 0.f;
-    for (int p = 0; p < P; ++p) t += __ldcg(scratch + 4 + (size_t)p * stride + (size_t)nout4 * 4 + threadIdx.x);
+    for (int p0 = 0; p0 < P; p0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = p0 + u < P ? __ldcg(scratch + 4 + (size_t)(p0 + u) * stride + (size_t)nout4 * 4 + threadIdx.x) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
     db[threadIdx.x] = t;
   }
   if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// second launch for the larger layers: a thread per float4 of dw (and per element of db) adds the P partials in CTA order
+__global__ void __launch_bounds__(LS_THREADS)
+linear_wgrad_small_sum_kernel(const float* __restrict__ scratch, int P, int K, int N, float* __restrict__ dw,
+                              float* __restrict__ db) {
+  pdl_enter();
+  const int K4 = (K + 3) >> 2, nout4 = N * K4;
+  const size_t stride = (size_t)nout4 * 4 + LS_MAXD;
+  const int o = blockIdx.x * LS_THREADS + threadIdx.x;
+  if (o < nout4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p0 = 0; p0 < P; p0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = p0 + u < P ? *reinterpret_cast<const float4*>(scratch + 4 + (size_t)o * 4 + (size_t)(p0 + u) * stride)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }
+    }
+    const int n = o / K4, k4 = o - n * K4;
+    float* dst = dw + (size_t)n * K + k4 * 4;
+    const int left = K - k4 * 4;
+    dst[0] = t.x;
+    if (left > 1) dst[1] = t.y;
+    if (left > 2) dst[2] = t.z;
+    if (left > 3) dst[3] = t.w;
+  } else if (db != nullptr && o < nout4 + N) {
+    const int n = o - nout4;
+    float t = 0.f;
+    for (int p = 0; p < P; ++p) t += scratch[4 + (size_t)p * stride + (size_t)nout4 * 4 + n];
+    db[n] = t;
+  }
 }
 
 // one arrival counter per scratch buffer, from a zeroed block allocated on first use (an eager pass: cudaMalloc is illegal
@@ -270,8 +320,9 @@ void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int
   const int K4 = (K + 3) / 4, nout4 = N * K4;
   const int J = (nout4 + LS_THREADS - 1) / LS_THREADS;
   const size_t smem = (size_t)LW_TR * (K4 * 4 + N) * sizeof(float);
-  const dim3 grid(lw_ctas(M));
-  unsigned int* ticket = lw_ticket(scratch, s);
+  const dim3 grid(lw_ctas(M, K, N));
+  const bool two = (long long)nout4 * 4 > LW_ONE_LAUNCH_ELEMS;
+  unsigned int* ticket = two ? nullptr : lw_ticket(scratch, s);
 #define PCG_LW(JJ) launch_k(linear_wgrad_small_kernel<JJ>, grid, dim3(LS_THREADS), smem, s, x, dy, M, K, N, scratch, ticket, dw, db)
   if (J <= 1) PCG_LW(1);
   else if (J <= 2) PCG_LW(2);
@@ -280,6 +331,11 @@ void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int
   else PCG_LW(16);
 #undef PCG_LW
   PCG_COUNT_LAUNCH();
+  if (two) {
+    launch_k(linear_wgrad_small_sum_kernel, dim3((nout4 + N + LS_THREADS - 1) / LS_THREADS), dim3(LS_THREADS), 0, s, scratch,
+             (int)grid.x, K, N, dw, db);
+    PCG_COUNT_LAUNCH();
+  }
   PCG_LAUNCH_CHECK();
 }
 

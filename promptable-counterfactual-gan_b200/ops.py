@@ -199,10 +199,13 @@ def linear_wgrad_small(x, dy, scratch, dw, db=None):
 _SMALL_WGRAD = os.environ.get("PCG_SMALL_WGRAD", "1") != "0"
 
 
-def linear_wgrad(x, dy, scratch, dw, db=None, stat=None):
+def linear_wgrad(x, dy, scratch, dw, db=None, stat=None, on_critical_path=False):
+    """dw, db of a Linear layer.  Small layers take the one-call kernel (fewer launches, less SM time) - unless the caller
+    knows the result is waited for: as a dependency chain four short launches (12-14 us) beat its product -> fence -> ticket
+    -> sum sequence (20-50 us at 4096 rows, tools/bench_wgrad_small.py)."""
     B, K = x.shape
     N = dy.shape[1]
-    if _SMALL_WGRAD:
+    if _SMALL_WGRAD and not on_critical_path:
         need = linear_wgrad_small_scratch_floats(B, K, N)
         if 0 < need <= scratch.numel() and scratch.data_ptr() % 16 == 0:
             linear_wgrad_small(x, dy, scratch, dw, db)

@@ -1,5 +1,5 @@
 """Per-launcher device time of one step of a Python-composed plan (eager, CUDA events on the launching stream).
-    python tools/prof_plan.py dcgan|kc|moons_cf|cgan_moons|simple_moons"""
+    python tools/prof_plan.py dcgan|kc|moons_cf|cgan_moons|simple_moons|cwgan"""
 import ctypes, json, sys
 sys.path.insert(0, '.')
 import torch
@@ -15,7 +15,7 @@ native_step(0); native_step(1); torch.cuda.synchronize()
 # find the plan object through the closure and force eager execution
 plan = [c.cell_contents for c in native_step.__closure__ if hasattr(c.cell_contents, "step")][0]
 if hasattr(plan, "use_graph"): plan.use_graph = False
-if hasattr(plan, "run"): plan.run.use_graph = False
+if hasattr(getattr(plan, "run", None), "use_graph"): plan.run.use_graph = False
 _lib.check(L.pcg_profile_begin())
 n = 3
 for i in range(n): native_step(i)
