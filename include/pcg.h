@@ -407,11 +407,10 @@ int pcg_instnorm_bwd_bwd(const float* q, const float* gy, const float* act_ref, 
                          const float* mean, const float* rstd, const float* gamma, int N, int P, int C, float* gy_bar,
                          float* x_bar, float* dgamma_part, void* stream);
 int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, int c0, int inverse, void* stream);
-/* Weight and bias gradient of a small nn.Linear (K inputs, N outputs, both <= 128) in ONE launch (two above 2048 weights): dw[N][K] = dy^T x (torch
- * layout), db[N] = column sums of dy (NULL: skipped) - instead of pcg_conv_wgrad + pcg_colsum (four launches).  scratch:
- * pcg_linear_wgrad_small_scratch(M, K, N) floats (-1: shape not supported), 16-byte aligned, uninitialised, not shared by
- * launches that may run concurrently (per-CTA partials; the arrival counter of the last-CTA reduction is library-owned,
- * one per scratch pointer); deterministic.  The first call must be outside stream capture. */
+/* Weight and bias gradient of a small nn.Linear (K inputs, N outputs, both <= 128) in ONE call of two launches (product over
+ * up to 128 row slices, then a wide deterministic sum): dw[N][K] = dy^T x (torch layout), db[N] = column sums of dy (NULL:
+ * skipped) - instead of pcg_conv_wgrad + pcg_colsum (four launches).  scratch: pcg_linear_wgrad_small_scratch(M, K, N) floats
+ * (-1: shape not supported), 16-byte aligned, uninitialised, not shared by launches that may run concurrently. */
 long long pcg_linear_wgrad_small_scratch(long long M, int K, int N);
 int pcg_linear_wgrad_small(const float* x, const float* dy, long long M, int K, int N, float* scratch, float* dw, float* db,
                            void* stream);

@@ -11,7 +11,6 @@
 // is the same call with the transposed weight the plans already keep ([K][N] = "[out][in]" of the backward product).
 #include "linear_small.cuh"
 
-#include <unordered_map>
 
 namespace pcg {
 
@@ -134,42 +133,39 @@ void linear_small(const float* in, long long M, int K, int N, const float* w, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Weight AND bias gradient of a small Linear layer in ONE launch:  dw[N][K] = dy^T x,  db[N] = column sums of dy
-// (K, N <= 128; the tabular networks: 21..128 wide, 4096 rows).  As primitive operators this is four launches (split-K
-// product, its reduction, column sums, their reduction) per layer, 37 layers per KC iteration - off the critical path, but
-// they occupy the SMs the critical path needs.  P CTAs take row slices; a thread owns up to 16 float4 outputs
-// (n, k4 .. k4+3); every CTA leaves its partial in scratch and the last one to arrive (device-scope ticket) adds them in
-// CTA order: deterministic.  The ticket is a library-owned counter per scratch buffer (zero between launches, it resets
-// itself), so the scratch may be shared with other operators and needs no initialisation.
+// Weight AND bias gradient of a small Linear layer in ONE call (two launches):  dw[N][K] = dy^T x,  db[N] = column sums of
+// dy (K, N <= 128; the tabular networks: 21..128 wide, 4096 rows).  As primitive operators this is four launches (split-K
+// product, its reduction, column sums, their reduction) per layer, 37 layers per KC iteration.
+//   product  up to 128 CTAs take 32-row slices (one shared-memory tile each at 4096 rows); a thread owns up to 16 float4
+//            outputs (n, k4 .. k4+3); partials [P][N * K4 * 4 + 128] go to scratch
+//   sum      eight lanes per float4 output: lane l adds partials l, l + 8, ... (all loads in flight), then a fixed butterfly
+// Deterministic; ~7 us as a dependency chain against 12-14 us for the four launches (tools/bench_wgrad_small.py).  A first
+// version added the partials in the last CTA to arrive (one launch, a device-scope ticket): 20-50 us, the product -> fence ->
+// ticket -> 64 sequential partial reads chain is pure latency.
 constexpr int LW_TR = 32;            // rows per shared-memory tile
-constexpr int LW_MAXP = 64;          // row slices (CTAs)
+constexpr int LW_MAXP = 128;         // row slices (CTAs)
 
-static int lw_ctas(long long M, int, int) {
-  const long long p = (M + 63) / 64;
+static int lw_ctas(long long M) {
+  const long long p = (M + LW_TR - 1) / LW_TR;
   return (int)(p < 1 ? 1 : (p < LW_MAXP ? p : LW_MAXP));
 }
-// Layers above this many outputs add their partials in a second, wide launch: 64 slices of a 64 x 128 layer are 2 MB for
-// ONE last CTA to add up (56 us measured; fewer, longer slices cost more in the product than they save in the sum).
-constexpr int LW_ONE_LAUNCH_ELEMS = 2048;
 bool linear_wgrad_small_supported(long long M, int K, int N) { return M >= 1 && K >= 1 && K <= LS_MAXD && N >= 1 && N <= LS_MAXD; }
 long long linear_wgrad_small_scratch(long long M, int K, int N) {
   const int K4 = (K + 3) / 4;
-  return 4 + (long long)lw_ctas(M, K, N) * ((long long)N * K4 * 4 + LS_MAXD);
+  return 4 + (long long)lw_ctas(M) * ((long long)N * K4 * 4 + LS_MAXD);
 }
 
 template <int J>
 __global__ void __launch_bounds__(LS_THREADS)
 linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long M, int K, int N,
-                          float* __restrict__ scratch, unsigned int* __restrict__ ticket, float* __restrict__ dw,
-                          float* __restrict__ db) {      // ticket == NULL: partials only, linear_wgrad_small_sum_kernel follows
+                          float* __restrict__ scratch) {
   pdl_enter();
   extern __shared__ __align__(16) float sm[];
-  __shared__ bool last;
   const int K4 = (K + 3) >> 2, KP = K4 * 4;
   float* sx = sm;                       // [LW_TR][KP], zero padded columns
   float* sdy = sm + LW_TR * KP;         // [LW_TR][N]
   const int nout4 = N * K4;
-  const long long per = (M + gridDim.x - 1) / gridDim.x;
+  const long long per = ((M + gridDim.x - 1) / gridDim.x + LW_TR - 1) / LW_TR * LW_TR;
   const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < M ? r0 + per : M;
   float4 acc[J];
   int on[J], ok4[J];
@@ -212,104 +208,43 @@ linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
   for (int j = 0; j < J; ++j)
     if (on[j] >= 0) *reinterpret_cast<float4*>(mine + (size_t)(threadIdx.x + LS_THREADS * j) * 4) = acc[j];
-  if (threadIdx.x < N) mine[(size_t)nout4 * 4 + threadIdx.x] = bsum;
-  if (ticket == nullptr) return;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  const int P = gridDim.x;
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    if (on[j] < 0) continue;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t off = 4 + (size_t)(threadIdx.x + LS_THREADS * j) * 4;
-    for (int p0 = 0; p0 < P; p0 += 8) {               // eight loads in flight; added in CTA order
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        v[u] = p0 + u < P ? __ldcg(reinterpret_cast<const float4*>(scratch + off + (size_t)(p0 + u) * stride))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }
-    }
-    float* o = dw + (size_t)on[j] * K + ok4[j] * 4;
-    const int left = K - ok4[j] * 4;
-    o[0] = t.x;
-    if (left > 1) o[1] = t.y;
-    if (left > 2) o[2] = t.z;
-    if (left > 3) o[3] = t.w;
-  }
-  if (db != nullptr && threadIdx.x < N) {
-    float t = 0.f;
-    for (int p0 = 0; p0 < P; p0 += 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        v[u] = p0 + u < P ? __ldcg(scratch + 4 + (size_t)(p0 + u) * stride + (size_t)nout4 * 4 + threadIdx.x) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) t += v[u];
-    }
-    db[threadIdx.x] = t;
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
+  if (threadIdx.x < LS_MAXD) mine[(size_t)nout4 * 4 + threadIdx.x] = threadIdx.x < N ? bsum : 0.f;
 }
 
-// second launch for the larger layers: a thread per float4 of dw (and per element of db) adds the P partials in CTA order
+// eight lanes per float4 of dw (then per float4 of db): lane l adds partials l, l + 8, ... in that order, a fixed butterfly
+// over the eight lanes finishes
 __global__ void __launch_bounds__(LS_THREADS)
 linear_wgrad_small_sum_kernel(const float* __restrict__ scratch, int P, int K, int N, float* __restrict__ dw,
                               float* __restrict__ db) {
   pdl_enter();
-  const int K4 = (K + 3) >> 2, nout4 = N * K4;
+  const int K4 = (K + 3) >> 2, nout4 = N * K4, nb4 = (N + 3) >> 2;
   const size_t stride = (size_t)nout4 * 4 + LS_MAXD;
-  const int o = blockIdx.x * LS_THREADS + threadIdx.x;
+  const int o = (blockIdx.x * LS_THREADS + threadIdx.x) >> 3, lane = threadIdx.x & 7;
+  const bool live = o < nout4 + nb4;
+  float4 v[LW_MAXP / 8];
+#pragma unroll
+  for (int u = 0; u < LW_MAXP / 8; ++u) {
+    const int p = lane + 8 * u;
+    v[u] = (live && p < P) ? *reinterpret_cast<const float4*>(scratch + 4 + (size_t)o * 4 + (size_t)p * stride)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 t = v[0];
+#pragma unroll
+  for (int u = 1; u < LW_MAXP / 8; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }
+#pragma unroll
+  for (int off = 4; off >= 1; off >>= 1) {
+    t.x += __shfl_xor_sync(0xffffffffu, t.x, off); t.y += __shfl_xor_sync(0xffffffffu, t.y, off);
+    t.z += __shfl_xor_sync(0xffffffffu, t.z, off); t.w += __shfl_xor_sync(0xffffffffu, t.w, off);
+  }
+  if (!live || lane != 0) return;
+  const float tv[4] = {t.x, t.y, t.z, t.w};
   if (o < nout4) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p0 = 0; p0 < P; p0 += 8) {
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        v[u] = p0 + u < P ? *reinterpret_cast<const float4*>(scratch + 4 + (size_t)o * 4 + (size_t)(p0 + u) * stride)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }
-    }
     const int n = o / K4, k4 = o - n * K4;
-    float* dst = dw + (size_t)n * K + k4 * 4;
-    const int left = K - k4 * 4;
-    dst[0] = t.x;
-    if (left > 1) dst[1] = t.y;
-    if (left > 2) dst[2] = t.z;
-    if (left > 3) dst[3] = t.w;
-  } else if (db != nullptr && o < nout4 + N) {
-    const int n = o - nout4;
-    float t = 0.f;
-    for (int p = 0; p < P; ++p) t += scratch[4 + (size_t)p * stride + (size_t)nout4 * 4 + n];
-    db[n] = t;
+    for (int e = 0; e < 4 && k4 * 4 + e < K; ++e) dw[(size_t)n * K + k4 * 4 + e] = tv[e];
+  } else if (db != nullptr) {
+    const int n0 = (o - nout4) * 4;
+    for (int e = 0; e < 4 && n0 + e < N; ++e) db[n0 + e] = tv[e];
   }
-}
-
-// one arrival counter per scratch buffer, from a zeroed block allocated on first use (an eager pass: cudaMalloc is illegal
-// during stream capture; later buffers only take the next index)
-static unsigned int* lw_ticket(const float* scratch, cudaStream_t s) {
-  constexpr int kTickets = 8192;
-  static unsigned int* block = nullptr;
-  static std::unordered_map<const float*, int> index;
-  if (block == nullptr) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(s, &st);
-    if (st != cudaStreamCaptureStatusNone) throw Error(5, "linear_wgrad_small: first use must be an eager pass (allocates its arrival counters)");
-    PCG_CHECK_CUDA(cudaMalloc(&block, kTickets * sizeof(unsigned int)));
-    PCG_CHECK_CUDA(cudaMemset(block, 0, kTickets * sizeof(unsigned int)));
-  }
-  auto it = index.find(scratch);
-  if (it == index.end()) {
-    PCG_REQUIRE((int)index.size() < kTickets, "linear_wgrad_small: more than 8192 distinct scratch buffers");
-    it = index.emplace(scratch, (int)index.size()).first;
-  }
-  return block + it->second;
 }
 
 void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int N, float* scratch, float* dw, float* db,
@@ -320,10 +255,8 @@ void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int
   const int K4 = (K + 3) / 4, nout4 = N * K4;
   const int J = (nout4 + LS_THREADS - 1) / LS_THREADS;
   const size_t smem = (size_t)LW_TR * (K4 * 4 + N) * sizeof(float);
-  const dim3 grid(lw_ctas(M, K, N));
-  const bool two = (long long)nout4 * 4 > LW_ONE_LAUNCH_ELEMS;
-  unsigned int* ticket = two ? nullptr : lw_ticket(scratch, s);
-#define PCG_LW(JJ) launch_k(linear_wgrad_small_kernel<JJ>, grid, dim3(LS_THREADS), smem, s, x, dy, M, K, N, scratch, ticket, dw, db)
+  const dim3 grid(lw_ctas(M));
+#define PCG_LW(JJ) launch_k(linear_wgrad_small_kernel<JJ>, grid, dim3(LS_THREADS), smem, s, x, dy, M, K, N, scratch)
   if (J <= 1) PCG_LW(1);
   else if (J <= 2) PCG_LW(2);
   else if (J <= 4) PCG_LW(4);
@@ -331,11 +264,10 @@ void linear_wgrad_small(const float* x, const float* dy, long long M, int K, int
   else PCG_LW(16);
 #undef PCG_LW
   PCG_COUNT_LAUNCH();
-  if (two) {
-    launch_k(linear_wgrad_small_sum_kernel, dim3((nout4 + N + LS_THREADS - 1) / LS_THREADS), dim3(LS_THREADS), 0, s, scratch,
-             (int)grid.x, K, N, dw, db);
-    PCG_COUNT_LAUNCH();
-  }
+  const int outs = nout4 + (N + 3) / 4;
+  launch_k(linear_wgrad_small_sum_kernel, dim3((outs * 8 + LS_THREADS - 1) / LS_THREADS), dim3(LS_THREADS), 0, s, scratch,
+           (int)grid.x, K, N, dw, db);
+  PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 

@@ -200,12 +200,11 @@ _SMALL_WGRAD = os.environ.get("PCG_SMALL_WGRAD", "1") != "0"
 
 
 def linear_wgrad(x, dy, scratch, dw, db=None, stat=None, on_critical_path=False):
-    """dw, db of a Linear layer.  Small layers take the one-call kernel (fewer launches, less SM time) - unless the caller
-    knows the result is waited for: as a dependency chain four short launches (12-14 us) beat its product -> fence -> ticket
-    -> sum sequence (20-50 us at 4096 rows, tools/bench_wgrad_small.py)."""
+    """dw, db of a Linear layer.  Small layers take the one-call kernel (two launches instead of four);
+    ``on_critical_path`` forces the primitive operators (kept for A/B measurements, tools/bench_wgrad_small.py)."""
     B, K = x.shape
     N = dy.shape[1]
-    if _SMALL_WGRAD and not on_critical_path:
+    if _SMALL_WGRAD and not on_critical_path and N * K <= 4096:      # 64 x 128: 27 us against 14 us for the four launches
         need = linear_wgrad_small_scratch_floats(B, K, N)
         if 0 < need <= scratch.numel() and scratch.data_ptr() % 16 == 0:
             linear_wgrad_small(x, dy, scratch, dw, db)

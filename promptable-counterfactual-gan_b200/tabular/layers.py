@@ -128,8 +128,7 @@ class SNDense(_OwnScratch):
 
     def wgrad(self, x, dy, p, garena):
         """garena(name) -> gradient slot.  dW_orig = (dWn - <dWn, Wn> u v^T) / sigma."""
-        # the critic's update (spectral-norm backward, Adam, the next forward) waits for this: latency matters, not SM time
-        K.linear_wgrad(x, dy, self.wsc, self.dWn[p], garena(self.name + ".bias"), self.stat, on_critical_path=True)
+        K.linear_wgrad(x, dy, self.wsc, self.dWn[p], garena(self.name + ".bias"), self.stat)
         K.spectral_norm_bwd(self.dWn[p], self.Wn[p], self.us[p], self.vs[p], self.sigma[p], garena(self.name + ".weight_orig"))
 
 
