@@ -1,6 +1,8 @@
 // HBM-bound kernels of the GAN step (see elementwise.cuh for the reference call sites).
 #include "elementwise.cuh"
 
+#include "cluster_reduce.cuh"
+
 #include <initializer_list>
 
 namespace pcg {
@@ -942,8 +944,11 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, const long long
                                float wgt, float* loss, float* __restrict__ dlogits) {
   pdl_enter();
   __shared__ float red[32];
+  __shared__ float slot;
+  long long rb, re;
+  cluster_slice(B, rb, re);
   float sl = 0.f;
-  for (int n = threadIdx.x; n < B; n += blockDim.x) {
+  for (int n = (int)rb + threadIdx.x; n < (int)re; n += blockDim.x) {
     const float* l = logits + (size_t)n * NC;
     float mx = l[0];
     for (int j = 1; j < NC; ++j) mx = fmaxf(mx, l[j]);
@@ -957,13 +962,13 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, const long long
       dlogits[(size_t)n * NC + j] = wgt * (p - (j == t ? 1.f : 0.f)) / (float)B;
     }
   }
-  sl = block_sum_1024(sl, red);
-  if (threadIdx.x == 0) loss[0] = sl / (float)B;
+  sl = cluster_total(block_sum_1024(sl, red), &slot);
+  if (cluster_leader()) loss[0] = sl / (float)B;
 }
 void ce_loss(const float* logits, const long long* target, int B, int NC, float wgt, float* loss, float* dlogits,
              cudaStream_t s) {
   PCG_PROFILE("small", s);
-  launch_k(ce_loss_kernel, dim3(1), dim3(256), 0, s, logits, target, B, NC, wgt, loss, dlogits);
+  launch_k_cluster(ce_loss_kernel, B, dim3(B >= CR_MIN_ITEMS ? 512 : 256), 0, s, logits, target, B, NC, wgt, loss, dlogits);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

@@ -4,6 +4,8 @@
 // problem sizes; the step plans capture them in a CUDA graph.
 #include "ops.cuh"
 
+#include "cluster_reduce.cuh"
+
 namespace pcg {
 
 static int blocks_for(long long n) {
@@ -196,19 +198,22 @@ __global__ void reduce_scalar_kernel(const float* __restrict__ x, long long n, i
                                      float gscale, float* __restrict__ dx) {
   pdl_enter();
   __shared__ float red[32];
+  __shared__ float slot;
+  long long i0, i1;
+  cluster_slice(n, i0, i1);
   float s = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     const float v = x[i];
     s += absval ? fabsf(v) : v;
     if (dx) dx[i] = absval ? gscale * ((v > 0.f) - (v < 0.f)) : gscale;
   }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) out[0] = s * scale;
+  s = cluster_total(block_sum(s, red), &slot);
+  if (cluster_leader()) out[0] = s * scale;
 }
 void reduce_scalar(const float* x, long long n, int absval, float scale, float* out, float gscale, float* dx,
                    cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  launch_k(reduce_scalar_kernel, dim3(1), dim3(1024), 0, s, x, n, absval, scale, out, gscale, dx);
+  launch_k_cluster(reduce_scalar_kernel, n / 8, dim3(1024), 0, s, x, n, absval, scale, out, gscale, dx);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -218,8 +223,11 @@ __global__ void rownorm_mean_kernel(const float* __restrict__ x, long long rows,
                                     float gscale, float* __restrict__ dx) {
   pdl_enter();
   __shared__ float red[32];
+  __shared__ float slot;
+  long long rb, re;
+  cluster_slice(rows, rb, re);
   float s = 0.f;
-  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+  for (long long r = rb + threadIdx.x; r < re; r += blockDim.x) {
     float a = 0.f;
     for (int c = 0; c < cols; ++c) {
       const float v = x[r * cols + c];
@@ -237,12 +245,12 @@ __global__ void rownorm_mean_kernel(const float* __restrict__ x, long long rows,
       }
     }
   }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) out[0] = s / (float)rows;
+  s = cluster_total(block_sum(s, red), &slot);
+  if (cluster_leader()) out[0] = s / (float)rows;
 }
 void rownorm_mean(const float* x, long long rows, int cols, int p, float* out, float gscale, float* dx, cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  launch_k(rownorm_mean_kernel, dim3(1), dim3(1024), 0, s, x, rows, cols, p, out, gscale, dx);
+  launch_k_cluster(rownorm_mean_kernel, rows, dim3(rows >= CR_MIN_ITEMS ? 512 : 1024), 0, s, x, rows, cols, p, out, gscale, dx);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -257,8 +265,11 @@ __global__ void gan_loss_kernel(const float* __restrict__ z, int n, int kind, fl
                                 float* out_aux, float* __restrict__ dz) {
   pdl_enter();
   __shared__ float red[32];
+  __shared__ float slot;
+  long long i0, i1;
+  cluster_slice(n, i0, i1);
   float sl = 0.f, sp = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = (int)i0 + threadIdx.x; i < (int)i1; i += blockDim.x) {
     const float v = z[i];
     if (kind == 2) {
       const float sign = t > 0.5f ? -1.f : 1.f;
@@ -274,9 +285,9 @@ __global__ void gan_loss_kernel(const float* __restrict__ z, int n, int kind, fl
       dz[i] = wgt * (t > 0.5f ? -(1.f - p) : p) / (float)n;
     }
   }
-  sl = block_sum(sl, red);
-  sp = block_sum(sp, red);
-  if (threadIdx.x == 0) {
+  sl = cluster_total(block_sum(sl, red), &slot);
+  sp = cluster_total(block_sum(sp, red), &slot);
+  if (cluster_leader()) {
     out_loss[0] = sl / (float)n;
     if (out_aux) out_aux[0] = sp / (float)n;
   }
@@ -284,7 +295,7 @@ __global__ void gan_loss_kernel(const float* __restrict__ z, int n, int kind, fl
 void gan_loss(const float* z, int n, int kind, float t, float wgt, float* out_loss, float* out_aux, float* dz,
               cudaStream_t s) {
   PCG_PROFILE("ops_small", s);
-  launch_k(gan_loss_kernel, dim3(1), dim3(256), 0, s, z, n, kind, t, wgt, out_loss, out_aux, dz);
+  launch_k_cluster(gan_loss_kernel, n, dim3(n >= CR_MIN_ITEMS ? 512 : 256), 0, s, z, n, kind, t, wgt, out_loss, out_aux, dz);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
