@@ -407,6 +407,19 @@ int pcg_instnorm_bwd_bwd(const float* q, const float* gy, const float* act_ref, 
                          const float* mean, const float* rstd, const float* gamma, int N, int P, int C, float* gy_bar,
                          float* x_bar, float* dgamma_part, void* stream);
 int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, int c0, int inverse, void* stream);
+/* The frozen classifier of the tabular CounteRGAN generator step (house_sales_kc_usa/trainer.py:300-303, moons/trainer.py:
+ * 85-87: F.cross_entropy(clf_model(x_cf), target) with clf_model in eval mode and frozen) in ONE launch: an MLP of L Linear
+ * layers (torch [out][in] weights W[j], their transposes WT[j] [in][out], biases b[j]: host arrays of device pointers;
+ * dims[0..L] = the widths; LeakyReLU(slope) between the layers - slope 0 is ReLU; eval-mode BatchNorms folded into the
+ * following Linear by the caller), its
+ * cross-entropy against `target` (loss_kind 0) or the mean of its outputs (loss_kind 1: a critic score inside the generator
+ * step, trainer.py:298; target may be NULL), and the backward pass down to dx = wgt * d loss / d x.  logits (NULL: not stored)
+ * [B][dims[L]]; loss_part: pcg_frozen_mlp_parts() floats (-1: shape not supported), sum(loss_part) / B = the mean loss.
+ * Hidden widths in {32, 64, 128, 256}, dims[0] <= 64, dims[L] <= 8. */
+int pcg_frozen_mlp_parts(int L, const int* dims, int B);
+int pcg_frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const float* const* WT, const float* const* b,
+                           float slope, const float* x, const long long* target, int loss_kind, int B, float wgt,
+                           float* logits, float* loss_part, float* dx, void* stream);
 /* Weight and bias gradient of a small nn.Linear (K inputs, N outputs, both <= 128) in ONE call of two launches (product over
  * up to 128 row slices, then a wide deterministic sum): dw[N][K] = dy^T x (torch layout), db[N] = column sums of dy (NULL:
  * skipped) - instead of pcg_conv_wgrad + pcg_colsum (four launches).  scratch: pcg_linear_wgrad_small_scratch(M, K, N) floats

@@ -11,6 +11,7 @@
 #include "ops.cuh"
 #include "instnorm.cuh"
 #include "film_layer.cuh"
+#include "frozen_mlp.cuh"
 
 using namespace pcg;
 
@@ -368,6 +369,15 @@ int pcg_linear_wgrad_small(const float* x, const float* dy, long long M, int K, 
   PCG_API_BEGIN
   PCG_REQUIRE(x && dy && scratch && dw, "linear_wgrad_small: null pointer");
   linear_wgrad_small(x, dy, M, K, N, scratch, dw, db, ST);
+  PCG_API_END
+}
+int pcg_frozen_mlp_parts(int L, const int* dims, int B) { return frozen_mlp_supported(L, dims) ? frozen_mlp_parts(B) : -1; }
+int pcg_frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const float* const* WT, const float* const* b,
+                           float slope, const float* x, const long long* target, int loss_kind, int B, float wgt,
+                           float* logits, float* loss_part, float* dx, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(dims && W && WT && b && x && loss_part && dx && B >= 1, "frozen_mlp_ce_grad: null pointer / empty batch");
+  frozen_mlp_ce_grad(L, dims, W, WT, b, slope, x, target, loss_kind, B, wgt, logits, loss_part, dx, ST);
   PCG_API_END
 }
 int pcg_film_layer_supported(long long M, int H) { return film_layer_supported(M, H) ? 1 : 0; }

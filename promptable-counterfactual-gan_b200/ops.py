@@ -430,6 +430,28 @@ def flatten_nchw(src, B, R, C, dst, ld, c0=0, inverse=False):
     _lib.check(_L().pcg_flatten_nchw(P(src), B, R, C, P(dst), ld, c0, 1 if inverse else 0, _s()))
 
 
+def frozen_mlp_parts(dims, B):
+    """Floats of the per-CTA loss parts of ``frozen_mlp_ce_grad``; -1 when the shape is not supported."""
+    arr = (ctypes.c_int * len(dims))(*dims)
+    return int(_L().pcg_frozen_mlp_parts(len(dims) - 1, arr, B))
+
+
+@_op("logits", "loss_part", "dx")
+def frozen_mlp_ce_grad(weights, weights_t, biases, x, target, loss_part, dx, wgt=1.0, slope=0.0, logits=None, mean_output=False):
+    """Frozen MLP classifier: forward, cross-entropy against ``target`` and the gradient with respect to ``x`` in one launch
+    (pcg_frozen_mlp_ce_grad).  weights[j] is the torch [out][in] matrix of layer j, weights_t[j] its transpose;
+    LeakyReLU(slope) between layers.  mean_output: the loss is the mean of the network's outputs (a critic score) instead
+    of the cross-entropy, ``target`` is not used."""
+    B, d0 = x.shape
+    dims = [d0] + [w.shape[0] for w in weights]
+    _chk(x, loss_part, dx, logits, *weights, *weights_t, *biases)
+    L = len(weights)
+    ptrs = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])  # noqa: E731
+    _lib.check(_L().pcg_frozen_mlp_ce_grad(L, (ctypes.c_int * (L + 1))(*dims), ptrs(weights), ptrs(weights_t), ptrs(biases),
+                                           _f(slope), P(x), P(target), 1 if mean_output else 0, B, _f(wgt), P(logits),
+                                           P(loss_part), P(dx), _s()))
+
+
 def film_layer_supported(M, H):
     return bool(_L().pcg_film_layer_supported(_ll(M), H))
 

@@ -210,6 +210,11 @@ class KcPlan:
         # primitive operators
         import os
         self.fused = os.environ.get("PCG_FILM_LAYER", "1") != "0" and K.film_layer_supported(B, h)
+        # the frozen classifier's forward + cross-entropy + input gradient as ONE launch (csrc/frozen_mlp.cu)
+        self.cls_parts = K.frozen_mlp_parts([d] + [b for _, b in cdims] + [nc], B)
+        self.fused_cls = os.environ.get("PCG_FROZEN_MLP", "1") != "0" and self.cls_parts > 0
+        self.cls_part = z(max(self.cls_parts, 1))
+        self.adv_part = z(max(self.cls_parts, 1))
         self.run = GraphStep(self._body, self._state, self.refresh, use_graph)
         self.refresh()
 
@@ -335,22 +340,23 @@ class KcPlan:
         K.combine([(1.0, self.scal[7:8]), (1.0, self.scal[8:9])], self.scal[0:1])
         D.flat.adam_step(self.lr_d)
         # ---- G update (:298-316)
-        out_g = D.fwd(self.xcf, self.t_oh, 1)
-        K.gan_loss(out_g, K.GAN_WASSERSTEIN, 1.0, self.scal[2:3], self.dz, out_aux=self.scal[10:11])
-        ddin = D.bwd(self.dz, 1, None, want_dx=True)
+        if self.fused_cls and D.fused_ok:
+            # adversarial term: critic forward, -mean(score) and its input gradient as one launch; the scalars off the path
+            out_g, ddin = D.input_gradient(self.xcf, self.t_oh, 1, -1.0, self.adv_part)
+            K.gan_loss(out_g, K.GAN_WASSERSTEIN, 1.0, self.scal[2:3], self.dz, out_aux=self.scal[10:11])
+        else:
+            out_g = D.fwd(self.xcf, self.t_oh, 1)
+            K.gan_loss(out_g, K.GAN_WASSERSTEIN, 1.0, self.scal[2:3], self.dz, out_aux=self.scal[10:11])
+            ddin = D.bwd(self.dz, 1, None, want_dx=True)
         K.copy_cols(ddin, 0, self.dx_adv, 0, d)
         # frozen classifier, BatchNorm folded (see __init__): forward and input gradient
-        self.cl[0].fwd(self.xcf, self.c_act[0], K.ACT_LRELU, 0.1)
-        for j in range(1, 4):
-            K.linear_fwd(self.c_act[j - 1], self.cwf[j], self.c_act[j], self.cbf[j], K.ACT_LRELU, 0.1)
-        K.linear_fwd(self.c_act[3], self.cwf[4], self.clog, self.cbf[4])
-        K.ce_loss(self.clog, self.target, self.scal[3:4], self.cdlog, wgt=lam[0])
-        dcur = self.cdlog
-        for j in range(4, 0, -1):
-            K.linear_dgrad(dcur, self.cwfT[j], self.c_dh[j - 1], self.cwf[j].shape[1], act_ref=self.c_act[j - 1],
-                           ref_act=K.ACT_LRELU, ref_slope=0.1)
-            dcur = self.c_dh[j - 1]
-        self.cl[0].dgrad(dcur, self.dx_cls)
+        if self.fused_cls:
+            K.frozen_mlp_ce_grad([self.cl[0].W()] + self.cwf[1:], [self.cl[0].wT] + self.cwfT[1:],
+                                 [self.cl[0].b()] + self.cbf[1:], self.xcf, self.target, self.cls_part, self.dx_cls,
+                                 wgt=lam[0], slope=0.1, logits=self.clog)
+            K.reduce_scalar(self.cls_part, self.scal[3:4], 1.0 / B)
+        else:
+            self._classifier_by_layers(lam)
         K.rownorm_mean(self.masked, 1, self.scal[4:5], dx=self.d_l1, gscale=lam[1])   # :305
         K.combine([(1.0, self.scal[2:3]), (lam[0], self.scal[3:4]), (lam[1], self.scal[4:5]), (lam[2], self.scal[5:6])],
                   self.scal[1:2])
@@ -365,6 +371,19 @@ class KcPlan:
             g_layers += [b[k] for k in ("fc1", "fc2", "fg", "fb")]
         K.transpose_multi([(L.W(), L.wT) for L in g_layers])            # dgrad operands of the updated generator
         # ---- diagnostics of trainer.py:319-343 that need an extra classifier pass are left to the caller
+
+    def _classifier_by_layers(self, lam):
+        self.cl[0].fwd(self.xcf, self.c_act[0], K.ACT_LRELU, 0.1)
+        for j in range(1, 4):
+            K.linear_fwd(self.c_act[j - 1], self.cwf[j], self.c_act[j], self.cbf[j], K.ACT_LRELU, 0.1)
+        K.linear_fwd(self.c_act[3], self.cwf[4], self.clog, self.cbf[4])
+        K.ce_loss(self.clog, self.target, self.scal[3:4], self.cdlog, wgt=lam[0])
+        dcur = self.cdlog
+        for j in range(4, 0, -1):
+            K.linear_dgrad(dcur, self.cwfT[j], self.c_dh[j - 1], self.cwf[j].shape[1], act_ref=self.c_act[j - 1],
+                           ref_act=K.ACT_LRELU, ref_slope=0.1)
+            dcur = self.c_dh[j - 1]
+        self.cl[0].dgrad(dcur, self.dx_cls)
 
     def _g_bwd(self):
         h = self.hlast

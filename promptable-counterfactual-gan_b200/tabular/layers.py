@@ -186,6 +186,24 @@ class Critic:
             d = self.dh[p][i - 1]
         return self.ddin
 
+    def input_gradient(self, x, onehot, p, wgt, loss_part):
+        """The generator's adversarial term in ONE launch (csrc/frozen_mlp.cu): forward pass p with the critic's current
+        weights (power iteration included, as ``fwd``), the loss ``mean(score)`` and d (wgt * loss) / d [x, onehot] -> ddin.
+        The scores land in h[p][-1] like ``fwd``'s.  Only when ``fused_ok``."""
+        xd = x.shape[1]
+        K.copy_cols(x, 0, self.din[p], 0, xd)
+        K.copy_cols(onehot, 0, self.din[p], xd, onehot.shape[1])
+        for L in self.layers:
+            L.normalise(p, True)
+        K.frozen_mlp_ce_grad([L.Wn[p] for L in self.layers], [L.WnT[p] for L in self.layers], [L.b() for L in self.layers],
+                             self.din[p], None, loss_part, self.ddin, wgt=wgt, slope=0.2, logits=self.h[p][-1],
+                             mean_output=True)
+        return self.h[p][-1], self.ddin
+
+    @property
+    def fused_ok(self):
+        return K.frozen_mlp_parts([self.dims[0][0]] + [b for _, b in self.dims], self.ctx.B) > 0
+
     def g1(self, n):
         return self.flat.g(n)
 
