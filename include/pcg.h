@@ -415,7 +415,7 @@ int pcg_flatten_nchw(const float* src, int B, int R, int C, float* dst, int ld, 
  * cross-entropy against `target` (loss_kind 0) or the mean of its outputs (loss_kind 1: a critic score inside the generator
  * step, trainer.py:298; target may be NULL), and the backward pass down to dx = wgt * d loss / d x.  logits (NULL: not stored)
  * [B][dims[L]]; loss_part: pcg_frozen_mlp_parts() floats (-1: shape not supported), sum(loss_part) / B = the mean loss.
- * Hidden widths in {32, 64, 128, 256}, dims[0] <= 64, dims[L] <= 8. */
+ * Hidden widths in {16, 32, 64, 128, 256}, dims[0] <= 64, dims[L] <= 8. */
 int pcg_frozen_mlp_parts(int L, const int* dims, int B);
 int pcg_frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const float* const* WT, const float* const* b,
                            float slope, const float* x, const long long* target, int loss_kind, int B, float wgt,

@@ -42,9 +42,10 @@ __device__ void fm_gemm(const float* __restrict__ Wq, int C, int Q, const float*
                         const float* __restrict__ bias, const float* __restrict__ maskT, float slope,
                         float* __restrict__ outT, float* __restrict__ panel) {
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7, half = threadIdx.x >> 8;
-  // columns of this lane: half * C/2 + lane * CW + e, e < CW = C/64 (C = 32: one column, the second half idles)
+  // columns of this lane: half * C/2 + lane * CW + e, e < CW = C/64 (C = 32 / 16: one column, the second half - and for
+  // 16 the upper lanes - idle)
   const int CW = C >= 64 ? C >> 6 : 1;
-  const bool live = C >= 64 || half == 0;
+  const bool live = C >= 64 || (half == 0 && lane < C);
   const int cbase = (C >= 64 ? half * (C >> 1) : 0) + lane * CW;
   float acc[4][4];
 #pragma unroll
@@ -223,7 +224,7 @@ bool frozen_mlp_supported(int L, const int* dims) {
   if (L < 2 || L > FM_MAX_LAYERS) return false;
   if (dims[0] < 1 || dims[0] > 64 || dims[L] < 1 || dims[L] > FM_MAX_CLASSES) return false;
   for (int j = 1; j < L; ++j)
-    if (dims[j] != 32 && dims[j] != 64 && dims[j] != 128 && dims[j] != 256) return false;
+    if (dims[j] != 16 && dims[j] != 32 && dims[j] != 64 && dims[j] != 128 && dims[j] != 256) return false;
   return true;
 }
 int frozen_mlp_parts(int B) { return (B + FM_ROWS - 1) / FM_ROWS; }
@@ -233,7 +234,7 @@ void frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const flo
                         const long long* target, int loss_kind, int B, float wgt, float* logits, float* loss_part, float* dx,
                         cudaStream_t s) {
   PCG_PROFILE("frozen_mlp", s);
-  PCG_REQUIRE(frozen_mlp_supported(L, dims), "frozen_mlp: 2..6 layers, input <= 64, hidden widths in {32, 64, 128, 256}, <= 8 classes");
+  PCG_REQUIRE(frozen_mlp_supported(L, dims), "frozen_mlp: 2..6 layers, input <= 64, hidden widths in {16, 32, 64, 128, 256}, <= 8 classes");
   FmArgs m;
   m.L = L;
   m.slope = slope;

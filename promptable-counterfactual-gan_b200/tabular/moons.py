@@ -113,6 +113,11 @@ class MoonsPlan:
         self.c0, self.c1, self.clog, self.cdlog = z(B, h), z(B, h), z(B, nc), z(B, nc)
         self.cd1, self.cd0 = z(B, h), z(B, h)
         self.scal = z(16)   # 0 d_loss 1 g_loss 2 g_adv 3 g_cls 4 l1 5 l2 6 mask_pen 7 d_real_term 8 d_fake_term 9/10 sigmoid means
+        import os
+        cdims = [self.cl[0].k] + [L.n for L in self.cl]
+        parts = K.frozen_mlp_parts(cdims, batch)
+        self.fused_frozen = os.environ.get("PCG_FROZEN_MLP", "1") != "0" and parts > 0 and self.D.fused_ok
+        self.cls_part, self.adv_part = ctx.z(max(parts, 1)), ctx.z(max(parts, 1))
         self.run = GraphStep(self._body, self._state, self.refresh, use_graph)
         self.refresh()
 
@@ -179,17 +184,26 @@ class MoonsPlan:
         K.combine([(1.0, self.scal[7:8]), (1.0, self.scal[8:9])], self.scal[0:1])
         D.flat.adam_step(self.lr_d)
         # ---- G update (:80-95)
-        out_g = D.fwd(self.xcf, self.t_oh, 1)
-        K.gan_loss(out_g, K.GAN_WASSERSTEIN, 1.0, self.scal[2:3], self.dz)
-        ddin = D.bwd(self.dz, 1, None, want_dx=True)
-        K.copy_cols(ddin, 0, self.dx_adv, 0, self.i)
-        self.cl[0].fwd(self.xcf, self.c0, K.ACT_RELU)
-        self.cl[1].fwd(self.c0, self.c1, K.ACT_RELU)
-        self.cl[2].fwd(self.c1, self.clog)
-        K.ce_loss(self.clog, self.target, self.scal[3:4], self.cdlog, wgt=lam[0])
-        self.cl[2].dgrad(self.cdlog, self.cd1, act_ref=self.c1, ref_act=K.ACT_RELU)
-        self.cl[1].dgrad(self.cd1, self.cd0, act_ref=self.c0, ref_act=K.ACT_RELU)
-        self.cl[0].dgrad(self.cd0, self.dx_cls)
+        if self.fused_frozen:
+            # the critic's score and the frozen classifier's cross-entropy with their input gradients: one launch each
+            out_g, ddin = D.input_gradient(self.xcf, self.t_oh, 1, -1.0, self.adv_part)
+            K.gan_loss(out_g, K.GAN_WASSERSTEIN, 1.0, self.scal[2:3], self.dz)
+            K.copy_cols(ddin, 0, self.dx_adv, 0, self.i)
+            K.frozen_mlp_ce_grad([L.W() for L in self.cl], [L.wT for L in self.cl], [L.b() for L in self.cl], self.xcf,
+                                 self.target, self.cls_part, self.dx_cls, wgt=lam[0], slope=0.0, logits=self.clog)
+            K.reduce_scalar(self.cls_part, self.scal[3:4], 1.0 / B)
+        else:
+            out_g = D.fwd(self.xcf, self.t_oh, 1)
+            K.gan_loss(out_g, K.GAN_WASSERSTEIN, 1.0, self.scal[2:3], self.dz)
+            ddin = D.bwd(self.dz, 1, None, want_dx=True)
+            K.copy_cols(ddin, 0, self.dx_adv, 0, self.i)
+            self.cl[0].fwd(self.xcf, self.c0, K.ACT_RELU)
+            self.cl[1].fwd(self.c0, self.c1, K.ACT_RELU)
+            self.cl[2].fwd(self.c1, self.clog)
+            K.ce_loss(self.clog, self.target, self.scal[3:4], self.cdlog, wgt=lam[0])
+            self.cl[2].dgrad(self.cdlog, self.cd1, act_ref=self.c1, ref_act=K.ACT_RELU)
+            self.cl[1].dgrad(self.cd1, self.cd0, act_ref=self.c0, ref_act=K.ACT_RELU)
+            self.cl[0].dgrad(self.cd0, self.dx_cls)
         K.rownorm_mean(self.masked, 1, self.scal[4:5], dx=self.d_l1, gscale=lam[1])
         K.rownorm_mean(self.masked, 2, self.scal[5:6], dx=self.d_l2, gscale=lam[2])
         K.combine([(1.0, self.scal[2:3]), (lam[0], self.scal[3:4]), (lam[1], self.scal[4:5]), (lam[2], self.scal[5:6]),

@@ -21,7 +21,7 @@ def grad_close(got, ref):
 
 
 @pytest.mark.parametrize("dims,slope", [([17, 256, 256, 128, 64, 4], 0.1), ([2, 32, 32, 3], 0.0), ([64, 128, 8], 0.2),
-                                        ([5, 64, 256, 32, 128, 256, 2], 0.1)])
+                                        ([5, 64, 256, 32, 128, 256, 2], 0.1), ([5, 32, 16, 16, 1], 0.2)])
 @pytest.mark.parametrize("B", [4096, 1000, 64, 5])
 def test_frozen_mlp_forward_loss_and_input_gradient(dims, slope, B):
     import pcg_b200  # noqa: F401
