@@ -420,6 +420,13 @@ int pcg_frozen_mlp_parts(int L, const int* dims, int B);
 int pcg_frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const float* const* WT, const float* const* b,
                            float slope, const float* x, const long long* target, int loss_kind, int B, float wgt,
                            float* logits, float* loss_part, float* dx, void* stream);
+/* pcg_frozen_mlp_ce_grad that also stores what the weight gradients of the SAME network need (a critic's own update,
+ * trainer.py:290-295): act_out[j] [B][dims[j + 1]] = activation of hidden layer j, grad_out[j] = gradient of the loss with
+ * respect to that layer's pre-activation (j = 0 .. L-2; host arrays of device pointers).  The gradient of the output layer's
+ * pre-activation is the caller's (wgt / B for the mean score).  dW_j = grad_out[j]^T act_out[j - 1] (pcg_linear_wgrad_small). */
+int pcg_mlp_fwd_bwd(int L, const int* dims, const float* const* W, const float* const* WT, const float* const* b, float slope,
+                    const float* x, const long long* target, int loss_kind, int B, float wgt, float* logits, float* loss_part,
+                    float* dx, float* const* act_out, float* const* grad_out, void* stream);
 /* Weight and bias gradient of a small nn.Linear (K inputs, N outputs, both <= 128) in ONE call of two launches (product over
  * up to 128 row slices, then a wide deterministic sum): dw[N][K] = dy^T x (torch layout), db[N] = column sums of dy (NULL:
  * skipped) - instead of pcg_conv_wgrad + pcg_colsum (four launches).  scratch: pcg_linear_wgrad_small_scratch(M, K, N) floats

@@ -380,6 +380,14 @@ int pcg_frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const 
   frozen_mlp_ce_grad(L, dims, W, WT, b, slope, x, target, loss_kind, B, wgt, logits, loss_part, dx, ST);
   PCG_API_END
 }
+int pcg_mlp_fwd_bwd(int L, const int* dims, const float* const* W, const float* const* WT, const float* const* b, float slope,
+                    const float* x, const long long* target, int loss_kind, int B, float wgt, float* logits, float* loss_part,
+                    float* dx, float* const* act_out, float* const* grad_out, void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(dims && W && WT && b && x && loss_part && dx && act_out && grad_out && B >= 1, "mlp_fwd_bwd: null pointer / empty batch");
+  frozen_mlp_ce_grad(L, dims, W, WT, b, slope, x, target, loss_kind, B, wgt, logits, loss_part, dx, ST, act_out, grad_out);
+  PCG_API_END
+}
 int pcg_film_layer_supported(long long M, int H) { return film_layer_supported(M, H) ? 1 : 0; }
 int pcg_film_layer_fwd(const float* x, long long M, int H, const float* W, const float* bias, const float* gamma,
                        const float* beta, float eps, float momentum, float* running_mean, float* running_var, long long* nbt,

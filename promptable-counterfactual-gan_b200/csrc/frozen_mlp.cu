@@ -31,6 +31,10 @@ struct FmArgs {
   int act_off[FM_MAX_LAYERS];  // shared-memory offsets (floats) of the transposed activations a_0 .. a_{L-2}
   int x_off, dy_off[2], panel_off, w0_off, wl_off;
   float slope;
+  // optional copies for a caller that also wants the weight gradients (a critic's own update): row-major [B][dims[j + 1]]
+  // activations a_j and pre-activation gradients g_j of the hidden layers j = 0 .. L-2 (NULL: not stored)
+  float* act_out[FM_MAX_LAYERS];
+  float* grad_out[FM_MAX_LAYERS];
 };
 
 // outT[c][r] = sum_q inT[q][r] * Wq[q][c] for the CTA's 32 rows; Wq is a row-major [Q][C] matrix (forward: the transposed
@@ -40,7 +44,8 @@ struct FmArgs {
 template <bool FWD>
 __device__ void fm_gemm(const float* __restrict__ Wq, int C, int Q, const float* __restrict__ inT,
                         const float* __restrict__ bias, const float* __restrict__ maskT, float slope,
-                        float* __restrict__ outT, float* __restrict__ panel) {
+                        float* __restrict__ outT, float* __restrict__ panel, float* __restrict__ copy, long long r0,
+                        int nrows) {
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7, half = threadIdx.x >> 8;
   // columns of this lane: half * C/2 + lane * CW + e, e < CW = C/64 (C = 32 / 16: one column, the second half - and for
   // 16 the upper lanes - idle)
@@ -124,6 +129,11 @@ __device__ void fm_gemm(const float* __restrict__ Wq, int C, int Q, const float*
       for (int i = 0; i < 4; ++i) ov[i] = mv[i] > 0.f ? acc[j][i] : acc[j][i] * slope;
     }
     *reinterpret_cast<float4*>(outT + (size_t)c * FM_ROWS + warp * 4) = o;
+    if (copy != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (warp * 4 + i < nrows) copy[(size_t)(r0 + warp * 4 + i) * C + c] = ov[i];
+    }
   }
   __syncthreads();
 }
@@ -155,7 +165,7 @@ frozen_mlp_ce_grad_kernel(FmArgs m, const float* __restrict__ x, const long long
   const float* inT = xT;
   for (int j = 0; j + 1 < L; ++j) {
     float* outT = sm + m.act_off[j];
-    fm_gemm<true>(m.WT[j], m.dims[j + 1], m.dims[j], inT, m.b[j], nullptr, m.slope, outT, panel);
+    fm_gemm<true>(m.WT[j], m.dims[j + 1], m.dims[j], inT, m.b[j], nullptr, m.slope, outT, panel, m.act_out[j], r0, nrows);
     inT = outT;
   }
   // ---- last layer (NC <= 8 classes), softmax cross-entropy, gradient of the logits
@@ -200,14 +210,17 @@ frozen_mlp_ce_grad_kernel(FmArgs m, const float* __restrict__ x, const long long
     float a = 0.f;
     for (int n = 0; n < NC; ++n) a = fmaf(s_dlogit[r][n], wls[n * H + k], a);
     const float act = inT[k * FM_ROWS + r];
-    dyT[i] = act > 0.f ? a : a * m.slope;
+    const float gv = act > 0.f ? a : a * m.slope;
+    dyT[i] = gv;
+    if (m.grad_out[L - 2] != nullptr && r < nrows) m.grad_out[L - 2][(size_t)(r0 + r) * H + k] = gv;
   }
   __syncthreads();
   int cur = 0;
   for (int j = L - 2; j >= 1; --j) {
     // g_{j-1} = (g_j W_j) * LeakyReLU'(a_{j-1}): reduction over layer j's outputs, W_j read row by row
     float* nxt = sm + m.dy_off[cur ^ 1];
-    fm_gemm<false>(m.W[j], m.dims[j], m.dims[j + 1], sm + m.dy_off[cur], nullptr, sm + m.act_off[j - 1], m.slope, nxt, panel);
+    fm_gemm<false>(m.W[j], m.dims[j], m.dims[j + 1], sm + m.dy_off[cur], nullptr, sm + m.act_off[j - 1], m.slope, nxt, panel,
+                   m.grad_out[j - 1], r0, nrows);
     cur ^= 1;
   }
   // input layer: dx[r][k] = sum_n g_0[n][r] * W_0[n][k]  (no activation in front of x); a warp: one k, 32 rows
@@ -232,7 +245,7 @@ int frozen_mlp_parts(int B) { return (B + FM_ROWS - 1) / FM_ROWS; }
 void frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const float* const* WT, const float* const* b,
                         float slope, const float* x,
                         const long long* target, int loss_kind, int B, float wgt, float* logits, float* loss_part, float* dx,
-                        cudaStream_t s) {
+                        cudaStream_t s, float* const* act_out, float* const* grad_out) {
   PCG_PROFILE("frozen_mlp", s);
   PCG_REQUIRE(frozen_mlp_supported(L, dims), "frozen_mlp: 2..6 layers, input <= 64, hidden widths in {16, 32, 64, 128, 256}, <= 8 classes");
   FmArgs m;
@@ -240,6 +253,10 @@ void frozen_mlp_ce_grad(int L, const int* dims, const float* const* W, const flo
   m.slope = slope;
   int off = 0, widest = 32;
   for (int j = 0; j <= L; ++j) m.dims[j] = dims[j];
+  for (int j = 0; j < FM_MAX_LAYERS; ++j) {
+    m.act_out[j] = (act_out != nullptr && j + 1 < L) ? act_out[j] : nullptr;
+    m.grad_out[j] = (grad_out != nullptr && j + 1 < L) ? grad_out[j] : nullptr;
+  }
   for (int j = 0; j < L; ++j) {
     m.W[j] = W[j]; m.WT[j] = WT[j]; m.b[j] = b[j];
     PCG_REQUIRE((reinterpret_cast<uintptr_t>(W[j]) & 15) == 0 && (reinterpret_cast<uintptr_t>(WT[j]) & 15) == 0,

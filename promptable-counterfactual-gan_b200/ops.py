@@ -452,6 +452,21 @@ def frozen_mlp_ce_grad(weights, weights_t, biases, x, target, loss_part, dx, wgt
                                            P(loss_part), P(dx), _s()))
 
 
+@_op("logits", "loss_part", "dx", "acts", "grads")
+def mlp_fwd_bwd(weights, weights_t, biases, x, target, loss_part, dx, acts, grads, wgt=1.0, slope=0.0, logits=None,
+                mean_output=False):
+    """``frozen_mlp_ce_grad`` that also stores the hidden activations (``acts[j]`` [B, width]) and the gradients of their
+    pre-activations (``grads[j]``) for the caller's weight gradients (pcg_mlp_fwd_bwd)."""
+    B, d0 = x.shape
+    dims = [d0] + [w.shape[0] for w in weights]
+    _chk(x, loss_part, dx, logits, *weights, *weights_t, *biases, *acts, *grads)
+    L = len(weights)
+    ptrs = lambda ts, n: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+    _lib.check(_L().pcg_mlp_fwd_bwd(L, (ctypes.c_int * (L + 1))(*dims), ptrs(weights, L), ptrs(weights_t, L), ptrs(biases, L),
+                                    _f(slope), P(x), P(target), 1 if mean_output else 0, B, _f(wgt), P(logits), P(loss_part),
+                                    P(dx), ptrs(acts, L - 1), ptrs(grads, L - 1), _s()))
+
+
 def film_layer_supported(M, H):
     return bool(_L().pcg_film_layer_supported(_ll(M), H))
 

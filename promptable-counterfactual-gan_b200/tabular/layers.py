@@ -149,6 +149,7 @@ class Critic:
         self.h = [[ctx.z(B, b) for (_, b) in dims] for _ in range(2)]
         self.dh = [[ctx.z(B, b) for (_, b) in dims] for _ in range(2)]
         self.ddin = ctx.z(B, dims[0][0])
+        self.ddin_scratch = [ctx.z(B, dims[0][0]) for _ in range(2)]
 
     def adopt(self, module):
         self.flat.adopt(module)
@@ -199,6 +200,24 @@ class Critic:
                              self.din[p], None, loss_part, self.ddin, wgt=wgt, slope=0.2, logits=self.h[p][-1],
                              mean_output=True)
         return self.h[p][-1], self.ddin
+
+    def update_pass(self, x, onehot, p, sign, garena, loss_part, dz):
+        """One pass of the critic's OWN update (forward, loss sign * mean(score), every weight gradient into ``garena``):
+        the forward / backward chain as one launch (pcg_mlp_fwd_bwd stores the activations and pre-activation gradients),
+        then the per-layer weight gradients side by side.  dz: the constant gradient of the scores, sign / B, [B,1]."""
+        xd = x.shape[1]
+        K.copy_cols(x, 0, self.din[p], 0, xd)
+        K.copy_cols(onehot, 0, self.din[p], xd, onehot.shape[1])
+        for L in self.layers:
+            L.normalise(p, True)
+        n = len(self.layers)
+        K.mlp_fwd_bwd([L.Wn[p] for L in self.layers], [L.WnT[p] for L in self.layers], [L.b() for L in self.layers],
+                      self.din[p], None, loss_part, self.ddin_scratch[p], self.h[p][:n - 1], self.dh[p][:n - 1], wgt=sign,
+                      slope=0.2, logits=self.h[p][-1], mean_output=True)
+        for i in range(n - 1, -1, -1):
+            xin = self.din[p] if i == 0 else self.h[p][i - 1]
+            self.layers[i].wgrad(xin, dz if i == n - 1 else self.dh[p][i], p, garena)
+        return self.h[p][-1]
 
     @property
     def fused_ok(self):

@@ -118,6 +118,9 @@ class MoonsPlan:
         parts = K.frozen_mlp_parts(cdims, batch)
         self.fused_frozen = os.environ.get("PCG_FROZEN_MLP", "1") != "0" and parts > 0 and self.D.fused_ok
         self.cls_part, self.adv_part = ctx.z(max(parts, 1)), ctx.z(max(parts, 1))
+        self.upd_part = [ctx.z(max(parts, 1)) for _ in range(2)]
+        self.fused_update = os.environ.get("PCG_FUSED_CRITIC_UPDATE", "1" if batch <= 1024 else "0") == "1"   # see tabular/kc.py
+        self.dzc = [torch.full((batch, 1), -1.0 / batch, device=dev), torch.full((batch, 1), 1.0 / batch, device=dev)]
         self.run = GraphStep(self._body, self._state, self.refresh, use_graph)
         self.refresh()
 
@@ -174,12 +177,18 @@ class MoonsPlan:
         K.reduce_scalar(self.rm, self.scal[6:7], 1.0 / n, absval=True, dx=self.d_rm, gscale=lam[3] / n)   # :67
         K.binary(self.d_rm, self.om, K.MUL, self.d_pen)
         # ---- D update (:72-77)
-        out_r = D.fwd(self.x, self.y_oh, 0)
-        K.gan_loss(out_r, K.GAN_WASSERSTEIN, 1.0, self.scal[7:8], self.dz_r, out_aux=self.scal[9:10])
-        D.bwd(self.dz_r, 0, D.g1)
-        out_f = D.fwd(self.xcf, self.t_oh, 1)
-        K.gan_loss(out_f, K.GAN_WASSERSTEIN, 0.0, self.scal[8:9], self.dz_f, out_aux=self.scal[10:11])
-        D.bwd(self.dz_f, 1, D.g2)
+        if self.fused_frozen and self.fused_update:
+            out_r = D.update_pass(self.x, self.y_oh, 0, -1.0, D.g1, self.upd_part[0], self.dzc[0])
+            K.gan_loss(out_r, K.GAN_WASSERSTEIN, 1.0, self.scal[7:8], self.dz_r, out_aux=self.scal[9:10])
+            out_f = D.update_pass(self.xcf, self.t_oh, 1, 1.0, D.g2, self.upd_part[1], self.dzc[1])
+            K.gan_loss(out_f, K.GAN_WASSERSTEIN, 0.0, self.scal[8:9], self.dz_f, out_aux=self.scal[10:11])
+        else:
+            out_r = D.fwd(self.x, self.y_oh, 0)
+            K.gan_loss(out_r, K.GAN_WASSERSTEIN, 1.0, self.scal[7:8], self.dz_r, out_aux=self.scal[9:10])
+            D.bwd(self.dz_r, 0, D.g1)
+            out_f = D.fwd(self.xcf, self.t_oh, 1)
+            K.gan_loss(out_f, K.GAN_WASSERSTEIN, 0.0, self.scal[8:9], self.dz_f, out_aux=self.scal[10:11])
+            D.bwd(self.dz_f, 1, D.g2)
         K.binary(D.flat.grad, D.grad2, K.ADD, D.flat.grad)
         K.combine([(1.0, self.scal[7:8]), (1.0, self.scal[8:9])], self.scal[0:1])
         D.flat.adam_step(self.lr_d)
