@@ -448,6 +448,18 @@ int pcg_film_layer_fwd(const float* x, long long M, int H, const float* W, const
                        const float* beta, float eps, float momentum, float* running_mean, float* running_var, long long* nbt,
                        float* mean, float* rstd, float* scale, float* shift, const float* fg, const float* fb,
                        const float* res, int relu, float* u, float* n, float* out, float* scratch, void* stream);
+/* A chain of n half blocks (the output of one is the input of the next: the generator's five residual blocks are ten) in
+ * n + 1 launches instead of 2 n: the BatchNorm + FiLM + activation of half k and the Linear of half k + 1 share a launch.
+ * Same results as n calls of pcg_film_layer_fwd.  res == NULL selects out = relu(f), otherwise out = res + f. */
+typedef struct pcg_film_half {
+  const float* W; const float* bias; const float* gamma; const float* beta;          /* Linear and BatchNorm parameters */
+  float* running_mean; float* running_var; long long* nbt;                            /* BatchNorm buffers (may be NULL) */
+  float* mean; float* rstd; float* scale; float* shift;                               /* saved statistics [H] */
+  const float* fg; const float* fb; const float* res;                                 /* FiLM tensors [M][H], residual */
+  float* u; float* n; float* out; float* scratch;                                     /* [M][H] each; scratch as above */
+} pcg_film_half;
+int pcg_film_chain_fwd(const float* x, long long M, int H, int n, const pcg_film_half* halves, float eps, float momentum,
+                       void* stream);
 int pcg_film_layer_bwd(const float* d_f, long long M, int H, const float* fg, const float* n, const float* u,
                        const float* mean, const float* rstd, const float* gamma, const float* W, const float* add_src,
                        const float* act_ref, int accumulate, float* dfg, float* dfb, float* du, float* dx, float* dgamma,

@@ -2,6 +2,8 @@
 // (pcg_b200/ops.py).  fp32, row-major / NHWC; see include/pcg.h for the contracts.
 #include "../../include/pcg.h"
 
+#include <vector>
+
 #include "common.cuh"
 #include "conv_auto.cuh"
 #include "conv_c1k4.cuh"
@@ -398,6 +400,21 @@ int pcg_film_layer_fwd(const float* x, long long M, int H, const float* W, const
               "film_layer_fwd: null pointer");
   film_layer_fwd(x, M, H, W, bias, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, rstd, scale, shift, fg,
                  fb, res, relu != 0, u, n, out, scratch, ST);
+  PCG_API_END
+}
+int pcg_film_chain_fwd(const float* x, long long M, int H, int n, const pcg_film_half* halves, float eps, float momentum,
+                       void* stream) {
+  PCG_API_BEGIN
+  PCG_REQUIRE(x && halves && n >= 1 && n <= 64, "film_chain_fwd: null pointer / 1..64 half blocks");
+  std::vector<FilmHalfFwd> hs(n);
+  for (int k = 0; k < n; ++k) {
+    const pcg_film_half& p = halves[k];
+    PCG_REQUIRE(p.W && p.bias && p.gamma && p.beta && p.mean && p.rstd && p.scale && p.shift && p.fg && p.fb && p.u && p.n &&
+                    p.out && p.scratch, "film_chain_fwd: null pointer in a half block");
+    hs[k] = FilmHalfFwd{p.W, p.bias, p.gamma, p.beta, p.running_mean, p.running_var, p.nbt, p.mean, p.rstd, p.scale, p.shift,
+                        p.fg, p.fb, p.res, p.res == nullptr ? 1 : 0, p.u, p.n, p.out, p.scratch};
+  }
+  film_chain_fwd(x, M, H, n, hs.data(), eps, momentum, ST);
   PCG_API_END
 }
 int pcg_film_layer_bwd(const float* d_f, long long M, int H, const float* fg, const float* n, const float* u,

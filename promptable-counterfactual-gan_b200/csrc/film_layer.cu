@@ -170,6 +170,99 @@ film_fwd_b_kernel(const float* __restrict__ u_i, const float* __restrict__ part,
   }
 }
 
+// B of half block k and A of half block k + 1 in one launch: the BatchNorm + FiLM + activation of a row tile feeds the
+// next Linear directly (both are row-local); only the batch statistics separate launches.  A chain of n half blocks is
+// n + 1 launches (A, BA x (n - 1), B) instead of 2 n.
+template <int H>
+__global__ void __launch_bounds__(FL_THREADS)
+film_fwd_ba_kernel(const float* __restrict__ u_i, const float* __restrict__ part, int nparts, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, float momentum, float* running_mean, float* running_var,
+                   long long* nbt, float* mean_o, float* rstd_o, float* scale_o, float* shift_o, const float* __restrict__ fg,
+                   const float* __restrict__ fb, const float* __restrict__ res, int relu, long long M, float* __restrict__ n_o,
+                   float* __restrict__ out, const float* __restrict__ Wn, const float* __restrict__ biasn,
+                   float* __restrict__ un_o, float* __restrict__ partn) {
+  pdl_enter();
+  constexpr int LANES = FL_THREADS / H, RPT = FL_TILE / LANES;
+  __shared__ __align__(16) float sx[FL_TILE * H];
+  __shared__ float flat[2 * FL_THREADS];
+  const int c = threadIdx.x % H, lane_row = threadIdx.x / H;
+  double ts, tq;
+  total_colsum2<H>(part, nparts, flat, c, lane_row, ts, tq);
+  const double mean = ts / (double)M;
+  double var = tq / (double)M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float a = gamma[c] * rstd;
+  const float b = beta[c] - (float)mean * a;
+  if (blockIdx.x == 0 && lane_row == 0) {
+    mean_o[c] = (float)mean;
+    rstd_o[c] = rstd;
+    scale_o[c] = a;
+    shift_o[c] = b;
+    if (running_mean != nullptr) {
+      const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+    if (c == 0 && nbt != nullptr) *nbt += 1;
+  }
+  float w[H];                          // row c of the NEXT layer's weight
+#pragma unroll
+  for (int k = 0; k < H; k += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(Wn + (size_t)c * H + k);
+    w[k] = t.x; w[k + 1] = t.y; w[k + 2] = t.z; w[k + 3] = t.w;
+  }
+  const float bcn = biasn[c];
+  float s = 0.f, q = 0.f;
+  for (long long t0 = (long long)blockIdx.x * FL_TILE; t0 < M; t0 += (long long)gridDim.x * FL_TILE) {
+    float uv[RPT], gv[RPT], bv[RPT], rv[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const long long r = t0 + lane_row + k * LANES;
+      const bool ok = r < M;
+      const size_t i = (size_t)r * H + c;
+      uv[k] = ok ? u_i[i] : 0.f;
+      gv[k] = ok ? fg[i] : 0.f;
+      bv[k] = ok ? fb[i] : 0.f;
+      rv[k] = (ok && !relu) ? res[i] : 0.f;
+    }
+    __syncthreads();                   // the previous tile's rows are no longer read
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int rl = lane_row + k * LANES;
+      const long long r = t0 + rl;
+      const float n = fmaf(uv[k], a, b);
+      const float f = fmaf(gv[k], n, bv[k]);
+      const float o = relu ? fmaxf(f, 0.f) : rv[k] + f;
+      sx[rl * H + c] = o;
+      if (r < M) {
+        const size_t i = (size_t)r * H + c;
+        n_o[i] = n;
+        out[i] = o;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int rl = lane_row + k * LANES;
+      if (t0 + rl < M) {
+        float acc = bcn;
+        const float4* xr = reinterpret_cast<const float4*>(sx + rl * H);
+#pragma unroll
+        for (int j = 0; j < H / 4; ++j) {
+          const float4 xv = xr[j];
+          acc = fmaf(xv.x, w[4 * j], acc); acc = fmaf(xv.y, w[4 * j + 1], acc);
+          acc = fmaf(xv.z, w[4 * j + 2], acc); acc = fmaf(xv.w, w[4 * j + 3], acc);
+        }
+        un_o[(size_t)(t0 + rl) * H + c] = acc;
+        s += acc;
+        q = fmaf(acc, acc, q);
+      }
+    }
+  }
+  cta_colsum2<H>(s, q, flat, partn, c, lane_row);
+}
+
 template <int H>
 __global__ void __launch_bounds__(FL_THREADS)
 film_bwd_a_kernel(const float* __restrict__ d_f, const float* __restrict__ fg, const float* __restrict__ n_i,
@@ -292,6 +385,32 @@ void film_layer_fwd(const float* x, long long M, int H, const float* W, const fl
 #undef PCG_L
   PCG_COUNT_LAUNCH();
   PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+void film_chain_fwd(const float* x, long long M, int H, int n, const FilmHalfFwd* h, float eps, float momentum, cudaStream_t s) {
+  PCG_PROFILE("film_layer", s);
+  PCG_REQUIRE(film_layer_supported(M, H) && n >= 1, "film_chain: H in {32, 64}, at least one half block");
+  for (int k = 0; k < n; ++k) {
+    PCG_REQUIRE(h[k].relu || h[k].res != nullptr, "film_chain: the residual form needs res");
+    PCG_REQUIRE((reinterpret_cast<uintptr_t>(h[k].W) & 15) == 0, "film_chain: 16-byte aligned weights");
+  }
+  PCG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "film_chain: 16-byte aligned input");
+  const int grid = fl_grid(M);
+#define PCG_L(HH)                                                                                                         \
+  launch_k(film_fwd_a_kernel<HH>, dim3(grid), dim3(FL_THREADS), 0, s, x, h[0].W, h[0].bias, M, h[0].u, h[0].part);         \
+  for (int k = 0; k + 1 < n; ++k)                                                                                         \
+    launch_k(film_fwd_ba_kernel<HH>, dim3(grid), dim3(FL_THREADS), 0, s, h[k].u, h[k].part, grid, h[k].gamma, h[k].beta,   \
+             eps, momentum, h[k].running_mean, h[k].running_var, h[k].nbt, h[k].mean, h[k].rstd, h[k].scale, h[k].shift,   \
+             h[k].fg, h[k].fb, h[k].res, h[k].relu, M, h[k].n, h[k].out, h[k + 1].W, h[k + 1].bias, h[k + 1].u,           \
+             h[k + 1].part);                                                                                              \
+  launch_k(film_fwd_b_kernel<HH>, dim3(grid), dim3(FL_THREADS), 0, s, h[n - 1].u, h[n - 1].part, grid, h[n - 1].gamma,     \
+           h[n - 1].beta, eps, momentum, h[n - 1].running_mean, h[n - 1].running_var, h[n - 1].nbt, h[n - 1].mean,        \
+           h[n - 1].rstd, h[n - 1].scale, h[n - 1].shift, h[n - 1].fg, h[n - 1].fb, h[n - 1].res, h[n - 1].relu, M,        \
+           h[n - 1].n, h[n - 1].out)
+  if (H == 32) { PCG_L(32); } else { PCG_L(64); }
+#undef PCG_L
+  for (int k = 0; k <= n; ++k) PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
 

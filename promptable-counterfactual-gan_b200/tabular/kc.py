@@ -210,6 +210,7 @@ class KcPlan:
         # primitive operators
         import os
         self.fused = os.environ.get("PCG_FILM_LAYER", "1") != "0" and K.film_layer_supported(B, h)
+        self.chain = os.environ.get("PCG_FILM_CHAIN", "1") != "0"        # forward: the ten half blocks as one chained call
         # the frozen classifier's forward + cross-entropy + input gradient as ONE launch (csrc/frozen_mlp.cu)
         self.cls_parts = K.frozen_mlp_parts([d] + [b for _, b in cdims] + [nc], B)
         self.fused_cls = os.environ.get("PCG_FROZEN_MLP", "1") != "0" and self.cls_parts > 0
@@ -279,6 +280,22 @@ class KcPlan:
         K.copy_cols(self.cond, 0, self.gin, d, self.cond_dim)
         self.fc_in.fwd(self.gin, self.h0, K.ACT_RELU)
         hcur = self.h0
+        if self.fused and training and self.chain:
+            # the ten half blocks as ONE call of eleven launches; the FiLM tensors of every block first
+            halves = []
+            for b in self.blk:
+                b["hin"] = hcur
+                b["fg"].fwd(self.cond, b["g"])
+                b["fb"].fwd(self.cond, b["b"])
+                for fc, bn, u, n, out, res in ((b["fc1"], b["bn1"], b["u1"], b["n1"], b["r1"], None),
+                                               (b["fc2"], b["bn2"], b["u2"], b["n2"], b["hout"], hcur)):
+                    halves.append((fc.W(), fc.b(), bn.flat.p(bn.name + ".weight"), bn.flat.p(bn.name + ".bias"), bn.rm, bn.rv,
+                                   bn.nbt, bn.st, b["g"], b["b"], res, u, n, out))
+                hcur = b["hout"]
+            K.film_chain_fwd(self.h0, halves)
+            self.hlast = hcur
+            self._g_heads(hcur)
+            return
         for b in self.blk:
             b["hin"] = hcur
             b["fg"].fwd(self.cond, b["g"])
@@ -298,6 +315,9 @@ class KcPlan:
             K.film_fwd(b["g"], b["n2"], b["b"], b["hout"], res=hcur)                  # h' = h + FiLM(BN2(fc2 r1))
             hcur = b["hout"]
         self.hlast = hcur
+        self._g_heads(hcur)
+
+    def _g_heads(self, hcur):
         self.fc_cont.fwd(hcur, self.contp)
         K.unary(self.contp, K.SCALE, self.cont_out, 0.1)
         for f, head in self.heads.items():

@@ -100,3 +100,43 @@ def test_kc_plan_fused_layers_match_primitive_operators(B, monkeypatch):
         for nm in ("bn1", "bn2"):
             # the running mean follows the (free-walking, see above) Linear bias: +-lr per step on either side
             assert (b0[nm].rm - b1[nm].rm).abs().max() < 5e-4 and rel(b0[nm].rv, b1[nm].rv) < 1e-4
+
+
+@pytest.mark.parametrize("M,H,n", [(4096, 32, 10), (777, 32, 3), (64, 64, 4), (300, 32, 1)])
+def test_chained_half_blocks_equal_single_calls(M, H, n):
+    """pcg_film_chain_fwd (n + 1 launches) against n calls of pcg_film_layer_fwd: same outputs, saved statistics and running
+    buffers (the two compute the same sums in the same order: bit-identical)."""
+    import pcg_b200  # noqa: F401
+    from pcg_b200 import ops as K
+    torch.manual_seed(M + H + n)
+    dev = "cuda"
+    x = torch.randn(M, H, device=dev)
+
+    def make():
+        torch.manual_seed(5)
+        hs = []
+        for k in range(n):
+            W = torch.randn(H, H, device=dev) * H ** -0.5
+            bias, gam, bet = torch.randn(H, device=dev) * 0.1, 1 + 0.1 * torch.randn(H, device=dev), 0.1 * torch.randn(H, device=dev)
+            fg, fb = 1 + 0.3 * torch.randn(M, H, device=dev), 0.3 * torch.randn(M, H, device=dev)
+            rm, rv = torch.zeros(H, device=dev), torch.ones(H, device=dev)
+            nbt = torch.zeros((), dtype=torch.int64, device=dev)
+            u, nn_, out = (torch.full((M, H), 9.0, device=dev) for _ in range(3))
+            hs.append([W, bias, gam, bet, rm, rv, nbt, K.BNState(H, dev), fg, fb, None, u, nn_, out])
+        return hs
+    a, b = make(), make()
+    # odd half blocks are residual: res = the input of the previous (relu) half block
+    cur = x
+    for k, h in enumerate(a):
+        res = None if k % 2 == 0 else (x if k == 1 else a[k - 2][13])
+        h[10] = res
+        K.film_layer_fwd(cur, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[11], h[12], h[13], res=res,
+                         relu=res is None)
+        cur = h[13]
+    for k, h in enumerate(b):
+        h[10] = None if k % 2 == 0 else (x if k == 1 else b[k - 2][13])
+    K.film_chain_fwd(x, [tuple(h) for h in b])
+    for k, (ha, hb) in enumerate(zip(a, b)):
+        for idx in (11, 12, 13, 4, 5):
+            assert torch.equal(ha[idx], hb[idx]), (k, idx)
+        assert torch.equal(ha[7].mean, hb[7].mean) and torch.equal(ha[7].rstd, hb[7].rstd) and ha[6].item() == hb[6].item() == 1
