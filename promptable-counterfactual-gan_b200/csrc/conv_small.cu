@@ -251,6 +251,13 @@ conv_few_kernel(const TIn* __restrict__ in, const bf16* __restrict__ wnk, const 
       for (int r4 = 0; r4 < 4; ++r4) {
         const int t = r4 & 1;                    // a0/a2: row rr, a1/a3: row rr + 8
         const int e0 = ks * 4 + (r4 >> 1) * 2;   // a0/a1: k pair 0, a2/a3: k pair +8
+        if (CS == 2 && sizeof(TIn) == 2) {
+          // two bf16 channels of one tap: the k pair (2q, 2q + 1) is ONE aligned 32-bit word of the NHWC input
+          const int hi = hb_[t] + kdr[e0], wi = wb_[t] + kds[e0];
+          const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+          a[ks][r4] = ok ? *reinterpret_cast<const uint32_t*>(in + base[t] + kdelta[e0]) : 0u;
+          continue;
+        }
         uint32_t bits[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
