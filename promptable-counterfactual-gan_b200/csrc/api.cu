@@ -212,7 +212,7 @@ int pcg_conv_tc64_dgrad_bnred(const void* in, int N, int H, int W, const void* w
 int pcg_conv_tc64_wgrad(const void* x, const void* dy, int N, int H, int W, float* part, float* dw, void* stream) {
   PCG_API_BEGIN
   conv_tc64_wgrad((const bf16*)x, (const bf16*)dy, N, H, W, part, (cudaStream_t)stream);
-  wgrad_reduce_tc(part, conv_tc64_grid(N, H, W), dw, (cudaStream_t)stream);
+  wgrad_reduce_tc(part, conv_tc64_grid(N, H, W), dw, (cudaStream_t)stream, conv_tc64_wgrad_swizzled());
   PCG_API_END
 }
 

@@ -1021,7 +1021,7 @@ void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* 
 // (the partials are L2-resident: 148 x 147 KB); the eight groups are then added in fixed order through shared memory.
 constexpr int WR_GROUPS = 8, WR_VEC = 32;
 __global__ void __launch_bounds__(WR_GROUPS * WR_VEC)
-wgrad_reduce_tc_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw) {
+wgrad_reduce_tc_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw, int swizzled) {
   pdl_enter();
   __shared__ float4 sm[WR_GROUPS][WR_VEC];
   const int v = threadIdx.x % WR_VEC, g = threadIdx.x / WR_VEC;
@@ -1048,8 +1048,9 @@ wgrad_reduce_tc_kernel(const float* __restrict__ part, int nparts, float* __rest
       const float4 u = sm[k][v];
       t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
-    const int idx = idx4 * 4;
-    const int co = idx & 63, ci = (idx >> 6) & 63, tap = idx >> 12;
+    // swizzled partials (conv_tc64_wgrad): 16-byte chunk c of row (tap, ci) is stored at chunk c ^ (ci & 15)
+    const int ci = (idx4 >> 4) & 63, tap = idx4 >> 10;
+    const int co = ((idx4 & 15) ^ (swizzled ? (ci & 15) : 0)) * 4;
     dw[((co + 0) * 64 + ci) * 9 + tap] = t.x;
     dw[((co + 1) * 64 + ci) * 9 + tap] = t.y;
     dw[((co + 2) * 64 + ci) * 9 + tap] = t.z;
@@ -1057,9 +1058,9 @@ wgrad_reduce_tc_kernel(const float* __restrict__ part, int nparts, float* __rest
   }
 }
 
-void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream) {
+void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream, bool swizzled) {
   PCG_PROFILE("wgrad_reduce_tc", stream);
-  launch_k(wgrad_reduce_tc_kernel, dim3(9216 / WR_VEC), dim3(WR_GROUPS * WR_VEC), 0, stream, part, nparts, dw);
+  launch_k(wgrad_reduce_tc_kernel, dim3(9216 / WR_VEC), dim3(WR_GROUPS * WR_VEC), 0, stream, part, nparts, dw, swizzled ? 1 : 0);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

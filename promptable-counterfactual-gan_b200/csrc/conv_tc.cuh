@@ -86,7 +86,9 @@ void conv_tc_wgrad64(const bf16* x, const bf16* dy, int N, int H, int W, float* 
                      cudaStream_t stream);
 // dw[co][ci][3][3] (fp32, torch OIHW) = sum_cta part[cta][tap][ci][co];  db[co] = sum_p dy[p][co]
 // is produced by the caller's BN/bias kernels, not here.
-void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream);
+// swizzled: the partials come from conv_tc64_wgrad's staged write-out (conv_tc64_wgrad_swizzled())
+void wgrad_reduce_tc(const float* part, int nparts, float* dw, cudaStream_t stream, bool swizzled = false);
+bool conv_tc64_wgrad_swizzled();
 
 // General tensor-core wgrad (3x3, pad 1, stride 1|2, Cin % 64 == 0, Cout % 64 == 0):
 //   part[z][co][(tap, ci)] fp32, z < conv_tc_wgrad_general_splits(...); reduce with wgrad_reduce_generic().

@@ -21,6 +21,7 @@
 //                            variant bit 1024 = the two-taps-per-accumulator scheme)
 // Variant bits (pcg_conv_tc64_set_variant / PCG_TC64_VARIANT): 1 descriptor base-offset policy (bring-up), 2 / 4 / 8 /
 // 16 / 64 / 128 timing experiments (results invalid), 256 one-class forward kernel, 1024 original weight-gradient scheme.
+// 2048: weight-gradient partials written by direct stores (linear layout) instead of staged bulk copies.
 #include <cstdlib>
 
 #include "conv_tc.cuh"
@@ -563,11 +564,47 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 // plus the two wrap-arounds, class 0 one row further down -> co 3 (r = 2) and class 3 one row further up -> co 0 (r = 0), N=64.
 // 72 MMAs per 512 positions instead of 144.  The epilogue is the one above, run once per output class.
 // ------------------------------------------------------------------------------------------
+// Epilogue specialisations (SPEC >= 0): the epilogue of the fused launches is bound by instruction issue (sixteen warps
+// x ~250 instructions per sub-tile against the ~4000 cycles of a super-tile's MMAs), and a good part of those
+// instructions only test launch-uniform switches.  The launches the MNIST step makes fix the switches at compile time;
+// SPEC < 0 reads every switch from the parameters (any other caller, every experiment variant).  A fixed SPEC implies:
+// act == NONE, no operand read from global memory, no last-CTA finalisation, no experiment variant.
+enum : int { SP_BIAS = 1, SP_BNBWD = 2, SP_DUAL = 4, SP_BN_NOACT = 8, SP_EXTRA = 16, SP_STATS = 32,
+              SP_F2 = 64 };    // SP_F2: the sums and the residual add as packed two-lane fp32 instructions (FADD2 / FFMA2:
+                               // the same round-to-nearest results, half the issue slots)
+constexpr int SPEC_FWD_STATS = SP_BIAS | SP_STATS;                                    // conv + bias, BatchNorm statistics
+constexpr int SPEC_BN1 = SP_BNBWD | SP_EXTRA | SP_STATS;                              // data gradient + BN1 backward sums
+constexpr int SPEC_BN2 = SP_BNBWD | SP_BN_NOACT | SP_EXTRA | SP_STATS;                // ... + BN2 backward sums
+constexpr int SPEC_BN2_DUAL = SPEC_BN2 | SP_DUAL;                                     // ... and the skip gradient added
+
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(b0, b1));
+  a0 = r.x; a1 = r.y;
+}
+// (c0, c1) = (a0 * b0 + c0, a1 * b1 + c1)
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  const float2 r = __ffma2_rn(make_float2(a0, a1), make_float2(b0, b1), make_float2(c0, c1));
+  c0 = r.x; c1 = r.y;
+}
+
+template <int SPEC>
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmExtra,
                         const __grid_constant__ CUtensorMap tmAdd, const F64Params p) {
   pdl_launch_dependents();                        // the prologue below touches no global memory: see pdl_wait() further down
+  constexpr bool kS = SPEC >= 0;
+  const bool k_bias = kS ? (SPEC & SP_BIAS) != 0 : true;       // run-time: a missing bias is added as zeros
+  const bool k_bn_bwd = kS ? (SPEC & SP_BNBWD) != 0 : p.bn_bwd != 0;
+  const bool k_dual = kS ? (SPEC & SP_DUAL) != 0 : p.dual != 0;
+  const bool k_bn_noact = kS ? (SPEC & SP_BN_NOACT) != 0 : p.bn_act == ACT_NONE;
+  const bool k_extra = kS ? (SPEC & SP_EXTRA) != 0 : p.n_extra != 0;
+  const bool k_extra_add = kS ? false : p.extra_is_add != 0;
+  const bool k_stats = kS ? (SPEC & SP_STATS) != 0 : p.stats != nullptr;
+  const int k_act = kS ? (int)ACT_NONE : p.act;
+  const int k_variant = kS ? 0 : p.variant;
+  const bool k_fin = kS ? false : p.fin.mode != 0;
+  constexpr bool kF2 = kS && (SPEC & SP_F2) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -577,10 +614,10 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   // loaded by TMA straight into the staging slot its result will leave from - every thread reads its 32 bytes, adds,
   // and writes the result back in place - so the slot ring (three deep) replaces a second operand ring that would not
   // fit: load (afull) -> epilogue in place (sfull) -> TMA store -> read out (sempty) -> next load.
-  const int nst = p.dual ? 3 : 2;
+  const int nst = k_dual ? 3 : 2;
   uint8_t* sout = sin + p.in_stages * p.in_stage_bytes; // output staging, 2 slots (dual: 3 in-place slots)
   uint8_t* sx = sout + nst * p.out_tile_bytes;          // epilogue operand ring, 2 slots (if n_extra)
-  float* stats_smem = reinterpret_cast<float*>(sx + (p.n_extra ? 2 : 0) * p.out_tile_bytes);
+  float* stats_smem = reinterpret_cast<float*>(sx + (k_extra ? 2 : 0) * p.out_tile_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + (16 * 2 * 16 + 64 + 4 * 64) * 4);
   uint64_t* full = bars;                 // [<= 8] ring of class regions
   uint64_t* empty = bars + 8;            // [<= 8]
@@ -600,8 +637,8 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmOut);
-    if (p.n_extra) tma_prefetch_desc(&tmExtra);
-    if (p.dual) tma_prefetch_desc(&tmAdd);
+    if (k_extra) tma_prefetch_desc(&tmExtra);
+    if (k_dual) tma_prefetch_desc(&tmAdd);
     for (int s = 0; s < 8; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&tfull[s], 1); }
     mbar_init(wfull, 1);
     for (int s = 0; s < 2; ++s) {
@@ -642,7 +679,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         for (int j = 0; j < 4; ++j) {
           const int cls = j == 0 ? 1 : (j == 1 ? 0 : j);          // class order 1, 0, 2, 3 (first touches of the accumulator)
           mbar_wait(&empty[stage], phase ^ 1);
-          if (p.variant & 16) {                      // experiment: no input traffic
+          if (k_variant & 16) {                      // experiment: no input traffic
             mbar_arrive(&full[stage]);
           } else {
             mbar_expect_tx(&full[stage], box_bytes);
@@ -653,7 +690,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
     }
   } else if (warp == F_EPI_WARP0 + F_EPI_WARPS) {
-    if (lane == 0 && p.n_extra) {
+    if (lane == 0 && k_extra) {
       int sub = 0, s3 = 0;
       uint32_t s3use = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -661,7 +698,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         for (int c = 0; c < 4; ++c, ++sub) {
           const int co = c < 2 ? 1 - c : c;                        // the epilogue's class order 1, 0, 2, 3
           const int slot = sub & 1;
-          if (p.dual) {                                            // residual tile into the next free in-place slot
+          if (k_dual) {                                            // residual tile into the next free in-place slot
             mbar_wait(&sempty[s3], (s3use & 1u) ^ 1u);
             mbar_expect_tx(&afull[s3], tile_bytes);
             tma_load_5d(&tmAdd, &afull[s3], sout + s3 * p.out_tile_bytes, 0, 0, co, i0, n);
@@ -677,7 +714,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     // Store warp: the epilogue warps never meet at a CTA-wide barrier; each thread writes its 32 bytes of the staging
     // slot, fences and arrives on sfull, this thread sends the slot off and hands it back through sempty once the
     // TMA engine has read it, so the sixteen epilogue warps drift apart and hide each other's latencies.
-    if (lane == 0 && !(p.variant & 2)) {
+    if (lane == 0 && !(k_variant & 2)) {
       int sub = 0, slot = 0, prev = 0;                // slot = sub % nst, use = sub / nst
       uint32_t use = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -725,9 +762,9 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16_lohi(d_tmem, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc192, (s | k) != 0 ? 1u : 0u);
-          } else if (p.variant & 8) {                       // experiment: 12 of the 72 MMAs
+          } else if (k_variant & 8) {                       // experiment: 12 of the 72 MMAs
           } else if (j == 1) {                              // class 0: one row down -> co 3 (r = 2); same row -> co 0,1 (r = 1, 0)
-            if (!(p.variant & 4))                           // experiment bit 4: no wrap-around MMAs
+            if (!(k_variant & 4))                           // experiment bit 4: no wrap-around MMAs
 #pragma unroll
             for (int s = 0; s < 3; ++s)
 #pragma unroll
@@ -746,7 +783,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               for (int k = 0; k < 4; ++k)
                 umma_f16_lohi(d_tmem + 64, a_lo + s * 8 + 2 * k, a_hi, b_lo + s * 1536 + 2 * k, b_hi, idesc192, 1u);
           } else {                                          // class 3 (region starts one row up): one row up -> co 0 (r = 0); same row -> co 2,3
-            if (!(p.variant & 4))
+            if (!(k_variant & 4))
 #pragma unroll
             for (int s = 0; s < 3; ++s)
 #pragma unroll
@@ -781,11 +818,11 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     for (int j2 = 0; j2 < 2; ++j2) soff[j2] = (uint32_t)drow * 128u + ((uint32_t)((cq * 2 + j2) ^ (drow & 7)) << 4);
     float* bias_s = stats_smem + 16 * 2 * 16;
     float* bnc = bias_s + 64;
-    if (e == 0) {
+    if (e == 0 && k_bias) {
       bias_s[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
       bias_s[lane + 32] = p.bias ? __ldg(p.bias + lane + 32) : 0.f;
     }
-    if (e == 1 && p.bn_bwd) {
+    if (e == 1 && k_bn_bwd) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = lane + 32 * h;
@@ -800,9 +837,9 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc_s[j] = acc_q[j] = 0.f;
     int nvalid = 0;
-    const bool want_stats = p.stats != nullptr;
-    const bf16* g_add = (p.n_extra && p.extra_is_add) ? nullptr : p.add_src;
-    const bf16* g_ref = (p.n_extra && !p.extra_is_add && !p.bn_bwd) ? nullptr : p.act_ref;
+    const bool want_stats = k_stats;
+    const bf16* g_add = (kS || (k_extra && k_extra_add)) ? nullptr : p.add_src;
+    const bf16* g_ref = (kS || (k_extra && !k_extra_add && !k_bn_bwd)) ? nullptr : p.act_ref;
     const float neg = p.ref_act == ACT_LRELU ? p.ref_slope : 0.f;
     const int nidx = p.H >> 2;                      // rows per class
     int acc = 0, sub = 0, sslot = 0;                // sslot = sub % nst: staging slot
@@ -823,27 +860,32 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           tc_fence_before();
           mbar_arrive(&tempty[acc]);                // the last block is in registers: release the accumulator
         }
-        if (p.variant & 2) {                        // experiment: no epilogue work
+        if (k_variant & 2) {                        // experiment: no epilogue work
           if (++sslot == nst) { sslot = 0; ++suse; }
           continue;
         }
         float v[16];
+        if (k_bias) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + j4 * 4);
-          v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
-          v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
-          v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
-          v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + j4 * 4);
+            v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
+            v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+            v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
+            v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
-        if (p.act == ACT_LRELU) {
+        if (k_act == ACT_LRELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-        } else if (p.act == ACT_RELU) {
+        } else if (k_act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.dual) {
+        if (k_dual) {
           // the residual tile sits in the staging slot this pass will write its result to
           mbar_wait(&afull[sslot], suse & 1u);
           if (valid) {
@@ -854,13 +896,18 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                v[j2 * 8 + t * 2] += __uint_as_float(w4[t] << 16);
-                v[j2 * 8 + t * 2 + 1] += __uint_as_float(w4[t] & 0xffff0000u);
+                const int j = j2 * 8 + t * 2;
+                if constexpr (kF2) {
+                  add2(v[j], v[j + 1], __uint_as_float(w4[t] << 16), __uint_as_float(w4[t] & 0xffff0000u));
+                } else {
+                  v[j] += __uint_as_float(w4[t] << 16);
+                  v[j + 1] += __uint_as_float(w4[t] & 0xffff0000u);
+                }
               }
             }
           }
         }
-        if (p.n_extra) {
+        if (k_extra) {
           mbar_wait(&xfull[slot], (sub >> 1) & 1);
           if (valid) {
             const uint8_t* xt = sx + slot * p.out_tile_bytes;
@@ -868,9 +915,19 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             for (int j2 = 0; j2 < 2; ++j2) {
               const uint4 u = *reinterpret_cast<const uint4*>(xt + soff[j2]);
               const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-              if (p.bn_bwd && p.bn_act == ACT_NONE) {
+              if (k_bn_bwd && k_bn_noact) {
                 // no activation between the BatchNorm and this gradient (BN2 of a residual block): g = v.  The second
                 // sum is taken as sum g*y and turned into sum g*(y - mean) after the last tile (acc_q -= mean * acc_s)
+#pragma unroll
+                if constexpr (kF2) {
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const int j = j2 * 8 + t * 2;
+                    add2(acc_s[j], acc_s[j + 1], v[j], v[j + 1]);
+                    fma2(acc_q[j], acc_q[j + 1], v[j], v[j + 1], __uint_as_float(w4[t] << 16),
+                         __uint_as_float(w4[t] & 0xffff0000u));
+                  }
+                } else {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                   const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
@@ -878,7 +935,8 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                   acc_s[j] += v[j];
                   acc_q[j] = fmaf(v[j], yv, acc_q[j]);
                 }
-              } else if (p.bn_bwd) {
+                }
+              } else if (k_bn_bwd) {
                 float ca[8], cb[8];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -890,6 +948,19 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                 }
                 const float neg_bn = p.bn_act == ACT_LRELU ? p.bn_slope : 0.f;
 #pragma unroll
+                if constexpr (kF2) {
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const int j = j2 * 8 + t * 2;
+                    const float y0 = __uint_as_float(w4[t] << 16), y1 = __uint_as_float(w4[t] & 0xffff0000u);
+                    float z0 = cb[t * 2], z1 = cb[t * 2 + 1];
+                    fma2(z0, z1, y0, y1, ca[t * 2], ca[t * 2 + 1]);
+                    const float g0 = z0 > 0.f ? v[j] : v[j] * neg_bn, g1 = z1 > 0.f ? v[j + 1] : v[j + 1] * neg_bn;
+                    add2(acc_s[j], acc_s[j + 1], g0, g1);
+                    fma2(acc_q[j], acc_q[j + 1], g0, g1, y0, y1);
+                  }
+                } else {
+#pragma unroll
                 for (int t = 0; t < 8; ++t) {
                   const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
                   const int j = j2 * 8 + t;
@@ -897,11 +968,12 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                   acc_s[j] += g;
                   acc_q[j] = fmaf(g, yv, acc_q[j]);
                 }
+                }
               } else {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                   const float lo = __uint_as_float(w4[t] << 16), hi = __uint_as_float(w4[t] & 0xffff0000u);
-                  if (p.extra_is_add) {
+                  if (k_extra_add) {
                     v[j2 * 8 + t * 2] += lo;
                     v[j2 * 8 + t * 2 + 1] += hi;
                   } else {
@@ -946,7 +1018,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           }
         }
         // staging slot: last read by the TMA store issued two passes ago (dual: already owned, the residual came in it)
-        if (!p.dual) mbar_wait(&sempty[sslot], (suse & 1u) ^ 1u);
+        if (!k_dual) mbar_wait(&sempty[sslot], (suse & 1u) ^ 1u);
         if (valid) {
           uint8_t* st = sout + sslot * p.out_tile_bytes;
 #pragma unroll
@@ -958,7 +1030,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             u.w = pack2(v[j2 * 8 + 6], v[j2 * 8 + 7]);
             *reinterpret_cast<uint4*>(st + soff[j2]) = u;
           }
-          if (want_stats && !p.bn_bwd) {
+          if (want_stats && !k_bn_bwd) {
             ++nvalid;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -977,7 +1049,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
     if (want_stats) {
       const float nv = (float)nvalid;
-      if (p.bn_bwd) {
+      if (k_bn_bwd) {
         // sum g*y -> sum g*(y - mean) * rstd = sum g*xhat; both sums scaled by bn_gscale
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -1008,7 +1080,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         for (int qq = 0; qq < 4; ++qq) s += stats_smem[(((c4 * 4 + qq) * 2) + which) * 16 + l];
         p.stats[(size_t)blockIdx.x * 128 + which * 64 + col] = s;
       }
-      if (p.fin.mode != 0) {
+      if (k_fin) {
         // the last CTA to get here finishes the statistics (fixed CTA order: deterministic)
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
@@ -1033,6 +1105,23 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// The compile-time epilogue of a launch, or -1 when its switches are not one of the instantiated combinations.
+// PCG_TC64_SPEC=0 keeps every launch on the run-time epilogue (A/B switch).
+static int epilogue_spec(const F64Params& p) {
+  static const int mode = [] { const char* e = getenv("PCG_TC64_SPEC"); return e == nullptr ? 2 : atoi(e); }();
+  if (mode == 0 || (p.variant & ~(1024 | 2048)) != 0 || p.fin.mode != 0 || p.act != ACT_NONE) return -1;   // 1024, 2048: weight-gradient bits
+  if (p.add_src != nullptr || p.act_ref != nullptr) return -1;       // (dual: the host has moved add_src to the TMA map)
+  int s = 0;
+  if (p.bias != nullptr) s |= SP_BIAS;
+  if (p.stats != nullptr) s |= SP_STATS;
+  if (p.n_extra) s |= SP_EXTRA;
+  if (p.bn_bwd) s |= SP_BNBWD | (p.bn_act == ACT_NONE ? SP_BN_NOACT : 0);
+  if (p.dual) s |= SP_DUAL;
+  if (s == SPEC_FWD_STATS) return s;
+  if (s == SPEC_BN1 || s == SPEC_BN2 || s == SPEC_BN2_DUAL) return mode == 2 ? (s | SP_F2) : s;
+  return -1;
 }
 
 // The stacked kernel is the default wherever it applies (H % 4 == 0); variant bit 256 selects the one-class-per-tile
@@ -1102,7 +1191,14 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   static bool configured = false;
   if (!configured) {
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_FWD_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2_DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN1 | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2 | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2_DUAL | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
   if (stacked) {
@@ -1111,7 +1207,18 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     CUtensorMap tmOut = make_tmap_nhwc_rowclass(out, N, H, W, 64, W, p.R);
     CUtensorMap tmExtra = make_tmap_nhwc_rowclass(extra != nullptr ? extra : out, N, H, W, 64, W, p.R);
     CUtensorMap tmAdd = make_tmap_nhwc_rowclass(add_tma != nullptr ? add_tma : out, N, H, W, 64, W, p.R);
-    launch_k_pdl(conv_tc64s_fprop_kernel, dim3(conv_tc64_fprop_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra,
+    auto kernel = conv_tc64s_fprop_kernel<-1>;
+    switch (epilogue_spec(p)) {
+      case SPEC_FWD_STATS: kernel = conv_tc64s_fprop_kernel<SPEC_FWD_STATS>; break;
+      case SPEC_BN1: kernel = conv_tc64s_fprop_kernel<SPEC_BN1>; break;
+      case SPEC_BN2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2>; break;
+      case SPEC_BN2_DUAL: kernel = conv_tc64s_fprop_kernel<SPEC_BN2_DUAL>; break;
+      case SPEC_BN1 | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN1 | SP_F2>; break;
+      case SPEC_BN2 | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2 | SP_F2>; break;
+      case SPEC_BN2_DUAL | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2_DUAL | SP_F2>; break;
+      default: break;
+    }
+    launch_k_pdl(kernel, dim3(conv_tc64_fprop_grid(N, H, W)), dim3(F_THREADS), total(), stream, tmX, tmW, tmOut, tmExtra,
              tmAdd, p);
     PCG_COUNT_LAUNCH();
     PCG_LAUNCH_CHECK();
@@ -1254,7 +1361,49 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     mbar_wait(done, 0);
     tc_fence_after();
     float* my = part + (size_t)blockIdx.x * 9 * 64 * 64;
-    if ((variant & 1024) == 0) {
+    if ((variant & (1024 | 2048)) == 0) {
+      // Default write-out.  A thread owns one accumulator row (tap, ci) = 256 contiguous bytes of the partial, so direct
+      // stores touch 32 different lines per warp instruction (~9,200 LSU transactions per CTA, ~4.7 us at the end of
+      // every launch).  Instead each warp stages its 32 rows of a tap (8 KB, contiguous in the partial) in the idle
+      // operand ring - 16-byte chunk c of row ci at chunk c ^ (ci & 15), which keeps the staging stores free of bank
+      // conflicts - and one bulk copy per warp and tap sends them off.  The partial therefore carries that chunk
+      // swizzle inside every 256-byte row; wgrad_reduce_tc(..., swizzled = true) undoes it when it writes dW.
+      uint8_t* stage = smem + (size_t)(warp - 2) * 5 * 8192;           // every MMA has completed: the ring is idle
+      const int ci = row & 63, hi = row >> 6;
+      int it = 0;
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+#pragma unroll 1
+        for (int jb = 0; jb < (a == 0 ? 3 : 2); ++jb, ++it) {
+          const int sc = a == 0 ? 2 - jb : hi + (jb == 0 ? 2 : 0);       // as below
+          const bool live = sc < 3;                                      // warp-uniform (hi is)
+          const int tap = (a == 0 ? hi : 2) * 3 + sc;
+          uint8_t* st = stage + it * 8192;
+#pragma unroll
+          for (int chunk = 0; chunk < 2; ++chunk) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + a * 192 + jb * 64 + chunk * 32, v);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<uint4*>(st + lane * 256 + (((chunk * 8 + j4) ^ (lane & 15)) << 4)) =
+                    make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            }
+          }
+          if (live) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) bulk_store(my + ((size_t)tap * 64 + (ci & 32)) * 64, st, 8192);
+          }
+        }
+      }
+      if (lane == 0) {
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
+      __syncwarp();
+    } else if ((variant & 1024) == 0) {
 #pragma unroll 1
       for (int a = 0; a < 2; ++a) {
         const int ci = row & 63, hi = row >> 6;
@@ -1306,6 +1455,9 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+// layout of the partials the kernel writes under the current variant (see the write-out above)
+bool conv_tc64_wgrad_swizzled() { return (g_variant & (1024 | 2048)) == 0; }
 
 void conv_tc64_wgrad(const bf16* x, const bf16* dy, int N, int H, int W, float* part, cudaStream_t stream) {
   PCG_PROFILE("conv_tc64_wgrad", stream);

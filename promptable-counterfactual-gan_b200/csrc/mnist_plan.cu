@@ -616,7 +616,7 @@ struct MnistPlan : PlanBase {
       }
       if (L.tc_wgrad && L.tc64) {
         conv_tc64_wgrad(in, dout, g.N, g.H, g.W, tc_part, s);
-        wgrad_reduce_tc(tc_part, conv_tc64_grid(g.N, g.H, g.W), L.dw, s);
+        wgrad_reduce_tc(tc_part, conv_tc64_grid(g.N, g.H, g.W), L.dw, s, conv_tc64_wgrad_swizzled());
         return;
       }
       if (L.tc_wgrad_gen) {

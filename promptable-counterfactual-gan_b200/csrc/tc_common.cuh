@@ -98,6 +98,11 @@ __device__ __forceinline__ void tma_store_5d(const void* desc, const void* src, 
       "r"(smem_u32(src)), "r"(c), "r"(w), "r"(k), "r"(h), "r"(n)
       : "memory");
 }
+// contiguous shared -> global copy by the TMA engine (no tensor map); `bytes` a multiple of 16, both sides 16-byte aligned
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // waits until at most N of this thread's bulk groups are still READING shared memory / are incomplete
 template <int N>

@@ -151,10 +151,11 @@ def test_stacked_and_one_class_kernels_agree():
     assert (outs[0] != outs[1]).float().mean().item() < 0.05
 
 
-@pytest.mark.parametrize("variant", [0, 1024])
+@pytest.mark.parametrize("variant", [0, 1024, 2048])
 @pytest.mark.parametrize("N,HW", [(3, 28), (8, 28), (301, 28), (5, 14), (5, 12)])
 def test_wgrad(N, HW, variant):
-    """variant 0: shifted views on both operands (16 MMAs per tile); 1024: two taps per accumulator (40 MMAs)."""
+    """variant 0: shifted views on both operands (16 MMAs per tile), partials staged in shared memory and sent off by
+    bulk copies (chunk-swizzled rows); 2048: the same MMAs, partials by direct stores; 1024: two taps per accumulator."""
     L, P, st, check = _env()
     L.pcg_conv_tc64_set_variant(variant)
     torch.manual_seed(N)
@@ -170,3 +171,24 @@ def test_wgrad(N, HW, variant):
     (gw,) = torch.autograd.grad(yy, wz, nchw(dyn))
     L.pcg_conv_tc64_set_variant(0)
     assert rel(dw, gw) < 2e-3
+
+
+@pytest.mark.parametrize("N,HW", [(8, 28), (301, 28), (5, 12)])
+def test_wgrad_staged_writeout_is_bit_identical(N, HW):
+    """The staged, chunk-swizzled write-out only changes where a partial sum is stored: dW must not change by a bit."""
+    L, P, st, check = _env()
+    torch.manual_seed(N + 1)
+    xn = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda"))
+    dyn = nhwc_bf16(torch.randn(N, 64, HW, HW, device="cuda") * 0.1)
+    grid = L.pcg_conv_tc64_grid(N, HW, HW)
+    outs = []
+    for variant in (0, 2048):
+        L.pcg_conv_tc64_set_variant(variant)
+        part = torch.full((grid, 9 * 64 * 64), float("nan"), device="cuda")
+        dw = torch.zeros(64, 64, 3, 3, device="cuda")
+        check(L.pcg_conv_tc64_wgrad(P(xn), P(dyn), N, HW, HW, P(part), P(dw), st))
+        torch.cuda.synchronize()
+        assert torch.isfinite(part).all()          # every element of every partial is written
+        outs.append(dw)
+    L.pcg_conv_tc64_set_variant(0)
+    assert torch.equal(outs[0], outs[1])
