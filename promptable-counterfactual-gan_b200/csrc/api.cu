@@ -26,6 +26,18 @@ static int env_pdl_edges() {
   return e ? (atoi(e) != 0) : 1;      // on by default: only the tcgen05 64->64 kernels, whose prologue runs before their wait
 }
 int g_pdl_edges = env_pdl_edges();
+static int env_pdl_small() {
+  const char* e = getenv("PCG_PDL_SMALL");
+  return e ? atoi(e) : 0;
+}
+int g_pdl_small = env_pdl_small();
+static int env_l2_hints() {
+  const char* e = getenv("PCG_L2_HINTS");
+  // all five on: MNIST step 2.84-2.87 -> 2.81 ms with bits 1 | 2 | 4, 2.73 -> 2.70 ms with 8 | 16 added, interleaved on
+  // one box each (profiles/exp_l2_hints_r2i.txt)
+  return e ? atoi(e) : 31;
+}
+int g_l2_hints = env_l2_hints();
 const char* g_prof_tag = nullptr;
 struct ProfRec { std::string name; cudaEvent_t e0, e1; };
 static std::vector<ProfRec> g_prof;

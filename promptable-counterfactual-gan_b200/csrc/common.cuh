@@ -92,6 +92,22 @@ inline void launch_k_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
   PCG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 
+// Experiment switch PCG_PDL_SMALL (default 0): 1 = the statistics-finalize kernels, 2 = also the BatchNorm apply kernels
+// are launched with the programmatic attribute, so that their launch latency overlaps the producer they wait for.
+extern int g_pdl_small;
+template <typename... KArgs, typename... Args>
+inline void launch_k_small(int level, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                           Args&&... args) {
+  if (g_pdl_small >= level) launch_k_pdl(kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+  else launch_k(kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+}
+
+// L2 eviction hints (PCG_L2_HINTS bit mask, experiment): 1 = the 64->64 weight gradient streams both operands with
+// evict_first (their last use), 2 = bn_bwd_apply reads with streaming loads (last use of both inputs), 4 = the skip
+// operand of a fused data gradient with evict_first, 8 = the forward BatchNorm apply kernels read with streaming loads,
+// 16 = the 64->64 forward convolution (with statistics) loads its input with evict_first.
+extern int g_l2_hints;
+
 // Number of SMs of the current device (cached).
 int sm_count();
 

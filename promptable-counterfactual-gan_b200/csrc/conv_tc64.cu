@@ -70,6 +70,8 @@ struct F64Params {
   float* stats;
   StatsFinalize fin;
   int variant;
+  int add_evict_first;                           // dual: the skip operand is read for the last time (PCG_L2_HINTS bit 4)
+  int in_evict_first;                            // forward + statistics: the input is not read again soon (bit 16)
 };
 
 // Runs in the epilogue warps (512 threads, named barrier 1) of the last CTA to finish: see StatsFinalize.
@@ -673,6 +675,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         tma_load_2d(&tmW, wfull, sw + ((tap % 3) * 3 + (2 - tap / 3)) * 8192, tap * 64, 0);
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t in_pol = l2_evict_first_policy();
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img, i0 = (tile % p.tiles_per_img) * p.R;
 #pragma unroll
@@ -683,6 +686,9 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             mbar_arrive(&full[stage]);
           } else {
             mbar_expect_tx(&full[stage], box_bytes);
+            if (p.in_evict_first)
+              tma_load_5d_hint(&tmX, &full[stage], sin + stage * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n, in_pol);
+            else
             tma_load_5d(&tmX, &full[stage], sin + stage * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n);
           }
           if (++stage == p.in_stages) { stage = 0; phase ^= 1; }
@@ -701,7 +707,8 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (k_dual) {                                            // residual tile into the next free in-place slot
             mbar_wait(&sempty[s3], (s3use & 1u) ^ 1u);
             mbar_expect_tx(&afull[s3], tile_bytes);
-            tma_load_5d(&tmAdd, &afull[s3], sout + s3 * p.out_tile_bytes, 0, 0, co, i0, n);
+            if (p.add_evict_first) tma_load_5d_hint(&tmAdd, &afull[s3], sout + s3 * p.out_tile_bytes, 0, 0, co, i0, n, l2_evict_first_policy());
+            else tma_load_5d(&tmAdd, &afull[s3], sout + s3 * p.out_tile_bytes, 0, 0, co, i0, n);
             if (++s3 == 3) { s3 = 0; ++s3use; }
           }
           mbar_wait(&xempty[slot], ((sub >> 1) & 1) ^ 1);
@@ -869,10 +876,17 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + j4 * 4);
+            if constexpr (kF2) {
+              v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]); v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]);
+              v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]); v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]);
+              add2(v[j4 * 4 + 0], v[j4 * 4 + 1], b.x, b.y);
+              add2(v[j4 * 4 + 2], v[j4 * 4 + 3], b.z, b.w);
+            } else {
             v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
             v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
             v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
             v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+            }
           }
         } else {
 #pragma unroll
@@ -1032,11 +1046,20 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           }
           if (want_stats && !k_bn_bwd) {
             ++nvalid;
+            if constexpr (kF2) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float a0 = __uint_as_float(r[j]), a1 = __uint_as_float(r[j + 1]);
+                add2(acc_s[j], acc_s[j + 1], a0, a1);
+                fma2(acc_q[j], acc_q[j + 1], a0, a1, a0, a1);
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float a = __uint_as_float(r[j]);
               acc_s[j] += a;
               acc_q[j] = fmaf(a, a, acc_q[j]);
+            }
             }
           }
         }
@@ -1110,7 +1133,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 // The compile-time epilogue of a launch, or -1 when its switches are not one of the instantiated combinations.
 // PCG_TC64_SPEC=0 keeps every launch on the run-time epilogue (A/B switch).
 static int epilogue_spec(const F64Params& p) {
-  static const int mode = [] { const char* e = getenv("PCG_TC64_SPEC"); return e == nullptr ? 2 : atoi(e); }();
+  static const int mode = [] { const char* e = getenv("PCG_TC64_SPEC"); return e == nullptr ? 3 : atoi(e); }();
   if (mode == 0 || (p.variant & ~(1024 | 2048)) != 0 || p.fin.mode != 0 || p.act != ACT_NONE) return -1;   // 1024, 2048: weight-gradient bits
   if (p.add_src != nullptr || p.act_ref != nullptr) return -1;       // (dual: the host has moved add_src to the TMA map)
   int s = 0;
@@ -1119,8 +1142,8 @@ static int epilogue_spec(const F64Params& p) {
   if (p.n_extra) s |= SP_EXTRA;
   if (p.bn_bwd) s |= SP_BNBWD | (p.bn_act == ACT_NONE ? SP_BN_NOACT : 0);
   if (p.dual) s |= SP_DUAL;
-  if (s == SPEC_FWD_STATS) return s;
-  if (s == SPEC_BN1 || s == SPEC_BN2 || s == SPEC_BN2_DUAL) return mode == 2 ? (s | SP_F2) : s;
+  if (s == SPEC_FWD_STATS) return mode >= 3 ? (s | SP_F2) : s;
+  if (s == SPEC_BN1 || s == SPEC_BN2 || s == SPEC_BN2_DUAL) return mode >= 2 ? (s | SP_F2) : s;
   return -1;
 }
 
@@ -1149,7 +1172,8 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
   p.total_tiles = N * p.tiles_per_img;
   p.bias = epi.bias; p.act = epi.act; p.slope = epi.slope; p.add_src = epi.add_src;
   p.act_ref = epi.ref_act != ACT_NONE ? epi.act_ref : nullptr; p.ref_act = epi.ref_act; p.ref_slope = epi.ref_slope;
-  p.stats = epi.stats; p.variant = g_variant;
+  p.stats = epi.stats; p.variant = g_variant; p.add_evict_first = (g_l2_hints & 4) ? 1 : 0;
+  p.in_evict_first = ((g_l2_hints & 16) && epi.stats != nullptr && epi.bn_y == nullptr) ? 1 : 0;
   p.fin = epi.fin;
   PCG_REQUIRE(p.fin.mode == 0 || (epi.stats != nullptr && p.fin.counter != nullptr && p.fin.M > 0),
               "statistics finalisation needs the partial buffer, a ticket counter and the element count");
@@ -1196,6 +1220,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2_DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_FWD_STATS | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN1 | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2 | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2_DUAL | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1213,6 +1238,7 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
       case SPEC_BN1: kernel = conv_tc64s_fprop_kernel<SPEC_BN1>; break;
       case SPEC_BN2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2>; break;
       case SPEC_BN2_DUAL: kernel = conv_tc64s_fprop_kernel<SPEC_BN2_DUAL>; break;
+      case SPEC_FWD_STATS | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_FWD_STATS | SP_F2>; break;
       case SPEC_BN1 | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN1 | SP_F2>; break;
       case SPEC_BN2 | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2 | SP_F2>; break;
       case SPEC_BN2_DUAL | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2_DUAL | SP_F2>; break;
@@ -1292,12 +1318,18 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol = l2_evict_first_policy();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n = tile / tiles_per_img, h0 = (tile % tiles_per_img) * R;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], xbytes + dybytes);
+        if (variant & 4096) {                      // both operands are read for the last time (PCG_L2_HINTS bit 1)
+          tma_load_4d_hint(&tmX, &full[stage], sx + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n, pol);
+          tma_load_4d_hint(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES + DY_PAD_BYTES, 0, 0, h0, n, pol);
+        } else {
         tma_load_4d(&tmX, &full[stage], sx + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n);
         tma_load_4d(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES + DY_PAD_BYTES, 0, 0, h0, n);
+        }
         if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -1472,7 +1504,7 @@ void conv_tc64_wgrad(const bf16* x, const bf16* dy, int N, int H, int W, float* 
     configured = true;
   }
   launch_k_pdl(conv_tc64_wgrad_kernel, dim3(conv_tc64_grid(N, H, W)), dim3(G_THREADS), G_SMEM_BYTES, stream, 
-      tmX, tmDY, N, H, W, WP, R, tiles_per_img, N * tiles_per_img, g_variant, part);
+      tmX, tmDY, N, H, W, WP, R, tiles_per_img, N * tiles_per_img, g_variant | ((g_l2_hints & 1) ? 4096 : 0), part);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

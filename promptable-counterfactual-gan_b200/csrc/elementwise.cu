@@ -49,6 +49,19 @@ __device__ __forceinline__ void ldv(const bf16* p, float (&v)[8]) {
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
+// evict-first ("streaming") variant for inputs that are read for the last time; only the 8 x bf16 vector has one
+template <typename T, int V>
+__device__ __forceinline__ void ldv_cs(const T* p, float (&v)[V]) { ldv(p, v); }
+template <>
+__device__ __forceinline__ void ldv_cs<bf16, 8>(const bf16* p, float (&v)[8]) {
+  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void stv(float* p, const float (&v)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -250,7 +263,7 @@ void bn_finalize(const float* part, int nparts, long long M, int C, const float*
                  float eps, float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
                  float* rstd, float* scale, float* shift, cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  launch_k(bn_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
+  launch_k_small(1, bn_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, M, C, gamma, beta, eps, momentum, running_mean,
                                                running_var, nbt, mean, rstd, scale, shift);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -268,7 +281,8 @@ static int ew_blocks(long long n) {
 template <typename T, int V, int ACT>
 __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, long long nv, int C,
-                                                          float slope, T* __restrict__ z, bf16* __restrict__ side) {
+                                                          float slope, T* __restrict__ z, bf16* __restrict__ side,
+                                                          int stream_loads) {
   pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,8 +294,13 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
     const long long i2 = i + stride;
     const bool two = i2 < nv;
     float va[V], vb[V];
-    ldv(y + i * V, va);
-    if (two) ldv(y + i2 * V, vb);
+    if (stream_loads) {                            // PCG_L2_HINTS bit 8: y is not read again before the backward
+      ldv_cs<T, V>(y + i * V, va);
+      if (two) ldv_cs<T, V>(y + i2 * V, vb);
+    } else {
+      ldv(y + i * V, va);
+      if (two) ldv(y + i2 * V, vb);
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) va[j] = act_fwd(fmaf(va[j], a[j], b[j]), ACT, slope);
     stv(z + i * V, va);
@@ -307,7 +326,7 @@ void bn_apply_act(const T* y, const float* scale, const float* shift, long long 
                   cudaStream_t s, bf16* side) {
   PCG_PROFILE("bn_apply", s);
   PCG_REQUIRE(C % 4 == 0, "C % 4");
-#define PCG_L(V, A) launch_k(bn_apply_act_kernel<T, V, A>, dim3(ew_blocks_periodic(nv, C / V)), dim3(256), 0, s, y, scale, shift, nv, C, slope, z, side)
+#define PCG_L(V, A) launch_k_small(2, bn_apply_act_kernel<T, V, A>, dim3(ew_blocks_periodic(nv, C / V)), dim3(256), 0, s, y, scale, shift, nv, C, slope, z, side, (g_l2_hints & 8) ? 1 : 0)
 #define PCG_LA(V) { if (act == ACT_LRELU) PCG_L(V, ACT_LRELU); else if (act == ACT_RELU) PCG_L(V, ACT_RELU); else PCG_L(V, ACT_NONE); }
   if (C % 8 == 0 && wide_ok<T>(8, {y, z})) {
     const long long nv = M * C / 8;
@@ -325,7 +344,8 @@ void bn_apply_act(const T* y, const float* scale, const float* shift, long long 
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 bn_apply_residual_kernel(const T* __restrict__ y, const T* __restrict__ h, const float* __restrict__ scale,
-                         const float* __restrict__ shift, float res_scale, long long nv, int C, T* __restrict__ out) {
+                         const float* __restrict__ shift, float res_scale, long long nv, int C, T* __restrict__ out,
+                         int stream_loads) {
   pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,9 +357,15 @@ bn_apply_residual_kernel(const T* __restrict__ y, const T* __restrict__ h, const
     const long long i2 = i + stride;
     const bool two = i2 < nv;
     float va[V], ha[V], vb[V], hb[V];
-    ldv(y + i * V, va);
-    ldv(h + i * V, ha);
-    if (two) { ldv(y + i2 * V, vb); ldv(h + i2 * V, hb); }
+    if (stream_loads) {                            // PCG_L2_HINTS bit 8
+      ldv_cs<T, V>(y + i * V, va);
+      ldv_cs<T, V>(h + i * V, ha);
+      if (two) { ldv_cs<T, V>(y + i2 * V, vb); ldv_cs<T, V>(h + i2 * V, hb); }
+    } else {
+      ldv(y + i * V, va);
+      ldv(h + i * V, ha);
+      if (two) { ldv(y + i2 * V, vb); ldv(h + i2 * V, hb); }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) va[j] = ha[j] + fmaf(va[j], a[j], b[j]);
     stv(out + i * V, va);
@@ -358,10 +384,10 @@ void bn_apply_residual(const T* y, const T* h, const float* scale, const float* 
   PCG_REQUIRE(C % 4 == 0, "C % 4");
   if (C % 8 == 0 && wide_ok<T>(8, {y, h, out})) {
     const long long nv = M * C / 8;
-    launch_k(bn_apply_residual_kernel<T, 8>, dim3(ew_blocks_periodic(nv, C / 8)), dim3(256), 0, s, y, h, scale, shift, res_scale, nv, C, out);
+    launch_k_small(2, bn_apply_residual_kernel<T, 8>, dim3(ew_blocks_periodic(nv, C / 8)), dim3(256), 0, s, y, h, scale, shift, res_scale, nv, C, out, (g_l2_hints & 8) ? 1 : 0);
   } else {
     const long long nv = M * C / 4;
-    launch_k(bn_apply_residual_kernel<T, 4>, dim3(ew_blocks_periodic(nv, C / 4)), dim3(256), 0, s, y, h, scale, shift, res_scale, nv, C, out);
+    launch_k_small(2, bn_apply_residual_kernel<T, 4>, dim3(ew_blocks_periodic(nv, C / 4)), dim3(256), 0, s, y, h, scale, shift, res_scale, nv, C, out, (g_l2_hints & 8) ? 1 : 0);
   }
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
@@ -382,6 +408,10 @@ __device__ __forceinline__ void unpack4(const uint2& r, float (&v)[4]) {
 template <typename T>
 __device__ __forceinline__ typename Raw4<T>::type ldraw(const T* p) {
   return *reinterpret_cast<const typename Raw4<T>::type*>(p);
+}
+template <typename T>
+__device__ __forceinline__ typename Raw4<T>::type ldraw_cs(const T* p) {
+  return __ldcs(reinterpret_cast<const typename Raw4<T>::type*>(p));
 }
 template <typename T>
 __device__ __forceinline__ typename Raw4<T>::type zero_raw() {
@@ -471,7 +501,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
 void bn_bwd_finalize(const float* part, int nparts, long long M, int C, float* dgamma, float* dbeta, float* c12,
                      cudaStream_t s) {
   PCG_PROFILE("bn_finalize", s);
-  launch_k(bn_bwd_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, M, C, dgamma, dbeta, c12);
+  launch_k_small(1, bn_bwd_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, M, C, dgamma, dbeta, c12);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }
@@ -483,7 +513,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ c12, float gscale, float slope, long long M, int C,
-                    T* __restrict__ dy, float* __restrict__ part_db, bf16* __restrict__ side) {
+                    T* __restrict__ dy, float* __restrict__ part_db, bf16* __restrict__ side, int stream_loads) {
   pdl_enter();
   const int lpr = C >> 2, rpp = 256 / lpr;
   const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
@@ -505,8 +535,13 @@ bn_bwd_apply_kernel(const T* __restrict__ dsrc, const T* __restrict__ y, const f
     for (int u = 0; u < BNB_UN; ++u) {
       const long long rr = r + u * rpp;
       const bool ok = rr < sl.end;
-      rd[u] = ok ? ldraw<T>(dsrc + rr * C + cg * 4) : zero_raw<T>();
-      rv[u] = ok ? ldraw<T>(y + rr * C + cg * 4) : zero_raw<T>();
+      if (stream_loads) {                          // last use of both inputs: evict-first loads (PCG_L2_HINTS bit 2)
+        rd[u] = ok ? ldraw_cs<T>(dsrc + rr * C + cg * 4) : zero_raw<T>();
+        rv[u] = ok ? ldraw_cs<T>(y + rr * C + cg * 4) : zero_raw<T>();
+      } else {
+        rd[u] = ok ? ldraw<T>(dsrc + rr * C + cg * 4) : zero_raw<T>();
+        rv[u] = ok ? ldraw<T>(y + rr * C + cg * 4) : zero_raw<T>();
+      }
     }
 #pragma unroll
     for (int u = 0; u < BNB_UN; ++u) {
@@ -538,7 +573,7 @@ void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rst
   PCG_PROFILE("bn_bwd_apply", s);
   (void)gamma;
   check_colshape(C);
-#define PCG_L(A) launch_k(bn_bwd_apply_kernel<T, A>, dim3(STAT_PARTS), dim3(256), 0, s, dsrc, y, mean, rstd, scale, shift, c12, gscale, slope, M, C, dy, part_db, side)
+#define PCG_L(A) launch_k_small(2, bn_bwd_apply_kernel<T, A>, dim3(STAT_PARTS), dim3(256), 0, s, dsrc, y, mean, rstd, scale, shift, c12, gscale, slope, M, C, dy, part_db, side, (g_l2_hints & 2) ? 1 : 0)
   if (act == ACT_LRELU) PCG_L(ACT_LRELU);
   else if (act == ACT_RELU) PCG_L(ACT_RELU);
   else PCG_L(ACT_NONE);
@@ -557,7 +592,25 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ part, int npart
 }
 void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s) {
   PCG_PROFILE("small", s);
-  launch_k(colsum_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, stride, C, out);
+  launch_k_small(1, colsum_finalize_kernel, dim3(C), dim3(FIN_THREADS), 0, s, part, nparts, stride, C, out);
+  PCG_COUNT_LAUNCH();
+  PCG_LAUNCH_CHECK();
+}
+
+// Several layers' column sums in one launch: slot k's partials are part + k * nparts * C (row stride C), its result goes
+// to outs.p[k].  Same fixed-order sum as colsum_finalize, so the results are bit-identical to one launch per layer.
+__global__ void colsum_finalize_multi_kernel(const float* __restrict__ part, int nparts, int C, ColsumOuts outs) {
+  pdl_enter();
+  const int c = blockIdx.x, k = blockIdx.y;
+  const int cols[1] = {c};
+  double sums[1];
+  block_colsum<1>(part + (size_t)k * nparts * C, nparts, (size_t)C, cols, sums);
+  if (threadIdx.x == 0) outs.p[k][c] = (float)sums[0];
+}
+void colsum_finalize_multi(const float* part, int nparts, int C, const ColsumOuts& outs, int nslots, cudaStream_t s) {
+  PCG_PROFILE("small", s);
+  PCG_REQUIRE(nslots >= 1 && nslots <= ColsumOuts::MAX, "colsum_finalize_multi: 1..16 slots per launch");
+  launch_k(colsum_finalize_multi_kernel, dim3(C, nslots), dim3(FIN_THREADS), 0, s, part, nparts, C, outs);
   PCG_COUNT_LAUNCH();
   PCG_LAUNCH_CHECK();
 }

@@ -41,6 +41,8 @@ void bn_bwd_apply(const T* dsrc, const T* y, const float* mean, const float* rst
                   long long M, int C, T* dy, float* part_db, cudaStream_t s, bf16* side = nullptr);
 // out[C] = sum over `nparts` rows of part[.][stride] (first C columns), fixed order, fp64 accumulate.
 void colsum_finalize(const float* part, int nparts, int stride, int C, float* out, cudaStream_t s);
+struct ColsumOuts { static constexpr int MAX = 16; float* p[MAX]; };
+void colsum_finalize_multi(const float* part, int nparts, int C, const ColsumOuts& outs, int nslots, cudaStream_t s);
 // part[STAT_PARTS][C] = column sums of a[M][C]
 template <typename T>
 void colsum_partial(const T* a, long long M, int C, float* part, cudaStream_t s);

@@ -269,6 +269,10 @@ struct MnistPlan : PlanBase {
   float *clogits, *cdlogits, *dxc;
   T *cdf1, *cd3, *cd2, *cd1;
   // scratch
+  float *stat_part3 = nullptr;                // partial rows of the bias gradient that runs on the weight-gradient stream
+  float *stat_db = nullptr;                   // [2 * nres][STAT_PARTS][ch]: conv-bias gradient partials of the residual blocks
+  bool batch_db = false;                      // PCG_BATCH_DB bit 0: one finalize launch for all of them at the end of the backward
+  bool side_mid_db = false;                   // PCG_BATCH_DB bit 1: conv_mid's bias gradient on the weight-gradient stream
   float *stat_part, *stat_part2, *stat_bn2 = nullptr, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp, *small_part;
   bool fuse_bn2_reduce = true, fuse_finalize = false, defer_c_bwd = false;
   unsigned int* fin_counter = nullptr;
@@ -464,6 +468,14 @@ struct MnistPlan : PlanBase {
     const int maxC = ch > 256 ? ch : 256;
     stat_part = alloc<float>((size_t)STAT_PARTS * 2 * maxC);
     stat_part2 = alloc<float>((size_t)STAT_PARTS * 2 * maxC);
+    {
+      const char* e = getenv("PCG_BATCH_DB");
+      const int mode = e ? atoi(e) : 0;            // default off: measured slower; bit 0 / bit 1
+      batch_db = (mode & 1) != 0 && 2 * nres <= ColsumOuts::MAX;
+      side_mid_db = (mode & 2) != 0;
+      if (batch_db) stat_db = alloc<float>((size_t)2 * nres * STAT_PARTS * ch);
+      if (side_mid_db) stat_part3 = alloc<float>((size_t)STAT_PARTS * maxC);
+    }
     c12 = alloc<float>(2 * maxC);
     wg_scratch = alloc<float>(wg_scratch_elems);
     PCG_REQUIRE(sm_count() <= STAT_PARTS, "more SMs than partial-row slots (STAT_PARTS)");
@@ -633,9 +645,10 @@ struct MnistPlan : PlanBase {
     }
     conv_wgrad_generic<TIn, TDy>(in, dout, g, wg_scratch, L.dw, s);
   }
-  void bias_grad(const T* dy, long long M, int C, float* db, cudaStream_t s) {
-    colsum_partial<T>(dy, M, C, stat_part2, s);
-    colsum_finalize(stat_part2, STAT_PARTS, C, C, db, s);
+  void bias_grad(const T* dy, long long M, int C, float* db, cudaStream_t s, float* part = nullptr) {
+    if (part == nullptr) part = stat_part2;
+    colsum_partial<T>(dy, M, C, part, s);
+    colsum_finalize(part, STAT_PARTS, C, C, db, s);
   }
 
   PackTable pack_g, pack_d, pack_c;
@@ -838,18 +851,32 @@ struct MnistPlan : PlanBase {
 
   void step_d_grads(const pcg_mnist_inputs& in, float* scal, cudaStream_t s) override {
     cudaStream_t side_w = wstream(s), side_c = cstream(s);
+    // The real half of the discriminator's input and the label vector need nothing from the generator: they are
+    // assembled on side_c beside the generator forward instead of between it and the discriminator forward.
+    auto d_real_inputs = [&](cudaStream_t c) {
+      d_input<T>(in.x, d_embed, in.y, B, 784, a0, c);
+      PCG_CHECK_CUDA(cudaMemcpyAsync(labels2, in.y, B * sizeof(long long), cudaMemcpyDeviceToDevice, c));
+      PCG_CHECK_CUDA(cudaMemcpyAsync(labels2 + B, in.target, B * sizeof(long long), cudaMemcpyDeviceToDevice, c));
+    };
+    cudaEvent_t pre = nullptr;
+    if (side_c != s) {
+      after(s, side_c);
+      d_real_inputs(side_c);
+      pre = ev_pool[ev_next++ % ev_pool.size()];
+      PCG_CHECK_CUDA(cudaEventRecord(pre, side_c));
+    }
     g_fwd(in.x, in.target, in.mask, true, s);
     after(s, side_c);
+    l1_finalize(l1_part, STAT_PARTS, 1.f / (float)MG, scal + PCG_S_REG_L1, side_c);   // writes REG_L1, MASK_PEN
     c_branch(in, scal, side_c);
-    l1_finalize(l1_part, STAT_PARTS, 1.f / (float)MG, scal + PCG_S_REG_L1, s);   // writes REG_L1, MASK_PEN
-    d_input<T>(in.x, d_embed, in.y, B, 784, a0, s);
+    if (pre != nullptr) PCG_CHECK_CUDA(cudaStreamWaitEvent(s, pre, 0));
+    else d_real_inputs(s);
     d_input<T>(x_cf, d_embed, in.target, B, 784, a0 + (size_t)MG * 2, s);
-    PCG_CHECK_CUDA(cudaMemcpyAsync(labels2, in.y, B * sizeof(long long), cudaMemcpyDeviceToDevice, s));
-    PCG_CHECK_CUDA(cudaMemcpyAsync(labels2 + B, in.target, B * sizeof(long long), cudaMemcpyDeviceToDevice, s));
     d_fwd(2 * B, s);
     bce_logits(dlogits_d, B, 2, 1.f, 0.f, 1.f, 1.f, scal + PCG_S_D_LOSS_REAL, scal + PCG_S_D_REAL_P, ddlogit, s);
+    after(s, side_w);                              // the loss scalar is off the gradient chain
     g_loss_combine(scal + PCG_S_D_LOSS_REAL, scal + PCG_S_D_LOSS_FAKE, scal + PCG_S_D_LOSS_REAL,
-                   scal + PCG_S_D_LOSS_REAL, 1.f, 1.f, 0.f, 0.f, scal + PCG_S_D_LOSS, s);
+                   scal + PCG_S_D_LOSS_REAL, 1.f, 1.f, 0.f, 0.f, scal + PCG_S_D_LOSS, side_w);
     d_bwd(2 * B, true, 1, s);
     embed_grad<float>(dxd, 1, 0, labels2, 2 * B, 784, 10, d_dembed, s);
     after(side_w, s);
@@ -921,21 +948,23 @@ struct MnistPlan : PlanBase {
     d_fwd(B, s);
     bce_logits(dlogits_d, B, 1, 1.f, 1.f, cfg.lambda_adv, cfg.lambda_adv, scal + PCG_S_G_ADV, scal_tmp, ddlogit, s);
     d_bwd(B, cfg.pollute_d_grads != 0, 0, s);
-    g_loss_combine(scal + PCG_S_G_ADV, scal + PCG_S_G_CLS, scal + PCG_S_REG_L1, scal + PCG_S_MASK_PEN, cfg.lambda_adv,
-                   cfg.lambda_cls, cfg.lambda_reg, cfg.lambda_mask, scal + PCG_S_G_LOSS, s);
     // --- through clamp / mask / scaling (trainer.py:97,99,119; generator.py:80-82)
     residual_head_bwd<T>(dxd, 1, dxc, raw, in.x, in.mask, cfg.residual_scaling, cfg.lambda_reg, cfg.lambda_mask, MG,
                          g_c, s);
     // --- generator backward
     // weight gradients go to side_w (see d_bwd); every dY they read has its own buffer
     after(s, side_w);
+    g_loss_combine(scal + PCG_S_G_ADV, scal + PCG_S_G_CLS, scal + PCG_S_REG_L1, scal + PCG_S_MASK_PEN, cfg.lambda_adv,
+                   cfg.lambda_cls, cfg.lambda_reg, cfg.lambda_mask, scal + PCG_S_G_LOSS, side_w);   // off the gradient chain
     wgrad<T, T>(g_out, hm, g_c, side_w);
     if (!g_out.to1_wgrad) bias_grad(g_c, MG, 1, g_out.db, s);
     {
       GenEpilogue<T> e; e.act_ref = hm; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f;
       dgrad<T, T>(g_out, g_c, e, g_hm, s);
     }
-    bias_grad(g_hm, MG, ch, g_mid.db, s);
+    // conv_mid's bias gradient (a full read of g_hm) is needed by the optimizer only; side_mid_db runs it on the
+    // weight-gradient stream, with its own partial rows (experiment switch)
+    if (!side_mid_db) bias_grad(g_hm, MG, ch, g_mid.db, s);
     dh = dhA;
     dh_other = dhB;
     // The reduction pass of BN2's backward (sum g, sum g*xhat over g = 0.1*dh, generator.py:22) rides in the epilogue of
@@ -947,6 +976,7 @@ struct MnistPlan : PlanBase {
       dgrad<T, T>(g_mid, g_hm, e, dh, s);
     }
     after(s, side_w);
+    if (side_mid_db) bias_grad(g_hm, MG, ch, g_mid.db, side_w, stat_part3);
     wgrad<T, T>(g_mid, h[nres], g_hm, side_w);
     }   // part != 2
     for (int i = i_hi; i >= i_lo; --i) {
@@ -960,9 +990,11 @@ struct MnistPlan : PlanBase {
         bn_bwd_partial<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, 0.1f, ACT_NONE, 0.f, MG, ch, stat_part, s);
         bn_bwd_finalize(stat_part, STAT_PARTS, MG, ch, q2.dgamma, q2.dbeta, c12, s);
       }
+      // conv-bias gradients: nothing reads them before the optimizer; with batch_db every layer keeps its own partial
+      // rows and ONE launch sums them all after the loop (experiment switch)
       bn_bwd_apply<T>(dh, y2[i], q2.mean, q2.rstd, q2.scale, q2.shift, q2.gamma, c12, 0.1f, ACT_NONE, 0.f, MG, ch, dy2[i],
-                      stat_part2, s);
-      colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c2[i].db, s);
+                      batch_db ? stat_db + (size_t)(2 * i) * STAT_PARTS * ch : stat_part2, s);
+      if (!batch_db) colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c2[i].db, s);
       // data gradient of conv2; on the tensor-core path its epilogue also does the reduction pass of BN1's backward
       // (sum g, sum g*xhat with g = dz1 * LReLU'(BN1(y1))), which saves one full read of dz1 and y1
       int bn1_parts = 0;
@@ -1000,8 +1032,8 @@ struct MnistPlan : PlanBase {
       }
       if (!bn1_fin_done) bn_bwd_finalize(stat_part, bn1_parts, MG, ch, q1.dgamma, q1.dbeta, c12, s);
       bn_bwd_apply<T>(dz1, y1[i], q1.mean, q1.rstd, q1.scale, q1.shift, q1.gamma, c12, 1.f, ACT_LRELU, 0.2f, MG, ch,
-                      dy1[i], stat_part2, s);
-      colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c1[i].db, s);
+                      dy1[i], batch_db ? stat_db + (size_t)(2 * i + 1) * STAT_PARTS * ch : stat_part2, s);
+      if (!batch_db) colsum_finalize(stat_part2, STAT_PARTS, ch, ch, g_c1[i].db, s);
       if (i == 0 || !dgrad_bn2(g_c1[i], dy1[i], dh, i - 1, dh_other)) {
         GenEpilogue<T> e; e.add_src = dh;
         if (i == 0) { e.act_ref = h[0]; e.ref_act = ACT_LRELU; e.ref_slope = 0.2f; }
@@ -1015,6 +1047,14 @@ struct MnistPlan : PlanBase {
       // no residual block consumed h0's activation derivative: apply it here via a copy-free trick
       GenEpilogue<T> e; (void)e;
       throw Error(1, "n_resblocks == 0 is not supported by the fused backward");
+    }
+    if (batch_db && i_hi >= i_lo) {
+      ColsumOuts outs;
+      for (int i = i_lo; i <= i_hi; ++i) {
+        outs.p[2 * (i - i_lo)] = g_c2[i].db;
+        outs.p[2 * (i - i_lo) + 1] = g_c1[i].db;
+      }
+      colsum_finalize_multi(stat_db + (size_t)(2 * i_lo) * STAT_PARTS * ch, STAT_PARTS, ch, outs, 2 * (i_hi - i_lo + 1), s);
     }
     if (part == 1) {                               // the caller reduces the finished half of the gradients now
       after(side_w, s);

@@ -83,6 +83,28 @@ __device__ __forceinline__ void tma_store_4d(const void* desc, const void* src, 
       "r"(smem_u32(src)), "r"(c), "r"(w), "r"(h), "r"(n)
       : "memory");
 }
+// L2 eviction policy for operands that are read for the last time (streamed through, first to be evicted)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(const void* desc, uint64_t* bar, void* dst, int c, int w, int h, int n,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_hint(const void* desc, uint64_t* bar, void* dst, int c, int w, int k, int h,
+                                                 int n, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(k), "r"(h), "r"(n), "l"(policy)
+      : "memory");
+}
 // 5-D tiled load / store (row-class view of an NHWC tensor): coordinates (c, w, class, idx, n).
 __device__ __forceinline__ void tma_load_5d(const void* desc, uint64_t* bar, void* dst, int c, int w, int k, int h, int n) {
   asm volatile(
