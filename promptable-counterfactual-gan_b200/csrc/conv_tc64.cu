@@ -570,14 +570,18 @@ conv_tc64_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 // x ~250 instructions per sub-tile against the ~4000 cycles of a super-tile's MMAs), and a good part of those
 // instructions only test launch-uniform switches.  The launches the MNIST step makes fix the switches at compile time;
 // SPEC < 0 reads every switch from the parameters (any other caller, every experiment variant).  A fixed SPEC implies:
-// act == NONE, no operand read from global memory, no last-CTA finalisation, no experiment variant.
+// act == NONE, no operand read from global memory, no experiment variant, last-CTA finalisation only with SP_FIN.
 enum : int { SP_BIAS = 1, SP_BNBWD = 2, SP_DUAL = 4, SP_BN_NOACT = 8, SP_EXTRA = 16, SP_STATS = 32,
-              SP_F2 = 64 };    // SP_F2: the sums and the residual add as packed two-lane fp32 instructions (FADD2 / FFMA2:
+              SP_F2 = 64, SP_FIN = 128,     // SP_FIN: the last CTA finishes the statistics (StatsFinalize)
+              SP_LRELU = 256,               // act == LRELU (conv_mid, folded-BatchNorm inference)
+              SP_EXTRA_ADD = 512 };         // the TMA operand is the residual (folded-BatchNorm inference)    // SP_F2: the sums and the residual add as packed two-lane fp32 instructions (FADD2 / FFMA2:
                                // the same round-to-nearest results, half the issue slots)
 constexpr int SPEC_FWD_STATS = SP_BIAS | SP_STATS;                                    // conv + bias, BatchNorm statistics
 constexpr int SPEC_BN1 = SP_BNBWD | SP_EXTRA | SP_STATS;                              // data gradient + BN1 backward sums
 constexpr int SPEC_BN2 = SP_BNBWD | SP_BN_NOACT | SP_EXTRA | SP_STATS;                // ... + BN2 backward sums
 constexpr int SPEC_BN2_DUAL = SPEC_BN2 | SP_DUAL;                                     // ... and the skip gradient added
+constexpr int SPEC_FWD_LRELU = SP_BIAS | SP_LRELU;                                    // conv + bias + LeakyReLU
+constexpr int SPEC_FWD_ADD = SP_BIAS | SP_EXTRA | SP_EXTRA_ADD;                       // conv + bias + residual
 
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
   const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(b0, b1));
@@ -601,11 +605,11 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const bool k_dual = kS ? (SPEC & SP_DUAL) != 0 : p.dual != 0;
   const bool k_bn_noact = kS ? (SPEC & SP_BN_NOACT) != 0 : p.bn_act == ACT_NONE;
   const bool k_extra = kS ? (SPEC & SP_EXTRA) != 0 : p.n_extra != 0;
-  const bool k_extra_add = kS ? false : p.extra_is_add != 0;
+  const bool k_extra_add = kS ? (SPEC & SP_EXTRA_ADD) != 0 : p.extra_is_add != 0;
   const bool k_stats = kS ? (SPEC & SP_STATS) != 0 : p.stats != nullptr;
-  const int k_act = kS ? (int)ACT_NONE : p.act;
+  const int k_act = kS ? ((SPEC & SP_LRELU) ? (int)ACT_LRELU : (int)ACT_NONE) : p.act;
   const int k_variant = kS ? 0 : p.variant;
-  const bool k_fin = kS ? false : p.fin.mode != 0;
+  const bool k_fin = kS ? (SPEC & SP_FIN) != 0 : p.fin.mode != 0;
   constexpr bool kF2 = kS && (SPEC & SP_F2) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -1134,15 +1138,20 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 // PCG_TC64_SPEC=0 keeps every launch on the run-time epilogue (A/B switch).
 static int epilogue_spec(const F64Params& p) {
   static const int mode = [] { const char* e = getenv("PCG_TC64_SPEC"); return e == nullptr ? 3 : atoi(e); }();
-  if (mode == 0 || (p.variant & ~(1024 | 2048)) != 0 || p.fin.mode != 0 || p.act != ACT_NONE) return -1;   // 1024, 2048: weight-gradient bits
-  if (p.add_src != nullptr || p.act_ref != nullptr) return -1;       // (dual: the host has moved add_src to the TMA map)
+  if (mode == 0 || (p.variant & ~(1024 | 2048)) != 0 || p.act == ACT_RELU) return -1;   // 1024, 2048: weight-gradient bits
+  if (p.act_ref != nullptr) return -1;
+  if (p.add_src != nullptr && !(p.n_extra && p.extra_is_add)) return -1;   // (dual: the host has moved add_src to the TMA map)
   int s = 0;
+  if (p.act == ACT_LRELU) s |= SP_LRELU;
+  if (p.n_extra && p.extra_is_add) s |= SP_EXTRA_ADD;
   if (p.bias != nullptr) s |= SP_BIAS;
   if (p.stats != nullptr) s |= SP_STATS;
   if (p.n_extra) s |= SP_EXTRA;
   if (p.bn_bwd) s |= SP_BNBWD | (p.bn_act == ACT_NONE ? SP_BN_NOACT : 0);
   if (p.dual) s |= SP_DUAL;
+  if (p.fin.mode != 0) return (s == SPEC_FWD_STATS && mode >= 3) ? (s | SP_F2 | SP_FIN) : -1;
   if (s == SPEC_FWD_STATS) return mode >= 3 ? (s | SP_F2) : s;
+  if (s == SPEC_FWD_LRELU || s == SPEC_FWD_ADD) return s;
   if (s == SPEC_BN1 || s == SPEC_BN2 || s == SPEC_BN2_DUAL) return mode >= 2 ? (s | SP_F2) : s;
   return -1;
 }
@@ -1221,6 +1230,9 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2_DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_FWD_STATS | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_FWD_STATS | SP_F2 | SP_FIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_FWD_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_FWD_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN1 | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2 | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PCG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc64s_fprop_kernel<SPEC_BN2_DUAL | SP_F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1239,6 +1251,9 @@ void conv_tc64_fprop(const bf16* in, int N, int H, int W, const bf16* wpk, const
       case SPEC_BN2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2>; break;
       case SPEC_BN2_DUAL: kernel = conv_tc64s_fprop_kernel<SPEC_BN2_DUAL>; break;
       case SPEC_FWD_STATS | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_FWD_STATS | SP_F2>; break;
+      case SPEC_FWD_STATS | SP_F2 | SP_FIN: kernel = conv_tc64s_fprop_kernel<SPEC_FWD_STATS | SP_F2 | SP_FIN>; break;
+      case SPEC_FWD_LRELU: kernel = conv_tc64s_fprop_kernel<SPEC_FWD_LRELU>; break;
+      case SPEC_FWD_ADD: kernel = conv_tc64s_fprop_kernel<SPEC_FWD_ADD>; break;
       case SPEC_BN1 | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN1 | SP_F2>; break;
       case SPEC_BN2 | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2 | SP_F2>; break;
       case SPEC_BN2_DUAL | SP_F2: kernel = conv_tc64s_fprop_kernel<SPEC_BN2_DUAL | SP_F2>; break;

@@ -274,7 +274,7 @@ struct MnistPlan : PlanBase {
   bool batch_db = false;                      // PCG_BATCH_DB bit 0: one finalize launch for all of them at the end of the backward
   bool side_mid_db = false;                   // PCG_BATCH_DB bit 1: conv_mid's bias gradient on the weight-gradient stream
   float *stat_part, *stat_part2, *stat_bn2 = nullptr, *c12, *wg_scratch, *tc_part, *l1_part, *scal_tmp, *small_part;
-  bool fuse_bn2_reduce = true, fuse_finalize = false, defer_c_bwd = false;
+  bool fuse_bn2_reduce = true, fuse_finalize = false, fuse_finalize_fwd = false, defer_c_bwd = false;
   unsigned int* fin_counter = nullptr;
   size_t wg_scratch_elems = 0;
 
@@ -486,6 +486,7 @@ struct MnistPlan : PlanBase {
     {
       const char* e = getenv("PCG_FUSE_FINALIZE");  // A/B switch: 1 = the last CTA of the convolution finishes the statistics
       fuse_finalize = e && atoi(e) == 1;       // default OFF: measured slower (negative results)
+      fuse_finalize_fwd = e && (atoi(e) == 1 || atoi(e) == 2);   // 2: the forward statistics only (no weight-gradient stream there)
     }
     {
       const char* e = getenv("PCG_FUSE_BN2");      // A/B switch: 0 = separate bn_bwd_partial pass (round-1 schedule)
@@ -759,7 +760,7 @@ struct MnistPlan : PlanBase {
     // also finishes them (mean, rstd, scale, shift, running buffers), which removes a launch from the serial chain
     auto conv_bn = [&](const ConvLayer<T>& L, const T* in, T* out, const BN& q) {
       if constexpr (kBf16) {
-        if (training && L.tc_fprop && L.tc64 && fuse_finalize) {
+        if (training && L.tc_fprop && L.tc64 && fuse_finalize_fwd) {
           ProfTag _tag(L.tag_f.c_str());
           ConvEpilogue c;
           c.bias = L.b; c.stats = stat_part;

@@ -1,9 +1,5 @@
-# A/B of kernel switches on one box: interleaved bench lines (ms/step, samples/s, e2e, roofline, launches)
+# A/B of kernel switches on one box: parity first, then interleaved bench lines
 mkdir -p gpurun_out
-line() { python bench.py --steps 50 --warmup 5 --skip-cpu 2>/dev/null | tail -1 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
-k = d['kernel_detail_ms_per_step']
-print(d['ms_per_step'], d['value'], 'e2e', d['e2e']['value'], d['roofline']['frac'], 'wgrad', k.get('conv_tc64_wgrad:g.res.wgrad'), 'bnapply', k.get('bn_bwd_apply'), d['clocks']['sm_mhz'])
-"; }
-for cfg in 7 15 23 31 7 15 23 31; do echo "L2_HINTS=$cfg"; PCG_L2_HINTS=$cfg line; done
+timeout 900 python -m pytest tests/test_conv_tc64_gpu.py tests/test_mnist_step_gpu.py tests/test_mnist_eval.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -2
+for cfg in 0 3 0 3; do echo "TC64_SPEC=$cfg"; PCG_TC64_SPEC=$cfg python bench.py --workload mnist_infer --steps 100 --warmup 10 2>/dev/null | tail -1 | cut -c1-260; done
+python bench.py --steps 50 --warmup 5 --skip-cpu 2>/dev/null | tail -1 | cut -c1-200
