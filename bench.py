@@ -389,8 +389,9 @@ def run_native(args):
             tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tp):                  # dram bytes (read + write) per launch from the committed ncu capture
                 traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
-            # the 6 data-gradient launches whose epilogue also does a BatchNorm-backward reduction are epilogue-paced;
-            # the other 20 (13 forward, 7 data gradient) are the plain convolution
+            # the 12 data-gradient launches whose epilogue also does a BatchNorm-backward reduction move two more
+            # operand tiles per sub-tile through shared memory; the other 14 (13 forward, 1 data gradient) are the plain
+            # convolution
             plain = [v for n_, v in detail.items() if n_ in ("conv_tc64_fprop:g.res.fprop", "conv_tc64_fprop:g.res.dgrad")]
             plain_ms = sum(v["ms"] for v in plain)
             plain_n = sum(v["launches"] for v in plain)
