@@ -693,7 +693,7 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             if (p.in_evict_first)
               tma_load_5d_hint(&tmX, &full[stage], sin + stage * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n, in_pol);
             else
-            tma_load_5d(&tmX, &full[stage], sin + stage * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n);
+              tma_load_5d(&tmX, &full[stage], sin + stage * p.in_stage_bytes, 0, -1, cls, cls == 3 ? i0 - 1 : i0, n);
           }
           if (++stage == p.in_stages) { stage = 0; phase ^= 1; }
         }
@@ -886,10 +886,10 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               add2(v[j4 * 4 + 0], v[j4 * 4 + 1], b.x, b.y);
               add2(v[j4 * 4 + 2], v[j4 * 4 + 3], b.z, b.w);
             } else {
-            v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
-            v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
-            v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
-            v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+              v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x;
+              v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+              v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z;
+              v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
             }
           }
         } else {
@@ -936,7 +936,6 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               if (k_bn_bwd && k_bn_noact) {
                 // no activation between the BatchNorm and this gradient (BN2 of a residual block): g = v.  The second
                 // sum is taken as sum g*y and turned into sum g*(y - mean) after the last tile (acc_q -= mean * acc_s)
-#pragma unroll
                 if constexpr (kF2) {
 #pragma unroll
                   for (int t = 0; t < 4; ++t) {
@@ -947,12 +946,12 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                   }
                 } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
-                  const int j = j2 * 8 + t;
-                  acc_s[j] += v[j];
-                  acc_q[j] = fmaf(v[j], yv, acc_q[j]);
-                }
+                  for (int t = 0; t < 8; ++t) {
+                    const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
+                    const int j = j2 * 8 + t;
+                    acc_s[j] += v[j];
+                    acc_q[j] = fmaf(v[j], yv, acc_q[j]);
+                  }
                 }
               } else if (k_bn_bwd) {
                 float ca[8], cb[8];
@@ -965,7 +964,6 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                   cb[h * 4] = fb.x; cb[h * 4 + 1] = fb.y; cb[h * 4 + 2] = fb.z; cb[h * 4 + 3] = fb.w;
                 }
                 const float neg_bn = p.bn_act == ACT_LRELU ? p.bn_slope : 0.f;
-#pragma unroll
                 if constexpr (kF2) {
 #pragma unroll
                   for (int t = 0; t < 4; ++t) {
@@ -979,13 +977,13 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                   }
                 } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
-                  const int j = j2 * 8 + t;
-                  const float g = fmaf(yv, ca[t], cb[t]) > 0.f ? v[j] : v[j] * neg_bn;
-                  acc_s[j] += g;
-                  acc_q[j] = fmaf(g, yv, acc_q[j]);
-                }
+                  for (int t = 0; t < 8; ++t) {
+                    const float yv = (t & 1) ? __uint_as_float(w4[t >> 1] & 0xffff0000u) : __uint_as_float(w4[t >> 1] << 16);
+                    const int j = j2 * 8 + t;
+                    const float g = fmaf(yv, ca[t], cb[t]) > 0.f ? v[j] : v[j] * neg_bn;
+                    acc_s[j] += g;
+                    acc_q[j] = fmaf(g, yv, acc_q[j]);
+                  }
                 }
               } else {
 #pragma unroll
@@ -1059,11 +1057,11 @@ conv_tc64s_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               }
             } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = __uint_as_float(r[j]);
-              acc_s[j] += a;
-              acc_q[j] = fmaf(a, a, acc_q[j]);
-            }
+              for (int j = 0; j < 16; ++j) {
+                const float a = __uint_as_float(r[j]);
+                acc_s[j] += a;
+                acc_q[j] = fmaf(a, a, acc_q[j]);
+              }
             }
           }
         }
@@ -1342,8 +1340,8 @@ conv_tc64_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           tma_load_4d_hint(&tmX, &full[stage], sx + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n, pol);
           tma_load_4d_hint(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES + DY_PAD_BYTES, 0, 0, h0, n, pol);
         } else {
-        tma_load_4d(&tmX, &full[stage], sx + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n);
-        tma_load_4d(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES + DY_PAD_BYTES, 0, 0, h0, n);
+          tma_load_4d(&tmX, &full[stage], sx + stage * IN_STAGE_BYTES, 0, -1, h0 - 1, n);
+          tma_load_4d(&tmDY, &full[stage], sdy + stage * DY_STAGE_BYTES + DY_PAD_BYTES, 0, 0, h0, n);
         }
         if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
